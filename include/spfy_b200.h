@@ -1,0 +1,190 @@
+/*
+ * spfy_b200.h -- C ABI of libsparsifyme_b200.so
+ *
+ * The B200-native (sm_100a) replacement for the device work behind the
+ * header-only `include/sparsify.me` API of owensgroup/sparsify.me.  The
+ * reference has no FFI: its "plugin boundary" is five function templates
+ * (SURVEY.md section 8b).  Every entry point below is what the corresponding
+ * template in our `include/sparsify.me/ *.hxx` forwards to, and each one names
+ * the reference call it replaces (file:line under the reference tree).
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: raw device pointers, sizes, enums as int;
+ *   - return 0 on success, a negative SPFY_E_* code otherwise; never throw;
+ *     `spfy_last_error_string()` returns a thread-local description;
+ *   - all device work is enqueued on the caller's stream (a cudaStream_t,
+ *     spelled `spfy_stream_t` so that this header needs no CUDA include);
+ *   - no hidden allocation on the hot path: temporaries come from a
+ *     caller-provided workspace, sized by the matching *_workspace_bytes query;
+ *   - there is NO host fallback: without a CUDA device every compute entry
+ *     point fails with SPFY_E_CUDA.
+ */
+#ifndef SPFY_B200_H_
+#define SPFY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SPFY_API
+#else
+#define SPFY_API __attribute__((visibility("default")))
+#endif
+
+typedef struct CUstream_st* spfy_stream_t; /* == cudaStream_t */
+
+/* ---- enums (passed as int) --------------------------------------------- */
+enum { SPFY_F16 = 0, SPFY_BF16 = 1, SPFY_F32 = 2, SPFY_F64 = 3 };
+
+/* prune24 modes.  STRIP_MAG is the contract mode (top-2-of-4 by |x| along K,
+ * tie -> lower index).  TILE_MAG is the 4x4-tile variant the reference asks
+ * cusparseLt for at include/sparsify.me/spmma.hxx:86. */
+enum { SPFY_PRUNE_STRIP_MAG = 0, SPFY_PRUNE_TILE_MAG = 1 };
+
+/* layouts of the compressed operand.
+ *   CANONICAL : values  [rows][ceil4(cols)/2]   row-major, ascending index
+ *               meta    [rows][ceil4(cols)/8]   bytes; group g of a row sits in
+ *                       byte g/2, low nibble for even g; nibble = i0 | i1<<2
+ *   SM100     : what spfy_spmma consumes.  values and metadata are split into
+ *               (128-row x 128-logical-k) tiles, tile (mt,kt) at index
+ *               mt*k_tiles+kt; a value tile is the 128B-swizzled shared-memory
+ *               image (16 KiB), a metadata tile the tcgen05 `128x128b` image
+ *               (2 KiB).  See DESIGN.md "Data layout in HBM". */
+enum { SPFY_LAYOUT_CANONICAL = 0, SPFY_LAYOUT_SM100 = 1 };
+
+enum { SPFY_OP_N = 0, SPFY_OP_T = 1 }; /* == cusparseOperation_t values */
+
+enum {
+  SPFY_OK = 0,
+  SPFY_E_INVALID = -1,     /* bad argument */
+  SPFY_E_UNSUPPORTED = -2, /* valid but not implemented for these arguments */
+  SPFY_E_CUDA = -3,        /* CUDA runtime / driver error (see last error)   */
+  SPFY_E_WORKSPACE = -4,   /* workspace too small                            */
+  SPFY_E_NCCL = -5
+};
+
+SPFY_API int spfy_version(void);
+SPFY_API const char* spfy_last_error_string(void);
+/* number of kernels this library launched in this process (bench: gpu_launches) */
+SPFY_API uint64_t spfy_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * A1  sparsifyme::sparsify<BLK_M,BLK_N>          include/sparsify.me/sparsify.hxx:24-82
+ * Exact positional semantics of the reference: mask <- 1 (:71); then for each
+ * of (m/blk_m)*(n/blk_n) linear blocks zero the first
+ * floor(blk_m*blk_n*sparsity_factor) offsets of the sequence h + w*blk_n,
+ * h outer / w inner (:53-65), in `weights` and in `mask`.  One fused kernel
+ * replaces thrust::fill_n + thrust::transform.  Writes that the reference
+ * would issue past m*n (BLK_N > BLK_M instantiations) are dropped.
+ * `mask` is an array of m*n 64-bit words (std::size_t in the reference).
+ * ---------------------------------------------------------------------- */
+SPFY_API int spfy_prune_blocks_ref(int dtype, void* weights, uint64_t* mask,
+                                   size_t m, size_t n, size_t blk_m, size_t blk_n,
+                                   float sparsity_factor, spfy_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * A2+A3  cusparseLtSpMMAPrune / PruneCheck / CompressedSize / Compress
+ *                                               include/sparsify.me/spmma.hxx:85-104
+ * One bandwidth-bound kernel: reads `in` (rows x cols, row-major, leading
+ * dimension ld_in elements) once and writes any subset of
+ *   out_dense : the pruned dense matrix (may alias `in`: in-place like :86)
+ *   comp_vals / meta : compressed operand in `layout`
+ *   mask      : rows*cols 64-bit keep flags (1 = kept), API parity with A1
+ * Null outputs are skipped.  dtype is SPFY_F16 or SPFY_BF16.
+ * ---------------------------------------------------------------------- */
+SPFY_API int spfy_compressed_bytes(int dtype, size_t rows, size_t cols, int layout,
+                                   size_t* vals_bytes, size_t* meta_bytes);
+SPFY_API int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in,
+                          void* out_dense, size_t ld_out, void* comp_vals, void* meta,
+                          uint64_t* mask, size_t rows, size_t cols, spfy_stream_t stream);
+/* A dense matrix obeys 2:4 along its rows iff *d_invalid == 0 afterwards
+ * (same convention as cusparseLtSpMMAPruneCheck, spmma.hxx:88-94). */
+SPFY_API int spfy_prune24_check(int dtype, const void* in, size_t ld_in, size_t rows,
+                                size_t cols, int* d_invalid, spfy_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * A4  cusparseLtMatmul                           include/sparsify.me/spmma.hxx:106-114
+ * D = alpha * A(2:4) * op(B) + beta * C, fp32 accumulate on tcgen05.mma.sp.
+ * A is the SM100-layout compressed operand of an m x k matrix (from
+ * spfy_prune24).  All dense operands are row-major like the reference's
+ * descriptors (:56-64): op(B) is k x n.  opB = N: B is k x n, ldb >= n;
+ * opB = T: B is n x k, ldb >= k.  C and D are m x n; D may alias C.
+ * n, ldb, ldc, ldd must be multiples of 8 elements and all base pointers
+ * 16-byte aligned (the reference's own fp16 contract, spmma.hxx:45-49).
+ * ---------------------------------------------------------------------- */
+SPFY_API int spfy_spmma_workspace_bytes(int dtype, size_t m, size_t n, size_t k,
+                                        size_t* bytes);
+SPFY_API int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha,
+                        const void* comp_vals, const void* meta, const void* B, size_t ldb,
+                        float beta, const void* C, size_t ldc, void* D, size_t ldd,
+                        void* workspace, size_t workspace_bytes, spfy_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Unstructured path (north_star subsystem 3).  Threshold prune keeps x iff
+ * |x| > threshold (compared in fp32) and emits COO sorted by (row, col) or CSR.
+ * dtype of `in` is F16/BF16/F32; emitted values are fp32 like the reference's
+ * CUDA_R_32F COO (include/sparsify.me/spmm.hxx:165-168).
+ * nnz is produced on the device (`d_nnz`, one int64) so the call never syncs.
+ * `capacity` bounds the number of entries written.
+ * ---------------------------------------------------------------------- */
+SPFY_API int spfy_threshold_workspace_bytes(size_t rows, size_t cols, size_t* bytes);
+SPFY_API int spfy_threshold_to_coo(int dtype, const void* in, size_t ld_in, size_t rows,
+                                   size_t cols, float threshold, int32_t* row_idx,
+                                   int32_t* col_idx, float* vals, size_t capacity,
+                                   int64_t* d_nnz, int32_t* d_row_ptr_or_null,
+                                   void* workspace, size_t workspace_bytes,
+                                   spfy_stream_t stream);
+/* COO (sorted by row) -> CSR row pointer (rows+1 int32). */
+SPFY_API int spfy_coo_to_csr(const int32_t* row_idx, size_t nnz, size_t rows,
+                             int32_t* row_ptr, spfy_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * A6  sparsifyme::batched::strided_coo           include/sparsify.me/spmm.hxx:140-193
+ * C_b = alpha * A * B_b + beta * C_b for b in [0, num_batches): ONE sparse A
+ * (stride 0, :169) shared by all batches; B_b = B + b*strideB is k x n
+ * column-major (ldb >= k, :160,:170); C_b = C + b*strideC is m x n column-major
+ * (ldc >= m, :161,:173).  fp32 values, int32 indices, fp32 accumulate.
+ * The COO triplets must be sorted by row (any column order); row_ptr is
+ * built internally in the workspace.
+ * ---------------------------------------------------------------------- */
+SPFY_API int spfy_spmm_workspace_bytes(size_t m, size_t nnz, size_t* bytes);
+SPFY_API int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n,
+                                           size_t num_batches, const int32_t* row_idx,
+                                           const int32_t* col_idx, const float* vals,
+                                           const float* B, size_t ldb, size_t strideB,
+                                           float* C, size_t ldc, size_t strideC, float alpha,
+                                           float beta, void* workspace, size_t workspace_bytes,
+                                           spfy_stream_t stream);
+/* Same product with A already in CSR. */
+SPFY_API int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
+                                           const int32_t* row_ptr, const int32_t* col_idx,
+                                           const float* vals, const float* B, size_t ldb,
+                                           size_t strideB, float* C, size_t ldc,
+                                           size_t strideC, float alpha, float beta,
+                                           spfy_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * A5  sparsifyme::batched::spmm (blocked-ELL)    include/sparsify.me/spmm.hxx:30-138
+ * For each batch b: C_b = alpha * A_b * B + beta * C_b.  A_b is blocked-ELL
+ * (containers/ell.hxx:24-33): rows x cols, square blocks of `block`,
+ * `ell_cols` stored columns per row; col_idx_b[(rows/block) x (ell_cols/block)]
+ * block-column ids (int64 here because the reference stores std::size_t,
+ * ell.hxx:31); values_b[rows x ell_cols] row-major.  B is k x n column-major
+ * ldb = k shared by all batches (:67); C_b is m x n column-major ldc = m (:63).
+ * `col_idx`, `values`, `Cs` are DEVICE arrays of num_batches device pointers.
+ * dtype is that of values/B/C (F16/BF16/F32); fp32 accumulate (:82).
+ * ---------------------------------------------------------------------- */
+SPFY_API int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n,
+                                    size_t block, size_t ell_cols, size_t num_batches,
+                                    const int64_t* const* col_idx, const void* const* values,
+                                    const void* B, size_t ldb, void* const* Cs, size_t ldc,
+                                    float alpha, float beta, spfy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPFY_B200_H_ */

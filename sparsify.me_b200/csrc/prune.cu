@@ -1,0 +1,484 @@
+// prune.cu -- bandwidth-bound pruning / compression kernels (sm_100a)
+//
+//   spfy_prune_blocks_ref : exact positional semantics of the reference's
+//                           sparsifyme::sparsify (include/sparsify.me/sparsify.hxx:24-82)
+//   spfy_prune24          : 2:4 magnitude prune + compress + metadata in ONE pass
+//                           (replaces cusparseLtSpMMAPrune/Compress,
+//                            include/sparsify.me/spmma.hxx:85-104)
+//   spfy_prune24_check    : cusparseLtSpMMAPruneCheck (spmma.hxx:88)
+//
+// All kernels are HBM-bound byte movers: 128-bit loads/stores, one pass over the
+// input, no shared memory (there is no reuse), grid sized in multiples of the SM
+// count.  See DESIGN.md for the algorithmic byte counts.
+#include "common.cuh"
+
+namespace spfy {
+namespace {
+
+// ------------------------------------------------------------------------
+// A1  positional block pruning
+// ------------------------------------------------------------------------
+struct OffsetList {
+  uint16_t off[256];  // offsets (relative to the block start) zeroed per block, in order
+  int count;
+  int in_block;       // 1 if every offset < blk_size (then a bitmap test is enough)
+  uint32_t bitmap[8]; // bit o set  <=>  o in off[] (valid when in_block)
+};
+
+template <typename T>
+__device__ __forceinline__ void store_zero(T* p) { *p = T(0); }
+
+// one thread = 4 consecutive elements: two 16-byte mask stores + scalar zero stores
+template <typename T>
+__global__ void __launch_bounds__(256)
+prune_blocks_ref_kernel(T* __restrict__ weights, uint64_t* __restrict__ mask, size_t total,
+                        size_t nblocks, uint32_t blk_size, const __grid_constant__ OffsetList L) {
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t * 4 < total; t += nthreads) {
+    const size_t e0 = t * 4;
+    unsigned zero = 0;  // bit i set -> element e0+i is pruned
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const size_t e = e0 + i;
+      if (e >= total) break;
+      if (L.in_block) {
+        const size_t blk = e / blk_size;
+        const uint32_t o = (uint32_t)(e - blk * blk_size);
+        if (blk < nblocks && (L.bitmap[o >> 5] >> (o & 31) & 1)) zero |= 1u << i;
+      } else {
+        for (int j = 0; j < L.count; ++j) {
+          const size_t o = L.off[j];
+          if (e >= o && (e - o) % blk_size == 0 && (e - o) / blk_size < nblocks) {
+            zero |= 1u << i;
+            break;
+          }
+        }
+      }
+    }
+    if (e0 + 4 <= total) {
+      ulonglong2 m01 = make_ulonglong2(zero & 1 ? 0ull : 1ull, zero & 2 ? 0ull : 1ull);
+      ulonglong2 m23 = make_ulonglong2(zero & 4 ? 0ull : 1ull, zero & 8 ? 0ull : 1ull);
+      *reinterpret_cast<ulonglong2*>(mask + e0) = m01;
+      *reinterpret_cast<ulonglong2*>(mask + e0 + 2) = m23;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (zero >> i & 1) store_zero(weights + e0 + i);
+    } else {
+      for (int i = 0; i < 4 && e0 + i < total; ++i) {
+        mask[e0 + i] = (zero >> i & 1) ? 0ull : 1ull;
+        if (zero >> i & 1) store_zero(weights + e0 + i);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------
+// A2/A3  2:4 magnitude prune + compress (STRIP mode)
+// ------------------------------------------------------------------------
+struct Prune24Params {
+  const uint16_t* in;
+  size_t ld_in;
+  uint16_t* out_dense;
+  size_t ld_out;
+  uint8_t* comp_vals;
+  uint8_t* meta;
+  uint64_t* mask;
+  uint32_t rows, cols;
+  uint32_t dom_rows;       // rows of the iteration domain (padded to 128 for SM100)
+  uint32_t units_per_row;  // 16-column units per row in the iteration domain
+  uint32_t G, mb;          // CANONICAL: groups per row, metadata bytes per row
+  uint32_t k_tiles;        // SM100: 128-column tiles per row
+  int layout;
+  int vec_in, vec_out, vec_cv;  // 16-byte fast paths allowed
+};
+
+// keep-mask (2 bits set) of the two largest keys, tie -> lower index
+__device__ __forceinline__ unsigned select2of4(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
+  // c_ij = 1 iff j beats i (j > i  =>  needs strictly larger key)
+  const int c01 = k1 > k0, c02 = k2 > k0, c03 = k3 > k0;
+  const int c12 = k2 > k1, c13 = k3 > k1, c23 = k3 > k2;
+  const int b0 = c01 + c02 + c03;
+  const int b1 = (1 - c01) + c12 + c13;
+  const int b2 = (1 - c02) + (1 - c12) + c23;
+  const int b3 = (1 - c03) + (1 - c13) + (1 - c23);
+  return (unsigned)(b0 < 2) | (unsigned)(b1 < 2) << 1 | (unsigned)(b2 < 2) << 2 |
+         (unsigned)(b3 < 2) << 3;
+}
+
+// streaming 128-bit load.  Not `.nc`: out_dense may alias the input (in-place prune).
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+prune24_strip_kernel(const __grid_constant__ Prune24Params P) {
+  const size_t total = (size_t)P.dom_rows * P.units_per_row;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+    const uint32_t row = (uint32_t)(t / P.units_per_row);
+    const uint32_t unit = (uint32_t)(t - (size_t)row * P.units_per_row);
+    const uint32_t c0 = unit * 16;
+
+    // ---- load 16 storage words (zeros outside the matrix) ----
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // two 16-bit values per word
+    const bool row_ok = row < P.rows;
+    if (row_ok && c0 < P.cols) {
+      const uint16_t* src = P.in + (size_t)row * P.ld_in + c0;
+      if (P.vec_in && c0 + 16 <= P.cols) {
+        const uint4 a = ldg_nc_v4(src), b = ldg_nc_v4(src + 8);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < P.cols) w[i >> 1] |= (uint32_t)src[i] << ((i & 1) * 16);
+      }
+    }
+
+    // ---- select per group of 4 ----
+    uint32_t d[8];       // pruned dense words
+    uint32_t cv[4];      // compressed: 2 values per group
+    unsigned nibs = 0;   // 4 nibbles
+    unsigned keep16 = 0; // keep bit per element
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t lo = w[2 * g], hi = w[2 * g + 1];
+      const uint32_t v0 = lo & 0xffffu, v1 = lo >> 16, v2 = hi & 0xffffu, v3 = hi >> 16;
+      const unsigned keep = select2of4(v0 & 0x7fffu, v1 & 0x7fffu, v2 & 0x7fffu, v3 & 0x7fffu);
+      const unsigned i0 = __ffs(keep) - 1, i1 = 31 - __clz(keep);
+      nibs |= (i0 | i1 << 2) << (4 * g);
+      keep16 |= keep << (4 * g);
+      const uint32_t a = i0 == 0 ? v0 : (i0 == 1 ? v1 : v2);
+      const uint32_t b = i1 == 1 ? v1 : (i1 == 2 ? v2 : v3);
+      cv[g] = a | b << 16;
+      d[2 * g] = (keep & 1 ? v0 : 0u) | (keep & 2 ? v1 : 0u) << 16;
+      d[2 * g + 1] = (keep & 4 ? v2 : 0u) | (keep & 8 ? v3 : 0u) << 16;
+    }
+
+    // ---- pruned dense (may alias the input: same thread, same addresses) ----
+    if (P.out_dense && row_ok && c0 < P.cols) {
+      uint16_t* dst = P.out_dense + (size_t)row * P.ld_out + c0;
+      if (P.vec_out && c0 + 16 <= P.cols) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(d[4], d[5], d[6], d[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < P.cols) dst[i] = (uint16_t)(d[i >> 1] >> ((i & 1) * 16));
+      }
+    }
+
+    // ---- keep mask (u64 per element, API parity with sparsify.hxx) ----
+    if (P.mask && row_ok && c0 < P.cols) {
+      uint64_t* mdst = P.mask + (size_t)row * P.cols + c0;
+      if (c0 + 16 <= P.cols && ((P.cols & 1) == 0) && ((uintptr_t)P.mask & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+          *reinterpret_cast<ulonglong2*>(mdst + i) =
+              make_ulonglong2(keep16 >> i & 1, keep16 >> (i + 1) & 1);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < P.cols) mdst[i] = keep16 >> i & 1;
+      }
+    }
+
+    // ---- compressed values + metadata ----
+    if (P.layout == SPFY_LAYOUT_SM100) {
+      const uint32_t r = row & 127, q = (c0 & 127) >> 4;
+      const size_t tile = (size_t)(row >> 7) * P.k_tiles + (c0 >> 7);
+      if (P.comp_vals)
+        *reinterpret_cast<uint4*>(P.comp_vals + tile * 16384 + r * 128 + ((q ^ (r & 7)) << 4)) =
+            make_uint4(cv[0], cv[1], cv[2], cv[3]);
+      if (P.meta)
+        *reinterpret_cast<uint16_t*>(P.meta + tile * 2048 + (r >> 4) * 256 + (q & 1) * 128 +
+                                     (r & 7) * 16 + (q >> 1) * 4 + ((r >> 3) & 1) * 2) =
+            (uint16_t)nibs;
+    } else if (row_ok) {
+      const uint32_t g0 = unit * 4;
+      const uint32_t ng = min(4u, P.G - g0);  // groups that exist in this unit
+      if (P.comp_vals) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(P.comp_vals) + (size_t)row * P.G + g0;
+        if (P.vec_cv && ng == 4) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g < (int)ng) dst[g] = cv[g];
+        }
+      }
+      if (P.meta) {
+        uint8_t* dst = P.meta + (size_t)row * P.mb + g0 / 2;
+        // an odd trailing group leaves its partner nibble 0 (CANONICAL contract)
+        const unsigned lo = nibs & (ng >= 2 ? 0xffu : 0x0fu);
+        dst[0] = (uint8_t)lo;
+        if (ng > 2) dst[1] = (uint8_t)((nibs >> 8) & (ng == 4 ? 0xffu : 0x0fu));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------
+// TILE mode: per 4x4 tile choose, among the 90 patterns with exactly two kept
+// entries in every row and every column, the one with the largest sum |x|.
+// One thread per tile; pattern table in constant memory (enumeration order is
+// the oracle's: rows top to bottom, pair masks {0011,0101,0110,1001,1010,1100}).
+// ------------------------------------------------------------------------
+__constant__ uint16_t c_tile_patterns[90];
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+prune24_tile_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint16_t* __restrict__ out,
+                    size_t ld_out, uint32_t rows, uint32_t cols) {
+  const uint32_t tiles_c = (cols + 3) / 4, tiles_r = (rows + 3) / 4;
+  const size_t total = (size_t)tiles_r * tiles_c;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+    const uint32_t tr = (uint32_t)(t / tiles_c), tc = (uint32_t)(t - (size_t)tr * tiles_c);
+    const uint32_t r0 = tr * 4, c0 = tc * 4;
+    uint16_t v[16];
+    float mag[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = r0 + i < rows && c0 + j < cols;
+        const uint16_t bits = ok ? in[(size_t)(r0 + i) * ld_in + c0 + j] : (uint16_t)0;
+        v[i * 4 + j] = bits;
+        const uint16_t ab = bits & 0x7fffu;
+        mag[i * 4 + j] = BF16 ? __uint_as_float((uint32_t)ab << 16)
+                              : __half2float(__ushort_as_half(ab));
+      }
+    float best = -1.f;
+    uint32_t best_p = 0;
+    for (int p = 0; p < 90; ++p) {
+      const uint32_t pat = c_tile_patterns[p];
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) s += (pat >> e & 1) ? mag[e] : 0.f;
+      if (s > best) best = s, best_p = pat;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + i < rows && c0 + j < cols)
+          out[(size_t)(r0 + i) * ld_out + c0 + j] = (best_p >> (i * 4 + j) & 1) ? v[i * 4 + j] : (uint16_t)0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+prune24_check_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint32_t rows, uint32_t cols,
+                     int* __restrict__ invalid) {
+  const uint32_t G = (cols + 3) / 4;
+  const size_t total = (size_t)rows * G;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+    const uint32_t row = (uint32_t)(t / G), g = (uint32_t)(t - (size_t)row * G);
+    int nz = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t c = g * 4 + i;
+      if (c < cols && (in[(size_t)row * ld_in + c] & 0x7fffu)) ++nz;
+    }
+    bad |= nz > 2;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(invalid, 1);
+}
+
+int grid_for(size_t work_items, int threads, int* grid) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  size_t blocks = ceil_div(work_items, (size_t)threads);
+  size_t cap = (size_t)di.sm_count * 16;  // 16 x 256 threads = 2 full waves of resident warps
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  *grid = (int)blocks;
+  return SPFY_OK;
+}
+
+void build_tile_patterns(uint16_t* out) {
+  static const unsigned pair[6] = {0x3, 0x5, 0x6, 0x9, 0xA, 0xC};
+  int n = 0;
+  for (int p0 = 0; p0 < 6; ++p0)
+    for (int p1 = 0; p1 < 6; ++p1)
+      for (int p2 = 0; p2 < 6; ++p2)
+        for (int p3 = 0; p3 < 6; ++p3) {
+          unsigned r[4] = {pair[p0], pair[p1], pair[p2], pair[p3]};
+          bool ok = true;
+          for (int c = 0; c < 4 && ok; ++c) {
+            int cnt = 0;
+            for (int q = 0; q < 4; ++q) cnt += r[q] >> c & 1;
+            ok = cnt == 2;
+          }
+          if (ok && n < 90) out[n++] = (uint16_t)(r[0] | r[1] << 4 | r[2] << 8 | r[3] << 12);
+        }
+}
+
+}  // namespace
+}  // namespace spfy
+
+using namespace spfy;
+
+extern "C" {
+
+int spfy_prune_blocks_ref(int dtype, void* weights, uint64_t* mask, size_t m, size_t n,
+                          size_t blk_m, size_t blk_n, float sparsity_factor,
+                          spfy_stream_t stream) {
+  const size_t eb = dtype_bytes(dtype);
+  if (!eb) return fail(SPFY_E_INVALID, "prune_blocks_ref: bad dtype %d", dtype);
+  if (!weights || !mask) return fail(SPFY_E_INVALID, "prune_blocks_ref: null pointer");
+  if (blk_m == 0 || blk_n == 0 || blk_m * blk_n > 256 || blk_m > 16 || blk_n > 16)
+    return fail(SPFY_E_UNSUPPORTED, "prune_blocks_ref: block %zux%zu not supported (<=16x16)", blk_m, blk_n);
+  const size_t total = m * n;
+  if (total == 0) return SPFY_OK;
+  const size_t blk_size = blk_m * blk_n;
+  const size_t nblocks = (m / blk_m) * (n / blk_n);
+  // sparsify.hxx:41 -- the product is evaluated in float
+  const size_t nz = (size_t)floorf((float)blk_size * sparsity_factor);
+  OffsetList L;
+  memset(&L, 0, sizeof(L));
+  L.in_block = 1;
+  size_t done = 0;
+  for (size_t h = 0; h < blk_m; ++h)
+    for (size_t w = 0; w < blk_n; ++w) {
+      if (done == nz) break;
+      size_t o = h + w * blk_n;  // sparsify.hxx:60
+      L.off[L.count++] = (uint16_t)o;
+      if (o >= blk_size) L.in_block = 0; else L.bitmap[o >> 5] |= 1u << (o & 31);
+      ++done;
+    }
+  int grid = 1;
+  int rc = grid_for(ceil_div(total, 4), 256, &grid);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (eb) {
+    case 2: prune_blocks_ref_kernel<uint16_t><<<grid, 256, 0, s>>>((uint16_t*)weights, mask, total, nblocks, (uint32_t)blk_size, L); break;
+    case 4: prune_blocks_ref_kernel<uint32_t><<<grid, 256, 0, s>>>((uint32_t*)weights, mask, total, nblocks, (uint32_t)blk_size, L); break;
+    default: prune_blocks_ref_kernel<uint64_t><<<grid, 256, 0, s>>>((uint64_t*)weights, mask, total, nblocks, (uint32_t)blk_size, L); break;
+  }
+  SPFY_LAUNCH_OK("prune_blocks_ref_kernel");
+  return SPFY_OK;
+}
+
+int spfy_compressed_bytes(int dtype, size_t rows, size_t cols, int layout, size_t* vals_bytes,
+                          size_t* meta_bytes) {
+  if (dtype != SPFY_F16 && dtype != SPFY_BF16)
+    return fail(SPFY_E_UNSUPPORTED, "compressed_bytes: dtype %d (need F16/BF16)", dtype);
+  size_t vb, mb;
+  if (layout == SPFY_LAYOUT_CANONICAL) {
+    const size_t G = ceil_div(cols, 4);
+    vb = rows * G * 2 * 2;
+    mb = rows * ceil_div(G, 2);
+  } else if (layout == SPFY_LAYOUT_SM100) {
+    const size_t tiles = ceil_div(rows, 128) * ceil_div(cols, 128);
+    vb = tiles * 16384;
+    mb = tiles * 2048;
+  } else {
+    return fail(SPFY_E_INVALID, "compressed_bytes: bad layout %d", layout);
+  }
+  if (vals_bytes) *vals_bytes = vb;
+  if (meta_bytes) *meta_bytes = mb;
+  return SPFY_OK;
+}
+
+int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, void* out_dense,
+                 size_t ld_out, void* comp_vals, void* meta, uint64_t* mask, size_t rows,
+                 size_t cols, spfy_stream_t stream) {
+  if (dtype != SPFY_F16 && dtype != SPFY_BF16)
+    return fail(SPFY_E_UNSUPPORTED, "prune24: dtype %d (need F16/BF16)", dtype);
+  if (layout != SPFY_LAYOUT_CANONICAL && layout != SPFY_LAYOUT_SM100)
+    return fail(SPFY_E_INVALID, "prune24: bad layout %d", layout);
+  if (!in) return fail(SPFY_E_INVALID, "prune24: null input");
+  if (ld_in < cols || (out_dense && ld_out < cols))
+    return fail(SPFY_E_INVALID, "prune24: leading dimension smaller than cols");
+  if (rows >= (1ull << 31) || cols >= (1ull << 31))
+    return fail(SPFY_E_UNSUPPORTED, "prune24: dimension too large");
+  if (rows == 0 || cols == 0) return SPFY_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  const uint16_t* src = (const uint16_t*)in;
+  size_t ld_src = ld_in;
+  if (mode == SPFY_PRUNE_TILE_MAG) {
+    if (!out_dense)
+      return fail(SPFY_E_INVALID, "prune24: TILE_MAG needs out_dense (it may alias the input)");
+    static std::atomic<int> tables_ready[64];
+    int dev = 0;
+    SPFY_CUDA_OK(cudaGetDevice(&dev));
+    if (!tables_ready[dev & 63].load()) {
+      uint16_t pats[90];
+      build_tile_patterns(pats);
+      SPFY_CUDA_OK(cudaMemcpyToSymbol(c_tile_patterns, pats, sizeof(pats)));
+      tables_ready[dev & 63].store(1);
+    }
+    int grid = 1;
+    int rc = grid_for(ceil_div(rows, 4) * ceil_div(cols, 4), 256, &grid);
+    if (rc) return rc;
+    if (dtype == SPFY_BF16)
+      prune24_tile_kernel<true><<<grid, 256, 0, s>>>(src, ld_in, (uint16_t*)out_dense, ld_out, (uint32_t)rows, (uint32_t)cols);
+    else
+      prune24_tile_kernel<false><<<grid, 256, 0, s>>>(src, ld_in, (uint16_t*)out_dense, ld_out, (uint32_t)rows, (uint32_t)cols);
+    SPFY_LAUNCH_OK("prune24_tile_kernel");
+    if (!comp_vals && !meta && !mask) return SPFY_OK;
+    // a valid 2:4 matrix is a fixed point of the strip selection: run it to compress
+    src = (const uint16_t*)out_dense;
+    ld_src = ld_out;
+    out_dense = nullptr;
+  } else if (mode != SPFY_PRUNE_STRIP_MAG) {
+    return fail(SPFY_E_INVALID, "prune24: bad mode %d", mode);
+  }
+
+  Prune24Params P;
+  memset(&P, 0, sizeof(P));
+  P.in = src;
+  P.ld_in = ld_src;
+  P.out_dense = (uint16_t*)out_dense;
+  P.ld_out = ld_out;
+  P.comp_vals = (uint8_t*)comp_vals;
+  P.meta = (uint8_t*)meta;
+  P.mask = mask;
+  P.rows = (uint32_t)rows;
+  P.cols = (uint32_t)cols;
+  P.layout = layout;
+  P.G = (uint32_t)ceil_div(cols, 4);
+  P.mb = (uint32_t)ceil_div(P.G, 2);
+  P.k_tiles = (uint32_t)ceil_div(cols, 128);
+  const bool sm100_out = layout == SPFY_LAYOUT_SM100 && (comp_vals || meta);
+  P.dom_rows = sm100_out ? (uint32_t)round_up(rows, 128) : (uint32_t)rows;
+  P.units_per_row = sm100_out ? P.k_tiles * 8 : (uint32_t)ceil_div(cols, 16);
+  P.vec_in = ((uintptr_t)src % 16 == 0) && (ld_src % 8 == 0);
+  P.vec_out = out_dense && ((uintptr_t)out_dense % 16 == 0) && (ld_out % 8 == 0);
+  P.vec_cv = comp_vals && ((uintptr_t)comp_vals % 16 == 0) && (P.G % 4 == 0);
+  if (layout == SPFY_LAYOUT_SM100 && ((comp_vals && (uintptr_t)comp_vals % 16) || (meta && (uintptr_t)meta % 16)))
+    return fail(SPFY_E_INVALID, "prune24: SM100 outputs must be 16-byte aligned");
+  int grid = 1;
+  int rc = grid_for((size_t)P.dom_rows * P.units_per_row, 256, &grid);
+  if (rc) return rc;
+  prune24_strip_kernel<<<grid, 256, 0, s>>>(P);
+  SPFY_LAUNCH_OK("prune24_strip_kernel");
+  return SPFY_OK;
+}
+
+int spfy_prune24_check(int dtype, const void* in, size_t ld_in, size_t rows, size_t cols,
+                       int* d_invalid, spfy_stream_t stream) {
+  if (dtype != SPFY_F16 && dtype != SPFY_BF16)
+    return fail(SPFY_E_UNSUPPORTED, "prune24_check: dtype %d (need F16/BF16)", dtype);
+  if (!in || !d_invalid) return fail(SPFY_E_INVALID, "prune24_check: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  SPFY_CUDA_OK(cudaMemsetAsync(d_invalid, 0, sizeof(int), s));
+  if (rows == 0 || cols == 0) return SPFY_OK;
+  int grid = 1;
+  int rc = grid_for(rows * ceil_div(cols, 4), 256, &grid);
+  if (rc) return rc;
+  prune24_check_kernel<<<grid, 256, 0, s>>>((const uint16_t*)in, ld_in, (uint32_t)rows, (uint32_t)cols, d_invalid);
+  SPFY_LAUNCH_OK("prune24_check_kernel");
+  return SPFY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,449 @@
+// spmm.cu -- unstructured path: threshold prune -> COO/CSR, and row-split SpMM
+//
+//   spfy_threshold_to_coo / spfy_coo_to_csr   magnitude-threshold compaction
+//   spfy_spmm_csr_strided_batched             C_b = alpha*A*B_b + beta*C_b  (A shared)
+//   spfy_spmm_coo_strided_batched             same, A in row-sorted COO
+//                                             (reference: include/sparsify.me/spmm.hxx:140-193)
+//   spfy_spmm_bell_batched                    blocked-ELL A_b per batch, B shared
+//                                             (reference: include/sparsify.me/spmm.hxx:30-138)
+//
+// SpMM design (all dense operands column-major like the reference's cuSPARSE
+// descriptors, spmm.hxx:63,67,170,173): a CTA owns a tile of TM rows x 32 columns.
+// The dense operand tile B[k-chunk x 32] is staged TRANSPOSED in shared memory so
+// that for one non-zero (i, c) the 32 lanes of a warp read 32 consecutive words
+// (one per output column).  A warp owns RPW rows; it loads 32 non-zeros with one
+// coalesced request and broadcasts them with shuffles.  Accumulators live in
+// registers; the C tile goes back through shared memory so the column-major
+// stores are coalesced along rows.
+#include "common.cuh"
+
+namespace spfy {
+namespace {
+
+// ------------------------------------------------------------------------
+// threshold -> COO/CSR.  Pass 1: per-row counts (warp per row).  Scan.  Pass 2:
+// ordered warp compaction (ballot + popc), so entries come out sorted by (row, col).
+// ------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void store_from_float(T* p, float v);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_from_float<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+threshold_count_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols,
+                       float thr, int32_t* __restrict__ row_counts) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const T* src = in + (size_t)r * ld;
+    int cnt = 0;
+    for (uint32_t c = lane; c < cols; c += 32) cnt += fabsf(load_as_float(src + c)) > thr;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) row_counts[r] = cnt;
+  }
+}
+
+// single-CTA exclusive scan of `rows` counts -> row_ptr[rows+1]; also nnz (int64)
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(const int32_t* __restrict__ counts, uint32_t rows,
+                      int32_t* __restrict__ row_ptr, int64_t* __restrict__ nnz_out) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < rows; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const int32_t v = i < rows ? counts[i] : 0;
+    int32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int32_t s = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= (uint32_t)o) s += y;
+      }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int32_t carry = carry_s;
+    const int32_t incl = x + (w ? warp_sums[w - 1] : 0) + carry;
+    if (i < rows) row_ptr[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    row_ptr[rows] = carry_s;
+    if (nnz_out) *nnz_out = carry_s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+threshold_fill_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols, float thr,
+                      const int32_t* __restrict__ row_ptr, int32_t* __restrict__ row_idx,
+                      int32_t* __restrict__ col_idx, float* __restrict__ vals, size_t capacity) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const T* src = in + (size_t)r * ld;
+    size_t out = (size_t)row_ptr[r];
+    for (uint32_t c0 = 0; c0 < cols; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      const float x = c < cols ? load_as_float(src + c) : 0.f;
+      const bool keep = c < cols && fabsf(x) > thr;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const size_t pos = out + __popc(bal & ((1u << lane) - 1));
+        if (pos < capacity) {
+          row_idx[pos] = (int32_t)r;
+          col_idx[pos] = (int32_t)c;
+          vals[pos] = x;
+        }
+      }
+      out += __popc(bal);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+coo_to_csr_kernel(const int32_t* __restrict__ row_idx, size_t nnz, uint32_t rows,
+                  int32_t* __restrict__ row_ptr) {
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz; i += nthreads) {
+    const int64_t prev = i == 0 ? -1 : (int64_t)row_idx[i - 1];
+    const int64_t cur = i == nnz ? (int64_t)rows : (int64_t)row_idx[i];
+    for (int64_t r = prev + 1; r <= cur && r <= (int64_t)rows; ++r) row_ptr[r] = (int32_t)i;
+  }
+}
+
+// ------------------------------------------------------------------------
+// Row-split SpMM.
+// ------------------------------------------------------------------------
+constexpr int SP_WARPS = 16;           // warps per CTA
+constexpr int SP_RPW = 8;              // rows per warp
+constexpr int SP_TM = SP_WARPS * SP_RPW;  // 128 rows per CTA
+constexpr int SP_TN = 32;              // columns per CTA (one per lane)
+constexpr int SP_PAD = SP_TN + 1;      // padded row of the transposed B tile
+
+struct CsrRows {  // A in CSR, shared by every batch
+  const int32_t* row_ptr;
+  const int32_t* col_idx;
+  const float* vals;
+  __device__ __forceinline__ void range(uint32_t, uint32_t row, uint32_t& b, uint32_t& e) const {
+    b = (uint32_t)row_ptr[row];
+    e = (uint32_t)row_ptr[row + 1];
+  }
+  __device__ __forceinline__ void fetch(uint32_t, uint32_t, uint32_t idx, int32_t& c, float& v) const {
+    c = col_idx[idx];
+    v = vals[idx];
+  }
+};
+
+template <typename T>
+struct BellRows {  // blocked-ELL, one matrix per batch (reference: containers/ell.hxx:24-33)
+  const int64_t* const* col_idx;  // [batch] -> [(rows/block) x (ell_cols/block)]
+  const T* const* values;         // [batch] -> [rows x ell_cols]
+  uint32_t block, ell_cols, bcols;
+  __device__ __forceinline__ void range(uint32_t, uint32_t, uint32_t& b, uint32_t& e) const {
+    b = 0;
+    e = ell_cols;
+  }
+  __device__ __forceinline__ void fetch(uint32_t batch, uint32_t row, uint32_t idx, int32_t& c, float& v) const {
+    const int64_t bc = col_idx[batch][(size_t)(row / block) * bcols + idx / block];
+    c = bc < 0 ? -1 : (int32_t)(bc * block + idx % block);
+    v = load_as_float(values[batch] + (size_t)row * ell_cols + idx);
+  }
+};
+
+struct SpmmDense {
+  const void* B;
+  void* C;                 // single slab (strided batches) ...
+  void* const* Cs;         // ... or per-batch pointers (BELL); one of the two is null
+  size_t ldb, strideB, ldc, strideC;
+  uint32_t m, k, n, num_batches;
+  uint32_t kc;             // rows of B staged per chunk
+  float alpha, beta;
+};
+
+template <typename T, typename Rows>
+__global__ void __launch_bounds__(SP_WARPS * 32, 1)
+spmm_rowsplit_kernel(const Rows A, const SpmmDense D) {
+  extern __shared__ float sB[];  // [kc][SP_PAD]; reused as [SP_TN][SP_TM+1] for the C tile
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_tiles = (D.m + SP_TM - 1) / SP_TM;
+  const uint32_t col_tiles = (D.n + SP_TN - 1) / SP_TN;
+  const uint32_t rt = blockIdx.x % row_tiles;         // row tile fastest: CTAs that share a
+  const uint32_t ct_all = blockIdx.x / row_tiles;     // B tile are co-resident (L2 reuse)
+  const uint32_t batch = ct_all / col_tiles, ct = ct_all % col_tiles;
+  const uint32_t j0 = ct * SP_TN, i0 = rt * SP_TM;
+  const T* Bb = reinterpret_cast<const T*>(D.B) + (size_t)batch * D.strideB;
+  T* Cb = D.Cs ? reinterpret_cast<T*>(D.Cs[batch]) : reinterpret_cast<T*>(D.C) + (size_t)batch * D.strideC;
+
+  float acc[SP_RPW];
+#pragma unroll
+  for (int r = 0; r < SP_RPW; ++r) acc[r] = 0.f;
+
+  for (uint32_t k0 = 0; k0 < D.k; k0 += D.kc) {
+    const uint32_t kn = min(D.kc, D.k - k0);
+    __syncthreads();
+    // stage B[k0:k0+kn, j0:j0+32] transposed: coalesced along k in global memory
+    for (uint32_t j = warp; j < SP_TN; j += SP_WARPS) {
+      const bool col_ok = j0 + j < D.n;
+      const T* src = Bb + (size_t)(j0 + j) * D.ldb + k0;
+      for (uint32_t kk = lane; kk < kn; kk += 32)
+        sB[kk * SP_PAD + j] = col_ok ? load_as_float(src + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SP_RPW; ++r) {
+      const uint32_t row = i0 + warp * SP_RPW + r;
+      if (row >= D.m) break;
+      uint32_t eb, ee;
+      A.range(batch, row, eb, ee);
+      for (uint32_t e0 = eb; e0 < ee; e0 += 32) {
+        int32_t c = -1;
+        float v = 0.f;
+        if (e0 + lane < ee) A.fetch(batch, row, e0 + lane, c, v);
+        const int32_t rel = c - (int32_t)k0;
+        const bool in_chunk = c >= 0 && rel >= 0 && rel < (int32_t)kn;
+        unsigned live = __ballot_sync(0xffffffffu, in_chunk);
+        while (live) {
+          const int src_lane = __ffs(live) - 1;
+          live &= live - 1;
+          const int32_t rc = __shfl_sync(0xffffffffu, rel, src_lane);
+          const float rv = __shfl_sync(0xffffffffu, v, src_lane);
+          acc[r] = fmaf(rv, sB[rc * SP_PAD + lane], acc[r]);
+        }
+      }
+    }
+  }
+
+  // C tile through shared memory: sC[j][i] so that global stores run along rows
+  __syncthreads();
+  float* sC = sB;
+#pragma unroll
+  for (int r = 0; r < SP_RPW; ++r) sC[lane * (SP_TM + 1) + warp * SP_RPW + r] = acc[r];
+  __syncthreads();
+  for (uint32_t idx = threadIdx.x; idx < SP_TN * SP_TM; idx += SP_WARPS * 32) {
+    const uint32_t j = idx / SP_TM, i = idx % SP_TM;
+    if (j0 + j < D.n && i0 + i < D.m) {
+      T* dst = Cb + (size_t)(j0 + j) * D.ldc + i0 + i;
+      float out = D.alpha * sC[j * (SP_TM + 1) + i];
+      if (D.beta != 0.f) out += D.beta * load_as_float(dst);
+      store_from_float(dst, out);
+    }
+  }
+}
+
+template <typename T, typename Rows>
+int launch_spmm(const Rows& A, SpmmDense D, cudaStream_t s) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  // chunk of k staged per pass: as much as fits next to the C tile
+  const size_t c_tile = (size_t)SP_TN * (SP_TM + 1) * 4;
+  size_t budget = (size_t)di.max_smem_optin - 1024;
+  size_t kc = budget / (SP_PAD * 4);
+  if (kc > D.k) kc = D.k;
+  if (kc == 0) kc = 1;
+  size_t smem = kc * SP_PAD * 4;
+  if (smem < c_tile) smem = c_tile;
+  D.kc = (uint32_t)kc;
+  static std::atomic<size_t> attr_bytes[64];
+  int dev = 0;
+  SPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_bytes[dev & 63].load() < smem) {
+    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_rowsplit_kernel<T, Rows>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    attr_bytes[dev & 63].store(budget);
+  }
+  const size_t row_tiles = ceil_div(D.m, SP_TM), col_tiles = ceil_div(D.n, SP_TN);
+  const size_t ctas = row_tiles * col_tiles * D.num_batches;
+  if (ctas == 0) return SPFY_OK;
+  if (ctas >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "spmm: grid too large");
+  spmm_rowsplit_kernel<T, Rows><<<(unsigned)ctas, SP_WARPS * 32, smem, s>>>(A, D);
+  SPFY_LAUNCH_OK("spmm_rowsplit_kernel");
+  return SPFY_OK;
+}
+
+int elementwise_grid(size_t items, int* grid) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  size_t blocks = ceil_div(items, 256);
+  const size_t cap = (size_t)di.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (!blocks) blocks = 1;
+  *grid = (int)blocks;
+  return SPFY_OK;
+}
+
+template <typename T>
+int threshold_impl(const void* in, size_t ld, size_t rows, size_t cols, float thr, int32_t* row_idx,
+                   int32_t* col_idx, float* vals, size_t capacity, int64_t* d_nnz,
+                   int32_t* row_ptr, int32_t* counts, cudaStream_t s) {
+  int grid = 1;
+  int rc = elementwise_grid(rows * 32, &grid);
+  if (rc) return rc;
+  threshold_count_kernel<T><<<grid, 256, 0, s>>>((const T*)in, ld, (uint32_t)rows, (uint32_t)cols, thr, counts);
+  SPFY_LAUNCH_OK("threshold_count_kernel");
+  exclusive_scan_kernel<<<1, 1024, 0, s>>>(counts, (uint32_t)rows, row_ptr, d_nnz);
+  SPFY_LAUNCH_OK("exclusive_scan_kernel");
+  threshold_fill_kernel<T><<<grid, 256, 0, s>>>((const T*)in, ld, (uint32_t)rows, (uint32_t)cols, thr,
+                                               row_ptr, row_idx, col_idx, vals, capacity);
+  SPFY_LAUNCH_OK("threshold_fill_kernel");
+  return SPFY_OK;
+}
+
+}  // namespace
+}  // namespace spfy
+
+using namespace spfy;
+
+extern "C" {
+
+int spfy_threshold_workspace_bytes(size_t rows, size_t cols, size_t* bytes) {
+  (void)cols;
+  if (bytes) *bytes = round_up((rows + 1) * 4, 256) * 2;  // counts + row_ptr
+  return SPFY_OK;
+}
+
+int spfy_threshold_to_coo(int dtype, const void* in, size_t ld_in, size_t rows, size_t cols,
+                          float threshold, int32_t* row_idx, int32_t* col_idx, float* vals,
+                          size_t capacity, int64_t* d_nnz, int32_t* d_row_ptr_or_null,
+                          void* workspace, size_t workspace_bytes, spfy_stream_t stream) {
+  if (!in || !row_idx || !col_idx || !vals || !d_nnz)
+    return fail(SPFY_E_INVALID, "threshold_to_coo: null pointer");
+  if (ld_in < cols) return fail(SPFY_E_INVALID, "threshold_to_coo: ld < cols");
+  if (rows >= (1ull << 31) || cols >= (1ull << 31) || rows * cols >= (1ull << 31))
+    return fail(SPFY_E_UNSUPPORTED, "threshold_to_coo: matrix too large for int32 offsets");
+  size_t need = 0;
+  spfy_threshold_workspace_bytes(rows, cols, &need);
+  if (!workspace || workspace_bytes < need)
+    return fail(SPFY_E_WORKSPACE, "threshold_to_coo: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* counts = (int32_t*)workspace;
+  int32_t* row_ptr = d_row_ptr_or_null ? d_row_ptr_or_null
+                                       : (int32_t*)((uint8_t*)workspace + need / 2);
+  if (rows == 0 || cols == 0) {
+    SPFY_CUDA_OK(cudaMemsetAsync(d_nnz, 0, sizeof(int64_t), s));
+    if (d_row_ptr_or_null) SPFY_CUDA_OK(cudaMemsetAsync(d_row_ptr_or_null, 0, (rows + 1) * 4, s));
+    return SPFY_OK;
+  }
+  switch (dtype) {
+    case SPFY_F32: return threshold_impl<float>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, counts, s);
+    case SPFY_F16: return threshold_impl<__half>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, counts, s);
+    case SPFY_BF16: return threshold_impl<__nv_bfloat16>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, counts, s);
+    default: return fail(SPFY_E_UNSUPPORTED, "threshold_to_coo: dtype %d", dtype);
+  }
+}
+
+int spfy_coo_to_csr(const int32_t* row_idx, size_t nnz, size_t rows, int32_t* row_ptr,
+                    spfy_stream_t stream) {
+  if ((!row_idx && nnz) || !row_ptr) return fail(SPFY_E_INVALID, "coo_to_csr: null pointer");
+  if (nnz >= (1ull << 31) || rows >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "coo_to_csr: too large");
+  int grid = 1;
+  int rc = elementwise_grid(nnz + 1, &grid);
+  if (rc) return rc;
+  coo_to_csr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(row_idx, nnz, (uint32_t)rows, row_ptr);
+  SPFY_LAUNCH_OK("coo_to_csr_kernel");
+  return SPFY_OK;
+}
+
+int spfy_spmm_workspace_bytes(size_t m, size_t nnz, size_t* bytes) {
+  (void)nnz;
+  if (bytes) *bytes = round_up((m + 1) * 4, 256);
+  return SPFY_OK;
+}
+
+int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
+                                  const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
+                                  const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
+                                  size_t strideC, float alpha, float beta, spfy_stream_t stream) {
+  if (m == 0 || n == 0 || num_batches == 0) return SPFY_OK;
+  if (!row_ptr || !B || !C) return fail(SPFY_E_INVALID, "spmm_csr: null pointer");
+  if (ldb < k || ldc < m) return fail(SPFY_E_INVALID, "spmm_csr: leading dimension too small");
+  if (m >= (1ull << 31) || n >= (1ull << 31) || k >= (1ull << 31))
+    return fail(SPFY_E_UNSUPPORTED, "spmm_csr: dimension too large");
+  CsrRows A{row_ptr, col_idx, vals};
+  SpmmDense D;
+  memset(&D, 0, sizeof(D));
+  D.B = B; D.C = C; D.Cs = nullptr;
+  D.ldb = ldb; D.strideB = strideB; D.ldc = ldc; D.strideC = strideC;
+  D.m = (uint32_t)m; D.k = (uint32_t)k; D.n = (uint32_t)n; D.num_batches = (uint32_t)num_batches;
+  D.alpha = alpha; D.beta = beta;
+  return launch_spmm<float, CsrRows>(A, D, (cudaStream_t)stream);
+}
+
+int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,
+                                  const int32_t* row_idx, const int32_t* col_idx, const float* vals,
+                                  const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
+                                  size_t strideC, float alpha, float beta, void* workspace,
+                                  size_t workspace_bytes, spfy_stream_t stream) {
+  size_t need = 0;
+  spfy_spmm_workspace_bytes(m, nnz, &need);
+  if (!workspace || workspace_bytes < need)
+    return fail(SPFY_E_WORKSPACE, "spmm_coo: workspace %zu < %zu bytes", workspace_bytes, need);
+  int rc = spfy_coo_to_csr(row_idx, nnz, m, (int32_t*)workspace, stream);
+  if (rc) return rc;
+  return spfy_spmm_csr_strided_batched(m, k, n, num_batches, (const int32_t*)workspace, col_idx, vals,
+                                       B, ldb, strideB, C, ldc, strideC, alpha, beta, stream);
+}
+
+int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t block,
+                           size_t ell_cols, size_t num_batches, const int64_t* const* col_idx,
+                           const void* const* values, const void* B, size_t ldb, void* const* Cs,
+                           size_t ldc, float alpha, float beta, spfy_stream_t stream) {
+  if (rows == 0 || n == 0 || num_batches == 0) return SPFY_OK;
+  if (!col_idx || !values || !B || !Cs) return fail(SPFY_E_INVALID, "spmm_bell: null pointer");
+  if (block == 0 || ell_cols % block) return fail(SPFY_E_INVALID, "spmm_bell: ell_cols must be a multiple of block");
+  if (ldb < cols || ldc < rows) return fail(SPFY_E_INVALID, "spmm_bell: leading dimension too small");
+  SpmmDense D;
+  memset(&D, 0, sizeof(D));
+  D.B = B; D.C = nullptr; D.Cs = Cs;
+  D.ldb = ldb; D.strideB = 0; D.ldc = ldc; D.strideC = 0;
+  D.m = (uint32_t)rows; D.k = (uint32_t)cols; D.n = (uint32_t)n; D.num_batches = (uint32_t)num_batches;
+  D.alpha = alpha; D.beta = beta;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case SPFY_F32: {
+      BellRows<float> A{col_idx, (const float* const*)values, (uint32_t)block, (uint32_t)ell_cols, (uint32_t)(ell_cols / block)};
+      return launch_spmm<float, BellRows<float>>(A, D, s);
+    }
+    case SPFY_F16: {
+      BellRows<__half> A{col_idx, (const __half* const*)values, (uint32_t)block, (uint32_t)ell_cols, (uint32_t)(ell_cols / block)};
+      return launch_spmm<__half, BellRows<__half>>(A, D, s);
+    }
+    case SPFY_BF16: {
+      BellRows<__nv_bfloat16> A{col_idx, (const __nv_bfloat16* const*)values, (uint32_t)block, (uint32_t)ell_cols, (uint32_t)(ell_cols / block)};
+      return launch_spmm<__nv_bfloat16, BellRows<__nv_bfloat16>>(A, D, s);
+    }
+    default: return fail(SPFY_E_UNSUPPORTED, "spmm_bell: dtype %d", dtype);
+  }
+}
+
+}  // extern "C"
