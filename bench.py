@@ -1,0 +1,407 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path of sparsify.me on B200: 2:4 magnitude prune+compress of every weight
+matrix of a ResNet shape table, then the 2:4 sparse GEMM (spmma) of every layer.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One STEP = one pass over one batch of synthetic input: ONE batched prune+compress launch over all
+layers' weights (spfy_prune24_batched) + one spmma launch per layer (spfy_spmma), weights
+orientation M = C_out, K = C_in*kh*kw, N = H*W*b.  Workload = BASELINE.json
+configs[1]: all of datasets/resnet50.csv, fp16, b = 32 images per GPU.  Every layer has its own
+B / D buffers (7.4 GB per step, far larger than the 126 MB L2), so nothing is re-read from L2
+between layers or steps.
+
+value  : dense-equivalent TFLOP/s (2*M*N*K summed over layers and ranks / step time), inputs
+         resident in HBM, device-timed with CUDA events, max over ranks.
+e2e    : the same metric through the reference-shaped public call `spmma(A, B, C, m, n, k, b)`
+         with HOST (pinned) buffers: H2D of A and B, prune+compress+multiply, D2H of C, per layer,
+         all inside the timed region.
+N > 1  : weak scaling -- every rank runs the same table on its own 32 images (the global batch is
+         sharded on image boundaries; no data-path collective).
+--impl reference : the CPU oracle port of the same math on the host cores (the reference has no
+         CPU path of its own and its cusparseLt build is closed source; when oracle/_ref holds the
+         cusparseLt comparator its B200 timing is added under "cusparselt").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "2:4 spmma TFLOP/s over ResNet-50 GEMM shapes (dense-equivalent 2MNK, prune+compress included)"
+UNIT = "TFLOP/s"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def layer_table(spfy, csv, batch):
+    shapes = spfy.shapes.read_shapes(csv)
+    return [spfy.shapes.to_gemm(s, "weights", batch) for s in shapes]
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(spfy, orc, gemms, dtype_code, seconds_target=15.0, ncols=2048):
+    """The oracle port (fp32 accumulate over the CANONICAL compressed operand, OpenMP over rows) on a
+    bounded sample of the same workload: every layer of the table, first `ncols` columns of N."""
+    import numpy as np
+    rng = np.random.default_rng(0x5EED)
+    flops = 0.0
+    t_total = 0.0
+    done = 0
+    for g in gemms:
+        n = min(ncols, g.N)
+        a_bits = orc.from_f32(dtype_code, rng.uniform(-1, 1, (g.M, g.K)).astype(np.float32))
+        b_bits = orc.from_f32(dtype_code, rng.uniform(-1, 1, (g.K, n)).astype(np.float32))
+        t0 = time.perf_counter()
+        pr = orc.prune24_strip(dtype_code, a_bits, want_mask=False)
+        orc.spmma_compressed_f32(dtype_code, pr["vals"], pr["meta"], g.M, g.K, b_bits)
+        t_total += time.perf_counter() - t0
+        flops += 2.0 * g.M * n * g.K
+        done += 1
+        if t_total > seconds_target:
+            break
+    return {"value": flops / t_total / 1e12, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "sample": f"prune24+spmma of the first {done} of {len(gemms)} layers, first {ncols} columns of N each, "
+                      f"{t_total:.1f} s of host time (oracle/spfy_oracle.cpp, OpenMP, fp32 accumulate)"}
+
+
+def cusparselt_comparator(csv, batch):
+    exe = os.path.join(ROOT, "oracle", "_ref", "cusparselt_ref")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "sweep", os.path.join(ROOT, "datasets", csv), str(batch)], capture_output=True,
+                             text=True, timeout=600)
+        for line in out.stdout.splitlines()[::-1]:
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": (out.stderr or out.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:300]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    spfy = ge.load_package()
+    orc = ge.load_oracle()
+    gemms = layer_table(spfy, args.csv, args.batch)
+    dt = 0 if args.dtype == "fp16" else 1
+    vals, best = [], None
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(spfy, orc, gemms, dt, seconds_target=max(2.0, 60.0 / (args.warmup + args.steps)), ncols=1024)
+        if i >= args.warmup:
+            vals.append(r["value"])
+            best = r
+    v = statistics.mean(vals)
+    flops_step = sum(spfy.shapes.spmma_flops(g) for g in gemms)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": flops_step / (v * 1e12) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dt == 0 else "bf16", "data": "synthetic",
+            "config": config_dict(args, len(gemms)),
+            "cpu_baseline": dict(best, value=v),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference has no CPU path (SURVEY.md 0.3): this is the oracle port of the same math on the host "
+                    "cores, each step a bounded sample scaled by FLOPs; ms_per_step is the extrapolated full-workload time"}
+    cmp_ = cusparselt_comparator(args.csv, args.batch)
+    if cmp_ is not None:
+        line["cusparselt"] = cmp_
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(args, nlayers):
+    return {"workload": f"datasets/{args.csv}: all {nlayers} layers, weights orientation (M=C_out, K=C_in*kh*kw, "
+                        f"N=H*W*b), b={args.batch} images per GPU, 2:4 magnitude prune+compress (one batched launch) "
+                        f"+ spmma per layer",
+            "csv": args.csv, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+            "l2_policy": "inputs larger than L2 (7.4 GB of distinct B/D buffers per step vs 126 MB L2)",
+            "parallelism": f"batch-sharded x{args.gpus}, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--csv", default="resnet50.csv")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--per-layer", action="store_true", help="also print a per-layer table to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import ctypes
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (sparsify.me_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spfy = ge.load_package()
+    tdt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    dcode = spfy.F16 if args.dtype == "fp16" else spfy.BF16
+    gemms = layer_table(spfy, args.csv, args.batch)
+    hbm_peak, tc_burst, tc_sust, peak_src = read_peaks()
+
+    # ---- resident synthetic inputs: per layer W [M,K], B [K,N], D [M,N], compressed operand ----
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x5EED + rank)
+    layers = []
+    for g in gemms:
+        w = (torch.rand(g.M, g.K, device=dev, generator=gen) * 2 - 1).to(tdt)
+        b = (torch.rand(g.K, g.N, device=dev, generator=gen) * 2 - 1).to(tdt)
+        d = torch.empty(g.M, g.N, device=dev, dtype=tdt)
+        vb, mb = spfy.compressed_bytes(tdt, g.M, g.K)
+        comp = spfy.Compressed24(torch.empty(vb, dtype=torch.uint8, device=dev),
+                                 torch.empty(mb, dtype=torch.uint8, device=dev), g.M, g.K, tdt, spfy.LAYOUT_SM100)
+        layers.append((g, w, b, d, comp))
+
+    class Item(ctypes.Structure):
+        _fields_ = [("in_", ctypes.c_void_p), ("ld_in", ctypes.c_size_t), ("out_dense", ctypes.c_void_p),
+                    ("ld_out", ctypes.c_size_t), ("comp_vals", ctypes.c_void_p), ("meta", ctypes.c_void_p),
+                    ("rows", ctypes.c_size_t), ("cols", ctypes.c_size_t)]
+
+    items = (Item * len(layers))()
+    for i, (g, w, b, d, comp) in enumerate(layers):
+        items[i] = Item(w.data_ptr(), w.stride(0), None, 0, comp.vals.data_ptr(), comp.meta.data_ptr(), g.M, g.K)
+    items_p = ctypes.cast(items, ctypes.c_void_p)
+
+    def prune_all():
+        spfy.capi.spfy_prune24_batched(dcode, spfy.LAYOUT_SM100, items_p, len(layers),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def spmma_all():
+        for g, w, b, d, comp in layers:
+            spfy.spmma_compressed(comp, b, out=d)
+
+    flops_step = sum(spfy.shapes.spmma_flops(g) for g in gemms)
+    spmma_bytes_step = sum(spfy.shapes.spmma_bytes(g) for g in gemms)
+    prune_bytes_step = sum(spfy.shapes.prune24_bytes(g.M, g.K) for g in gemms)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        prune_all()
+        spmma_all()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = spfy.launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0.record()
+    for s in range(args.steps):
+        ev[s][0].record()
+        prune_all()
+        ev[s][1].record()
+        spmma_all()
+        ev[s][2].record()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = spfy.launch_count() - launches0
+    total_ms = e0.elapsed_time(e1)
+    prune_ms = sum(ev[s][0].elapsed_time(ev[s][1]) for s in range(args.steps)) / args.steps
+    spmma_ms = sum(ev[s][1].elapsed_time(ev[s][2]) for s in range(args.steps)) / args.steps
+    t = torch.tensor([total_ms, prune_ms, spmma_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, prune_ms, spmma_ms = (float(x) for x in t.tolist())
+    ms_per_step = total_ms / args.steps
+    value = flops_step * world / (ms_per_step * 1e-3) / 1e12
+
+    # ---- end to end through the reference-shaped call with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        hostbuf = {}
+
+        def pinned(key, shape):
+            if key not in hostbuf:
+                hostbuf[key] = torch.empty(shape, dtype=tdt).pin_memory()
+            return hostbuf[key]
+
+        for g, w, b, d, comp in layers:  # host images of the inputs, one per unique shape
+            if ("w", g) not in hostbuf:
+                pinned(("w", g), (g.M, g.K)).copy_(w)
+                pinned(("b", g), (g.K, g.N)).copy_(b)
+                pinned(("d", g), (g.M, g.N))
+        h2d = sum((g.M * g.K + g.K * g.N) * 2 for g in gemms)
+        d2h = sum(g.M * g.N * 2 for g in gemms)
+
+        def e2e_step():
+            for g, w, b, d, comp in layers:
+                w.copy_(hostbuf[("w", g)], non_blocking=True)
+                b.copy_(hostbuf[("b", g)], non_blocking=True)
+                spfy.spmma(w, b, d, g.M, g.N, g.K, args.batch)
+                hostbuf[("d", g)].copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item()) / args.e2e_steps
+        e2e = {"value": flops_step * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+               "api": "spmma(A, B, C, m, n, k, b) per layer: pinned H2D of A and B, prune in place + compress + "
+                      "tcgen05 matmul, D2H of C"}
+        # restore the resident weights for anything that follows
+        del hostbuf
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    achieved = spmma_bytes_step / (spmma_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
+        "config": config_dict(args, len(gemms)),
+        "clocks": clocks, "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "spmma_kernel (tcgen05.mma.sp)", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": spmma_bytes_step, "launches_per_step": len(layers),
+                     "ms_per_step": spmma_ms,
+                     "tflops": flops_step / (spmma_ms * 1e-3) / 1e12,
+                     "frac_of_sparse_tensor_peak": flops_step / (spmma_ms * 1e-3) / 1e12 / (2 * tc_sust)},
+        "prune": {"kernel": "prune24_batched_kernel", "gbs": prune_bytes_step / (prune_ms * 1e-3) / 1e9,
+                  "frac": prune_bytes_step / (prune_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_step": prune_ms,
+                  "algorithmic_bytes_per_step": prune_bytes_step,
+                  "note": "all layers' weights in one launch; 23.5 M elements, 3.125 B/element"},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu and world == 1:
+        orc = ge.load_oracle()
+        line["cpu_baseline"] = cpu_baseline(spfy, orc, gemms, 0 if args.dtype == "fp16" else 1)
+    if args.per_layer:
+        per_layer_report(spfy, layers, hbm_peak, tc_sust)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def per_layer_report(spfy, layers, hbm_peak, tc_peak):
+    """Per-shape timing (unique shapes), cold operands: stderr table for profiles/."""
+    import torch
+    seen = {}
+    for g, w, b, d, comp in layers:
+        if g in seen:
+            continue
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=b.device)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0.record()
+            spfy.spmma_compressed(comp, b, out=d)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = statistics.median(ts)
+        by = spfy.shapes.spmma_bytes(g)
+        fl = spfy.shapes.spmma_flops(g)
+        seen[g] = ms
+        print(f"layer M={g.M:5d} K={g.K:5d} N={g.N:7d}  {ms*1e3:8.1f} us  {by/ms/1e6:7.0f} GB/s ({by/ms/1e6/hbm_peak:5.2f} of HBM)"
+              f"  {fl/ms/1e9:7.1f} TFLOP/s ({fl/ms/1e9/(2*tc_peak):5.2f} of sparse TC)", file=sys.stderr)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -114,11 +114,9 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
-__global__ void __launch_bounds__(256)
-prune24_strip_kernel(const __grid_constant__ Prune24Params P) {
-  const size_t total = (size_t)P.dom_rows * P.units_per_row;
-  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+// one 16-column unit of one row: load, select, write every requested output
+__device__ __forceinline__ void prune24_unit(const Prune24Params& P, size_t t) {
+  {
     const uint32_t row = (uint32_t)(t / P.units_per_row);
     const uint32_t unit = (uint32_t)(t - (size_t)row * P.units_per_row);
     const uint32_t c0 = unit * 16;
@@ -222,6 +220,39 @@ prune24_strip_kernel(const __grid_constant__ Prune24Params P) {
   }
 }
 
+__global__ void __launch_bounds__(256)
+prune24_strip_kernel(const __grid_constant__ Prune24Params P) {
+  const size_t total = (size_t)P.dom_rows * P.units_per_row;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads)
+    prune24_unit(P, t);
+}
+
+// Many matrices in one launch (a whole model's weight set: the per-layer matrices are
+// <= 4.7 MB, so one launch per layer is launch-latency-bound).  Work is cut into CTA tiles
+// of 256 units; every tile belongs to exactly one matrix, so the table lookup is CTA-uniform.
+constexpr int PRUNE_BATCH_MAX = 96;
+struct Prune24Batch {
+  Prune24Params item[PRUNE_BATCH_MAX];
+  uint32_t tile_prefix[PRUNE_BATCH_MAX + 1];  // tile_prefix[i] = first CTA tile of item i
+  int count;
+};
+
+__global__ void __launch_bounds__(256)
+prune24_batched_kernel(const __grid_constant__ Prune24Batch Bt) {
+  const uint32_t tiles = Bt.tile_prefix[Bt.count];
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int lo = 0, hi = Bt.count - 1;  // last item with tile_prefix <= tile
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (Bt.tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+    }
+    const Prune24Params& P = Bt.item[lo];
+    const size_t t = (size_t)(tile - Bt.tile_prefix[lo]) * 256 + threadIdx.x;
+    if (t < (size_t)P.dom_rows * P.units_per_row) prune24_unit(P, t);
+  }
+}
+
 // ------------------------------------------------------------------------
 // TILE mode: per 4x4 tile choose, among the 90 patterns with exactly two kept
 // entries in every row and every column, the one with the largest sum |x|.
@@ -300,6 +331,36 @@ int grid_for(size_t work_items, int threads, int* grid) {
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
   *grid = (int)blocks;
+  return SPFY_OK;
+}
+
+// validate one matrix and fill the kernel's parameter block
+int fill_prune24(Prune24Params* out, int layout, const uint16_t* src, size_t ld_src, void* out_dense,
+                 size_t ld_out, void* comp_vals, void* meta, uint64_t* mask, size_t rows, size_t cols) {
+  Prune24Params P;
+  memset(&P, 0, sizeof(P));
+  P.in = src;
+  P.ld_in = ld_src;
+  P.out_dense = (uint16_t*)out_dense;
+  P.ld_out = ld_out;
+  P.comp_vals = (uint8_t*)comp_vals;
+  P.meta = (uint8_t*)meta;
+  P.mask = mask;
+  P.rows = (uint32_t)rows;
+  P.cols = (uint32_t)cols;
+  P.layout = layout;
+  P.G = (uint32_t)ceil_div(cols, 4);
+  P.mb = (uint32_t)ceil_div(P.G, 2);
+  P.k_tiles = (uint32_t)ceil_div(cols, 128);
+  const bool sm100_out = layout == SPFY_LAYOUT_SM100 && (comp_vals || meta);
+  P.dom_rows = sm100_out ? (uint32_t)round_up(rows, 128) : (uint32_t)rows;
+  P.units_per_row = sm100_out ? P.k_tiles * 8 : (uint32_t)ceil_div(cols, 16);
+  P.vec_in = ((uintptr_t)src % 16 == 0) && (ld_src % 8 == 0);
+  P.vec_out = out_dense && ((uintptr_t)out_dense % 16 == 0) && (ld_out % 8 == 0);
+  P.vec_cv = comp_vals && ((uintptr_t)comp_vals % 16 == 0) && (P.G % 4 == 0);
+  if (layout == SPFY_LAYOUT_SM100 && ((comp_vals && (uintptr_t)comp_vals % 16) || (meta && (uintptr_t)meta % 16)))
+    return fail(SPFY_E_INVALID, "prune24: SM100 outputs must be 16-byte aligned");
+  *out = P;
   return SPFY_OK;
 }
 
@@ -435,33 +496,56 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
   }
 
   Prune24Params P;
-  memset(&P, 0, sizeof(P));
-  P.in = src;
-  P.ld_in = ld_src;
-  P.out_dense = (uint16_t*)out_dense;
-  P.ld_out = ld_out;
-  P.comp_vals = (uint8_t*)comp_vals;
-  P.meta = (uint8_t*)meta;
-  P.mask = mask;
-  P.rows = (uint32_t)rows;
-  P.cols = (uint32_t)cols;
-  P.layout = layout;
-  P.G = (uint32_t)ceil_div(cols, 4);
-  P.mb = (uint32_t)ceil_div(P.G, 2);
-  P.k_tiles = (uint32_t)ceil_div(cols, 128);
-  const bool sm100_out = layout == SPFY_LAYOUT_SM100 && (comp_vals || meta);
-  P.dom_rows = sm100_out ? (uint32_t)round_up(rows, 128) : (uint32_t)rows;
-  P.units_per_row = sm100_out ? P.k_tiles * 8 : (uint32_t)ceil_div(cols, 16);
-  P.vec_in = ((uintptr_t)src % 16 == 0) && (ld_src % 8 == 0);
-  P.vec_out = out_dense && ((uintptr_t)out_dense % 16 == 0) && (ld_out % 8 == 0);
-  P.vec_cv = comp_vals && ((uintptr_t)comp_vals % 16 == 0) && (P.G % 4 == 0);
-  if (layout == SPFY_LAYOUT_SM100 && ((comp_vals && (uintptr_t)comp_vals % 16) || (meta && (uintptr_t)meta % 16)))
-    return fail(SPFY_E_INVALID, "prune24: SM100 outputs must be 16-byte aligned");
+  int rc = fill_prune24(&P, layout, src, ld_src, out_dense, ld_out, comp_vals, meta, mask, rows, cols);
+  if (rc) return rc;
   int grid = 1;
-  int rc = grid_for((size_t)P.dom_rows * P.units_per_row, 256, &grid);
+  rc = grid_for((size_t)P.dom_rows * P.units_per_row, 256, &grid);
   if (rc) return rc;
   prune24_strip_kernel<<<grid, 256, 0, s>>>(P);
   SPFY_LAUNCH_OK("prune24_strip_kernel");
+  return SPFY_OK;
+}
+
+int spfy_prune24_batched(int dtype, int layout, const spfy_prune24_item* items, size_t count,
+                         spfy_stream_t stream) {
+  if (dtype != SPFY_F16 && dtype != SPFY_BF16)
+    return fail(SPFY_E_UNSUPPORTED, "prune24_batched: dtype %d (need F16/BF16)", dtype);
+  if (layout != SPFY_LAYOUT_CANONICAL && layout != SPFY_LAYOUT_SM100)
+    return fail(SPFY_E_INVALID, "prune24_batched: bad layout %d", layout);
+  if (count && !items) return fail(SPFY_E_INVALID, "prune24_batched: null item table");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  static thread_local Prune24Batch Bt;  // 10 KB: keep it off the stack
+  size_t i = 0;
+  while (i < count) {
+    Bt.count = 0;
+    Bt.tile_prefix[0] = 0;
+    for (; i < count && Bt.count < PRUNE_BATCH_MAX; ++i) {
+      const spfy_prune24_item& it = items[i];
+      if (it.rows == 0 || it.cols == 0) continue;
+      if (!it.in) return fail(SPFY_E_INVALID, "prune24_batched: item %zu has a null input", i);
+      if (it.ld_in < it.cols || (it.out_dense && it.ld_out < it.cols))
+        return fail(SPFY_E_INVALID, "prune24_batched: item %zu leading dimension smaller than cols", i);
+      if (it.rows >= (1ull << 31) || it.cols >= (1ull << 31))
+        return fail(SPFY_E_UNSUPPORTED, "prune24_batched: item %zu too large", i);
+      Prune24Params& P = Bt.item[Bt.count];
+      rc = fill_prune24(&P, layout, (const uint16_t*)it.in, it.ld_in, it.out_dense, it.ld_out,
+                        it.comp_vals, it.meta, nullptr, it.rows, it.cols);
+      if (rc) return rc;
+      const size_t tiles = ceil_div((size_t)P.dom_rows * P.units_per_row, 256);
+      if ((size_t)Bt.tile_prefix[Bt.count] + tiles >= (1ull << 32))
+        return fail(SPFY_E_UNSUPPORTED, "prune24_batched: batch too large");
+      Bt.tile_prefix[Bt.count + 1] = Bt.tile_prefix[Bt.count] + (uint32_t)tiles;
+      ++Bt.count;
+    }
+    if (Bt.count == 0) continue;
+    const uint32_t tiles = Bt.tile_prefix[Bt.count];
+    const uint32_t cap = (uint32_t)di.sm_count * 16;
+    prune24_batched_kernel<<<tiles < cap ? tiles : cap, 256, 0, s>>>(Bt);
+    SPFY_LAUNCH_OK("prune24_batched_kernel");
+  }
   return SPFY_OK;
 }
 

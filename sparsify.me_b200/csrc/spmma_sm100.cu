@@ -329,7 +329,7 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
           const uint32_t e_col = tmem_base + TMEM_E_COL + (kiter & 1) * 4;
-          tc_cp_128x128b(e_col, make_smem_desc(smem_base + SMEM_E + stage * E_TILE_BYTES, 0, 128, LAYOUT_NONE));
+          tc_cp_128x128b(e_col, make_smem_desc(smem_base + SMEM_E + stage * E_TILE_BYTES, 16, 128, LAYOUT_NONE));
           const uint32_t k_left = P.k - kt * BK;
           const uint32_t nk = k_left >= BK ? 4u : (k_left + 31u) / 32u;
           const uint32_t sa = smem_base + SMEM_A + stage * A_TILE_BYTES;
@@ -338,12 +338,12 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           for (uint32_t j = 0; j < 4; ++j) {
             if (j < nk) {
               // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
-              const uint64_t da = make_smem_desc(sa + j * 32, 0, 1024, LAYOUT_SW128);
+              const uint64_t da = make_smem_desc(sa + j * 32, 16, 1024, LAYOUT_SW128);
               uint64_t db;
               if (!OPB_T)  // MN-major SW128: 8 k-rows per 1024B atom, 64-column groups BK*128 apart
                 db = make_smem_desc(sb + j * 32 * 128, BK * 128, 1024, LAYOUT_SW128);
               else         // K-major SW128: two 64-wide k halves, 64 bytes per MMA inside a row
-                db = make_smem_desc(sb + (j >> 1) * (BN * 128) + (j & 1) * 64, 0, 1024, LAYOUT_SW128);
+                db = make_smem_desc(sb + (j >> 1) * (BN * 128) + (j & 1) * 64, 16, 1024, LAYOUT_SW128);
               const uint32_t col = e_col + j;
               tc_mma_sp_f16(tmem_d, da, db, col & ~1u, P.idesc | (col & 1u), (kt | j) != 0);
             }

@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference's operator API on top of the C ABI (capi).
+
+Names, argument meaning, defaults and return values follow the reference templates:
+  sparsify            include/sparsify.me/sparsify.hxx:24-30  (weights, mask, m, n, sparsity_factor=0.5, stream)
+  spmma               include/sparsify.me/spmma.hxx:21-33     -> [prune_ms, compress_ms, mul_ms] (:117)
+  batched.spmm        include/sparsify.me/spmm.hxx:30-41      -> ms
+  batched.strided_coo include/sparsify.me/spmm.hxx:140-153    -> ms
+Tensors are torch CUDA tensors used as raw device buffers; all work is enqueued on torch's
+current stream.  Nothing here computes on the host.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import capi
+
+_DT = {torch.float16: capi.F16, torch.bfloat16: capi.BF16, torch.float32: capi.F32,
+       torch.float64: capi.F64}
+
+
+def _dtype_code(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise capi.SpfyError(capi.E_UNSUPPORTED, "dtype", f"unsupported dtype {t.dtype}")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise capi.SpfyError(capi.E_INVALID, "device pointer",
+                             "operand is not a CUDA tensor (sparsify.me_b200 has no host path)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class _Timer:
+    """cudaEvent pair on the current stream -- the reference's util::timer_t
+    (include/sparsify.me/util/timer.hxx:24-55): begin/end record + synchronise."""
+
+    def __init__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+
+    def begin(self):
+        self.a.record()
+
+    def end(self):
+        self.b.record()
+        self.b.synchronize()
+        return self.a.elapsed_time(self.b)
+
+
+# ----------------------------------------------------------------------------- A1
+def sparsify(weights, mask, m, n, sparsity_factor=0.5, blk=(2, 2)):
+    """sparsifyme::sparsify<BLK_M,BLK_N> (sparsify.hxx:24-82), exact positional semantics.
+    `weights`: m*n elements (any 2/4/8-byte float type), pruned in place;
+    `mask`: m*n int64/uint64 words (std::size_t in the reference)."""
+    if mask.element_size() != 8:
+        raise capi.SpfyError(capi.E_INVALID, "sparsify", "mask must hold 64-bit words")
+    capi.spfy_prune_blocks_ref(_dtype_code(weights), _ptr(weights), _ptr(mask), m, n, blk[0], blk[1],
+                               float(sparsity_factor), _stream())
+
+
+# ------------------------------------------------------------------------- A2 / A3
+@dataclass
+class Compressed24:
+    """The compressed 2:4 operand (what cusparseLtSpMMACompress returns, spmma.hxx:97-104)."""
+    vals: torch.Tensor      # uint8 buffer
+    meta: torch.Tensor      # uint8 buffer
+    rows: int
+    cols: int
+    dtype: torch.dtype
+    layout: int
+
+
+def compressed_bytes(dtype, rows, cols, layout=capi.LAYOUT_SM100):
+    vb, mb = ctypes.c_size_t(), ctypes.c_size_t()
+    capi.spfy_compressed_bytes(_DT[dtype], rows, cols, layout, ctypes.byref(vb), ctypes.byref(mb))
+    return vb.value, mb.value
+
+
+def prune24(a, out_dense=None, mask=None, layout=capi.LAYOUT_SM100, mode=capi.PRUNE_STRIP_MAG,
+            compress=True, inplace=False, out=None):
+    """2:4 magnitude prune (+ compress) of the row-major matrix `a` [rows, cols] in ONE kernel.
+    Replaces cusparseLtSpMMAPrune + cusparseLtSpMMACompress (spmma.hxx:85-104).
+    Returns a Compressed24 (or None when compress=False)."""
+    assert a.dim() == 2 and a.stride(1) == 1
+    rows, cols = a.shape
+    if inplace:
+        out_dense = a
+    comp = out
+    if compress and comp is None:
+        vb, mb = compressed_bytes(a.dtype, rows, cols, layout)
+        comp = Compressed24(torch.empty(vb, dtype=torch.uint8, device=a.device),
+                            torch.empty(mb, dtype=torch.uint8, device=a.device), rows, cols, a.dtype,
+                            layout)
+    capi.spfy_prune24(_dtype_code(a), mode, layout, _ptr(a), a.stride(0), _ptr(out_dense),
+                      out_dense.stride(0) if out_dense is not None else 0,
+                      _ptr(comp.vals) if comp else None, _ptr(comp.meta) if comp else None,
+                      _ptr(mask), rows, cols, _stream())
+    return comp
+
+
+def prune24_check(a):
+    """cusparseLtSpMMAPruneCheck (spmma.hxx:88-94): 0 iff `a` obeys 2:4 along its rows."""
+    flag = torch.empty(1, dtype=torch.int32, device=a.device)
+    capi.spfy_prune24_check(_dtype_code(a), _ptr(a), a.stride(0), a.shape[0], a.shape[1], _ptr(flag),
+                            _stream())
+    return int(flag.item())
+
+
+# ----------------------------------------------------------------------------- A4
+def spmma_compressed(comp, b, c=None, out=None, alpha=1.0, beta=0.0, op_b=capi.OP_N):
+    """D = alpha * A(2:4) * op(B) + beta * C on tcgen05.mma.sp (cusparseLtMatmul, spmma.hxx:106-114).
+    All dense operands row-major.  Returns D (== out, or a new tensor)."""
+    assert comp.layout == capi.LAYOUT_SM100
+    m, k = comp.rows, comp.cols
+    n = b.shape[1] if op_b == capi.OP_N else b.shape[0]
+    assert (b.shape[0] if op_b == capi.OP_N else b.shape[1]) == k
+    if out is None:
+        out = torch.empty(m, n, dtype=comp.dtype, device=b.device)
+    capi.spfy_spmma(_DT[comp.dtype], op_b, m, n, k, float(alpha), _ptr(comp.vals), _ptr(comp.meta),
+                    _ptr(b), b.stride(0), float(beta), _ptr(c), c.stride(0) if c is not None else 0,
+                    _ptr(out), out.stride(0), None, 0, _stream())
+    return out
+
+
+def spmma(a, b, c, m, n, k, batch_size=1, transpose_a=capi.OP_N, transpose_b=capi.OP_N, alpha=1.0,
+          beta=0.0):
+    """sparsifyme::spmma (spmma.hxx:21-118): prune A in place (2:4 magnitude), compress, multiply
+    into C (D aliases C, :52-53).  Returns [prune_ms, compress_ms, mul_ms] like :117.  Our prune and
+    compress are one fused kernel, so it is timed under `prune` and `compress` only times the
+    (empty) remainder; batch_size is accepted and unused exactly like the reference (:29)."""
+    del batch_size
+    if transpose_a != capi.OP_N:
+        raise capi.SpfyError(capi.E_UNSUPPORTED, "spmma", "transpose_a is not supported")
+    if m % 8 or n % 8 or k % 8:  # spmma.hxx:45-49 (warning only, execution continues)
+        print("Matrix sizes must be a multiple of 8 for (sparse) Tensor Cores.")
+    a2 = a.view(-1)[: m * k].view(m, k)
+    b2 = b.view(-1)[: k * n].view(k, n) if transpose_b == capi.OP_N else b.view(-1)[: k * n].view(n, k)
+    c2 = c.view(-1)[: m * n].view(m, n)
+    vb, mb = compressed_bytes(a.dtype, m, k)
+    t = _Timer()
+    t.begin()
+    comp = Compressed24(torch.empty(vb, dtype=torch.uint8, device=a.device),
+                        torch.empty(mb, dtype=torch.uint8, device=a.device), m, k, a.dtype,
+                        capi.LAYOUT_SM100)
+    prune24(a2, inplace=True, out=comp)
+    prune_ms = t.end()
+    t.begin()
+    compress_ms = t.end()
+    t.begin()
+    spmma_compressed(comp, b2, c=c2 if beta != 0.0 else None, out=c2, alpha=alpha, beta=beta,
+                     op_b=transpose_b)
+    mul_ms = t.end()
+    return [prune_ms, compress_ms, mul_ms]
+
+
+# ------------------------------------------------------------------- unstructured path
+def threshold_to_coo(a, threshold, capacity=None, want_csr=False):
+    """Unstructured magnitude prune: keep x iff |x| > threshold; COO sorted by (row, col),
+    fp32 values, int32 indices (the operand format of spmm.hxx:165-168).
+    Returns (row_idx, col_idx, vals, nnz[, row_ptr]); index/value tensors are trimmed to nnz."""
+    rows, cols = a.shape
+    cap = rows * cols if capacity is None else capacity
+    dev = a.device
+    ri = torch.empty(cap, dtype=torch.int32, device=dev)
+    ci = torch.empty(cap, dtype=torch.int32, device=dev)
+    va = torch.empty(cap, dtype=torch.float32, device=dev)
+    nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    rp = torch.empty(rows + 1, dtype=torch.int32, device=dev)
+    wb = ctypes.c_size_t()
+    capi.spfy_threshold_workspace_bytes(rows, cols, ctypes.byref(wb))
+    ws = torch.empty(max(wb.value, 16), dtype=torch.uint8, device=dev)
+    capi.spfy_threshold_to_coo(_dtype_code(a), _ptr(a), a.stride(0), rows, cols, float(threshold),
+                               _ptr(ri), _ptr(ci), _ptr(va), cap, _ptr(nnz), _ptr(rp), _ptr(ws),
+                               ws.numel(), _stream())
+    n = int(nnz.item())
+    kept = min(n, cap)
+    res = (ri[:kept], ci[:kept], va[:kept], n)
+    return res + (rp,) if want_csr else res
+
+
+def coo_to_csr(row_idx, rows):
+    rp = torch.empty(rows + 1, dtype=torch.int32, device=row_idx.device)
+    capi.spfy_coo_to_csr(_ptr(row_idx), row_idx.numel(), rows, _ptr(rp), _stream())
+    return rp
+
+
+class batched:
+    """namespace sparsifyme::batched"""
+
+    @staticmethod
+    def strided_coo(a_num_rows, a_num_cols, a_nnz, b_num_rows, b_num_cols, num_batches, a_rows, a_cols,
+                    a_values, b, c, alpha=1.0, beta=0.0):
+        """batched::strided_coo (spmm.hxx:140-193): C_b = alpha*A*B_b + beta*C_b with ONE COO A
+        (row-sorted), B_b = b[i] k x n column-major (ldb = k), C_b m x n column-major (ldc = m);
+        b and c are single slabs strided by ldb*n / ldc*n (:172,:175 intent).  Returns ms."""
+        assert b_num_rows == a_num_cols
+        ldb, ldc = b_num_rows, a_num_rows
+        wb = ctypes.c_size_t()
+        capi.spfy_spmm_workspace_bytes(a_num_rows, a_nnz, ctypes.byref(wb))
+        ws = torch.empty(max(wb.value, 16), dtype=torch.uint8, device=b.device)
+        t = _Timer()
+        t.begin()
+        capi.spfy_spmm_coo_strided_batched(a_num_rows, a_num_cols, a_nnz, b_num_cols, num_batches,
+                                           _ptr(a_rows), _ptr(a_cols), _ptr(a_values), _ptr(b), ldb,
+                                           ldb * b_num_cols, _ptr(c), ldc, ldc * b_num_cols,
+                                           float(alpha), float(beta), _ptr(ws), ws.numel(), _stream())
+        return t.end()
+
+    @staticmethod
+    def csr(m, k, n, num_batches, row_ptr, col_idx, vals, b, c, alpha=1.0, beta=0.0):
+        capi.spfy_spmm_csr_strided_batched(m, k, n, num_batches, _ptr(row_ptr), _ptr(col_idx),
+                                           _ptr(vals), _ptr(b), k, k * n, _ptr(c), m, m * n,
+                                           float(alpha), float(beta), _stream())
+
+    @staticmethod
+    def spmm(col_idx_list, values_list, b, c_list, m, n, k, block, ell_cols, alpha=1.0, beta=0.0):
+        """batched::spmm (spmm.hxx:30-138): per batch C_b = alpha*A_b*B + beta*C_b, A_b blocked-ELL
+        (containers/ell.hxx:24-33), B k x n column-major shared, C_b m x n column-major.
+        One launch covers every batch element (the reference fans out one host thread +
+        stream per batch, :94-115).  Returns ms."""
+        dev = b.device
+        nb = len(values_list)
+        ci = torch.tensor([t.data_ptr() for t in col_idx_list], dtype=torch.int64, device=dev)
+        va = torch.tensor([t.data_ptr() for t in values_list], dtype=torch.int64, device=dev)
+        cs = torch.tensor([t.data_ptr() for t in c_list], dtype=torch.int64, device=dev)
+        t = _Timer()
+        t.begin()
+        capi.spfy_spmm_bell_batched(_dtype_code(b), m, k, n, block, ell_cols, nb, _ptr(ci), _ptr(va),
+                                    _ptr(b), k, _ptr(cs), m, float(alpha), float(beta), _stream())
+        return t.end()

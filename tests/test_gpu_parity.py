@@ -1,0 +1,377 @@
+"""GPU parity tests: every CUDA entry point (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bit-exact for masks / compressed values / metadata / indices; GEMM outputs within
+max relative error 1e-2 of the fp64 oracle (north_star tolerance for fp16/bf16)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-2  # BASELINE.json north_star: "max relative error 1e-2 for fp16/bf16"
+
+
+def rand_bits(orc, dtype, shape, seed, lo=-1.0, hi=1.0):
+    rng = np.random.default_rng(seed)
+    return orc.from_f32(dtype, rng.uniform(lo, hi, shape).astype(np.float32))
+
+
+def to_dev(bits, dtype_code, dev):
+    tdt = torch.float16 if dtype_code == 0 else torch.bfloat16
+    return torch.from_numpy(np.ascontiguousarray(bits).view(np.int16).copy()).to(dev).view(tdt)
+
+
+def bits_of(t):
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def rel_err(got, want):
+    scale = np.maximum(np.abs(want), 1e-2 * max(np.abs(want).max(), 1e-30))
+    return float(np.max(np.abs(got - want) / scale))
+
+
+# ------------------------------------------------------------------ A1 positional sparsify
+@pytest.mark.parametrize("m,n", [(8, 8), (12544, 147), (196, 4608), (7, 5), (1, 1), (64, 64)])
+@pytest.mark.parametrize("np_dtype,t_dtype", [(np.float32, torch.float32), (np.float16, torch.float16),
+                                              (np.float64, torch.float64)])
+def test_sparsify_positional_matches_oracle(spfy, orc, cuda, m, n, np_dtype, t_dtype):
+    w = (1.0 + (np.arange(m * n) % 251)).astype(np_dtype)
+    want_w, want_mask = orc.prune_blocks_ref(w, m, n, 2, 2, 0.5)
+    dw = torch.from_numpy(w.copy()).to(cuda)
+    dmask = torch.full((m * n,), 77, dtype=torch.int64, device=cuda)
+    spfy.sparsify(dw, dmask, m, n)
+    assert np.array_equal(dw.cpu().numpy(), want_w)
+    assert np.array_equal(dmask.cpu().numpy().view(np.uint64), want_mask)
+
+
+@pytest.mark.parametrize("blk,sf", [((2, 2), 0.25), ((2, 2), 0.75), ((4, 4), 0.5), ((4, 2), 0.5),
+                                    ((2, 4), 0.5), ((1, 1), 0.5), ((1, 1), 1.0), ((2, 2), 1.0)])
+def test_sparsify_other_blocks(spfy, orc, cuda, blk, sf):
+    m, n = 36, 52
+    w = (1.0 + (np.arange(m * n) % 251)).astype(np.float32)
+    want_w, want_mask = orc.prune_blocks_ref(w, m, n, blk[0], blk[1], sf)
+    dw = torch.from_numpy(w.copy()).to(cuda)
+    dmask = torch.zeros(m * n, dtype=torch.int64, device=cuda)
+    spfy.sparsify(dw, dmask, m, n, sparsity_factor=sf, blk=blk)
+    assert np.array_equal(dw.cpu().numpy(), want_w)
+    assert np.array_equal(dmask.cpu().numpy().view(np.uint64), want_mask)
+
+
+# ------------------------------------------------------------------ A2/A3 prune + compress
+PRUNE_SHAPES = [(64, 147), (128, 128), (64, 64), (256, 2304), (512, 4608), (130, 260), (1, 4), (3, 1),
+                (2048, 512), (100, 1000), (5, 37)]
+
+
+@pytest.mark.parametrize("rows,cols", PRUNE_SHAPES)
+@pytest.mark.parametrize("dt", [0, 1])
+def test_prune24_canonical_bit_exact(spfy, orc, cuda, rows, cols, dt):
+    bits = rand_bits(orc, dt, (rows, cols), seed=rows * 7919 + cols)
+    want = orc.prune24_strip(dt, bits)
+    a = to_dev(bits, dt, cuda)
+    dense = torch.empty_like(a)
+    mask = torch.zeros(rows * cols, dtype=torch.int64, device=cuda)
+    comp = spfy.prune24(a, out_dense=dense, mask=mask, layout=spfy.LAYOUT_CANONICAL)
+    assert np.array_equal(bits_of(dense), want["dense"])
+    assert np.array_equal(mask.cpu().numpy().view(np.uint64).reshape(rows, cols), want["mask"])
+    assert np.array_equal(comp.vals.cpu().numpy().view(np.uint16).reshape(rows, -1), want["vals"])
+    assert np.array_equal(comp.meta.cpu().numpy().reshape(rows, -1), want["meta"])
+    assert spfy.prune24_check(dense) == 0
+    assert orc.prune24_check(dt, want["dense"]) == 0
+
+
+@pytest.mark.parametrize("rows,cols", PRUNE_SHAPES)
+def test_prune24_sm100_layout_bit_exact(spfy, orc, cuda, rows, cols):
+    bits = rand_bits(orc, 0, (rows, cols), seed=rows * 31 + cols)
+    want = orc.prune24_strip(0, bits)
+    ov, om = orc.pack_sm100(want["vals"], want["meta"], rows, cols)
+    a = to_dev(bits, 0, cuda)
+    comp = spfy.prune24(a, layout=spfy.LAYOUT_SM100)
+    assert np.array_equal(comp.vals.cpu().numpy(), ov)
+    assert np.array_equal(comp.meta.cpu().numpy(), om)
+
+
+def test_prune24_inplace_and_strided(spfy, orc, cuda):
+    rows, cols, ld = 96, 200, 256
+    bits = rand_bits(orc, 0, (rows, ld), seed=5)
+    want = orc.prune24_strip(0, bits[:, :cols])
+    buf = to_dev(bits, 0, cuda)
+    a = buf[:, :cols]
+    spfy.prune24(a, inplace=True, compress=False)
+    got = bits_of(buf)
+    assert np.array_equal(got[:, :cols], want["dense"])
+    assert np.array_equal(got[:, cols:], bits[:, cols:])  # padding columns untouched
+
+
+def test_prune24_special_values(spfy, orc, cuda):
+    """ties, +-0, inf, nan, denormals: the tie-break (lower index wins) and the key order
+    (NaN > Inf > finite, -0 == +0) must agree bit for bit."""
+    specials = np.array([0x0000, 0x8000, 0x7C00, 0xFC00, 0x7E00, 0xFE01, 0x0001, 0x8001, 0x3C00, 0xBC00,
+                         0x3C01, 0x7BFF, 0xFBFF, 0x0400, 0x83FF, 0x3800], dtype=np.uint16)
+    rng = np.random.default_rng(11)
+    bits = rng.choice(specials, size=(64, 256)).astype(np.uint16)
+    for dt in (0, 1):
+        want = orc.prune24_strip(dt, bits)
+        a = to_dev(bits, dt, cuda)
+        dense = torch.empty_like(a)
+        comp = spfy.prune24(a, out_dense=dense, layout=spfy.LAYOUT_CANONICAL)
+        assert np.array_equal(bits_of(dense), want["dense"])
+        assert np.array_equal(comp.meta.cpu().numpy().reshape(64, -1), want["meta"])
+        assert np.array_equal(comp.vals.cpu().numpy().view(np.uint16).reshape(64, -1), want["vals"])
+
+
+def test_prune24_all_ties_keeps_first_two(spfy, cuda):
+    a = torch.ones(4, 16, dtype=torch.float16, device=cuda)
+    dense = torch.empty_like(a)
+    spfy.prune24(a, out_dense=dense, compress=False)
+    want = torch.tensor([1, 1, 0, 0] * 4, dtype=torch.float16, device=cuda).expand(4, 16)
+    assert torch.equal(dense, want)
+
+
+def test_prune24_idempotent_full_size(spfy, cuda):
+    """size-independent property at a BASELINE-size operand: pruning a pruned matrix is a no-op,
+    every group of 4 keeps exactly 2 slots, and kept entries are unchanged."""
+    torch.manual_seed(3)
+    a = (torch.rand(512, 4608, device=cuda) * 2 - 1).half()
+    d1 = torch.empty_like(a)
+    c1 = spfy.prune24(a, out_dense=d1)
+    d2 = torch.empty_like(a)
+    c2 = spfy.prune24(d1, out_dense=d2)
+    assert torch.equal(d1, d2)
+    assert torch.equal(c1.vals, c2.vals) and torch.equal(c1.meta, c2.meta)
+    nz = (d1 != 0).view(512, -1, 4).sum(-1)
+    assert int(nz.max()) <= 2
+    kept = d1 != 0
+    assert torch.equal(d1[kept], a[kept])
+    # magnitude property: every dropped entry is <= the smaller kept entry of its group
+    g = a.abs().float().view(512, -1, 4)
+    top2 = g.topk(2, dim=-1).values[..., 1]
+    dropped = torch.where(kept.view(512, -1, 4), torch.zeros_like(g), g)
+    assert bool((dropped.max(-1).values <= top2).all())
+
+
+def test_prune24_tile_mode_matches_oracle(spfy, orc, cuda):
+    bits = rand_bits(orc, 0, (64, 96), seed=21)
+    want_dense, _ = orc.prune24_tile(0, bits)
+    a = to_dev(bits, 0, cuda)
+    dense = torch.empty_like(a)
+    spfy.prune24(a, out_dense=dense, mode=spfy.PRUNE_TILE_MAG, compress=False)
+    got = bits_of(dense)
+    assert np.array_equal(got, want_dense)
+    nz = (got.reshape(16, 4, 24, 4) != 0)
+    assert (nz.sum(axis=3) <= 2).all() and (nz.sum(axis=1) <= 2).all()
+
+
+def test_prune24_batched_equals_single(spfy, orc, cuda):
+    import ctypes
+    shapes = [(64, 147), (64, 576), (128, 1152), (256, 2304), (512, 4608), (130, 260)] * 20  # > 96 items
+    ins, comps, singles = [], [], []
+    for i, (r, c) in enumerate(shapes):
+        a = to_dev(rand_bits(orc, 0, (r, c), seed=1000 + i), 0, cuda)
+        ins.append(a)
+        vb, mb = spfy.compressed_bytes(torch.float16, r, c)
+        comps.append((torch.zeros(vb, dtype=torch.uint8, device=cuda), torch.zeros(mb, dtype=torch.uint8, device=cuda)))
+        singles.append(spfy.prune24(a))
+
+    class Item(ctypes.Structure):
+        _fields_ = [("in_", ctypes.c_void_p), ("ld_in", ctypes.c_size_t), ("out_dense", ctypes.c_void_p),
+                    ("ld_out", ctypes.c_size_t), ("comp_vals", ctypes.c_void_p), ("meta", ctypes.c_void_p),
+                    ("rows", ctypes.c_size_t), ("cols", ctypes.c_size_t)]
+
+    items = (Item * len(shapes))()
+    for i, ((r, c), a, (v, m)) in enumerate(zip(shapes, ins, comps)):
+        items[i] = Item(a.data_ptr(), a.stride(0), None, 0, v.data_ptr(), m.data_ptr(), r, c)
+    spfy.capi.spfy_prune24_batched(spfy.F16, spfy.LAYOUT_SM100, ctypes.cast(items, ctypes.c_void_p), len(shapes),
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for (v, m), s in zip(comps, singles):
+        assert torch.equal(v, s.vals) and torch.equal(m, s.meta)
+
+
+# ------------------------------------------------------------------ A4 spmma
+SPMMA_SHAPES = [  # (M, K, N)
+    (128, 128, 128), (128, 256, 256), (64, 64, 512), (64, 147, 1024), (64, 148, 1000), (256, 512, 384),
+    (512, 1152, 520), (130, 260, 264), (2048, 512, 392), (16, 32, 8), (128, 4608, 128),
+]
+
+
+@pytest.mark.parametrize("M,K,N", SPMMA_SHAPES)
+@pytest.mark.parametrize("dt", [0, 1])
+def test_spmma_matches_fp64_oracle(spfy, orc, cuda, M, K, N, dt):
+    a_bits = rand_bits(orc, dt, (M, K), seed=M + 3 * K + 7 * N)
+    b_bits = rand_bits(orc, dt, (K, N), seed=M + 3 * K + 7 * N + 1)
+    pr = orc.prune24_strip(dt, a_bits, want_mask=False)
+    want = orc.spmma_f64(dt, pr["dense"], b_bits)
+    comp = spfy.prune24(to_dev(a_bits, dt, cuda))
+    d = spfy.spmma_compressed(comp, to_dev(b_bits, dt, cuda))
+    got = d.float().cpu().numpy().astype(np.float64)
+    assert rel_err(got, want) <= REL_TOL
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 256, 256), (64, 147 + 5, 520), (256, 1024, 136)])
+def test_spmma_transposed_b(spfy, orc, cuda, M, K, N):
+    a_bits = rand_bits(orc, 0, (M, K), seed=91)
+    bt_bits = rand_bits(orc, 0, (N, K), seed=92)
+    pr = orc.prune24_strip(0, a_bits, want_mask=False)
+    want = orc.spmma_f64(0, pr["dense"], bt_bits, op_b=1)
+    comp = spfy.prune24(to_dev(a_bits, 0, cuda))
+    d = spfy.spmma_compressed(comp, to_dev(bt_bits, 0, cuda), op_b=spfy.OP_T)
+    assert rel_err(d.float().cpu().numpy().astype(np.float64), want) <= REL_TOL
+
+
+def test_spmma_alpha_beta(spfy, orc, cuda):
+    M, K, N = 192, 320, 264
+    a_bits = rand_bits(orc, 0, (M, K), seed=1)
+    b_bits = rand_bits(orc, 0, (K, N), seed=2)
+    c_bits = rand_bits(orc, 0, (M, N), seed=3)
+    pr = orc.prune24_strip(0, a_bits, want_mask=False)
+    want = orc.spmma_f64(0, pr["dense"], b_bits, c_bits=c_bits, alpha=0.5, beta=-1.5)
+    comp = spfy.prune24(to_dev(a_bits, 0, cuda))
+    c = to_dev(c_bits, 0, cuda)
+    d = spfy.spmma_compressed(comp, to_dev(b_bits, 0, cuda), c=c, out=c, alpha=0.5, beta=-1.5)  # D aliases C
+    assert rel_err(d.float().cpu().numpy().astype(np.float64), want) <= REL_TOL
+
+
+def test_spmma_exact_on_small_integers(spfy, orc, cuda):
+    """integer-valued inputs make the fp32 accumulation exact: the output must then EQUAL the oracle,
+    which pins the metadata semantics (a wrong index would pick a different B row)."""
+    rng = np.random.default_rng(5)
+    M, K, N = 256, 384, 256
+    a = rng.integers(-4, 5, (M, K)).astype(np.float32)
+    b = rng.integers(-4, 5, (K, N)).astype(np.float32)
+    a_bits, b_bits = orc.from_f32(0, a), orc.from_f32(0, b)
+    pr = orc.prune24_strip(0, a_bits, want_mask=False)
+    want = orc.spmma_f64(0, pr["dense"], b_bits)
+    comp = spfy.prune24(to_dev(a_bits, 0, cuda))
+    d = spfy.spmma_compressed(comp, to_dev(b_bits, 0, cuda))
+    assert np.array_equal(d.float().cpu().numpy().astype(np.float64), want)
+
+
+def test_spmma_linearity_full_size(spfy, cuda):
+    """BASELINE-size property check (ResNet-50 layer 196,512,4608,32 in the weights orientation):
+    the kernel is linear in B, and equals a dense matmul of the pruned weights."""
+    torch.manual_seed(0)
+    M, K, N = 512, 4608, 6272
+    w = (torch.rand(M, K, device=cuda) * 2 - 1).half()
+    wd = torch.empty_like(w)
+    comp = spfy.prune24(w, out_dense=wd)
+    b1 = torch.randint(-2, 3, (K, N), device=cuda).half()
+    b2 = torch.randint(-2, 3, (K, N), device=cuda).half()
+    d1 = spfy.spmma_compressed(comp, b1).float()
+    d2 = spfy.spmma_compressed(comp, b2).float()
+    d12 = spfy.spmma_compressed(comp, b1 + b2).float()
+    ref = wd.float() @ (b1 + b2).float()
+    scale = ref.abs().max()
+    assert float((d12 - ref).abs().max() / scale) < 2e-3
+    assert float((d1 + d2 - d12).abs().max() / scale) < 4e-3
+
+
+def test_spmma_reference_style_call(spfy, orc, cuda):
+    """the reference-shaped entry point: prune in place, compress, multiply into C; three timings"""
+    m, n, k = 128, 256, 512
+    a_bits = rand_bits(orc, 0, (m, k), seed=8)
+    b_bits = rand_bits(orc, 0, (k, n), seed=9)
+    a = to_dev(a_bits, 0, cuda).reshape(-1)
+    b = to_dev(b_bits, 0, cuda).reshape(-1)
+    c = torch.zeros(m * n, dtype=torch.float16, device=cuda)
+    times = spfy.spmma(a, b, c, m, n, k, 1)
+    assert len(times) == 3 and all(t >= 0 for t in times)
+    pr = orc.prune24_strip(0, a_bits, want_mask=False)
+    assert np.array_equal(bits_of(a).reshape(m, k), pr["dense"])  # A pruned in place (spmma.hxx:86)
+    want = orc.spmma_f64(0, pr["dense"], b_bits)
+    assert rel_err(c.view(m, n).float().cpu().numpy().astype(np.float64), want) <= REL_TOL
+
+
+def test_spmma_rejects_bad_arguments(spfy, cuda):
+    a = torch.zeros(128, 128, dtype=torch.float16, device=cuda)
+    comp = spfy.prune24(a)
+    b = torch.zeros(128, 12, dtype=torch.float16, device=cuda)  # n = 12 is not a multiple of 8
+    with pytest.raises(spfy.SpfyError) as e:
+        spfy.spmma_compressed(comp, b)
+    assert e.value.code == spfy.capi.E_UNSUPPORTED
+
+
+# ------------------------------------------------------------------ unstructured path
+@pytest.mark.parametrize("rows,cols", [(64, 147), (128, 1152), (1, 1), (300, 37), (256, 2304)])
+@pytest.mark.parametrize("sparsity", [0.5, 0.9, 0.95])
+@pytest.mark.parametrize("tdt,code", [(torch.float32, 2), (torch.float16, 0)])
+def test_threshold_to_coo_bit_exact(spfy, orc, cuda, rows, cols, sparsity, tdt, code):
+    rng = np.random.default_rng(rows * 13 + cols)
+    w = rng.uniform(-1, 1, (rows, cols)).astype(np.float32)
+    if code == 0:
+        wb = orc.from_f32(0, w)
+        w = orc.to_f32(0, wb)
+        a = to_dev(wb, 0, cuda)
+        host = wb
+    else:
+        a = torch.from_numpy(w).to(cuda)
+        host = w
+    thr = float(np.quantile(np.abs(w), sparsity))
+    ri, ci, va, rp = orc.threshold_to_coo(code, host, thr)
+    gri, gci, gva, nnz, grp = spfy.threshold_to_coo(a, thr, want_csr=True)
+    assert nnz == ri.size
+    assert np.array_equal(gri.cpu().numpy(), ri) and np.array_equal(gci.cpu().numpy(), ci)
+    assert np.array_equal(gva.cpu().numpy(), va)
+    assert np.array_equal(grp.cpu().numpy(), rp)
+    assert np.array_equal(spfy.coo_to_csr(gri, rows).cpu().numpy(), orc.coo_to_csr(ri, rows))
+
+
+@pytest.mark.parametrize("m,k,n,nb,sparsity", [(64, 147, 96, 2, 0.5), (128, 576, 200, 3, 0.9), (256, 1152, 49, 4, 0.95),
+                                              (33, 70, 17, 1, 0.5), (512, 512, 64, 2, 0.9)])
+def test_batched_coo_spmm_matches_oracle(spfy, orc, cuda, m, k, n, nb, sparsity):
+    rng = np.random.default_rng(m + k + n)
+    w = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    thr = float(np.quantile(np.abs(w), sparsity))
+    ri, ci, va, _ = orc.threshold_to_coo(2, w, thr)
+    B = rng.uniform(-1, 1, (nb, n, k)).astype(np.float32)
+    C0 = rng.uniform(-1, 1, (nb, n, m)).astype(np.float32)
+    for alpha, beta in [(1.0, 0.0), (0.75, 0.5)]:
+        want = orc.spmm_coo_batched_f64(m, k, n, nb, ri, ci, va, B, C0, alpha, beta)
+        dC = torch.from_numpy(C0.copy()).to(cuda)
+        ms = spfy.batched.strided_coo(m, k, ri.size, k, n, nb, torch.from_numpy(ri).to(cuda),
+                                      torch.from_numpy(ci).to(cuda), torch.from_numpy(va).to(cuda),
+                                      torch.from_numpy(B).to(cuda), dC, alpha=alpha, beta=beta)
+        assert ms >= 0
+        assert np.allclose(dC.cpu().numpy(), want, rtol=2e-4, atol=2e-4)
+
+
+def test_batched_coo_spmm_empty_rows_and_unsorted_columns(spfy, orc, cuda):
+    m, k, n, nb = 40, 64, 24, 2
+    ri = np.array([0, 0, 0, 5, 5, 39], dtype=np.int32)
+    ci = np.array([63, 1, 30, 7, 7, 0], dtype=np.int32)  # unsorted within a row + a duplicate entry
+    va = np.array([1.0, -2.0, 0.5, 3.0, 1.0, -1.0], dtype=np.float32)
+    rng = np.random.default_rng(0)
+    B = rng.uniform(-1, 1, (nb, n, k)).astype(np.float32)
+    want = orc.spmm_coo_batched_f64(m, k, n, nb, ri, ci, va, B)
+    dC = torch.full((nb, n, m), 9.0, dtype=torch.float32, device=cuda)
+    spfy.batched.strided_coo(m, k, ri.size, k, n, nb, torch.from_numpy(ri).to(cuda), torch.from_numpy(ci).to(cuda),
+                             torch.from_numpy(va).to(cuda), torch.from_numpy(B).to(cuda), dC)
+    assert np.allclose(dC.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("tdt", [torch.float32, torch.float16])
+def test_blocked_ell_spmm_matches_oracle(spfy, orc, cuda, tdt):
+    """the reference driver's construction (examples/spmm.cu:45-84): block 2, ell_cols = k/2,
+    values 1.., sorted unique block-column ids per block row."""
+    m, n, k, nb, block = 64, 48, 128, 3, 2
+    ell_cols = k // 2
+    bcols = ell_cols // block
+    rng = np.random.default_rng(4)
+    B = (rng.integers(-3, 4, (n, k))).astype(np.float32)
+    cis, vas, cs, wants = [], [], [], []
+    for b in range(nb):
+        ci = np.stack([np.sort(rng.choice(k // block, bcols, replace=False)) for _ in range(m // block)]).astype(np.int64)
+        va = ((np.arange(m * ell_cols) % 7) - 3).astype(np.float32).reshape(m, ell_cols)
+        wants.append(orc.spmm_bell_f64(m, k, n, block, ell_cols, ci, va, B))
+        cis.append(torch.from_numpy(ci).to(cuda))
+        vas.append(torch.from_numpy(va).to(cuda).to(tdt))
+        cs.append(torch.zeros(n, m, dtype=tdt, device=cuda))
+    ms = spfy.batched.spmm(cis, vas, torch.from_numpy(B).to(cuda).to(tdt), cs, m, n, k, block, ell_cols)
+    assert ms >= 0
+    for c, want in zip(cs, wants):
+        assert np.array_equal(c.float().cpu().numpy().astype(np.float64), want)
+
+
+def test_launch_counter_moves(spfy, cuda):
+    before = spfy.launch_count()
+    a = torch.zeros(128, 128, dtype=torch.float16, device=cuda)
+    spfy.prune24(a)
+    assert spfy.launch_count() == before + 1
