@@ -1,0 +1,87 @@
+// detail/cabi.hxx -- glue between the header-only `sparsifyme` templates and the C ABI of
+// libsparsifyme_b200.so (include/spfy_b200.h).  Nothing here touches cuSPARSE / cusparseLt:
+// `cusparseOperation_t` is only a parameter TYPE of the reference signatures
+// (reference: include/sparsify.me/spmma.hxx:30-31, spmm.hxx:38-39); when <cusparse.h> is not
+// on the include path a value-compatible enum is declared instead.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+
+#include "../../spfy_b200.h"
+
+#if defined(__has_include)
+#if __has_include(<cusparse.h>)
+#include <cusparse.h>  // types only; no cuSPARSE symbol is referenced
+#define SPARSIFYME_HAVE_CUSPARSE_TYPES 1
+#endif
+#endif
+#ifndef SPARSIFYME_HAVE_CUSPARSE_TYPES
+typedef enum {
+  CUSPARSE_OPERATION_NON_TRANSPOSE = 0,
+  CUSPARSE_OPERATION_TRANSPOSE = 1,
+  CUSPARSE_OPERATION_CONJUGATE_TRANSPOSE = 2
+} cusparseOperation_t;
+#endif
+
+namespace sparsifyme {
+namespace detail {
+
+template <typename T> struct dtype_of { static constexpr int value = -1; };
+template <> struct dtype_of<__half> { static constexpr int value = SPFY_F16; };
+template <> struct dtype_of<__nv_bfloat16> { static constexpr int value = SPFY_BF16; };
+template <> struct dtype_of<float> { static constexpr int value = SPFY_F32; };
+template <> struct dtype_of<double> { static constexpr int value = SPFY_F64; };
+
+// The reference never reports errors: it prints and carries on.  We do the
+// same by default; define SPARSIFYME_STRICT to get exceptions instead.
+inline bool ok(int status, const char* where) {
+  if (status == SPFY_OK) return true;
+  std::string msg = std::string(where) + ": " + spfy_last_error_string();
+#ifdef SPARSIFYME_STRICT
+  throw std::runtime_error(msg);
+#else
+  std::cerr << "sparsify.me: " << msg << std::endl;
+  return false;
+#endif
+}
+inline bool cuda_ok(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) return true;
+  std::string msg = std::string(where) + ": " + cudaGetErrorString(e);
+#ifdef SPARSIFYME_STRICT
+  throw std::runtime_error(msg);
+#else
+  std::cerr << "sparsify.me: " << msg << std::endl;
+  return false;
+#endif
+}
+
+inline int op_code(cusparseOperation_t op) {
+  return op == CUSPARSE_OPERATION_NON_TRANSPOSE ? SPFY_OP_N : SPFY_OP_T;
+}
+
+// stream-ordered scratch that frees itself (temporaries live inside each call, like the
+// reference's: spmma.hxx:101,115-116)
+struct scratch {
+  void* ptr = nullptr;
+  cudaStream_t stream;
+  scratch(std::size_t bytes, cudaStream_t s) : stream(s) {
+    if (bytes) cuda_ok(cudaMallocAsync(&ptr, bytes, s), "cudaMallocAsync");
+  }
+  ~scratch() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+  scratch(const scratch&) = delete;
+  scratch& operator=(const scratch&) = delete;
+  template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+}  // namespace detail
+}  // namespace sparsifyme

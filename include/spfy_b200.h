@@ -72,6 +72,11 @@ SPFY_API const char* spfy_last_error_string(void);
 /* number of kernels this library launched in this process (bench: gpu_launches) */
 SPFY_API uint64_t spfy_launch_count(void);
 
+/* Element-wise dtype conversion between F32 and F16/BF16 (round to nearest even), used by
+ * the header templates when a driver instantiates spmma<float> (examples/spmma.cu:24). */
+SPFY_API int spfy_convert(int src_dtype, int dst_dtype, const void* src, void* dst, size_t count,
+                          spfy_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * A1  sparsifyme::sparsify<BLK_M,BLK_N>          include/sparsify.me/sparsify.hxx:24-82
  * Exact positional semantics of the reference: mask <- 1 (:71); then for each

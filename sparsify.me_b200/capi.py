@@ -40,6 +40,7 @@ SIGNATURES = {
     "spfy_version": (c_int, []),
     "spfy_last_error_string": (c_char_p, []),
     "spfy_launch_count": (c_uint64, []),
+    "spfy_convert": (c_int, [c_int, c_int, _P, _P, _SZ, _P]),
     "spfy_prune_blocks_ref": (c_int, [c_int, _P, _P, _SZ, _SZ, _SZ, _SZ, c_float, _P]),
     "spfy_compressed_bytes": (c_int, [c_int, _SZ, _SZ, c_int, POINTER(_SZ), POINTER(_SZ)]),
     "spfy_prune24": (c_int, [c_int, c_int, c_int, _P, _SZ, _P, _SZ, _P, _P, _P, _SZ, _SZ, _P]),

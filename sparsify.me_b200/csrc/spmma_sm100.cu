@@ -27,6 +27,8 @@
 // `tcgen05.cp.128x128b` source image of the kind::f16 sparse-metadata TMEM layout.
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 
 namespace spfy {
@@ -69,6 +71,7 @@ struct SpmmaParams {
   float alpha, beta;
   uint32_t idesc;
   uint64_t hint_b;
+  uint32_t dbg;  // development switches (SPFY_SPMMA_DEBUG), 0 in production
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -288,7 +291,7 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         const uint32_t m_blk = t % P.m_tiles, n_blk = t / P.m_tiles;
         const uint32_t rows_left = P.m - m_blk * BM;
         const uint32_t rows_valid = rows_left >= BM ? BM : ((rows_left + 15u) & ~15u);
-        const uint32_t tx = rows_valid * 128u + rows_valid * 16u + B_STAGE_BYTES;
+        const uint32_t tx = rows_valid * 128u + rows_valid * 16u + ((P.dbg & 4) ? 0u : B_STAGE_BYTES);
         for (uint32_t kt = 0; kt < P.k_tiles; ++kt) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1);
           const uint32_t full = bar_full + stage * 8;
@@ -299,7 +302,8 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           bulk_load_1d(smem_base + SMEM_E + stage * E_TILE_BYTES, P.a_meta + tile * E_TILE_BYTES,
                        rows_valid * 16u, full, HINT_EVICT_LAST);
           const uint32_t sb = smem_base + SMEM_B + stage * B_STAGE_BYTES;
-          if (!OPB_T) {
+          if (P.dbg & 4) {
+          } else if (!OPB_T) {
             // B is k x n row-major: boxes of [BK rows of k][64 columns of n] -> MN-major SW128
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
@@ -336,7 +340,7 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           const uint32_t sb = smem_base + SMEM_B + stage * B_STAGE_BYTES;
 #pragma unroll
           for (uint32_t j = 0; j < 4; ++j) {
-            if (j < nk) {
+            if (j < nk && !(P.dbg & 8)) {
               // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
               const uint64_t da = make_smem_desc(sa + j * 32, 16, 1024, LAYOUT_SW128);
               uint64_t db;
@@ -370,7 +374,7 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         uint32_t acc[64];
-        if (warp_has_rows) {
+        if (warp_has_rows && !(P.dbg & 2)) {
           const uint32_t taddr = tmem_base + as * BN + c * 64 + ((ew * 32) << 16);
           tmem_ld_x32(taddr, acc);
           tmem_ld_x32(taddr + 32, acc + 32);
@@ -384,7 +388,7 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         if (ethread == 0) bulk_wait_read<C_BUFS - 1>();  // the buffer we are about to fill is free
         epi_bar_sync();
         const uint32_t sc = smem_base + SMEM_C + cbuf * C_BUF_BYTES;
-        if (warp_has_rows) {
+        if (warp_has_rows && !(P.dbg & 2)) {
           const uint32_t grow = m0 + row;
           const uint32_t gcol0 = n0 + c * 64;
           const bool use_c = P.beta != 0.f && grow < P.m;
@@ -410,7 +414,7 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         }
         fence_proxy_async_smem();
         epi_bar_sync();
-        if (ethread == 0) {
+        if (ethread == 0 && !(P.dbg & 3)) {
           tma_store_2d(&tmap_d, sc, (int)(n0 + c * 64), (int)m0);
           bulk_commit();
         }
@@ -559,6 +563,10 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
   // B is streamed once when a single row of tiles covers M; otherwise the other
   // m-tiles of the same columns will want it from L2 again.
   P.hint_b = P.m_tiles == 1 ? HINT_EVICT_FIRST : HINT_EVICT_NORMAL;
+  {
+    const char* e = getenv("SPFY_SPMMA_DEBUG");
+    P.dbg = e ? (uint32_t)atoi(e) : 0u;
+  }
 
   const size_t tiles = (size_t)P.m_tiles * P.n_tiles;
   const int grid = (int)(tiles < (size_t)di.sm_count ? tiles : (size_t)di.sm_count);

@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Per-shape spmma sweep over a datasets/*.csv table (unique shapes), cold operands.
+
+For every unique (M, K, N) of the table: median-of-R CUDA-event time of one spfy_spmma launch with
+the L2 flushed before each launch, algorithmic GB/s and dense-equivalent TFLOP/s, and the fraction
+of the per-shape roofline min(HBM, sparse tensor).  Writes a CSV line per shape to stdout.
+
+    python tools/layer_sweep.py [--csv resnet50.csv] [--batch 32] [--dtype fp16] [--reps 7]
+"""
+import argparse
+import collections
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--csv", default="resnet50.csv")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--dtype", default="fp16")
+    ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--warm", action="store_true", help="no L2 flush between launches")
+    ap.add_argument("--tag", default="")
+    args = ap.parse_args()
+    import torch
+    spfy = ge.load_package()
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    tdt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(p)) if os.path.exists(p) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    hbm, tc = peaks["hbm_gbs"], 2 * peaks["bf16_tflops"]
+    cnt = collections.Counter(spfy.shapes.to_gemm(s, "weights", args.batch) for s in spfy.shapes.read_shapes(args.csv))
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    print("tag,M,K,N,count,us,GBs,frac_hbm,TFLOPs,frac_tc,roofline_us,frac_roofline")
+    tot_t = tot_r = 0.0
+    for g, c in sorted(cnt.items(), key=lambda kv: (-kv[0].N, kv[0].M, kv[0].K)):
+        w = (torch.rand(g.M, g.K, device=dev) * 2 - 1).to(tdt)
+        b = (torch.rand(g.K, g.N, device=dev) * 2 - 1).to(tdt)
+        d = torch.empty(g.M, g.N, device=dev, dtype=tdt)
+        comp = spfy.prune24(w)
+        for _ in range(2):
+            spfy.spmma_compressed(comp, b, out=d)
+        ts = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(args.reps):
+            if not args.warm:
+                flush.zero_()
+            e0.record()
+            spfy.spmma_compressed(comp, b, out=d)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = statistics.median(ts)
+        by, fl = spfy.shapes.spmma_bytes(g), spfy.shapes.spmma_flops(g)
+        roof = max(by / hbm / 1e3, fl / tc / 1e6)
+        tot_t += us * c
+        tot_r += roof * c
+        print(f"{args.tag},{g.M},{g.K},{g.N},{c},{us:.1f},{by/us/1e3:.0f},{by/us/1e3/hbm:.3f},{fl/us/1e6:.1f},"
+              f"{fl/us/1e6/tc:.3f},{roof:.1f},{roof/us:.3f}")
+        del w, b, d, comp
+    print(f"# {args.tag} total {tot_t:.0f} us vs roofline {tot_r:.0f} us -> {tot_r/tot_t:.3f}")
+
+
+if __name__ == "__main__":
+    main()
