@@ -90,19 +90,25 @@ struct Prune24Params {
   uint32_t k_tiles;        // SM100: 128-column tiles per row
   int layout;
   int vec_in, vec_out, vec_cv;  // 16-byte fast paths allowed
+  int tile_order;               // iterate in SM100 tile storage order
+  int fits32;                   // dom_rows * units_per_row < 2^32
 };
 
-// keep-mask (2 bits set) of the two largest keys, tie -> lower index
-__device__ __forceinline__ unsigned select2of4(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
-  // c_ij = 1 iff j beats i (j > i  =>  needs strictly larger key)
-  const int c01 = k1 > k0, c02 = k2 > k0, c03 = k3 > k0;
-  const int c12 = k2 > k1, c13 = k3 > k1, c23 = k3 > k2;
-  const int b0 = c01 + c02 + c03;
-  const int b1 = (1 - c01) + c12 + c13;
-  const int b2 = (1 - c02) + (1 - c12) + c23;
-  const int b3 = (1 - c03) + (1 - c13) + (1 - c23);
-  return (unsigned)(b0 < 2) | (unsigned)(b1 < 2) << 1 | (unsigned)(b2 < 2) << 2 |
-         (unsigned)(b3 < 2) << 3;
+// Indices i0 < i1 of the two largest magnitudes among the four 16-bit values packed in
+// (lo, hi); tie -> lower index.  The 15 magnitude bits are widened to unique 17-bit keys
+// (key << 2 | 3 - index: among equal magnitudes the lower index is the larger key), then a
+// 4-input max/min network yields the largest and second largest key.
+__device__ __forceinline__ void top2of4(uint32_t lo, uint32_t hi, uint32_t& i0, uint32_t& i1) {
+  const uint32_t a = ((lo << 2) & 0x1fffcu) | 3u;
+  const uint32_t b = ((lo >> 14) & 0x1fffcu) | 2u;
+  const uint32_t c = ((hi << 2) & 0x1fffcu) | 1u;
+  const uint32_t d = (hi >> 14) & 0x1fffcu;
+  const uint32_t m01 = max(a, b), n01 = min(a, b), m23 = max(c, d), n23 = min(c, d);
+  const uint32_t top = max(m01, m23);
+  const uint32_t second = max(min(m01, m23), m01 > m23 ? n01 : n23);
+  const uint32_t ia = 3u - (top & 3u), ib = 3u - (second & 3u);
+  i0 = min(ia, ib);
+  i1 = max(ia, ib);
 }
 
 // streaming 128-bit load.  Not `.nc`: out_dense may alias the input (in-place prune).
@@ -117,8 +123,20 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 // one 16-column unit of one row: load, select, write every requested output
 __device__ __forceinline__ void prune24_unit(const Prune24Params& P, size_t t) {
   {
-    const uint32_t row = (uint32_t)(t / P.units_per_row);
-    const uint32_t unit = (uint32_t)(t - (size_t)row * P.units_per_row);
+    uint32_t row, unit;
+    if (P.tile_order) {
+      // SM100 outputs: walk the (128-row x 128-column) tiles in storage order, 8 units per row
+      const uint32_t tile = (uint32_t)(t >> 10);
+      const uint32_t mt = tile / P.k_tiles;
+      row = mt * 128u + ((uint32_t)(t >> 3) & 127u);
+      unit = (tile - mt * P.k_tiles) * 8u + ((uint32_t)t & 7u);
+    } else if (P.fits32) {
+      row = (uint32_t)t / P.units_per_row;
+      unit = (uint32_t)t - row * P.units_per_row;
+    } else {
+      row = (uint32_t)(t / P.units_per_row);
+      unit = (uint32_t)(t - (size_t)row * P.units_per_row);
+    }
     const uint32_t c0 = unit * 16;
 
     // ---- load 16 storage words (zeros outside the matrix) ----
@@ -142,19 +160,21 @@ __device__ __forceinline__ void prune24_unit(const Prune24Params& P, size_t t) {
     uint32_t cv[4];      // compressed: 2 values per group
     unsigned nibs = 0;   // 4 nibbles
     unsigned keep16 = 0; // keep bit per element
+    const bool want_dense = P.out_dense != nullptr || P.mask != nullptr;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const uint32_t lo = w[2 * g], hi = w[2 * g + 1];
-      const uint32_t v0 = lo & 0xffffu, v1 = lo >> 16, v2 = hi & 0xffffu, v3 = hi >> 16;
-      const unsigned keep = select2of4(v0 & 0x7fffu, v1 & 0x7fffu, v2 & 0x7fffu, v3 & 0x7fffu);
-      const unsigned i0 = __ffs(keep) - 1, i1 = 31 - __clz(keep);
+      uint32_t i0, i1;
+      top2of4(lo, hi, i0, i1);
       nibs |= (i0 | i1 << 2) << (4 * g);
-      keep16 |= keep << (4 * g);
-      const uint32_t a = i0 == 0 ? v0 : (i0 == 1 ? v1 : v2);
-      const uint32_t b = i1 == 1 ? v1 : (i1 == 2 ? v2 : v3);
-      cv[g] = a | b << 16;
-      d[2 * g] = (keep & 1 ? v0 : 0u) | (keep & 2 ? v1 : 0u) << 16;
-      d[2 * g + 1] = (keep & 4 ? v2 : 0u) | (keep & 8 ? v3 : 0u) << 16;
+      // halfword i of {lo, hi} is bytes (2i, 2i+1): one PRMT gathers the kept pair
+      cv[g] = __byte_perm(lo, hi, (i0 + (i1 << 8)) * 0x22u + 0x1010u);
+      if (want_dense) {
+        const unsigned keep = (1u << i0) | (1u << i1);
+        keep16 |= keep << (4 * g);
+        d[2 * g] = lo & (((keep & 1u) * 0xffffu) | ((keep >> 1 & 1u) * 0xffff0000u));
+        d[2 * g + 1] = hi & (((keep >> 2 & 1u) * 0xffffu) | ((keep >> 3 & 1u) * 0xffff0000u));
+      }
     }
 
     // ---- pruned dense (may alias the input: same thread, same addresses) ----
@@ -355,6 +375,10 @@ int fill_prune24(Prune24Params* out, int layout, const uint16_t* src, size_t ld_
   const bool sm100_out = layout == SPFY_LAYOUT_SM100 && (comp_vals || meta);
   P.dom_rows = sm100_out ? (uint32_t)round_up(rows, 128) : (uint32_t)rows;
   P.units_per_row = sm100_out ? P.k_tiles * 8 : (uint32_t)ceil_div(cols, 16);
+  P.tile_order = sm100_out ? 1 : 0;
+  P.fits32 = (size_t)P.dom_rows * P.units_per_row < (1ull << 32);
+  if (sm100_out && ceil_div(rows, 128) * ceil_div(cols, 128) >= (1ull << 22))
+    return fail(SPFY_E_UNSUPPORTED, "prune24: more than 2^22 SM100 tiles");
   P.vec_in = ((uintptr_t)src % 16 == 0) && (ld_src % 8 == 0);
   P.vec_out = out_dense && ((uintptr_t)out_dense % 16 == 0) && (ld_out % 8 == 0);
   P.vec_cv = comp_vals && ((uintptr_t)comp_vals % 16 == 0) && (P.G % 4 == 0);

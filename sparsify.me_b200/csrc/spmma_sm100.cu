@@ -386,9 +386,9 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           if (lane == 0) mbar_arrive(bar_acc_empty + as * 8);
         }
         if (ethread == 0) bulk_wait_read<C_BUFS - 1>();  // the buffer we are about to fill is free
-        epi_bar_sync();
+        if (!(P.dbg & 32)) epi_bar_sync();
         const uint32_t sc = smem_base + SMEM_C + cbuf * C_BUF_BYTES;
-        if (warp_has_rows && !(P.dbg & 2)) {
+        if (warp_has_rows && !(P.dbg & (2 | 16))) {
           const uint32_t grow = m0 + row;
           const uint32_t gcol0 = n0 + c * 64;
           const bool use_c = P.beta != 0.f && grow < P.m;
@@ -413,7 +413,7 @@ spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           }
         }
         fence_proxy_async_smem();
-        epi_bar_sync();
+        if (!(P.dbg & 32)) epi_bar_sync();
         if (ethread == 0 && !(P.dbg & 3)) {
           tma_store_2d(&tmap_d, sc, (int)(n0 + c * 64), (int)m0);
           bulk_commit();

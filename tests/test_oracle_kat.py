@@ -1,0 +1,159 @@
+"""Known-answer tests of the CPU oracle itself (no GPU): conversions, top-2-of-4 selection with the
+documented tie-break, metadata nibbles, SM100 packing, threshold/COO/CSR, fp64 GEMM, blocked-ELL."""
+import numpy as np
+import pytest
+
+
+def h(orc, *vals):
+    return orc.from_f32(orc.F16, np.array(vals, dtype=np.float32))
+
+
+def test_float_conversions_round_to_nearest_even(orc):
+    x = np.array([0.0, -0.0, 1.0, 65504.0, 65520.0, 1e-8, 5.9604645e-08, 2.0 ** -24 * 1.5, np.inf, -np.inf, 0.1,
+                  1.0009765625, 1.00048828125, 1.00146484375], dtype=np.float32)
+    assert np.array_equal(orc.from_f32(orc.F16, x), x.astype(np.float16).view(np.uint16))
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal(20000) * 10 ** rng.uniform(-9, 5, 20000)).astype(np.float32)
+    assert np.array_equal(orc.from_f32(orc.F16, y), y.astype(np.float16).view(np.uint16))
+    assert np.array_equal(orc.to_f32(orc.F16, np.arange(65536, dtype=np.uint16))[:0x7c00],
+                          np.arange(0x7c00, dtype=np.uint16).view(np.float16).astype(np.float32))
+    # bf16: RN-even on the upper 16 bits
+    b = orc.from_f32(orc.BF16, np.array([1.0, 1.00390625, 1.01171875, -2.5, 3.0e38], dtype=np.float32))
+    assert list(b) == [0x3F80, 0x3F80, 0x3F82, 0xC020, 0x7F62]
+    assert np.array_equal(orc.to_f32(orc.BF16, b).view(np.uint32), b.astype(np.uint32) << 16)
+
+
+@pytest.mark.parametrize("vals,keep,nib", [
+    ((1, -2, 3, 0.5), (1, 2), 0x9),       # plain magnitudes
+    ((1, 1, 1, 1), (0, 1), 0x4),          # all tied -> the two lowest indices
+    ((0, 0, 0, 0), (0, 1), 0x4),          # zeros still keep exactly two slots
+    ((2, 1, 2, 1), (0, 2), 0x8),          # tie for first place
+    ((1, 2, 1, 2), (1, 3), 0xD),
+    ((1, 2, 2, 2), (1, 2), 0x9),          # three-way tie for the top: lower indices win
+    ((3, 1, 1, 1), (0, 1), 0x4),          # tie for second place -> lowest index
+    ((-0.0, 0.0, -1, 0), (0, 2), 0x8),    # -0 == +0, then index order
+    ((1, 1, 2, 3), (2, 3), 0xE),
+])
+def test_select_top2_of_4(orc, vals, keep, nib):
+    r = orc.prune24_strip(orc.F16, h(orc, *vals).reshape(1, 4))
+    assert tuple(np.nonzero(r["mask"][0])[0]) == keep
+    assert r["meta"][0, 0] == nib
+    src = h(orc, *vals)
+    assert list(r["vals"][0]) == [src[keep[0]], src[keep[1]]]
+    want_dense = np.where(r["mask"][0] == 1, src, 0)
+    assert np.array_equal(r["dense"][0], want_dense)
+
+
+def test_nan_and_inf_ordering(orc):
+    bits = np.array([[0x7E00, 0x7C00, 0x7BFF, 0x3C00]], dtype=np.uint16)  # NaN > Inf > max finite > 1
+    r = orc.prune24_strip(orc.F16, bits)
+    assert list(r["mask"][0]) == [1, 1, 0, 0]
+    bits = np.array([[0x3C00, 0xFC00, 0x0001, 0xFE00]], dtype=np.uint16)  # 1, -Inf, denormal, -NaN
+    assert list(orc.prune24_strip(orc.F16, bits)["mask"][0]) == [0, 1, 0, 1]
+
+
+def test_ragged_k_is_zero_padded(orc):
+    """k = 147 (datasets/resnet18.csv:2): 36 full groups + one group of 3 real + 1 virtual zero."""
+    rng = np.random.default_rng(1)
+    a = orc.from_f32(orc.F16, rng.uniform(-1, 1, (5, 147)).astype(np.float32))
+    r = orc.prune24_strip(orc.F16, a)
+    assert r["vals"].shape == (5, 74) and r["meta"].shape == (5, 19)
+    padded = np.zeros((5, 148), dtype=np.uint16)
+    padded[:, :147] = a
+    rp = orc.prune24_strip(orc.F16, padded)
+    assert np.array_equal(r["vals"], rp["vals"]) and np.array_equal(r["meta"], rp["meta"])
+    assert np.array_equal(r["dense"], rp["dense"][:, :147])
+    assert (r["meta"][:, 18] >> 4 == 0).all()  # odd trailing group: partner nibble stays 0
+
+
+def test_metadata_roundtrip_reconstructs_dense(orc):
+    rng = np.random.default_rng(2)
+    a = orc.from_f32(orc.BF16, rng.uniform(-1, 1, (33, 64)).astype(np.float32))
+    r = orc.prune24_strip(orc.BF16, a)
+    rebuilt = np.zeros_like(a)
+    for g in range(16):
+        nib = (r["meta"][:, g // 2] >> ((g & 1) * 4)) & 0xF
+        i0, i1 = nib & 3, nib >> 2
+        assert (i0 < i1).all()
+        rows = np.arange(33)
+        rebuilt[rows, g * 4 + i0] = r["vals"][:, 2 * g]
+        rebuilt[rows, g * 4 + i1] = r["vals"][:, 2 * g + 1]
+    assert np.array_equal(rebuilt, r["dense"])
+
+
+def test_sm100_packing_is_a_permutation(orc):
+    """every (value, nibble) of the CANONICAL layout appears exactly once at the documented offset"""
+    rows, cols = 130, 260
+    rng = np.random.default_rng(3)
+    a = orc.from_f32(orc.F16, rng.uniform(-1, 1, (rows, cols)).astype(np.float32))
+    r = orc.prune24_strip(orc.F16, a, want_mask=False)
+    ov, om = orc.pack_sm100(r["vals"], r["meta"], rows, cols)
+    kt_n = (cols + 127) // 128
+    assert ov.size == 2 * kt_n * 16384 and om.size == 2 * kt_n * 2048
+    v16 = ov.view(np.uint16)
+    for (row, g) in [(0, 0), (5, 3), (127, 31), (128, 32), (129, 64), (77, 40)]:
+        mt, r_in, kt, gq = row // 128, row % 128, g // 32, g % 32
+        p = gq * 2
+        off = (mt * kt_n + kt) * 16384 + r_in * 128 + (((p >> 3) ^ (r_in & 7)) << 4) + (p & 7) * 2
+        assert v16[off // 2] == r["vals"][row, 2 * g] and v16[off // 2 + 1] == r["vals"][row, 2 * g + 1]
+        q, j = gq // 4, gq % 4
+        eoff = (mt * kt_n + kt) * 2048 + (r_in >> 4) * 256 + (q & 1) * 128 + (r_in & 7) * 16 + (q >> 1) * 4 + ((r_in >> 3) & 1) * 2
+        word = int(om[eoff]) | int(om[eoff + 1]) << 8
+        nib = (r["meta"][row, g // 2] >> ((g & 1) * 4)) & 0xF
+        assert (word >> (4 * j)) & 0xF == nib
+    # padding rows carry value 0 and the neutral nibble 0x4
+    pad_word_off = (1 * kt_n + 0) * 2048 + (100 >> 4) * 256 + (100 & 7) * 16 + ((100 >> 3) & 1) * 2
+    assert om[pad_word_off] == 0x44 and om[pad_word_off + 1] == 0x44
+
+
+def test_positional_reference_semantics(orc):
+    """sparsify.hxx:53-65 for <2,2>, 0.5: offsets {0,2} of every run of 4; tail untouched"""
+    m, n = 5, 3  # tile_m*tile_n = 2 blocks -> 8 of the 15 elements are visited
+    w = np.arange(1, 16, dtype=np.float32)
+    got, mask = orc.prune_blocks_ref(w, m, n)
+    assert list(got) == [0, 2, 0, 4, 0, 6, 0, 8, 9, 10, 11, 12, 13, 14, 15]
+    assert list(mask) == [0, 1, 0, 1, 0, 1, 0, 1, 1, 1, 1, 1, 1, 1, 1]
+    got, mask = orc.prune_blocks_ref(np.ones(16, dtype=np.float64), 4, 4, 2, 2, 0.75)  # nz = 3: offsets 0,2,1
+    assert list(mask) == [0, 0, 0, 1] * 4
+    got, mask = orc.prune_blocks_ref(np.ones(8, dtype=np.float16), 2, 4, 2, 2, 0.1)  # nz = 0
+    assert mask.sum() == 8 and (got == 1).all()
+
+
+def test_threshold_coo_csr(orc):
+    a = np.array([[0.5, -0.9, 0.1], [0.0, 0.0, 0.0], [-0.95, 0.2, 0.91]], dtype=np.float32)
+    ri, ci, va, rp = orc.threshold_to_coo(orc.F32, a, 0.5)
+    assert list(ri) == [0, 2, 2] and list(ci) == [1, 0, 2] and list(rp) == [0, 1, 1, 3]
+    assert np.allclose(va, [-0.9, -0.95, 0.91])
+    assert list(orc.coo_to_csr(ri, 3)) == [0, 1, 1, 3]
+    ri, ci, va, rp = orc.threshold_to_coo(orc.F32, a, 2.0)
+    assert ri.size == 0 and list(rp) == [0, 0, 0, 0]
+
+
+def test_gemm_oracles_against_numpy(orc):
+    rng = np.random.default_rng(4)
+    m, k, n = 24, 40, 16
+    a = orc.from_f32(orc.F16, rng.uniform(-1, 1, (m, k)).astype(np.float32))
+    b = orc.from_f32(orc.F16, rng.uniform(-1, 1, (k, n)).astype(np.float32))
+    c = orc.from_f32(orc.F16, rng.uniform(-1, 1, (m, n)).astype(np.float32))
+    pr = orc.prune24_strip(orc.F16, a, want_mask=False)
+    A, B, C = (orc.to_f32(orc.F16, x).astype(np.float64) for x in (pr["dense"], b, c))
+    assert np.allclose(orc.spmma_f64(orc.F16, pr["dense"], b), A @ B, rtol=0, atol=1e-12)
+    assert np.allclose(orc.spmma_f64(orc.F16, pr["dense"], b, c_bits=c, alpha=0.5, beta=2.0), 0.5 * A @ B + 2 * C, atol=1e-12)
+    bt = np.ascontiguousarray(b.T)
+    assert np.allclose(orc.spmma_f64(orc.F16, pr["dense"], bt, op_b=1), A @ B, atol=1e-12)
+    # COO
+    w = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    ri, ci, va, _ = orc.threshold_to_coo(orc.F32, w, 0.6)
+    Bc = rng.uniform(-1, 1, (2, n, k)).astype(np.float32)
+    want = np.stack([(np.where(np.abs(w) > 0.6, w, 0).astype(np.float64) @ Bc[i].T.astype(np.float64)).T for i in range(2)])
+    assert np.allclose(orc.spmm_coo_batched_f64(m, k, n, 2, ri, ci, va, Bc), want, atol=1e-12)
+    # blocked ELL (block 2)
+    ell_cols, block = 8, 2
+    ci2 = np.stack([np.sort(rng.choice(k // block, ell_cols // block, replace=False)) for _ in range(m // block)]).astype(np.int64)
+    vals = rng.uniform(-1, 1, (m, ell_cols)).astype(np.float32)
+    dense = np.zeros((m, k))
+    for i in range(m):
+        for e in range(ell_cols):
+            dense[i, ci2[i // block, e // block] * block + e % block] += vals[i, e]
+    Bf = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    assert np.allclose(orc.spmm_bell_f64(m, k, n, block, ell_cols, ci2, vals, Bf), (dense @ Bf.T.astype(np.float64)).T, atol=1e-12)

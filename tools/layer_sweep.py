@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--warm", action="store_true", help="no L2 flush between launches")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--only", default="", help="M,K,N filter")
     args = ap.parse_args()
     import torch
     spfy = ge.load_package()
@@ -41,6 +42,8 @@ def main():
     print("tag,M,K,N,count,us,GBs,frac_hbm,TFLOPs,frac_tc,roofline_us,frac_roofline")
     tot_t = tot_r = 0.0
     for g, c in sorted(cnt.items(), key=lambda kv: (-kv[0].N, kv[0].M, kv[0].K)):
+        if args.only and args.only != f"{g.M},{g.K},{g.N}":
+            continue
         w = (torch.rand(g.M, g.K, device=dev) * 2 - 1).to(tdt)
         b = (torch.rand(g.K, g.N, device=dev) * 2 - 1).to(tdt)
         d = torch.empty(g.M, g.N, device=dev, dtype=tdt)
