@@ -51,9 +51,10 @@ enum { SPFY_PRUNE_STRIP_MAG = 0, SPFY_PRUNE_TILE_MAG = 1 };
  *                       byte g/2, low nibble for even g; nibble = i0 | i1<<2
  *   SM100     : what spfy_spmma consumes.  values and metadata are split into
  *               (128-row x 128-logical-k) tiles, tile (mt,kt) at index
- *               mt*k_tiles+kt; a value tile is the 128B-swizzled shared-memory
- *               image (16 KiB), a metadata tile the tcgen05 `128x128b` image
- *               (2 KiB).  See DESIGN.md "Data layout in HBM". */
+ *               mt*k_tiles+kt; a value tile (16 KiB) is two 8 KiB K-slices, each the
+ *               64B-swizzled K-major shared-memory image of 128 rows x 32 stored
+ *               values; a metadata tile (2 KiB) is the tcgen05 `128x128b` image.
+ *               See DESIGN.md "Data layout in HBM". */
 enum { SPFY_LAYOUT_CANONICAL = 0, SPFY_LAYOUT_SM100 = 1 };
 
 enum { SPFY_OP_N = 0, SPFY_OP_T = 1 }; /* == cusparseOperation_t values */
@@ -142,6 +143,32 @@ SPFY_API int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float 
                         const void* comp_vals, const void* meta, const void* B, size_t ldb,
                         float beta, const void* C, size_t ldc, void* D, size_t ldd,
                         void* workspace, size_t workspace_bytes, spfy_stream_t stream);
+
+/* Many independent problems (the per-layer GEMMs of a datasets/ *.csv table) as ONE plan:
+ * tensor maps and the tile schedule are built once (like cusparseLtMatmulPlanInit,
+ * spmma.hxx:79, which the reference also keeps outside its timers) and every run issues at
+ * most three persistent launches that walk all problems' tiles, so neither launch latency
+ * nor per-layer wave quantisation is paid per layer.  Problems must not alias each other's
+ * outputs.  plan_create allocates a small device table; plan_run never allocates or syncs. */
+typedef struct spfy_spmma_problem {
+  int opB;                 /* SPFY_OP_N / SPFY_OP_T */
+  size_t m, n, k;
+  const void* comp_vals;   /* SM100-layout compressed A (spfy_prune24) */
+  const void* meta;
+  const void* B;
+  size_t ldb;
+  const void* C;           /* may be null when beta == 0 */
+  size_t ldc;
+  void* D;
+  size_t ldd;
+  float alpha, beta;
+} spfy_spmma_problem;
+typedef struct spfy_spmma_plan_st* spfy_spmma_plan_t;
+SPFY_API int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t count,
+                                    spfy_spmma_plan_t* plan);
+SPFY_API int spfy_spmma_plan_run(spfy_spmma_plan_t plan, spfy_stream_t stream);
+SPFY_API int spfy_spmma_plan_launches(spfy_spmma_plan_t plan); /* kernel launches per run */
+SPFY_API int spfy_spmma_plan_destroy(spfy_spmma_plan_t plan);
 
 /* ------------------------------------------------------------------------
  * Unstructured path (north_star subsystem 3).  Threshold prune keeps x iff

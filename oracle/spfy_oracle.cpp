@@ -344,8 +344,9 @@ void orc_compress24(int dtype, const void* in, size_t ld_in, size_t rows, size_t
 // ------------------------------------------------------------------------
 // CANONICAL -> SM100 layout (the device format spfy_spmma consumes; OUR format,
 // documented in DESIGN.md).  m_tiles = ceil(rows/128), k_tiles = ceil(cols/128).
-//   values tile (mt,kt): 128 rows x 64 physical fp16; element (r,p) at byte
-//       r*128 + (((p>>3) ^ (r&7)) << 4) + (p&7)*2         [128B swizzle image]
+//   values tile (mt,kt): 128 rows x 64 physical fp16 as two 8 KiB K-slices of 32 halves;
+//       element (r,p) at byte (p>>5)*8192 + r*64 + ((((p&31)>>3) ^ ((r>>1)&3)) << 4) + (p&7)*2
+//       [each slice is the 64-byte-swizzled K-major shared-memory image]
 //   meta tile (mt,kt): 2048 bytes; the 16-bit word holding the 4 nibbles of
 //       logical columns [16*q, 16*q+16) of in-tile row r  (q = 0..7) sits at
 //       (r>>4)*256 + (q&1)*128 + (r&7)*16 + (q>>1)*4 + ((r>>3)&1)*2
@@ -377,8 +378,9 @@ void orc_pack_sm100(const void* comp_vals, const uint8_t* meta, size_t rows, siz
               v1 = cv[(row * G + g) * 2 + 1];
             }
             word |= (uint16_t)(nib << (4 * j));
-            size_t p = q * 8 + j * 2;  // physical column inside the tile
-            size_t off = r * 128 + ((((p >> 3) ^ (r & 7))) << 4) + (p & 7) * 2;
+            size_t p = q * 8 + j * 2;  // physical column inside the tile (0..63)
+            // two K-slices of 32 stored halves each; inside a slice the 64-byte swizzle image
+            size_t off = (p >> 5) * 8192 + r * 64 + (((((p & 31) >> 3) ^ ((r >> 1) & 3))) << 4) + (p & 7) * 2;
             std::memcpy(vt + off, &v0, 2);
             std::memcpy(vt + off + 2, &v1, 2);
           }

@@ -49,6 +49,10 @@ SIGNATURES = {
     "spfy_spmma_workspace_bytes": (c_int, [c_int, _SZ, _SZ, _SZ, POINTER(_SZ)]),
     "spfy_spmma": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, c_float, _P, _SZ,
                            _P, _SZ, _P, _SZ, _P]),
+    "spfy_spmma_plan_create": (c_int, [c_int, _P, _SZ, POINTER(c_void_p)]),
+    "spfy_spmma_plan_run": (c_int, [_P, _P]),
+    "spfy_spmma_plan_launches": (c_int, [_P]),
+    "spfy_spmma_plan_destroy": (c_int, [_P]),
     "spfy_threshold_workspace_bytes": (c_int, [_SZ, _SZ, POINTER(_SZ)]),
     "spfy_threshold_to_coo": (c_int, [c_int, _P, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, _P, _P,
                                       _P, _SZ, _P]),
@@ -62,7 +66,20 @@ SIGNATURES = {
                                        c_float, c_float, _P]),
 }
 
-_NO_STATUS = {"spfy_version", "spfy_last_error_string", "spfy_launch_count"}
+_NO_STATUS = {"spfy_version", "spfy_last_error_string", "spfy_launch_count", "spfy_spmma_plan_launches"}
+
+
+class SpmmaProblem(ctypes.Structure):
+    """struct spfy_spmma_problem"""
+    _fields_ = [("opB", c_int), ("m", c_size_t), ("n", c_size_t), ("k", c_size_t), ("comp_vals", c_void_p),
+                ("meta", c_void_p), ("B", c_void_p), ("ldb", c_size_t), ("C", c_void_p), ("ldc", c_size_t),
+                ("D", c_void_p), ("ldd", c_size_t), ("alpha", c_float), ("beta", c_float)]
+
+
+class Prune24Item(ctypes.Structure):
+    """struct spfy_prune24_item"""
+    _fields_ = [("in_", c_void_p), ("ld_in", c_size_t), ("out_dense", c_void_p), ("ld_out", c_size_t),
+                ("comp_vals", c_void_p), ("meta", c_void_p), ("rows", c_size_t), ("cols", c_size_t)]
 
 
 def last_error():

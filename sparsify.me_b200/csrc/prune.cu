@@ -210,7 +210,8 @@ __device__ __forceinline__ void prune24_unit(const Prune24Params& P, size_t t) {
       const uint32_t r = row & 127, q = (c0 & 127) >> 4;
       const size_t tile = (size_t)(row >> 7) * P.k_tiles + (c0 >> 7);
       if (P.comp_vals)
-        *reinterpret_cast<uint4*>(P.comp_vals + tile * 16384 + r * 128 + ((q ^ (r & 7)) << 4)) =
+        *reinterpret_cast<uint4*>(P.comp_vals + tile * 16384 + (q >> 2) * 8192 + r * 64 +
+                                  (((q & 3) ^ ((r >> 1) & 3)) << 4)) =
             make_uint4(cv[0], cv[1], cv[2], cv[3]);
       if (P.meta)
         *reinterpret_cast<uint16_t*>(P.meta + tile * 2048 + (r >> 4) * 256 + (q & 1) * 128 +

@@ -1,77 +1,97 @@
-// spmma_sm100.cu -- 2:4 structured-sparse GEMM on tcgen05.mma.sp (sm_100a)
+// spmma_sm100.cu -- 2:4 structured-sparse GEMM on tcgen05.mma.sp (sm_100a), v2
 //
 // Replaces cusparseLtMatmul (reference: include/sparsify.me/spmma.hxx:106-114):
 //     D[m x n] = alpha * A(2:4)[m x k] * op(B)[k x n] + beta * C[m x n]
-// all row-major like the reference's descriptors (spmma.hxx:56-64), fp16 or bf16
-// in, fp32 accumulate in TMEM, fp16/bf16 out.
+// all row-major like the reference's descriptors (spmma.hxx:56-64), fp16 or bf16 in, fp32
+// accumulation in TMEM, fp16/bf16 out.  Two entry points share one kernel:
+//     spfy_spmma            one problem (what the header template calls)
+//     spfy_spmma_plan_*     a list of independent problems (the per-layer GEMMs of a
+//                           datasets/*.csv table) executed by at most three persistent launches
 //
-// Shape of the kernel (one persistent CTA per SM, 256 threads, 1 CTA/SM):
-//   warp 0   producer   : cp.async.bulk of the pre-swizzled A-value tile (<=16 KiB)
-//                         and its metadata tile (<=2 KiB), TMA tensor loads of the
-//                         B tile, all landing on one mbarrier per stage
-//   warp 1   MMA issuer : tcgen05.cp (metadata smem -> TMEM), then up to four
-//                         tcgen05.mma.sp.kind::f16 (M128 x N128 x K32) per stage;
-//                         tcgen05.commit releases the stage / publishes the accumulator
-//   warp 2   TMEM allocator (512 columns: 2 x 128 accumulator + 2 x 4 metadata)
-//   warps 4-7 epilogue  : tcgen05.ld -> alpha/beta -> fp16/bf16 -> 128B-swizzled smem
-//                         -> TMA tensor store (clips the ragged M / N edges)
-// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the
-// main loop of tile i+1.  Every ResNet shape in datasets/*.csv is HBM-bound for this
-// operator, so the design goal is: read B exactly once from HBM, keep
-// many bytes in flight, never stall the stream on the epilogue.
+// Every ResNet shape is HBM-bound for this operator, and the chip-wide L2->SM throughput is only
+// ~1.9x the HBM bandwidth, so the kernel is built to move every operand byte
+// into an SM as few times as possible:
+//   * work unit = (problem, n-tile of 128 columns, group of G <= 2 m-tiles): one B slice in
+//     shared memory feeds the MMAs of both m-tiles of the group;
+//   * "resident" problems (whole compressed A <= 96 KiB): A values + metadata are loaded into
+//     shared memory once per CTA and problem, the ring then streams B only;
+//   * units are dealt round-robin to the persistent CTAs, so neighbouring CTAs stream
+//     neighbouring B columns at the same time (DRAM page locality, L2 hits for the other m-group).
 //
-// The compressed operand comes from spfy_prune24(layout = SPFY_LAYOUT_SM100): tile
-// (mt,kt) of A covers rows [128mt,128mt+128) x logical cols [128kt,128kt+128); its
-// value tile is the exact 128B-swizzled K-major shared-memory image (row r at r*128,
-// 16-byte chunk c stored at chunk c ^ (r & 7)), its metadata tile the exact
-// `tcgen05.cp.128x128b` source image of the kind::f16 sparse-metadata TMEM layout.
+// CTA = 320 threads, 1 CTA/SM:
+//   warp 0      producer : cp.async.bulk (A value slices / metadata tiles, pre-swizzled by
+//                          spfy_prune24) + TMA tensor loads (B), one mbarrier per ring stage
+//   warp 1      MMA      : one thread issues tcgen05.cp (metadata smem -> TMEM) and
+//                          tcgen05.mma.sp.cta_group::1.kind::f16 (M128 x N128 x K32);
+//                          tcgen05.commit frees ring stages / publishes accumulators
+//   warps 2-9   epilogue : each warp owns 32 rows x 64 columns of an accumulator:
+//                          tcgen05.ld -> alpha/beta -> fp16/bf16 -> its own swizzled 4 KiB staging
+//                          buffer -> its own TMA store.  No CTA-wide barrier in steady state.
+// TMEM: three 128-column accumulator slots used as a ring over (unit, m-tile) jobs, so the epilogue
+// of one job overlaps the MMAs of the next ones; metadata lives in 16 columns behind them.
+//
+// Operand format (spfy_prune24, layout SPFY_LAYOUT_SM100): tile (mt, kt) covers rows
+// [128mt, 128mt+128) x logical columns [128kt, 128kt+128).  Its 16 KiB value tile is two 8 KiB
+// K-slices (64 logical columns = 32 stored halves = 64 bytes per row), each the exact
+// 64B-swizzled K-major shared-memory image (row r at r*64, 16-byte chunk c at c ^ ((r>>1)&3)); its
+// 2 KiB metadata tile is the exact `tcgen05.cp.128x128b` source image of the kind::f16 sparse
+// metadata layout.
 #include "common.cuh"
 
-#include <cstdlib>
-
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
+
+#include <vector>
 
 namespace spfy {
 namespace {
 
-constexpr int BM = 128;        // rows of A per tile (UMMA M)
-constexpr int BN = 128;        // columns of B/D per tile (UMMA N)
-constexpr int BK = 128;        // logical K per stage (4 MMAs of K=32)
-constexpr int STAGES = 3;
-constexpr int A_TILE_BYTES = 16384;
-constexpr int E_TILE_BYTES = 2048;
-constexpr int B_STAGE_BYTES = BK * BN * 2;
-constexpr int C_BUF_BYTES = BM * 64 * 2;
-constexpr int C_BUFS = 2;
-constexpr int NUM_THREADS = 256;
+constexpr int BM = 128;              // rows of A per m-tile (UMMA M)
+constexpr int BN = 128;              // columns of B/D per unit (UMMA N)
+constexpr int BK = 64;               // logical K per ring stage (2 MMAs of K=32)
+constexpr int MAX_G = 2;             // m-tiles that share one B slice
+constexpr int A_SLICE_BYTES = 8192;  // 128 rows x 64 bytes
+constexpr int E_TILE_BYTES = 2048;   // metadata of 128 rows x 128 logical k
+constexpr int B_SLICE_BYTES = BK * BN * 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int C_BUF_BYTES = 32 * 128;  // one epilogue warp: 32 rows x 64 columns x 2 bytes
+constexpr int ACC_SLOTS = 3;
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_E_COL = 2 * BN;  // metadata columns start after the two accumulators
-
-constexpr int SMEM_A = 0;
-constexpr int SMEM_B = SMEM_A + STAGES * A_TILE_BYTES;
-constexpr int SMEM_C = SMEM_B + STAGES * B_STAGE_BYTES;
-constexpr int SMEM_E = SMEM_C + C_BUFS * C_BUF_BYTES;
-constexpr int SMEM_BAR = SMEM_E + STAGES * E_TILE_BYTES;
-constexpr int NUM_BARS = 2 * STAGES + 4;
-constexpr int SMEM_TMEM_PTR = SMEM_BAR + NUM_BARS * 8;
-constexpr int SMEM_TOTAL = SMEM_TMEM_PTR + 16;
-constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack for the 1024-byte alignment
+constexpr int TMEM_E_COL = ACC_SLOTS * BN;  // 384: metadata columns
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in maximum per CTA
 
 constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
 constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 
-struct SpmmaParams {
+// one GEMM as the kernel sees it (lives in kernel-parameter space for spfy_spmma, in a device
+// table for plans; the tensor maps must be 64-byte aligned)
+struct alignas(64) ProblemDev {
+  CUtensorMap tmap_b;  // B: OPB_N -> [k][n] boxes (64 n, 64 k); OPB_T -> [n][k] boxes (64 k, 128 n)
+  CUtensorMap tmap_d;  // D: [m][n] boxes (64 n, 32 m)
   const uint8_t* a_vals;
   const uint8_t* a_meta;
-  const void* C;  // only read when beta != 0
-  size_t ldc;
+  const void* C;       // only read when beta != 0
+  uint64_t ldc;
   uint32_t m, n, k;
-  uint32_t m_tiles, n_tiles, k_tiles;
+  uint32_t m_tiles, k_tiles, k_slices, n_tiles, m_groups;
+  uint32_t G;          // m-tiles per unit
+  uint32_t resident;   // whole A lives in shared memory
+  uint32_t unit_begin, units;  // this problem's range in the launch-wide unit order
   float alpha, beta;
-  uint32_t idesc;
   uint64_t hint_b;
-  uint32_t dbg;  // development switches (SPFY_SPMMA_DEBUG), 0 in production
+};
+
+struct LaunchParams {
+  const ProblemDev* table;  // null -> the single problem passed by value
+  uint32_t num_problems;
+  uint32_t total_units;
+  uint32_t idesc;
+  // shared-memory geometry of this launch
+  uint32_t stages, stage_bytes, a_off, e_off;  // ring stage: [B slice][A slice x G][E tile x G]
+  uint32_t res_off, res_e_off;                 // resident A values / metadata
+  uint32_t c_off, bar_off;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -147,9 +167,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -209,7 +228,6 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
@@ -223,7 +241,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
          (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32 | (uint64_t)1 << 46 |
          (uint64_t)layout_type << 61;
 }
-constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_NONE = 0;
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_NONE = 0;
 
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -244,184 +262,301 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
   }
 }
 
+__device__ __forceinline__ uint32_t rows_valid_of(uint32_t m, uint32_t mt) {
+  const uint32_t left = m - mt * BM;
+  return left >= (uint32_t)BM ? (uint32_t)BM : ((left + 15u) & ~15u);
+}
+
+// All three roles walk the same sequence of units: u = blockIdx.x, blockIdx.x + gridDim.x, ...
+struct UnitWalker {
+  const ProblemDev* single;
+  const ProblemDev* table;
+  uint32_t num_problems, total_units;
+  uint32_t u, p;
+  __device__ __forceinline__ UnitWalker(const ProblemDev* s, const LaunchParams& L)
+      : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units),
+        u(blockIdx.x), p(0) {}
+  __device__ __forceinline__ const ProblemDev* prob(uint32_t i) const { return table ? table + i : single; }
+  __device__ __forceinline__ bool valid() const { return u < total_units; }
+  // problem of the current unit (units are visited in increasing order, so p only advances)
+  __device__ __forceinline__ const ProblemDev* current() {
+    while (p + 1 < num_problems && u >= prob(p)->unit_begin + prob(p)->units) ++p;
+    return prob(p);
+  }
+  __device__ __forceinline__ void next() { u += gridDim.x; }
+  // is the current unit this CTA's last one inside problem P?
+  __device__ __forceinline__ bool last_of_problem(const ProblemDev* P) const {
+    const uint32_t nu = u + gridDim.x;
+    return nu >= total_units || nu >= P->unit_begin + P->units;
+  }
+};
+
 // ------------------------------------------------------------------- kernel
 template <bool BF16, bool OPB_T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-spmma_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_d,
-             const SpmmaParams P) {
+spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ LaunchParams L) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t bar_full = smem_base + SMEM_BAR;              // [STAGES]
-  const uint32_t bar_empty = bar_full + STAGES * 8;            // [STAGES]
-  const uint32_t bar_acc_full = bar_empty + STAGES * 8;        // [2]
-  const uint32_t bar_acc_empty = bar_acc_full + 2 * 8;         // [2]
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_TMEM_PTR);
+  const uint32_t NS = L.stages;
+  const uint32_t bar_full = smem_base + L.bar_off;              // [MAX_STAGES]
+  const uint32_t bar_empty = bar_full + MAX_STAGES * 8;         // [MAX_STAGES]
+  const uint32_t bar_acc_full = bar_empty + MAX_STAGES * 8;     // [ACC_SLOTS]
+  const uint32_t bar_acc_empty = bar_acc_full + ACC_SLOTS * 8;  // [ACC_SLOTS]
+  const uint32_t bar_res_full = bar_acc_empty + ACC_SLOTS * 8;
+  const uint32_t bar_res_empty = bar_res_full + 8;
+  const uint32_t tmem_ptr_off = L.bar_off + (2 * MAX_STAGES + 2 * ACC_SLOTS + 2) * 8;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + tmem_ptr_off);
 
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_b);
-    prefetch_tmap(&tmap_d);
-  }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (uint32_t s = 0; s < (uint32_t)MAX_STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
       mbar_init(bar_empty + s * 8, 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < ACC_SLOTS; ++a) {
       mbar_init(bar_acc_full + a * 8, 1);
-      mbar_init(bar_acc_empty + a * 8, 4);  // one arrive per epilogue warp
+      mbar_init(bar_acc_empty + a * 8, NUM_EPI_WARPS);  // every epilogue warp reads a part of every job
     }
+    mbar_init(bar_res_full, 1);
+    mbar_init(bar_res_empty, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_base + SMEM_TMEM_PTR, TMEM_COLS);
+  if (warp == 2) tmem_alloc(smem_base + tmem_ptr_off, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const uint32_t num_tiles = P.m_tiles * P.n_tiles;
+  UnitWalker W(&single, L);
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const uint32_t m_blk = t % P.m_tiles, n_blk = t / P.m_tiles;
-        const uint32_t rows_left = P.m - m_blk * BM;
-        const uint32_t rows_valid = rows_left >= BM ? BM : ((rows_left + 15u) & ~15u);
-        const uint32_t tx = rows_valid * 128u + rows_valid * 16u + ((P.dbg & 4) ? 0u : B_STAGE_BYTES);
-        for (uint32_t kt = 0; kt < P.k_tiles; ++kt) {
-          mbar_wait(bar_empty + stage * 8, phase ^ 1);
-          const uint32_t full = bar_full + stage * 8;
-          mbar_expect_tx(full, tx);
-          const size_t tile = (size_t)m_blk * P.k_tiles + kt;
-          bulk_load_1d(smem_base + SMEM_A + stage * A_TILE_BYTES, P.a_vals + tile * A_TILE_BYTES,
-                       rows_valid * 128u, full, HINT_EVICT_LAST);
-          bulk_load_1d(smem_base + SMEM_E + stage * E_TILE_BYTES, P.a_meta + tile * E_TILE_BYTES,
-                       rows_valid * 16u, full, HINT_EVICT_LAST);
-          const uint32_t sb = smem_base + SMEM_B + stage * B_STAGE_BYTES;
-          if (P.dbg & 4) {
-          } else if (!OPB_T) {
-            // B is k x n row-major: boxes of [BK rows of k][64 columns of n] -> MN-major SW128
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmap_b, (int)(n_blk * BN + j * 64), (int)(kt * BK),
-                          full, P.hint_b);
-          } else {
-            // B is n x k row-major: boxes of [BN rows of n][64 columns of k] -> K-major SW128
-#pragma unroll
-            for (int j = 0; j < BK / 64; ++j)
-              tma_load_2d(sb + j * (BN * 128), &tmap_b, (int)(kt * BK + j * 64), (int)(n_blk * BN),
-                          full, P.hint_b);
+      uint32_t it = 0;         // ring position (continuous over units)
+      uint32_t res_loads = 0;  // resident (re)loads issued so far
+      const ProblemDev* res_owner = nullptr;
+      const ProblemDev* last = nullptr;
+      for (; W.valid(); W.next()) {
+        const ProblemDev* P = W.current();
+        if (P != last) {
+          prefetch_tmap(&P->tmap_b);
+          last = P;
+        }
+        const uint32_t local = W.u - P->unit_begin;
+        const uint32_t nt = local / P->m_groups, mg = local - nt * P->m_groups;
+        const uint32_t mt0 = mg * P->G;
+        const uint32_t g_count = min(P->G, P->m_tiles - mt0);
+        if (P->resident && res_owner != P) {
+          // (re)load the whole compressed A of this problem into the resident region
+          mbar_wait(bar_res_empty, (res_loads & 1u) ^ 1u);
+          uint32_t bytes = 0;
+          for (uint32_t mt = 0; mt < P->m_tiles; ++mt) {
+            const uint32_t rv = rows_valid_of(P->m, mt);
+            bytes += rv * 64u * P->k_slices + rv * 16u * P->k_tiles;
           }
-          if (++stage == STAGES) stage = 0, phase ^= 1;
+          mbar_expect_tx(bar_res_full, bytes);
+          for (uint32_t mt = 0; mt < P->m_tiles; ++mt) {
+            const uint32_t rv = rows_valid_of(P->m, mt);
+            for (uint32_t ks = 0; ks < P->k_slices; ++ks)
+              bulk_load_1d(smem_base + L.res_off + (mt * P->k_slices + ks) * A_SLICE_BYTES,
+                           P->a_vals + ((size_t)mt * P->k_tiles * 2 + ks) * A_SLICE_BYTES, rv * 64u,
+                           bar_res_full, HINT_EVICT_LAST);
+            for (uint32_t kt = 0; kt < P->k_tiles; ++kt)
+              bulk_load_1d(smem_base + L.res_e_off + (mt * P->k_tiles + kt) * E_TILE_BYTES,
+                           P->a_meta + ((size_t)mt * P->k_tiles + kt) * E_TILE_BYTES, rv * 16u,
+                           bar_res_full, HINT_EVICT_LAST);
+          }
+          res_owner = P;
+          ++res_loads;
+        }
+        for (uint32_t ks = 0; ks < P->k_slices; ++ks, ++it) {
+          const uint32_t stage = it % NS, phase = (it / NS) & 1u;
+          mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+          const uint32_t full = bar_full + stage * 8;
+          const uint32_t sbase = smem_base + stage * L.stage_bytes;
+          uint32_t tx = B_SLICE_BYTES;
+          if (!P->resident) {
+            for (uint32_t g = 0; g < g_count; ++g) {
+              const uint32_t rv = rows_valid_of(P->m, mt0 + g);
+              tx += rv * 64u + ((ks & 1u) ? 0u : rv * 16u);
+            }
+          }
+          mbar_expect_tx(full, tx);
+          if (!P->resident) {
+            for (uint32_t g = 0; g < g_count; ++g) {
+              const uint32_t mt = mt0 + g, rv = rows_valid_of(P->m, mt);
+              bulk_load_1d(sbase + L.a_off + g * A_SLICE_BYTES,
+                           P->a_vals + ((size_t)mt * P->k_tiles * 2 + ks) * A_SLICE_BYTES, rv * 64u, full,
+                           HINT_EVICT_LAST);
+              if (!(ks & 1u))
+                bulk_load_1d(sbase + L.e_off + g * E_TILE_BYTES,
+                             P->a_meta + ((size_t)mt * P->k_tiles + (ks >> 1)) * E_TILE_BYTES, rv * 16u, full,
+                             HINT_EVICT_LAST);
+            }
+          }
+          if (!OPB_T) {
+            // B is k x n row-major: two boxes of [64 rows of k][64 columns of n] -> MN-major SW128
+            tma_load_2d(sbase, &P->tmap_b, (int)(nt * BN), (int)(ks * BK), full, P->hint_b);
+            tma_load_2d(sbase + BK * 128, &P->tmap_b, (int)(nt * BN + 64), (int)(ks * BK), full, P->hint_b);
+          } else {
+            // B is n x k row-major: one box of [128 rows of n][64 columns of k] -> K-major SW128
+            tma_load_2d(sbase, &P->tmap_b, (int)(ks * BK), (int)(nt * BN), full, P->hint_b);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, it = 0, kiter = 0;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait(bar_acc_empty + as * 8, aphase ^ 1);
+      uint32_t it = 0, job = 0, eblk = 0, res_loads = 0;
+      const ProblemDev* res_owner = nullptr;
+      for (; W.valid(); W.next()) {
+        const ProblemDev* P = W.current();
+        const uint32_t local = W.u - P->unit_begin;
+        const uint32_t mg = local % P->m_groups;
+        const uint32_t mt0 = mg * P->G;
+        const uint32_t g_count = min(P->G, P->m_tiles - mt0);
+        if (P->resident && res_owner != P) {
+          mbar_wait(bar_res_full, res_loads & 1u);
+          res_owner = P;
+          ++res_loads;
+        }
+        // accumulator slots of this unit's jobs
+        uint32_t slot[MAX_G] = {0, 0};
+#pragma unroll
+        for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g) {
+          if (g < g_count) {
+            const uint32_t a = job + g;
+            slot[g] = a % ACC_SLOTS;
+            mbar_wait(bar_acc_empty + slot[g] * 8, ((a / ACC_SLOTS) & 1u) ^ 1u);
+          }
+        }
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (uint32_t kt = 0; kt < P.k_tiles; ++kt, ++kiter) {
+        uint32_t ecol[MAX_G] = {0, 0};
+        for (uint32_t ks = 0; ks < P->k_slices; ++ks, ++it) {
+          const uint32_t stage = it % NS, phase = (it / NS) & 1u;
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
-          const uint32_t e_col = tmem_base + TMEM_E_COL + (kiter & 1) * 4;
-          tc_cp_128x128b(e_col, make_smem_desc(smem_base + SMEM_E + stage * E_TILE_BYTES, 16, 128, LAYOUT_NONE));
-          const uint32_t k_left = P.k - kt * BK;
-          const uint32_t nk = k_left >= BK ? 4u : (k_left + 31u) / 32u;
-          const uint32_t sa = smem_base + SMEM_A + stage * A_TILE_BYTES;
-          const uint32_t sb = smem_base + SMEM_B + stage * B_STAGE_BYTES;
+          const uint32_t sbase = smem_base + stage * L.stage_bytes;
+          if (!(ks & 1u)) {
+            // metadata of the next 128 logical k (this slice and the following one) -> TMEM
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) {
-            if (j < nk && !(P.dbg & 8)) {
-              // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
-              const uint64_t da = make_smem_desc(sa + j * 32, 16, 1024, LAYOUT_SW128);
-              uint64_t db;
-              if (!OPB_T)  // MN-major SW128: 8 k-rows per 1024B atom, 64-column groups BK*128 apart
-                db = make_smem_desc(sb + j * 32 * 128, BK * 128, 1024, LAYOUT_SW128);
-              else         // K-major SW128: two 64-wide k halves, 64 bytes per MMA inside a row
-                db = make_smem_desc(sb + (j >> 1) * (BN * 128) + (j & 1) * 64, 16, 1024, LAYOUT_SW128);
-              const uint32_t col = e_col + j;
-              tc_mma_sp_f16(tmem_d, da, db, col & ~1u, P.idesc | (col & 1u), (kt | j) != 0);
+            for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g) {
+              if (g < g_count) {
+                ecol[g] = tmem_base + TMEM_E_COL + ((eblk & 1u) * MAX_G + g) * 4u;
+                const uint32_t esrc =
+                    P->resident ? smem_base + L.res_e_off + ((mt0 + g) * P->k_tiles + (ks >> 1)) * E_TILE_BYTES
+                                : sbase + L.e_off + g * E_TILE_BYTES;
+                tc_cp_128x128b(ecol[g], make_smem_desc(esrc, 16, 128, LAYOUT_NONE));
+              }
+            }
+            ++eblk;
+          }
+          const uint32_t k_left = P->k - ks * BK;
+          const uint32_t nk = k_left >= (uint32_t)BK ? 2u : (k_left + 31u) / 32u;
+#pragma unroll
+          for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g) {
+            if (g < g_count) {
+              const uint32_t sa = P->resident
+                                      ? smem_base + L.res_off + ((mt0 + g) * P->k_slices + ks) * A_SLICE_BYTES
+                                      : sbase + L.a_off + g * A_SLICE_BYTES;
+              const uint32_t tmem_d = tmem_base + slot[g] * BN;
+#pragma unroll
+              for (uint32_t j = 0; j < 2; ++j) {
+                if (j < nk) {
+                  // A: K-major SW64, 32 logical = 16 stored halves = 32 bytes per MMA
+                  const uint64_t da = make_smem_desc(sa + j * 32, 16, 512, LAYOUT_SW64);
+                  uint64_t db;
+                  if (!OPB_T)  // MN-major SW128: 8 k-rows per 1024 B atom, 64-column groups BK*128 apart
+                    db = make_smem_desc(sbase + j * 32 * 128, BK * 128, 1024, LAYOUT_SW128);
+                  else         // K-major SW128: 64 bytes (32 k) per MMA inside a 128-byte row
+                    db = make_smem_desc(sbase + j * 64, 16, 1024, LAYOUT_SW128);
+                  const uint32_t col = ecol[g] + (ks & 1u) * 2u + j;
+                  tc_mma_sp_f16(tmem_d, da, db, col & ~1u, L.idesc | (col & 1u), (ks | j) != 0);
+                }
+              }
             }
           }
           tc_commit(bar_empty + stage * 8);
-          if (++stage == STAGES) stage = 0, phase ^= 1;
         }
-        tc_commit(bar_acc_full + as * 8);
+#pragma unroll
+        for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g)
+          if (g < g_count) tc_commit(bar_acc_full + slot[g] * 8);
+        job += g_count;
+        if (P->resident && W.last_of_problem(P)) {
+          tc_commit(bar_res_empty);  // every MMA that reads the resident region has completed
+          res_owner = nullptr;
+        }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const uint32_t ew = warp - 4;              // == warp % 4: TMEM lane quarter
-    const uint32_t row = ew * 32 + lane;       // row inside the tile == TMEM lane
-    const uint32_t ethread = threadIdx.x - 128;
-    uint32_t it = 0, cbuf = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const uint32_t m_blk = t % P.m_tiles, n_blk = t / P.m_tiles;
-      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const uint32_t m0 = m_blk * BM, n0 = n_blk * BN;
-      const bool warp_has_rows = m0 + ew * 32 < P.m;
-      mbar_wait(bar_acc_full + as * 8, aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const uint32_t e = warp - 2;
+    const uint32_t quarter = warp & 3u;  // TMEM lanes this warp may read: [32*quarter, 32*quarter+32)
+    const uint32_t half = e >> 2;        // column half of the accumulator
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    const uint32_t sc = smem_base + L.c_off + e * C_BUF_BYTES;
+    uint32_t job = 0;
+    for (; W.valid(); W.next()) {
+      const ProblemDev* P = W.current();
+      const uint32_t local = W.u - P->unit_begin;
+      const uint32_t nt = local / P->m_groups, mg = local - nt * P->m_groups;
+      const uint32_t mt0 = mg * P->G;
+      const uint32_t g_count = min(P->G, P->m_tiles - mt0);
+      const float alpha = P->alpha, beta = P->beta;
+      for (uint32_t g = 0; g < g_count; ++g, ++job) {
+        const uint32_t slot = job % ACC_SLOTS;
+        const uint32_t m0 = (mt0 + g) * BM, n0 = nt * BN + half * 64;
+        const bool warp_has_rows = m0 + quarter * 32 < P->m && n0 < P->n;
+        mbar_wait(bar_acc_full + slot * 8, (job / ACC_SLOTS) & 1u);
+        tc_fence_after();
         uint32_t acc[64];
-        if (warp_has_rows && !(P.dbg & 2)) {
-          const uint32_t taddr = tmem_base + as * BN + c * 64 + ((ew * 32) << 16);
+        if (warp_has_rows) {
+          const uint32_t taddr = tmem_base + slot * BN + half * 64 + ((quarter * 32) << 16);
           tmem_ld_x32(taddr, acc);
           tmem_ld_x32(taddr + 32, acc + 32);
           tmem_wait_ld();
         }
-        if (c == BN / 64 - 1) {  // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
+        // accumulator read: hand the slot back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
+        if (warp_has_rows) {
+          if (lane == 0) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + as * 8);
-        }
-        if (ethread == 0) bulk_wait_read<C_BUFS - 1>();  // the buffer we are about to fill is free
-        if (!(P.dbg & 32)) epi_bar_sync();
-        const uint32_t sc = smem_base + SMEM_C + cbuf * C_BUF_BYTES;
-        if (warp_has_rows && !(P.dbg & (2 | 16))) {
-          const uint32_t grow = m0 + row;
-          const uint32_t gcol0 = n0 + c * 64;
-          const bool use_c = P.beta != 0.f && grow < P.m;
+          const uint32_t grow = m0 + row_in_tile;
+          const bool use_c = beta != 0.f && grow < P->m;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = P.alpha * __uint_as_float(acc[q * 8 + e]);
-            if (use_c && gcol0 + q * 8 < P.n) {
+            for (int x = 0; x < 8; ++x) v[x] = alpha * __uint_as_float(acc[q * 8 + x]);
+            if (use_c && n0 + q * 8 < P->n) {
               const uint4 cw = *reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const uint16_t*>(P.C) + (size_t)grow * P.ldc + gcol0 + q * 8);
+                  reinterpret_cast<const uint16_t*>(P->C) + (size_t)grow * P->ldc + n0 + q * 8);
               const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack2<BF16>(cws[e]);
-                v[2 * e] += P.beta * f.x;
-                v[2 * e + 1] += P.beta * f.y;
+              for (int x = 0; x < 4; ++x) {
+                const float2 f = unpack2<BF16>(cws[x]);
+                v[2 * x] += beta * f.x;
+                v[2 * x + 1] += beta * f.y;
               }
             }
-            st_shared_v4(sc + row * 128 + ((q ^ (row & 7)) << 4), pack2<BF16>(v[0], v[1]),
+            st_shared_v4(sc + lane * 128 + ((q ^ (lane & 7)) << 4), pack2<BF16>(v[0], v[1]),
                          pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&P->tmap_d, sc, (int)n0, (int)(m0 + quarter * 32));
+            bulk_commit();
+          }
         }
-        fence_proxy_async_smem();
-        if (!(P.dbg & 32)) epi_bar_sync();
-        if (ethread == 0 && !(P.dbg & 3)) {
-          tma_store_2d(&tmap_d, sc, (int)(n0 + c * 64), (int)m0);
-          bulk_commit();
-        }
-        cbuf ^= 1;
       }
     }
-    if (ethread == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -472,21 +607,162 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t inner, 
   return SPFY_OK;
 }
 
+struct HostProblem {
+  int opB;
+  size_t m, n, k;
+  const void *comp_vals, *meta, *B, *C;
+  void* D;
+  size_t ldb, ldc, ldd;
+  float alpha, beta;
+};
+
+int validate(int dtype, const HostProblem& h, const char* who) {
+  if (dtype != SPFY_F16 && dtype != SPFY_BF16)
+    return fail(SPFY_E_UNSUPPORTED, "%s: dtype %d (need F16/BF16)", who, dtype);
+  if (h.opB != SPFY_OP_N && h.opB != SPFY_OP_T) return fail(SPFY_E_INVALID, "%s: bad opB %d", who, h.opB);
+  if (h.m == 0 || h.n == 0) return SPFY_OK;
+  if (!h.comp_vals || !h.meta || !h.B || !h.D) return fail(SPFY_E_INVALID, "%s: null operand", who);
+  if (h.beta != 0.f && !h.C) return fail(SPFY_E_INVALID, "%s: beta != 0 needs C", who);
+  if (h.k == 0) return fail(SPFY_E_UNSUPPORTED, "%s: k == 0", who);
+  if (h.m >= (1u << 31) || h.n >= (1u << 31) || h.k >= (1u << 31))
+    return fail(SPFY_E_UNSUPPORTED, "%s: dimension too large", who);
+  const size_t b_inner = h.opB == SPFY_OP_N ? h.n : h.k;
+  if (h.ldb < b_inner || h.ldd < h.n || (h.beta != 0.f && h.ldc < h.n))
+    return fail(SPFY_E_INVALID, "%s: leading dimension too small", who);
+  // TMA contract == the reference's own fp16 contract (spmma.hxx:45-49): multiples of 8
+  if (h.ldb % 8 || h.ldd % 8 || (h.beta != 0.f && h.ldc % 8) || h.n % 8 || (h.opB == SPFY_OP_T && h.k % 8))
+    return fail(SPFY_E_UNSUPPORTED,
+                "%s: n, ldb, ldc, ldd (and k for opB=T) must be multiples of 8 elements "
+                "(n=%zu k=%zu ldb=%zu ldc=%zu ldd=%zu)", who, h.n, h.k, h.ldb, h.ldc, h.ldd);
+  if ((uintptr_t)h.B % 16 || (uintptr_t)h.D % 16 || (h.beta != 0.f && (uintptr_t)h.C % 16) ||
+      (uintptr_t)h.comp_vals % 16 || (uintptr_t)h.meta % 16)
+    return fail(SPFY_E_INVALID, "%s: operands must be 16-byte aligned", who);
+  return SPFY_OK;
+}
+
+// launch classes: problems of one class share a shared-memory geometry and one launch
+enum { CLASS_RESIDENT = 0, CLASS_STREAM_G1 = 1, CLASS_STREAM_G2 = 2, NUM_CLASSES = 3 };
+constexpr uint32_t C_BYTES = NUM_EPI_WARPS * C_BUF_BYTES;  // 32 KiB
+constexpr uint32_t BAR_BYTES = 256;
+constexpr uint32_t RES_MAX_BYTES = 96 * 1024;  // resident A (values + metadata)
+
+size_t resident_bytes(size_t m, size_t k) {
+  const size_t m_tiles = ceil_div(m, BM), k_tiles = ceil_div(k, 128);
+  return m_tiles * k_tiles * (2 * A_SLICE_BYTES + E_TILE_BYTES);
+}
+
+int classify(const HostProblem& h, bool grouped, int sm_count) {
+  const size_t m_tiles = ceil_div(h.m, BM), n_tiles = ceil_div(h.n, BN);
+  if (resident_bytes(h.m, h.k) <= RES_MAX_BYTES && n_tiles >= (size_t)sm_count) return CLASS_RESIDENT;
+  if (m_tiles >= 2 && (grouped || ceil_div(m_tiles, 2) * n_tiles >= 2 * (size_t)sm_count))
+    return CLASS_STREAM_G2;
+  return CLASS_STREAM_G1;
+}
+
+// fill the device view of one problem (tensor maps included); unit_begin is set by the caller
+int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
+  memset(d, 0, sizeof(*d));
+  int rc;
+  if (h.opB == SPFY_OP_N)
+    rc = make_tmap_2d(&d->tmap_b, dtype, h.B, h.n, h.k, h.ldb, 64, BK);
+  else
+    rc = make_tmap_2d(&d->tmap_b, dtype, h.B, h.k, h.n, h.ldb, 64, BN);
+  if (rc) return rc;
+  rc = make_tmap_2d(&d->tmap_d, dtype, h.D, h.n, h.m, h.ldd, 64, 32);
+  if (rc) return rc;
+  d->a_vals = (const uint8_t*)h.comp_vals;
+  d->a_meta = (const uint8_t*)h.meta;
+  d->C = h.C;
+  d->ldc = h.ldc;
+  d->m = (uint32_t)h.m;
+  d->n = (uint32_t)h.n;
+  d->k = (uint32_t)h.k;
+  d->m_tiles = (uint32_t)ceil_div(h.m, BM);
+  d->k_tiles = (uint32_t)ceil_div(h.k, 128);
+  d->k_slices = (uint32_t)ceil_div(h.k, BK);
+  d->n_tiles = (uint32_t)ceil_div(h.n, BN);
+  d->resident = cls == CLASS_RESIDENT;
+  d->G = (cls == CLASS_STREAM_G1) ? 1u : (d->m_tiles >= 2 ? 2u : 1u);
+  d->m_groups = (uint32_t)ceil_div(d->m_tiles, d->G);
+  d->units = d->m_groups * d->n_tiles;
+  d->alpha = h.alpha;
+  d->beta = h.beta;
+  // B is streamed once when one unit covers all of M; otherwise the other m-groups of the same
+  // columns will want it from L2 shortly after
+  d->hint_b = d->m_groups == 1 ? HINT_EVICT_FIRST : HINT_EVICT_NORMAL;
+  return SPFY_OK;
+}
+
+// shared-memory geometry of a class
+void geometry(int cls, LaunchParams* L, uint32_t* smem_bytes) {
+  uint32_t stage, res = 0;
+  L->a_off = B_SLICE_BYTES;
+  if (cls == CLASS_RESIDENT) {
+    stage = B_SLICE_BYTES;
+    L->e_off = stage;
+    res = RES_MAX_BYTES;
+  } else {
+    const uint32_t G = cls == CLASS_STREAM_G2 ? 2u : 1u;
+    L->e_off = B_SLICE_BYTES + G * A_SLICE_BYTES;
+    stage = L->e_off + G * E_TILE_BYTES;
+  }
+  const uint32_t fixed = 1024 /*alignment slack*/ + C_BYTES + BAR_BYTES + res;
+  uint32_t stages = (SMEM_LIMIT - fixed) / stage;
+  if (stages > (uint32_t)MAX_STAGES) stages = MAX_STAGES;
+  L->stages = stages;
+  L->stage_bytes = stage;
+  L->res_off = stages * stage;
+  L->res_e_off = L->res_off;  // set per launch: metadata sits behind the largest value block
+  L->c_off = L->res_off + res;
+  L->bar_off = L->c_off + C_BYTES;
+  *smem_bytes = L->bar_off + BAR_BYTES + 1024;
+}
+
+uint32_t make_idesc(int dtype, int opB) {
+  // instruction descriptor (kind::f16, sparse): c=F32, a/b format, b major, N>>3, M>>4
+  const uint32_t fmt = dtype == SPFY_BF16 ? 1u : 0u;
+  return (1u << 2) | (1u << 4) | (fmt << 7) | (fmt << 10) | ((opB == SPFY_OP_N ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
 template <bool BF16, bool OPB_T>
-int launch(const CUtensorMap& tb, const CUtensorMap& td, const SpmmaParams& P, int grid,
-           cudaStream_t s) {
+int launch_t(const ProblemDev& single, const LaunchParams& L, uint32_t smem, int grid, cudaStream_t s) {
   static std::atomic<int> attr_set[64];
   int dev = 0;
   SPFY_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63].load()) {
     SPFY_CUDA_OK(cudaFuncSetAttribute(spmma_kernel<BF16, OPB_T>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set[dev & 63].store(1);
   }
-  spmma_kernel<BF16, OPB_T><<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(tb, td, P);
+  spmma_kernel<BF16, OPB_T><<<grid, NUM_THREADS, smem, s>>>(single, L);
   SPFY_LAUNCH_OK("spmma_kernel");
   return SPFY_OK;
 }
+
+int launch(int dtype, int opB, const ProblemDev& single, const LaunchParams& L, uint32_t smem, int grid,
+           cudaStream_t s) {
+  if (dtype == SPFY_BF16)
+    return opB == SPFY_OP_N ? launch_t<true, false>(single, L, smem, grid, s)
+                            : launch_t<true, true>(single, L, smem, grid, s);
+  return opB == SPFY_OP_N ? launch_t<false, false>(single, L, smem, grid, s)
+                          : launch_t<false, true>(single, L, smem, grid, s);
+}
+
+uint32_t res_values_bytes(const ProblemDev& d) { return d.m_tiles * d.k_slices * A_SLICE_BYTES; }
+
+struct Plan {
+  int dtype = 0;
+  ProblemDev* d_table = nullptr;  // all launches back to back
+  struct Launch {
+    int opB;
+    uint32_t first, count;  // range in d_table
+    LaunchParams L;
+    uint32_t smem;
+    int grid;
+  };
+  std::vector<Launch> launches;
+};
 
 }  // namespace
 }  // namespace spfy
@@ -505,75 +781,127 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
                const void* meta, const void* B, size_t ldb, float beta, const void* C, size_t ldc,
                void* D, size_t ldd, void* workspace, size_t workspace_bytes, spfy_stream_t stream) {
   (void)workspace; (void)workspace_bytes;
-  if (dtype != SPFY_F16 && dtype != SPFY_BF16)
-    return fail(SPFY_E_UNSUPPORTED, "spmma: dtype %d (need F16/BF16)", dtype);
-  if (opB != SPFY_OP_N && opB != SPFY_OP_T) return fail(SPFY_E_INVALID, "spmma: bad opB %d", opB);
+  HostProblem h{opB, m, n, k, comp_vals, meta, B, C, D, ldb, ldc, ldd, alpha, beta};
+  int rc = validate(dtype, h, "spmma");
+  if (rc) return rc;
   if (m == 0 || n == 0) return SPFY_OK;
-  if (!comp_vals || !meta || !B || !D) return fail(SPFY_E_INVALID, "spmma: null operand");
-  if (beta != 0.f && !C) return fail(SPFY_E_INVALID, "spmma: beta != 0 needs C");
-  if (k == 0) return fail(SPFY_E_UNSUPPORTED, "spmma: k == 0");
-  if (m >= (1u << 31) || n >= (1u << 31) || k >= (1u << 31))
-    return fail(SPFY_E_UNSUPPORTED, "spmma: dimension too large");
-  const size_t b_inner = opB == SPFY_OP_N ? n : k;
-  if (ldb < b_inner || ldd < n || (beta != 0.f && ldc < n))
-    return fail(SPFY_E_INVALID, "spmma: leading dimension too small");
-  // TMA contract == the reference's own fp16 contract (spmma.hxx:45-49): multiples of 8
-  if (ldb % 8 || ldd % 8 || (beta != 0.f && ldc % 8) || n % 8 || (opB == SPFY_OP_T && k % 8))
-    return fail(SPFY_E_UNSUPPORTED,
-                "spmma: n, ldb, ldc, ldd (and k for opB=T) must be multiples of 8 elements "
-                "(n=%zu k=%zu ldb=%zu ldc=%zu ldd=%zu)", n, k, ldb, ldc, ldd);
-  if ((uintptr_t)B % 16 || (uintptr_t)D % 16 || (beta != 0.f && (uintptr_t)C % 16) ||
-      (uintptr_t)comp_vals % 16 || (uintptr_t)meta % 16)
-    return fail(SPFY_E_INVALID, "spmma: operands must be 16-byte aligned");
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  if (di.cc_major != 10)
+    return fail(SPFY_E_UNSUPPORTED, "spmma: needs an sm_100a device, found sm_%d%d", di.cc_major, di.cc_minor);
+  const int cls = classify(h, false, di.sm_count);
+  ProblemDev d;
+  rc = fill_problem(&d, dtype, h, cls);
+  if (rc) return rc;
+  d.unit_begin = 0;
+  LaunchParams L;
+  memset(&L, 0, sizeof(L));
+  uint32_t smem = 0;
+  geometry(cls, &L, &smem);
+  L.res_e_off = L.res_off + res_values_bytes(d);
+  L.table = nullptr;
+  L.num_problems = 1;
+  L.total_units = d.units;
+  L.idesc = make_idesc(dtype, opB);
+  const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
+  return launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
+}
 
+int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t count,
+                           spfy_spmma_plan_t* out) {
+  if (!out) return fail(SPFY_E_INVALID, "spmma_plan_create: null plan pointer");
+  *out = nullptr;
+  if (count && !problems) return fail(SPFY_E_INVALID, "spmma_plan_create: null problem list");
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
   if (di.cc_major != 10)
-    return fail(SPFY_E_UNSUPPORTED, "spmma: needs an sm_100a device, found sm_%d%d", di.cc_major, di.cc_minor);
-
-  CUtensorMap tb, td;
-  if (opB == SPFY_OP_N)
-    rc = make_tmap_2d(&tb, dtype, B, n, k, ldb, 64, BK);
-  else
-    rc = make_tmap_2d(&tb, dtype, B, k, n, ldb, 64, BN);
-  if (rc) return rc;
-  rc = make_tmap_2d(&td, dtype, D, n, m, ldd, 64, BM);
-  if (rc) return rc;
-
-  SpmmaParams P;
-  memset(&P, 0, sizeof(P));
-  P.a_vals = (const uint8_t*)comp_vals;
-  P.a_meta = (const uint8_t*)meta;
-  P.C = C;
-  P.ldc = ldc;
-  P.m = (uint32_t)m;
-  P.n = (uint32_t)n;
-  P.k = (uint32_t)k;
-  P.m_tiles = (uint32_t)ceil_div(m, BM);
-  P.n_tiles = (uint32_t)ceil_div(n, BN);
-  P.k_tiles = (uint32_t)ceil_div(k, BK);
-  P.alpha = alpha;
-  P.beta = beta;
-  // instruction descriptor (kind::f16, sparse): c=F32, a/b format, b major, N>>3, M>>4
-  const uint32_t fmt = dtype == SPFY_BF16 ? 1u : 0u;
-  P.idesc = (1u << 2) | (1u << 4) | (fmt << 7) | (fmt << 10) |
-            ((opB == SPFY_OP_N ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-            ((uint32_t)(BM >> 4) << 24);
-  // B is streamed once when a single row of tiles covers M; otherwise the other
-  // m-tiles of the same columns will want it from L2 again.
-  P.hint_b = P.m_tiles == 1 ? HINT_EVICT_FIRST : HINT_EVICT_NORMAL;
-  {
-    const char* e = getenv("SPFY_SPMMA_DEBUG");
-    P.dbg = e ? (uint32_t)atoi(e) : 0u;
+    return fail(SPFY_E_UNSUPPORTED, "spmma_plan_create: needs an sm_100a device, found sm_%d%d", di.cc_major,
+                di.cc_minor);
+  Plan* plan = new Plan();
+  plan->dtype = dtype;
+  std::vector<ProblemDev> table;
+  for (int cls = 0; cls < NUM_CLASSES; ++cls) {
+    for (int opB = 0; opB < 2; ++opB) {
+      Plan::Launch ln;
+      memset(&ln.L, 0, sizeof(ln.L));
+      ln.opB = opB;
+      ln.first = (uint32_t)table.size();
+      ln.count = 0;
+      uint32_t units = 0, res_vals = 0;
+      for (size_t i = 0; i < count; ++i) {
+        const spfy_spmma_problem& q = problems[i];
+        HostProblem h{q.opB, q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
+        if (h.opB != opB) continue;
+        rc = validate(dtype, h, "spmma_plan_create");
+        if (rc) {
+          delete plan;
+          return rc;
+        }
+        if (h.m == 0 || h.n == 0) continue;
+        if (classify(h, true, di.sm_count) != cls) continue;
+        ProblemDev d;
+        rc = fill_problem(&d, dtype, h, cls);
+        if (rc) {
+          delete plan;
+          return rc;
+        }
+        d.unit_begin = units;
+        if ((uint64_t)units + d.units >= (1ull << 32)) {
+          delete plan;
+          return fail(SPFY_E_UNSUPPORTED, "spmma_plan_create: too many tiles");
+        }
+        units += d.units;
+        if (d.resident && res_values_bytes(d) > res_vals) res_vals = res_values_bytes(d);
+        table.push_back(d);
+        ++ln.count;
+      }
+      if (!ln.count) continue;
+      geometry(cls, &ln.L, &ln.smem);
+      ln.L.res_e_off = ln.L.res_off + res_vals;
+      ln.L.num_problems = ln.count;
+      ln.L.total_units = units;
+      ln.L.idesc = make_idesc(dtype, opB);
+      ln.grid = (int)(units < (uint32_t)di.sm_count ? units : (uint32_t)di.sm_count);
+      plan->launches.push_back(ln);
+    }
   }
+  if (!table.empty()) {
+    cudaError_t e = cudaMalloc((void**)&plan->d_table, table.size() * sizeof(ProblemDev));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(plan->d_table, table.data(), table.size() * sizeof(ProblemDev), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      if (plan->d_table) cudaFree(plan->d_table);
+      delete plan;
+      return fail(SPFY_E_CUDA, "spmma_plan_create: %s", cudaGetErrorString(e));
+    }
+    for (auto& ln : plan->launches) ln.L.table = plan->d_table + ln.first;
+  }
+  *out = (spfy_spmma_plan_t)plan;
+  return SPFY_OK;
+}
 
-  const size_t tiles = (size_t)P.m_tiles * P.n_tiles;
-  const int grid = (int)(tiles < (size_t)di.sm_count ? tiles : (size_t)di.sm_count);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == SPFY_BF16)
-    return opB == SPFY_OP_N ? launch<true, false>(tb, td, P, grid, s) : launch<true, true>(tb, td, P, grid, s);
-  return opB == SPFY_OP_N ? launch<false, false>(tb, td, P, grid, s) : launch<false, true>(tb, td, P, grid, s);
+int spfy_spmma_plan_run(spfy_spmma_plan_t p, spfy_stream_t stream) {
+  if (!p) return fail(SPFY_E_INVALID, "spmma_plan_run: null plan");
+  Plan* plan = (Plan*)p;
+  ProblemDev dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  for (const auto& ln : plan->launches) {
+    int rc = launch(plan->dtype, ln.opB, dummy, ln.L, ln.smem, ln.grid, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return SPFY_OK;
+}
+
+int spfy_spmma_plan_launches(spfy_spmma_plan_t p) { return p ? (int)((Plan*)p)->launches.size() : 0; }
+
+int spfy_spmma_plan_destroy(spfy_spmma_plan_t p) {
+  if (!p) return SPFY_OK;
+  Plan* plan = (Plan*)p;
+  if (plan->d_table) cudaFree(plan->d_table);
+  delete plan;
+  return SPFY_OK;
 }
 
 }  // extern "C"

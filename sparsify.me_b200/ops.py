@@ -115,6 +115,63 @@ def prune24_check(a):
     return int(flag.item())
 
 
+def prune24_batched(mats, comps, layout=capi.LAYOUT_SM100):
+    """Prune+compress a whole list of weight matrices with as few launches as possible
+    (spfy_prune24_batched).  `mats`: 2-D row-major tensors; `comps`: matching Compressed24."""
+    items = (capi.Prune24Item * len(mats))()
+    for i, (a, c) in enumerate(zip(mats, comps)):
+        items[i] = capi.Prune24Item(a.data_ptr(), a.stride(0), None, 0, c.vals.data_ptr(), c.meta.data_ptr(),
+                                    a.shape[0], a.shape[1])
+    capi.spfy_prune24_batched(_dtype_code(mats[0]), layout, ctypes.cast(items, ctypes.c_void_p), len(mats),
+                              _stream())
+
+
+def alloc_compressed(dtype, rows, cols, device, layout=capi.LAYOUT_SM100):
+    vb, mb = compressed_bytes(dtype, rows, cols, layout)
+    return Compressed24(torch.empty(vb, dtype=torch.uint8, device=device),
+                        torch.empty(mb, dtype=torch.uint8, device=device), rows, cols, dtype, layout)
+
+
+class SpmmaPlan:
+    """spfy_spmma_plan_*: a list of independent D_i = alpha_i * A_i(2:4) * op(B_i) + beta_i * C_i executed
+    by at most three persistent launches (tensor maps + tile schedule built once, like
+    cusparseLtMatmulPlanInit at spmma.hxx:79).  `problems`: dicts with comp, b, out and optional c, alpha,
+    beta, op_b.  The plan keeps the tensors alive."""
+
+    def __init__(self, problems):
+        self._keep = problems
+        n = len(problems)
+        arr = (capi.SpmmaProblem * n)()
+        dtype = None
+        for i, q in enumerate(problems):
+            comp, b, out = q["comp"], q["b"], q["out"]
+            c = q.get("c")
+            op_b = q.get("op_b", capi.OP_N)
+            dtype = comp.dtype
+            nn = b.shape[1] if op_b == capi.OP_N else b.shape[0]
+            arr[i] = capi.SpmmaProblem(op_b, comp.rows, nn, comp.cols, comp.vals.data_ptr(), comp.meta.data_ptr(),
+                                       b.data_ptr(), b.stride(0), c.data_ptr() if c is not None else None,
+                                       c.stride(0) if c is not None else 0, out.data_ptr(), out.stride(0),
+                                       float(q.get("alpha", 1.0)), float(q.get("beta", 0.0)))
+        self._h = ctypes.c_void_p()
+        capi.spfy_spmma_plan_create(_DT[dtype], ctypes.cast(arr, ctypes.c_void_p), n, ctypes.byref(self._h))
+        self.launches = capi.spfy_spmma_plan_launches(self._h)
+
+    def run(self):
+        capi.spfy_spmma_plan_run(self._h, _stream())
+
+    def close(self):
+        if self._h:
+            capi.spfy_spmma_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 # ----------------------------------------------------------------------------- A4
 def spmma_compressed(comp, b, c=None, out=None, alpha=1.0, beta=0.0, op_b=capi.OP_N):
     """D = alpha * A(2:4) * op(B) + beta * C on tcgen05.mma.sp (cusparseLtMatmul, spmma.hxx:106-114).

@@ -206,6 +206,81 @@ def test_spmma_matches_fp64_oracle(spfy, orc, cuda, M, K, N, dt):
     assert rel_err(got, want) <= REL_TOL
 
 
+# one shape per launch class of the v2 kernel (single-problem entry point):
+#   resident A (whole compressed A in shared memory, N >= 148 tiles), streaming G=2 (two m-tiles share a
+#   B slice), streaming G=1; ragged M / K / N edges in each
+CLASS_SHAPES = [(64, 147, 19008), (200, 72, 19080), (512, 128, 18944), (100, 576, 19000),  # resident
+                (512, 200, 9600), (300, 264, 9480), (1024, 256, 4800),                       # stream, G=2
+                (128, 1152, 2048), (96, 2304, 1000)]                                         # stream, G=1
+
+
+@pytest.mark.parametrize("M,K,N", CLASS_SHAPES)
+def test_spmma_every_launch_class(spfy, orc, cuda, M, K, N):
+    a_bits = rand_bits(orc, 0, (M, K), seed=M * 3 + K)
+    b_bits = rand_bits(orc, 0, (K, N), seed=N)
+    pr = orc.prune24_strip(0, a_bits, want_mask=False)
+    want = orc.spmma_f64(0, pr["dense"], b_bits)
+    comp = spfy.prune24(to_dev(a_bits, 0, cuda))
+    d = spfy.spmma_compressed(comp, to_dev(b_bits, 0, cuda))
+    assert rel_err(d.float().cpu().numpy().astype(np.float64), want) <= REL_TOL
+
+
+def test_spmma_plan_matches_single_calls_and_oracle(spfy, orc, cuda):
+    """grouped persistent launch over a mixed list (all three classes, both opB, alpha/beta, bf16 is a
+    separate plan): every output must equal the single-call result bit for bit and the oracle within tol."""
+    shapes = [(64, 147, 19008), (512, 128, 18944), (256, 64, 20000), (512, 200, 1600), (1024, 256, 1200),
+              (128, 1152, 520), (256, 2304, 392), (2048, 512, 264), (64, 576, 19000), (130, 260, 264)]
+    problems, singles, wants = [], [], []
+    for i, (M, K, N) in enumerate(shapes):
+        a_bits = rand_bits(orc, 0, (M, K), seed=500 + i)
+        op_t = i % 4 == 3
+        b_bits = rand_bits(orc, 0, (N, K) if op_t else (K, N), seed=600 + i)
+        alpha, beta = (0.5, 0.25) if i % 3 == 1 else (1.0, 0.0)
+        c_bits = rand_bits(orc, 0, (M, N), seed=700 + i) if beta else None
+        pr = orc.prune24_strip(0, a_bits, want_mask=False)
+        wants.append(orc.spmma_f64(0, pr["dense"], b_bits, c_bits=c_bits, alpha=alpha, beta=beta, op_b=int(op_t)))
+        comp = spfy.prune24(to_dev(a_bits, 0, cuda))
+        b = to_dev(b_bits, 0, cuda)
+        c = to_dev(c_bits, 0, cuda) if beta else None
+        op_b = spfy.OP_T if op_t else spfy.OP_N
+        singles.append(spfy.spmma_compressed(comp, b, c=c, alpha=alpha, beta=beta, op_b=op_b))
+        problems.append(dict(comp=comp, b=b, c=c, out=torch.zeros(M, N, dtype=torch.float16, device=cuda), alpha=alpha,
+                             beta=beta, op_b=op_b))
+    plan = spfy.SpmmaPlan(problems)
+    assert 1 <= plan.launches <= 6
+    before = spfy.launch_count()
+    plan.run()
+    plan.run()  # a plan is reusable
+    torch.cuda.synchronize()
+    assert spfy.launch_count() - before == 2 * plan.launches
+    for q, single, want in zip(problems, singles, wants):
+        assert torch.equal(q["out"], single)
+        assert rel_err(q["out"].float().cpu().numpy().astype(np.float64), want) <= REL_TOL
+    plan.close()
+
+
+def test_spmma_plan_resnet18_table(spfy, cuda):
+    """BASELINE config 1 end to end at reduced batch: every layer of datasets/resnet18.csv through the
+    batched prune + plan path equals a dense matmul of the pruned weights."""
+    torch.manual_seed(1)
+    gemms = [spfy.shapes.to_gemm(s, "weights", 2) for s in spfy.shapes.read_shapes("resnet18.csv")]
+    ws = [(torch.rand(g.M, g.K, device=cuda) * 2 - 1).half() for g in gemms]
+    comps = [spfy.alloc_compressed(torch.float16, g.M, g.K, cuda) for g in gemms]
+    spfy.prune24_batched(ws, comps)
+    problems = []
+    for g, comp in zip(gemms, comps):
+        b = torch.randint(-2, 3, (g.K, g.N), device=cuda).half()
+        problems.append(dict(comp=comp, b=b, out=torch.empty(g.M, g.N, dtype=torch.float16, device=cuda)))
+    plan = spfy.SpmmaPlan(problems)
+    plan.run()
+    torch.cuda.synchronize()
+    for w, q in zip(ws, problems):
+        wd = torch.empty_like(w)
+        spfy.prune24(w, out_dense=wd, compress=False)
+        ref = wd.float() @ q["b"].float()
+        assert float((q["out"].float() - ref).abs().max() / ref.abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("M,K,N", [(128, 256, 256), (64, 147 + 5, 520), (256, 1024, 136)])
 def test_spmma_transposed_b(spfy, orc, cuda, M, K, N):
     a_bits = rand_bits(orc, 0, (M, K), seed=91)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warm", action="store_true", help="no L2 flush between launches")
     ap.add_argument("--tag", default="")
     ap.add_argument("--only", default="", help="M,K,N filter")
+    ap.add_argument("--plan", action="store_true", help="also time the whole table as ONE plan (grouped launches)")
     args = ap.parse_args()
     import torch
     spfy = ge.load_package()
@@ -69,6 +70,29 @@ def main():
               f"{fl/us/1e6/tc:.3f},{roof:.1f},{roof/us:.3f}")
         del w, b, d, comp
     print(f"# {args.tag} total {tot_t:.0f} us vs roofline {tot_r:.0f} us -> {tot_r/tot_t:.3f}")
+    if args.plan:
+        gemms = [spfy.shapes.to_gemm(s, "weights", args.batch) for s in spfy.shapes.read_shapes(args.csv)]
+        problems = []
+        for g in gemms:
+            w = (torch.rand(g.M, g.K, device=dev) * 2 - 1).to(tdt)
+            problems.append(dict(comp=spfy.prune24(w), b=(torch.rand(g.K, g.N, device=dev) * 2 - 1).to(tdt),
+                                 out=torch.empty(g.M, g.N, device=dev, dtype=tdt)))
+        plan = spfy.SpmmaPlan(problems)
+        for _ in range(3):
+            plan.run()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.reps):
+            e0.record()
+            plan.run()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = statistics.median(ts)
+        by = sum(spfy.shapes.spmma_bytes(g) for g in gemms)
+        fl = sum(spfy.shapes.spmma_flops(g) for g in gemms)
+        print(f"# {args.tag} PLAN {len(gemms)} layers in {plan.launches} launches: {us:.0f} us, {by/us/1e3:.0f} GB/s "
+              f"({by/us/1e3/hbm:.3f} of HBM), {fl/us/1e6:.1f} TFLOP/s, roofline {tot_r:.0f} us -> {tot_r/us:.3f}")
 
 
 if __name__ == "__main__":
