@@ -168,6 +168,10 @@ SPFY_API int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problem
                                     spfy_spmma_plan_t* plan);
 SPFY_API int spfy_spmma_plan_run(spfy_spmma_plan_t plan, spfy_stream_t stream);
 SPFY_API int spfy_spmma_plan_launches(spfy_spmma_plan_t plan); /* kernel launches per run */
+/* introspection / profiling: run one of the plan's launches, or describe it */
+SPFY_API int spfy_spmma_plan_run_launch(spfy_spmma_plan_t plan, int index, spfy_stream_t stream);
+SPFY_API int spfy_spmma_plan_launch_info(spfy_spmma_plan_t plan, int index, int* problems, int* units,
+                                         int* stages, int* smem_bytes);
 SPFY_API int spfy_spmma_plan_destroy(spfy_spmma_plan_t plan);
 
 /* ------------------------------------------------------------------------

@@ -344,10 +344,11 @@ void orc_compress24(int dtype, const void* in, size_t ld_in, size_t rows, size_t
 // ------------------------------------------------------------------------
 // CANONICAL -> SM100 layout (the device format spfy_spmma consumes; OUR format,
 // documented in DESIGN.md).  m_tiles = ceil(rows/128), k_tiles = ceil(cols/128).
-//   values tile (mt,kt): 128 rows x 64 physical fp16 as two 8 KiB K-slices of 32 halves;
-//       element (r,p) at byte (p>>5)*8192 + r*64 + ((((p&31)>>3) ^ ((r>>1)&3)) << 4) + (p&7)*2
-//       [each slice is the 64-byte-swizzled K-major shared-memory image]
-//   meta tile (mt,kt): 2048 bytes; the 16-bit word holding the 4 nibbles of
+//   tile (mt,kt) sits at index kt*m_tiles + mt in both arrays (k-tile major: the m-tiles that
+//   share one B slice in the GEMM are adjacent, so one bulk copy fetches a pair)
+//   values tile: 128 rows x 64 physical fp16; element (r,p) at byte
+//       r*128 + (((p>>3) ^ (r&7)) << 4) + (p&7)*2         [128B-swizzled K-major smem image]
+//   meta tile: 2048 bytes; the 16-bit word holding the 4 nibbles of
 //       logical columns [16*q, 16*q+16) of in-tile row r  (q = 0..7) sits at
 //       (r>>4)*256 + (q&1)*128 + (r&7)*16 + (q>>1)*4 + ((r>>3)&1)*2
 //       [tcgen05.cp 128x128b image of the kind::f16 sparse-metadata layout]
@@ -362,8 +363,8 @@ void orc_pack_sm100(const void* comp_vals, const uint8_t* meta, size_t rows, siz
   uint8_t* om = (uint8_t*)out_meta;
   for (size_t mt = 0; mt < mt_n; ++mt)
     for (size_t kt = 0; kt < kt_n; ++kt) {
-      uint8_t* vt = ov + (mt * kt_n + kt) * 16384;
-      uint8_t* et = om + (mt * kt_n + kt) * 2048;
+      uint8_t* vt = ov + (kt * mt_n + mt) * 16384;
+      uint8_t* et = om + (kt * mt_n + mt) * 2048;
       for (size_t r = 0; r < 128; ++r) {
         size_t row = mt * 128 + r;
         for (size_t q = 0; q < 8; ++q) {  // 16 logical columns = 4 groups = 8 values
@@ -378,9 +379,8 @@ void orc_pack_sm100(const void* comp_vals, const uint8_t* meta, size_t rows, siz
               v1 = cv[(row * G + g) * 2 + 1];
             }
             word |= (uint16_t)(nib << (4 * j));
-            size_t p = q * 8 + j * 2;  // physical column inside the tile (0..63)
-            // two K-slices of 32 stored halves each; inside a slice the 64-byte swizzle image
-            size_t off = (p >> 5) * 8192 + r * 64 + (((((p & 31) >> 3) ^ ((r >> 1) & 3))) << 4) + (p & 7) * 2;
+            size_t p = q * 8 + j * 2;  // physical column inside the tile
+            size_t off = r * 128 + ((((p >> 3) ^ (r & 7))) << 4) + (p & 7) * 2;
             std::memcpy(vt + off, &v0, 2);
             std::memcpy(vt + off + 2, &v1, 2);
           }

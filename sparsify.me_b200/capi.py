@@ -52,6 +52,8 @@ SIGNATURES = {
     "spfy_spmma_plan_create": (c_int, [c_int, _P, _SZ, POINTER(c_void_p)]),
     "spfy_spmma_plan_run": (c_int, [_P, _P]),
     "spfy_spmma_plan_launches": (c_int, [_P]),
+    "spfy_spmma_plan_run_launch": (c_int, [_P, c_int, _P]),
+    "spfy_spmma_plan_launch_info": (c_int, [_P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "spfy_spmma_plan_destroy": (c_int, [_P]),
     "spfy_threshold_workspace_bytes": (c_int, [_SZ, _SZ, POINTER(_SZ)]),
     "spfy_threshold_to_coo": (c_int, [c_int, _P, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, _P, _P,

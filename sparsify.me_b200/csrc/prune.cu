@@ -88,6 +88,7 @@ struct Prune24Params {
   uint32_t units_per_row;  // 16-column units per row in the iteration domain
   uint32_t G, mb;          // CANONICAL: groups per row, metadata bytes per row
   uint32_t k_tiles;        // SM100: 128-column tiles per row
+  uint32_t m_tiles;        // SM100: 128-row tiles per column
   int layout;
   int vec_in, vec_out, vec_cv;  // 16-byte fast paths allowed
   int tile_order;               // iterate in SM100 tile storage order
@@ -208,10 +209,9 @@ __device__ __forceinline__ void prune24_unit(const Prune24Params& P, size_t t) {
     // ---- compressed values + metadata ----
     if (P.layout == SPFY_LAYOUT_SM100) {
       const uint32_t r = row & 127, q = (c0 & 127) >> 4;
-      const size_t tile = (size_t)(row >> 7) * P.k_tiles + (c0 >> 7);
+      const size_t tile = (size_t)(c0 >> 7) * P.m_tiles + (row >> 7);  // k-tile major
       if (P.comp_vals)
-        *reinterpret_cast<uint4*>(P.comp_vals + tile * 16384 + (q >> 2) * 8192 + r * 64 +
-                                  (((q & 3) ^ ((r >> 1) & 3)) << 4)) =
+        *reinterpret_cast<uint4*>(P.comp_vals + tile * 16384 + r * 128 + ((q ^ (r & 7)) << 4)) =
             make_uint4(cv[0], cv[1], cv[2], cv[3]);
       if (P.meta)
         *reinterpret_cast<uint16_t*>(P.meta + tile * 2048 + (r >> 4) * 256 + (q & 1) * 128 +
@@ -373,6 +373,7 @@ int fill_prune24(Prune24Params* out, int layout, const uint16_t* src, size_t ld_
   P.G = (uint32_t)ceil_div(cols, 4);
   P.mb = (uint32_t)ceil_div(P.G, 2);
   P.k_tiles = (uint32_t)ceil_div(cols, 128);
+  P.m_tiles = (uint32_t)ceil_div(rows, 128);
   const bool sm100_out = layout == SPFY_LAYOUT_SM100 && (comp_vals || meta);
   P.dom_rows = sm100_out ? (uint32_t)round_up(rows, 128) : (uint32_t)rows;
   P.units_per_row = sm100_out ? P.k_tiles * 8 : (uint32_t)ceil_div(cols, 16);

@@ -1,4 +1,4 @@
-// spmma_sm100.cu -- 2:4 structured-sparse GEMM on tcgen05.mma.sp (sm_100a), v2
+// spmma_sm100.cu -- 2:4 structured-sparse GEMM on tcgen05.mma.sp (sm_100a)
 //
 // Replaces cusparseLtMatmul (reference: include/sparsify.me/spmma.hxx:106-114):
 //     D[m x n] = alpha * A(2:4)[m x k] * op(B)[k x n] + beta * C[m x n]
@@ -8,38 +8,43 @@
 //     spfy_spmma_plan_*     a list of independent problems (the per-layer GEMMs of a
 //                           datasets/*.csv table) executed by at most three persistent launches
 //
-// Every ResNet shape is HBM-bound for this operator, and the chip-wide L2->SM throughput is only
-// ~1.9x the HBM bandwidth, so the kernel is built to move every operand byte
-// into an SM as few times as possible:
-//   * work unit = (problem, n-tile of 128 columns, group of G <= 2 m-tiles): one B slice in
-//     shared memory feeds the MMAs of both m-tiles of the group;
+// Every ResNet shape is HBM-bound for this operator.  Two measured facts shape the kernel
+// (DESIGN.md section 4): the chip-wide L2->SM throughput is only ~1.9x the HBM bandwidth, so
+// operand re-reads from L2 are nearly as expensive as DRAM traffic; and one trip of the
+// single-thread producer/MMA handshake costs ~600 cycles whatever it carries, so a ring stage
+// must carry tens of KiB.  Hence:
+//   * work unit = (problem, n-tile of 128 columns, group of G <= 2 m-tiles): one 32 KiB B stage
+//     in shared memory feeds the MMAs of both m-tiles of the group;
 //   * "resident" problems (whole compressed A <= 96 KiB): A values + metadata are loaded into
 //     shared memory once per CTA and problem, the ring then streams B only;
+//   * a stage is 128 logical k and is filled by at most three bulk/TMA operations;
 //   * units are dealt round-robin to the persistent CTAs, so neighbouring CTAs stream
 //     neighbouring B columns at the same time (DRAM page locality, L2 hits for the other m-group).
 //
 // CTA = 320 threads, 1 CTA/SM:
-//   warp 0      producer : cp.async.bulk (A value slices / metadata tiles, pre-swizzled by
+//   warp 0      producer : cp.async.bulk (A value tiles / metadata tiles, pre-swizzled by
 //                          spfy_prune24) + TMA tensor loads (B), one mbarrier per ring stage
 //   warp 1      MMA      : one thread issues tcgen05.cp (metadata smem -> TMEM) and
 //                          tcgen05.mma.sp.cta_group::1.kind::f16 (M128 x N128 x K32);
 //                          tcgen05.commit frees ring stages / publishes accumulators
-//   warps 2-9   epilogue : each warp owns 32 rows x 64 columns of an accumulator:
-//                          tcgen05.ld -> alpha/beta -> fp16/bf16 -> its own swizzled 4 KiB staging
-//                          buffer -> its own TMA store.  No CTA-wide barrier in steady state.
+//   warps 2-9   epilogue : a warp owns 32 rows x 64 columns of an accumulator: tcgen05.ld ->
+//                          alpha/beta -> fp16/bf16 -> its own swizzled 4 KiB staging buffer -> its own
+//                          TMA store.  No CTA-wide barrier in steady state.  Streaming classes
+//                          run 4 of the 8 warps (2 column halves each) to leave room for the ring.
 // TMEM: three 128-column accumulator slots used as a ring over (unit, m-tile) jobs, so the epilogue
 // of one job overlaps the MMAs of the next ones; metadata lives in 16 columns behind them.
 //
 // Operand format (spfy_prune24, layout SPFY_LAYOUT_SM100): tile (mt, kt) covers rows
-// [128mt, 128mt+128) x logical columns [128kt, 128kt+128).  Its 16 KiB value tile is two 8 KiB
-// K-slices (64 logical columns = 32 stored halves = 64 bytes per row), each the exact
-// 64B-swizzled K-major shared-memory image (row r at r*64, 16-byte chunk c at c ^ ((r>>1)&3)); its
-// 2 KiB metadata tile is the exact `tcgen05.cp.128x128b` source image of the kind::f16 sparse
-// metadata layout.
+// [128mt, 128mt+128) x logical columns [128kt, 128kt+128) and sits at index kt*m_tiles + mt
+// (k-tile major, so the m-tiles of a group are adjacent).  A 16 KiB value tile is the exact
+// 128B-swizzled K-major shared-memory image (row r at r*128, 16-byte chunk c at c ^ (r&7)); a 2 KiB
+// metadata tile is the exact `tcgen05.cp.128x128b` source image of the kind::f16 sparse-metadata
+// TMEM layout.
 #include "common.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 
+#include <cstdlib>
 #include <vector>
 
 namespace spfy {
@@ -47,11 +52,11 @@ namespace {
 
 constexpr int BM = 128;              // rows of A per m-tile (UMMA M)
 constexpr int BN = 128;              // columns of B/D per unit (UMMA N)
-constexpr int BK = 64;               // logical K per ring stage (2 MMAs of K=32)
-constexpr int MAX_G = 2;             // m-tiles that share one B slice
-constexpr int A_SLICE_BYTES = 8192;  // 128 rows x 64 bytes
+constexpr int BK = 128;              // logical K per ring stage (4 MMAs of K=32)
+constexpr int MAX_G = 2;             // m-tiles that share one B stage
+constexpr int A_TILE_BYTES = 16384;  // 128 rows x 128 bytes
 constexpr int E_TILE_BYTES = 2048;   // metadata of 128 rows x 128 logical k
-constexpr int B_SLICE_BYTES = BK * BN * 2;
+constexpr int B_STAGE_BYTES = BK * BN * 2;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
 constexpr int C_BUF_BYTES = 32 * 128;  // one epilogue warp: 32 rows x 64 columns x 2 bytes
@@ -68,16 +73,19 @@ constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 // one GEMM as the kernel sees it (lives in kernel-parameter space for spfy_spmma, in a device
 // table for plans; the tensor maps must be 64-byte aligned)
 struct alignas(64) ProblemDev {
-  CUtensorMap tmap_b;  // B: OPB_N -> [k][n] boxes (64 n, 64 k); OPB_T -> [n][k] boxes (64 k, 128 n)
+  // B.  b3d: viewed as [groups of 64 inner elements][outer rows][64]: one box (64, 128, 2) fills a
+  // whole stage; otherwise 2-D with two (64, 128) boxes per stage.
+  CUtensorMap tmap_b;
   CUtensorMap tmap_d;  // D: [m][n] boxes (64 n, 32 m)
   const uint8_t* a_vals;
   const uint8_t* a_meta;
   const void* C;       // only read when beta != 0
   uint64_t ldc;
   uint32_t m, n, k;
-  uint32_t m_tiles, k_tiles, k_slices, n_tiles, m_groups;
+  uint32_t m_tiles, k_tiles, n_tiles, m_groups;
   uint32_t G;          // m-tiles per unit
   uint32_t resident;   // whole A lives in shared memory
+  uint32_t b3d;
   uint32_t unit_begin, units;  // this problem's range in the launch-wide unit order
   float alpha, beta;
   uint64_t hint_b;
@@ -89,9 +97,11 @@ struct LaunchParams {
   uint32_t total_units;
   uint32_t idesc;
   // shared-memory geometry of this launch
-  uint32_t stages, stage_bytes, a_off, e_off;  // ring stage: [B slice][A slice x G][E tile x G]
+  uint32_t stages, stage_bytes, a_off, e_off;  // ring stage: [B 32 KiB][A tile x G][E tile x G]
   uint32_t res_off, res_e_off;                 // resident A values / metadata
   uint32_t c_off, bar_off;
+  uint32_t epi_warps;  // 8: one column half per warp; 4: warps 2-5 do both halves
+  uint32_t dbg;        // development switches (SPFY_SPMMA_DEBUG): 2 no epilogue work, 4 no B loads, 8 no MMAs
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -151,6 +161,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes,
@@ -241,7 +259,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
          (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32 | (uint64_t)1 << 46 |
          (uint64_t)layout_type << 61;
 }
-constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_NONE = 0;
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_NONE = 0;
 
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -284,11 +302,6 @@ struct UnitWalker {
     return prob(p);
   }
   __device__ __forceinline__ void next() { u += gridDim.x; }
-  // is the current unit this CTA's last one inside problem P?
-  __device__ __forceinline__ bool last_of_problem(const ProblemDev* P) const {
-    const uint32_t nu = u + gridDim.x;
-    return nu >= total_units || nu >= P->unit_begin + P->units;
-  }
 };
 
 // ------------------------------------------------------------------- kernel
@@ -317,7 +330,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     }
     for (int a = 0; a < ACC_SLOTS; ++a) {
       mbar_init(bar_acc_full + a * 8, 1);
-      mbar_init(bar_acc_empty + a * 8, NUM_EPI_WARPS);  // every epilogue warp reads a part of every job
+      mbar_init(bar_acc_empty + a * 8, L.epi_warps);  // every active epilogue warp reads a part of every job
     }
     mbar_init(bar_res_full, 1);
     mbar_init(bar_res_empty, 1);
@@ -330,228 +343,271 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   UnitWalker W(&single, L);
+  // NOTE on the role loops: every PTX wrapper is an `asm volatile` with a "memory" clobber, so
+  // anything read through a pointer inside a loop is re-loaded on every trip.  The single-thread
+  // producer / MMA loops are latency-bound scalar code, so all per-problem and per-unit state is
+  // copied into registers first and the ring position is advanced without divisions.
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      uint32_t it = 0;         // ring position (continuous over units)
-      uint32_t res_loads = 0;  // resident (re)loads issued so far
+      uint32_t stage = 0, phase = 0;  // ring position (continuous over units)
+      uint32_t res_loads = 0;         // resident (re)loads issued so far
       const ProblemDev* res_owner = nullptr;
       const ProblemDev* last = nullptr;
+      const CUtensorMap* tmap_b = nullptr;
+      const uint8_t *a_vals = nullptr, *a_meta = nullptr;
+      uint32_t pm = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, b3d = 0;
+      uint64_t hint_b = 0;
+      const bool no_b = (L.dbg & 4u) != 0;
       for (; W.valid(); W.next()) {
         const ProblemDev* P = W.current();
         if (P != last) {
-          prefetch_tmap(&P->tmap_b);
           last = P;
+          tmap_b = &P->tmap_b;
+          prefetch_tmap(tmap_b);
+          a_vals = P->a_vals; a_meta = P->a_meta;
+          pm = P->m; k_tiles = P->k_tiles; m_tiles = P->m_tiles; b3d = P->b3d;
+          m_groups = P->m_groups; G = P->G; resident = P->resident; unit_begin = P->unit_begin;
+          hint_b = P->hint_b;
         }
-        const uint32_t local = W.u - P->unit_begin;
-        const uint32_t nt = local / P->m_groups, mg = local - nt * P->m_groups;
-        const uint32_t mt0 = mg * P->G;
-        const uint32_t g_count = min(P->G, P->m_tiles - mt0);
-        if (P->resident && res_owner != P) {
+        const uint32_t local = W.u - unit_begin;
+        const uint32_t nt = local / m_groups, mg = local - nt * m_groups;
+        const uint32_t mt0 = mg * G;
+        const uint32_t g_count = min(G, m_tiles - mt0);
+        if (resident && res_owner != P) {
           // (re)load the whole compressed A of this problem into the resident region
           mbar_wait(bar_res_empty, (res_loads & 1u) ^ 1u);
-          uint32_t bytes = 0;
-          for (uint32_t mt = 0; mt < P->m_tiles; ++mt) {
-            const uint32_t rv = rows_valid_of(P->m, mt);
-            bytes += rv * 64u * P->k_slices + rv * 16u * P->k_tiles;
-          }
-          mbar_expect_tx(bar_res_full, bytes);
-          for (uint32_t mt = 0; mt < P->m_tiles; ++mt) {
-            const uint32_t rv = rows_valid_of(P->m, mt);
-            for (uint32_t ks = 0; ks < P->k_slices; ++ks)
-              bulk_load_1d(smem_base + L.res_off + (mt * P->k_slices + ks) * A_SLICE_BYTES,
-                           P->a_vals + ((size_t)mt * P->k_tiles * 2 + ks) * A_SLICE_BYTES, rv * 64u,
+          if (m_tiles == 1) {
+            // a single, possibly short, m-tile: compact rows, one copy per k-tile and array
+            const uint32_t rv = rows_valid_of(pm, 0);
+            mbar_expect_tx(bar_res_full, k_tiles * rv * 144u);
+            for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+              bulk_load_1d(smem_base + L.res_off + kt * rv * 128u, a_vals + (size_t)kt * A_TILE_BYTES, rv * 128u,
                            bar_res_full, HINT_EVICT_LAST);
-            for (uint32_t kt = 0; kt < P->k_tiles; ++kt)
-              bulk_load_1d(smem_base + L.res_e_off + (mt * P->k_tiles + kt) * E_TILE_BYTES,
-                           P->a_meta + ((size_t)mt * P->k_tiles + kt) * E_TILE_BYTES, rv * 16u,
+              bulk_load_1d(smem_base + L.res_e_off + kt * rv * 16u, a_meta + (size_t)kt * E_TILE_BYTES, rv * 16u,
                            bar_res_full, HINT_EVICT_LAST);
+            }
+          } else {
+            // the arrays are contiguous (padding rows included): two copies fetch everything
+            const uint32_t tiles = k_tiles * m_tiles;
+            mbar_expect_tx(bar_res_full, tiles * (uint32_t)(A_TILE_BYTES + E_TILE_BYTES));
+            bulk_load_1d(smem_base + L.res_off, a_vals, tiles * A_TILE_BYTES, bar_res_full, HINT_EVICT_LAST);
+            bulk_load_1d(smem_base + L.res_e_off, a_meta, tiles * E_TILE_BYTES, bar_res_full, HINT_EVICT_LAST);
           }
           res_owner = P;
           ++res_loads;
         }
-        for (uint32_t ks = 0; ks < P->k_slices; ++ks, ++it) {
-          const uint32_t stage = it % NS, phase = (it / NS) & 1u;
+        // per-unit registers: the G tiles of a k-tile are adjacent, so one copy per array and stage
+        const uint32_t rv0 = rows_valid_of(pm, mt0);
+        const uint32_t rv1 = g_count > 1 ? rows_valid_of(pm, mt0 + 1) : 0u;
+        const uint32_t a_bytes = g_count > 1 ? (uint32_t)A_TILE_BYTES + rv1 * 128u : rv0 * 128u;
+        const uint32_t e_bytes = g_count > 1 ? (uint32_t)E_TILE_BYTES + rv1 * 16u : rv0 * 16u;
+        const uint8_t* av = a_vals + (size_t)mt0 * A_TILE_BYTES;
+        const uint8_t* am = a_meta + (size_t)mt0 * E_TILE_BYTES;
+        const size_t av_step = (size_t)m_tiles * A_TILE_BYTES, am_step = (size_t)m_tiles * E_TILE_BYTES;
+        const uint32_t tx = (no_b ? 0u : (uint32_t)B_STAGE_BYTES) + (resident ? 0u : a_bytes + e_bytes);
+        for (uint32_t kt = 0; kt < k_tiles; ++kt) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1u);
           const uint32_t full = bar_full + stage * 8;
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
-          uint32_t tx = B_SLICE_BYTES;
-          if (!P->resident) {
-            for (uint32_t g = 0; g < g_count; ++g) {
-              const uint32_t rv = rows_valid_of(P->m, mt0 + g);
-              tx += rv * 64u + ((ks & 1u) ? 0u : rv * 16u);
-            }
+          if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
+          if (!resident) {
+            bulk_load_1d(sbase + L.a_off, av, a_bytes, full, HINT_EVICT_LAST);
+            bulk_load_1d(sbase + L.e_off, am, e_bytes, full, HINT_EVICT_LAST);
+            av += av_step;
+            am += am_step;
           }
-          mbar_expect_tx(full, tx);
-          if (!P->resident) {
-            for (uint32_t g = 0; g < g_count; ++g) {
-              const uint32_t mt = mt0 + g, rv = rows_valid_of(P->m, mt);
-              bulk_load_1d(sbase + L.a_off + g * A_SLICE_BYTES,
-                           P->a_vals + ((size_t)mt * P->k_tiles * 2 + ks) * A_SLICE_BYTES, rv * 64u, full,
-                           HINT_EVICT_LAST);
-              if (!(ks & 1u))
-                bulk_load_1d(sbase + L.e_off + g * E_TILE_BYTES,
-                             P->a_meta + ((size_t)mt * P->k_tiles + (ks >> 1)) * E_TILE_BYTES, rv * 16u, full,
-                             HINT_EVICT_LAST);
-            }
-          }
-          if (!OPB_T) {
-            // B is k x n row-major: two boxes of [64 rows of k][64 columns of n] -> MN-major SW128
-            tma_load_2d(sbase, &P->tmap_b, (int)(nt * BN), (int)(ks * BK), full, P->hint_b);
-            tma_load_2d(sbase + BK * 128, &P->tmap_b, (int)(nt * BN + 64), (int)(ks * BK), full, P->hint_b);
+          if (no_b) {
+          } else if (b3d) {
+            // one box fills the stage: [2 groups of 64][128 outer rows][64]
+            if (!OPB_T) tma_load_3d(sbase, tmap_b, 0, (int)(kt * BK), (int)(nt * 2), full, hint_b);
+            else        tma_load_3d(sbase, tmap_b, 0, (int)(nt * BN), (int)(kt * 2), full, hint_b);
+          } else if (!OPB_T) {
+            // B is k x n row-major: boxes of [128 rows of k][64 columns of n] -> MN-major SW128
+            tma_load_2d(sbase, tmap_b, (int)(nt * BN), (int)(kt * BK), full, hint_b);
+            tma_load_2d(sbase + BK * 128, tmap_b, (int)(nt * BN + 64), (int)(kt * BK), full, hint_b);
           } else {
-            // B is n x k row-major: one box of [128 rows of n][64 columns of k] -> K-major SW128
-            tma_load_2d(sbase, &P->tmap_b, (int)(ks * BK), (int)(nt * BN), full, P->hint_b);
+            // B is n x k row-major: boxes of [128 rows of n][64 columns of k] -> K-major SW128
+            tma_load_2d(sbase, tmap_b, (int)(kt * BK), (int)(nt * BN), full, hint_b);
+            tma_load_2d(sbase + BN * 128, tmap_b, (int)(kt * BK + 64), (int)(nt * BN), full, hint_b);
           }
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t it = 0, job = 0, eblk = 0, res_loads = 0;
+      uint32_t stage = 0, phase = 0, job = 0, eblk = 0, res_loads = 0;
       const ProblemDev* res_owner = nullptr;
+      const ProblemDev* last = nullptr;
+      uint32_t pm = 0, pk = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, units = 0;
+      const bool no_mma = (L.dbg & 8u) != 0;
+      // constant halves of the shared-memory descriptors (the start address is OR-ed in per MMA)
+      const uint64_t desc_a_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      const uint64_t desc_b_hi = OPB_T ? make_smem_desc(0, 16, 1024, LAYOUT_SW128)
+                                       : make_smem_desc(0, BK * 128, 1024, LAYOUT_SW128);
+      const uint64_t desc_e_hi = make_smem_desc(0, 16, 128, LAYOUT_NONE);
       for (; W.valid(); W.next()) {
         const ProblemDev* P = W.current();
-        const uint32_t local = W.u - P->unit_begin;
-        const uint32_t mg = local % P->m_groups;
-        const uint32_t mt0 = mg * P->G;
-        const uint32_t g_count = min(P->G, P->m_tiles - mt0);
-        if (P->resident && res_owner != P) {
+        if (P != last) {
+          last = P;
+          pm = P->m; pk = P->k; k_tiles = P->k_tiles; m_tiles = P->m_tiles;
+          m_groups = P->m_groups; G = P->G; resident = P->resident; unit_begin = P->unit_begin; units = P->units;
+        }
+        const uint32_t local = W.u - unit_begin;
+        const uint32_t mg = local % m_groups;
+        const uint32_t mt0 = mg * G;
+        const uint32_t g_count = min(G, m_tiles - mt0);
+        if (resident && res_owner != P) {
           mbar_wait(bar_res_full, res_loads & 1u);
           res_owner = P;
           ++res_loads;
         }
         // accumulator slots of this unit's jobs
-        uint32_t slot[MAX_G] = {0, 0};
-#pragma unroll
-        for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g) {
-          if (g < g_count) {
-            const uint32_t a = job + g;
-            slot[g] = a % ACC_SLOTS;
-            mbar_wait(bar_acc_empty + slot[g] * 8, ((a / ACC_SLOTS) & 1u) ^ 1u);
-          }
-        }
+        const uint32_t slot0 = job % ACC_SLOTS, use0 = job / ACC_SLOTS;
+        const uint32_t slot1 = (job + 1) % ACC_SLOTS, use1 = (job + 1) / ACC_SLOTS;
+        mbar_wait(bar_acc_empty + slot0 * 8, (use0 & 1u) ^ 1u);
+        if (g_count > 1) mbar_wait(bar_acc_empty + slot1 * 8, (use1 & 1u) ^ 1u);
         tc_fence_after();
-        uint32_t ecol[MAX_G] = {0, 0};
-        for (uint32_t ks = 0; ks < P->k_slices; ++ks, ++it) {
-          const uint32_t stage = it % NS, phase = (it / NS) & 1u;
+        const uint32_t tmem_d0 = tmem_base + slot0 * BN, tmem_d1 = tmem_base + slot1 * BN;
+        // resident operands: tile (kt, mt) at (kt*m_tiles + mt) * stride
+        const uint32_t rv_single = rows_valid_of(pm, 0);
+        const uint32_t rsv = m_tiles == 1 ? rv_single * 128u : (uint32_t)A_TILE_BYTES;
+        const uint32_t rse = m_tiles == 1 ? rv_single * 16u : (uint32_t)E_TILE_BYTES;
+        uint32_t ra = smem_base + L.res_off + mt0 * rsv, re = smem_base + L.res_e_off + mt0 * rse;
+        uint32_t k_left = pk;
+        for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= BK, ra += m_tiles * rsv, re += m_tiles * rse) {
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
-          if (!(ks & 1u)) {
-            // metadata of the next 128 logical k (this slice and the following one) -> TMEM
+          // metadata of these 128 logical k -> TMEM (4 columns per m-tile)
+          const uint32_t ecol0 = tmem_base + TMEM_E_COL + (eblk & 1u) * (MAX_G * 4u), ecol1 = ecol0 + 4u;
+          ++eblk;
+          const uint32_t e0 = resident ? re : sbase + L.e_off;
+          const uint32_t sa0 = resident ? ra : sbase + L.a_off;
+          tc_cp_128x128b(ecol0, desc_e_hi | (uint64_t)((e0 >> 4) & 0x3fffu));
+          if (g_count > 1)
+            tc_cp_128x128b(ecol1, desc_e_hi | (uint64_t)(((e0 + (resident ? rse : (uint32_t)E_TILE_BYTES)) >> 4) & 0x3fffu));
+          const uint32_t sa1 = sa0 + (resident ? rsv : (uint32_t)A_TILE_BYTES);
+          const uint32_t nk = k_left >= (uint32_t)BK ? 4u : (k_left + 31u) / 32u;
+          if (!no_mma) {
 #pragma unroll
-            for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g) {
-              if (g < g_count) {
-                ecol[g] = tmem_base + TMEM_E_COL + ((eblk & 1u) * MAX_G + g) * 4u;
-                const uint32_t esrc =
-                    P->resident ? smem_base + L.res_e_off + ((mt0 + g) * P->k_tiles + (ks >> 1)) * E_TILE_BYTES
-                                : sbase + L.e_off + g * E_TILE_BYTES;
-                tc_cp_128x128b(ecol[g], make_smem_desc(esrc, 16, 128, LAYOUT_NONE));
-              }
-            }
-            ++eblk;
-          }
-          const uint32_t k_left = P->k - ks * BK;
-          const uint32_t nk = k_left >= (uint32_t)BK ? 2u : (k_left + 31u) / 32u;
-#pragma unroll
-          for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g) {
-            if (g < g_count) {
-              const uint32_t sa = P->resident
-                                      ? smem_base + L.res_off + ((mt0 + g) * P->k_slices + ks) * A_SLICE_BYTES
-                                      : sbase + L.a_off + g * A_SLICE_BYTES;
-              const uint32_t tmem_d = tmem_base + slot[g] * BN;
-#pragma unroll
-              for (uint32_t j = 0; j < 2; ++j) {
-                if (j < nk) {
-                  // A: K-major SW64, 32 logical = 16 stored halves = 32 bytes per MMA
-                  const uint64_t da = make_smem_desc(sa + j * 32, 16, 512, LAYOUT_SW64);
-                  uint64_t db;
-                  if (!OPB_T)  // MN-major SW128: 8 k-rows per 1024 B atom, 64-column groups BK*128 apart
-                    db = make_smem_desc(sbase + j * 32 * 128, BK * 128, 1024, LAYOUT_SW128);
-                  else         // K-major SW128: 64 bytes (32 k) per MMA inside a 128-byte row
-                    db = make_smem_desc(sbase + j * 64, 16, 1024, LAYOUT_SW128);
-                  const uint32_t col = ecol[g] + (ks & 1u) * 2u + j;
-                  tc_mma_sp_f16(tmem_d, da, db, col & ~1u, L.idesc | (col & 1u), (ks | j) != 0);
+            for (uint32_t j = 0; j < 4; ++j) {
+              if (j < nk) {
+                // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
+                // B: MN-major SW128 (8 k-rows per 1024 B atom, 64-column groups BK*128 apart) or
+                //    K-major SW128 (two 64-wide k halves, 64 bytes per MMA inside a row)
+                const uint32_t sb = OPB_T ? sbase + (j >> 1) * (BN * 128) + (j & 1u) * 64u : sbase + j * (32u * 128u);
+                const uint64_t db = desc_b_hi | (uint64_t)((sb >> 4) & 0x3fffu);
+                const uint32_t col0 = ecol0 + j;
+                tc_mma_sp_f16(tmem_d0, desc_a_hi | (uint64_t)(((sa0 + j * 32u) >> 4) & 0x3fffu), db, col0 & ~1u,
+                              L.idesc | (col0 & 1u), (kt | j) != 0);
+                if (g_count > 1) {
+                  const uint32_t col1 = ecol1 + j;
+                  tc_mma_sp_f16(tmem_d1, desc_a_hi | (uint64_t)(((sa1 + j * 32u) >> 4) & 0x3fffu), db, col1 & ~1u,
+                                L.idesc | (col1 & 1u), (kt | j) != 0);
                 }
               }
             }
           }
           tc_commit(bar_empty + stage * 8);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
-#pragma unroll
-        for (uint32_t g = 0; g < (uint32_t)MAX_G; ++g)
-          if (g < g_count) tc_commit(bar_acc_full + slot[g] * 8);
+        tc_commit(bar_acc_full + slot0 * 8);
+        if (g_count > 1) tc_commit(bar_acc_full + slot1 * 8);
         job += g_count;
-        if (P->resident && W.last_of_problem(P)) {
+        const uint32_t nu = W.u + gridDim.x;
+        if (resident && (nu >= L.total_units || nu >= unit_begin + units)) {
           tc_commit(bar_res_empty);  // every MMA that reads the resident region has completed
           res_owner = nullptr;
         }
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..9) =====================
+  } else if (warp - 2 < L.epi_warps) {
+    // ===================== epilogue (warps 2..9, or 2..5 doing both column halves) =====================
     const uint32_t e = warp - 2;
     const uint32_t quarter = warp & 3u;  // TMEM lanes this warp may read: [32*quarter, 32*quarter+32)
-    const uint32_t half = e >> 2;        // column half of the accumulator
+    const uint32_t halves = L.epi_warps == (uint32_t)NUM_EPI_WARPS ? 1u : 2u;
+    const uint32_t half0 = halves == 1u ? (e >> 2) : 0u;
     const uint32_t row_in_tile = quarter * 32 + lane;
     const uint32_t sc = smem_base + L.c_off + e * C_BUF_BYTES;
+    const uint32_t st_base = sc + lane * 128;
+    const uint32_t sw = lane & 7u;
+    const bool no_epi = (L.dbg & 2u) != 0;
     uint32_t job = 0;
+    const ProblemDev* last = nullptr;
+    const CUtensorMap* tmap_d = nullptr;
+    const uint16_t* Cptr = nullptr;
+    uint64_t ldc = 0;
+    uint32_t pm = 0, pn = 0, m_tiles = 0, m_groups = 1, G = 1, unit_begin = 0;
+    float alpha = 1.f, beta = 0.f;
     for (; W.valid(); W.next()) {
       const ProblemDev* P = W.current();
-      const uint32_t local = W.u - P->unit_begin;
-      const uint32_t nt = local / P->m_groups, mg = local - nt * P->m_groups;
-      const uint32_t mt0 = mg * P->G;
-      const uint32_t g_count = min(P->G, P->m_tiles - mt0);
-      const float alpha = P->alpha, beta = P->beta;
+      if (P != last) {
+        last = P;
+        tmap_d = &P->tmap_d;
+        Cptr = reinterpret_cast<const uint16_t*>(P->C);
+        ldc = P->ldc;
+        pm = P->m; pn = P->n; m_tiles = P->m_tiles; m_groups = P->m_groups; G = P->G; unit_begin = P->unit_begin;
+        alpha = P->alpha; beta = P->beta;
+      }
+      const uint32_t local = W.u - unit_begin;
+      const uint32_t nt = local / m_groups, mg = local - nt * m_groups;
+      const uint32_t mt0 = mg * G;
+      const uint32_t g_count = min(G, m_tiles - mt0);
       for (uint32_t g = 0; g < g_count; ++g, ++job) {
         const uint32_t slot = job % ACC_SLOTS;
-        const uint32_t m0 = (mt0 + g) * BM, n0 = nt * BN + half * 64;
-        const bool warp_has_rows = m0 + quarter * 32 < P->m && n0 < P->n;
+        const uint32_t m0 = (mt0 + g) * BM;
         mbar_wait(bar_acc_full + slot * 8, (job / ACC_SLOTS) & 1u);
         tc_fence_after();
-        uint32_t acc[64];
-        if (warp_has_rows) {
-          const uint32_t taddr = tmem_base + slot * BN + half * 64 + ((quarter * 32) << 16);
-          tmem_ld_x32(taddr, acc);
-          tmem_ld_x32(taddr + 32, acc + 32);
-          tmem_wait_ld();
-        }
-        // accumulator read: hand the slot back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
-        if (warp_has_rows) {
-          if (lane == 0) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
-          __syncwarp();
-          const uint32_t grow = m0 + row_in_tile;
-          const bool use_c = beta != 0.f && grow < P->m;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float v[8];
-#pragma unroll
-            for (int x = 0; x < 8; ++x) v[x] = alpha * __uint_as_float(acc[q * 8 + x]);
-            if (use_c && n0 + q * 8 < P->n) {
-              const uint4 cw = *reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const uint16_t*>(P->C) + (size_t)grow * P->ldc + n0 + q * 8);
-              const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
-#pragma unroll
-              for (int x = 0; x < 4; ++x) {
-                const float2 f = unpack2<BF16>(cws[x]);
-                v[2 * x] += beta * f.x;
-                v[2 * x + 1] += beta * f.y;
-              }
-            }
-            st_shared_v4(sc + lane * 128 + ((q ^ (lane & 7)) << 4), pack2<BF16>(v[0], v[1]),
-                         pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
+        for (uint32_t hh = 0; hh < halves; ++hh) {
+          const uint32_t half = half0 + hh;
+          const uint32_t n0 = nt * BN + half * 64;
+          const bool warp_has_rows = m0 + quarter * 32 < pm && n0 < pn;
+          uint32_t acc[64];
+          if (warp_has_rows) {
+            const uint32_t taddr = tmem_base + slot * BN + half * 64 + ((quarter * 32) << 16);
+            tmem_ld_x32(taddr, acc);
+            tmem_ld_x32(taddr + 32, acc + 32);
+            tmem_wait_ld();
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&P->tmap_d, sc, (int)n0, (int)(m0 + quarter * 32));
-            bulk_commit();
+          if (hh + 1 == halves) {
+            // accumulator fully read by this warp: hand the slot back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
+          }
+          if (warp_has_rows && !no_epi) {
+            if (lane == 0) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
+            __syncwarp();
+            const uint32_t grow = m0 + row_in_tile;
+            const bool use_c = beta != 0.f && grow < pm;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float v[8];
+#pragma unroll
+              for (int x = 0; x < 8; ++x) v[x] = alpha * __uint_as_float(acc[q * 8 + x]);
+              if (use_c && n0 + q * 8 < pn) {
+                const uint4 cw = *reinterpret_cast<const uint4*>(Cptr + (size_t)grow * ldc + n0 + q * 8);
+                const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  const float2 f = unpack2<BF16>(cws[x]);
+                  v[2 * x] += beta * f.x;
+                  v[2 * x + 1] += beta * f.y;
+                }
+              }
+              st_shared_v4(st_base + ((q ^ sw) << 4), pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]),
+                           pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(tmap_d, sc, (int)n0, (int)(m0 + quarter * 32));
+              bulk_commit();
+            }
           }
         }
       }
@@ -607,6 +663,28 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t inner, 
   return SPFY_OK;
 }
 
+// The same matrix (inner % 64 == 0) viewed as [inner/64 groups][outer][64]: a box of
+// (64, box_outer, 2) lands in shared memory as two consecutive 128B-swizzled (box_outer x 64)
+// blocks -- exactly the two halves of a B stage -- with ONE TMA instruction.
+int make_tmap_grouped(CUtensorMap* map, int dtype, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t ld, uint32_t box_outer) {
+  EncodeTiledFn enc;
+  int rc = get_encoder(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[3] = {64, outer, inner / 64};
+  cuuint64_t strides[2] = {ld * 2, 128};
+  cuuint32_t box[3] = {64, box_outer, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, dtype == SPFY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SPFY_E_CUDA, "cuTensorMapEncodeTiled (grouped) failed (%d) for %llu x %llu ld %llu", (int)r,
+                (unsigned long long)outer, (unsigned long long)inner, (unsigned long long)ld);
+  return SPFY_OK;
+}
+
 struct HostProblem {
   int opB;
   size_t m, n, k;
@@ -642,13 +720,13 @@ int validate(int dtype, const HostProblem& h, const char* who) {
 
 // launch classes: problems of one class share a shared-memory geometry and one launch
 enum { CLASS_RESIDENT = 0, CLASS_STREAM_G1 = 1, CLASS_STREAM_G2 = 2, NUM_CLASSES = 3 };
-constexpr uint32_t C_BYTES = NUM_EPI_WARPS * C_BUF_BYTES;  // 32 KiB
-constexpr uint32_t BAR_BYTES = 256;
+constexpr uint32_t BAR_BYTES = 512;
 constexpr uint32_t RES_MAX_BYTES = 96 * 1024;  // resident A (values + metadata)
 
 size_t resident_bytes(size_t m, size_t k) {
   const size_t m_tiles = ceil_div(m, BM), k_tiles = ceil_div(k, 128);
-  return m_tiles * k_tiles * (2 * A_SLICE_BYTES + E_TILE_BYTES);
+  const size_t rows = m_tiles == 1 ? round_up(m, 16) : 128;
+  return m_tiles * k_tiles * rows * 144;  // 128 B of values + 16 B of metadata per row and k-tile
 }
 
 int classify(const HostProblem& h, bool grouped, int sm_count) {
@@ -663,10 +741,13 @@ int classify(const HostProblem& h, bool grouped, int sm_count) {
 int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   memset(d, 0, sizeof(*d));
   int rc;
-  if (h.opB == SPFY_OP_N)
-    rc = make_tmap_2d(&d->tmap_b, dtype, h.B, h.n, h.k, h.ldb, 64, BK);
-  else
-    rc = make_tmap_2d(&d->tmap_b, dtype, h.B, h.k, h.n, h.ldb, 64, BN);
+  // B: inner = contiguous dimension (n for opB = N, k for opB = T), outer = the other one
+  const size_t b_inner = h.opB == SPFY_OP_N ? h.n : h.k, b_outer = h.opB == SPFY_OP_N ? h.k : h.n;
+  d->b3d = b_inner % 64 == 0;
+  rc = SPFY_OK;
+  if (d->b3d && make_tmap_grouped(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 128) != SPFY_OK)
+    d->b3d = 0;  // the driver refused the grouped view: fall back to two 2-D boxes per stage
+  if (!d->b3d) rc = make_tmap_2d(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 64, 128);
   if (rc) return rc;
   rc = make_tmap_2d(&d->tmap_d, dtype, h.D, h.n, h.m, h.ldd, 64, 32);
   if (rc) return rc;
@@ -679,7 +760,6 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   d->k = (uint32_t)h.k;
   d->m_tiles = (uint32_t)ceil_div(h.m, BM);
   d->k_tiles = (uint32_t)ceil_div(h.k, 128);
-  d->k_slices = (uint32_t)ceil_div(h.k, BK);
   d->n_tiles = (uint32_t)ceil_div(h.n, BN);
   d->resident = cls == CLASS_RESIDENT;
   d->G = (cls == CLASS_STREAM_G1) ? 1u : (d->m_tiles >= 2 ? 2u : 1u);
@@ -693,28 +773,31 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   return SPFY_OK;
 }
 
-// shared-memory geometry of a class
-void geometry(int cls, LaunchParams* L, uint32_t* smem_bytes) {
+// shared-memory geometry of a class; `res_vals` / `res_meta` = bytes of the largest resident problem
+void geometry(int cls, uint32_t res_vals, uint32_t res_meta, LaunchParams* L, uint32_t* smem_bytes) {
   uint32_t stage, res = 0;
-  L->a_off = B_SLICE_BYTES;
+  L->a_off = B_STAGE_BYTES;
   if (cls == CLASS_RESIDENT) {
-    stage = B_SLICE_BYTES;
+    stage = B_STAGE_BYTES;
     L->e_off = stage;
-    res = RES_MAX_BYTES;
+    res = (uint32_t)round_up(res_vals, 1024) + (uint32_t)round_up(res_meta, 1024);
+    L->epi_warps = NUM_EPI_WARPS;  // small K: the epilogue is the hot part
   } else {
     const uint32_t G = cls == CLASS_STREAM_G2 ? 2u : 1u;
-    L->e_off = B_SLICE_BYTES + G * A_SLICE_BYTES;
+    L->e_off = B_STAGE_BYTES + G * A_TILE_BYTES;
     stage = L->e_off + G * E_TILE_BYTES;
+    L->epi_warps = NUM_EPI_WARPS / 2;  // large K: shared memory goes to the ring instead
   }
-  const uint32_t fixed = 1024 /*alignment slack*/ + C_BYTES + BAR_BYTES + res;
+  const uint32_t c_bytes = L->epi_warps * C_BUF_BYTES;
+  const uint32_t fixed = 1024 /*alignment slack*/ + c_bytes + BAR_BYTES + res;
   uint32_t stages = (SMEM_LIMIT - fixed) / stage;
   if (stages > (uint32_t)MAX_STAGES) stages = MAX_STAGES;
   L->stages = stages;
   L->stage_bytes = stage;
   L->res_off = stages * stage;
-  L->res_e_off = L->res_off;  // set per launch: metadata sits behind the largest value block
+  L->res_e_off = L->res_off + (uint32_t)round_up(res_vals, 1024);
   L->c_off = L->res_off + res;
-  L->bar_off = L->c_off + C_BYTES;
+  L->bar_off = L->c_off + c_bytes;
   *smem_bytes = L->bar_off + BAR_BYTES + 1024;
 }
 
@@ -749,7 +832,9 @@ int launch(int dtype, int opB, const ProblemDev& single, const LaunchParams& L, 
                           : launch_t<false, true>(single, L, smem, grid, s);
 }
 
-uint32_t res_values_bytes(const ProblemDev& d) { return d.m_tiles * d.k_slices * A_SLICE_BYTES; }
+uint32_t res_rows(const ProblemDev& d) { return d.m_tiles == 1 ? (uint32_t)round_up(d.m, 16) : 128u; }
+uint32_t res_values_bytes(const ProblemDev& d) { return d.m_tiles * d.k_tiles * res_rows(d) * 128u; }
+uint32_t res_meta_bytes(const ProblemDev& d) { return d.m_tiles * d.k_tiles * res_rows(d) * 16u; }
 
 struct Plan {
   int dtype = 0;
@@ -798,12 +883,15 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
   LaunchParams L;
   memset(&L, 0, sizeof(L));
   uint32_t smem = 0;
-  geometry(cls, &L, &smem);
-  L.res_e_off = L.res_off + res_values_bytes(d);
+  geometry(cls, res_values_bytes(d), res_meta_bytes(d), &L, &smem);
   L.table = nullptr;
   L.num_problems = 1;
   L.total_units = d.units;
   L.idesc = make_idesc(dtype, opB);
+  {
+    const char* e = getenv("SPFY_SPMMA_DEBUG");
+    L.dbg = e ? (uint32_t)atoi(e) : 0u;
+  }
   const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
   return launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
 }
@@ -829,7 +917,7 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
       ln.opB = opB;
       ln.first = (uint32_t)table.size();
       ln.count = 0;
-      uint32_t units = 0, res_vals = 0;
+      uint32_t units = 0, res_vals = 0, res_meta = 0;
       for (size_t i = 0; i < count; ++i) {
         const spfy_spmma_problem& q = problems[i];
         HostProblem h{q.opB, q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
@@ -854,12 +942,12 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
         }
         units += d.units;
         if (d.resident && res_values_bytes(d) > res_vals) res_vals = res_values_bytes(d);
+        if (d.resident && res_meta_bytes(d) > res_meta) res_meta = res_meta_bytes(d);
         table.push_back(d);
         ++ln.count;
       }
       if (!ln.count) continue;
-      geometry(cls, &ln.L, &ln.smem);
-      ln.L.res_e_off = ln.L.res_off + res_vals;
+      geometry(cls, res_vals, res_meta, &ln.L, &ln.smem);
       ln.L.num_problems = ln.count;
       ln.L.total_units = units;
       ln.L.idesc = make_idesc(dtype, opB);
@@ -895,6 +983,31 @@ int spfy_spmma_plan_run(spfy_spmma_plan_t p, spfy_stream_t stream) {
 }
 
 int spfy_spmma_plan_launches(spfy_spmma_plan_t p) { return p ? (int)((Plan*)p)->launches.size() : 0; }
+
+int spfy_spmma_plan_run_launch(spfy_spmma_plan_t p, int index, spfy_stream_t stream) {
+  if (!p) return fail(SPFY_E_INVALID, "spmma_plan_run_launch: null plan");
+  Plan* plan = (Plan*)p;
+  if (index < 0 || index >= (int)plan->launches.size())
+    return fail(SPFY_E_INVALID, "spmma_plan_run_launch: launch %d of %zu", index, plan->launches.size());
+  ProblemDev dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  const auto& ln = plan->launches[index];
+  return launch(plan->dtype, ln.opB, dummy, ln.L, ln.smem, ln.grid, (cudaStream_t)stream);
+}
+
+int spfy_spmma_plan_launch_info(spfy_spmma_plan_t p, int index, int* problems, int* units, int* stages,
+                                int* smem_bytes) {
+  if (!p) return fail(SPFY_E_INVALID, "spmma_plan_launch_info: null plan");
+  Plan* plan = (Plan*)p;
+  if (index < 0 || index >= (int)plan->launches.size())
+    return fail(SPFY_E_INVALID, "spmma_plan_launch_info: launch %d of %zu", index, plan->launches.size());
+  const auto& ln = plan->launches[index];
+  if (problems) *problems = (int)ln.count;
+  if (units) *units = (int)ln.L.total_units;
+  if (stages) *stages = (int)ln.L.stages;
+  if (smem_bytes) *smem_bytes = (int)ln.smem;
+  return SPFY_OK;
+}
 
 int spfy_spmma_plan_destroy(spfy_spmma_plan_t p) {
   if (!p) return SPFY_OK;

@@ -160,6 +160,14 @@ class SpmmaPlan:
     def run(self):
         capi.spfy_spmma_plan_run(self._h, _stream())
 
+    def run_launch(self, index):
+        capi.spfy_spmma_plan_run_launch(self._h, index, _stream())
+
+    def launch_info(self, index):
+        v = [ctypes.c_int() for _ in range(4)]
+        capi.spfy_spmma_plan_launch_info(self._h, index, *[ctypes.byref(x) for x in v])
+        return dict(zip(("problems", "units", "stages", "smem_bytes"), (x.value for x in v)))
+
     def close(self):
         if self._h:
             capi.spfy_spmma_plan_destroy(self._h)

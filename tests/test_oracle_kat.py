@@ -94,15 +94,15 @@ def test_sm100_packing_is_a_permutation(orc):
     for (row, g) in [(0, 0), (5, 3), (127, 31), (128, 32), (129, 64), (77, 40)]:
         mt, r_in, kt, gq = row // 128, row % 128, g // 32, g % 32
         p = gq * 2
-        off = (mt * kt_n + kt) * 16384 + (p >> 5) * 8192 + r_in * 64 + ((((p & 31) >> 3) ^ ((r_in >> 1) & 3)) << 4) + (p & 7) * 2
+        off = (kt * 2 + mt) * 16384 + r_in * 128 + (((p >> 3) ^ (r_in & 7)) << 4) + (p & 7) * 2
         assert v16[off // 2] == r["vals"][row, 2 * g] and v16[off // 2 + 1] == r["vals"][row, 2 * g + 1]
         q, j = gq // 4, gq % 4
-        eoff = (mt * kt_n + kt) * 2048 + (r_in >> 4) * 256 + (q & 1) * 128 + (r_in & 7) * 16 + (q >> 1) * 4 + ((r_in >> 3) & 1) * 2
+        eoff = (kt * 2 + mt) * 2048 + (r_in >> 4) * 256 + (q & 1) * 128 + (r_in & 7) * 16 + (q >> 1) * 4 + ((r_in >> 3) & 1) * 2
         word = int(om[eoff]) | int(om[eoff + 1]) << 8
         nib = (r["meta"][row, g // 2] >> ((g & 1) * 4)) & 0xF
         assert (word >> (4 * j)) & 0xF == nib
     # padding rows carry value 0 and the neutral nibble 0x4
-    pad_word_off = (1 * kt_n + 0) * 2048 + (100 >> 4) * 256 + (100 & 7) * 16 + ((100 >> 3) & 1) * 2
+    pad_word_off = (0 * 2 + 1) * 2048 + (100 >> 4) * 256 + (100 & 7) * 16 + ((100 >> 3) & 1) * 2
     assert om[pad_word_off] == 0x44 and om[pad_word_off + 1] == 0x44
 
 

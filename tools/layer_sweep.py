@@ -91,6 +91,16 @@ def main():
         us = statistics.median(ts)
         by = sum(spfy.shapes.spmma_bytes(g) for g in gemms)
         fl = sum(spfy.shapes.spmma_flops(g) for g in gemms)
+        for i in range(plan.launches):
+            tl = []
+            for _ in range(args.reps):
+                flush.zero_()
+                e0.record()
+                plan.run_launch(i)
+                e1.record()
+                torch.cuda.synchronize()
+                tl.append(e0.elapsed_time(e1) * 1e3)
+            print(f"# {args.tag} plan launch {i}: {plan.launch_info(i)} {statistics.median(tl):.0f} us")
         print(f"# {args.tag} PLAN {len(gemms)} layers in {plan.launches} launches: {us:.0f} us, {by/us/1e3:.0f} GB/s "
               f"({by/us/1e3/hbm:.3f} of HBM), {fl/us/1e6:.1f} TFLOP/s, roofline {tot_r:.0f} us -> {tot_r/us:.3f}")
 
