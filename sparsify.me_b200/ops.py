@@ -9,6 +9,7 @@ Tensors are torch CUDA tensors used as raw device buffers; all work is enqueued 
 current stream.  Nothing here computes on the host.
 """
 import ctypes
+import sys
 from dataclasses import dataclass
 
 import torch
@@ -206,7 +207,7 @@ def spmma(a, b, c, m, n, k, batch_size=1, transpose_a=capi.OP_N, transpose_b=cap
     if transpose_a != capi.OP_N:
         raise capi.SpfyError(capi.E_UNSUPPORTED, "spmma", "transpose_a is not supported")
     if m % 8 or n % 8 or k % 8:  # spmma.hxx:45-49 (warning only, execution continues)
-        print("Matrix sizes must be a multiple of 8 for (sparse) Tensor Cores.")
+        print("Invalid matrix sizes for data type __half. Rows and columns must be divisible by 8.", file=sys.stderr)
     a2 = a.view(-1)[: m * k].view(m, k)
     b2 = b.view(-1)[: k * n].view(k, n) if transpose_b == capi.OP_N else b.view(-1)[: k * n].view(n, k)
     c2 = c.view(-1)[: m * n].view(m, n)
