@@ -51,21 +51,67 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    The timed region is tens of milliseconds, so the sampler polls NVML directly (nvidia_ml_py) about
+    once per millisecond from a thread; `nvidia-smi -lms` is only the fallback when NVML cannot be loaded.
+    """
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.rows = []
+        self.uuid = uuid
+        self.rows = []       # nvidia-smi fallback lines
+        self.samples = []    # (sm_mhz, reasons bitmask) from NVML
         self.proc = None
+        self.nvml = None
+        self.handle = None
+        self.sm_max = None
+        self.power = []
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:  # noqa: BLE001
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, h
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(mhz), int(rs)))
+                if len(self.samples) % 16 == 1:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except OSError:
@@ -76,8 +122,25 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self._stop.set()
+            self.t.join(timeout=2)
+            nv = self.nvml
+            names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+            reasons = set()
+            for mhz, rs in self.samples:
+                for name, attr, dflt in names:
+                    if rs & int(getattr(nv, attr, dflt)):
+                        reasons.add(name)
+            sm = [s[0] for s in self.samples]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
+                    "reasons": sorted(reasons), "power_w_max": max(self.power) if self.power else None,
+                    "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -98,7 +161,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def layer_table(spfy, csv, batch):
@@ -192,7 +255,7 @@ def config_dict(args, nlayers):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--csv", default="resnet50.csv")
@@ -259,7 +322,7 @@ def main():
         prune_all()
         spmma_all()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, str(torch.cuda.get_device_properties(local).uuid))
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = spfy.launch_count()
@@ -307,12 +370,23 @@ def main():
         h2d = sum((g.M * g.K + g.K * g.N) * 2 for g in gemms)
         d2h = sum(g.M * g.N * 2 for g in gemms)
 
+        # three streams so that PCIe runs full duplex and the GPU works under the copies: layer i+1's
+        # H2D and layer i-1's D2H overlap layer i's prune+compress+multiply
+        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
         def e2e_step():
             for g, w, b, d, comp in layers:
-                w.copy_(hostbuf[("w", g)], non_blocking=True)
-                b.copy_(hostbuf[("b", g)], non_blocking=True)
-                spfy.spmma(w, b, d, g.M, g.N, g.K, args.batch)
-                hostbuf[("d", g)].copy_(d, non_blocking=True)
+                with torch.cuda.stream(s_in):
+                    w.copy_(hostbuf[("w", g)], non_blocking=True)
+                    b.copy_(hostbuf[("b", g)], non_blocking=True)
+                    ready = s_in.record_event()
+                with torch.cuda.stream(s_run):
+                    s_run.wait_event(ready)
+                    spfy.spmma(w, b, d, g.M, g.N, g.K, args.batch)
+                    done = s_run.record_event()
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    hostbuf[("d", g)].copy_(d, non_blocking=True)
             torch.cuda.synchronize()
 
         e2e_step()
@@ -330,7 +404,7 @@ def main():
         e2e = {"value": flops_step * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
                "api": "spmma(A, B, C, m, n, k, b) per layer: pinned H2D of A and B, prune in place + compress + "
-                      "tcgen05 matmul, D2H of C"}
+                      "tcgen05 matmul, D2H of C; copy-in / compute / copy-out on three streams"}
         # restore the resident weights for anything that follows
         del hostbuf
 

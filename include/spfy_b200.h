@@ -210,12 +210,15 @@ SPFY_API int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_
                                            float* C, size_t ldc, size_t strideC, float alpha,
                                            float beta, void* workspace, size_t workspace_bytes,
                                            spfy_stream_t stream);
-/* Same product with A already in CSR. */
+/* Same product with A already in CSR (same workspace query; only its last 256 bytes are used:
+ * one device word that records whether the column indices ascend inside every row, which
+ * selects the kernel's one-visit-per-non-zero mode). */
 SPFY_API int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
                                            const int32_t* row_ptr, const int32_t* col_idx,
                                            const float* vals, const float* B, size_t ldb,
                                            size_t strideB, float* C, size_t ldc,
                                            size_t strideC, float alpha, float beta,
+                                           void* workspace, size_t workspace_bytes,
                                            spfy_stream_t stream);
 
 /* ------------------------------------------------------------------------

@@ -63,7 +63,7 @@ SIGNATURES = {
     "spfy_spmm_coo_strided_batched": (c_int, [_SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P,
                                               _SZ, _SZ, c_float, c_float, _P, _SZ, _P]),
     "spfy_spmm_csr_strided_batched": (c_int, [_SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P, _SZ,
-                                              _SZ, c_float, c_float, _P]),
+                                              _SZ, c_float, c_float, _P, _SZ, _P]),
     "spfy_spmm_bell_batched": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _SZ, _P, _SZ,
                                        c_float, c_float, _P]),
 }

@@ -93,6 +93,7 @@ struct Prune24Params {
   int vec_in, vec_out, vec_cv;  // 16-byte fast paths allowed
   int tile_order;               // iterate in SM100 tile storage order
   int fits32;                   // dom_rows * units_per_row < 2^32
+  int fast;                     // every unit is a full, 16-byte aligned 16-column unit and no mask is wanted
 };
 
 // Indices i0 < i1 of the two largest magnitudes among the four 16-bit values packed in
@@ -241,6 +242,176 @@ __device__ __forceinline__ void prune24_unit(const Prune24Params& P, size_t t) {
   }
 }
 
+// ------------------------------------------------------------------------
+// Fast path: every 16-column unit is complete and 16-byte aligned (all datasets/*.csv weight
+// matrices except the k = 147 first convolution).  The generic unit above spends ~290 warp
+// instructions per 16 elements, which makes the kernel integer-ALU-bound at about a third of the
+// HBM rate; this one needs ~90.  Two groups of four are selected at once with packed 16-bit
+// arithmetic:
+//   * the magnitudes of element e of both groups share one word (group g in half g);
+//   * x >= y per half is bit 15 / 31 of (x - y + 0x80008000)  (magnitudes are 15 bits wide, so the
+//     halves never borrow from each other);
+//   * with "earlier beats later on >=" (the documented tie-break: lower index wins) an element is
+//     kept iff it loses at most one of its three duels, i.e. a 3-input majority of duel bits --
+//     one LOP3 each;
+//   * one PRMT in sign-replicate mode widens the keep bits to halfword masks, and bitwise selects
+//     pick the first / second kept value and the index nibble.
+// ------------------------------------------------------------------------
+// prmt.b32 in its default mode: selector nibble bit 3 replicates the sign bit of the selected byte
+// (the __byte_perm intrinsic only honours the low three bits)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t x, uint32_t y, uint32_t z) { return (x & y) | (x & z) | (y & z); }
+__device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
+
+// groups (w0, w1) and (w2, w3) -> their compressed words, nibbles (group 0: bits 0-3, group 1:
+// bits 16-19) and, when wanted, the four pruned dense words
+template <bool DENSE>
+__device__ __forceinline__ void select_two_groups(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                                                  uint32_t& cv0, uint32_t& cv1, uint32_t& nib, uint32_t* d) {
+  const uint32_t A = __byte_perm(w0, w2, 0x5410), B = __byte_perm(w0, w2, 0x7632);
+  const uint32_t C = __byte_perm(w1, w3, 0x5410), D = __byte_perm(w1, w3, 0x7632);
+  const uint32_t a = A & 0x7fff7fffu, b = B & 0x7fff7fffu, c = C & 0x7fff7fffu, e = D & 0x7fff7fffu;
+  const uint32_t ab = a - b + 0x80008000u, ac = a - c + 0x80008000u, ad = a - e + 0x80008000u;
+  const uint32_t bc = b - c + 0x80008000u, bd = b - e + 0x80008000u, cd = c - e + 0x80008000u;
+  const uint32_t ka = maj3(ab, ac, ad), kb = maj3(~ab, bc, bd), kc = maj3(~ac, ~bc, cd), kd = maj3(~ad, ~bd, ~cd);
+  // bit 15 -> bytes 0,1 ; bit 31 -> bytes 2,3
+  const uint32_t MA = prmt(ka, 0, 0xBB99), MB = prmt(kb, 0, 0xBB99);
+  const uint32_t MC = prmt(kc, 0, 0xBB99), MD = prmt(kd, 0, 0xBB99);
+  const uint32_t first = bsel(MA, A, bsel(MB, B, C));   // a, else b, else c
+  const uint32_t second = bsel(MD, D, bsel(MC, C, B));  // d, else c, else b
+  cv0 = __byte_perm(first, second, 0x5410);
+  cv1 = __byte_perm(first, second, 0x7632);
+  // i0 = a ? 0 : b ? 1 : 2  ->  bit0 = ~a & b, bit1 = ~a & ~b ;  i1 = d ? 3 : c ? 2 : 1  ->  bit2 = d | ~c, bit3 = d | c
+  const uint32_t n01 = bsel(0x00010001u, ~MA & MB, ~MA & ~MB);
+  const uint32_t n23 = bsel(0x00040004u, MD | ~MC, MD | MC);
+  nib = (n01 & 0x00030003u) | (n23 & 0x000c000cu);
+  if (DENSE) {
+    d[0] = w0 & __byte_perm(MA, MB, 0x5410);
+    d[1] = w1 & __byte_perm(MC, MD, 0x5410);
+    d[2] = w2 & __byte_perm(MA, MB, 0x7632);
+    d[3] = w3 & __byte_perm(MC, MD, 0x7632);
+  }
+}
+
+// 16 elements (8 words) -> 4 compressed words + 16 metadata bits (+ 8 pruned words)
+template <bool DENSE>
+__device__ __forceinline__ void select_unit(const uint4& x, const uint4& y, uint4& cv, uint32_t& nibs, uint4& dx, uint4& dy) {
+  uint32_t n0, n1, d0[4], d1[4];
+  select_two_groups<DENSE>(x.x, x.y, x.z, x.w, cv.x, cv.y, n0, d0);
+  select_two_groups<DENSE>(y.x, y.y, y.z, y.w, cv.z, cv.w, n1, d1);
+  const uint32_t t = n0 | (n1 << 8);  // g0: 0-3, g2: 8-11, g1: 16-19, g3: 24-27
+  nibs = (t | (t >> 12)) & 0xffffu;
+  if (DENSE) {
+    dx = make_uint4(d0[0], d0[1], d0[2], d0[3]);
+    dy = make_uint4(d1[0], d1[1], d1[2], d1[3]);
+  }
+}
+
+constexpr int FAST_UNITS = 4;  // units per thread and pass: all loads are issued before the first select
+
+// SM100 layout: one pass = one (128-row x 128-column) tile = 1024 units; `tile` is the storage index
+// (k-tile major).  8 consecutive threads read 256 contiguous bytes of one row and write 128
+// contiguous bytes of one swizzled value row.
+template <bool DENSE>
+__device__ __forceinline__ void prune24_fast_tile_sm100(const Prune24Params& P, uint32_t tile) {
+  const uint32_t kt = tile / P.m_tiles, mt = tile - kt * P.m_tiles;
+  uint4 x[FAST_UNITS], y[FAST_UNITS];
+  const uint32_t q = threadIdx.x & 7u, col = kt * 128u + q * 16u;
+  const bool col_ok = col < P.cols;
+#pragma unroll
+  for (int i = 0; i < FAST_UNITS; ++i) {
+    const uint32_t r = (threadIdx.x >> 3) + i * 32u, row = mt * 128u + r;
+    x[i] = y[i] = make_uint4(0, 0, 0, 0);
+    if (col_ok && row < P.rows) {
+      const uint16_t* src = P.in + (size_t)row * P.ld_in + col;
+      x[i] = ldg_nc_v4(src);
+      y[i] = ldg_nc_v4(src + 8);
+    }
+  }
+  uint8_t* vt = P.comp_vals ? P.comp_vals + (size_t)tile * 16384 : nullptr;
+  uint8_t* et = P.meta ? P.meta + (size_t)tile * 2048 : nullptr;
+#pragma unroll
+  for (int i = 0; i < FAST_UNITS; ++i) {
+    const uint32_t r = (threadIdx.x >> 3) + i * 32u, row = mt * 128u + r;
+    uint4 cv, dx, dy;
+    uint32_t nibs;
+    select_unit<DENSE>(x[i], y[i], cv, nibs, dx, dy);
+    if (DENSE && col_ok && row < P.rows) {
+      uint16_t* dst = P.out_dense + (size_t)row * P.ld_out + col;
+      *reinterpret_cast<uint4*>(dst) = dx;
+      *reinterpret_cast<uint4*>(dst + 8) = dy;
+    }
+    if (vt) *reinterpret_cast<uint4*>(vt + r * 128u + ((q ^ (r & 7u)) << 4)) = cv;
+    if (et)
+      *reinterpret_cast<uint16_t*>(et + (r >> 4) * 256u + (q & 1u) * 128u + (r & 7u) * 16u + (q >> 1) * 4u +
+                                   ((r >> 3) & 1u) * 2u) = (uint16_t)nibs;
+  }
+}
+
+// CANONICAL layout: one pass = 1024 consecutive units of the row-major unit order
+template <bool DENSE>
+__device__ __forceinline__ void prune24_fast_chunk_canonical(const Prune24Params& P, uint32_t chunk) {
+  const size_t total = (size_t)P.dom_rows * P.units_per_row;
+  uint4 x[FAST_UNITS], y[FAST_UNITS];
+  uint32_t rows_[FAST_UNITS], units_[FAST_UNITS];
+#pragma unroll
+  for (int i = 0; i < FAST_UNITS; ++i) {
+    const size_t t = (size_t)chunk * 1024 + i * 256 + threadIdx.x;
+    x[i] = y[i] = make_uint4(0, 0, 0, 0);
+    rows_[i] = 0xffffffffu;
+    units_[i] = 0;
+    if (t < total) {
+      const uint32_t row = P.fits32 ? (uint32_t)t / P.units_per_row : (uint32_t)(t / P.units_per_row);
+      const uint32_t unit = (uint32_t)(t - (size_t)row * P.units_per_row);
+      rows_[i] = row;
+      units_[i] = unit;
+      const uint16_t* src = P.in + (size_t)row * P.ld_in + unit * 16u;
+      x[i] = ldg_nc_v4(src);
+      y[i] = ldg_nc_v4(src + 8);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < FAST_UNITS; ++i) {
+    if (rows_[i] == 0xffffffffu) continue;
+    const uint32_t row = rows_[i], unit = units_[i];
+    uint4 cv, dx, dy;
+    uint32_t nibs;
+    select_unit<DENSE>(x[i], y[i], cv, nibs, dx, dy);
+    if (DENSE) {
+      uint16_t* dst = P.out_dense + (size_t)row * P.ld_out + unit * 16u;
+      *reinterpret_cast<uint4*>(dst) = dx;
+      *reinterpret_cast<uint4*>(dst + 8) = dy;
+    }
+    if (P.comp_vals)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(P.comp_vals) + (size_t)row * P.G + unit * 4u) = cv;
+    if (P.meta) *reinterpret_cast<uint16_t*>(P.meta + (size_t)row * P.mb + unit * 2u) = (uint16_t)nibs;
+  }
+}
+
+// number of 1024-unit passes of a matrix
+__host__ __device__ inline uint32_t fast_passes(const Prune24Params& P) {
+  return P.tile_order ? P.k_tiles * P.m_tiles
+                      : (uint32_t)(((size_t)P.dom_rows * P.units_per_row + 1023) / 1024);
+}
+
+__device__ __forceinline__ void prune24_fast_pass(const Prune24Params& P, uint32_t pass) {
+  if (P.tile_order) {
+    if (P.out_dense) prune24_fast_tile_sm100<true>(P, pass); else prune24_fast_tile_sm100<false>(P, pass);
+  } else {
+    if (P.out_dense) prune24_fast_chunk_canonical<true>(P, pass); else prune24_fast_chunk_canonical<false>(P, pass);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+prune24_fast_kernel(const __grid_constant__ Prune24Params P) {
+  const uint32_t passes = fast_passes(P);
+  for (uint32_t pass = blockIdx.x; pass < passes; pass += gridDim.x) prune24_fast_pass(P, pass);
+}
+
 __global__ void __launch_bounds__(256)
 prune24_strip_kernel(const __grid_constant__ Prune24Params P) {
   const size_t total = (size_t)P.dom_rows * P.units_per_row;
@@ -251,7 +422,7 @@ prune24_strip_kernel(const __grid_constant__ Prune24Params P) {
 
 // Many matrices in one launch (a whole model's weight set: the per-layer matrices are
 // <= 4.7 MB, so one launch per layer is launch-latency-bound).  Work is cut into CTA tiles
-// of 256 units; every tile belongs to exactly one matrix, so the table lookup is CTA-uniform.
+// of 1024 units (one SM100 tile); every tile belongs to exactly one matrix, so the lookup is CTA-uniform.
 constexpr int PRUNE_BATCH_MAX = 96;
 struct Prune24Batch {
   Prune24Params item[PRUNE_BATCH_MAX];
@@ -269,8 +440,17 @@ prune24_batched_kernel(const __grid_constant__ Prune24Batch Bt) {
       if (Bt.tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
     }
     const Prune24Params& P = Bt.item[lo];
-    const size_t t = (size_t)(tile - Bt.tile_prefix[lo]) * 256 + threadIdx.x;
-    if (t < (size_t)P.dom_rows * P.units_per_row) prune24_unit(P, t);
+    const uint32_t pass = tile - Bt.tile_prefix[lo];
+    if (P.fast) {
+      prune24_fast_pass(P, pass);
+    } else {
+      const size_t total = (size_t)P.dom_rows * P.units_per_row;
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const size_t t = (size_t)pass * 1024 + i * 256 + threadIdx.x;
+        if (t < total) prune24_unit(P, t);
+      }
+    }
   }
 }
 
@@ -386,6 +566,9 @@ int fill_prune24(Prune24Params* out, int layout, const uint16_t* src, size_t ld_
   P.vec_cv = comp_vals && ((uintptr_t)comp_vals % 16 == 0) && (P.G % 4 == 0);
   if (layout == SPFY_LAYOUT_SM100 && ((comp_vals && (uintptr_t)comp_vals % 16) || (meta && (uintptr_t)meta % 16)))
     return fail(SPFY_E_INVALID, "prune24: SM100 outputs must be 16-byte aligned");
+  P.fast = !mask && P.vec_in && cols % 16 == 0 && (!out_dense || P.vec_out) &&
+           (sm100_out || ((!comp_vals || P.vec_cv) && (uintptr_t)meta % 2 == 0)) &&
+           fast_passes(P) < (1u << 31);
   *out = P;
   return SPFY_OK;
 }
@@ -525,6 +708,13 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
   int rc = fill_prune24(&P, layout, src, ld_src, out_dense, ld_out, comp_vals, meta, mask, rows, cols);
   if (rc) return rc;
   int grid = 1;
+  if (P.fast) {
+    rc = grid_for((size_t)fast_passes(P) * 256, 256, &grid);
+    if (rc) return rc;
+    prune24_fast_kernel<<<grid, 256, 0, s>>>(P);
+    SPFY_LAUNCH_OK("prune24_fast_kernel");
+    return SPFY_OK;
+  }
   rc = grid_for((size_t)P.dom_rows * P.units_per_row, 256, &grid);
   if (rc) return rc;
   prune24_strip_kernel<<<grid, 256, 0, s>>>(P);
@@ -560,7 +750,7 @@ int spfy_prune24_batched(int dtype, int layout, const spfy_prune24_item* items, 
       rc = fill_prune24(&P, layout, (const uint16_t*)it.in, it.ld_in, it.out_dense, it.ld_out,
                         it.comp_vals, it.meta, nullptr, it.rows, it.cols);
       if (rc) return rc;
-      const size_t tiles = ceil_div((size_t)P.dom_rows * P.units_per_row, 256);
+      const size_t tiles = P.fast ? fast_passes(P) : ceil_div((size_t)P.dom_rows * P.units_per_row, 1024);
       if ((size_t)Bt.tile_prefix[Bt.count] + tiles >= (1ull << 32))
         return fail(SPFY_E_UNSUPPORTED, "prune24_batched: batch too large");
       Bt.tile_prefix[Bt.count + 1] = Bt.tile_prefix[Bt.count] + (uint32_t)tiles;

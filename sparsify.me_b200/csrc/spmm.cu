@@ -149,20 +149,6 @@ constexpr int SP_TM = SP_WARPS * SP_RPW;  // 128 rows per CTA
 constexpr int SP_TN = 32;              // columns per CTA (one per lane)
 constexpr int SP_PAD = SP_TN + 1;      // padded row of the transposed B tile
 
-struct CsrRows {  // A in CSR, shared by every batch
-  const int32_t* row_ptr;
-  const int32_t* col_idx;
-  const float* vals;
-  __device__ __forceinline__ void range(uint32_t, uint32_t row, uint32_t& b, uint32_t& e) const {
-    b = (uint32_t)row_ptr[row];
-    e = (uint32_t)row_ptr[row + 1];
-  }
-  __device__ __forceinline__ void fetch(uint32_t, uint32_t, uint32_t idx, int32_t& c, float& v) const {
-    c = col_idx[idx];
-    v = vals[idx];
-  }
-};
-
 template <typename T>
 struct BellRows {  // blocked-ELL, one matrix per batch (reference: containers/ell.hxx:24-33)
   const int64_t* const* col_idx;  // [batch] -> [(rows/block) x (ell_cols/block)]
@@ -302,6 +288,235 @@ int elementwise_grid(size_t items, int* grid) {
   return SPFY_OK;
 }
 
+// ------------------------------------------------------------------------
+// CSR / COO SpMM, fp32 (the operand types of spmm.hxx:165-180): C_b = alpha * A * B_b + beta * C_b,
+// one sparse A shared by all batch elements, B_b / C_b column-major.
+//
+// Every FMA needs one dynamically addressed B element, which can only come from shared memory, so
+// the kernel is bound by shared-memory wavefronts (128 B/clk/SM), not by the FMA pipe: a lane owns
+// CSR_TJ = 4 columns, one non-zero costs one broadcast LDS.64 (value + column) plus four LDS.32 for
+// four FMAs.  CTA tile = (16 warps x RPW rows) x 128 columns; K is walked in chunks of 192 rows of
+// B staged as sB[column][k] (odd row pitch: conflict-free both for the coalesced fill along k and
+// for the per-non-zero reads across columns); two CTAs per SM, so one stages while the other
+// multiplies.  A warp reads the non-zeros of a row 32 at a time with one coalesced request,
+// compacts the ones that fall into the staged chunk into a per-warp scratch line and replays them.
+// With ascending columns inside a row (what spfy_threshold_to_coo emits; `*sorted` says so) a
+// per-row cursor makes this one visit per non-zero; otherwise every chunk rescans the row.
+// The C tile goes back through shared memory so the column-major stores run along rows.
+// ------------------------------------------------------------------------
+constexpr int CSR_WARPS = 16;
+constexpr int CSR_TN = 128;
+constexpr int CSR_TJ = CSR_TN / 32;
+constexpr int CSR_KC = 192;
+constexpr int CSR_PITCH = CSR_KC + 1;
+
+struct CsrSpmmParams {
+  const int32_t* row_ptr;
+  const int32_t* col_idx;
+  const float* vals;
+  const float* B;
+  float* C;
+  const int* sorted;        // device flag: columns ascend inside every row
+  size_t ldb, strideB, ldc, strideC;
+  uint32_t m, k, n, num_batches;
+  uint32_t row_tiles, col_tiles;  // col tiles over the num_batches * n columns
+  uint32_t vec;                    // B columns are 16-byte aligned: 128-bit fill
+  float alpha, beta;
+};
+
+__global__ void __launch_bounds__(256)
+csr_check_sorted_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, uint32_t m,
+                        int* __restrict__ sorted) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  bool bad = false;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < m; r += warps) {
+    const int32_t b = row_ptr[r], e = row_ptr[r + 1];
+    for (int32_t i = b + 1 + (int32_t)lane; i < e; i += 32) bad |= col_idx[i] < col_idx[i - 1];
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(sorted, 0);
+}
+
+template <int RPW>
+__global__ void __launch_bounds__(CSR_WARPS * 32, 2)
+spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
+  constexpr int TM = CSR_WARPS * RPW;
+  extern __shared__ float smem_f[];
+  float* sB = smem_f;                                                         // [CSR_TN][CSR_PITCH]
+  uint2* scratch = reinterpret_cast<uint2*>(smem_f + CSR_TN * CSR_PITCH) + (threadIdx.x >> 5) * 32;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool sorted = *P.sorted != 0;
+  const uint32_t nnz_total = (uint32_t)P.row_ptr[P.m];
+  const uint64_t ncols = (uint64_t)P.n * P.num_batches;
+  const uint32_t tiles = P.row_tiles * P.col_tiles;
+
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint32_t rt = tile % P.row_tiles, ct = tile / P.row_tiles;  // row tile fastest: CTAs that
+    const uint32_t i0 = rt * TM + warp * RPW;                          // share B columns run together
+    const uint64_t j0 = (uint64_t)ct * CSR_TN;
+
+    uint32_t cur[RPW];  // scan position of every row (row ends are re-read per chunk: registers are scarce)
+    float acc[RPW][CSR_TJ];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const uint32_t row = i0 + r;
+      cur[r] = row < P.m ? (uint32_t)P.row_ptr[row] : 0u;
+#pragma unroll
+      for (int j = 0; j < CSR_TJ; ++j) acc[r][j] = 0.f;
+    }
+
+    for (uint32_t k0 = 0; k0 < P.k; k0 += CSR_KC) {
+      const uint32_t kn = min((uint32_t)CSR_KC, P.k - k0);
+      __syncthreads();  // everyone is done with the previous chunk (or the previous tile's C)
+      // ---- stage B[k0 : k0+kn, j0 : j0+128] as sB[column][k] ----
+      if (P.vec && kn == (uint32_t)CSR_KC) {
+        // half a warp per column: 16 lanes x 3 x 16 bytes = 192 floats
+        const uint32_t hl = lane & 15u;
+#pragma unroll
+        for (int s = 0; s < CSR_TN / (2 * CSR_WARPS); ++s) {
+          const uint32_t jj = s * (2 * CSR_WARPS) + warp * 2 + (lane >> 4);
+          const uint64_t J = j0 + jj;
+          float4 v[3];
+          if (J < ncols) {
+            const uint32_t bt = (uint32_t)(J / P.n);
+            const float* src = P.B + (size_t)bt * P.strideB + (size_t)(J - (uint64_t)bt * P.n) * P.ldb + k0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(src) + q * 16 + hl);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float* dst = sB + jj * CSR_PITCH + hl * 4;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            dst[q * 64 + 0] = v[q].x;
+            dst[q * 64 + 1] = v[q].y;
+            dst[q * 64 + 2] = v[q].z;
+            dst[q * 64 + 3] = v[q].w;
+          }
+        }
+      } else {
+        for (uint32_t jj = warp; jj < (uint32_t)CSR_TN; jj += CSR_WARPS) {
+          const uint64_t J = j0 + jj;
+          const bool ok = J < ncols;
+          const uint32_t bt = ok ? (uint32_t)(J / P.n) : 0u;
+          const float* src = P.B + (size_t)bt * P.strideB + (size_t)(ok ? J - (uint64_t)bt * P.n : 0) * P.ldb + k0;
+          for (uint32_t kk = lane; kk < kn; kk += 32) sB[jj * CSR_PITCH + kk] = ok ? __ldg(src + kk) : 0.f;
+        }
+      }
+      __syncthreads();
+
+      // ---- multiply: every warp walks its RPW rows ----
+      const uint32_t k_end = k0 + kn;
+      const float* sBl = sB + lane * CSR_PITCH;
+      // rows are handled four at a time: the first request of each of the four goes out before any is
+      // processed (cur[] doubles as the scan position; unsorted rows restart from the row start)
+#pragma unroll
+      for (int r0 = 0; r0 < RPW; r0 += 4) {
+        int32_t c_[4];
+        float v_[4];
+        uint32_t end[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = r0 + q;
+          const bool row_ok = i0 + r < P.m;
+          if (!sorted) cur[r] = row_ok ? (uint32_t)P.row_ptr[i0 + r] : 0u;
+          end[q] = row_ok ? (uint32_t)P.row_ptr[i0 + r + 1] : 0u;
+          // the request does not wait for the row end: any index below nnz is readable
+          const uint32_t idx = cur[r] + lane;
+          const bool rd = idx < nnz_total;
+          c_[q] = rd ? P.col_idx[idx] : 0x7fffffff;
+          v_[q] = rd ? P.vals[idx] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (cur[r0 + q] + lane >= end[q]) c_[q] = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = r0 + q;
+          while (true) {
+            const int32_t c = c_[q];
+            const bool in = c >= (int32_t)k0 && c < (int32_t)k_end;
+            const unsigned in_mask = __ballot_sync(0xffffffffu, in);
+            const unsigned adv = __popc(__ballot_sync(0xffffffffu, c < (int32_t)k_end));  // sorted: a prefix
+            const unsigned cnt = __popc(in_mask);
+            if (in)
+              scratch[__popc(in_mask & ((1u << lane) - 1u))] =
+                  make_uint2((uint32_t)(c - (int32_t)k0), __float_as_uint(v_[q]));
+            __syncwarp();
+#pragma unroll 4
+            for (unsigned t = 0; t < cnt; ++t) {
+              const uint2 e = scratch[t];
+              const float a = __uint_as_float(e.y);
+              const float* bp = sBl + e.x;
+#pragma unroll
+              for (int j = 0; j < CSR_TJ; ++j) acc[r][j] = fmaf(a, bp[j * 32 * CSR_PITCH], acc[r][j]);
+            }
+            __syncwarp();
+            bool more;
+            if (sorted) {
+              cur[r] += adv;
+              more = adv == 32u;       // the whole request was below k_end: the row may continue in this chunk
+            } else {
+              cur[r] += 32u;
+              more = cur[r] < end[q];  // unsorted: scan the whole row for every chunk
+            }
+            if (!more) break;
+            const uint32_t idx = cur[r] + lane;
+            const bool ok = idx < end[q];
+            c_[q] = ok ? P.col_idx[idx] : 0x7fffffff;
+            v_[q] = ok ? P.vals[idx] : 0.f;
+          }
+        }
+      }
+    }
+
+    // ---- C tile through shared memory: sC[column][row], stores run along rows ----
+    __syncthreads();
+    float* sC = smem_f;  // [CSR_TN][TM + 1]
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int j = 0; j < CSR_TJ; ++j) sC[(lane + 32 * j) * (TM + 1) + warp * RPW + r] = acc[r][j];
+    __syncthreads();
+    const uint32_t rbase = rt * TM;
+    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * TM); idx += CSR_WARPS * 32) {
+      const uint32_t jj = idx / TM, i = idx % TM;
+      const uint64_t J = j0 + jj;
+      if (J < ncols && rbase + i < P.m) {
+        const uint32_t bt = (uint32_t)(J / P.n);
+        float* dst = P.C + (size_t)bt * P.strideC + (size_t)(J - (uint64_t)bt * P.n) * P.ldc + rbase + i;
+        float out = P.alpha * sC[jj * (TM + 1) + i];
+        if (P.beta != 0.f) out += P.beta * *dst;
+        *dst = out;
+      }
+    }
+  }
+}
+
+template <int RPW>
+int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
+  constexpr int TM = CSR_WARPS * RPW;
+  size_t smem = ((size_t)CSR_TN * CSR_PITCH) * 4 + (size_t)CSR_WARPS * 32 * 8;
+  const size_t c_tile = (size_t)CSR_TN * (TM + 1) * 4;
+  if (smem < c_tile) smem = c_tile;
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  SPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63].load()) {
+    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need the full shared-memory carve-out
+    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
+    attr_set[dev & 63].store(1);
+  }
+  const uint32_t tiles = P.row_tiles * P.col_tiles;
+  const uint32_t grid = tiles < (uint32_t)(2 * sm_count) ? tiles : (uint32_t)(2 * sm_count);
+  spmm_csr_kernel<RPW><<<grid, CSR_WARPS * 32, smem, s>>>(P);
+  SPFY_LAUNCH_OK("spmm_csr_kernel");
+  return SPFY_OK;
+}
+
 template <typename T>
 int threshold_impl(const void* in, size_t ld, size_t rows, size_t cols, float thr, int32_t* row_idx,
                    int32_t* col_idx, float* vals, size_t capacity, int64_t* d_nnz,
@@ -376,27 +591,56 @@ int spfy_coo_to_csr(const int32_t* row_idx, size_t nnz, size_t rows, int32_t* ro
 
 int spfy_spmm_workspace_bytes(size_t m, size_t nnz, size_t* bytes) {
   (void)nnz;
-  if (bytes) *bytes = round_up((m + 1) * 4, 256);
+  if (bytes) *bytes = round_up((m + 1) * 4, 256) + 256;  // row_ptr (COO entry) + the "sorted" word
   return SPFY_OK;
 }
 
 int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
                                   const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
                                   const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
-                                  size_t strideC, float alpha, float beta, spfy_stream_t stream) {
+                                  size_t strideC, float alpha, float beta, void* workspace,
+                                  size_t workspace_bytes, spfy_stream_t stream) {
   if (m == 0 || n == 0 || num_batches == 0) return SPFY_OK;
   if (!row_ptr || !B || !C) return fail(SPFY_E_INVALID, "spmm_csr: null pointer");
+  size_t need = 0;
+  spfy_spmm_workspace_bytes(m, 0, &need);
+  if (!workspace || workspace_bytes < need)
+    return fail(SPFY_E_WORKSPACE, "spmm_csr: workspace %zu < %zu bytes", workspace_bytes, need);
   if (ldb < k || ldc < m) return fail(SPFY_E_INVALID, "spmm_csr: leading dimension too small");
   if (m >= (1ull << 31) || n >= (1ull << 31) || k >= (1ull << 31))
     return fail(SPFY_E_UNSUPPORTED, "spmm_csr: dimension too large");
-  CsrRows A{row_ptr, col_idx, vals};
-  SpmmDense D;
-  memset(&D, 0, sizeof(D));
-  D.B = B; D.C = C; D.Cs = nullptr;
-  D.ldb = ldb; D.strideB = strideB; D.ldc = ldc; D.strideC = strideC;
-  D.m = (uint32_t)m; D.k = (uint32_t)k; D.n = (uint32_t)n; D.num_batches = (uint32_t)num_batches;
-  D.alpha = alpha; D.beta = beta;
-  return launch_spmm<float, CsrRows>(A, D, (cudaStream_t)stream);
+  if (m * 1ull >= (1ull << 31) || (unsigned long long)n * num_batches >= (1ull << 40))
+    return fail(SPFY_E_UNSUPPORTED, "spmm_csr: problem too large");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  // one device word: "columns ascend inside every row" (decides between cursor and rescan mode)
+  int* d_sorted = (int*)((uint8_t*)workspace + need - 256);
+  SPFY_CUDA_OK(cudaMemsetAsync(d_sorted, 0xff, sizeof(int), s));
+  {
+    int grid = 1;
+    rc = elementwise_grid(m * 32, &grid);
+    if (rc) return rc;
+    csr_check_sorted_kernel<<<grid, 256, 0, s>>>(row_ptr, col_idx, (uint32_t)m, d_sorted);
+    SPFY_LAUNCH_OK("csr_check_sorted_kernel");
+  }
+  CsrSpmmParams P;
+  memset(&P, 0, sizeof(P));
+  P.row_ptr = row_ptr; P.col_idx = col_idx; P.vals = vals;
+  P.B = B; P.C = C; P.sorted = d_sorted;
+  P.ldb = ldb; P.strideB = strideB; P.ldc = ldc; P.strideC = strideC;
+  P.m = (uint32_t)m; P.k = (uint32_t)k; P.n = (uint32_t)n; P.num_batches = (uint32_t)num_batches;
+  P.alpha = alpha; P.beta = beta;
+  P.vec = ((uintptr_t)B % 16 == 0) && ldb % 4 == 0 && strideB % 4 == 0;
+  const size_t total_cols = n * num_batches;
+  const size_t col_tiles = ceil_div(total_cols, CSR_TN);
+  // 64-row tiles (16 warps x 4 rows): 128-row tiles would halve the re-staging of B for m > 64, but
+  // their 32 accumulators per lane do not fit the 64-register budget of two 512-thread CTAs per SM
+  P.row_tiles = (uint32_t)ceil_div(m, 64);
+  if (col_tiles * P.row_tiles >= (1ull << 32)) return fail(SPFY_E_UNSUPPORTED, "spmm_csr: too many tiles");
+  P.col_tiles = (uint32_t)col_tiles;
+  return launch_spmm_csr<4>(P, di.sm_count, s);
 }
 
 int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,
@@ -411,7 +655,8 @@ int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size
   int rc = spfy_coo_to_csr(row_idx, nnz, m, (int32_t*)workspace, stream);
   if (rc) return rc;
   return spfy_spmm_csr_strided_batched(m, k, n, num_batches, (const int32_t*)workspace, col_idx, vals,
-                                       B, ldb, strideB, C, ldc, strideC, alpha, beta, stream);
+                                       B, ldb, strideB, C, ldc, strideC, alpha, beta, workspace,
+                                       workspace_bytes, stream);
 }
 
 int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t block,

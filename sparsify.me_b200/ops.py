@@ -283,9 +283,12 @@ class batched:
 
     @staticmethod
     def csr(m, k, n, num_batches, row_ptr, col_idx, vals, b, c, alpha=1.0, beta=0.0):
+        wb = ctypes.c_size_t()
+        capi.spfy_spmm_workspace_bytes(m, col_idx.numel(), ctypes.byref(wb))
+        ws = torch.empty(max(wb.value, 16), dtype=torch.uint8, device=b.device)
         capi.spfy_spmm_csr_strided_batched(m, k, n, num_batches, _ptr(row_ptr), _ptr(col_idx),
                                            _ptr(vals), _ptr(b), k, k * n, _ptr(c), m, m * n,
-                                           float(alpha), float(beta), _stream())
+                                           float(alpha), float(beta), _ptr(ws), ws.numel(), _stream())
 
     @staticmethod
     def spmm(col_idx_list, values_list, b, c_list, m, n, k, block, ell_cols, alpha=1.0, beta=0.0):

@@ -89,6 +89,33 @@ def test_prune24_sm100_layout_bit_exact(spfy, orc, cuda, rows, cols):
     assert np.array_equal(comp.meta.cpu().numpy(), om)
 
 
+@pytest.mark.parametrize("rows,cols", [(128, 128), (256, 2304), (200, 96), (130, 272), (2048, 512), (1, 16), (129, 4608)])
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("dt", [0, 1])
+def test_prune24_fast_path_both_layouts(spfy, orc, cuda, rows, cols, dense, dt):
+    """cols % 16 == 0 and no mask: the packed-select kernel (prune24_fast_kernel), with and without the
+    pruned dense copy, tie-rich inputs included."""
+    bits = rand_bits(orc, dt, (rows, cols), seed=rows * 131 + cols + dense)
+    bits[::3, : cols // 2] &= 0xFC00  # few distinct magnitudes: plenty of ties inside groups
+    want = orc.prune24_strip(dt, bits)
+    ov, om = orc.pack_sm100(want["vals"], want["meta"], rows, cols)
+    a = to_dev(bits, dt, cuda)
+    for layout in (spfy.LAYOUT_SM100, spfy.LAYOUT_CANONICAL):
+        out = torch.empty_like(a) if dense else None
+        comp = spfy.prune24(a, out_dense=out, layout=layout)
+        if dense:
+            assert np.array_equal(bits_of(out), want["dense"])
+        if layout == spfy.LAYOUT_SM100:
+            assert np.array_equal(comp.vals.cpu().numpy(), ov)
+            assert np.array_equal(comp.meta.cpu().numpy(), om)
+        else:
+            assert np.array_equal(comp.vals.cpu().numpy().view(np.uint16).reshape(rows, -1), want["vals"])
+            assert np.array_equal(comp.meta.cpu().numpy().reshape(rows, -1), want["meta"])
+    # in place (the reference's spmma mutates A: spmma.hxx:86)
+    spfy.prune24(a, inplace=True, compress=False)
+    assert np.array_equal(bits_of(a), want["dense"])
+
+
 def test_prune24_inplace_and_strided(spfy, orc, cuda):
     rows, cols, ld = 96, 200, 256
     bits = rand_bits(orc, 0, (rows, ld), seed=5)
@@ -420,6 +447,30 @@ def test_batched_coo_spmm_empty_rows_and_unsorted_columns(spfy, orc, cuda):
     spfy.batched.strided_coo(m, k, ri.size, k, n, nb, torch.from_numpy(ri).to(cuda), torch.from_numpy(ci).to(cuda),
                              torch.from_numpy(va).to(cuda), torch.from_numpy(B).to(cuda), dC)
     assert np.allclose(dC.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_batched_coo_spmm_many_chunks(spfy, orc, cuda, shuffle):
+    """K spans several staged chunks and rows hold more than one 32-entry request; with shuffled
+    columns inside every row the kernel must fall back from its per-row cursor to rescanning."""
+    m, k, n, nb = 96, 960, 150, 2
+    rng = np.random.default_rng(11)
+    w = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    w[5] = 0.0   # an empty row
+    w[7, :] = rng.uniform(1, 2, k)  # a dense row
+    thr = float(np.quantile(np.abs(w), 0.8))
+    ri, ci, va, _ = orc.threshold_to_coo(2, w, thr)
+    if shuffle:
+        for r in range(m):
+            sel = np.nonzero(ri == r)[0]
+            p = rng.permutation(sel.size)
+            ci[sel], va[sel] = ci[sel][p], va[sel][p]
+    B = rng.uniform(-1, 1, (nb, n, k)).astype(np.float32)
+    want = orc.spmm_coo_batched_f64(m, k, n, nb, ri, ci, va, B)
+    dC = torch.full((nb, n, m), 7.0, dtype=torch.float32, device=cuda)
+    spfy.batched.strided_coo(m, k, ri.size, k, n, nb, torch.from_numpy(ri).to(cuda), torch.from_numpy(ci).to(cuda),
+                             torch.from_numpy(va).to(cuda), torch.from_numpy(B).to(cuda), dC)
+    assert np.allclose(dC.cpu().numpy(), want, rtol=2e-4, atol=2e-4)
 
 
 @pytest.mark.parametrize("tdt", [torch.float32, torch.float16])

@@ -1,0 +1,28 @@
+#!/bin/bash
+# flexible GPU visit; steps chosen by words in $2..: test bench prune spmm sweep ref ncu_spmm ncu_spmma ncu_prune dbg
+TAG=${1:-r1}; shift
+OUT=gpurun_out
+mkdir -p $OUT
+for step in "$@"; do
+case $step in
+test) python -m pytest tests -m gpu -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -8 $OUT/pytest_gpu_$TAG.log;;
+bench) python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?";;
+prune) python tools/prune_probe.py --tag $TAG > $OUT/prune_probe_$TAG.csv 2>&1; echo "prune probe rc=$?";;
+spmm) python tools/spmm_sweep.py --tag $TAG > $OUT/spmm_sweep_$TAG.csv 2>&1; echo "spmm sweep rc=$?";;
+sweep) python tools/layer_sweep.py --plan --tag $TAG > $OUT/sweep_$TAG.csv 2>&1; echo "sweep rc=$?";;
+ref) python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?";;
+dbg) for d in 2 8 10; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --tag dbg$d > $OUT/sweep_${TAG}_dbg$d.csv 2>&1; echo "dbg$d rc=$?"; done;;
+ncu_spmm)
+  CMD="python tools/spmm_one.py 64 576 12544 32 0.9"
+  $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
+ncu_spmma)
+  CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+  $CMD > $OUT/plain_$TAG.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'spmma_kernel|prune24' -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_l_$TAG.log 2>&1; echo "launch list rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:spmma_kernel -s 9 -c 3 -o $OUT/prof_spmma_$TAG -f $CMD > $OUT/ncu_s_$TAG.log 2>&1; echo "ncu spmma rc=$?";;
+ncu_prune)
+  CMD="python tools/prune_probe.py --reps 1 --only-large"
+  $CMD > $OUT/plain_prune_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:prune24_fast -s 3 -c 1 -o $OUT/prof_prune_$TAG -f $CMD > $OUT/ncu_p_$TAG.log 2>&1; echo "ncu prune rc=$?";;
+esac
+done

@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Per-shape spmma sweep over a datasets/*.csv table (unique shapes), cold operands.
 
-For every unique (M, K, N) of the table: median-of-R CUDA-event time of one spfy_spmma launch with
-the L2 flushed before each launch, algorithmic GB/s and dense-equivalent TFLOP/s, and the fraction
+For every unique (M, K, N) of the table: median-of-R CUDA-event time per launch of a train of
+spfy_spmma launches that rotate over enough operand sets to stay out of L2, algorithmic GB/s and dense-equivalent TFLOP/s, and the fraction
 of the per-shape roofline min(HBM, sparse tensor).  Writes a CSV line per shape to stdout.
 
     python tools/layer_sweep.py [--csv resnet50.csv] [--batch 32] [--dtype fp16] [--reps 7]
@@ -25,7 +25,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--reps", type=int, default=7)
-    ap.add_argument("--warm", action="store_true", help="no L2 flush between launches")
+    ap.add_argument("--warm", action="store_true", help="one buffer set: operands may stay in L2")
+    ap.add_argument("--train", type=int, default=16, help="launches per timed train")
     ap.add_argument("--tag", default="")
     ap.add_argument("--only", default="", help="M,K,N filter")
     ap.add_argument("--plan", action="store_true", help="also time the whole table as ONE plan (grouped launches)")
@@ -46,21 +47,25 @@ def main():
         if args.only and args.only != f"{g.M},{g.K},{g.N}":
             continue
         w = (torch.rand(g.M, g.K, device=dev) * 2 - 1).to(tdt)
-        b = (torch.rand(g.K, g.N, device=dev) * 2 - 1).to(tdt)
-        d = torch.empty(g.M, g.N, device=dev, dtype=tdt)
         comp = spfy.prune24(w)
-        for _ in range(2):
-            spfy.spmma_compressed(comp, b, out=d)
+        # rotate over enough (B, D) sets that a launch never finds its operands in the 126 MB L2, and time
+        # a train of launches under one event pair (one launch is 20-90 us; the event clock ticks at ~2 us)
+        per_set = (g.K * g.N + g.M * g.N) * 2
+        nsets = 1 if args.warm else max(2, min(16, -(-400_000_000 // per_set)))
+        b = [(torch.rand(g.K, g.N, device=dev) * 2 - 1).to(tdt) for _ in range(nsets)]
+        d = [torch.empty(g.M, g.N, device=dev, dtype=tdt) for _ in range(nsets)]
+        for i in range(nsets):
+            spfy.spmma_compressed(comp, b[i], out=d[i])
         ts = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(args.reps):
-            if not args.warm:
-                flush.zero_()
+            torch.cuda.synchronize()
             e0.record()
-            spfy.spmma_compressed(comp, b, out=d)
+            for i in range(args.train):
+                spfy.spmma_compressed(comp, b[i % nsets], out=d[i % nsets])
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e3)
+            ts.append(e0.elapsed_time(e1) * 1e3 / args.train)
         us = statistics.median(ts)
         by, fl = spfy.shapes.spmma_bytes(g), spfy.shapes.spmma_flops(g)
         roof = max(by / hbm / 1e3, fl / tc / 1e6)
