@@ -313,12 +313,14 @@ __device__ __forceinline__ void select_unit(const uint4& x, const uint4& y, uint
 
 constexpr int FAST_UNITS = 4;  // units per thread and pass: all loads are issued before the first select
 
-// SM100 layout: one pass = one (128-row x 128-column) tile = 1024 units; `tile` is the storage index
-// (k-tile major).  8 consecutive threads read 256 contiguous bytes of one row and write 128
+// SM100 layout: one pass = one (128-row x 128-column) tile = 1024 units.  8 consecutive threads read 256 contiguous bytes of one row and write 128
 // contiguous bytes of one swizzled value row.
 template <bool DENSE>
-__device__ __forceinline__ void prune24_fast_tile_sm100(const Prune24Params& P, uint32_t tile) {
-  const uint32_t kt = tile / P.m_tiles, mt = tile - kt * P.m_tiles;
+__device__ __forceinline__ void prune24_fast_tile_sm100(const Prune24Params& P, uint32_t pass) {
+  // passes walk a 128-row block left to right (k-tile fastest): CTAs that run together read
+  // neighbouring 256-byte pieces of the same rows (DRAM page locality); the storage index is k-tile major
+  const uint32_t mt = pass / P.k_tiles, kt = pass - mt * P.k_tiles;
+  const uint32_t tile = kt * P.m_tiles + mt;
   uint4 x[FAST_UNITS], y[FAST_UNITS];
   const uint32_t q = threadIdx.x & 7u, col = kt * 128u + q * 16u;
   const bool col_ok = col < P.cols;

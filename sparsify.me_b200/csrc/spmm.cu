@@ -295,20 +295,24 @@ int elementwise_grid(size_t items, int* grid) {
 // Every FMA needs one dynamically addressed B element, which can only come from shared memory, so
 // the kernel is bound by shared-memory wavefronts (128 B/clk/SM), not by the FMA pipe: a lane owns
 // CSR_TJ = 4 columns, one non-zero costs one broadcast LDS.64 (value + column) plus four LDS.32 for
-// four FMAs.  CTA tile = (16 warps x RPW rows) x 128 columns; K is walked in chunks of 192 rows of
-// B staged as sB[column][k] (odd row pitch: conflict-free both for the coalesced fill along k and
-// for the per-non-zero reads across columns); two CTAs per SM, so one stages while the other
-// multiplies.  A warp reads the non-zeros of a row 32 at a time with one coalesced request,
-// compacts the ones that fall into the staged chunk into a per-warp scratch line and replays them.
-// With ascending columns inside a row (what spfy_threshold_to_coo emits; `*sorted` says so) a
-// per-row cursor makes this one visit per non-zero; otherwise every chunk rescans the row.
-// The C tile goes back through shared memory so the column-major stores run along rows.
+// four FMAs.  CTA tile = (16 warps x RPW rows) x 128 columns, one CTA per SM; K is walked in chunks
+// of 192 rows of B staged as sB[column][k] (odd row pitch: conflict-free both for the fill along k
+// and for the per-non-zero reads across columns).  The fill is software-pipelined through
+// registers: the 48 floats a thread contributes to chunk c+1 are requested before chunk c is
+// multiplied and stored after it, so a whole chunk (96 KiB per SM) is in flight under the math.
+// A warp reads the non-zeros of a row 32 at a time with one coalesced request, compacts the ones
+// that fall into the staged chunk into a per-warp scratch line and replays them.  With ascending
+// columns inside a row (what spfy_threshold_to_coo emits; `*sorted` says so) a per-row cursor makes
+// this one visit per non-zero; otherwise every chunk rescans the row.  The C tile goes back through
+// shared memory so the column-major stores run along rows.
 // ------------------------------------------------------------------------
 constexpr int CSR_WARPS = 16;
+constexpr int CSR_THREADS = CSR_WARPS * 32;
 constexpr int CSR_TN = 128;
 constexpr int CSR_TJ = CSR_TN / 32;
 constexpr int CSR_KC = 192;
 constexpr int CSR_PITCH = CSR_KC + 1;
+constexpr int CSR_PF = CSR_TN * CSR_KC / CSR_THREADS;  // 48 floats per thread and chunk
 
 struct CsrSpmmParams {
   const int32_t* row_ptr;
@@ -337,23 +341,101 @@ csr_check_sorted_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __re
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(sorted, 0);
 }
 
+// the 48 floats of one thread for the chunk starting at k0.  `wide`: a quarter warp per column and
+// request (8 lanes x 16 bytes = one line; the four columns of a request fall into four different
+// bank groups, so the scalar stores are conflict-free); otherwise a warp per column, lanes along k.
+__device__ __forceinline__ void csr_chunk_load(float (&pf)[CSR_PF], const CsrSpmmParams& P, const size_t* colB,
+                                               uint32_t k0, uint32_t kn, bool wide, uint32_t warp, uint32_t lane) {
+  if (wide) {
+    const uint32_t l8 = lane & 7u;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t jj = s * 64 + warp * 4 + (lane >> 3);
+      const size_t off = colB[jj];
+      const float4* src = reinterpret_cast<const float4*>(P.B + (off == ~(size_t)0 ? 0 : off) + k0);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (off != ~(size_t)0) v = __ldg(src + q * 8 + l8);
+        pf[(s * 6 + q) * 4 + 0] = v.x;
+        pf[(s * 6 + q) * 4 + 1] = v.y;
+        pf[(s * 6 + q) * 4 + 2] = v.z;
+        pf[(s * 6 + q) * 4 + 3] = v.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const uint32_t jj = s * 16 + warp;
+      const size_t off = colB[jj];
+      const float* src = P.B + (off == ~(size_t)0 ? 0 : off) + k0;
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const uint32_t kk = u * 32 + lane;
+        pf[s * 6 + u] = (off != ~(size_t)0 && kk < kn) ? __ldg(src + kk) : 0.f;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void csr_chunk_store(const float (&pf)[CSR_PF], float* sB, bool wide, uint32_t warp,
+                                                uint32_t lane) {
+  if (wide) {
+    const uint32_t l8 = lane & 7u;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      float* dst = sB + (s * 64 + warp * 4 + (lane >> 3)) * CSR_PITCH + l8 * 4;
+#pragma unroll
+      for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[q * 32 + i] = pf[(s * 6 + q) * 4 + i];
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      float* dst = sB + (s * 16 + warp) * CSR_PITCH + lane;
+#pragma unroll
+      for (int u = 0; u < 6; ++u) dst[u * 32] = pf[s * 6 + u];
+    }
+  }
+}
+
 template <int RPW>
-__global__ void __launch_bounds__(CSR_WARPS * 32, 2)
+__global__ void __launch_bounds__(CSR_THREADS, 1)
 spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   constexpr int TM = CSR_WARPS * RPW;
   extern __shared__ float smem_f[];
   float* sB = smem_f;                                                         // [CSR_TN][CSR_PITCH]
   uint2* scratch = reinterpret_cast<uint2*>(smem_f + CSR_TN * CSR_PITCH) + (threadIdx.x >> 5) * 32;
+  size_t* colB = reinterpret_cast<size_t*>(smem_f + CSR_TN * CSR_PITCH + CSR_WARPS * 64);  // [CSR_TN]
+  size_t* colC = colB + CSR_TN;                                                              // [CSR_TN]
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool sorted = *P.sorted != 0;
   const uint32_t nnz_total = (uint32_t)P.row_ptr[P.m];
   const uint64_t ncols = (uint64_t)P.n * P.num_batches;
   const uint32_t tiles = P.row_tiles * P.col_tiles;
+  const uint32_t nchunks = (P.k + CSR_KC - 1) / CSR_KC;
 
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const uint32_t rt = tile % P.row_tiles, ct = tile / P.row_tiles;  // row tile fastest: CTAs that
     const uint32_t i0 = rt * TM + warp * RPW;                          // share B columns run together
     const uint64_t j0 = (uint64_t)ct * CSR_TN;
+
+    __syncthreads();  // the previous tile's C stores have left shared memory
+    if (threadIdx.x < CSR_TN) {
+      // element offsets of this tile's columns inside B and C (~0: past the last column)
+      const uint64_t J = j0 + threadIdx.x;
+      size_t ob = ~(size_t)0, oc = ~(size_t)0;
+      if (J < ncols) {
+        const uint32_t bt = ncols <= 0xffffffffull ? (uint32_t)J / P.n : (uint32_t)(J / P.n);
+        const size_t jc = (size_t)(J - (uint64_t)bt * P.n);
+        ob = (size_t)bt * P.strideB + jc * P.ldb;
+        oc = (size_t)bt * P.strideC + jc * P.ldc;
+      }
+      colB[threadIdx.x] = ob;
+      colC[threadIdx.x] = oc;
+    }
+    __syncthreads();
 
     uint32_t cur[RPW];  // scan position of every row (row ends are re-read per chunk: registers are scarce)
     float acc[RPW][CSR_TJ];
@@ -365,46 +447,19 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
       for (int j = 0; j < CSR_TJ; ++j) acc[r][j] = 0.f;
     }
 
-    for (uint32_t k0 = 0; k0 < P.k; k0 += CSR_KC) {
+    float pf[CSR_PF];
+    csr_chunk_load(pf, P, colB, 0, min((uint32_t)CSR_KC, P.k), P.vec && P.k >= (uint32_t)CSR_KC, warp, lane);
+
+    for (uint32_t ch = 0; ch < nchunks; ++ch) {
+      const uint32_t k0 = ch * CSR_KC;
       const uint32_t kn = min((uint32_t)CSR_KC, P.k - k0);
-      __syncthreads();  // everyone is done with the previous chunk (or the previous tile's C)
-      // ---- stage B[k0 : k0+kn, j0 : j0+128] as sB[column][k] ----
-      if (P.vec && kn == (uint32_t)CSR_KC) {
-        // half a warp per column: 16 lanes x 3 x 16 bytes = 192 floats
-        const uint32_t hl = lane & 15u;
-#pragma unroll
-        for (int s = 0; s < CSR_TN / (2 * CSR_WARPS); ++s) {
-          const uint32_t jj = s * (2 * CSR_WARPS) + warp * 2 + (lane >> 4);
-          const uint64_t J = j0 + jj;
-          float4 v[3];
-          if (J < ncols) {
-            const uint32_t bt = (uint32_t)(J / P.n);
-            const float* src = P.B + (size_t)bt * P.strideB + (size_t)(J - (uint64_t)bt * P.n) * P.ldb + k0;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(src) + q * 16 + hl);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          float* dst = sB + jj * CSR_PITCH + hl * 4;
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            dst[q * 64 + 0] = v[q].x;
-            dst[q * 64 + 1] = v[q].y;
-            dst[q * 64 + 2] = v[q].z;
-            dst[q * 64 + 3] = v[q].w;
-          }
-        }
-      } else {
-        for (uint32_t jj = warp; jj < (uint32_t)CSR_TN; jj += CSR_WARPS) {
-          const uint64_t J = j0 + jj;
-          const bool ok = J < ncols;
-          const uint32_t bt = ok ? (uint32_t)(J / P.n) : 0u;
-          const float* src = P.B + (size_t)bt * P.strideB + (size_t)(ok ? J - (uint64_t)bt * P.n : 0) * P.ldb + k0;
-          for (uint32_t kk = lane; kk < kn; kk += 32) sB[jj * CSR_PITCH + kk] = ok ? __ldg(src + kk) : 0.f;
-        }
-      }
+      if (ch) __syncthreads();  // everyone is done with the previous chunk
+      csr_chunk_store(pf, sB, P.vec && kn == (uint32_t)CSR_KC, warp, lane);
       __syncthreads();
+      if (ch + 1 < nchunks) {
+        const uint32_t k1 = k0 + CSR_KC, kn1 = min((uint32_t)CSR_KC, P.k - k1);
+        csr_chunk_load(pf, P, colB, k1, kn1, P.vec && kn1 == (uint32_t)CSR_KC, warp, lane);
+      }
 
       // ---- multiply: every warp walks its RPW rows ----
       const uint32_t k_end = k0 + kn;
@@ -480,12 +535,12 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
       for (int j = 0; j < CSR_TJ; ++j) sC[(lane + 32 * j) * (TM + 1) + warp * RPW + r] = acc[r][j];
     __syncthreads();
     const uint32_t rbase = rt * TM;
-    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * TM); idx += CSR_WARPS * 32) {
+#pragma unroll 4
+    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * TM); idx += CSR_THREADS) {
       const uint32_t jj = idx / TM, i = idx % TM;
-      const uint64_t J = j0 + jj;
-      if (J < ncols && rbase + i < P.m) {
-        const uint32_t bt = (uint32_t)(J / P.n);
-        float* dst = P.C + (size_t)bt * P.strideC + (size_t)(J - (uint64_t)bt * P.n) * P.ldc + rbase + i;
+      const size_t oc = colC[jj];
+      if (oc != ~(size_t)0 && rbase + i < P.m) {
+        float* dst = P.C + oc + rbase + i;
         float out = P.alpha * sC[jj * (TM + 1) + i];
         if (P.beta != 0.f) out += P.beta * *dst;
         *dst = out;
@@ -497,22 +552,20 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
 template <int RPW>
 int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
   constexpr int TM = CSR_WARPS * RPW;
-  size_t smem = ((size_t)CSR_TN * CSR_PITCH) * 4 + (size_t)CSR_WARPS * 32 * 8;
+  size_t smem = ((size_t)CSR_TN * CSR_PITCH) * 4;
   const size_t c_tile = (size_t)CSR_TN * (TM + 1) * 4;
   if (smem < c_tile) smem = c_tile;
+  smem += (size_t)CSR_WARPS * 32 * 8 + 2 * CSR_TN * sizeof(size_t);  // scratch lines + column offsets
   static std::atomic<int> attr_set[64];
   int dev = 0;
   SPFY_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63].load()) {
     SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two CTAs per SM need the full shared-memory carve-out
-    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      (int)cudaSharedmemCarveoutMaxShared));
     attr_set[dev & 63].store(1);
   }
   const uint32_t tiles = P.row_tiles * P.col_tiles;
-  const uint32_t grid = tiles < (uint32_t)(2 * sm_count) ? tiles : (uint32_t)(2 * sm_count);
-  spmm_csr_kernel<RPW><<<grid, CSR_WARPS * 32, smem, s>>>(P);
+  const uint32_t grid = tiles < (uint32_t)sm_count ? tiles : (uint32_t)sm_count;
+  spmm_csr_kernel<RPW><<<grid, CSR_THREADS, smem, s>>>(P);
   SPFY_LAUNCH_OK("spmm_csr_kernel");
   return SPFY_OK;
 }
@@ -635,12 +688,12 @@ int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batch
   P.vec = ((uintptr_t)B % 16 == 0) && ldb % 4 == 0 && strideB % 4 == 0;
   const size_t total_cols = n * num_batches;
   const size_t col_tiles = ceil_div(total_cols, CSR_TN);
-  // 64-row tiles (16 warps x 4 rows): 128-row tiles would halve the re-staging of B for m > 64, but
-  // their 32 accumulators per lane do not fit the 64-register budget of two 512-thread CTAs per SM
-  P.row_tiles = (uint32_t)ceil_div(m, 64);
+  // 128-row tiles halve the re-staging of B when A has more than 64 rows
+  const bool tall = m > 64;
+  P.row_tiles = (uint32_t)ceil_div(m, tall ? 128 : 64);
   if (col_tiles * P.row_tiles >= (1ull << 32)) return fail(SPFY_E_UNSUPPORTED, "spmm_csr: too many tiles");
   P.col_tiles = (uint32_t)col_tiles;
-  return launch_spmm_csr<4>(P, di.sm_count, s);
+  return tall ? launch_spmm_csr<8>(P, di.sm_count, s) : launch_spmm_csr<4>(P, di.sm_count, s);
 }
 
 int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,

@@ -101,7 +101,8 @@ struct LaunchParams {
   uint32_t res_off, res_e_off;                 // resident A values / metadata
   uint32_t c_off, bar_off;
   uint32_t epi_warps;  // 8: one column half per warp; 4: warps 2-5 do both halves
-  uint32_t dbg;        // development switches (SPFY_SPMMA_DEBUG): 2 no epilogue work, 4 no B loads, 8 no MMAs
+  uint32_t dbg;        // development switches (SPFY_SPMMA_DEBUG): 2 no epilogue work, 4 no B loads, 8 no MMAs,
+                       // 16 no streamed A loads (timing experiments only: results are garbage)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -359,7 +360,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       const uint8_t *a_vals = nullptr, *a_meta = nullptr;
       uint32_t pm = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, b3d = 0;
       uint64_t hint_b = 0;
-      const bool no_b = (L.dbg & 4u) != 0;
+      const bool no_b = (L.dbg & 4u) != 0, no_a = (L.dbg & 16u) != 0;
       for (; W.valid(); W.next()) {
         const ProblemDev* P = W.current();
         if (P != last) {
@@ -406,13 +407,13 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const uint8_t* av = a_vals + (size_t)mt0 * A_TILE_BYTES;
         const uint8_t* am = a_meta + (size_t)mt0 * E_TILE_BYTES;
         const size_t av_step = (size_t)m_tiles * A_TILE_BYTES, am_step = (size_t)m_tiles * E_TILE_BYTES;
-        const uint32_t tx = (no_b ? 0u : (uint32_t)B_STAGE_BYTES) + (resident ? 0u : a_bytes + e_bytes);
+        const uint32_t tx = (no_b ? 0u : (uint32_t)B_STAGE_BYTES) + (resident || no_a ? 0u : a_bytes + e_bytes);
         for (uint32_t kt = 0; kt < k_tiles; ++kt) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1u);
           const uint32_t full = bar_full + stage * 8;
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
           if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
-          if (!resident) {
+          if (!resident && !no_a) {
             bulk_load_1d(sbase + L.a_off, av, a_bytes, full, HINT_EVICT_LAST);
             bulk_load_1d(sbase + L.e_off, am, e_bytes, full, HINT_EVICT_LAST);
             av += av_step;
@@ -951,6 +952,10 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
       ln.L.num_problems = ln.count;
       ln.L.total_units = units;
       ln.L.idesc = make_idesc(dtype, opB);
+      {
+        const char* e = getenv("SPFY_SPMMA_DEBUG");
+        ln.L.dbg = e ? (uint32_t)atoi(e) : 0u;
+      }
       ln.grid = (int)(units < (uint32_t)di.sm_count ? units : (uint32_t)di.sm_count);
       plan->launches.push_back(ln);
     }

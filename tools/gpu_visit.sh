@@ -12,6 +12,7 @@ spmm) python tools/spmm_sweep.py --tag $TAG > $OUT/spmm_sweep_$TAG.csv 2>&1; ech
 sweep) python tools/layer_sweep.py --plan --tag $TAG > $OUT/sweep_$TAG.csv 2>&1; echo "sweep rc=$?";;
 ref) python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?";;
 dbg) for d in 2 8 10; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --tag dbg$d > $OUT/sweep_${TAG}_dbg$d.csv 2>&1; echo "dbg$d rc=$?"; done;;
+plandbg) for d in 0 2 8 10 16 18 26; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --plan-only --tag dbg$d > $OUT/plan_${TAG}_dbg$d.txt 2>&1; echo "plan dbg$d rc=$?"; done;;
 ncu_spmm)
   CMD="python tools/spmm_one.py 64 576 12544 32 0.9"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--only", default="", help="M,K,N filter")
     ap.add_argument("--plan", action="store_true", help="also time the whole table as ONE plan (grouped launches)")
+    ap.add_argument("--plan-only", action="store_true", help="skip the per-shape part")
     args = ap.parse_args()
     import torch
     spfy = ge.load_package()
@@ -41,9 +42,14 @@ def main():
     hbm, tc = peaks["hbm_gbs"], 2 * peaks["bf16_tflops"]
     cnt = collections.Counter(spfy.shapes.to_gemm(s, "weights", args.batch) for s in spfy.shapes.read_shapes(args.csv))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     print("tag,M,K,N,count,us,GBs,frac_hbm,TFLOPs,frac_tc,roofline_us,frac_roofline")
     tot_t = tot_r = 0.0
     for g, c in sorted(cnt.items(), key=lambda kv: (-kv[0].N, kv[0].M, kv[0].K)):
+        by, fl = spfy.shapes.spmma_bytes(g), spfy.shapes.spmma_flops(g)
+        if args.plan_only:
+            tot_r += max(by / hbm / 1e3, fl / tc / 1e6) * c
+            continue
         if args.only and args.only != f"{g.M},{g.K},{g.N}":
             continue
         w = (torch.rand(g.M, g.K, device=dev) * 2 - 1).to(tdt)
@@ -74,8 +80,9 @@ def main():
         print(f"{args.tag},{g.M},{g.K},{g.N},{c},{us:.1f},{by/us/1e3:.0f},{by/us/1e3/hbm:.3f},{fl/us/1e6:.1f},"
               f"{fl/us/1e6/tc:.3f},{roof:.1f},{roof/us:.3f}")
         del w, b, d, comp
-    print(f"# {args.tag} total {tot_t:.0f} us vs roofline {tot_r:.0f} us -> {tot_r/tot_t:.3f}")
-    if args.plan:
+    if tot_t:
+        print(f"# {args.tag} total {tot_t:.0f} us vs roofline {tot_r:.0f} us -> {tot_r/tot_t:.3f}")
+    if args.plan or args.plan_only:
         gemms = [spfy.shapes.to_gemm(s, "weights", args.batch) for s in spfy.shapes.read_shapes(args.csv)]
         problems = []
         for g in gemms:
