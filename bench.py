@@ -242,10 +242,11 @@ def run_reference(args):
     return 0
 
 
-def config_dict(args, nlayers):
+def config_dict(args, nlayers, launches=None):
+    how = f"one plan, {launches} persistent launches" if launches else "one plan of persistent launches"
     return {"workload": f"datasets/{args.csv}: all {nlayers} layers, weights orientation (M=C_out, K=C_in*kh*kw, "
                         f"N=H*W*b), b={args.batch} images per GPU, 2:4 magnitude prune+compress (one batched launch) "
-                        f"+ spmma of every layer (one plan, 3 persistent launches)",
+                        f"+ spmma of every layer ({how})",
             "csv": args.csv, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
             "l2_policy": "inputs larger than L2 (7.4 GB of distinct B/D buffers per step vs 126 MB L2)",
             "parallelism": f"batch-sharded x{args.gpus}, no data-path collective"}
@@ -282,6 +283,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
     spfy = ge.load_package()
     tdt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
@@ -418,9 +420,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
-        "config": config_dict(args, len(gemms)),
+        "config": config_dict(args, len(gemms), plan.launches),
         "clocks": clocks, "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "spmma_kernel (tcgen05.mma.sp, 3 persistent launches per step)", "achieved": achieved, "peak": hbm_peak,
+        "roofline": {"bound": "hbm", "kernel": f"spmma_kernel (tcgen05.mma.sp, {plan.launches} persistent launches per step)", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": spmma_bytes_step, "launches_per_step": plan.launches, "layers_per_step": len(layers),
                      "ms_per_step": spmma_ms,

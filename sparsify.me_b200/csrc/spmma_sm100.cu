@@ -101,6 +101,7 @@ struct LaunchParams {
   uint32_t res_off, res_e_off;                 // resident A values / metadata
   uint32_t c_off, bar_off;
   uint32_t epi_warps;  // 8: one column half per warp; 4: warps 2-5 do both halves
+  uint32_t bk;         // logical k per ring stage: 128, or 64 for the k <= 64 class (half-size stages)
   uint32_t dbg;        // development switches (SPFY_SPMMA_DEBUG): 2 no epilogue work, 4 no B loads, 8 no MMAs,
                        // 16 no streamed A loads (timing experiments only: results are garbage)
 };
@@ -324,6 +325,10 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
   const uint32_t tmem_ptr_off = L.bar_off + (2 * MAX_STAGES + 2 * ACC_SLOTS + 2) * 8;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + tmem_ptr_off);
 
+  // The launches of a plan are independent problems issued back to back with programmatic stream
+  // serialization: letting the next launch's CTAs in as soon as ours retire overlaps its ramp-up with
+  // our tail (nobody calls griddepcontrol.wait -- there is no data dependence between them).
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 1 && lane == 0) {
     for (uint32_t s = 0; s < (uint32_t)MAX_STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
@@ -407,18 +412,12 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const uint8_t* av = a_vals + (size_t)mt0 * A_TILE_BYTES;
         const uint8_t* am = a_meta + (size_t)mt0 * E_TILE_BYTES;
         const size_t av_step = (size_t)m_tiles * A_TILE_BYTES, am_step = (size_t)m_tiles * E_TILE_BYTES;
-        const uint32_t tx = (no_b ? 0u : (uint32_t)B_STAGE_BYTES) + (resident || no_a ? 0u : a_bytes + e_bytes);
+        const uint32_t tx = (no_b ? 0u : L.bk * (uint32_t)(BN * 2)) + (resident || no_a ? 0u : a_bytes + e_bytes);
         for (uint32_t kt = 0; kt < k_tiles; ++kt) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1u);
           const uint32_t full = bar_full + stage * 8;
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
           if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
-          if (!resident && !no_a) {
-            bulk_load_1d(sbase + L.a_off, av, a_bytes, full, HINT_EVICT_LAST);
-            bulk_load_1d(sbase + L.e_off, am, e_bytes, full, HINT_EVICT_LAST);
-            av += av_step;
-            am += am_step;
-          }
           if (no_b) {
           } else if (b3d) {
             // one box fills the stage: [2 groups of 64][128 outer rows][64]
@@ -427,11 +426,18 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           } else if (!OPB_T) {
             // B is k x n row-major: boxes of [128 rows of k][64 columns of n] -> MN-major SW128
             tma_load_2d(sbase, tmap_b, (int)(nt * BN), (int)(kt * BK), full, hint_b);
-            tma_load_2d(sbase + BK * 128, tmap_b, (int)(nt * BN + 64), (int)(kt * BK), full, hint_b);
+            tma_load_2d(sbase + L.bk * 128u, tmap_b, (int)(nt * BN + 64), (int)(kt * BK), full, hint_b);
           } else {
             // B is n x k row-major: boxes of [128 rows of n][64 columns of k] -> K-major SW128
             tma_load_2d(sbase, tmap_b, (int)(kt * BK), (int)(nt * BN), full, hint_b);
-            tma_load_2d(sbase + BN * 128, tmap_b, (int)(kt * BK + 64), (int)(nt * BN), full, hint_b);
+            if (L.bk == (uint32_t)BK) tma_load_2d(sbase + BN * 128, tmap_b, (int)(kt * BK + 64), (int)(nt * BN), full, hint_b);
+          }
+          // B first: it comes from DRAM and is the long pole of the stage; A and its metadata are L2 hits
+          if (!resident && !no_a) {
+            bulk_load_1d(sbase + L.a_off, av, a_bytes, full, HINT_EVICT_LAST);
+            bulk_load_1d(sbase + L.e_off, am, e_bytes, full, HINT_EVICT_LAST);
+            av += av_step;
+            am += am_step;
           }
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
@@ -448,7 +454,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       // constant halves of the shared-memory descriptors (the start address is OR-ed in per MMA)
       const uint64_t desc_a_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       const uint64_t desc_b_hi = OPB_T ? make_smem_desc(0, 16, 1024, LAYOUT_SW128)
-                                       : make_smem_desc(0, BK * 128, 1024, LAYOUT_SW128);
+                                       : make_smem_desc(0, L.bk * 128u, 1024, LAYOUT_SW128);
       const uint64_t desc_e_hi = make_smem_desc(0, 16, 128, LAYOUT_NONE);
       for (; W.valid(); W.next()) {
         const ProblemDev* P = W.current();
@@ -498,7 +504,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             for (uint32_t j = 0; j < 4; ++j) {
               if (j < nk) {
                 // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
-                // B: MN-major SW128 (8 k-rows per 1024 B atom, 64-column groups BK*128 apart) or
+                // B: MN-major SW128 (8 k-rows per 1024 B atom, 64-column groups bk*128 apart) or
                 //    K-major SW128 (two 64-wide k halves, 64 bytes per MMA inside a row)
                 const uint32_t sb = OPB_T ? sbase + (j >> 1) * (BN * 128) + (j & 1u) * 64u : sbase + j * (32u * 128u);
                 const uint64_t db = desc_b_hi | (uint64_t)((sb >> 4) & 0x3fffu);
@@ -668,13 +674,13 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t inner, 
 // (64, box_outer, 2) lands in shared memory as two consecutive 128B-swizzled (box_outer x 64)
 // blocks -- exactly the two halves of a B stage -- with ONE TMA instruction.
 int make_tmap_grouped(CUtensorMap* map, int dtype, const void* base, uint64_t inner, uint64_t outer,
-                      uint64_t ld, uint32_t box_outer) {
+                      uint64_t ld, uint32_t box_outer, uint32_t box_groups) {
   EncodeTiledFn enc;
   int rc = get_encoder(&enc);
   if (rc) return rc;
   cuuint64_t dims[3] = {64, outer, inner / 64};
   cuuint64_t strides[2] = {ld * 2, 128};
-  cuuint32_t box[3] = {64, box_outer, 2};
+  cuuint32_t box[3] = {64, box_outer, box_groups};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dtype == SPFY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -720,9 +726,15 @@ int validate(int dtype, const HostProblem& h, const char* who) {
 }
 
 // launch classes: problems of one class share a shared-memory geometry and one launch
-enum { CLASS_RESIDENT = 0, CLASS_STREAM_G1 = 1, CLASS_STREAM_G2 = 2, NUM_CLASSES = 3 };
+// resident classes differ in ring depth: the smaller the resident operand, the more B stages fit, and
+// more B in flight is what the HBM-bound shapes need (measured: 1/2/3/4 stages -> 0.45/0.69/0.79/0.93 of
+// the copy rate); k <= 64 gets half-size stages so that no stage is half empty.
+enum { CLASS_RES_K64 = 0, CLASS_RES_SMALL = 1, CLASS_RES_LARGE = 2, CLASS_STREAM_G1 = 3, CLASS_STREAM_G2 = 4,
+       NUM_CLASSES = 5 };
+inline bool is_resident_class(int cls) { return cls <= CLASS_RES_LARGE; }
 constexpr uint32_t BAR_BYTES = 512;
-constexpr uint32_t RES_MAX_BYTES = 96 * 1024;  // resident A (values + metadata)
+constexpr uint32_t RES_MAX_BYTES = 96 * 1024;    // resident A (values + metadata)
+constexpr uint32_t RES_SMALL_BYTES = 48 * 1024;  // ... small enough for a fourth 32 KiB stage
 
 size_t resident_bytes(size_t m, size_t k) {
   const size_t m_tiles = ceil_div(m, BM), k_tiles = ceil_div(k, 128);
@@ -732,7 +744,10 @@ size_t resident_bytes(size_t m, size_t k) {
 
 int classify(const HostProblem& h, bool grouped, int sm_count) {
   const size_t m_tiles = ceil_div(h.m, BM), n_tiles = ceil_div(h.n, BN);
-  if (resident_bytes(h.m, h.k) <= RES_MAX_BYTES && n_tiles >= (size_t)sm_count) return CLASS_RESIDENT;
+  if (resident_bytes(h.m, h.k) <= RES_MAX_BYTES && n_tiles >= (size_t)sm_count) {
+    if (h.k <= 64) return CLASS_RES_K64;
+    return resident_bytes(h.m, h.k) <= RES_SMALL_BYTES ? CLASS_RES_SMALL : CLASS_RES_LARGE;
+  }
   if (m_tiles >= 2 && (grouped || ceil_div(m_tiles, 2) * n_tiles >= 2 * (size_t)sm_count))
     return CLASS_STREAM_G2;
   return CLASS_STREAM_G1;
@@ -740,15 +755,19 @@ int classify(const HostProblem& h, bool grouped, int sm_count) {
 
 // fill the device view of one problem (tensor maps included); unit_begin is set by the caller
 int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
+  const uint32_t bk = cls == CLASS_RES_K64 ? 64u : (uint32_t)BK;
   memset(d, 0, sizeof(*d));
   int rc;
   // B: inner = contiguous dimension (n for opB = N, k for opB = T), outer = the other one
   const size_t b_inner = h.opB == SPFY_OP_N ? h.n : h.k, b_outer = h.opB == SPFY_OP_N ? h.k : h.n;
   d->b3d = b_inner % 64 == 0;
   rc = SPFY_OK;
-  if (d->b3d && make_tmap_grouped(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 128) != SPFY_OK)
-    d->b3d = 0;  // the driver refused the grouped view: fall back to two 2-D boxes per stage
-  if (!d->b3d) rc = make_tmap_2d(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 64, 128);
+  // one stage of B: opB = N -> bk rows of k x 128 columns (two 64-column groups);
+  //                 opB = T -> 128 rows of n x bk columns of k (bk/64 groups)
+  const uint32_t box_outer = h.opB == SPFY_OP_N ? bk : 128u, box_groups = h.opB == SPFY_OP_N ? 2u : bk / 64u;
+  if (d->b3d && make_tmap_grouped(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, box_outer, box_groups) != SPFY_OK)
+    d->b3d = 0;  // the driver refused the grouped view: fall back to 2-D boxes (64 inner elements each)
+  if (!d->b3d) rc = make_tmap_2d(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 64, box_outer);
   if (rc) return rc;
   rc = make_tmap_2d(&d->tmap_d, dtype, h.D, h.n, h.m, h.ldd, 64, 32);
   if (rc) return rc;
@@ -762,7 +781,7 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   d->m_tiles = (uint32_t)ceil_div(h.m, BM);
   d->k_tiles = (uint32_t)ceil_div(h.k, 128);
   d->n_tiles = (uint32_t)ceil_div(h.n, BN);
-  d->resident = cls == CLASS_RESIDENT;
+  d->resident = is_resident_class(cls);
   d->G = (cls == CLASS_STREAM_G1) ? 1u : (d->m_tiles >= 2 ? 2u : 1u);
   d->m_groups = (uint32_t)ceil_div(d->m_tiles, d->G);
   d->units = d->m_groups * d->n_tiles;
@@ -778,8 +797,9 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
 void geometry(int cls, uint32_t res_vals, uint32_t res_meta, LaunchParams* L, uint32_t* smem_bytes) {
   uint32_t stage, res = 0;
   L->a_off = B_STAGE_BYTES;
-  if (cls == CLASS_RESIDENT) {
-    stage = B_STAGE_BYTES;
+  L->bk = cls == CLASS_RES_K64 ? 64u : (uint32_t)BK;
+  if (is_resident_class(cls)) {
+    stage = L->bk * (uint32_t)(BN * 2);
     L->e_off = stage;
     res = (uint32_t)round_up(res_vals, 1024) + (uint32_t)round_up(res_meta, 1024);
     L->epi_warps = NUM_EPI_WARPS;  // small K: the epilogue is the hot part
@@ -793,6 +813,10 @@ void geometry(int cls, uint32_t res_vals, uint32_t res_meta, LaunchParams* L, ui
   const uint32_t fixed = 1024 /*alignment slack*/ + c_bytes + BAR_BYTES + res;
   uint32_t stages = (SMEM_LIMIT - fixed) / stage;
   if (stages > (uint32_t)MAX_STAGES) stages = MAX_STAGES;
+  if (const char* cap = getenv("SPFY_SPMMA_STAGES")) {  // tuning experiment: fewer ring stages
+    const uint32_t c = (uint32_t)atoi(cap);
+    if (c >= 1 && c < stages) stages = c;
+  }
   L->stages = stages;
   L->stage_bytes = stage;
   L->res_off = stages * stage;
@@ -810,7 +834,8 @@ uint32_t make_idesc(int dtype, int opB) {
 }
 
 template <bool BF16, bool OPB_T>
-int launch_t(const ProblemDev& single, const LaunchParams& L, uint32_t smem, int grid, cudaStream_t s) {
+int launch_t(const ProblemDev& single, const LaunchParams& L, uint32_t smem, int grid, cudaStream_t s,
+             bool overlap_previous) {
   static std::atomic<int> attr_set[64];
   int dev = 0;
   SPFY_CUDA_OK(cudaGetDevice(&dev));
@@ -819,18 +844,31 @@ int launch_t(const ProblemDev& single, const LaunchParams& L, uint32_t smem, int
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set[dev & 63].store(1);
   }
-  spmma_kernel<BF16, OPB_T><<<grid, NUM_THREADS, smem, s>>>(single, L);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = overlap_previous ? 1 : 0;
+  SPFY_CUDA_OK(cudaLaunchKernelEx(&cfg, spmma_kernel<BF16, OPB_T>, single, L));
   SPFY_LAUNCH_OK("spmma_kernel");
   return SPFY_OK;
 }
 
+// overlap_previous: the kernel launched just before on this stream is another launch of the same plan
 int launch(int dtype, int opB, const ProblemDev& single, const LaunchParams& L, uint32_t smem, int grid,
-           cudaStream_t s) {
+           cudaStream_t s, bool overlap_previous = false) {
   if (dtype == SPFY_BF16)
-    return opB == SPFY_OP_N ? launch_t<true, false>(single, L, smem, grid, s)
-                            : launch_t<true, true>(single, L, smem, grid, s);
-  return opB == SPFY_OP_N ? launch_t<false, false>(single, L, smem, grid, s)
-                          : launch_t<false, true>(single, L, smem, grid, s);
+    return opB == SPFY_OP_N ? launch_t<true, false>(single, L, smem, grid, s, overlap_previous)
+                            : launch_t<true, true>(single, L, smem, grid, s, overlap_previous);
+  return opB == SPFY_OP_N ? launch_t<false, false>(single, L, smem, grid, s, overlap_previous)
+                          : launch_t<false, true>(single, L, smem, grid, s, overlap_previous);
 }
 
 uint32_t res_rows(const ProblemDev& d) { return d.m_tiles == 1 ? (uint32_t)round_up(d.m, 16) : 128u; }
@@ -980,9 +1018,12 @@ int spfy_spmma_plan_run(spfy_spmma_plan_t p, spfy_stream_t stream) {
   Plan* plan = (Plan*)p;
   ProblemDev dummy;
   memset(&dummy, 0, sizeof(dummy));
+  static const bool serial = getenv("SPFY_SPMMA_NO_OVERLAP") != nullptr;
+  bool first = true;
   for (const auto& ln : plan->launches) {
-    int rc = launch(plan->dtype, ln.opB, dummy, ln.L, ln.smem, ln.grid, (cudaStream_t)stream);
+    int rc = launch(plan->dtype, ln.opB, dummy, ln.L, ln.smem, ln.grid, (cudaStream_t)stream, !first && !serial);
     if (rc) return rc;
+    first = false;
   }
   return SPFY_OK;
 }

@@ -234,9 +234,11 @@ def test_spmma_matches_fp64_oracle(spfy, orc, cuda, M, K, N, dt):
 
 
 # one shape per launch class of the v2 kernel (single-problem entry point):
-#   resident A (whole compressed A in shared memory, N >= 148 tiles), streaming G=2 (two m-tiles share a
+#   resident A (whole compressed A in shared memory, N >= 148 tiles; three ring geometries), streaming G=2 (two m-tiles share a
 #   B slice), streaming G=1; ragged M / K / N edges in each
 CLASS_SHAPES = [(64, 147, 19008), (200, 72, 19080), (512, 128, 18944), (100, 576, 19000),  # resident
+                (64, 64, 19008), (256, 64, 19200), (200, 40, 19080), (130, 24, 18960),        # resident, k <= 64 (half stages)
+                (128, 512, 19008),                                                             # resident, large operand
                 (512, 200, 9600), (300, 264, 9480), (1024, 256, 4800),                       # stream, G=2
                 (128, 1152, 2048), (96, 2304, 1000)]                                         # stream, G=1
 
@@ -308,7 +310,8 @@ def test_spmma_plan_resnet18_table(spfy, cuda):
         assert float((q["out"].float() - ref).abs().max() / ref.abs().max()) < 2e-3
 
 
-@pytest.mark.parametrize("M,K,N", [(128, 256, 256), (64, 147 + 5, 520), (256, 1024, 136)])
+@pytest.mark.parametrize("M,K,N", [(128, 256, 256), (64, 147 + 5, 520), (256, 1024, 136), (64, 64, 19008),
+                                   (128, 48, 19200), (64, 256, 19008)])
 def test_spmma_transposed_b(spfy, orc, cuda, M, K, N):
     a_bits = rand_bits(orc, 0, (M, K), seed=91)
     bt_bits = rand_bits(orc, 0, (N, K), seed=92)

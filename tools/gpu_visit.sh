@@ -13,6 +13,14 @@ sweep) python tools/layer_sweep.py --plan --tag $TAG > $OUT/sweep_$TAG.csv 2>&1;
 ref) python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?";;
 dbg) for d in 2 8 10; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --tag dbg$d > $OUT/sweep_${TAG}_dbg$d.csv 2>&1; echo "dbg$d rc=$?"; done;;
 plandbg) for d in 0 2 8 10 16 18 26; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --plan-only --tag dbg$d > $OUT/plan_${TAG}_dbg$d.txt 2>&1; echo "plan dbg$d rc=$?"; done;;
+pfsweep) for d in 0 2 4 6 8 12 16 24; do SPFY_SPMMA_PF=$d python tools/layer_sweep.py --plan-only --tag pf$d > $OUT/plan_${TAG}_pf$d.txt 2>&1; echo "plan pf$d rc=$?"; grep "^#" $OUT/plan_${TAG}_pf$d.txt | sed 's/{[^}]*}//'; done;;
+g1exp) SPFY_SPMMA_FORCE_G1=1 python tools/layer_sweep.py --plan-only --tag g1 > $OUT/plan_${TAG}_g1.txt 2>&1; grep "^#" $OUT/plan_${TAG}_g1.txt | sed 's/{[^}]*}//';;
+stexp) for c in 1 2; do SPFY_SPMMA_STAGES=$c python tools/layer_sweep.py --plan-only --tag st$c > $OUT/plan_${TAG}_st$c.txt 2>&1; grep "^#" $OUT/plan_${TAG}_st$c.txt | sed 's/{[^}]*}//'; done;;
+examples)
+  ( cd examples && ./bin/sparsify 12544 147 && ./bin/spmma 64 25088 576 32 && ./bin/spmm 64 64 128 4 && ./bin/batched_coo 64 196 576 8 && ./bin/gemm 64 196 576 8 && ./bin/sweep ../datasets/resnet18.csv weights ) > $OUT/examples_$TAG.log 2>&1; echo "examples rc=$?"; tail -5 $OUT/examples_$TAG.log;;
+mg)
+  NG=${NGPUS:-2}
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --steps 50 --warmup 5 > $OUT/bench_mg${NG}_$TAG.json 2> $OUT/bench_mg${NG}_$TAG.err; echo "mg rc=$?"; tail -c 600 $OUT/bench_mg${NG}_$TAG.json;;
 ncu_spmm)
   CMD="python tools/spmm_one.py 64 576 12544 32 0.9"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
