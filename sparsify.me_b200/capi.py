@@ -11,7 +11,7 @@ from ctypes import (c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint
                     POINTER)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsparsifyme_b200.so")
+LIB_PATH = os.environ.get("SPFY_LIB") or os.path.join(HERE, "lib", "libsparsifyme_b200.so")  # SPFY_LIB: A/B builds
 
 # enums of include/spfy_b200.h
 F16, BF16, F32, F64 = 0, 1, 2, 3

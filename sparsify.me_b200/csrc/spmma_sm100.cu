@@ -287,6 +287,31 @@ __device__ __forceinline__ uint32_t rows_valid_of(uint32_t m, uint32_t mt) {
   return left >= (uint32_t)BM ? (uint32_t)BM : ((left + 15u) & ~15u);
 }
 
+// The producer and MMA roles are executed by a whole, converged warp whose lanes all hold the same
+// values; only the instruction that must be issued once sits under `if (leader)`.  ptxas can then keep
+// descriptors, coordinates and barrier addresses in uniform registers and feed UTMALDG / UTCHMMA
+// directly.  (Running those loops inside `if (lane == 0)` instead makes every operand "possibly
+// divergent": each MMA was then preceded by an ELECT + seven R2UR.BROADCAST waterfall, ~25 scalar
+// instructions per MMA on the one thread the whole SM waits for.)  Values that come from memory are
+// re-broadcast from lane 0 so that the compiler can prove them uniform.
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t uni(uint64_t v) {
+  return (uint64_t)uni((uint32_t)v) | (uint64_t)uni((uint32_t)(v >> 32)) << 32;
+}
+template <typename T>
+__device__ __forceinline__ const T* uni(const T* p) { return reinterpret_cast<const T*>(uni((uint64_t)(uintptr_t)p)); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // All three roles walk the same sequence of units: u = blockIdx.x, blockIdx.x + gridDim.x, ...
 struct UnitWalker {
   const ProblemDev* single;
@@ -301,6 +326,7 @@ struct UnitWalker {
   // problem of the current unit (units are visited in increasing order, so p only advances)
   __device__ __forceinline__ const ProblemDev* current() {
     while (p + 1 < num_problems && u >= prob(p)->unit_begin + prob(p)->units) ++p;
+    p = uni(p);  // the table reads above hide from the compiler that every lane took the same path
     return prob(p);
   }
   __device__ __forceinline__ void next() { u += gridDim.x; }
@@ -355,8 +381,9 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
   // copied into registers first and the ring position is advanced without divisions.
 
   if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
+    // ===================== producer (whole warp, one lane issues) =====================
+    {
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0;  // ring position (continuous over units)
       uint32_t res_loads = 0;         // resident (re)loads issued so far
       const ProblemDev* res_owner = nullptr;
@@ -371,11 +398,11 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         if (P != last) {
           last = P;
           tmap_b = &P->tmap_b;
-          prefetch_tmap(tmap_b);
-          a_vals = P->a_vals; a_meta = P->a_meta;
-          pm = P->m; k_tiles = P->k_tiles; m_tiles = P->m_tiles; b3d = P->b3d;
-          m_groups = P->m_groups; G = P->G; resident = P->resident; unit_begin = P->unit_begin;
-          hint_b = P->hint_b;
+          if (leader) prefetch_tmap(tmap_b);
+          a_vals = uni(P->a_vals); a_meta = uni(P->a_meta);
+          pm = uni(P->m); k_tiles = uni(P->k_tiles); m_tiles = uni(P->m_tiles); b3d = uni(P->b3d);
+          m_groups = uni(P->m_groups); G = uni(P->G); resident = uni(P->resident); unit_begin = uni(P->unit_begin);
+          hint_b = uni(P->hint_b);
         }
         const uint32_t local = W.u - unit_begin;
         const uint32_t nt = local / m_groups, mg = local - nt * m_groups;
@@ -384,22 +411,24 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         if (resident && res_owner != P) {
           // (re)load the whole compressed A of this problem into the resident region
           mbar_wait(bar_res_empty, (res_loads & 1u) ^ 1u);
-          if (m_tiles == 1) {
-            // a single, possibly short, m-tile: compact rows, one copy per k-tile and array
-            const uint32_t rv = rows_valid_of(pm, 0);
-            mbar_expect_tx(bar_res_full, k_tiles * rv * 144u);
-            for (uint32_t kt = 0; kt < k_tiles; ++kt) {
-              bulk_load_1d(smem_base + L.res_off + kt * rv * 128u, a_vals + (size_t)kt * A_TILE_BYTES, rv * 128u,
-                           bar_res_full, HINT_EVICT_LAST);
-              bulk_load_1d(smem_base + L.res_e_off + kt * rv * 16u, a_meta + (size_t)kt * E_TILE_BYTES, rv * 16u,
-                           bar_res_full, HINT_EVICT_LAST);
+          if (leader) {
+            if (m_tiles == 1) {
+              // a single, possibly short, m-tile: compact rows, one copy per k-tile and array
+              const uint32_t rv = rows_valid_of(pm, 0);
+              mbar_expect_tx(bar_res_full, k_tiles * rv * 144u);
+              for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+                bulk_load_1d(smem_base + L.res_off + kt * rv * 128u, a_vals + (size_t)kt * A_TILE_BYTES, rv * 128u,
+                             bar_res_full, HINT_EVICT_LAST);
+                bulk_load_1d(smem_base + L.res_e_off + kt * rv * 16u, a_meta + (size_t)kt * E_TILE_BYTES, rv * 16u,
+                             bar_res_full, HINT_EVICT_LAST);
+              }
+            } else {
+              // the arrays are contiguous (padding rows included): two copies fetch everything
+              const uint32_t tiles = k_tiles * m_tiles;
+              mbar_expect_tx(bar_res_full, tiles * (uint32_t)(A_TILE_BYTES + E_TILE_BYTES));
+              bulk_load_1d(smem_base + L.res_off, a_vals, tiles * A_TILE_BYTES, bar_res_full, HINT_EVICT_LAST);
+              bulk_load_1d(smem_base + L.res_e_off, a_meta, tiles * E_TILE_BYTES, bar_res_full, HINT_EVICT_LAST);
             }
-          } else {
-            // the arrays are contiguous (padding rows included): two copies fetch everything
-            const uint32_t tiles = k_tiles * m_tiles;
-            mbar_expect_tx(bar_res_full, tiles * (uint32_t)(A_TILE_BYTES + E_TILE_BYTES));
-            bulk_load_1d(smem_base + L.res_off, a_vals, tiles * A_TILE_BYTES, bar_res_full, HINT_EVICT_LAST);
-            bulk_load_1d(smem_base + L.res_e_off, a_meta, tiles * E_TILE_BYTES, bar_res_full, HINT_EVICT_LAST);
           }
           res_owner = P;
           ++res_loads;
@@ -412,40 +441,43 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const uint8_t* av = a_vals + (size_t)mt0 * A_TILE_BYTES;
         const uint8_t* am = a_meta + (size_t)mt0 * E_TILE_BYTES;
         const size_t av_step = (size_t)m_tiles * A_TILE_BYTES, am_step = (size_t)m_tiles * E_TILE_BYTES;
-        const uint32_t tx = (no_b ? 0u : L.bk * (uint32_t)(BN * 2)) + (resident || no_a ? 0u : a_bytes + e_bytes);
-        for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+        const bool stream_a = !resident && !no_a;
+        const uint32_t tx = (no_b ? 0u : L.bk * (uint32_t)(BN * 2)) + (stream_a ? a_bytes + e_bytes : 0u);
+        for (uint32_t kt = 0; kt < k_tiles; ++kt, av += av_step, am += am_step) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1u);
           const uint32_t full = bar_full + stage * 8;
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
-          if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
-          if (no_b) {
-          } else if (b3d) {
-            // one box fills the stage: [2 groups of 64][128 outer rows][64]
-            if (!OPB_T) tma_load_3d(sbase, tmap_b, 0, (int)(kt * BK), (int)(nt * 2), full, hint_b);
-            else        tma_load_3d(sbase, tmap_b, 0, (int)(nt * BN), (int)(kt * 2), full, hint_b);
-          } else if (!OPB_T) {
-            // B is k x n row-major: boxes of [128 rows of k][64 columns of n] -> MN-major SW128
-            tma_load_2d(sbase, tmap_b, (int)(nt * BN), (int)(kt * BK), full, hint_b);
-            tma_load_2d(sbase + L.bk * 128u, tmap_b, (int)(nt * BN + 64), (int)(kt * BK), full, hint_b);
-          } else {
-            // B is n x k row-major: boxes of [128 rows of n][64 columns of k] -> K-major SW128
-            tma_load_2d(sbase, tmap_b, (int)(kt * BK), (int)(nt * BN), full, hint_b);
-            if (L.bk == (uint32_t)BK) tma_load_2d(sbase + BN * 128, tmap_b, (int)(kt * BK + 64), (int)(nt * BN), full, hint_b);
-          }
-          // B first: it comes from DRAM and is the long pole of the stage; A and its metadata are L2 hits
-          if (!resident && !no_a) {
-            bulk_load_1d(sbase + L.a_off, av, a_bytes, full, HINT_EVICT_LAST);
-            bulk_load_1d(sbase + L.e_off, am, e_bytes, full, HINT_EVICT_LAST);
-            av += av_step;
-            am += am_step;
+          if (leader) {
+            if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
+            // B first: it comes from DRAM and is the long pole of the stage; A and its metadata are L2 hits
+            if (no_b) {
+            } else if (b3d) {
+              // one box fills the stage: [2 groups of 64][128 outer rows][64]
+              if (!OPB_T) tma_load_3d(sbase, tmap_b, 0, (int)(kt * BK), (int)(nt * 2), full, hint_b);
+              else        tma_load_3d(sbase, tmap_b, 0, (int)(nt * BN), (int)(kt * 2), full, hint_b);
+            } else if (!OPB_T) {
+              // B is k x n row-major: boxes of [128 rows of k][64 columns of n] -> MN-major SW128
+              tma_load_2d(sbase, tmap_b, (int)(nt * BN), (int)(kt * BK), full, hint_b);
+              tma_load_2d(sbase + L.bk * 128u, tmap_b, (int)(nt * BN + 64), (int)(kt * BK), full, hint_b);
+            } else {
+              // B is n x k row-major: boxes of [128 rows of n][64 columns of k] -> K-major SW128
+              tma_load_2d(sbase, tmap_b, (int)(kt * BK), (int)(nt * BN), full, hint_b);
+              if (L.bk == (uint32_t)BK) tma_load_2d(sbase + BN * 128, tmap_b, (int)(kt * BK + 64), (int)(nt * BN), full, hint_b);
+            }
+            if (stream_a) {
+              bulk_load_1d(sbase + L.a_off, av, a_bytes, full, HINT_EVICT_LAST);
+              bulk_load_1d(sbase + L.e_off, am, e_bytes, full, HINT_EVICT_LAST);
+            }
           }
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, one lane issues) =====================
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_b = uni(tmem_base);
       uint32_t stage = 0, phase = 0, job = 0, eblk = 0, res_loads = 0;
       const ProblemDev* res_owner = nullptr;
       const ProblemDev* last = nullptr;
@@ -460,8 +492,9 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const ProblemDev* P = W.current();
         if (P != last) {
           last = P;
-          pm = P->m; pk = P->k; k_tiles = P->k_tiles; m_tiles = P->m_tiles;
-          m_groups = P->m_groups; G = P->G; resident = P->resident; unit_begin = P->unit_begin; units = P->units;
+          pm = uni(P->m); pk = uni(P->k); k_tiles = uni(P->k_tiles); m_tiles = uni(P->m_tiles);
+          m_groups = uni(P->m_groups); G = uni(P->G); resident = uni(P->resident);
+          unit_begin = uni(P->unit_begin); units = uni(P->units);
         }
         const uint32_t local = W.u - unit_begin;
         const uint32_t mg = local % m_groups;
@@ -478,7 +511,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         mbar_wait(bar_acc_empty + slot0 * 8, (use0 & 1u) ^ 1u);
         if (g_count > 1) mbar_wait(bar_acc_empty + slot1 * 8, (use1 & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d0 = tmem_base + slot0 * BN, tmem_d1 = tmem_base + slot1 * BN;
+        const uint32_t tmem_d0 = tmem_b + slot0 * BN, tmem_d1 = tmem_b + slot1 * BN;
         // resident operands: tile (kt, mt) at (kt*m_tiles + mt) * stride
         const uint32_t rv_single = rows_valid_of(pm, 0);
         const uint32_t rsv = m_tiles == 1 ? rv_single * 128u : (uint32_t)A_TILE_BYTES;
@@ -490,46 +523,49 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
           // metadata of these 128 logical k -> TMEM (4 columns per m-tile)
-          const uint32_t ecol0 = tmem_base + TMEM_E_COL + (eblk & 1u) * (MAX_G * 4u), ecol1 = ecol0 + 4u;
+          const uint32_t ecol0 = tmem_b + TMEM_E_COL + (eblk & 1u) * (MAX_G * 4u), ecol1 = ecol0 + 4u;
           ++eblk;
           const uint32_t e0 = resident ? re : sbase + L.e_off;
           const uint32_t sa0 = resident ? ra : sbase + L.a_off;
-          tc_cp_128x128b(ecol0, desc_e_hi | (uint64_t)((e0 >> 4) & 0x3fffu));
-          if (g_count > 1)
-            tc_cp_128x128b(ecol1, desc_e_hi | (uint64_t)(((e0 + (resident ? rse : (uint32_t)E_TILE_BYTES)) >> 4) & 0x3fffu));
           const uint32_t sa1 = sa0 + (resident ? rsv : (uint32_t)A_TILE_BYTES);
+          const uint32_t e1 = e0 + (resident ? rse : (uint32_t)E_TILE_BYTES);
           const uint32_t nk = k_left >= (uint32_t)BK ? 4u : (k_left + 31u) / 32u;
-          if (!no_mma) {
+          if (leader) {
+            tc_cp_128x128b(ecol0, desc_e_hi | (uint64_t)((e0 >> 4) & 0x3fffu));
+            if (g_count > 1) tc_cp_128x128b(ecol1, desc_e_hi | (uint64_t)((e1 >> 4) & 0x3fffu));
+            if (!no_mma) {
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) {
-              if (j < nk) {
-                // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
-                // B: MN-major SW128 (8 k-rows per 1024 B atom, 64-column groups bk*128 apart) or
-                //    K-major SW128 (two 64-wide k halves, 64 bytes per MMA inside a row)
-                const uint32_t sb = OPB_T ? sbase + (j >> 1) * (BN * 128) + (j & 1u) * 64u : sbase + j * (32u * 128u);
-                const uint64_t db = desc_b_hi | (uint64_t)((sb >> 4) & 0x3fffu);
-                const uint32_t col0 = ecol0 + j;
-                tc_mma_sp_f16(tmem_d0, desc_a_hi | (uint64_t)(((sa0 + j * 32u) >> 4) & 0x3fffu), db, col0 & ~1u,
-                              L.idesc | (col0 & 1u), (kt | j) != 0);
-                if (g_count > 1) {
-                  const uint32_t col1 = ecol1 + j;
-                  tc_mma_sp_f16(tmem_d1, desc_a_hi | (uint64_t)(((sa1 + j * 32u) >> 4) & 0x3fffu), db, col1 & ~1u,
-                                L.idesc | (col1 & 1u), (kt | j) != 0);
+              for (uint32_t j = 0; j < 4; ++j) {
+                if (j < nk) {
+                  // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
+                  // B: MN-major SW128 (8 k-rows per 1024 B atom, 64-column groups bk*128 apart) or
+                  //    K-major SW128 (two 64-wide k halves, 64 bytes per MMA inside a row)
+                  const uint32_t sb = OPB_T ? sbase + (j >> 1) * (BN * 128) + (j & 1u) * 64u : sbase + j * (32u * 128u);
+                  const uint64_t db = desc_b_hi | (uint64_t)((sb >> 4) & 0x3fffu);
+                  const uint32_t col0 = ecol0 + j;
+                  tc_mma_sp_f16(tmem_d0, desc_a_hi | (uint64_t)(((sa0 + j * 32u) >> 4) & 0x3fffu), db, col0 & ~1u,
+                                L.idesc | (col0 & 1u), (kt | j) != 0);
+                  if (g_count > 1) {
+                    const uint32_t col1 = ecol1 + j;
+                    tc_mma_sp_f16(tmem_d1, desc_a_hi | (uint64_t)(((sa1 + j * 32u) >> 4) & 0x3fffu), db, col1 & ~1u,
+                                  L.idesc | (col1 & 1u), (kt | j) != 0);
+                  }
                 }
               }
             }
+            tc_commit(bar_empty + stage * 8);
           }
-          tc_commit(bar_empty + stage * 8);
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(bar_acc_full + slot0 * 8);
-        if (g_count > 1) tc_commit(bar_acc_full + slot1 * 8);
-        job += g_count;
         const uint32_t nu = W.u + gridDim.x;
-        if (resident && (nu >= L.total_units || nu >= unit_begin + units)) {
-          tc_commit(bar_res_empty);  // every MMA that reads the resident region has completed
-          res_owner = nullptr;
+        const bool last_of_problem = resident && (nu >= L.total_units || nu >= unit_begin + units);
+        if (leader) {
+          tc_commit(bar_acc_full + slot0 * 8);
+          if (g_count > 1) tc_commit(bar_acc_full + slot1 * 8);
+          if (last_of_problem) tc_commit(bar_res_empty);  // every MMA that reads the resident region has completed
         }
+        job += g_count;
+        if (last_of_problem) res_owner = nullptr;
       }
     }
   } else if (warp - 2 < L.epi_warps) {

@@ -21,6 +21,10 @@ examples)
 mg)
   NG=${NGPUS:-2}
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --steps 50 --warmup 5 > $OUT/bench_mg${NG}_$TAG.json 2> $OUT/bench_mg${NG}_$TAG.err; echo "mg rc=$?"; tail -c 600 $OUT/bench_mg${NG}_$TAG.json;;
+ktable) python tools/kernel_table.py --tag $TAG > $OUT/kernels_$TAG.csv 2> $OUT/kernels_$TAG.err; echo "ktable rc=$?"; tail -3 $OUT/kernels_$TAG.err;;
+ab) for r in 1 2 3; do for v in prev cur; do
+      if [ $v = prev ]; then export SPFY_LIB=$PWD/gpurun_ab/lib_prev.so; else unset SPFY_LIB; fi
+      python tools/layer_sweep.py --plan-only --tag $v$r 2>&1 | grep "^#" | sed 's/{[^}]*}//' | tr '\n' ' '; echo; done; done; unset SPFY_LIB;;
 ncu_spmm)
   CMD="python tools/spmm_one.py 64 576 12544 32 0.9"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
@@ -28,7 +32,7 @@ ncu_spmma)
   CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
   $CMD > $OUT/plain_$TAG.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'spmma_kernel|prune24' -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_l_$TAG.log 2>&1; echo "launch list rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:spmma_kernel -s 9 -c 3 -o $OUT/prof_spmma_$TAG -f $CMD > $OUT/ncu_s_$TAG.log 2>&1; echo "ncu spmma rc=$?";;
+  ncu --set full --clock-control none --import-source on -k regex:spmma_kernel -s 15 -c 5 -o $OUT/prof_spmma_$TAG -f $CMD > $OUT/ncu_s_$TAG.log 2>&1; echo "ncu spmma rc=$?";;
 ncu_prune)
   CMD="python tools/prune_probe.py --reps 1 --only-large"
   $CMD > $OUT/plain_prune_$TAG.log 2>&1 &&
