@@ -44,6 +44,7 @@
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -993,6 +994,9 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
       ln.first = (uint32_t)table.size();
       ln.count = 0;
       uint32_t units = 0, res_vals = 0, res_meta = 0;
+      // members of this launch, longest units first: the CTAs walk the unit list with a fixed stride, so
+      // whatever comes last sets the tail -- it should be the problems whose units are short
+      std::vector<size_t> members;
       for (size_t i = 0; i < count; ++i) {
         const spfy_spmma_problem& q = problems[i];
         HostProblem h{q.opB, q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
@@ -1004,6 +1008,14 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
         }
         if (h.m == 0 || h.n == 0) continue;
         if (classify(h, true, di.sm_count) != cls) continue;
+        members.push_back(i);
+      }
+      std::stable_sort(members.begin(), members.end(), [&](size_t a, size_t b) {
+        return ceil_div(problems[a].k, 128) > ceil_div(problems[b].k, 128);
+      });
+      for (size_t i : members) {
+        const spfy_spmma_problem& q = problems[i];
+        HostProblem h{q.opB, q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
         ProblemDev d;
         rc = fill_problem(&d, dtype, h, cls);
         if (rc) {
