@@ -986,7 +986,9 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
   Plan* plan = new Plan();
   plan->dtype = dtype;
   std::vector<ProblemDev> table;
-  for (int cls = 0; cls < NUM_CLASSES; ++cls) {
+  // launches overlap tail-to-head (programmatic stream serialization), so only the last launch's tail is
+  // exposed: go from the class with the longest units (streaming, G = 2) to the one with the shortest (k <= 64)
+  for (int cls = NUM_CLASSES - 1; cls >= 0; --cls) {
     for (int opB = 0; opB < 2; ++opB) {
       Plan::Launch ln;
       memset(&ln.L, 0, sizeof(ln.L));
