@@ -50,6 +50,27 @@ def read_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def ncu_traffic():
+    """DRAM bytes per step of the spmma launches from the committed `ncu --set full` summary
+    (profiles/rNN_spmma_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum over the launches of one
+    step), or None when no capture is committed."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_spmma_ncu.csv")))
+    if not files:
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total = 0.0
+    try:
+        with open(files[-1]) as f:
+            for row in csv.reader(f):
+                if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += sum(float(x) for x in row[2:]) * scale.get(row[1], 1.0)
+    except (OSError, ValueError):
+        return None, None
+    return (total or None), os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region.
 
@@ -416,6 +437,7 @@ def main():
         return 0
 
     achieved = spmma_bytes_step / (spmma_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic() if args.csv == "resnet50.csv" and args.batch == 32 else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -423,7 +445,8 @@ def main():
         "config": config_dict(args, len(gemms), plan.launches),
         "clocks": clocks, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": f"spmma_kernel (tcgen05.mma.sp, {plan.launches} persistent launches per step)", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_step": spmma_bytes_step, "launches_per_step": plan.launches, "layers_per_step": len(layers),
                      "ms_per_step": spmma_ms,
                      "tflops": flops_step / (spmma_ms * 1e-3) / 1e12,

@@ -26,7 +26,7 @@ ab) for r in 1 2 3; do for v in prev cur; do
       if [ $v = prev ]; then export SPFY_LIB=$PWD/gpurun_ab/lib_prev.so; else unset SPFY_LIB; fi
       python tools/layer_sweep.py --plan-only --tag $v$r 2>&1 | grep "^#" | sed 's/{[^}]*}//' | tr '\n' ' '; echo; done; done; unset SPFY_LIB;;
 ncu_spmm)
-  CMD="python tools/spmm_one.py 64 576 12544 32 0.9"
+  CMD="python tools/spmm_one.py 64 576 12544 32 0.95"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
 ncu_spmma)
   CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
