@@ -71,11 +71,14 @@ float spmm(ell_t<type_t, memory_space_t::device>* As,
   nvtxRangePushA("batched-SpMM");
 #endif
   const void* const* tab = d_ptrs.as<const void*>();
+  std::size_t ws_bytes = 0;
+  detail::ok(spfy_spmm_workspace_bytes(As[0].rows, 0, &ws_bytes), "batched::spmm");
+  detail::scratch ws(ws_bytes, stream);
   detail::ok(spfy_spmm_bell_batched(detail::dtype_of<type_t>::value, As[0].rows, As[0].cols, n,
                                     As[0].block_size, As[0].ell_cols, batch_size,
                                     reinterpret_cast<const std::int64_t* const*>(tab), tab + batch_size, B, k,
                                     const_cast<void* const*>(reinterpret_cast<const void* const*>(tab + 2 * batch_size)),
-                                    m, alpha, beta, reinterpret_cast<spfy_stream_t>(stream)),
+                                    m, alpha, beta, ws.ptr, ws_bytes, reinterpret_cast<spfy_stream_t>(stream)),
              "batched::spmm");
   detail::cuda_ok(cudaDeviceSynchronize(), "batched::spmm");
 #ifdef SPARSIFYME_NVTX

@@ -236,7 +236,8 @@ SPFY_API int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t 
                                     size_t block, size_t ell_cols, size_t num_batches,
                                     const int64_t* const* col_idx, const void* const* values,
                                     const void* B, size_t ldb, void* const* Cs, size_t ldc,
-                                    float alpha, float beta, spfy_stream_t stream);
+                                    float alpha, float beta, void* workspace,
+                                    size_t workspace_bytes, spfy_stream_t stream);
 
 #ifdef __cplusplus
 }

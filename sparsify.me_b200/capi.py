@@ -65,7 +65,7 @@ SIGNATURES = {
     "spfy_spmm_csr_strided_batched": (c_int, [_SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P, _SZ,
                                               _SZ, c_float, c_float, _P, _SZ, _P]),
     "spfy_spmm_bell_batched": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _SZ, _P, _SZ,
-                                       c_float, c_float, _P]),
+                                       c_float, c_float, _P, _SZ, _P]),
 }
 
 _NO_STATUS = {"spfy_version", "spfy_last_error_string", "spfy_launch_count", "spfy_spmma_plan_launches"}

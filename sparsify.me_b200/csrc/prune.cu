@@ -28,45 +28,110 @@ struct OffsetList {
 template <typename T>
 __device__ __forceinline__ void store_zero(T* p) { *p = T(0); }
 
-// one thread = 4 consecutive elements: two 16-byte mask stores + scalar zero stores
-template <typename T>
-__global__ void __launch_bounds__(256)
-prune_blocks_ref_kernel(T* __restrict__ weights, uint64_t* __restrict__ mask, size_t total,
-                        size_t nblocks, uint32_t blk_size, const __grid_constant__ OffsetList L) {
-  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t * 4 < total; t += nthreads) {
-    const size_t e0 = t * 4;
-    unsigned zero = 0;  // bit i set -> element e0+i is pruned
+// which of the 4 elements starting at e0 does the reference zero? (bit i set -> element e0+i)
+__device__ __forceinline__ unsigned blocks_ref_zero_bits(size_t e0, size_t total, size_t nblocks, uint32_t blk_size,
+                                                        const OffsetList& L) {
+  unsigned zero = 0;
+  if (L.in_block) {
+    // one division per chunk: block and in-block offset of e0, then step
+    size_t blk = e0 / blk_size;
+    uint32_t o = (uint32_t)(e0 - blk * blk_size);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (e0 + i >= total) break;
+      if (blk < nblocks && (L.bitmap[o >> 5] >> (o & 31) & 1)) zero |= 1u << i;
+      if (++o == blk_size) { o = 0; ++blk; }
+    }
+  } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const size_t e = e0 + i;
       if (e >= total) break;
-      if (L.in_block) {
-        const size_t blk = e / blk_size;
-        const uint32_t o = (uint32_t)(e - blk * blk_size);
-        if (blk < nblocks && (L.bitmap[o >> 5] >> (o & 31) & 1)) zero |= 1u << i;
-      } else {
-        for (int j = 0; j < L.count; ++j) {
-          const size_t o = L.off[j];
-          if (e >= o && (e - o) % blk_size == 0 && (e - o) / blk_size < nblocks) {
-            zero |= 1u << i;
-            break;
-          }
+      for (int j = 0; j < L.count; ++j) {
+        const size_t o = L.off[j];
+        if (e >= o && (e - o) % blk_size == 0 && (e - o) / blk_size < nblocks) {
+          zero |= 1u << i;
+          break;
         }
       }
     }
-    if (e0 + 4 <= total) {
-      ulonglong2 m01 = make_ulonglong2(zero & 1 ? 0ull : 1ull, zero & 2 ? 0ull : 1ull);
-      ulonglong2 m23 = make_ulonglong2(zero & 4 ? 0ull : 1ull, zero & 8 ? 0ull : 1ull);
-      *reinterpret_cast<ulonglong2*>(mask + e0) = m01;
-      *reinterpret_cast<ulonglong2*>(mask + e0 + 2) = m23;
+  }
+  return zero;
+}
+
+// 4 elements of 2 / 4 / 8 bytes as 32-bit words
+template <int BYTES> struct Quad { uint32_t w[BYTES]; };
+template <int BYTES>
+__device__ __forceinline__ Quad<BYTES> quad_load(const void* p) {
+  Quad<BYTES> q;
+  if (BYTES == 2) { const uint2 v = *reinterpret_cast<const uint2*>(p); q.w[0] = v.x; q.w[1] = v.y; }
+  else if (BYTES == 4) { const uint4 v = *reinterpret_cast<const uint4*>(p); q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w; }
+  else {
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *(reinterpret_cast<const uint4*>(p) + 1);
+    q.w[0] = a.x; q.w[1] = a.y; q.w[2] = a.z; q.w[3] = a.w; q.w[4] = b.x; q.w[5] = b.y; q.w[6] = b.z; q.w[7] = b.w;
+  }
+  return q;
+}
+template <int BYTES>
+__device__ __forceinline__ void quad_zero_store(void* p, Quad<BYTES> q, unsigned zero) {
+  if (BYTES == 2) {
+    if (zero & 1) q.w[0] &= 0xffff0000u;
+    if (zero & 2) q.w[0] &= 0x0000ffffu;
+    if (zero & 4) q.w[1] &= 0xffff0000u;
+    if (zero & 8) q.w[1] &= 0x0000ffffu;
+    *reinterpret_cast<uint2*>(p) = make_uint2(q.w[0], q.w[1]);
+  } else if (BYTES == 4) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (zero >> i & 1) store_zero(weights + e0 + i);
-    } else {
-      for (int i = 0; i < 4 && e0 + i < total; ++i) {
-        mask[e0 + i] = (zero >> i & 1) ? 0ull : 1ull;
-        if (zero >> i & 1) store_zero(weights + e0 + i);
+    for (int i = 0; i < 4; ++i) if (zero >> i & 1) q.w[i] = 0;
+    *reinterpret_cast<uint4*>(p) = make_uint4(q.w[0], q.w[1], q.w[2], q.w[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (zero >> i & 1) q.w[2 * i] = q.w[2 * i + 1] = 0;
+    *reinterpret_cast<uint4*>(p) = make_uint4(q.w[0], q.w[1], q.w[2], q.w[3]);
+    *(reinterpret_cast<uint4*>(p) + 1) = make_uint4(q.w[4], q.w[5], q.w[6], q.w[7]);
+  }
+}
+
+// one chunk = 4 consecutive elements: two 16-byte mask stores + the weights.  The weights are updated
+// by a whole-vector read-modify-write (masked partial-sector stores ran at 2.3 TB/s); a thread keeps
+// BR_UNROLL chunks in flight so that the reads overlap.
+constexpr int BR_UNROLL = 4;
+template <typename T>
+__global__ void __launch_bounds__(256)
+prune_blocks_ref_kernel(T* __restrict__ weights, uint64_t* __restrict__ mask, size_t total,
+                        size_t nblocks, uint32_t blk_size, int vec_w, const __grid_constant__ OffsetList L) {
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t0 * 4 < total; t0 += nthreads * BR_UNROLL) {
+    unsigned zero[BR_UNROLL];
+    bool full[BR_UNROLL];
+    Quad<sizeof(T)> q[BR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BR_UNROLL; ++u) {
+      const size_t e0 = (t0 + u * nthreads) * 4;
+      full[u] = e0 + 4 <= total;
+      zero[u] = e0 < total ? blocks_ref_zero_bits(e0, total, nblocks, blk_size, L) : 0u;
+      if (vec_w && full[u] && zero[u]) q[u] = quad_load<sizeof(T)>(weights + e0);
+    }
+#pragma unroll
+    for (int u = 0; u < BR_UNROLL; ++u) {
+      const size_t e0 = (t0 + u * nthreads) * 4;
+      if (e0 >= total) break;
+      const unsigned z = zero[u];
+      if (full[u]) {
+        *reinterpret_cast<ulonglong2*>(mask + e0) = make_ulonglong2(z & 1 ? 0ull : 1ull, z & 2 ? 0ull : 1ull);
+        *reinterpret_cast<ulonglong2*>(mask + e0 + 2) = make_ulonglong2(z & 4 ? 0ull : 1ull, z & 8 ? 0ull : 1ull);
+        if (vec_w) {
+          if (z) quad_zero_store<sizeof(T)>(weights + e0, q[u], z);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (z >> i & 1) store_zero(weights + e0 + i);
+        }
+      } else {
+        for (int i = 0; i < 4 && e0 + i < total; ++i) {
+          mask[e0 + i] = (z >> i & 1) ? 0ull : 1ull;
+          if (z >> i & 1) store_zero(weights + e0 + i);
+        }
       }
     }
   }
@@ -630,10 +695,11 @@ int spfy_prune_blocks_ref(int dtype, void* weights, uint64_t* mask, size_t m, si
   int rc = grid_for(ceil_div(total, 4), 256, &grid);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  const int vec_w = (uintptr_t)weights % (eb == 8 ? 16 : 4 * eb) == 0 && (uintptr_t)mask % 16 == 0;
   switch (eb) {
-    case 2: prune_blocks_ref_kernel<uint16_t><<<grid, 256, 0, s>>>((uint16_t*)weights, mask, total, nblocks, (uint32_t)blk_size, L); break;
-    case 4: prune_blocks_ref_kernel<uint32_t><<<grid, 256, 0, s>>>((uint32_t*)weights, mask, total, nblocks, (uint32_t)blk_size, L); break;
-    default: prune_blocks_ref_kernel<uint64_t><<<grid, 256, 0, s>>>((uint64_t*)weights, mask, total, nblocks, (uint32_t)blk_size, L); break;
+    case 2: prune_blocks_ref_kernel<uint16_t><<<grid, 256, 0, s>>>((uint16_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, L); break;
+    case 4: prune_blocks_ref_kernel<uint32_t><<<grid, 256, 0, s>>>((uint32_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, L); break;
+    default: prune_blocks_ref_kernel<uint64_t><<<grid, 256, 0, s>>>((uint64_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, L); break;
   }
   SPFY_LAUNCH_OK("prune_blocks_ref_kernel");
   return SPFY_OK;

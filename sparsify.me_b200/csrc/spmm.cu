@@ -326,7 +326,30 @@ struct CsrSpmmParams {
   uint32_t row_tiles, col_tiles;  // col tiles over the num_batches * n columns
   uint32_t vec;                    // B columns are 16-byte aligned: 128-bit fill
   float alpha, beta;
+  // blocked-ELL source (spmm.hxx:30-138): one A per batch element, B shared, one C pointer per batch
+  const int64_t* const* bell_cols;  // [batch] -> [(m / block) x bcols] block-column ids, < 0 = padding
+  const float* const* bell_vals;    // [batch] -> [m x ell_cols]
+  float* const* Cs;                 // [batch] -> m x n column-major
+  uint32_t block, ell_cols, bcols;
 };
+
+// blocked-ELL rows are "sorted" when block-column ids ascend and padding only trails
+__global__ void __launch_bounds__(256)
+bell_check_sorted_kernel(const int64_t* const* __restrict__ cols, uint32_t block_rows, uint32_t bcols,
+                         uint32_t num_batches, int* __restrict__ sorted) {
+  const size_t total = (size_t)num_batches * block_rows * bcols;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const uint32_t j = (uint32_t)(i % bcols);
+    if (j == 0) continue;
+    const size_t br = i / bcols;
+    const int64_t* c = cols[br / block_rows] + (br % block_rows) * (size_t)bcols;
+    const int64_t a = c[j - 1], b = c[j];
+    bad |= a < 0 ? b >= 0 : (b >= 0 && b < a);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(sorted, 0);
+}
 
 __global__ void __launch_bounds__(256)
 csr_check_sorted_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, uint32_t m,
@@ -400,7 +423,25 @@ __device__ __forceinline__ void csr_chunk_store(const float (&pf)[CSR_PF], float
   }
 }
 
-template <int RPW>
+// one request of a row: lane `lane` reads entry `idx` (CSR: position in col_idx / vals; blocked-ELL: slot
+// of the row); returns the column (0x7fffffff = nothing) and the value
+template <bool BELL>
+__device__ __forceinline__ void csr_fetch(const CsrSpmmParams& P, uint32_t batch, uint32_t row, uint32_t idx,
+                                          bool ok, int32_t& c, float& v) {
+  c = 0x7fffffff;
+  v = 0.f;
+  if (!ok) return;
+  if (BELL) {
+    const int64_t bc = P.bell_cols[batch][(size_t)(row / P.block) * P.bcols + idx / P.block];
+    if (bc >= 0) c = (int32_t)(bc * P.block + idx % P.block);
+    v = P.bell_vals[batch][(size_t)row * P.ell_cols + idx];
+  } else {
+    c = P.col_idx[idx];
+    v = P.vals[idx];
+  }
+}
+
+template <int RPW, bool BELL>
 __global__ void __launch_bounds__(CSR_THREADS, 1)
 spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   constexpr int TM = CSR_WARPS * RPW;
@@ -411,15 +452,19 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   size_t* colC = colB + CSR_TN;                                                              // [CSR_TN]
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool sorted = *P.sorted != 0;
-  const uint32_t nnz_total = (uint32_t)P.row_ptr[P.m];
-  const uint64_t ncols = (uint64_t)P.n * P.num_batches;
-  const uint32_t tiles = P.row_tiles * P.col_tiles;
+  const uint32_t nnz_total = BELL ? P.ell_cols : (uint32_t)P.row_ptr[P.m];
+  // CSR: the batch elements' columns form one long column axis; blocked-ELL: tiles are per batch element
+  const uint64_t ncols = BELL ? (uint64_t)P.n : (uint64_t)P.n * P.num_batches;
+  const uint32_t tiles = P.row_tiles * P.col_tiles * (BELL ? P.num_batches : 1u);
   const uint32_t nchunks = (P.k + CSR_KC - 1) / CSR_KC;
 
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const uint32_t rt = tile % P.row_tiles, ct = tile / P.row_tiles;  // row tile fastest: CTAs that
-    const uint32_t i0 = rt * TM + warp * RPW;                          // share B columns run together
+    const uint32_t rt = tile % P.row_tiles, ct_all = tile / P.row_tiles;  // row tile fastest: CTAs that
+    const uint32_t i0 = rt * TM + warp * RPW;                              // share B columns run together
+    const uint32_t batch = BELL ? ct_all / P.col_tiles : 0u;
+    const uint32_t ct = BELL ? ct_all - batch * P.col_tiles : ct_all;
     const uint64_t j0 = (uint64_t)ct * CSR_TN;
+    float* const Cbase = BELL ? P.Cs[batch] : P.C;
 
     __syncthreads();  // the previous tile's C stores have left shared memory
     if (threadIdx.x < CSR_TN) {
@@ -427,7 +472,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
       const uint64_t J = j0 + threadIdx.x;
       size_t ob = ~(size_t)0, oc = ~(size_t)0;
       if (J < ncols) {
-        const uint32_t bt = ncols <= 0xffffffffull ? (uint32_t)J / P.n : (uint32_t)(J / P.n);
+        const uint32_t bt = BELL ? 0u : (ncols <= 0xffffffffull ? (uint32_t)J / P.n : (uint32_t)(J / P.n));
         const size_t jc = (size_t)(J - (uint64_t)bt * P.n);
         ob = (size_t)bt * P.strideB + jc * P.ldb;
         oc = (size_t)bt * P.strideC + jc * P.ldc;
@@ -442,7 +487,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const uint32_t row = i0 + r;
-      cur[r] = row < P.m ? (uint32_t)P.row_ptr[row] : 0u;
+      cur[r] = (!BELL && row < P.m) ? (uint32_t)P.row_ptr[row] : 0u;
 #pragma unroll
       for (int j = 0; j < CSR_TJ; ++j) acc[r][j] = 0.f;
     }
@@ -475,13 +520,11 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
         for (int q = 0; q < 4; ++q) {
           const int r = r0 + q;
           const bool row_ok = i0 + r < P.m;
-          if (!sorted) cur[r] = row_ok ? (uint32_t)P.row_ptr[i0 + r] : 0u;
-          end[q] = row_ok ? (uint32_t)P.row_ptr[i0 + r + 1] : 0u;
+          if (!sorted) cur[r] = (!BELL && row_ok) ? (uint32_t)P.row_ptr[i0 + r] : 0u;
+          end[q] = row_ok ? (BELL ? P.ell_cols : (uint32_t)P.row_ptr[i0 + r + 1]) : 0u;
           // the request does not wait for the row end: any index below nnz is readable
           const uint32_t idx = cur[r] + lane;
-          const bool rd = idx < nnz_total;
-          c_[q] = rd ? P.col_idx[idx] : 0x7fffffff;
-          v_[q] = rd ? P.vals[idx] : 0.f;
+          csr_fetch<BELL>(P, batch, i0 + r, idx, idx < nnz_total && (!BELL || row_ok), c_[q], v_[q]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -518,9 +561,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
             }
             if (!more) break;
             const uint32_t idx = cur[r] + lane;
-            const bool ok = idx < end[q];
-            c_[q] = ok ? P.col_idx[idx] : 0x7fffffff;
-            v_[q] = ok ? P.vals[idx] : 0.f;
+            csr_fetch<BELL>(P, batch, i0 + r, idx, idx < end[q], c_[q], v_[q]);
           }
         }
       }
@@ -540,7 +581,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
       const uint32_t jj = idx / TM, i = idx % TM;
       const size_t oc = colC[jj];
       if (oc != ~(size_t)0 && rbase + i < P.m) {
-        float* dst = P.C + oc + rbase + i;
+        float* dst = Cbase + oc + rbase + i;
         float out = P.alpha * sC[jj * (TM + 1) + i];
         if (P.beta != 0.f) out += P.beta * *dst;
         *dst = out;
@@ -549,7 +590,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   }
 }
 
-template <int RPW>
+template <int RPW, bool BELL>
 int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
   constexpr int TM = CSR_WARPS * RPW;
   size_t smem = ((size_t)CSR_TN * CSR_PITCH) * 4;
@@ -560,12 +601,12 @@ int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
   int dev = 0;
   SPFY_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63].load()) {
-    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW, BELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev & 63].store(1);
   }
-  const uint32_t tiles = P.row_tiles * P.col_tiles;
+  const uint32_t tiles = P.row_tiles * P.col_tiles * (BELL ? P.num_batches : 1u);
   const uint32_t grid = tiles < (uint32_t)sm_count ? tiles : (uint32_t)sm_count;
-  spmm_csr_kernel<RPW><<<grid, CSR_THREADS, smem, s>>>(P);
+  spmm_csr_kernel<RPW, BELL><<<grid, CSR_THREADS, smem, s>>>(P);
   SPFY_LAUNCH_OK("spmm_csr_kernel");
   return SPFY_OK;
 }
@@ -693,7 +734,7 @@ int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batch
   P.row_tiles = (uint32_t)ceil_div(m, tall ? 128 : 64);
   if (col_tiles * P.row_tiles >= (1ull << 32)) return fail(SPFY_E_UNSUPPORTED, "spmm_csr: too many tiles");
   P.col_tiles = (uint32_t)col_tiles;
-  return tall ? launch_spmm_csr<8>(P, di.sm_count, s) : launch_spmm_csr<4>(P, di.sm_count, s);
+  return tall ? launch_spmm_csr<8, false>(P, di.sm_count, s) : launch_spmm_csr<4, false>(P, di.sm_count, s);
 }
 
 int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,
@@ -715,11 +756,49 @@ int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size
 int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t block,
                            size_t ell_cols, size_t num_batches, const int64_t* const* col_idx,
                            const void* const* values, const void* B, size_t ldb, void* const* Cs,
-                           size_t ldc, float alpha, float beta, spfy_stream_t stream) {
+                           size_t ldc, float alpha, float beta, void* workspace, size_t workspace_bytes,
+                           spfy_stream_t stream) {
   if (rows == 0 || n == 0 || num_batches == 0) return SPFY_OK;
   if (!col_idx || !values || !B || !Cs) return fail(SPFY_E_INVALID, "spmm_bell: null pointer");
   if (block == 0 || ell_cols % block) return fail(SPFY_E_INVALID, "spmm_bell: ell_cols must be a multiple of block");
   if (ldb < cols || ldc < rows) return fail(SPFY_E_INVALID, "spmm_bell: leading dimension too small");
+  if (dtype == SPFY_F32 && rows < (1ull << 31) && n < (1ull << 31) && cols < (1ull << 31) &&
+      ell_cols < (1ull << 31) && ceil_div(rows, 64) * ceil_div(n, CSR_TN) * num_batches < (1ull << 32)) {
+    // fp32 (what the reference driver instantiates, examples/spmm.cu:26): the shared-memory kernel of the
+    // CSR path with a blocked-ELL row source
+    size_t need = 0;
+    spfy_spmm_workspace_bytes(rows, 0, &need);
+    if (!workspace || workspace_bytes < need)
+      return fail(SPFY_E_WORKSPACE, "spmm_bell: workspace %zu < %zu bytes", workspace_bytes, need);
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int* d_sorted = (int*)((uint8_t*)workspace + need - 256);
+    SPFY_CUDA_OK(cudaMemsetAsync(d_sorted, 0xff, sizeof(int), s));
+    const size_t block_rows = ceil_div(rows, block), bcols = ell_cols / block;
+    if (bcols > 1) {
+      int grid = 1;
+      rc = elementwise_grid(num_batches * block_rows * bcols, &grid);
+      if (rc) return rc;
+      bell_check_sorted_kernel<<<grid, 256, 0, s>>>(col_idx, (uint32_t)block_rows, (uint32_t)bcols,
+                                                   (uint32_t)num_batches, d_sorted);
+      SPFY_LAUNCH_OK("bell_check_sorted_kernel");
+    }
+    CsrSpmmParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = (const float*)B; P.sorted = d_sorted;
+    P.ldb = ldb; P.ldc = ldc;
+    P.m = (uint32_t)rows; P.k = (uint32_t)cols; P.n = (uint32_t)n; P.num_batches = (uint32_t)num_batches;
+    P.alpha = alpha; P.beta = beta;
+    P.vec = ((uintptr_t)B % 16 == 0) && ldb % 4 == 0;
+    P.bell_cols = col_idx; P.bell_vals = (const float* const*)values; P.Cs = (float* const*)Cs;
+    P.block = (uint32_t)block; P.ell_cols = (uint32_t)ell_cols; P.bcols = (uint32_t)bcols;
+    const bool tall = rows > 64;
+    P.row_tiles = (uint32_t)ceil_div(rows, tall ? 128 : 64);
+    P.col_tiles = (uint32_t)ceil_div(n, CSR_TN);
+    return tall ? launch_spmm_csr<8, true>(P, di.sm_count, s) : launch_spmm_csr<4, true>(P, di.sm_count, s);
+  }
   SpmmDense D;
   memset(&D, 0, sizeof(D));
   D.B = B; D.C = nullptr; D.Cs = Cs;

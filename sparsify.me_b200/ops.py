@@ -301,8 +301,12 @@ class batched:
         ci = torch.tensor([t.data_ptr() for t in col_idx_list], dtype=torch.int64, device=dev)
         va = torch.tensor([t.data_ptr() for t in values_list], dtype=torch.int64, device=dev)
         cs = torch.tensor([t.data_ptr() for t in c_list], dtype=torch.int64, device=dev)
+        wb = ctypes.c_size_t()
+        capi.spfy_spmm_workspace_bytes(m, 0, ctypes.byref(wb))
+        ws = torch.empty(max(wb.value, 16), dtype=torch.uint8, device=dev)
         t = _Timer()
         t.begin()
         capi.spfy_spmm_bell_batched(_dtype_code(b), m, k, n, block, ell_cols, nb, _ptr(ci), _ptr(va),
-                                    _ptr(b), k, _ptr(cs), m, float(alpha), float(beta), _stream())
+                                    _ptr(b), k, _ptr(cs), m, float(alpha), float(beta), _ptr(ws), ws.numel(),
+                                    _stream())
         return t.end()

@@ -499,6 +499,33 @@ def test_blocked_ell_spmm_matches_oracle(spfy, orc, cuda, tdt):
         assert np.array_equal(c.float().cpu().numpy().astype(np.float64), want)
 
 
+@pytest.mark.parametrize("order", ["sorted", "shuffled", "padded"])
+def test_blocked_ell_spmm_multi_chunk(spfy, orc, cuda, order):
+    """fp32 blocked-ELL through the shared-memory kernel: several staged chunks of k, 128-row tiles, ragged
+    n; block-column ids ascending (cursor mode), shuffled, or with padding slots (< 0) in the middle
+    (both fall back to rescanning every row per chunk)."""
+    m, n, k, nb, block = 200, 150, 448, 2, 4
+    ell_cols = k // 2
+    bcols = ell_cols // block
+    rng = np.random.default_rng(21)
+    B = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    cis, vas, cs, wants = [], [], [], []
+    for b in range(nb):
+        ci = np.stack([np.sort(rng.choice(k // block, bcols, replace=False)) for _ in range(m // block)]).astype(np.int64)
+        if order == "shuffled":
+            ci = np.stack([rng.permutation(r) for r in ci])
+        elif order == "padded":
+            ci[:, ::5] = -1
+        va = rng.uniform(-1, 1, (m, ell_cols)).astype(np.float32)
+        wants.append(orc.spmm_bell_f64(m, k, n, block, ell_cols, ci, va, B))
+        cis.append(torch.from_numpy(ci).to(cuda))
+        vas.append(torch.from_numpy(va).to(cuda))
+        cs.append(torch.full((n, m), 3.0, dtype=torch.float32, device=cuda))
+    spfy.batched.spmm(cis, vas, torch.from_numpy(B).to(cuda), cs, m, n, k, block, ell_cols)
+    for c, want in zip(cs, wants):
+        assert np.allclose(c.cpu().numpy().astype(np.float64), want, rtol=2e-4, atol=2e-4)
+
+
 def test_launch_counter_moves(spfy, cuda):
     before = spfy.launch_count()
     a = torch.zeros(128, 128, dtype=torch.float16, device=cuda)
