@@ -7,6 +7,10 @@ tests/golden/make_golden.py; nothing here needs a GPU or /root/reference).
                        -> orc_prune24_strip must be bit-exact with PRUNE_SPMMA_STRIP (incl. the tie-break);
                           orc_prune24_tile is only a documented match rate (closed source, SURVEY.md 8c);
                           the fp64 GEMM oracle must agree with cusparseLtMatmul within fp16 rounding.
+  cusparse_coo_*.npz, cusparse_bell_*.npz : cuSPARSE 12.x driven with the reference's call sequences for
+                       batched::strided_coo (spmm.hxx:164-187, COO_ALG4) and batched::spmm (blocked-ELL,
+                       :57-67,107-110).  Inputs are multiples of 1/64, so every sum is exact in fp32 and the
+                       fp64 oracles must reproduce the library's output BIT FOR BIT.
 """
 import glob
 import hashlib
@@ -19,7 +23,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
 sys.path.insert(0, GOLD)
-from make_golden import gen  # noqa: E402
+from make_golden import gen, gen_f32  # noqa: E402
 
 
 def sha(a):
@@ -30,8 +34,48 @@ SPARSIFY = sorted(glob.glob(os.path.join(GOLD, "ref_sparsify_*.npz")))
 CUSPLT = sorted(glob.glob(os.path.join(GOLD, "cusparselt_*.npz")))
 
 
+CUSP_COO = sorted(glob.glob(os.path.join(GOLD, "cusparse_coo_*.npz")))
+CUSP_BELL = sorted(glob.glob(os.path.join(GOLD, "cusparse_bell_*.npz")))
+
+
 def test_fixtures_present():
-    assert len(SPARSIFY) >= 12 and len(CUSPLT) >= 5
+    assert len(SPARSIFY) >= 12 and len(CUSPLT) >= 5 and len(CUSP_COO) >= 4 and len(CUSP_BELL) >= 3
+
+
+def coo_case(z):
+    """inputs of a cusparse_coo fixture, regenerated (same generator as oracle/cusparse_ref.cu)"""
+    m, k, n, nb = int(z["m"]), int(z["k"]), int(z["n"]), int(z["nb"])
+    a = gen_f32(1, m * k).reshape(m, k)
+    B = gen_f32(2, nb * n * k).reshape(nb, n, k)
+    C0 = gen_f32(3, nb * n * m).reshape(nb, n, m)
+    return m, k, n, nb, a, B, C0, float(z["thr"]), float(z["alpha"]), float(z["beta"])
+
+
+def bell_case(z):
+    m, k, n, nb, block, ell_cols = (int(z[x]) for x in ("m", "k", "n", "nb", "block", "ell_cols"))
+    V = gen_f32(4, nb * m * ell_cols).reshape(nb, m, ell_cols)
+    B = gen_f32(5, n * k).reshape(n, k)
+    return m, k, n, nb, block, ell_cols, V, B
+
+
+@pytest.mark.parametrize("path", CUSP_COO, ids=os.path.basename)
+def test_threshold_and_coo_spmm_oracles_are_bit_exact_with_cusparse(orc, path):
+    z = np.load(path)
+    m, k, n, nb, a, B, C0, thr, alpha, beta = coo_case(z)
+    ri, ci, va, _ = orc.threshold_to_coo(2, a, thr)
+    assert ri.size == int(z["nnz"]) and sha(np.concatenate([ri, ci])) == str(z["coo_sha256"])
+    want = orc.spmm_coo_batched_f64(m, k, n, nb, ri, ci, va, B, C0, alpha, beta)
+    assert np.array_equal(want.astype(np.float32), z["c"])
+    assert np.array_equal(want, z["c"].astype(np.float64))  # nothing was rounded on the way
+
+
+@pytest.mark.parametrize("path", CUSP_BELL, ids=os.path.basename)
+def test_blocked_ell_oracle_is_bit_exact_with_cusparse(orc, path):
+    z = np.load(path)
+    m, k, n, nb, block, ell_cols, V, B = bell_case(z)
+    for b in range(nb):
+        want = orc.spmm_bell_f64(m, k, n, block, ell_cols, z["col_idx"][b], V[b], B)
+        assert np.array_equal(want, z["c"][b].astype(np.float64))
 
 
 @pytest.mark.parametrize("path", SPARSIFY, ids=os.path.basename)
