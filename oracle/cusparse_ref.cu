@@ -171,7 +171,65 @@ static int run_bell(int argc, char** argv) {
   return 0;
 }
 
+// cusparse_ref time <m> <k> <n> <nb> <keep_fraction> : median-of-5 time of the batched COO SpMM (ALG4) on random
+// fp32 data with ~keep_fraction of A kept -- the comparator column of tools/spmm_sweep.py
+static int run_time(int argc, char** argv) {
+  if (argc < 7) return 2;
+  const int64_t m = atoll(argv[2]), k = atoll(argv[3]), n = atoll(argv[4]), nb = atoll(argv[5]);
+  const double keep = atof(argv[6]);
+  std::vector<int32_t> rows, cols;
+  std::vector<float> vals;
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+  for (int64_t i = 0; i < m; ++i)
+    for (int64_t j = 0; j < k; ++j)
+      if (rnd() < keep) { rows.push_back((int32_t)i); cols.push_back((int32_t)j); vals.push_back((float)(2 * rnd() - 1)); }
+  const int64_t nnz = (int64_t)vals.size();
+  int32_t *dr = to_dev(rows), *dc = to_dev(cols);
+  float* dv = to_dev(vals);
+  float *dB = nullptr, *dC = nullptr;
+  CK(cudaMalloc(&dB, (size_t)nb * n * k * 4));
+  CK(cudaMalloc(&dC, (size_t)nb * n * m * 4));
+  CK(cudaMemset(dB, 0x3c, (size_t)nb * n * k * 4));
+  CK(cudaMemset(dC, 0, (size_t)nb * n * m * 4));
+  cusparseHandle_t h;
+  CKS(cusparseCreate(&h));
+  cusparseSpMatDescr_t A;
+  cusparseDnMatDescr_t mB, mC;
+  const float alpha = 1.f, beta = 0.f;
+  CKS(cusparseCreateCoo(&A, m, k, nnz, dr, dc, dv, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_R_32F));
+  CKS(cusparseCooSetStridedBatch(A, (int)nb, 0));
+  CKS(cusparseCreateDnMat(&mB, k, n, k, dB, CUDA_R_32F, CUSPARSE_ORDER_COL));
+  CKS(cusparseDnMatSetStridedBatch(mB, (int)nb, k * n));
+  CKS(cusparseCreateDnMat(&mC, m, n, m, dC, CUDA_R_32F, CUSPARSE_ORDER_COL));
+  CKS(cusparseDnMatSetStridedBatch(mC, (int)nb, m * n));
+  size_t bufsz = 0;
+  CKS(cusparseSpMM_bufferSize(h, CUSPARSE_OPERATION_NON_TRANSPOSE, CUSPARSE_OPERATION_NON_TRANSPOSE, &alpha, A, mB,
+                              &beta, mC, CUDA_R_32F, CUSPARSE_SPMM_COO_ALG4, &bufsz));
+  void* buf = nullptr;
+  CK(cudaMalloc(&buf, bufsz + 16));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  std::vector<float> ts;
+  for (int it = 0; it < 7; ++it) {
+    CK(cudaEventRecord(e0));
+    CKS(cusparseSpMM(h, CUSPARSE_OPERATION_NON_TRANSPOSE, CUSPARSE_OPERATION_NON_TRANSPOSE, &alpha, A, mB, &beta, mC,
+                     CUDA_R_32F, CUSPARSE_SPMM_COO_ALG4, buf));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (it >= 2) ts.push_back(ms);
+  }
+  std::sort(ts.begin(), ts.end());
+  std::printf("{\"library\": \"cuSPARSE COO_ALG4\", \"m\": %lld, \"k\": %lld, \"n\": %lld, \"nb\": %lld, \"nnz\": %lld, \"us\": %.1f}\n",
+              (long long)m, (long long)k, (long long)n, (long long)nb, (long long)nnz, ts[ts.size() / 2] * 1e3);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "time") return run_time(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "coo") return run_coo(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "bell") return run_bell(argc, argv);
   std::fprintf(stderr, "usage: cusparse_ref coo <m> <k> <n> <nb> <thr> <alpha> <beta> <out.bin>\n"

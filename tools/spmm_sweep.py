@@ -16,6 +16,7 @@ import argparse
 import collections
 import json
 import os
+import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,6 +31,7 @@ def main():
     ap.add_argument("--sparsity", default="0.5,0.9,0.95")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE comparator column")
     args = ap.parse_args()
     import torch
     spfy = ge.load_package()
@@ -41,7 +43,10 @@ def main():
     cnt = collections.Counter((s.n, s.k, s.m) for s in shapes)  # (M, K, n = H*W)
     nb = args.batch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    print("tag,sparsity,M,K,n,nb,count,nnz,thr_us,thr_GBs,spmm_us,spmm_GBs,spmm_frac_hbm,spmm_GFLOPs")
+    cusp = os.path.join(ROOT, "oracle", "_ref", "cusparse_ref")  # comparator: cuSPARSE COO_ALG4 on the same GPU
+    have_cusp = os.path.exists(cusp) and not args.no_cusparse
+    print("tag,sparsity,M,K,n,nb,count,nnz,thr_us,thr_GBs,spmm_us,spmm_GBs,spmm_frac_hbm,spmm_GFLOPs,cusparse_us")
+    tot_c = collections.defaultdict(float)
     tot = collections.defaultdict(lambda: [0.0, 0.0])
     for (M, K, n), c in sorted(cnt.items(), key=lambda kv: (-kv[0][2], kv[0][0], kv[0][1])):
         gen = torch.Generator(device=dev)
@@ -71,13 +76,24 @@ def main():
             thr_bytes = 2 * 4 * M * K + 12 * nnz
             by = 12 * nnz + 4 * K * n * nb + 4 * M * n * nb
             fl = 2.0 * nnz * n * nb
+            cus = ""
+            if have_cusp:
+                try:
+                    torch.cuda.synchronize()
+                    r = subprocess.run([cusp, "time", str(M), str(K), str(n), str(nb), str(1.0 - s)], capture_output=True,
+                                       text=True, timeout=300)
+                    cus = json.loads(r.stdout.strip().splitlines()[-1])["us"]
+                    tot_c[s] += cus * c
+                except Exception:  # noqa: BLE001
+                    cus = ""
             print(f"{args.tag},{s},{M},{K},{n},{nb},{c},{nnz},{thr_us:.1f},{thr_bytes/thr_us/1e3:.0f},{us:.1f},"
-                  f"{by/us/1e3:.0f},{by/us/1e3/hbm:.3f},{fl/us/1e3:.0f}", flush=True)
+                  f"{by/us/1e3:.0f},{by/us/1e3/hbm:.3f},{fl/us/1e3:.0f},{cus}", flush=True)
             tot[s][0] += us * c
             tot[s][1] += by / (hbm * 1e3) * c
         del w, b, cbuf
     for s, (t, r) in tot.items():
-        print(f"# {args.tag} sparsity {s}: table total {t:.0f} us vs HBM roofline {r:.0f} us -> {r/t:.3f}")
+        extra = f"; cuSPARSE COO_ALG4 {tot_c[s]:.0f} us" if tot_c.get(s) else ""
+        print(f"# {args.tag} sparsity {s}: table total {t:.0f} us vs HBM roofline {r:.0f} us -> {r/t:.3f}{extra}")
 
 
 if __name__ == "__main__":
