@@ -6,7 +6,7 @@ matrix of a ResNet shape table, then the 2:4 sparse GEMM (spmma) of every layer.
 
 One STEP = one pass over one batch of synthetic input: ONE batched prune+compress launch over all
 layers' weights (spfy_prune24_batched) + the spmma of every layer through one plan
-(spfy_spmma_plan_run: three persistent launches that walk all layers' tiles; the plan -- tensor maps
+(spfy_spmma_plan_run: one persistent launch per ring-geometry class that walks all layers' tiles; the plan -- tensor maps
 and tile schedule -- is built once outside the timed region, like cusparseLtMatmulPlanInit in the
 reference, spmma.hxx:51-80), weights orientation M = C_out, K = C_in*kh*kw, N = H*W*b.  Workload = BASELINE.json
 configs[1]: all of datasets/resnet50.csv, fp16, b = 32 images per GPU.  Every layer has its own

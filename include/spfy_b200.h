@@ -147,7 +147,7 @@ SPFY_API int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float 
 /* Many independent problems (the per-layer GEMMs of a datasets/ *.csv table) as ONE plan:
  * tensor maps and the tile schedule are built once (like cusparseLtMatmulPlanInit,
  * spmma.hxx:79, which the reference also keeps outside its timers) and every run issues at
- * most three persistent launches that walk all problems' tiles, so neither launch latency
+ * most one persistent launch per ring-geometry class (six) and operand orientation that walk all problems' tiles, so neither launch latency
  * nor per-layer wave quantisation is paid per layer.  Problems must not alias each other's
  * outputs.  plan_create allocates a small device table; plan_run never allocates or syncs. */
 typedef struct spfy_spmma_problem {

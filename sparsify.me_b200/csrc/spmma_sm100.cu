@@ -6,7 +6,8 @@
 // accumulation in TMEM, fp16/bf16 out.  Two entry points share one kernel:
 //     spfy_spmma            one problem (what the header template calls)
 //     spfy_spmma_plan_*     a list of independent problems (the per-layer GEMMs of a
-//                           datasets/*.csv table) executed by at most three persistent launches
+//                           datasets/*.csv table) executed by one persistent launch per launch class
+//                           present (ring geometry; six classes), chained tail-to-head
 //
 // Every ResNet shape is HBM-bound for this operator.  Two measured facts shape the kernel
 // (DESIGN.md section 4): the chip-wide L2->SM throughput is only ~1.9x the HBM bandwidth, so
@@ -766,8 +767,11 @@ int validate(int dtype, const HostProblem& h, const char* who) {
 // resident classes differ in ring depth: the smaller the resident operand, the more B stages fit, and
 // more B in flight is what the HBM-bound shapes need (measured: 1/2/3/4 stages -> 0.45/0.69/0.79/0.93 of
 // the copy rate); k <= 64 gets half-size stages so that no stage is half empty.
-enum { CLASS_RES_K64 = 0, CLASS_RES_SMALL = 1, CLASS_RES_LARGE = 2, CLASS_STREAM_G1 = 3, CLASS_STREAM_G2 = 4,
-       NUM_CLASSES = 5 };
+// Streaming problems with few k-tiles per unit (K <= 512) write far more than they read: they trade ring
+// depth (2 stages) for all eight epilogue warps.
+enum { CLASS_RES_K64 = 0, CLASS_RES_SMALL = 1, CLASS_RES_LARGE = 2, CLASS_STREAM_G2_SHORT = 3, CLASS_STREAM_G1 = 4,
+       CLASS_STREAM_G2 = 5, NUM_CLASSES = 6 };
+constexpr size_t SHORT_K = 512;
 inline bool is_resident_class(int cls) { return cls <= CLASS_RES_LARGE; }
 constexpr uint32_t BAR_BYTES = 512;
 constexpr uint32_t RES_MAX_BYTES = 96 * 1024;    // resident A (values + metadata)
@@ -786,7 +790,7 @@ int classify(const HostProblem& h, bool grouped, int sm_count) {
     return resident_bytes(h.m, h.k) <= RES_SMALL_BYTES ? CLASS_RES_SMALL : CLASS_RES_LARGE;
   }
   if (m_tiles >= 2 && (grouped || ceil_div(m_tiles, 2) * n_tiles >= 2 * (size_t)sm_count))
-    return CLASS_STREAM_G2;
+    return h.k <= SHORT_K ? CLASS_STREAM_G2_SHORT : CLASS_STREAM_G2;
   return CLASS_STREAM_G1;
 }
 
@@ -841,10 +845,11 @@ void geometry(int cls, uint32_t res_vals, uint32_t res_meta, LaunchParams* L, ui
     res = (uint32_t)round_up(res_vals, 1024) + (uint32_t)round_up(res_meta, 1024);
     L->epi_warps = NUM_EPI_WARPS;  // small K: the epilogue is the hot part
   } else {
-    const uint32_t G = cls == CLASS_STREAM_G2 ? 2u : 1u;
+    const uint32_t G = cls == CLASS_STREAM_G1 ? 1u : 2u;
     L->e_off = B_STAGE_BYTES + G * A_TILE_BYTES;
     stage = L->e_off + G * E_TILE_BYTES;
-    L->epi_warps = NUM_EPI_WARPS / 2;  // large K: shared memory goes to the ring instead
+    // large K: shared memory goes to the ring instead of staging buffers for four more epilogue warps
+    L->epi_warps = cls == CLASS_STREAM_G2_SHORT ? NUM_EPI_WARPS : NUM_EPI_WARPS / 2;
   }
   const uint32_t c_bytes = L->epi_warps * C_BUF_BYTES;
   const uint32_t fixed = 1024 /*alignment slack*/ + c_bytes + BAR_BYTES + res;

@@ -135,7 +135,7 @@ def alloc_compressed(dtype, rows, cols, device, layout=capi.LAYOUT_SM100):
 
 class SpmmaPlan:
     """spfy_spmma_plan_*: a list of independent D_i = alpha_i * A_i(2:4) * op(B_i) + beta_i * C_i executed
-    by at most three persistent launches (tensor maps + tile schedule built once, like
+    by one persistent launch per ring-geometry class present (tensor maps + tile schedule built once, like
     cusparseLtMatmulPlanInit at spmma.hxx:79).  `problems`: dicts with comp, b, out and optional c, alpha,
     beta, op_b.  The plan keeps the tensors alive."""
 

@@ -276,7 +276,7 @@ def test_spmma_plan_matches_single_calls_and_oracle(spfy, orc, cuda):
         problems.append(dict(comp=comp, b=b, c=c, out=torch.zeros(M, N, dtype=torch.float16, device=cuda), alpha=alpha,
                              beta=beta, op_b=op_b))
     plan = spfy.SpmmaPlan(problems)
-    assert 1 <= plan.launches <= 6
+    assert 1 <= plan.launches <= 12  # one per (launch class, opB) present
     before = spfy.launch_count()
     plan.run()
     plan.run()  # a plan is reusable

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--only", default="", help="M,K,N filter")
     ap.add_argument("--plan", action="store_true", help="also time the whole table as ONE plan (grouped launches)")
     ap.add_argument("--plan-only", action="store_true", help="skip the per-shape part")
+    ap.add_argument("--plan-shapes", default="", help="semicolon list of M,K,N: plan over those layers of the table only")
     args = ap.parse_args()
     import torch
     spfy = ge.load_package()
@@ -84,6 +85,10 @@ def main():
         print(f"# {args.tag} total {tot_t:.0f} us vs roofline {tot_r:.0f} us -> {tot_r/tot_t:.3f}")
     if args.plan or args.plan_only:
         gemms = [spfy.shapes.to_gemm(s, "weights", args.batch) for s in spfy.shapes.read_shapes(args.csv)]
+        if args.plan_shapes:
+            keep = set(args.plan_shapes.split(";"))
+            gemms = [g for g in gemms if f"{g.M},{g.K},{g.N}" in keep]
+            tot_r = sum(max(spfy.shapes.spmma_bytes(g) / hbm / 1e3, spfy.shapes.spmma_flops(g) / tc / 1e6) for g in gemms)
         problems = []
         for g in gemms:
             w = (torch.rand(g.M, g.K, device=dev) * 2 - 1).to(tdt)
