@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prune-large", action="store_true", help="skip the large-matrix prune24 measurement")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--per-layer", action="store_true", help="also print a per-layer table to stderr")
     args = ap.parse_args()
@@ -431,6 +432,28 @@ def main():
         # restore the resident weights for anything that follows
         del hostbuf
 
+    # ---- prune24 on a matrix large enough to be bandwidth- rather than ramp-bound (the weight set of one
+    #      model is 47 MB: a 15-20 us launch) -- the "prune GB/s" half of the metric
+    prune_large = None
+    if rank == 0 and not args.no_prune_large:
+        rows = cols = 16384
+        big = (torch.rand(rows, cols, device=dev, generator=gen) * 2 - 1).to(tdt)
+        bcomp = spfy.alloc_compressed(tdt, rows, cols, dev)
+        for _ in range(3):
+            spfy.prune24(big, out=bcomp)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            spfy.prune24(big, out=bcomp)
+        e1.record()
+        torch.cuda.synchronize()
+        pl_ms = e0.elapsed_time(e1) / 10
+        pl_bytes = spfy.shapes.prune24_bytes(rows, cols)
+        prune_large = {"kernel": "prune24_fast_kernel", "case": f"{rows}x{cols} {args.dtype} -> SM100 layout", "ms": pl_ms,
+                       "gbs": pl_bytes / (pl_ms * 1e-3) / 1e9, "frac": pl_bytes / (pl_ms * 1e-3) / 1e9 / hbm_peak,
+                       "algorithmic_bytes": pl_bytes}
+        del big, bcomp
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -456,6 +479,8 @@ def main():
                   "algorithmic_bytes_per_step": prune_bytes_step,
                   "note": "all layers' weights in one launch; 23.5 M elements, 3.125 B/element"},
     }
+    if prune_large:
+        line["prune_large"] = prune_large
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu and world == 1:

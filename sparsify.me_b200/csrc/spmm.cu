@@ -534,13 +534,20 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
           const int r = r0 + q;
           while (true) {
             const int32_t c = c_[q];
-            const bool in = c >= (int32_t)k0 && c < (int32_t)k_end;
-            const unsigned in_mask = __ballot_sync(0xffffffffu, in);
-            const unsigned adv = __popc(__ballot_sync(0xffffffffu, c < (int32_t)k_end));  // sorted: a prefix
-            const unsigned cnt = __popc(in_mask);
-            if (in)
-              scratch[__popc(in_mask & ((1u << lane) - 1u))] =
-                  make_uint2((uint32_t)(c - (int32_t)k0), __float_as_uint(v_[q]));
+            unsigned cnt, adv;
+            if (sorted) {
+              // everything at or after the cursor is >= k0, and what is below k_end is a prefix of the request
+              cnt = adv = __popc(__ballot_sync(0xffffffffu, c < (int32_t)k_end));
+              if (lane < cnt) scratch[lane] = make_uint2((uint32_t)(c - (int32_t)k0), __float_as_uint(v_[q]));
+            } else {
+              const bool in = c >= (int32_t)k0 && c < (int32_t)k_end;
+              const unsigned in_mask = __ballot_sync(0xffffffffu, in);
+              cnt = __popc(in_mask);
+              adv = 32u;
+              if (in)
+                scratch[__popc(in_mask & ((1u << lane) - 1u))] =
+                    make_uint2((uint32_t)(c - (int32_t)k0), __float_as_uint(v_[q]));
+            }
             __syncwarp();
 #pragma unroll 4
             for (unsigned t = 0; t < cnt; ++t) {

@@ -29,10 +29,10 @@ ncu_spmm)
   CMD="python tools/spmm_one.py 64 576 12544 32 0.95"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
 ncu_spmma)
-  CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+  CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-prune-large"
   $CMD > $OUT/plain_$TAG.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'spmma_kernel|prune24' -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_l_$TAG.log 2>&1; echo "launch list rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:spmma_kernel -s 15 -c 5 -o $OUT/prof_spmma_$TAG -f $CMD > $OUT/ncu_s_$TAG.log 2>&1; echo "ncu spmma rc=$?";;
+  ncu --set full --clock-control none --import-source on -k regex:spmma_kernel -s 18 -c 6 -o $OUT/prof_spmma_$TAG -f $CMD > $OUT/ncu_s_$TAG.log 2>&1; echo "ncu spmma rc=$?";;
 ncu_prune)
   CMD="python tools/prune_probe.py --reps 1 --only-large"
   $CMD > $OUT/plain_prune_$TAG.log 2>&1 &&
