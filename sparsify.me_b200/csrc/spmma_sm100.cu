@@ -105,7 +105,8 @@ struct LaunchParams {
   uint32_t epi_warps;  // 8: one column half per warp; 4: warps 2-5 do both halves
   uint32_t bk;         // logical k per ring stage: 128, or 64 for the k <= 64 class (half-size stages)
   uint32_t dbg;        // development switches (SPFY_SPMMA_DEBUG): 2 no epilogue work, 4 no B loads, 8 no MMAs,
-                       // 16 no streamed A loads (timing experiments only: results are garbage)
+                       // 16 no streamed A loads, 32 no TMA stores, 64 no wait for the previous store's
+                       // smem read (timing experiments only: results are garbage)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -580,7 +581,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     const uint32_t sc = smem_base + L.c_off + e * C_BUF_BYTES;
     const uint32_t st_base = sc + lane * 128;
     const uint32_t sw = lane & 7u;
-    const bool no_epi = (L.dbg & 2u) != 0;
+    const bool no_epi = (L.dbg & 2u) != 0, no_store = (L.dbg & 32u) != 0, no_wait = (L.dbg & 64u) != 0;
     uint32_t job = 0;
     const ProblemDev* last = nullptr;
     const CUtensorMap* tmap_d = nullptr;
@@ -625,31 +626,44 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
           }
           if (warp_has_rows && !no_epi) {
-            if (lane == 0) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
+            if (lane == 0 && !no_wait) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
             __syncwarp();
             const uint32_t grow = m0 + row_in_tile;
-            const bool use_c = beta != 0.f && grow < pm;
+            if (alpha == 1.f && beta == 0.f) {
+              // the common case (the reference's defaults, spmma.hxx:32-33): convert and stage, nothing else.
+              // Kept apart from the general path: predicated-off C loads / FMAs still cost issue slots, and
+              // with two epilogue warps per scheduler the conversion loop is what bounds the small-K classes.
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float v[8];
+              for (int q = 0; q < 8; ++q)
+                st_shared_v4(st_base + ((q ^ sw) << 4),
+                             pack2<BF16>(__uint_as_float(acc[q * 8 + 0]), __uint_as_float(acc[q * 8 + 1])),
+                             pack2<BF16>(__uint_as_float(acc[q * 8 + 2]), __uint_as_float(acc[q * 8 + 3])),
+                             pack2<BF16>(__uint_as_float(acc[q * 8 + 4]), __uint_as_float(acc[q * 8 + 5])),
+                             pack2<BF16>(__uint_as_float(acc[q * 8 + 6]), __uint_as_float(acc[q * 8 + 7])));
+            } else {
+              const bool use_c = beta != 0.f && grow < pm;
 #pragma unroll
-              for (int x = 0; x < 8; ++x) v[x] = alpha * __uint_as_float(acc[q * 8 + x]);
-              if (use_c && n0 + q * 8 < pn) {
-                const uint4 cw = *reinterpret_cast<const uint4*>(Cptr + (size_t)grow * ldc + n0 + q * 8);
-                const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+              for (int q = 0; q < 8; ++q) {
+                float v[8];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                  const float2 f = unpack2<BF16>(cws[x]);
-                  v[2 * x] += beta * f.x;
-                  v[2 * x + 1] += beta * f.y;
+                for (int x = 0; x < 8; ++x) v[x] = alpha * __uint_as_float(acc[q * 8 + x]);
+                if (use_c && n0 + q * 8 < pn) {
+                  const uint4 cw = *reinterpret_cast<const uint4*>(Cptr + (size_t)grow * ldc + n0 + q * 8);
+                  const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                  for (int x = 0; x < 4; ++x) {
+                    const float2 f = unpack2<BF16>(cws[x]);
+                    v[2 * x] += beta * f.x;
+                    v[2 * x + 1] += beta * f.y;
+                  }
                 }
+                st_shared_v4(st_base + ((q ^ sw) << 4), pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]),
+                             pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
               }
-              st_shared_v4(st_base + ((q ^ sw) << 4), pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]),
-                           pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !no_store) {
               tma_store_2d(tmap_d, sc, (int)n0, (int)(m0 + quarter * 32));
               bulk_commit();
             }
