@@ -105,8 +105,7 @@ struct LaunchParams {
   uint32_t epi_warps;  // 8: one column half per warp; 4: warps 2-5 do both halves
   uint32_t bk;         // logical k per ring stage: 128, or 64 for the k <= 64 class (half-size stages)
   uint32_t dbg;        // development switches (SPFY_SPMMA_DEBUG): 2 no epilogue work, 4 no B loads, 8 no MMAs,
-                       // 16 no streamed A loads, 32 no TMA stores, 64 no wait for the previous store's
-                       // smem read (timing experiments only: results are garbage)
+                       // 16 no streamed A loads, 32 no TMA stores (timing experiments only: results are garbage)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -581,7 +580,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     const uint32_t sc = smem_base + L.c_off + e * C_BUF_BYTES;
     const uint32_t st_base = sc + lane * 128;
     const uint32_t sw = lane & 7u;
-    const bool no_epi = (L.dbg & 2u) != 0, no_store = (L.dbg & 32u) != 0, no_wait = (L.dbg & 64u) != 0;
+    const bool no_epi = (L.dbg & 2u) != 0, no_store = (L.dbg & 32u) != 0;
     uint32_t job = 0;
     const ProblemDev* last = nullptr;
     const CUtensorMap* tmap_d = nullptr;
@@ -626,7 +625,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
           }
           if (warp_has_rows && !no_epi) {
-            if (lane == 0 && !no_wait) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
+            if (lane == 0) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
             __syncwarp();
             const uint32_t grow = m0 + row_in_tile;
             if (alpha == 1.f && beta == 0.f) {

@@ -12,7 +12,7 @@ spmm) python tools/spmm_sweep.py --tag $TAG > $OUT/spmm_sweep_$TAG.csv 2>&1; ech
 sweep) python tools/layer_sweep.py --plan --tag $TAG > $OUT/sweep_$TAG.csv 2>&1; echo "sweep rc=$?";;
 ref) python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?";;
 dbg) for d in 2 8 10; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --tag dbg$d > $OUT/sweep_${TAG}_dbg$d.csv 2>&1; echo "dbg$d rc=$?"; done;;
-plandbg) for d in 0 32 64 2; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --plan-only --tag dbg$d > $OUT/plan_${TAG}_dbg$d.txt 2>&1; echo "plan dbg$d rc=$?"; done;;
+plandbg) for d in 32 160 288 416; do SPFY_SPMMA_DEBUG=$d python tools/layer_sweep.py --plan-only --tag dbg$d > $OUT/plan_${TAG}_dbg$d.txt 2>&1; echo "plan dbg$d rc=$?"; done;;
 pfsweep) for d in 0 2 4 6 8 12 16 24; do SPFY_SPMMA_PF=$d python tools/layer_sweep.py --plan-only --tag pf$d > $OUT/plan_${TAG}_pf$d.txt 2>&1; echo "plan pf$d rc=$?"; grep "^#" $OUT/plan_${TAG}_pf$d.txt | sed 's/{[^}]*}//'; done;;
 g1exp) SPFY_SPMMA_FORCE_G1=1 python tools/layer_sweep.py --plan-only --tag g1 > $OUT/plan_${TAG}_g1.txt 2>&1; grep "^#" $OUT/plan_${TAG}_g1.txt | sed 's/{[^}]*}//';;
 stexp) for c in 1 2; do SPFY_SPMMA_STAGES=$c python tools/layer_sweep.py --plan-only --tag st$c > $OUT/plan_${TAG}_st$c.txt 2>&1; grep "^#" $OUT/plan_${TAG}_st$c.txt | sed 's/{[^}]*}//'; done;;
