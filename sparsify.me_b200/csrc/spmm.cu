@@ -401,13 +401,14 @@ __device__ __forceinline__ void csr_chunk_load(float (&pf)[CSR_PF], const CsrSpm
   }
 }
 
+template <int PITCH>
 __device__ __forceinline__ void csr_chunk_store(const float (&pf)[CSR_PF], float* sB, bool wide, uint32_t warp,
                                                 uint32_t lane) {
   if (wide) {
     const uint32_t l8 = lane & 7u;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      float* dst = sB + (s * 64 + warp * 4 + (lane >> 3)) * CSR_PITCH + l8 * 4;
+      float* dst = sB + (s * 64 + warp * 4 + (lane >> 3)) * PITCH + l8 * 4;
 #pragma unroll
       for (int q = 0; q < 6; ++q)
 #pragma unroll
@@ -416,7 +417,7 @@ __device__ __forceinline__ void csr_chunk_store(const float (&pf)[CSR_PF], float
   } else {
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-      float* dst = sB + (s * 16 + warp) * CSR_PITCH + lane;
+      float* dst = sB + (s * 16 + warp) * PITCH + lane;
 #pragma unroll
       for (int u = 0; u < 6; ++u) dst[u * 32] = pf[s * 6 + u];
     }
@@ -441,14 +442,26 @@ __device__ __forceinline__ void csr_fetch(const CsrSpmmParams& P, uint32_t batch
   }
 }
 
-template <int RPW, bool BELL>
+// MODE 0: CSR rows.  MODE 1: blocked-ELL rows, every slot an independent non-zero (any block size).
+// MODE 2: blocked-ELL with an even block size, walked as (row pair) x (column pair): the two rows of a pair
+// share their block-column ids, so one 64-bit read of B[c], B[c+1] per output column feeds four FMAs -- half
+// the shared-memory wavefronts per FMA of MODE 1 (even row pitch: the 64-bit reads are aligned and
+// conflict-free per half warp).
+enum { SPMM_CSR = 0, SPMM_BELL = 1, SPMM_BELL_PAIRS = 2 };
+constexpr int CSR_PITCH_PAIRS = CSR_KC + 2;
+constexpr int CSR_SCRATCH_FLOATS = CSR_WARPS * 32 * 5;  // per warp: 32 x (column + up to four values)
+
+template <int RPW, int MODE>
 __global__ void __launch_bounds__(CSR_THREADS, 1)
 spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
+  constexpr bool BELL = MODE != SPMM_CSR;
+  constexpr int PITCH = MODE == SPMM_BELL_PAIRS ? CSR_PITCH_PAIRS : CSR_PITCH;
   constexpr int TM = CSR_WARPS * RPW;
   extern __shared__ float smem_f[];
-  float* sB = smem_f;                                                         // [CSR_TN][CSR_PITCH]
-  uint2* scratch = reinterpret_cast<uint2*>(smem_f + CSR_TN * CSR_PITCH) + (threadIdx.x >> 5) * 32;
-  size_t* colB = reinterpret_cast<size_t*>(smem_f + CSR_TN * CSR_PITCH + CSR_WARPS * 64);  // [CSR_TN]
+  float* sB = smem_f;                                                         // [CSR_TN][PITCH]
+  float* scratch_f = smem_f + CSR_TN * CSR_PITCH_PAIRS + (threadIdx.x >> 5) * (32 * 5);
+  uint2* scratch = reinterpret_cast<uint2*>(scratch_f);                       // MODE 0/1: 32 x (column, value)
+  size_t* colB = reinterpret_cast<size_t*>(smem_f + CSR_TN * CSR_PITCH_PAIRS + CSR_SCRATCH_FLOATS);  // [CSR_TN]
   size_t* colC = colB + CSR_TN;                                                              // [CSR_TN]
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool sorted = *P.sorted != 0;
@@ -499,7 +512,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
       const uint32_t k0 = ch * CSR_KC;
       const uint32_t kn = min((uint32_t)CSR_KC, P.k - k0);
       if (ch) __syncthreads();  // everyone is done with the previous chunk
-      csr_chunk_store(pf, sB, P.vec && kn == (uint32_t)CSR_KC, warp, lane);
+      csr_chunk_store<PITCH>(pf, sB, P.vec && kn == (uint32_t)CSR_KC, warp, lane);
       __syncthreads();
       if (ch + 1 < nchunks) {
         const uint32_t k1 = k0 + CSR_KC, kn1 = min((uint32_t)CSR_KC, P.k - k1);
@@ -508,7 +521,72 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
 
       // ---- multiply: every warp walks its RPW rows ----
       const uint32_t k_end = k0 + kn;
-      const float* sBl = sB + lane * CSR_PITCH;
+      const float* sBl = sB + lane * PITCH;
+      if (MODE == SPMM_BELL_PAIRS) {
+        // ---- blocked-ELL, (row pair) x (column pair); cur[2*rp] is the pair cursor of row pair rp ----
+        uint32_t* sc = reinterpret_cast<uint32_t*>(scratch_f);       // [32] column (relative to k0)
+        float4* sv = reinterpret_cast<float4*>(scratch_f + 32);      // [32] a(r0,c) a(r0,c+1) a(r0+1,c) a(r0+1,c+1)
+        const uint32_t npairs = P.ell_cols / 2;
+#pragma unroll
+        for (int rp = 0; rp < RPW / 2; ++rp) {
+          const uint32_t r0 = i0 + 2 * rp;
+          if (r0 >= P.m) break;
+          const bool r1_ok = r0 + 1 < P.m;
+          const int64_t* bcol = P.bell_cols[batch] + (size_t)(r0 / P.block) * P.bcols;
+          const float* v0p = P.bell_vals[batch] + (size_t)r0 * P.ell_cols;
+          const float* v1p = v0p + P.ell_cols;
+          uint32_t pos = sorted ? cur[2 * rp] : 0u;
+          while (pos < npairs) {
+            const uint32_t p = pos + lane;
+            int32_t c = 0x7fffffff;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < npairs) {
+              const int64_t bc = bcol[(2 * p) / P.block];
+              if (bc >= 0) c = (int32_t)(bc * P.block + (2 * p) % P.block);
+              a.x = v0p[2 * p];
+              a.y = v0p[2 * p + 1];
+              if (r1_ok) {
+                a.z = v1p[2 * p];
+                a.w = v1p[2 * p + 1];
+              }
+            }
+            unsigned cnt, adv;
+            if (sorted) {
+              cnt = adv = __popc(__ballot_sync(0xffffffffu, c < (int32_t)k_end));
+              if (lane < cnt) {
+                sc[lane] = (uint32_t)(c - (int32_t)k0);
+                sv[lane] = a;
+              }
+            } else {
+              const bool in = c >= (int32_t)k0 && c < (int32_t)k_end;
+              const unsigned in_mask = __ballot_sync(0xffffffffu, in);
+              cnt = __popc(in_mask);
+              adv = 32u;
+              if (in) {
+                const unsigned at = __popc(in_mask & ((1u << lane) - 1u));
+                sc[at] = (uint32_t)(c - (int32_t)k0);
+                sv[at] = a;
+              }
+            }
+            __syncwarp();
+#pragma unroll 2
+            for (unsigned t = 0; t < cnt; ++t) {
+              const float4 av = sv[t];
+              const float* bp = sBl + sc[t];
+#pragma unroll
+              for (int j = 0; j < CSR_TJ; ++j) {
+                const float2 b = *reinterpret_cast<const float2*>(bp + j * 32 * PITCH);
+                acc[2 * rp][j] = fmaf(av.y, b.y, fmaf(av.x, b.x, acc[2 * rp][j]));
+                acc[2 * rp + 1][j] = fmaf(av.w, b.y, fmaf(av.z, b.x, acc[2 * rp + 1][j]));
+              }
+            }
+            __syncwarp();
+            pos += adv;
+            if (sorted && adv < 32u) break;  // the rest of the row pair lies beyond this chunk
+          }
+          if (sorted) cur[2 * rp] = pos;
+        }
+      } else
       // rows are handled four at a time: the first request of each of the four goes out before any is
       // processed (cur[] doubles as the scan position; unsorted rows restart from the row start)
 #pragma unroll
@@ -555,7 +633,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
               const float a = __uint_as_float(e.y);
               const float* bp = sBl + e.x;
 #pragma unroll
-              for (int j = 0; j < CSR_TJ; ++j) acc[r][j] = fmaf(a, bp[j * 32 * CSR_PITCH], acc[r][j]);
+              for (int j = 0; j < CSR_TJ; ++j) acc[r][j] = fmaf(a, bp[j * 32 * PITCH], acc[r][j]);
             }
             __syncwarp();
             bool more;
@@ -597,23 +675,21 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   }
 }
 
-template <int RPW, bool BELL>
+template <int RPW, int MODE>
 int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
-  constexpr int TM = CSR_WARPS * RPW;
-  size_t smem = ((size_t)CSR_TN * CSR_PITCH) * 4;
-  const size_t c_tile = (size_t)CSR_TN * (TM + 1) * 4;
-  if (smem < c_tile) smem = c_tile;
-  smem += (size_t)CSR_WARPS * 32 * 8 + 2 * CSR_TN * sizeof(size_t);  // scratch lines + column offsets
+  constexpr bool BELL = MODE != SPMM_CSR;
+  size_t smem = ((size_t)CSR_TN * CSR_PITCH_PAIRS) * 4;  // >= the C tile [CSR_TN][TM + 1] for TM <= 128
+  smem += (size_t)CSR_SCRATCH_FLOATS * 4 + 2 * CSR_TN * sizeof(size_t);  // scratch lines + column offsets
   static std::atomic<int> attr_set[64];
   int dev = 0;
   SPFY_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63].load()) {
-    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW, BELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_csr_kernel<RPW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev & 63].store(1);
   }
   const uint32_t tiles = P.row_tiles * P.col_tiles * (BELL ? P.num_batches : 1u);
   const uint32_t grid = tiles < (uint32_t)sm_count ? tiles : (uint32_t)sm_count;
-  spmm_csr_kernel<RPW, BELL><<<grid, CSR_THREADS, smem, s>>>(P);
+  spmm_csr_kernel<RPW, MODE><<<grid, CSR_THREADS, smem, s>>>(P);
   SPFY_LAUNCH_OK("spmm_csr_kernel");
   return SPFY_OK;
 }
@@ -741,7 +817,7 @@ int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batch
   P.row_tiles = (uint32_t)ceil_div(m, tall ? 128 : 64);
   if (col_tiles * P.row_tiles >= (1ull << 32)) return fail(SPFY_E_UNSUPPORTED, "spmm_csr: too many tiles");
   P.col_tiles = (uint32_t)col_tiles;
-  return tall ? launch_spmm_csr<8, false>(P, di.sm_count, s) : launch_spmm_csr<4, false>(P, di.sm_count, s);
+  return tall ? launch_spmm_csr<8, SPMM_CSR>(P, di.sm_count, s) : launch_spmm_csr<4, SPMM_CSR>(P, di.sm_count, s);
 }
 
 int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,
@@ -804,7 +880,10 @@ int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t
     const bool tall = rows > 64;
     P.row_tiles = (uint32_t)ceil_div(rows, tall ? 128 : 64);
     P.col_tiles = (uint32_t)ceil_div(n, CSR_TN);
-    return tall ? launch_spmm_csr<8, true>(P, di.sm_count, s) : launch_spmm_csr<4, true>(P, di.sm_count, s);
+    if (block % 2 == 0 && ell_cols % 2 == 0 && cols % 2 == 0)
+      return tall ? launch_spmm_csr<8, SPMM_BELL_PAIRS>(P, di.sm_count, s)
+                  : launch_spmm_csr<4, SPMM_BELL_PAIRS>(P, di.sm_count, s);
+    return tall ? launch_spmm_csr<8, SPMM_BELL>(P, di.sm_count, s) : launch_spmm_csr<4, SPMM_BELL>(P, di.sm_count, s);
   }
   SpmmDense D;
   memset(&D, 0, sizeof(D));

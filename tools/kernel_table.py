@@ -111,7 +111,7 @@ def main():
     cs = [torch.empty(n, m, device=dev) for _ in range(nb)]
     us = timed(lambda: spfy.batched.spmm(cis, vas, B, cs, m, n, k, block, ell_cols), reps=3)
     by = nb * (m * ell_cols * 4 + (m // block) * bcols * 8 + m * n * 4) + k * n * 4
-    line("A5", "spmm_rowsplit_kernel<bell>", f"m={m} n={n} k={k} nb={nb} block 2", us, by,
+    line("A5", "spmm_csr_kernel<blocked-ELL pairs>", f"m={m} n={n} k={k} nb={nb} block 2", us, by,
          f"{2.0*nb*m*ell_cols*n/us/1e6:.1f} TFLOP/s fp32")
 
 
