@@ -1,9 +1,11 @@
-// examples/spmma.cu -- bin/spmma m n k b : 2:4 prune + compress + sparse GEMM, prints the three
-// phase timings (same CLI and stdout lines as the reference driver, examples/spmma.cu:22-66).
-// Differences: runs on compute capability 10.x (the reference insists on 8.0, :35-40) and uses
-// fp16 data (the reference feeds float buffers to an fp16 descriptor, spmma.hxx:40).
+// examples/spmma.cu -- bin/spmma m n k b : 2:4 prune + compress + sparse GEMM of one problem, printing the
+// three phase times exactly as examples/profiling.py:8-17 of the reference parses them
+// ("Prune time: … ms" / "Compress time: … ms" / "Multiplication time: … ms").
+// Unlike the reference driver (examples/spmma.cu:35-40 insists on compute capability 8.0 and feeds float
+// buffers to an fp16 descriptor, spmma.hxx:40) this one runs on 10.x and on real fp16 data.
 #include <cstdlib>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include <cuda_fp16.h>
@@ -13,33 +15,39 @@
 #include <sparsify.me/spmma.hxx>
 #include <sparsify.me/util/util.hxx>
 
-int main(int argc, char** argv) {
-  using namespace sparsifyme;
-  using type_t = __half;
-  int major = 0, minor = 0;
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, 0);
-  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, 0);
-  if (major != 10) {
-    std::cerr << "\nthis build of spmma runs tcgen05.mma.sp and needs compute capability 10.x (found " << major << "."
-              << minor << ")\n" << std::endl;
-    return EXIT_FAILURE;
-  }
-  std::size_t m = 32, n = 32, k = 32, batch_size = 1;
-  if (argc >= 5) {
-    m = std::strtoull(argv[1], nullptr, 10);
-    n = std::strtoull(argv[2], nullptr, 10);
-    k = std::strtoull(argv[3], nullptr, 10);
-    batch_size = std::strtoull(argv[4], nullptr, 10);
-  }
-  // like the reference (:48-59) the buffers hold `batch_size` problems; spmma multiplies the first
-  thrust::host_vector<type_t> hA(m * k * batch_size), hB(k * n * batch_size);
-  for (auto& a : hA) a = __float2half(util::get_random());
-  for (auto& b : hB) b = __float2half(util::get_random());
-  thrust::device_vector<type_t> dA = hA, dB = hB, dC(m * n * batch_size);
+namespace {
 
-  std::vector<float> times = spmma(dA.data().get(), dB.data().get(), dC.data().get(), m, n, k, batch_size);
-  std::cout << "Prune time: " << times[0] << " ms" << std::endl;
-  std::cout << "Compress time: " << times[1] << " ms" << std::endl;
-  std::cout << "Multiplication time: " << times[2] << " ms" << std::endl;
+bool device_is_blackwell() {
+  int cc[2] = {0, 0};
+  cudaDeviceGetAttribute(&cc[0], cudaDevAttrComputeCapabilityMajor, 0);
+  cudaDeviceGetAttribute(&cc[1], cudaDevAttrComputeCapabilityMinor, 0);
+  if (cc[0] == 10) return true;
+  std::cerr << "\nthis build of spmma issues tcgen05.mma.sp and needs compute capability 10.x (found " << cc[0] << "."
+            << cc[1] << ")\n" << std::endl;
+  return false;
+}
+
+thrust::device_vector<__half> random_halves(std::size_t count) {
+  thrust::host_vector<__half> h(count);
+  for (std::size_t i = 0; i < count; ++i) h[i] = __float2half(sparsifyme::util::get_random());
+  return h;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (!device_is_blackwell()) return EXIT_FAILURE;
+  std::size_t dims[4] = {32, 32, 32, 1};  // m n k b
+  if (argc >= 5)
+    for (int i = 0; i < 4; ++i) dims[i] = std::strtoull(argv[i + 1], nullptr, 10);
+  const std::size_t m = dims[0], n = dims[1], k = dims[2], batch = dims[3];
+
+  // the buffers are sized for `batch` problems like the reference's (:48-59); spmma multiplies the first
+  thrust::device_vector<__half> A = random_halves(m * k * batch), B = random_halves(k * n * batch);
+  thrust::device_vector<__half> C(m * n * batch);
+  const std::vector<float> ms = sparsifyme::spmma(A.data().get(), B.data().get(), C.data().get(), m, n, k, batch);
+
+  const char* phase[3] = {"Prune", "Compress", "Multiplication"};
+  for (int i = 0; i < 3; ++i) std::cout << phase[i] << " time: " << ms[i] << " ms" << std::endl;
   return 0;
 }
