@@ -17,9 +17,12 @@
 //     behaviour of the cusparseLt calls at include/sparsify.me/spmma.hxx:86-113
 //     and are cross-checked against cusparseLt 0.7.1 on a B200
 //     (oracle/cusparselt_ref.cu -> tests/golden/cusparselt_*.npz).
-//   * the unstructured routines (orc_threshold_to_coo, orc_spmm_*) restate the
-//     cuSPARSE generic-API contract used at include/sparsify.me/spmm.hxx:57-110,
-//     160-187; for those: parity unpinned (no runnable reference output).
+//   * the unstructured routines (orc_threshold_to_coo, orc_spmm_coo_batched_f64,
+//     orc_spmm_bell_f64) restate the cuSPARSE generic-API contract used at
+//     include/sparsify.me/spmm.hxx:57-110,160-187 and are checked BIT FOR BIT
+//     against cuSPARSE 12.5 itself, driven with the reference's call sequences
+//     on a B200 (oracle/cusparse_ref.cu -> tests/golden/cusparse_*.npz; the
+//     reference's own drivers for this path do not compile at HEAD).
 //
 // Build: see oracle/Makefile (g++ -O3 -fopenmp -shared).
 #include <algorithm>
