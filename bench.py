@@ -282,6 +282,103 @@ def config_dict(args, nlayers, launches=None):
             "parallelism": f"batch-sharded x{args.gpus}, no data-path collective"}
 
 
+# ------------------------------------------------------------------------------ unstructured workload
+def run_coo(args):
+    """BASELINE.json configs[2]/[3]: magnitude-threshold prune of every layer's weights to COO, then the batched COO
+    SpMM of every layer (A = W shared by the batch, B_b = [K x H*W] column-major per image, fp32 -- the operand
+    types of spmm.hxx:165-180).  The batch of `--batch` images is sharded on image boundaries across the ranks
+    (STRONG scaling: the job is fixed), no data-path collective.  One step = threshold->COO + SpMM of all layers."""
+    import collections
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (sparsify.me_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    spfy = ge.load_package()
+    csv = args.csv if args.csv != "resnet50.csv" else "resnet101.csv"
+    shapes = spfy.shapes.read_shapes(csv)
+    lo, hi = spfy.multigpu.shard_batch(args.batch, world, rank)
+    nb = hi - lo
+    hbm_peak, _, _, peak_src = read_peaks()
+    cnt = collections.Counter((s.n, s.k, s.m) for s in shapes)  # (M, K, n = H*W) -> layers of that shape
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x5EED)  # same weights on every rank (replicated, pruned redundantly)
+    work = []
+    for (M, K, n), c in cnt.items():
+        w = torch.rand(M, K, device=dev, generator=gen) * 2 - 1
+        kth = max(1, min(M * K, int(args.sparsity * M * K)))
+        thr = float(torch.kthvalue(w.abs().flatten(), kth).values)
+        per_set = 4 * (K + M) * n * max(nb, 1)
+        nsets = max(1, min(4, -(-300_000_000 // max(per_set, 1))))  # rotate so that nothing is served from L2
+        bs = [torch.rand(max(nb, 1), n, K, device=dev) * 2 - 1 for _ in range(nsets)]
+        cs = [torch.empty(max(nb, 1), n, M, device=dev) for _ in range(nsets)]
+        work.append(dict(M=M, K=K, n=n, count=c, w=w, thr=thr, b=bs, c=cs))
+
+    def step(it):
+        fl = by = 0.0
+        for x in work:
+            for rep in range(x["count"]):
+                ri, ci, va, nnz = spfy.threshold_to_coo(x["w"], x["thr"])
+                if nb:
+                    j = (it * x["count"] + rep) % len(x["b"])
+                    spfy.batched.strided_coo(x["M"], x["K"], nnz, x["K"], x["n"], nb, ri, ci, va, x["b"][j], x["c"][j])
+                fl += 2.0 * nnz * x["n"] * nb
+                by += 12 * nnz + 4.0 * (x["K"] + x["M"]) * x["n"] * nb
+        return fl, by
+
+    for i in range(max(1, min(args.warmup, 3))):
+        step(i)
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 20))  # a step is tens of milliseconds
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = spfy.launch_count()
+    sampler = ClockSampler(local, str(torch.cuda.get_device_properties(local).uuid))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0.record()
+    for i in range(steps):
+        fl, by = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1) / steps, fl, by], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t[0] = tmax[0]
+    ms, fl_all, by_all = (float(x) for x in t.tolist())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "batched COO SpMM TFLOP/s (2*nnz*N) over a ResNet table, threshold prune included", "value": fl_all / ms / 1e9,
+            "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"datasets/{csv}: all {len(shapes)} layers, weights kept above the {args.sparsity:.2f} magnitude "
+                                   f"quantile -> COO, batched COO SpMM over {args.batch} images sharded across {world} rank(s)",
+                       "csv": csv, "global_batch": args.batch, "sparsity": args.sparsity,
+                       "l2_policy": "operand sets rotated so that a launch never finds B in L2",
+                       "parallelism": f"batch-sharded x{world}, no data-path collective"},
+            "clocks": clocks, "gpu_launches": spfy.launch_count() - launches0,
+            "roofline": {"bound": "hbm", "kernel": "spmm_csr_kernel", "achieved": by_all / ms / 1e6, "peak": hbm_peak * world,
+                         "unit": "GB/s", "frac": by_all / ms / 1e6 / (hbm_peak * world), "traffic": None, "peak_source": peak_src,
+                         "note": "the binding roofline of this kernel is shared-memory wavefronts, not HBM (DESIGN.md 4)"}}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 # ------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -297,9 +394,15 @@ def main():
     ap.add_argument("--no-prune-large", action="store_true", help="skip the large-matrix prune24 measurement")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--per-layer", action="store_true", help="also print a per-layer table to stderr")
+    ap.add_argument("--workload", default="spmma", choices=["spmma", "coo"],
+                    help="spmma: the headline (BASELINE.json configs[1]); coo: unstructured threshold prune + batched COO "
+                         "SpMM over a table, batch-sharded across ranks (configs[2]/[3])")
+    ap.add_argument("--sparsity", type=float, default=0.9, help="--workload coo: fraction of the weights dropped")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "coo":
+        return run_coo(args)
 
     import ctypes
     import numpy as np
