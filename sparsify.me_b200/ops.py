@@ -229,10 +229,12 @@ def spmma(a, b, c, m, n, k, batch_size=1, transpose_a=capi.OP_N, transpose_b=cap
 
 
 # ------------------------------------------------------------------- unstructured path
-def threshold_to_coo(a, threshold, capacity=None, want_csr=False):
+def threshold_to_coo(a, threshold, capacity=None, want_csr=False, sync=True):
     """Unstructured magnitude prune: keep x iff |x| > threshold; COO sorted by (row, col),
     fp32 values, int32 indices (the operand format of spmm.hxx:165-168).
-    Returns (row_idx, col_idx, vals, nnz[, row_ptr]); index/value tensors are trimmed to nnz."""
+    Returns (row_idx, col_idx, vals, nnz[, row_ptr]); index/value tensors are trimmed to nnz.
+    sync=False skips the nnz read-back: the arrays keep their full capacity, nnz is a device tensor and
+    row_ptr is always returned (feed it to batched.csr, which needs no host-side nnz)."""
     rows, cols = a.shape
     cap = rows * cols if capacity is None else capacity
     dev = a.device
@@ -247,6 +249,8 @@ def threshold_to_coo(a, threshold, capacity=None, want_csr=False):
     capi.spfy_threshold_to_coo(_dtype_code(a), _ptr(a), a.stride(0), rows, cols, float(threshold),
                                _ptr(ri), _ptr(ci), _ptr(va), cap, _ptr(nnz), _ptr(rp), _ptr(ws),
                                ws.numel(), _stream())
+    if not sync:
+        return ri, ci, va, nnz, rp
     n = int(nnz.item())
     kept = min(n, cap)
     res = (ri[:kept], ci[:kept], va[:kept], n)

@@ -25,6 +25,12 @@ ktable) python tools/kernel_table.py --tag $TAG > $OUT/kernels_$TAG.csv 2> $OUT/
 ab) for r in 1 2 3; do for v in prev cur; do
       if [ $v = prev ]; then export SPFY_LIB=$PWD/gpurun_ab/lib_prev.so; else unset SPFY_LIB; fi
       python tools/layer_sweep.py --plan-only --tag $v$r 2>&1 | grep "^#" | sed 's/{[^}]*}//' | tr '\n' ' '; echo; done; done; unset SPFY_LIB;;
+mgcoo)
+  NG=${NGPUS:-2}
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 bench.py --workload coo --gpus $NG --steps 5 --warmup 2 > $OUT/bench_coo_mg${NG}_$TAG.json 2> $OUT/bench_coo_mg${NG}_$TAG.err; echo "mgcoo rc=$?"; tail -c 400 $OUT/bench_coo_mg${NG}_$TAG.json;;
+mg152)
+  NG=${NGPUS:-2}
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29515 bench.py --csv resnet152.csv --batch 32 --gpus $NG --steps 30 --warmup 5 --no-cpu --no-prune-large > $OUT/bench_r152_mg${NG}_$TAG.json 2> $OUT/bench_r152_mg${NG}_$TAG.err; echo "mg152 rc=$?"; tail -c 300 $OUT/bench_r152_mg${NG}_$TAG.json;;
 ncu_spmm)
   CMD="python tools/spmm_one.py 64 576 12544 32 0.95"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
