@@ -33,6 +33,17 @@ import sys
 import threading
 import time
 
+
+def claim_stdout():
+    """stdout carries the one JSON line only.  NCCL prints its version banner to fd 1 whatever NCCL_DEBUG_FILE
+    says, so multi-rank runs keep a private duplicate of the real stdout for the JSON line and point fd 1 at
+    stderr for everything else (libraries included)."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return out
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
@@ -298,8 +309,8 @@ def run_coo(args):
         raise SystemExit("bench.py: no CUDA device (sparsify.me_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_out = claim_stdout() if world > 1 else sys.stdout
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     spfy = ge.load_package()
     csv = args.csv if args.csv != "resnet50.csv" else "resnet101.csv"
@@ -392,7 +403,8 @@ def run_coo(args):
             "roofline": {"bound": "hbm", "kernel": "spmm_csr_kernel", "achieved": by_all / spmm_ms / 1e6, "peak": hbm_peak * world,
                          "unit": "GB/s", "frac": by_all / spmm_ms / 1e6 / (hbm_peak * world), "traffic": None,
                          "peak_source": peak_src,
-                         "note": "the binding roofline of this kernel is shared-memory wavefronts, not HBM (DESIGN.md 4)"}}))
+                         "note": "the binding roofline of this kernel is shared-memory wavefronts, not HBM (DESIGN.md 4)"}}),
+              file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -435,8 +447,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (sparsify.me_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_out = claim_stdout() if world > 1 else sys.stdout
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
     spfy = ge.load_package()
     tdt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
@@ -619,7 +631,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline(spfy, orc, gemms, 0 if args.dtype == "fp16" else 1)
     if args.per_layer:
         per_layer_report(spfy, layers, hbm_peak, tc_sust)
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
