@@ -532,26 +532,27 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           const uint32_t sa1 = sa0 + (resident ? rsv : (uint32_t)A_TILE_BYTES);
           const uint32_t e1 = e0 + (resident ? rse : (uint32_t)E_TILE_BYTES);
           const uint32_t nk = k_left >= (uint32_t)BK ? 4u : (k_left + 31u) / 32u;
+          // Descriptor start addresses in 16-byte units (shared memory < 256 KiB: they fit the 14-bit field and
+          // adding the per-MMA step cannot carry out of it), so every operand below is "base + constant":
+          //   A: K-major SW128, 32 logical k = 16 stored halves = 32 bytes per MMA              -> +2 per j
+          //   B: MN-major SW128 (8 k-rows per 1024 B atom): 32 k-rows = 4096 bytes per MMA      -> +256 per j
+          //      K-major SW128 (opB = T): two 64-wide k halves BN*128 bytes apart, 64 B per MMA  -> (j>>1)*1024 + (j&1)*4
+          //   metadata: TMEM columns ecol + (j & 2), instruction-descriptor selector bit j & 1 (ecol is even)
+          const uint32_t a0 = (sa0 >> 4) & 0x3fffu, a1 = (sa1 >> 4) & 0x3fffu, b0 = (sbase >> 4) & 0x3fffu;
+          const bool two = g_count > 1;
           if (leader) {
             tc_cp_128x128b(ecol0, desc_e_hi | (uint64_t)((e0 >> 4) & 0x3fffu));
-            if (g_count > 1) tc_cp_128x128b(ecol1, desc_e_hi | (uint64_t)((e1 >> 4) & 0x3fffu));
+            if (two) tc_cp_128x128b(ecol1, desc_e_hi | (uint64_t)((e1 >> 4) & 0x3fffu));
             if (!no_mma) {
 #pragma unroll
               for (uint32_t j = 0; j < 4; ++j) {
                 if (j < nk) {
-                  // A: K-major SW128, 32 logical = 16 stored halves = 32 bytes per MMA
-                  // B: MN-major SW128 (8 k-rows per 1024 B atom, 64-column groups bk*128 apart) or
-                  //    K-major SW128 (two 64-wide k halves, 64 bytes per MMA inside a row)
-                  const uint32_t sb = OPB_T ? sbase + (j >> 1) * (BN * 128) + (j & 1u) * 64u : sbase + j * (32u * 128u);
-                  const uint64_t db = desc_b_hi | (uint64_t)((sb >> 4) & 0x3fffu);
-                  const uint32_t col0 = ecol0 + j;
-                  tc_mma_sp_f16(tmem_d0, desc_a_hi | (uint64_t)(((sa0 + j * 32u) >> 4) & 0x3fffu), db, col0 & ~1u,
-                                L.idesc | (col0 & 1u), (kt | j) != 0);
-                  if (g_count > 1) {
-                    const uint32_t col1 = ecol1 + j;
-                    tc_mma_sp_f16(tmem_d1, desc_a_hi | (uint64_t)(((sa1 + j * 32u) >> 4) & 0x3fffu), db, col1 & ~1u,
-                                  L.idesc | (col1 & 1u), (kt | j) != 0);
-                  }
+                  const uint32_t bj = OPB_T ? b0 + (j >> 1) * (uint32_t)(BN * 128 / 16) + (j & 1u) * 4u : b0 + j * 256u;
+                  const uint64_t db = desc_b_hi | (uint64_t)bj;
+                  const uint32_t first = j ? 1u : kt;  // accumulate except for the very first MMA of the unit
+                  tc_mma_sp_f16(tmem_d0, desc_a_hi | (uint64_t)(a0 + 2u * j), db, ecol0 + (j & 2u), L.idesc | (j & 1u), first);
+                  if (two)
+                    tc_mma_sp_f16(tmem_d1, desc_a_hi | (uint64_t)(a1 + 2u * j), db, ecol1 + (j & 2u), L.idesc | (j & 1u), first);
                 }
               }
             }
