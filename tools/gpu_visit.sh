@@ -32,7 +32,7 @@ mg152)
   NG=${NGPUS:-2}
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29515 bench.py --csv resnet152.csv --batch 32 --gpus $NG --steps 30 --warmup 5 --no-cpu --no-prune-large > $OUT/bench_r152_mg${NG}_$TAG.json 2> $OUT/bench_r152_mg${NG}_$TAG.err; echo "mg152 rc=$?"; tail -c 300 $OUT/bench_r152_mg${NG}_$TAG.json;;
 ncu_spmm)
-  CMD="python tools/spmm_one.py 64 576 12544 32 0.95"
+  CMD="python tools/spmm_one.py 256 2304 784 32 0.9"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
 ncu_spmma)
   CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-prune-large"
