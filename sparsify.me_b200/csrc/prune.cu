@@ -570,22 +570,45 @@ prune24_tile_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint16_t* __r
   }
 }
 
+// number of non-zero halfwords (sign ignored) in a word: 0, 1 or 2
+__device__ __forceinline__ uint32_t nz_halves(uint32_t w) {
+  const uint32_t m = w & 0x7fff7fffu;
+  return ((m & 0xffffu) != 0u) + ((m >> 16) != 0u);
+}
+
+// cusparseLtSpMMAPruneCheck: flag any group of 4 with more than 2 non-zeros.  `vec`: rows are 16-byte
+// aligned and cols % 16 == 0 -> a thread checks 16 elements from two 128-bit loads; otherwise one group per
+// thread with scalar loads (ragged edges count as zeros).
 __global__ void __launch_bounds__(256)
-prune24_check_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint32_t rows, uint32_t cols,
+prune24_check_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint32_t rows, uint32_t cols, int vec,
                      int* __restrict__ invalid) {
-  const uint32_t G = (cols + 3) / 4;
-  const size_t total = (size_t)rows * G;
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
   bool bad = false;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
-    const uint32_t row = (uint32_t)(t / G), g = (uint32_t)(t - (size_t)row * G);
-    int nz = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t c = g * 4 + i;
-      if (c < cols && (in[(size_t)row * ld_in + c] & 0x7fffu)) ++nz;
+  if (vec) {
+    const uint32_t upr = cols / 16;
+    const size_t total = (size_t)rows * upr;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+      const uint32_t row = (uint32_t)(t / upr), unit = (uint32_t)(t - (size_t)row * upr);
+      const uint16_t* src = in + (size_t)row * ld_in + unit * 16u;
+      const uint4 a = ldg_nc_v4(src), b = ldg_nc_v4(src + 8);
+      bad |= nz_halves(a.x) + nz_halves(a.y) > 2u;
+      bad |= nz_halves(a.z) + nz_halves(a.w) > 2u;
+      bad |= nz_halves(b.x) + nz_halves(b.y) > 2u;
+      bad |= nz_halves(b.z) + nz_halves(b.w) > 2u;
     }
-    bad |= nz > 2;
+  } else {
+    const uint32_t G = (cols + 3) / 4;
+    const size_t total = (size_t)rows * G;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+      const uint32_t row = (uint32_t)(t / G), g = (uint32_t)(t - (size_t)row * G);
+      int nz = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t c = g * 4 + i;
+        if (c < cols && (in[(size_t)row * ld_in + c] & 0x7fffu)) ++nz;
+      }
+      bad |= nz > 2;
+    }
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(invalid, 1);
 }
@@ -841,10 +864,11 @@ int spfy_prune24_check(int dtype, const void* in, size_t ld_in, size_t rows, siz
   cudaStream_t s = (cudaStream_t)stream;
   SPFY_CUDA_OK(cudaMemsetAsync(d_invalid, 0, sizeof(int), s));
   if (rows == 0 || cols == 0) return SPFY_OK;
+  const int vec = cols % 16 == 0 && ld_in % 8 == 0 && (uintptr_t)in % 16 == 0;
   int grid = 1;
-  int rc = grid_for(rows * ceil_div(cols, 4), 256, &grid);
+  int rc = grid_for(vec ? rows * (cols / 16) : rows * ceil_div(cols, 4), 256, &grid);
   if (rc) return rc;
-  prune24_check_kernel<<<grid, 256, 0, s>>>((const uint16_t*)in, ld_in, (uint32_t)rows, (uint32_t)cols, d_invalid);
+  prune24_check_kernel<<<grid, 256, 0, s>>>((const uint16_t*)in, ld_in, (uint32_t)rows, (uint32_t)cols, vec, d_invalid);
   SPFY_LAUNCH_OK("prune24_check_kernel");
   return SPFY_OK;
 }

@@ -116,6 +116,24 @@ def test_prune24_fast_path_both_layouts(spfy, orc, cuda, rows, cols, dense, dt):
     assert np.array_equal(bits_of(a), want["dense"])
 
 
+@pytest.mark.parametrize("rows,cols", [(64, 256), (33, 148), (128, 4608)])
+def test_prune24_check_flags_violations(spfy, orc, cuda, rows, cols):
+    """cusparseLtSpMMAPruneCheck semantics (spmma.hxx:88-94): 0 for a valid 2:4 matrix, non-zero as soon as
+    one group of four keeps three values; -0 counts as zero; both the 128-bit and the scalar path."""
+    bits = rand_bits(orc, 0, (rows, cols), seed=rows + cols)
+    pruned = orc.prune24_strip(0, bits, want_mask=False)["dense"]
+    d = to_dev(pruned, 0, cuda)
+    assert spfy.prune24_check(d) == 0 and orc.prune24_check(0, pruned) == 0
+    bad = pruned.copy()
+    r, g = rows - 1, (cols // 4) - 1
+    bad[r, 4 * g: 4 * g + 3] = 0x3C00  # three ones in the last full group of the last row
+    assert orc.prune24_check(0, bad) != 0
+    assert spfy.prune24_check(to_dev(bad, 0, cuda)) != 0
+    negz = pruned.copy()
+    negz[0, :4] = [0x8000, 0x3C00, 0x8000, 0x3C00]  # two values + two negative zeros: still valid
+    assert spfy.prune24_check(to_dev(negz, 0, cuda)) == 0 and orc.prune24_check(0, negz) == 0
+
+
 def test_prune24_inplace_and_strided(spfy, orc, cuda):
     rows, cols, ld = 96, 200, 256
     bits = rand_bits(orc, 0, (rows, ld), seed=5)
