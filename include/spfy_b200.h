@@ -69,6 +69,11 @@ enum {
 };
 
 SPFY_API int spfy_version(void);
+/* Loads the library's device code on the current device (CUDA loads kernels lazily at first use, tens of
+ * milliseconds for the large ones).  Optional and idempotent; the header templates call it before they start
+ * their timers -- the counterpart of the handle / plan creation the reference keeps outside its timers
+ * (spmma.hxx:51-80). */
+SPFY_API int spfy_init(void);
 SPFY_API const char* spfy_last_error_string(void);
 /* number of kernels this library launched in this process (bench: gpu_launches) */
 SPFY_API uint64_t spfy_launch_count(void);

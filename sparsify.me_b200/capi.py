@@ -38,6 +38,7 @@ _SZ = c_size_t
 # name -> (restype, argtypes); status-returning functions have restype c_int
 SIGNATURES = {
     "spfy_version": (c_int, []),
+    "spfy_init": (c_int, []),
     "spfy_last_error_string": (c_char_p, []),
     "spfy_launch_count": (c_uint64, []),
     "spfy_convert": (c_int, [c_int, c_int, _P, _P, _SZ, _P]),

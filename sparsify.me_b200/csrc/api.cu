@@ -68,6 +68,27 @@ extern "C" {
 
 int spfy_version(void) { return 100; }  // 0.1.0
 
+int spfy_init(void) {
+  static std::atomic<int> done[64];
+  int dev = 0;
+  SPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(SPFY_E_CUDA, "device index %d out of range", dev);
+  if (done[dev].load(std::memory_order_acquire)) return SPFY_OK;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  spfy::warm_prune_kernels();
+  spfy::warm_spmma_kernels();
+  spfy::warm_spmm_kernels();
+  touch_kernel(convert_kernel<float, __half>);
+  touch_kernel(convert_kernel<float, __nv_bfloat16>);
+  touch_kernel(convert_kernel<__half, float>);
+  touch_kernel(convert_kernel<__nv_bfloat16, float>);
+  (void)cudaGetLastError();
+  done[dev].store(1, std::memory_order_release);
+  return SPFY_OK;
+}
+
 const char* spfy_last_error_string(void) { return spfy::err_buf(); }
 
 uint64_t spfy_launch_count(void) { return spfy::launch_counter().load(std::memory_order_relaxed); }

@@ -77,6 +77,17 @@ inline int device_info(DeviceInfo* out) {
   return SPFY_OK;
 }
 
+// CUDA loads device code lazily, kernel by kernel, at first use (tens of milliseconds for the big ones).
+// Each translation unit lists its kernels here so that spfy_init() can pay that once, outside anybody's timers.
+template <typename K>
+inline void touch_kernel(K kernel) {
+  cudaFuncAttributes a;
+  (void)cudaFuncGetAttributes(&a, kernel);
+}
+void warm_prune_kernels();
+void warm_spmma_kernels();
+void warm_spmm_kernels();
+
 inline size_t dtype_bytes(int dtype) {
   switch (dtype) {
     case SPFY_F16:

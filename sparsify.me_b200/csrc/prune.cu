@@ -684,6 +684,18 @@ void build_tile_patterns(uint16_t* out) {
 }  // namespace
 }  // namespace spfy
 
+void spfy::warm_prune_kernels() {
+  touch_kernel(prune_blocks_ref_kernel<uint16_t>);
+  touch_kernel(prune_blocks_ref_kernel<uint32_t>);
+  touch_kernel(prune_blocks_ref_kernel<uint64_t>);
+  touch_kernel(prune24_strip_kernel);
+  touch_kernel(prune24_fast_kernel);
+  touch_kernel(prune24_batched_kernel);
+  touch_kernel(prune24_tile_kernel<false>);
+  touch_kernel(prune24_tile_kernel<true>);
+  touch_kernel(prune24_check_kernel);
+}
+
 using namespace spfy;
 
 extern "C" {

@@ -714,6 +714,25 @@ int threshold_impl(const void* in, size_t ld, size_t rows, size_t cols, float th
 }  // namespace
 }  // namespace spfy
 
+void spfy::warm_spmm_kernels() {
+  touch_kernel(threshold_count_kernel<float>);
+  touch_kernel(threshold_count_kernel<__half>);
+  touch_kernel(threshold_count_kernel<__nv_bfloat16>);
+  touch_kernel(threshold_fill_kernel<float>);
+  touch_kernel(threshold_fill_kernel<__half>);
+  touch_kernel(threshold_fill_kernel<__nv_bfloat16>);
+  touch_kernel(exclusive_scan_kernel);
+  touch_kernel(coo_to_csr_kernel);
+  touch_kernel(csr_check_sorted_kernel);
+  touch_kernel(bell_check_sorted_kernel);
+  touch_kernel(spmm_csr_kernel<4, SPMM_CSR>);
+  touch_kernel(spmm_csr_kernel<8, SPMM_CSR>);
+  touch_kernel(spmm_csr_kernel<4, SPMM_BELL>);
+  touch_kernel(spmm_csr_kernel<8, SPMM_BELL>);
+  touch_kernel(spmm_csr_kernel<4, SPMM_BELL_PAIRS>);
+  touch_kernel(spmm_csr_kernel<8, SPMM_BELL_PAIRS>);
+}
+
 using namespace spfy;
 
 extern "C" {

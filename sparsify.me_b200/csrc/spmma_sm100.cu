@@ -947,6 +947,15 @@ struct Plan {
 }  // namespace
 }  // namespace spfy
 
+void spfy::warm_spmma_kernels() {
+  touch_kernel(spmma_kernel<false, false>);
+  touch_kernel(spmma_kernel<false, true>);
+  touch_kernel(spmma_kernel<true, false>);
+  touch_kernel(spmma_kernel<true, true>);
+  EncodeTiledFn enc;
+  (void)get_encoder(&enc);
+}
+
 using namespace spfy;
 
 extern "C" {
