@@ -4,7 +4,12 @@
 // (include/sparsify.me/spmma.hxx:21-118), but every cusparseLt call is replaced by our own
 // sm_100a kernels behind the C ABI:
 //   cusparseLtSpMMAPrune + PruneCheck + CompressedSize + Compress (:85-104) -> spfy_prune24
-//        (ONE bandwidth-bound kernel: prunes A in place and writes the compressed operand)
+//        (prunes A in place and writes the compressed operand).  The pruning algorithm is the one the
+//        reference asks the library for, CUSPARSELT_PRUNE_SPMMA_TILE (:86): best 2:4 pattern per 4x4
+//        tile, two kept per row AND per column -- bit-exact with cusparseLt 0.7.1 including ties
+//        (tests/golden/tile_*.npz).  Compile with -DSPARSIFYME_PRUNE_STRIP for the per-row
+//        top-2-of-4 variant (CUSPARSELT_PRUNE_SPMMA_STRIP, also bit-exact), which is ONE fused
+//        bandwidth-bound pass instead of two.
 //   cusparseLtMatmul (:106-114)                                             -> spfy_spmma
 //        (tcgen05.mma.sp, TMA-fed, fp32 accumulation in TMEM)
 // Operands are row-major: A m x k (ld k), B k x n (ld n), C m x n (ld n); D aliases C (:52-64).
@@ -71,7 +76,12 @@ std::vector<float> spmma(
 
   // --- prune (+ compress, fused): A is pruned in place like cusparseLtSpMMAPrune(dA, dA) ---
   t.begin(stream);
-  detail::ok(spfy_prune24(dtype, SPFY_PRUNE_STRIP_MAG, SPFY_LAYOUT_SM100, A16, k, A16, k, vals.ptr, meta.ptr,
+#ifdef SPARSIFYME_PRUNE_STRIP
+  constexpr int prune_alg = SPFY_PRUNE_STRIP_MAG;
+#else
+  constexpr int prune_alg = SPFY_PRUNE_TILE_MAG;
+#endif
+  detail::ok(spfy_prune24(dtype, prune_alg, SPFY_LAYOUT_SM100, A16, k, A16, k, vals.ptr, meta.ptr,
                           nullptr, m, k, s),
              "spmma(prune)");
   if (is_f32) detail::ok(spfy_convert(SPFY_F16, SPFY_F32, A16, dA, m * k, s), "spmma(convert A back)");

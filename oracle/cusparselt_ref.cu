@@ -13,6 +13,8 @@
 //   cusparselt_ref golden <m> <k> <n> <tile|strip> <out.bin>
 //        deterministic fp16 inputs (splitmix64 counter RNG, see gen()); dumps
 //        header{m,k,n,alg,valid}, A_in[m*k], A_pruned[m*k], B[k*n], D[m*n] (all uint16 fp16 bits)
+//   cusparselt_ref prunefile <m> <k> <tile|strip> <f16|bf16> <in.bin> <out.bin>
+//        prune a 16-bit matrix read from a file (tie-break probes, tests/golden/make_tile_probe.py)
 //   cusparselt_ref sweep <shapes.csv> <batch>
 //        weights orientation (M = n_csv, K = k_csv, N = m_csv*batch); per layer: prune / compress /
 //        matmul ms (median of 5 after warm-up, cold L2); last line: one JSON object with totals
@@ -65,12 +67,12 @@ struct Problem {
   cusparseLtMatmulAlgSelection_t alg;
   cusparseLtMatmulPlan_t plan;
   size_t ws = 0;
-  int init(cusparseLtHandle_t* handle, int64_t m, int64_t n, int64_t k) {
+  int init(cusparseLtHandle_t* handle, int64_t m, int64_t n, int64_t k, cudaDataType dt = CUDA_R_16F) {
     h = handle;
-    CKS(cusparseLtStructuredDescriptorInit(h, &dA, m, k, k, 16, CUDA_R_16F, CUSPARSE_ORDER_ROW,
+    CKS(cusparseLtStructuredDescriptorInit(h, &dA, m, k, k, 16, dt, CUSPARSE_ORDER_ROW,
                                            CUSPARSELT_SPARSITY_50_PERCENT));
-    CKS(cusparseLtDenseDescriptorInit(h, &dB, k, n, n, 16, CUDA_R_16F, CUSPARSE_ORDER_ROW));
-    CKS(cusparseLtDenseDescriptorInit(h, &dC, m, n, n, 16, CUDA_R_16F, CUSPARSE_ORDER_ROW));
+    CKS(cusparseLtDenseDescriptorInit(h, &dB, k, n, n, 16, dt, CUSPARSE_ORDER_ROW));
+    CKS(cusparseLtDenseDescriptorInit(h, &dC, m, n, n, 16, dt, CUSPARSE_ORDER_ROW));
     CKS(cusparseLtMatmulDescriptorInit(h, &mm, CUSPARSE_OPERATION_NON_TRANSPOSE,
                                        CUSPARSE_OPERATION_NON_TRANSPOSE, &dA, &dB, &dC, &dC,
                                        CUSPARSE_COMPUTE_32F));
@@ -135,6 +137,37 @@ static int golden(int argc, char** argv) {
   std::fclose(f);
   std::printf("golden %lldx%lldx%lld %s: PruneCheck=%d compressed=%zu bytes\n", (long long)m, (long long)k,
               (long long)n, argv[5], valid, csz);
+  p.destroy();
+  cusparseLtDestroy(&h);
+  return 0;
+}
+
+// prunefile <m> <k> <tile|strip> <f16|bf16> <in.bin> <out.bin>: cusparseLtSpMMAPrune (spmma.hxx:86) on the
+// 16-bit matrix stored in in.bin (m*k uint16, row-major); writes the pruned matrix.  Used by
+// tests/golden/make_tile_probe.py to learn how the closed library breaks ties between 4x4 patterns.
+static int prunefile(int argc, char** argv) {
+  if (argc != 8) return 2;
+  int64_t m = std::atoll(argv[2]), k = std::atoll(argv[3]);
+  const bool tile = std::string(argv[4]) == "tile";
+  const cudaDataType dt = std::string(argv[5]) == "bf16" ? CUDA_R_16BF : CUDA_R_16F;
+  std::vector<uint16_t> hA(m * k);
+  FILE* f = std::fopen(argv[6], "rb");
+  if (!f || std::fread(hA.data(), 2, m * k, f) != (size_t)(m * k)) return 5;
+  std::fclose(f);
+  void* A;
+  CK(cudaMalloc(&A, m * k * 2));
+  CK(cudaMemcpy(A, hA.data(), m * k * 2, cudaMemcpyHostToDevice));
+  cusparseLtHandle_t h;
+  CKS(cusparseLtInit(&h));
+  Problem p;
+  if (int rc = p.init(&h, m, 64, k, dt)) return rc;
+  CKS(cusparseLtSpMMAPrune(&h, &p.mm, A, A, tile ? CUSPARSELT_PRUNE_SPMMA_TILE : CUSPARSELT_PRUNE_SPMMA_STRIP, 0));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(hA.data(), A, m * k * 2, cudaMemcpyDeviceToHost));
+  f = std::fopen(argv[7], "wb");
+  if (!f) return 5;
+  std::fwrite(hA.data(), 2, m * k, f);
+  std::fclose(f);
   p.destroy();
   cusparseLtDestroy(&h);
   return 0;
@@ -257,6 +290,7 @@ static int sweep(int argc, char** argv) {
 int main(int argc, char** argv) {
   if (argc >= 2 && std::string(argv[1]) == "golden") return golden(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "sweep") return sweep(argc, argv);
+  if (argc >= 2 && std::string(argv[1]) == "prunefile") return prunefile(argc, argv);
   std::fprintf(stderr, "usage: %s golden m k n tile|strip out.bin | sweep shapes.csv batch\n", argv[0]);
   return 2;
 }

@@ -17,6 +17,8 @@
 // stores are coalesced along rows.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace spfy {
 namespace {
 
@@ -321,6 +323,7 @@ struct CsrSpmmParams {
   const float* B;
   float* C;
   const int* sorted;        // device flag: columns ascend inside every row
+  const int* walk;          // device flag (null = run): 1 -> the dense-walk kernel runs, 0 -> the per-non-zero one
   size_t ldb, strideB, ldc, strideC;
   uint32_t m, k, n, num_batches;
   uint32_t row_tiles, col_tiles;  // col tiles over the num_batches * n columns
@@ -353,8 +356,9 @@ bell_check_sorted_kernel(const int64_t* const* __restrict__ cols, uint32_t block
 
 __global__ void __launch_bounds__(256)
 csr_check_sorted_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, uint32_t m,
-                        int* __restrict__ sorted) {
+                        int* __restrict__ sorted, int* __restrict__ walk, uint32_t walk_nnz) {
   const uint32_t lane = threadIdx.x & 31;
+  if (walk && blockIdx.x == 0 && threadIdx.x == 0) *walk = (uint32_t)row_ptr[m] >= walk_nnz;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   bool bad = false;
   for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < m; r += warps) {
@@ -464,6 +468,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   size_t* colB = reinterpret_cast<size_t*>(smem_f + CSR_TN * CSR_PITCH_PAIRS + CSR_SCRATCH_FLOATS);  // [CSR_TN]
   size_t* colC = colB + CSR_TN;                                                              // [CSR_TN]
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (P.walk && *P.walk != 0) return;  // this A is dense enough for spmm_dense_walk_kernel (launched next)
   const bool sorted = *P.sorted != 0;
   const uint32_t nnz_total = BELL ? P.ell_cols : (uint32_t)P.row_ptr[P.m];
   // CSR: the batch elements' columns form one long column axis; blocked-ELL: tiles are per batch element
@@ -675,6 +680,303 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   }
 }
 
+// ------------------------------------------------------------------------
+// Dense walk: the same product for an A that is not sparse enough for the kernel above.  There every
+// FMA costs a shared-memory wavefront of its own (one B word per lane and FMA), which caps it at a
+// quarter of the FP32 pipe; at 50 % sparsity (BASELINE configs[2], and the reference driver's
+// blocked-ELL construction, examples/spmm.cu:47-48) it is cheaper to multiply by the zeros:
+// per k-chunk a warp scatters its RPW rows of A into a zero-filled dense strip sA[row][k] and then
+// walks k four at a time -- RPW broadcast LDS.128 of A and four LDS.128 of B feed 16 * RPW FMAs, so
+// the FP32 pipe is the limit.  A broadcast LDS.128 costs two wavefronts and a per-lane one four (ncu), i.e.
+// 16 + 2 * RPW wavefronts per 16 * RPW FMA instructions and warp: with RPW = 8 the shared-memory pipe is as
+// busy as the FP32 pipe (measured: both 44 %), so a warp owns RPW = 16 rows (64 accumulators per lane, hence
+// 8 warps per CTA).  Tile (8 warps x RPW rows) x 128 columns, same B/C conventions and sortedness handling
+// as above; B chunks of 96 k
+// are double-buffered with 16-byte cp.async (row pitch 100 floats: 16-byte aligned, and the eight
+// lanes of a quarter warp land in eight different bank groups), so the next chunk streams in under
+// the multiply.  Duplicate (row, column) entries add up (shared-memory atomics).
+// Chosen when nnz >= SPFY_SPMM_WALK_DENSITY (default 0.2) * m * k: by the host when it knows nnz (COO
+// entry, blocked-ELL), else by a device flag that lets exactly one of the two kernels run.
+// ------------------------------------------------------------------------
+constexpr int DW_KC = 96;
+constexpr int DW_PITCH = 100;
+constexpr int DW_Q = DW_PITCH / 4;
+constexpr int DW_WARPS = 8;  // 256 threads: a warp needs 16 rows x 4 columns of accumulators per lane (see above)
+constexpr int DW_THREADS = DW_WARPS * 32;
+
+__device__ __forceinline__ void cp_async_16(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const uint32_t n = valid ? 16u : 0u;  // 0: the 16 bytes are zero-filled, src is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage B[k0 .. k0+kn) x (the tile's 128 columns) as buf[column][k]; k in [kn, 96) is zero-filled
+__device__ __forceinline__ void dw_fill(float* buf, const CsrSpmmParams& P, const size_t* colB, uint32_t k0,
+                                        uint32_t kn, bool vec) {
+  if (vec && kn == (uint32_t)DW_KC) {
+#pragma unroll
+    for (int i = 0; i < CSR_TN * (DW_KC / 4) / DW_THREADS; ++i) {
+      const uint32_t p = threadIdx.x + i * DW_THREADS;
+      const uint32_t col = p / (DW_KC / 4), q = p % (DW_KC / 4);
+      const size_t off = colB[col];
+      const bool ok = off != ~(size_t)0;
+      cp_async_16(buf + col * DW_PITCH + q * 4, P.B + (ok ? off + k0 + q * 4 : 0), ok);
+    }
+  } else {
+    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * DW_KC); idx += DW_THREADS) {
+      const uint32_t col = idx / DW_KC, kk = idx % DW_KC;
+      const size_t off = colB[col];
+      buf[col * DW_PITCH + kk] = (off != ~(size_t)0 && kk < kn) ? __ldg(P.B + off + k0 + kk) : 0.f;
+    }
+  }
+}
+
+// packed fp32 pairs (sm_100 FFMA2): a three-register FFMA issues every other cycle per scheduler, so the FP32
+// peak is only reachable two FMAs per instruction
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
+// A strip of a warp: sA[k][RPW rows], the 4-row chunks of a k rotated by k / 2 so that the entries of one row
+// (what a scatter request holds) spread over eight banks instead of two; the multiply undoes the rotation
+// statically (two q per trip)
+template <int RPW>
+__device__ __forceinline__ uint32_t dw_a_slot(uint32_t kk, int r) {
+  constexpr uint32_t NCH = RPW / 4;
+  return kk * RPW + ((((uint32_t)r >> 2) + (kk >> 1)) & (NCH - 1)) * 4 + ((uint32_t)r & 3u);
+}
+
+template <int RPW, bool BELL>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+spmm_dense_walk_kernel(const __grid_constant__ CsrSpmmParams P) {
+  constexpr int TM = DW_WARPS * RPW;
+  extern __shared__ __align__(16) float smem_f[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (P.walk && *P.walk == 0) return;  // sparse enough for spmm_csr_kernel (launched just before)
+  float* const sB0 = smem_f;                                        // [2][CSR_TN][DW_PITCH]
+  float* const sA = smem_f + 2 * CSR_TN * DW_PITCH + warp * RPW * DW_PITCH;  // this warp's strip [DW_KC][RPW]
+  size_t* colB = reinterpret_cast<size_t*>(smem_f + 2 * CSR_TN * DW_PITCH + DW_WARPS * 16 * DW_PITCH);  // [CSR_TN]
+  size_t* colC = colB + CSR_TN;
+  const bool sorted = *P.sorted != 0;
+  const uint64_t ncols = BELL ? (uint64_t)P.n : (uint64_t)P.n * P.num_batches;
+  const uint32_t tiles = P.row_tiles * P.col_tiles * (BELL ? P.num_batches : 1u);
+  const uint32_t nchunks = (P.k + DW_KC - 1) / DW_KC;
+
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint32_t rt = tile % P.row_tiles, ct_all = tile / P.row_tiles;
+    const uint32_t i0 = rt * TM + warp * RPW;
+    const uint32_t batch = BELL ? ct_all / P.col_tiles : 0u;
+    const uint32_t ct = BELL ? ct_all - batch * P.col_tiles : ct_all;
+    const uint64_t j0 = (uint64_t)ct * CSR_TN;
+    float* const Cbase = BELL ? P.Cs[batch] : P.C;
+
+    __syncthreads();  // the previous tile's C stores have left shared memory
+    if (threadIdx.x < CSR_TN) {
+      const uint64_t J = j0 + threadIdx.x;
+      size_t ob = ~(size_t)0, oc = ~(size_t)0;
+      if (J < ncols) {
+        const uint32_t bt = BELL ? 0u : (ncols <= 0xffffffffull ? (uint32_t)J / P.n : (uint32_t)(J / P.n));
+        const size_t jc = (size_t)(J - (uint64_t)bt * P.n);
+        ob = (size_t)bt * P.strideB + jc * P.ldb;
+        oc = (size_t)bt * P.strideC + jc * P.ldc;
+      }
+      colB[threadIdx.x] = ob;
+      colC[threadIdx.x] = oc;
+    }
+    __syncthreads();
+
+    uint32_t cur[RPW], end[RPW];
+    int32_t pc[RPW];  // first request of every row for the coming chunk (cursor mode)
+    float pv[RPW];
+    unsigned long long acc2[RPW / 2][CSR_TJ];  // rows (2p, 2p + 1) of column j as one packed pair
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const uint32_t row = i0 + r;
+      const bool row_ok = row < P.m;
+      cur[r] = (!BELL && row_ok) ? (uint32_t)P.row_ptr[row] : 0u;
+      end[r] = row_ok ? (BELL ? P.ell_cols : (uint32_t)P.row_ptr[row + 1]) : 0u;
+    }
+#pragma unroll
+    for (int p2 = 0; p2 < RPW / 2; ++p2)
+#pragma unroll
+      for (int j = 0; j < CSR_TJ; ++j) acc2[p2][j] = 0ull;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+      csr_fetch<BELL>(P, batch, i0 + r, cur[r] + lane, sorted && cur[r] + lane < end[r], pc[r], pv[r]);
+
+    dw_fill(sB0, P, colB, 0, min((uint32_t)DW_KC, P.k), P.vec != 0);
+    cp_async_commit();
+
+    for (uint32_t ch = 0; ch < nchunks; ++ch) {
+      const uint32_t k0 = ch * DW_KC;
+      const uint32_t kn = min((uint32_t)DW_KC, P.k - k0);
+      const uint32_t k_end = k0 + kn;
+      float* const sB = sB0 + (ch & 1u) * (CSR_TN * DW_PITCH);
+      cp_async_wait_all();
+      __syncthreads();  // chunk ch has landed for everyone; everyone is done with chunk ch - 1
+      if (ch + 1 < nchunks) {
+        const uint32_t k1 = k0 + DW_KC;
+        dw_fill(sB0 + ((ch + 1) & 1u) * (CSR_TN * DW_PITCH), P, colB, k1, min((uint32_t)DW_KC, P.k - k1), P.vec != 0);
+      }
+      cp_async_commit();
+
+      // ---- densify this warp's rows of A for k in [k0, k_end) ----
+      for (uint32_t i = lane; i < (uint32_t)(RPW * DW_KC / 4); i += 32)
+        reinterpret_cast<float4*>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      if (sorted) {
+        // cursor mode.  The first request of every row was issued before the previous chunk's multiply
+        // (pc / pv); further requests of all rows that need one go out together, so a chunk exposes the
+        // global-load latency once per round, not once per row.
+        unsigned more = 0;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const int32_t c = pc[r];
+          if (c < (int32_t)k_end) atomicAdd(sA + dw_a_slot<RPW>((uint32_t)(c - (int32_t)k0), r), pv[r]);  // c >= k0: at/after the cursor
+          const unsigned cnt = __popc(__ballot_sync(0xffffffffu, c < (int32_t)k_end));
+          cur[r] += cnt;
+          if (cnt == 32u) more |= 1u << r;
+        }
+        while (more) {
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < RPW; ++r)
+            if (more >> r & 1u) csr_fetch<BELL>(P, batch, i0 + r, cur[r] + lane, cur[r] + lane < end[r], pc[r], pv[r]);
+          unsigned again = 0;
+#pragma unroll
+          for (int r = 0; r < RPW; ++r)
+            if (more >> r & 1u) {
+              const int32_t c = pc[r];
+              if (c < (int32_t)k_end) atomicAdd(sA + dw_a_slot<RPW>((uint32_t)(c - (int32_t)k0), r), pv[r]);
+              const unsigned cnt = __popc(__ballot_sync(0xffffffffu, c < (int32_t)k_end));
+              cur[r] += cnt;
+              if (cnt == 32u) again |= 1u << r;
+            }
+          more = again;
+        }
+        if (ch + 1 < nchunks) {
+#pragma unroll
+          for (int r = 0; r < RPW; ++r)
+            csr_fetch<BELL>(P, batch, i0 + r, cur[r] + lane, cur[r] + lane < end[r], pc[r], pv[r]);
+        }
+      } else {
+        // columns in no particular order: every chunk rescans the whole row
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const uint32_t beg = (!BELL && i0 + r < P.m) ? (uint32_t)P.row_ptr[i0 + r] : 0u;
+          for (uint32_t pos = beg; pos < end[r]; pos += 32u) {
+            int32_t c;
+            float v;
+            csr_fetch<BELL>(P, batch, i0 + r, pos + lane, pos + lane < end[r], c, v);
+            if (c >= (int32_t)k0 && c < (int32_t)k_end) atomicAdd(sA + dw_a_slot<RPW>((uint32_t)(c - (int32_t)k0), r), v);
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---- multiply.  One k is a rank-1 update of the warp's RPW x 128 block: RPW / 4 broadcast LDS.128 of A
+      // (four rows each) against the lane's four columns -- 2 * RPW packed FMAs (row pairs) none of which depends
+      // on another;
+      // B arrives four k at a time (one LDS.128 per column).  k in [kn, 96) is zero on both sides. ----
+      constexpr int NCH = RPW / 4;
+      const float4* a4 = reinterpret_cast<const float4*>(sA);
+      const float4* b4 = reinterpret_cast<const float4*>(sB) + lane * DW_Q;
+      const uint32_t nq = ((kn + 3u) / 4u + 1u) & ~1u;
+      for (uint32_t q2 = 0; q2 < nq; q2 += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t q = q2 + h;
+          float b[CSR_TJ][4];
+#pragma unroll
+          for (int j = 0; j < CSR_TJ; ++j) {
+            const float4 t = b4[j * 32 * DW_Q + q];
+            b[j][0] = t.x; b[j][1] = t.y; b[j][2] = t.z; b[j][3] = t.w;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int rot = (2 * h + (c >> 1)) & (NCH - 1);  // = ((4q + c) / 2) mod NCH, q2 being even
+            unsigned long long ap[RPW / 2], bb[CSR_TJ];
+#pragma unroll
+            for (int g = 0; g < NCH; ++g) {
+              const float4 t = a4[(q * 4 + c) * NCH + ((g + rot) & (NCH - 1))];
+              ap[2 * g] = pack2(t.x, t.y);
+              ap[2 * g + 1] = pack2(t.z, t.w);
+            }
+#pragma unroll
+            for (int j = 0; j < CSR_TJ; ++j) bb[j] = pack2(b[j][c], b[j][c]);
+#pragma unroll
+            for (int p2 = 0; p2 < RPW / 2; ++p2)
+#pragma unroll
+              for (int j = 0; j < CSR_TJ; ++j) fma2(acc2[p2][j], ap[p2], bb[j]);
+          }
+        }
+      }
+    }
+
+    // ---- C tile through shared memory: sC[column][row], stores run along rows ----
+    __syncthreads();
+    float* sC = smem_f;  // [CSR_TN][TM + 1] <= the two B buffers
+#pragma unroll
+    for (int p2 = 0; p2 < RPW / 2; ++p2)
+#pragma unroll
+      for (int j = 0; j < CSR_TJ; ++j) {
+        float lo, hi;
+        unpack2(acc2[p2][j], lo, hi);
+        sC[(lane + 32 * j) * (TM + 1) + warp * RPW + 2 * p2] = lo;
+        sC[(lane + 32 * j) * (TM + 1) + warp * RPW + 2 * p2 + 1] = hi;
+      }
+    __syncthreads();
+    const uint32_t rbase = rt * TM;
+#pragma unroll 4
+    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * TM); idx += DW_THREADS) {
+      const uint32_t jj = idx / TM, i = idx % TM;
+      const size_t oc = colC[jj];
+      if (oc != ~(size_t)0 && rbase + i < P.m) {
+        float* dst = Cbase + oc + rbase + i;
+        float out = P.alpha * sC[jj * (TM + 1) + i];
+        if (P.beta != 0.f) out += P.beta * *dst;
+        *dst = out;
+      }
+    }
+  }
+}
+
+template <int RPW, bool BELL>
+int launch_spmm_dense_walk(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
+  const size_t smem = ((size_t)2 * CSR_TN * DW_PITCH + (size_t)DW_WARPS * 16 * DW_PITCH) * 4 + 2 * CSR_TN * sizeof(size_t);
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  SPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63].load()) {
+    SPFY_CUDA_OK(cudaFuncSetAttribute(spmm_dense_walk_kernel<RPW, BELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev & 63].store(1);
+  }
+  const uint32_t tiles = P.row_tiles * P.col_tiles * (BELL ? P.num_batches : 1u);
+  const uint32_t grid = tiles < (uint32_t)sm_count ? tiles : (uint32_t)sm_count;
+  spmm_dense_walk_kernel<RPW, BELL><<<grid, DW_THREADS, smem, s>>>(P);
+  SPFY_LAUNCH_OK("spmm_dense_walk_kernel");
+  return SPFY_OK;
+}
+
+// fraction of non-zeros from which the dense walk is used (SPFY_SPMM_WALK_DENSITY; > 1 disables it)
+double walk_density() {
+  static const double d = [] {
+    const char* e = getenv("SPFY_SPMM_WALK_DENSITY");
+    return e ? atof(e) : 0.2;
+  }();
+  return d;
+}
+
 template <int RPW, int MODE>
 int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
   constexpr bool BELL = MODE != SPMM_CSR;
@@ -731,6 +1033,10 @@ void spfy::warm_spmm_kernels() {
   touch_kernel(spmm_csr_kernel<8, SPMM_BELL>);
   touch_kernel(spmm_csr_kernel<4, SPMM_BELL_PAIRS>);
   touch_kernel(spmm_csr_kernel<8, SPMM_BELL_PAIRS>);
+  touch_kernel(spmm_dense_walk_kernel<8, false>);
+  touch_kernel(spmm_dense_walk_kernel<16, false>);
+  touch_kernel(spmm_dense_walk_kernel<8, true>);
+  touch_kernel(spmm_dense_walk_kernel<16, true>);
 }
 
 using namespace spfy;
@@ -791,11 +1097,12 @@ int spfy_spmm_workspace_bytes(size_t m, size_t nnz, size_t* bytes) {
   return SPFY_OK;
 }
 
-int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
-                                  const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
-                                  const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
-                                  size_t strideC, float alpha, float beta, void* workspace,
-                                  size_t workspace_bytes, spfy_stream_t stream) {
+// nnz_host < 0: the host does not know nnz (CSR entry) -- both kernels are launched and a device flag lets one run
+static int spmm_csr_impl(size_t m, size_t k, size_t n, size_t num_batches,
+                         const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
+                         const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
+                         size_t strideC, float alpha, float beta, void* workspace,
+                         size_t workspace_bytes, spfy_stream_t stream, long long nnz_host) {
   if (m == 0 || n == 0 || num_batches == 0) return SPFY_OK;
   if (!row_ptr || !B || !C) return fail(SPFY_E_INVALID, "spmm_csr: null pointer");
   size_t need = 0;
@@ -813,12 +1120,16 @@ int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batch
   cudaStream_t s = (cudaStream_t)stream;
   // one device word: "columns ascend inside every row" (decides between cursor and rescan mode)
   int* d_sorted = (int*)((uint8_t*)workspace + need - 256);
+  int* d_walk = d_sorted + 1;
   SPFY_CUDA_OK(cudaMemsetAsync(d_sorted, 0xff, sizeof(int), s));
+  const double walk_nnz_f = walk_density() * (double)m * (double)k;
+  const uint32_t walk_nnz = walk_nnz_f >= 4294967295.0 ? 0xffffffffu : (uint32_t)walk_nnz_f + 1u;
   {
     int grid = 1;
     rc = elementwise_grid(m * 32, &grid);
     if (rc) return rc;
-    csr_check_sorted_kernel<<<grid, 256, 0, s>>>(row_ptr, col_idx, (uint32_t)m, d_sorted);
+    csr_check_sorted_kernel<<<grid, 256, 0, s>>>(row_ptr, col_idx, (uint32_t)m, d_sorted,
+                                                 nnz_host < 0 ? d_walk : nullptr, walk_nnz);
     SPFY_LAUNCH_OK("csr_check_sorted_kernel");
   }
   CsrSpmmParams P;
@@ -836,7 +1147,25 @@ int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batch
   P.row_tiles = (uint32_t)ceil_div(m, tall ? 128 : 64);
   if (col_tiles * P.row_tiles >= (1ull << 32)) return fail(SPFY_E_UNSUPPORTED, "spmm_csr: too many tiles");
   P.col_tiles = (uint32_t)col_tiles;
-  return tall ? launch_spmm_csr<8, SPMM_CSR>(P, di.sm_count, s) : launch_spmm_csr<4, SPMM_CSR>(P, di.sm_count, s);
+  const bool run_sparse = nnz_host < 0 || (unsigned long long)nnz_host < walk_nnz;
+  const bool run_walk = nnz_host < 0 ? walk_nnz != 0xffffffffu : !run_sparse;
+  P.walk = nnz_host < 0 && run_walk ? d_walk : nullptr;
+  if (run_sparse) {
+    rc = tall ? launch_spmm_csr<8, SPMM_CSR>(P, di.sm_count, s) : launch_spmm_csr<4, SPMM_CSR>(P, di.sm_count, s);
+    if (rc) return rc;
+  }
+  if (run_walk)
+    return tall ? launch_spmm_dense_walk<16, false>(P, di.sm_count, s) : launch_spmm_dense_walk<8, false>(P, di.sm_count, s);
+  return SPFY_OK;
+}
+
+int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
+                                  const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
+                                  const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
+                                  size_t strideC, float alpha, float beta, void* workspace,
+                                  size_t workspace_bytes, spfy_stream_t stream) {
+  return spmm_csr_impl(m, k, n, num_batches, row_ptr, col_idx, vals, B, ldb, strideB, C, ldc, strideC, alpha, beta,
+                       workspace, workspace_bytes, stream, -1);
 }
 
 int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,
@@ -850,9 +1179,8 @@ int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size
     return fail(SPFY_E_WORKSPACE, "spmm_coo: workspace %zu < %zu bytes", workspace_bytes, need);
   int rc = spfy_coo_to_csr(row_idx, nnz, m, (int32_t*)workspace, stream);
   if (rc) return rc;
-  return spfy_spmm_csr_strided_batched(m, k, n, num_batches, (const int32_t*)workspace, col_idx, vals,
-                                       B, ldb, strideB, C, ldc, strideC, alpha, beta, workspace,
-                                       workspace_bytes, stream);
+  return spmm_csr_impl(m, k, n, num_batches, (const int32_t*)workspace, col_idx, vals, B, ldb, strideB, C, ldc,
+                       strideC, alpha, beta, workspace, workspace_bytes, stream, (long long)nnz);
 }
 
 int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t block,
@@ -899,6 +1227,8 @@ int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t
     const bool tall = rows > 64;
     P.row_tiles = (uint32_t)ceil_div(rows, tall ? 128 : 64);
     P.col_tiles = (uint32_t)ceil_div(n, CSR_TN);
+    if ((double)ell_cols >= walk_density() * (double)cols)  // e.g. the reference driver's ell_cols = k / 2
+      return tall ? launch_spmm_dense_walk<16, true>(P, di.sm_count, s) : launch_spmm_dense_walk<8, true>(P, di.sm_count, s);
     if (block % 2 == 0 && ell_cols % 2 == 0 && cols % 2 == 0)
       return tall ? launch_spmm_csr<8, SPMM_BELL_PAIRS>(P, di.sm_count, s)
                   : launch_spmm_csr<4, SPMM_BELL_PAIRS>(P, di.sm_count, s);

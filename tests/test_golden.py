@@ -5,8 +5,12 @@ tests/golden/make_golden.py; nothing here needs a GPU or /root/reference).
                        (include/sparsify.me/sparsify.hxx:24-82)  -> orc_prune_blocks_ref must be bit-exact.
   cusparselt_*.npz   : the closed library behind the reference's spmma (spmma.hxx:86-113), v0.7.1
                        -> orc_prune24_strip must be bit-exact with PRUNE_SPMMA_STRIP (incl. the tie-break);
-                          orc_prune24_tile is only a documented match rate (closed source, SURVEY.md 8c);
+                          orc_prune24_tile must be bit-exact with PRUNE_SPMMA_TILE (what spmma.hxx:86 requests);
                           the fp64 GEMM oracle must agree with cusparseLtMatmul within fp16 rounding.
+  tile_*.npz         : cusparseLt 0.7.1 PRUNE_SPMMA_TILE on the probes of tests/golden/make_tile_probe.py: every
+                       face of the 4x4 pattern polytope (= every possible exact tie), every 2-level subset
+                       weighting, tie-rich small integers, and wide-range inputs whose fp32 sums round
+                       -> orc_prune24_tile must pick the library's pattern on every tile.
   cusparse_coo_*.npz, cusparse_bell_*.npz : cuSPARSE 12.x driven with the reference's call sequences for
                        batched::strided_coo (spmm.hxx:164-187, COO_ALG4) and batched::spmm (blocked-ELL,
                        :57-67,107-110).  Inputs are multiples of 1/64, so every sum is exact in fp32 and the
@@ -105,19 +109,62 @@ def test_oracle_strip_prune_is_bit_exact_with_cusparselt(orc, path):
 
 
 @pytest.mark.parametrize("path", [p for p in CUSPLT if "_tile_" in p], ids=os.path.basename)
-def test_oracle_tile_prune_match_rate(orc, path):
-    """TILE mode is closed source: we only require a valid 2:4 pattern, the same kept L1 mass per tile
-    up to ties, and a >= 98% identical-group rate (measured 98.6-99.2%)."""
+def test_oracle_tile_prune_bit_exact_with_cusparselt(orc, path):
+    """TILE mode (spmma.hxx:86) is closed source; the oracle's selection rule was fitted on the tile_*.npz probes
+    and must reproduce the library's pruned matrix bit for bit on these independent tie-rich inputs too."""
     z = np.load(path)
     m, k = int(z["m"]), int(z["k"])
     a = gen(1, m * k).view(np.uint16).reshape(m, k)
     mine, _ = orc.prune24_tile(orc.F16, a)
-    ref = z["a_pruned"]
+    assert np.array_equal(mine, z["a_pruned"])
     assert orc.prune24_check(orc.F16, mine) == 0
-    same_groups = (mine == ref).reshape(m, -1, 4).all(-1).mean()
-    assert same_groups >= 0.98
-    mag = lambda x: np.abs(orc.to_f32(orc.F16, x)).reshape(m // 4, 4, k // 4, 4).sum(axis=(1, 3))  # noqa: E731
-    assert np.all(mag(mine) >= mag(ref) - 1e-3)  # our pattern never keeps less L1 mass than the library's
+
+
+def tile_fixture(path):
+    """(dtype id name, tiles [T,16] uint16, library pattern [T] uint16) of a tile_*.npz fixture"""
+    from make_tile_probe import all_faces
+    z = np.load(path)
+    dt = str(z["dtype"])
+    if "regenerate" in z.files:
+        kind = str(z["regenerate"])
+        if kind == "subsets":
+            t = np.arange(65536, dtype=np.uint32)
+            w = 1.0 + ((t[:, None] >> np.arange(16)) & 1)
+        else:
+            fc = np.array(all_faces(), dtype=np.uint32)
+            w = 1.0 + ((fc[:, 1:2] >> np.arange(16)) & 1) + ((fc[:, 0:1] >> np.arange(16)) & 1)
+        tiles = w.astype(np.float16).view(np.uint16)
+    else:
+        tiles = z["tiles"]
+    return dt, tiles, z["pattern"]
+
+
+def tiles_as_matrix(tiles):
+    """[T,16] -> a (4 x 4T) matrix whose t-th 4x4 tile is tiles[t]"""
+    T = tiles.shape[0]
+    return np.ascontiguousarray(tiles.reshape(T, 4, 4).transpose(1, 0, 2).reshape(4, 4 * T))
+
+
+TILE_FIX = sorted(glob.glob(os.path.join(GOLD, "tile_*.npz")))
+
+
+def test_tile_fixtures_present():
+    names = {os.path.basename(p) for p in TILE_FIX}
+    assert {"tile_subsets.npz", "tile_faces.npz", "tile_small.npz", "tile_wide.npz"} <= names
+
+
+@pytest.mark.parametrize("path", TILE_FIX, ids=os.path.basename)
+def test_oracle_tile_selection_is_cusparselts(orc, path):
+    dt, tiles, pattern = tile_fixture(path)
+    assert len(tiles) == len(pattern)
+    a = tiles_as_matrix(tiles)
+    mine, mask = orc.prune24_tile(orc.F16 if dt == "f16" else orc.BF16, a)
+    T = len(tiles)
+    got = (mask.reshape(4, T, 4).transpose(1, 0, 2).reshape(T, 16).astype(np.uint32) << np.arange(16)).sum(1)
+    assert np.array_equal(got.astype(np.uint16), pattern), f"{int((got != pattern).sum())} of {T} tiles differ"
+    keep = ((pattern[:, None] >> np.arange(16)) & 1).astype(bool)
+    want = np.where(keep, tiles, 0).astype(np.uint16)
+    assert np.array_equal(mine, tiles_as_matrix(want))
 
 
 @pytest.mark.parametrize("path", CUSPLT, ids=os.path.basename)

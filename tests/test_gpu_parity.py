@@ -205,6 +205,51 @@ def test_prune24_tile_mode_matches_oracle(spfy, orc, cuda):
     assert (nz.sum(axis=3) <= 2).all() and (nz.sum(axis=1) <= 2).all()
 
 
+def _tile_fixtures():
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tile_*.npz")))
+
+
+@pytest.mark.parametrize("path", _tile_fixtures(), ids=lambda p: p.rsplit("/", 1)[-1])
+def test_prune24_tile_kernel_is_bit_exact_with_cusparselt(spfy, cuda, path):
+    """the CUDA TILE kernel against what cusparseLt 0.7.1 (the library behind spmma.hxx:86) chose on the probe
+    tiles: every exact tie set, tie-rich integers and fp32-rounding cases -- no oracle in between"""
+    from test_golden import tile_fixture, tiles_as_matrix
+    dt, tiles, pattern = tile_fixture(path)
+    code = 0 if dt == "f16" else 1
+    keep = ((pattern[:, None] >> np.arange(16)) & 1).astype(bool)
+    want = tiles_as_matrix(np.where(keep, tiles, 0).astype(np.uint16))
+    a = to_dev(tiles_as_matrix(tiles), code, cuda)
+    dense = torch.empty_like(a)
+    spfy.prune24(a, out_dense=dense, mode=spfy.PRUNE_TILE_MAG, compress=False)
+    assert np.array_equal(bits_of(dense), want)
+    # in place (the reference prunes dA into dA: spmma.hxx:86)
+    spfy.prune24(a, out_dense=a, mode=spfy.PRUNE_TILE_MAG, compress=False)
+    assert np.array_equal(bits_of(a), want)
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", [(64, 96), (130, 262), (7, 5), (4, 4), (1024, 512)])
+def test_prune24_tile_ragged_and_compress(spfy, orc, cuda, dtype, shape):
+    """ragged edges are padded with +0 like the oracle; TILE + compress equals STRIP-compress of the TILE result"""
+    bits = rand_bits(orc, dtype, shape, seed=77 + shape[0])
+    want_dense, _ = orc.prune24_tile(dtype, bits)
+    a = to_dev(bits, dtype, cuda)
+    dense = torch.empty_like(a)
+    comp = spfy.prune24(a, out_dense=dense, mode=spfy.PRUNE_TILE_MAG, layout=spfy.LAYOUT_CANONICAL)
+    assert np.array_equal(bits_of(dense), want_dense)
+    ref = orc.prune24_strip(dtype, want_dense, want_mask=False)
+    assert np.array_equal(comp.vals.cpu().numpy().view(np.uint16).reshape(shape[0], -1), ref["vals"])
+    assert np.array_equal(comp.meta.cpu().numpy().reshape(shape[0], -1), ref["meta"])
+    # column-strided views take the scalar path (rows not 8-byte aligned)
+    wide = torch.zeros(shape[0], shape[1] + 3, dtype=a.dtype, device=cuda)
+    wide[:, 1:1 + shape[1]] = a
+    view = wide[:, 1:1 + shape[1]]
+    spfy.prune24(view, out_dense=view, mode=spfy.PRUNE_TILE_MAG, compress=False)
+    assert np.array_equal(bits_of(view), want_dense)
+
+
 def test_prune24_batched_equals_single(spfy, orc, cuda):
     import ctypes
     shapes = [(64, 147), (64, 576), (128, 1152), (256, 2304), (512, 4608), (130, 260)] * 20  # > 96 items
@@ -539,6 +584,71 @@ def test_blocked_ell_spmm_multi_chunk(spfy, orc, cuda, order):
         cis.append(torch.from_numpy(ci).to(cuda))
         vas.append(torch.from_numpy(va).to(cuda))
         cs.append(torch.full((n, m), 3.0, dtype=torch.float32, device=cuda))
+    spfy.batched.spmm(cis, vas, torch.from_numpy(B).to(cuda), cs, m, n, k, block, ell_cols)
+    for c, want in zip(cs, wants):
+        assert np.allclose(c.cpu().numpy().astype(np.float64), want, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("density", [0.6, 0.05])
+@pytest.mark.parametrize("m,k,n,nb", [(96, 250, 131, 2), (200, 97, 64, 3), (64, 1000, 40, 1)])
+def test_csr_entry_picks_its_kernel_on_the_device(spfy, orc, cuda, m, k, n, nb, density):
+    """the CSR entry has no host-side nnz: both SpMM kernels are launched and a device flag lets exactly one
+    run (dense walk from 20 % non-zeros).  k is not a multiple of the 96-wide chunk (nor of 4), rows are
+    shuffled (rescan mode) and one entry is duplicated (entries of one cell add up, like cuSPARSE COO)."""
+    rng = np.random.default_rng(m * k + n)
+    w = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    ri, ci, va, _ = orc.threshold_to_coo(2, w, float(np.quantile(np.abs(w), 1.0 - density)))
+    ri, ci, va = (np.concatenate([x, x[-1:]]) for x in (ri, ci, va))  # duplicate of the last entry
+    for r in range(0, m, 3):
+        sel = np.nonzero(ri == r)[0]
+        pm = rng.permutation(sel.size)
+        ci[sel], va[sel] = ci[sel][pm], va[sel][pm]
+    B = rng.uniform(-1, 1, (nb, n, k)).astype(np.float32)
+    C0 = rng.uniform(-1, 1, (nb, n, m)).astype(np.float32)
+    want = orc.spmm_coo_batched_f64(m, k, n, nb, ri, ci, va, B, C0, 0.5, 2.0)
+    dri = torch.from_numpy(ri).to(cuda)
+    rp = spfy.coo_to_csr(dri, m)
+    dC = torch.from_numpy(C0.copy()).to(cuda)
+    spfy.batched.csr(m, k, n, nb, rp, torch.from_numpy(ci).to(cuda), torch.from_numpy(va).to(cuda),
+                     torch.from_numpy(B).to(cuda), dC, alpha=0.5, beta=2.0)
+    assert np.allclose(dC.cpu().numpy(), want, rtol=2e-4, atol=2e-4)
+
+
+def test_dense_walk_unaligned_b_and_exact_integers(spfy, orc, cuda):
+    """B columns that are not 16-byte aligned take the scalar staging path; small integers make every sum
+    exact, so the result must equal the fp64 oracle bit for bit"""
+    m, k, n, nb = 130, 333, 70, 2
+    rng = np.random.default_rng(5)
+    w = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    ri, ci, va, _ = orc.threshold_to_coo(2, w, 1.5)  # ~ 55 % non-zeros
+    B = rng.integers(-3, 4, (nb, n, k)).astype(np.float32)
+    want = orc.spmm_coo_batched_f64(m, k, n, nb, ri, ci, va, B)
+    slab = torch.zeros(nb * n * k + 1, dtype=torch.float32, device=cuda)
+    db = slab[1:]  # 4 bytes off a 16-byte boundary
+    db.copy_(torch.from_numpy(B).to(cuda).view(-1))
+    dC = torch.full((nb, n, m), 7.0, dtype=torch.float32, device=cuda)
+    spfy.batched.strided_coo(m, k, ri.size, k, n, nb, torch.from_numpy(ri).to(cuda), torch.from_numpy(ci).to(cuda),
+                             torch.from_numpy(va).to(cuda), db, dC)
+    assert np.array_equal(dC.cpu().numpy().astype(np.float64), want)
+
+
+@pytest.mark.parametrize("block", [2, 3])
+def test_blocked_ell_sparse_rows_keep_the_per_nonzero_kernel(spfy, orc, cuda, block):
+    """ell_cols = k / 8 is below the dense-walk density: the (row pair) x (column pair) walk for even blocks,
+    the per-slot walk for odd ones"""
+    m, n, k, nb = 132, 100, 24 * 8 * block, 2
+    ell_cols = k // 8
+    bcols = ell_cols // block
+    rng = np.random.default_rng(31 + block)
+    B = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    cis, vas, cs, wants = [], [], [], []
+    for b in range(nb):
+        ci = np.stack([np.sort(rng.choice(k // block, bcols, replace=False)) for _ in range(m // block)]).astype(np.int64)
+        va = rng.uniform(-1, 1, (m, ell_cols)).astype(np.float32)
+        wants.append(orc.spmm_bell_f64(m, k, n, block, ell_cols, ci, va, B))
+        cis.append(torch.from_numpy(ci).to(cuda))
+        vas.append(torch.from_numpy(va).to(cuda))
+        cs.append(torch.zeros(n, m, dtype=torch.float32, device=cuda))
     spfy.batched.spmm(cis, vas, torch.from_numpy(B).to(cuda), cs, m, n, k, block, ell_cols)
     for c, want in zip(cs, wants):
         assert np.allclose(c.cpu().numpy().astype(np.float64), want, rtol=2e-4, atol=2e-4)

@@ -21,6 +21,13 @@ examples)
 mg)
   NG=${NGPUS:-2}
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --steps 50 --warmup 5 > $OUT/bench_mg${NG}_$TAG.json 2> $OUT/bench_mg${NG}_$TAG.err; echo "mg rc=$?"; tail -c 600 $OUT/bench_mg${NG}_$TAG.json;;
+tileprobe)
+  bash tests/golden/run_tile_probe.sh > $OUT/tileprobe_$TAG.log 2>&1; echo "tile probe rc=$?"
+  python tests/golden/make_tile_probe.py fixtures $OUT/tileprobe tests/golden > $OUT/tilefix_$TAG.log 2>&1; echo "tile fixtures rc=$?"; tail -15 $OUT/tilefix_$TAG.log
+  mkdir -p $OUT/golden_tile && cp tests/golden/tile_*.npz $OUT/golden_tile/
+  cp $OUT/tileprobe/special.in.bin $OUT/tileprobe/special.tile.bin $OUT/golden_tile/ 2>/dev/null
+  rm -rf $OUT/tileprobe;;  # 60 MB of regenerable probe matrices: gpurun_out/ must stay under 64 MiB
+pcie) python tools/pcie_probe.py > $OUT/pcie_$TAG.csv 2>&1; echo "pcie rc=$?"; cat $OUT/pcie_$TAG.csv;;
 ktable) python tools/kernel_table.py --tag $TAG > $OUT/kernels_$TAG.csv 2> $OUT/kernels_$TAG.err; echo "ktable rc=$?"; tail -3 $OUT/kernels_$TAG.err;;
 ab) for r in 1 2 3; do for v in prev cur; do
       if [ $v = prev ]; then export SPFY_LIB=$PWD/gpurun_ab/lib_prev.so; else unset SPFY_LIB; fi
@@ -34,6 +41,9 @@ mg152)
 ncu_spmm)
   CMD="python tools/spmm_one.py 256 2304 784 32 0.9"
   $CMD > $OUT/spmm_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_csr -s 1 -c 1 -o $OUT/prof_spmm_$TAG -f $CMD > $OUT/ncu_spmm_$TAG.log 2>&1; echo "ncu spmm rc=$?";;
+ncu_walk)
+  CMD="python tools/spmm_one.py 256 2304 784 32 0.5"
+  $CMD > $OUT/walk_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_dense_walk -s 1 -c 1 -o $OUT/prof_walk_$TAG -f $CMD > $OUT/ncu_walk_$TAG.log 2>&1; echo "ncu walk rc=$?"; cat $OUT/walk_one_$TAG.log;;
 ncu_spmma)
   CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-prune-large"
   $CMD > $OUT/plain_$TAG.log 2>&1 &&
