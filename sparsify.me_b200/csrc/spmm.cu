@@ -23,8 +23,8 @@ namespace spfy {
 namespace {
 
 // ------------------------------------------------------------------------
-// threshold -> COO/CSR.  Pass 1: per-row counts (warp per row).  Scan.  Pass 2:
-// ordered warp compaction (ballot + popc), so entries come out sorted by (row, col).
+// threshold -> COO/CSR in one pass (chained scan over 4096-element chunks, see threshold_compact_kernel);
+// entries come out sorted by (row, col).
 // ------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ float load_as_float(const T* p);
@@ -44,89 +44,242 @@ __device__ __forceinline__ void store_from_float<__half>(__half* p, float v) { *
 template <>
 __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// One pass, chained scan.  The matrix is walked in row-major element order in chunks of 4096 elements
+// (256 threads x 4 groups of 4), one per CTA.  A CTA counts the kept elements of its chunk, publishes the count,
+// looks back over its predecessors' (aggregate | inclusive prefix) words, 32 per step, until it meets an inclusive prefix,
+// publishes its own, and writes its entries at prefix + rank: the input is read from DRAM once and the COO
+// comes out sorted by (row, column).  The kept elements wait in shared memory at their rank inside the chunk,
+// so the look-back overlaps that staging and the entries leave as full, coalesced lines.  A warp request covers 128 consecutive elements (32 lanes x 4): with
+// 16-byte aligned rows one 128-bit (fp32) or 64-bit (fp16 / bf16) load per lane.  The counts of a thread's four
+// groups travel as four bytes of one word, so one shuffle scan per warp serves all four.  row_ptr[r] is the
+// position of the first element of row r, written by whoever holds that element.
+constexpr int TC_THREADS = 256;
+constexpr int TC_GROUPS = 4;                          // groups of 4 elements per thread
+constexpr int TC_CHUNK = TC_THREADS * TC_GROUPS * 4;  // elements per chunk
+constexpr unsigned long long TC_AGGREGATE = 1ull << 62, TC_PREFIX = 2ull << 62, TC_VALUE = (1ull << 62) - 1;
+
 template <typename T>
-__global__ void __launch_bounds__(256)
-threshold_count_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols,
-                       float thr, int32_t* __restrict__ row_counts) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
-    const T* src = in + (size_t)r * ld;
-    int cnt = 0;
-    for (uint32_t c = lane; c < cols; c += 32) cnt += fabsf(load_as_float(src + c)) > thr;
+__device__ __forceinline__ void load_group(const T* p, bool vec, uint32_t n, float (&x)[4]);
+template <>
+__device__ __forceinline__ void load_group<float>(const float* p, bool vec, uint32_t n, float (&x)[4]) {
+  if (vec) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  } else {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) row_counts[r] = cnt;
+    for (int i = 0; i < 4; ++i) x[i] = (uint32_t)i < n ? __ldg(p + i) : 0.f;
+  }
+}
+template <>
+__device__ __forceinline__ void load_group<__half>(const __half* p, bool vec, uint32_t n, float (&x)[4]) {
+  if (vec) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const __half2 lo = *reinterpret_cast<const __half2*>(&v.x), hi = *reinterpret_cast<const __half2*>(&v.y);
+    x[0] = __low2float(lo); x[1] = __high2float(lo); x[2] = __low2float(hi); x[3] = __high2float(hi);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (uint32_t)i < n ? __half2float(p[i]) : 0.f;
+  }
+}
+template <>
+__device__ __forceinline__ void load_group<__nv_bfloat16>(const __nv_bfloat16* p, bool vec, uint32_t n, float (&x)[4]) {
+  if (vec) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xffff0000u);
+    x[2] = __uint_as_float(v.y << 16); x[3] = __uint_as_float(v.y & 0xffff0000u);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (uint32_t)i < n ? __bfloat162float(p[i]) : 0.f;
   }
 }
 
-// single-CTA exclusive scan of `rows` counts -> row_ptr[rows+1]; also nnz (int64)
-__global__ void __launch_bounds__(1024)
-exclusive_scan_kernel(const int32_t* __restrict__ counts, uint32_t rows,
-                      int32_t* __restrict__ row_ptr, int64_t* __restrict__ nnz_out) {
-  __shared__ int32_t warp_sums[32];
-  __shared__ int32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < rows; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const int32_t v = i < rows ? counts[i] : 0;
-    int32_t x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= (uint32_t)o) x += y;
-    }
-    if (lane == 31) warp_sums[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      int32_t s = warp_sums[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int32_t y = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= (uint32_t)o) s += y;
-      }
-      warp_sums[lane] = s;
-    }
-    __syncthreads();
-    const int32_t carry = carry_s;
-    const int32_t incl = x + (w ? warp_sums[w - 1] : 0) + carry;
-    if (i < rows) row_ptr[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    row_ptr[rows] = carry_s;
-    if (nnz_out) *nnz_out = carry_s;
-  }
+// n / cols for n < 2^31 with the host-made multiplier floor(2^(31+l) / cols) + 1, l = ceil(log2 cols)
+__device__ __forceinline__ uint32_t tc_div(uint32_t n, uint32_t cols, uint32_t mul, uint32_t shift) {
+  return cols == 1u ? n : __umulhi(n, mul) >> shift;
 }
 
+// the 16 elements of one thread for one chunk: values, and row / column of the first element of every group
 template <typename T>
-__global__ void __launch_bounds__(256)
-threshold_fill_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols, float thr,
-                      const int32_t* __restrict__ row_ptr, int32_t* __restrict__ row_idx,
-                      int32_t* __restrict__ col_idx, float* __restrict__ vals, size_t capacity) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
-    const T* src = in + (size_t)r * ld;
-    size_t out = (size_t)row_ptr[r];
-    for (uint32_t c0 = 0; c0 < cols; c0 += 32) {
-      const uint32_t c = c0 + lane;
-      const float x = c < cols ? load_as_float(src + c) : 0.f;
-      const bool keep = c < cols && fabsf(x) > thr;
-      const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const size_t pos = out + __popc(bal & ((1u << lane) - 1));
-        if (pos < capacity) {
-          row_idx[pos] = (int32_t)r;
-          col_idx[pos] = (int32_t)c;
-          vals[pos] = x;
+__device__ __forceinline__ void tc_load(const T* __restrict__ in, size_t ld, uint32_t cols, uint32_t div_mul,
+                                        uint32_t div_shift, int vec, uint32_t total, uint32_t e_chunk, uint32_t warp,
+                                        uint32_t lane, float (&x)[TC_GROUPS][4], uint32_t (&gr)[TC_GROUPS],
+                                        uint32_t (&gc)[TC_GROUPS]) {
+#pragma unroll
+  for (int g = 0; g < TC_GROUPS; ++g) {
+    // group g of this lane: elements e0 .. e0+3, 128 consecutive elements per warp and g
+    const uint32_t e0 = e_chunk + (warp * TC_GROUPS + g) * 128u + lane * 4u;
+    const uint32_t n = e0 < total ? min(4u, total - e0) : 0u;
+    uint32_t r = 0, c = 0;
+    if (n) {
+      r = tc_div(e0, cols, div_mul, div_shift);
+      c = e0 - r * cols;
+    }
+    gr[g] = r;
+    gc[g] = c;
+    if (n && vec) {
+      load_group<T>(in + (size_t)r * ld + c, true, 4, x[g]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[g][i] = 0.f;
+        if ((uint32_t)i < n) {
+          const uint32_t cc = c + i;  // may run past the row end when a group straddles rows
+          const uint32_t dr = tc_div(cc, cols, div_mul, div_shift);
+          float one[4];
+          load_group<T>(in + (size_t)(r + dr) * ld + (cc - dr * cols), false, 1, one);
+          x[g][i] = one[0];
         }
       }
-      out += __popc(bal);
+    }
+  }
+}
+
+// vec: cols % 4 == 0, ld % 4 == 0 and the base is aligned to four elements, so a group never straddles a row.
+// One chunk per CTA, chunk = block index: blocks are dispatched in index order, so every predecessor of a
+// running chunk is running or done (the assumption CUB's decoupled look-back scans make).  Measured
+// alternatives that lost: a ticket counter in front of the loads (+1 L2 round trip per CTA), and a persistent
+// grid with ticketed chunks and prefetched loads (a CTA's next chunk then gates some other CTA's current one).
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS, 6)
+threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols, uint32_t div_mul,
+                         uint32_t div_shift, float thr, int vec, uint32_t nchunks,
+                         int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, float* __restrict__ vals,
+                         size_t capacity, int32_t* __restrict__ row_ptr, int64_t* __restrict__ nnz_out,
+                         unsigned long long* __restrict__ status) {
+  __shared__ uint32_t s_warp_total[TC_THREADS / 32];
+  __shared__ float s_val[TC_CHUNK];      // the chunk's kept values in output order ...
+  __shared__ uint16_t s_elem[TC_CHUNK];  // ... and where in the chunk each one came from
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t total = rows * cols;  // < 2^31 (checked by the host)
+
+  const uint32_t chunk = blockIdx.x;
+  float x[TC_GROUPS][4];
+  uint32_t gr[TC_GROUPS], gc[TC_GROUPS];
+  tc_load<T>(in, ld, cols, div_mul, div_shift, vec, total, chunk * (uint32_t)TC_CHUNK, warp, lane, x, gr, gc);
+
+  {
+    const uint32_t e_chunk = chunk * (uint32_t)TC_CHUNK;
+    unsigned keep = 0;    // 4 bits per group
+    uint32_t packed = 0;  // kept count of group g in byte g
+#pragma unroll
+    for (int g = 0; g < TC_GROUPS; ++g) {
+      const uint32_t e0 = e_chunk + (warp * TC_GROUPS + g) * 128u + lane * 4u;
+      const uint32_t n = e0 < total ? min(4u, total - e0) : 0u;
+      unsigned k4 = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) k4 |= ((uint32_t)i < n && fabsf(x[g][i]) > thr) ? 1u << i : 0u;
+      keep |= k4 << (4 * g);
+      packed |= (uint32_t)__popc(k4) << (8 * g);
+    }
+    // inclusive scan over the lanes, all four byte lanes at once (a byte holds at most 32 * 4 = 128)
+    uint32_t incl = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += y;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);  // per-group totals of this warp
+    const uint32_t excl = incl - packed;
+    // group g of the warp precedes group g+1: bases of the four groups inside the warp
+    const uint32_t t0 = tot & 0xffu, t1 = (tot >> 8) & 0xffu, t2 = (tot >> 16) & 0xffu, t3 = tot >> 24;
+    if (lane == 0) s_warp_total[warp] = t0 + t1 + t2 + t3;
+    __syncthreads();
+    uint32_t warp_base = 0, cta_total = 0;
+#pragma unroll
+    for (int w = 0; w < TC_THREADS / 32; ++w) {
+      const uint32_t v = s_warp_total[w];
+      if ((uint32_t)w < warp) warp_base += v;
+      cta_total += v;
+    }
+    // the count goes out first: successors can already add it while this chunk is still looking back
+    if (threadIdx.x == 0 && chunk > 0) atomicExch(&status[chunk], TC_AGGREGATE | (unsigned long long)cta_total);
+
+    // ---- kept elements to shared memory at their rank inside the chunk ----
+    const uint32_t gbase[TC_GROUPS] = {0u, t0, t0 + t1, t0 + t1 + t2};
+    uint32_t first_rank[TC_GROUPS];  // chunk-local rank of the first element of every group (kept or not)
+#pragma unroll
+    for (int g = 0; g < TC_GROUPS; ++g) {
+      uint32_t rank = warp_base + gbase[g] + ((excl >> (8 * g)) & 0xffu);
+      first_rank[g] = rank;
+      const unsigned k4 = (keep >> (4 * g)) & 0xfu;
+      const uint32_t local = (warp * TC_GROUPS + g) * 128u + lane * 4u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (k4 >> i & 1u) {
+          s_val[rank] = x[g][i];
+          s_elem[rank] = (uint16_t)(local + i);
+          ++rank;
+        }
+    }
+    // ---- chained scan across chunks.  The whole CTA looks back, 256 predecessors per step (thread i reads
+    // the word of chunk - 1 - i) ----
+    uint32_t before = 0;  // kept elements in all earlier chunks (the same value in every thread)
+    for (int64_t j0 = (int64_t)chunk - 1; chunk > 0; j0 -= TC_THREADS) {
+      const int64_t j = j0 - (int64_t)threadIdx.x;
+      unsigned long long w = TC_PREFIX;  // before the first chunk: an inclusive prefix of 0
+      if (j >= 0) {
+        do {
+          w = *reinterpret_cast<volatile unsigned long long*>(&status[j]);
+        } while ((w >> 62) == 0);
+      }
+      const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+      const uint32_t upto = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 31u;  // nearest inclusive prefix
+      uint32_t v = lane <= upto ? (uint32_t)(w & TC_VALUE) : 0u;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      __syncthreads();  // s_warp_total is free (everyone has read it / the previous step's result)
+      if (lane == 0) s_warp_total[warp] = v | (has_prefix ? 0x80000000u : 0u);  // counts are < 2^31
+      __syncthreads();
+      bool done = false;
+#pragma unroll
+      for (int w8 = 0; w8 < TC_THREADS / 32; ++w8) {
+        const uint32_t t = s_warp_total[w8];
+        if (!done) before += t & 0x7fffffffu;
+        done = done || (t >> 31);
+      }
+      if (done) break;
+    }
+    if (threadIdx.x == 0) {
+      atomicExch(&status[chunk], TC_PREFIX | (unsigned long long)(before + cta_total));
+      if (chunk + 1 == nchunks) {
+        if (nnz_out) *nnz_out = (int64_t)(before + cta_total);
+        if (row_ptr) row_ptr[rows] = (int32_t)(before + cta_total);
+      }
+    }
+    __syncthreads();  // the staged entries of all warps are in place
+    const uint32_t base = before;
+
+    // ---- entries out, coalesced; (row, column) are recomputed from the element index ----
+    for (uint32_t i = threadIdx.x; i < cta_total; i += TC_THREADS) {
+      const size_t pos = (size_t)base + i;
+      if (pos < capacity) {
+        const uint32_t e = e_chunk + s_elem[i];
+        const uint32_t r = tc_div(e, cols, div_mul, div_shift);
+        row_idx[pos] = (int32_t)r;
+        col_idx[pos] = (int32_t)(e - r * cols);
+        vals[pos] = s_val[i];
+      }
+    }
+    // ---- row_ptr[r] = position of the first element of row r ----
+    if (row_ptr) {
+#pragma unroll
+      for (int g = 0; g < TC_GROUPS; ++g) {
+        const uint32_t e0 = e_chunk + (warp * TC_GROUPS + g) * 128u + lane * 4u;
+        const unsigned k4 = (keep >> (4 * g)) & 0xfu;
+        uint32_t r = gr[g], c = gc[g], rank = first_rank[g];
+        if (c != 0 && c + 4u <= cols) continue;  // no row starts inside this group
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (e0 + i < total) {
+            if (c == 0) row_ptr[r] = (int32_t)(base + rank);
+            rank += k4 >> i & 1u;
+            if (++c == cols) {
+              c = 0;
+              ++r;
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -695,8 +848,9 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
 // are double-buffered with 16-byte cp.async (row pitch 100 floats: 16-byte aligned, and the eight
 // lanes of a quarter warp land in eight different bank groups), so the next chunk streams in under
 // the multiply.  Duplicate (row, column) entries add up (shared-memory atomics).
-// Chosen when nnz >= SPFY_SPMM_WALK_DENSITY (default 0.2) * m * k: by the host when it knows nnz (COO
-// entry, blocked-ELL), else by a device flag that lets exactly one of the two kernels run.
+// Chosen for CSR / COO operands when nnz >= SPFY_SPMM_WALK_DENSITY (default 0.2) * m * k: by the host when it
+// knows nnz (COO entry), else by a device flag that lets exactly one of the two kernels run.  Blocked-ELL
+// operands stay on the per-non-zero kernel (measured: see spfy_spmm_bell_batched).
 // ------------------------------------------------------------------------
 constexpr int DW_KC = 96;
 constexpr int DW_PITCH = 100;
@@ -999,17 +1153,21 @@ int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
 template <typename T>
 int threshold_impl(const void* in, size_t ld, size_t rows, size_t cols, float thr, int32_t* row_idx,
                    int32_t* col_idx, float* vals, size_t capacity, int64_t* d_nnz,
-                   int32_t* row_ptr, int32_t* counts, cudaStream_t s) {
-  int grid = 1;
-  int rc = elementwise_grid(rows * 32, &grid);
-  if (rc) return rc;
-  threshold_count_kernel<T><<<grid, 256, 0, s>>>((const T*)in, ld, (uint32_t)rows, (uint32_t)cols, thr, counts);
-  SPFY_LAUNCH_OK("threshold_count_kernel");
-  exclusive_scan_kernel<<<1, 1024, 0, s>>>(counts, (uint32_t)rows, row_ptr, d_nnz);
-  SPFY_LAUNCH_OK("exclusive_scan_kernel");
-  threshold_fill_kernel<T><<<grid, 256, 0, s>>>((const T*)in, ld, (uint32_t)rows, (uint32_t)cols, thr,
-                                               row_ptr, row_idx, col_idx, vals, capacity);
-  SPFY_LAUNCH_OK("threshold_fill_kernel");
+                   int32_t* row_ptr, unsigned long long* status, size_t status_bytes, cudaStream_t s) {
+  const size_t chunks = ceil_div(rows * cols, (size_t)TC_CHUNK);
+  SPFY_CUDA_OK(cudaMemsetAsync(status, 0, status_bytes, s));
+  const int vec = cols % 4 == 0 && ld % 4 == 0 && (uintptr_t)in % (4 * sizeof(T)) == 0;
+  uint32_t div_mul = 0, div_shift = 0;
+  if (cols > 1) {
+    uint32_t l = 0;
+    while ((1ull << l) < cols) ++l;  // ceil(log2 cols) >= 1
+    div_mul = (uint32_t)((1ull << (31 + l)) / cols + 1);
+    div_shift = l - 1;
+  }
+  threshold_compact_kernel<T><<<(unsigned)chunks, TC_THREADS, 0, s>>>((const T*)in, ld, (uint32_t)rows, (uint32_t)cols,
+                                                                     div_mul, div_shift, thr, vec, (uint32_t)chunks, row_idx,
+                                                                     col_idx, vals, capacity, row_ptr, d_nnz, status);
+  SPFY_LAUNCH_OK("threshold_compact_kernel");
   return SPFY_OK;
 }
 
@@ -1017,13 +1175,9 @@ int threshold_impl(const void* in, size_t ld, size_t rows, size_t cols, float th
 }  // namespace spfy
 
 void spfy::warm_spmm_kernels() {
-  touch_kernel(threshold_count_kernel<float>);
-  touch_kernel(threshold_count_kernel<__half>);
-  touch_kernel(threshold_count_kernel<__nv_bfloat16>);
-  touch_kernel(threshold_fill_kernel<float>);
-  touch_kernel(threshold_fill_kernel<__half>);
-  touch_kernel(threshold_fill_kernel<__nv_bfloat16>);
-  touch_kernel(exclusive_scan_kernel);
+  touch_kernel(threshold_compact_kernel<float>);
+  touch_kernel(threshold_compact_kernel<__half>);
+  touch_kernel(threshold_compact_kernel<__nv_bfloat16>);
   touch_kernel(coo_to_csr_kernel);
   touch_kernel(csr_check_sorted_kernel);
   touch_kernel(bell_check_sorted_kernel);
@@ -1035,8 +1189,6 @@ void spfy::warm_spmm_kernels() {
   touch_kernel(spmm_csr_kernel<8, SPMM_BELL_PAIRS>);
   touch_kernel(spmm_dense_walk_kernel<8, false>);
   touch_kernel(spmm_dense_walk_kernel<16, false>);
-  touch_kernel(spmm_dense_walk_kernel<8, true>);
-  touch_kernel(spmm_dense_walk_kernel<16, true>);
 }
 
 using namespace spfy;
@@ -1044,8 +1196,8 @@ using namespace spfy;
 extern "C" {
 
 int spfy_threshold_workspace_bytes(size_t rows, size_t cols, size_t* bytes) {
-  (void)cols;
-  if (bytes) *bytes = round_up((rows + 1) * 4, 256) * 2;  // counts + row_ptr
+  // one 64-bit scan word per 4096-element chunk
+  if (bytes) *bytes = round_up(ceil_div(rows * cols, (size_t)TC_CHUNK) * 8 + 8, 256);
   return SPFY_OK;
 }
 
@@ -1063,18 +1215,18 @@ int spfy_threshold_to_coo(int dtype, const void* in, size_t ld_in, size_t rows, 
   if (!workspace || workspace_bytes < need)
     return fail(SPFY_E_WORKSPACE, "threshold_to_coo: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t s = (cudaStream_t)stream;
-  int32_t* counts = (int32_t*)workspace;
-  int32_t* row_ptr = d_row_ptr_or_null ? d_row_ptr_or_null
-                                       : (int32_t*)((uint8_t*)workspace + need / 2);
+  unsigned long long* status = (unsigned long long*)workspace;
+  int32_t* row_ptr = d_row_ptr_or_null;
+  if ((uintptr_t)workspace % 8) return fail(SPFY_E_INVALID, "threshold_to_coo: workspace must be 8-byte aligned");
   if (rows == 0 || cols == 0) {
     SPFY_CUDA_OK(cudaMemsetAsync(d_nnz, 0, sizeof(int64_t), s));
     if (d_row_ptr_or_null) SPFY_CUDA_OK(cudaMemsetAsync(d_row_ptr_or_null, 0, (rows + 1) * 4, s));
     return SPFY_OK;
   }
   switch (dtype) {
-    case SPFY_F32: return threshold_impl<float>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, counts, s);
-    case SPFY_F16: return threshold_impl<__half>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, counts, s);
-    case SPFY_BF16: return threshold_impl<__nv_bfloat16>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, counts, s);
+    case SPFY_F32: return threshold_impl<float>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, status, need, s);
+    case SPFY_F16: return threshold_impl<__half>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, status, need, s);
+    case SPFY_BF16: return threshold_impl<__nv_bfloat16>(in, ld_in, rows, cols, threshold, row_idx, col_idx, vals, capacity, d_nnz, row_ptr, status, need, s);
     default: return fail(SPFY_E_UNSUPPORTED, "threshold_to_coo: dtype %d", dtype);
   }
 }
@@ -1227,8 +1379,9 @@ int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t
     const bool tall = rows > 64;
     P.row_tiles = (uint32_t)ceil_div(rows, tall ? 128 : 64);
     P.col_tiles = (uint32_t)ceil_div(n, CSR_TN);
-    if ((double)ell_cols >= walk_density() * (double)cols)  // e.g. the reference driver's ell_cols = k / 2
-      return tall ? launch_spmm_dense_walk<16, true>(P, di.sm_count, s) : launch_spmm_dense_walk<8, true>(P, di.sm_count, s);
+    // (the dense walk loses here -- 570 vs 493 us on the reference driver's ell_cols = k / 2 construction,
+    // 79 vs 38 ms over the compare.csv table: every batch element brings its own A, so the strip is rebuilt
+    // per tile without being reused, and n is often below the 128-column tile)
     if (block % 2 == 0 && ell_cols % 2 == 0 && cols % 2 == 0)
       return tall ? launch_spmm_csr<8, SPMM_BELL_PAIRS>(P, di.sm_count, s)
                   : launch_spmm_csr<4, SPMM_BELL_PAIRS>(P, di.sm_count, s);

@@ -633,9 +633,8 @@ def test_dense_walk_unaligned_b_and_exact_integers(spfy, orc, cuda):
 
 
 @pytest.mark.parametrize("block", [2, 3])
-def test_blocked_ell_sparse_rows_keep_the_per_nonzero_kernel(spfy, orc, cuda, block):
-    """ell_cols = k / 8 is below the dense-walk density: the (row pair) x (column pair) walk for even blocks,
-    the per-slot walk for odd ones"""
+def test_blocked_ell_sparse_rows(spfy, orc, cuda, block):
+    """ell_cols = k / 8: the (row pair) x (column pair) walk for even blocks, the per-slot walk for odd ones"""
     m, n, k, nb = 132, 100, 24 * 8 * block, 2
     ell_cols = k // 8
     bcols = ell_cols // block

@@ -27,6 +27,8 @@ tileprobe)
   mkdir -p $OUT/golden_tile && cp tests/golden/tile_*.npz $OUT/golden_tile/
   cp $OUT/tileprobe/special.in.bin $OUT/tileprobe/special.tile.bin $OUT/golden_tile/ 2>/dev/null
   rm -rf $OUT/tileprobe;;  # 60 MB of regenerable probe matrices: gpurun_out/ must stay under 64 MiB
+compare) ( cd examples && ./bin/compare ../datasets/resnet50.csv > ../$OUT/compare_$TAG.csv 2> ../$OUT/compare_$TAG.err ); echo "compare rc=$?"; tail -2 $OUT/compare_$TAG.csv;;
+thr) for a in "8192 8192 0.5" "8192 8192 0.1" "16384 8192 0.5 f16" "401408 147 0.1"; do timeout 100 python tools/thr_one.py $a | tail -1; done > $OUT/thr_one_$TAG.log 2>&1; cat $OUT/thr_one_$TAG.log; timeout 120 python tools/thr_probe.py 2>&1 | grep "C ABI" | tee -a $OUT/thr_one_$TAG.log;;
 pcie) python tools/pcie_probe.py > $OUT/pcie_$TAG.csv 2>&1; echo "pcie rc=$?"; cat $OUT/pcie_$TAG.csv;;
 ktable) python tools/kernel_table.py --tag $TAG > $OUT/kernels_$TAG.csv 2> $OUT/kernels_$TAG.err; echo "ktable rc=$?"; tail -3 $OUT/kernels_$TAG.err;;
 ab) for r in 1 2 3; do for v in prev cur; do

@@ -84,8 +84,8 @@ def main():
         thr = s
         ri, ci, va, nnz = spfy.threshold_to_coo(wf, thr)
         us = timed(lambda: spfy.threshold_to_coo(wf, thr), reps=5)
-        line("A6-prep", "threshold_count/scan/fill", f"fp32 {rows}x{cols} keep |x|>{thr}", us, 2 * 4 * rows * cols + 12 * nnz,
-             f"nnz={nnz}; two passes over the input + 12 B per kept entry; includes the nnz read-back")
+        line("A6-prep", "threshold_compact_kernel", f"fp32 {rows}x{cols} keep |x|>{thr}", us, 4 * rows * cols + 12 * nnz + 4 * rows,
+             f"nnz={nnz}; input read once + 12 B per kept entry + row_ptr; python wrapper incl. the nnz read-back (kernel alone: tools/thr_one.py)")
     del wf
 
     # ---- A6 batched COO SpMM (spmm.hxx:140-193): one ResNet-34 layer per regime
@@ -99,7 +99,7 @@ def main():
         us = timed(lambda: spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, c), reps=5)
         by = 12 * nnz + 4 * K * n * nb + 4 * M * n * nb
         lds_us = nnz * n * nb / 32 / 148 / 1.9e3  # one shared-memory wavefront per 32 FMAs, 148 SMs, ~1.9 GHz
-        line("A6", "spmm_csr_kernel", f"M={M} K={K} n={n} nb={nb} sparsity {s}", us, by,
+        line("A6", "spmm_dense_walk_kernel" if nnz >= 0.2 * M * K else "spmm_csr_kernel", f"M={M} K={K} n={n} nb={nb} sparsity {s}", us, by,
              f"nnz={nnz}; {2.0*nnz*n*nb/us/1e6:.1f} TFLOP/s fp32; shared-memory-wavefront bound {lds_us:.0f} us")
         del w, b, c
 
