@@ -535,33 +535,46 @@ prune24_batched_kernel(const __grid_constant__ Prune24Batch Bt) {
 // all sums in fp32 as (row0 + row1) + (row2 + row3); candidates compared in that order, first maximum wins.
 // One thread per tile; `VEC`: four aligned 64-bit loads / stores per tile.
 // ------------------------------------------------------------------------
+// pattern of every candidate, in the order they are compared: 36 complementary (x * 6 + y), 6 same (36 + x),
+// 48 mixed (42 + 4 * group + 2 * [rows 0/1 swapped] + [rows 2/3 swapped], groups (i, j) in lexicographic order)
+__constant__ uint16_t c_tile_pattern[90] = {
+    0xc3c3, 0xa5c3, 0x96c3, 0x69c3, 0x5ac3, 0x3cc3, 0xc3a5, 0xa5a5, 0x96a5, 0x69a5, 0x5aa5, 0x3ca5, 0xc396, 0xa596, 0x9696, 0x6996, 0x5a96, 0x3c96, 0xc369, 0xa569, 0x9669, 0x6969, 0x5a69, 0x3c69, 0xc35a, 0xa55a, 0x965a, 0x695a, 0x5a5a, 0x3c5a, 0xc33c, 0xa53c, 0x963c, 0x693c, 0x5a3c, 0x3c3c, 0xcc33, 0xaa55, 0x9966, 0x6699, 0x55aa, 0x33cc, 0xac35, 0xca35, 0xac53, 0xca53, 0x9c36, 0xc936, 0x9c63, 0xc963, 0x6c39, 0xc639, 0x6c93, 0xc693, 0x5c3a, 0xc53a, 0x5ca3, 0xc5a3, 0x9a56, 0xa956, 0x9a65, 0xa965, 0x6a59, 0xa659, 0x6a95, 0xa695, 0x3a5c, 0xa35c, 0x3ac5, 0xa3c5, 0x596a, 0x956a, 0x59a6, 0x95a6, 0x396c, 0x936c, 0x39c6, 0x93c6, 0x569a, 0x659a, 0x56a9, 0x65a9, 0x369c, 0x639c, 0x36c9, 0x63c9, 0x35ac, 0x53ac, 0x35ca, 0x53ca};
+
+// returns the candidate code (index into c_tile_pattern); the selection is tracked as small integers and
+// turned into a keep mask once -- the first version carried 16-bit patterns through every compare and was
+// integer-ALU bound (600 instructions per tile)
 __device__ __forceinline__ uint32_t tile_select(const float (&m)[16]) {
   // column-pair index -> (c0, c1); the complement of pair i is pair 5 - i
   constexpr int C0[6] = {0, 0, 1, 0, 1, 2}, C1[6] = {1, 2, 2, 3, 3, 3};
-  constexpr uint32_t PM[6] = {0x3u, 0x5u, 0x6u, 0x9u, 0xAu, 0xCu};
   float rp[4][6];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int i = 0; i < 6; ++i) rp[r][i] = __fadd_rn(m[r * 4 + C0[i]], m[r * 4 + C1[i]]);
-  // complementary class
+  // complementary class: x and y maximised independently, first maximum wins
   float b01 = __fadd_rn(rp[0][0], rp[1][5]), b23 = __fadd_rn(rp[2][0], rp[3][5]);
-  uint32_t p01 = PM[0] | PM[5] << 4, p23 = PM[0] << 8 | PM[5] << 12;
+  uint32_t x01 = 0, y23 = 0;
 #pragma unroll
   for (int x = 1; x < 6; ++x) {
     const float g = __fadd_rn(rp[0][x], rp[1][5 - x]), h = __fadd_rn(rp[2][x], rp[3][5 - x]);
-    if (g > b01) b01 = g, p01 = PM[x] | PM[5 - x] << 4;
-    if (h > b23) b23 = h, p23 = PM[x] << 8 | PM[5 - x] << 12;
+    const bool pg = g > b01, ph = h > b23;
+    b01 = pg ? g : b01;
+    x01 = pg ? (uint32_t)x : x01;
+    b23 = ph ? h : b23;
+    y23 = ph ? (uint32_t)x : y23;
   }
   float best = __fadd_rn(b01, b23);
-  uint32_t pat = p01 | p23;
+  uint32_t code = x01 * 6u + y23;
   // same class
 #pragma unroll
   for (int x = 0; x < 6; ++x) {
     const float s = __fadd_rn(__fadd_rn(rp[0][x], rp[1][x]), __fadd_rn(rp[2][5 - x], rp[3][5 - x]));
-    if (s > best) best = s, pat = PM[x] | PM[x] << 4 | PM[5 - x] << 8 | PM[5 - x] << 12;
+    const bool p = s > best;
+    best = p ? s : best;
+    code = p ? (uint32_t)(36 + x) : code;
   }
   // mixed class
+  int g = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -571,13 +584,13 @@ __device__ __forceinline__ uint32_t tile_select(const float (&m)[16]) {
       const float t1 = __fadd_rn(rp[2][5 - i], rp[3][5 - j]), t2 = __fadd_rn(rp[2][5 - j], rp[3][5 - i]);
       const bool sw01 = s2 > s1, sw23 = t2 > t1;
       const float s = __fadd_rn(sw01 ? s2 : s1, sw23 ? t2 : t1);
-      if (s > best) {
-        best = s;
-        pat = (sw01 ? (PM[i] | PM[j] << 4) : (PM[j] | PM[i] << 4)) |
-              (sw23 ? (PM[5 - j] << 8 | PM[5 - i] << 12) : (PM[5 - i] << 8 | PM[5 - j] << 12));
-      }
+      const uint32_t c = (uint32_t)(42 + 4 * g) + (sw01 ? 2u : 0u) + (sw23 ? 1u : 0u);
+      const bool p = s > best;
+      best = p ? s : best;
+      code = p ? c : code;
+      ++g;
     }
-  return pat;
+  return code;
 }
 
 template <bool BF16>
@@ -609,7 +622,7 @@ prune24_tile_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint16_t* __r
         mag[i * 4 + 2] = tile_mag<BF16>(w[i].y);
         mag[i * 4 + 3] = tile_mag<BF16>(w[i].y >> 16);
       }
-      const uint32_t pat = tile_select(mag);
+      const uint32_t pat = c_tile_pattern[tile_select(mag)];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (r0 + i >= rows) break;
@@ -629,7 +642,7 @@ prune24_tile_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint16_t* __r
           v[i * 4 + j] = ok ? in[(size_t)(r0 + i) * ld_in + c0 + j] : (uint16_t)0;
           mag[i * 4 + j] = tile_mag<BF16>(v[i * 4 + j]);
         }
-      const uint32_t pat = tile_select(mag);
+      const uint32_t pat = c_tile_pattern[tile_select(mag)];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll

@@ -46,6 +46,12 @@ ncu_spmm)
 ncu_walk)
   CMD="python tools/spmm_one.py 256 2304 784 32 0.5"
   $CMD > $OUT/walk_one_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:spmm_dense_walk -s 1 -c 1 -o $OUT/prof_walk_$TAG -f $CMD > $OUT/ncu_walk_$TAG.log 2>&1; echo "ncu walk rc=$?"; cat $OUT/walk_one_$TAG.log;;
+ncu_thr)
+  CMD="python tools/thr_one.py 8192 8192 0.5"
+  ncu --set full --clock-control none --import-source on -k regex:threshold_compact -s 1 -c 1 -o $OUT/prof_thr_$TAG -f $CMD > $OUT/ncu_thr_$TAG.log 2>&1; echo "ncu thr rc=$?";;
+ncu_tile)
+  CMD="python tools/kernel_table.py --reps 1"
+  ncu --set full --clock-control none --import-source on -k regex:prune24_tile -s 1 -c 1 -o $OUT/prof_tile_$TAG -f $CMD > $OUT/ncu_tile_$TAG.log 2>&1; echo "ncu tile rc=$?";;
 ncu_spmma)
   CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-prune-large"
   $CMD > $OUT/plain_$TAG.log 2>&1 &&
