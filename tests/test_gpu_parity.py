@@ -593,7 +593,7 @@ def test_blocked_ell_spmm_multi_chunk(spfy, orc, cuda, order):
 @pytest.mark.parametrize("m,k,n,nb", [(96, 250, 131, 2), (200, 97, 64, 3), (64, 1000, 40, 1)])
 def test_csr_entry_picks_its_kernel_on_the_device(spfy, orc, cuda, m, k, n, nb, density):
     """the CSR entry has no host-side nnz: both SpMM kernels are launched and a device flag lets exactly one
-    run (dense walk from 20 % non-zeros).  k is not a multiple of the 96-wide chunk (nor of 4), rows are
+    run (dense walk from 35 % non-zeros).  k is not a multiple of the 96-wide chunk (nor of 4), rows are
     shuffled (rescan mode) and one entry is duplicated (entries of one cell add up, like cuSPARSE COO)."""
     rng = np.random.default_rng(m * k + n)
     w = rng.uniform(-1, 1, (m, k)).astype(np.float32)

@@ -99,7 +99,7 @@ def main():
         us = timed(lambda: spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, c), reps=5)
         by = 12 * nnz + 4 * K * n * nb + 4 * M * n * nb
         lds_us = nnz * n * nb / 32 / 148 / 1.9e3  # one shared-memory wavefront per 32 FMAs, 148 SMs, ~1.9 GHz
-        line("A6", "spmm_dense_walk_kernel" if nnz >= 0.2 * M * K else "spmm_csr_kernel", f"M={M} K={K} n={n} nb={nb} sparsity {s}", us, by,
+        line("A6", "spmm_dense_walk_kernel" if nnz >= 0.35 * M * K else "spmm_csr_kernel", f"M={M} K={K} n={n} nb={nb} sparsity {s}", us, by,
              f"nnz={nnz}; {2.0*nnz*n*nb/us/1e6:.1f} TFLOP/s fp32; shared-memory-wavefront bound {lds_us:.0f} us")
         del w, b, c
 
