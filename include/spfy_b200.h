@@ -185,7 +185,11 @@ SPFY_API int spfy_spmma_plan_destroy(spfy_spmma_plan_t plan);
  * dtype of `in` is F16/BF16/F32; emitted values are fp32 like the reference's
  * CUDA_R_32F COO (include/sparsify.me/spmm.hxx:165-168).
  * nnz is produced on the device (`d_nnz`, one int64) so the call never syncs.
- * `capacity` bounds the number of entries written.
+ * `capacity` bounds the number of entries written.  `d_row_ptr_or_null`
+ * (rows+1 int32), when given, receives the CSR row pointer of the same entries.
+ * One pass over the input: one memset of the workspace (8 bytes per 4096
+ * elements, size from the query; must be 8-byte aligned) + one kernel.
+ * rows * cols must be below 2^31.
  * ---------------------------------------------------------------------- */
 SPFY_API int spfy_threshold_workspace_bytes(size_t rows, size_t cols, size_t* bytes);
 SPFY_API int spfy_threshold_to_coo(int dtype, const void* in, size_t ld_in, size_t rows,
@@ -216,8 +220,11 @@ SPFY_API int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_
                                            float beta, void* workspace, size_t workspace_bytes,
                                            spfy_stream_t stream);
 /* Same product with A already in CSR (same workspace query; only its last 256 bytes are used:
- * one device word that records whether the column indices ascend inside every row, which
- * selects the kernel's one-visit-per-non-zero mode). */
+ * two device words -- whether the column indices ascend inside every row, which selects the
+ * kernels' cursor mode, and whether A holds >= 35 % non-zeros (SPFY_SPMM_WALK_DENSITY), in which
+ * case the dense-walk kernel runs instead of the per-non-zero one.  The COO entry knows nnz on the
+ * host and launches only the kernel that will run; this entry launches both and the flag lets
+ * exactly one do the work, so it never reads anything back). */
 SPFY_API int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
                                            const int32_t* row_ptr, const int32_t* col_idx,
                                            const float* vals, const float* B, size_t ldb,
