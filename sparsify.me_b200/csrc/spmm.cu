@@ -138,7 +138,9 @@ __device__ __forceinline__ void tc_load(const T* __restrict__ in, size_t ld, uin
 // One chunk per CTA, chunk = block index: blocks are dispatched in index order, so every predecessor of a
 // running chunk is running or done (the assumption CUB's decoupled look-back scans make).  Measured
 // alternatives that lost: a ticket counter in front of the loads (+1 L2 round trip per CTA), and a persistent
-// grid with ticketed chunks and prefetched loads (a CTA's next chunk then gates some other CTA's current one).
+// grid with ticketed chunks and prefetched loads, and four consecutive chunks per CTA (in both, a CTA's later
+// chunk gates some other CTA's current one: the chain turns serial, 379 us and 48 ms).  What is left is the rate
+// at which CTAs start: ~100 chunks per microsecond whatever a chunk holds (fp32, fp16 and 147-column inputs alike).
 template <typename T>
 __global__ void __launch_bounds__(TC_THREADS, 6)
 threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols, uint32_t div_mul,
@@ -203,14 +205,14 @@ threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uin
       first_rank[g] = rank;
       const unsigned k4 = (keep >> (4 * g)) & 0xfu;
       const uint32_t local = (warp * TC_GROUPS + g) * 128u + lane * 4u;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (k4 >> i & 1u) {
-          s_val[rank] = x[g][i];
-          s_elem[rank] = (uint16_t)(local + i);
-          ++rank;
-        }
+      // ranks written out instead of a running counter: four independent predicated store pairs, no branches
+      const uint32_t r1 = rank + (k4 & 1u), r2 = r1 + (k4 >> 1 & 1u), r3 = r2 + (k4 >> 2 & 1u);
+      if (k4 & 1u) { s_val[rank] = x[g][0]; s_elem[rank] = (uint16_t)local; }
+      if (k4 & 2u) { s_val[r1] = x[g][1]; s_elem[r1] = (uint16_t)(local + 1u); }
+      if (k4 & 4u) { s_val[r2] = x[g][2]; s_elem[r2] = (uint16_t)(local + 2u); }
+      if (k4 & 8u) { s_val[r3] = x[g][3]; s_elem[r3] = (uint16_t)(local + 3u); }
     }
+
     // ---- chained scan across chunks.  The whole CTA looks back, 256 predecessors per step (thread i reads
     // the word of chunk - 1 - i) ----
     uint32_t before = 0;  // kept elements in all earlier chunks (the same value in every thread)
@@ -250,15 +252,18 @@ threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uin
     const uint32_t base = before;
 
     // ---- entries out, coalesced; (row, column) are recomputed from the element index ----
-    for (uint32_t i = threadIdx.x; i < cta_total; i += TC_THREADS) {
-      const size_t pos = (size_t)base + i;
-      if (pos < capacity) {
-        const uint32_t e = e_chunk + s_elem[i];
-        const uint32_t r = tc_div(e, cols, div_mul, div_shift);
-        row_idx[pos] = (int32_t)r;
-        col_idx[pos] = (int32_t)(e - r * cols);
-        vals[pos] = s_val[i];
-      }
+    // positions are < 2^31: 32-bit compares, and entries beyond `capacity` are dropped by shortening the loop
+    const uint32_t cap32 = capacity > 0x7fffffffull ? 0x7fffffffu : (uint32_t)capacity;
+    const uint32_t n_out = base >= cap32 ? 0u : min(cta_total, cap32 - base);
+    int32_t* const ro = row_idx + base;
+    int32_t* const co = col_idx + base;
+    float* const vo = vals + base;
+    for (uint32_t i = threadIdx.x; i < n_out; i += TC_THREADS) {
+      const uint32_t e = e_chunk + s_elem[i];
+      const uint32_t r = tc_div(e, cols, div_mul, div_shift);
+      ro[i] = (int32_t)r;
+      co[i] = (int32_t)(e - r * cols);
+      vo[i] = s_val[i];
     }
     // ---- row_ptr[r] = position of the first element of row r ----
     if (row_ptr) {
