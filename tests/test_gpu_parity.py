@@ -482,6 +482,51 @@ def test_threshold_to_coo_bit_exact(spfy, orc, cuda, rows, cols, sparsity, tdt, 
     assert np.array_equal(spfy.coo_to_csr(gri, rows).cpu().numpy(), orc.coo_to_csr(ri, rows))
 
 
+@pytest.mark.parametrize("rows,cols,tdt", [(4096, 4608, torch.float32), (12544, 147, torch.float32),
+                                            (8192, 2304, torch.float16), (1, 70000, torch.float32)])
+@pytest.mark.parametrize("keep", [0.5, 0.02])
+def test_threshold_full_size_properties(spfy, cuda, rows, cols, tdt, keep):
+    """sizes the CPU oracle would take too long on: the COO must be the masked input itself (scatter it back),
+    sorted by (row, column), with nnz and row_ptr that agree with a count done by torch -- many chunks of the
+    chained scan, rows shorter and longer than a chunk, and the 16-bit / unaligned load paths"""
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    a = (torch.rand(rows, cols, device=cuda, generator=g) * 2 - 1).to(tdt)
+    thr = 1.0 - keep
+    ri, ci, va, nnz, rp = spfy.threshold_to_coo(a, thr, want_csr=True)
+    mask = a.float().abs() > thr
+    assert nnz == int(mask.sum())
+    key = ri.long() * cols + ci.long()
+    assert bool((key[1:] > key[:-1]).all())
+    back = torch.zeros(rows, cols, dtype=torch.float32, device=cuda)
+    back[ri.long(), ci.long()] = va
+    assert torch.equal(back, torch.where(mask, a.float(), torch.zeros((), device=cuda)))
+    want_rp = torch.zeros(rows + 1, dtype=torch.int64, device=cuda)
+    want_rp[1:] = mask.sum(1).cumsum(0)
+    assert torch.equal(rp.long(), want_rp)
+
+
+def test_prune24_tile_full_size_properties(spfy, cuda):
+    """TILE on the largest ResNet weight matrix (512 x 4608) and a 4096 x 4608 one: two kept per row AND per
+    column of every 4x4 tile, kept entries untouched, idempotent, and never lighter than any fixed pattern"""
+    for rows, cols in ((512, 4608), (4096, 4608)):
+        g = torch.Generator(device="cuda").manual_seed(rows)
+        a = (torch.rand(rows, cols, device=cuda, generator=g) * 2 - 1).half()
+        d1 = torch.empty_like(a)
+        spfy.prune24(a, out_dense=d1, mode=spfy.PRUNE_TILE_MAG, compress=False)
+        t = (d1 != 0).view(rows // 4, 4, cols // 4, 4)
+        assert int(t.sum(3).max()) <= 2 and int(t.sum(1).max()) <= 2
+        kept = d1 != 0
+        assert torch.equal(d1[kept], a[kept])
+        d2 = torch.empty_like(a)
+        spfy.prune24(d1, out_dense=d2, mode=spfy.PRUNE_TILE_MAG, compress=False)
+        assert torch.equal(d1, d2)
+        mass = d1.float().abs().view(rows // 4, 4, cols // 4, 4).sum((1, 3))
+        checker = torch.tensor([[1, 1, 0, 0], [0, 0, 1, 1], [1, 1, 0, 0], [0, 0, 1, 1]], device=cuda, dtype=torch.float32)
+        fixed = (a.float().abs().view(rows // 4, 4, cols // 4, 4) * checker.view(1, 4, 1, 4)).sum((1, 3))
+        assert bool((mass >= fixed - 1e-3).all())
+        assert spfy.prune24_check(d1) == 0
+
+
 @pytest.mark.parametrize("m,k,n,nb,sparsity", [(64, 147, 96, 2, 0.5), (128, 576, 200, 3, 0.9), (256, 1152, 49, 4, 0.95),
                                               (33, 70, 17, 1, 0.5), (512, 512, 64, 2, 0.9)])
 def test_batched_coo_spmm_matches_oracle(spfy, orc, cuda, m, k, n, nb, sparsity):
