@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t tc_div(uint32_t n, uint32_t cols, uint32_t m
 }
 
 // the 16 elements of one thread for one chunk: values, and row / column of the first element of every group
-template <typename T>
+template <typename T, bool FAST>
 __device__ __forceinline__ void tc_load(const T* __restrict__ in, size_t ld, uint32_t cols, uint32_t div_mul,
                                         uint32_t div_shift, int vec, uint32_t total, uint32_t e_chunk, uint32_t warp,
                                         uint32_t lane, float (&x)[TC_GROUPS][4], uint32_t (&gr)[TC_GROUPS],
@@ -108,7 +108,7 @@ __device__ __forceinline__ void tc_load(const T* __restrict__ in, size_t ld, uin
   for (int g = 0; g < TC_GROUPS; ++g) {
     // group g of this lane: elements e0 .. e0+3, 128 consecutive elements per warp and g
     const uint32_t e0 = e_chunk + (warp * TC_GROUPS + g) * 128u + lane * 4u;
-    const uint32_t n = e0 < total ? min(4u, total - e0) : 0u;
+    const uint32_t n = FAST ? 4u : (e0 < total ? min(4u, total - e0) : 0u);
     uint32_t r = 0, c = 0;
     if (n) {
       r = tc_div(e0, cols, div_mul, div_shift);
@@ -116,7 +116,7 @@ __device__ __forceinline__ void tc_load(const T* __restrict__ in, size_t ld, uin
     }
     gr[g] = r;
     gc[g] = c;
-    if (n && vec) {
+    if (FAST || (n && vec)) {
       load_group<T>(in + (size_t)r * ld + c, true, 4, x[g]);
     } else {
 #pragma unroll
@@ -141,23 +141,22 @@ __device__ __forceinline__ void tc_load(const T* __restrict__ in, size_t ld, uin
 // grid with ticketed chunks and prefetched loads, and four consecutive chunks per CTA (in both, a CTA's later
 // chunk gates some other CTA's current one: the chain turns serial, 379 us and 48 ms).  What is left is the rate
 // at which CTAs start: ~100 chunks per microsecond whatever a chunk holds (fp32, fp16 and 147-column inputs alike).
-template <typename T>
-__global__ void __launch_bounds__(TC_THREADS, 6)
-threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols, uint32_t div_mul,
-                         uint32_t div_shift, float thr, int vec, uint32_t nchunks,
-                         int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, float* __restrict__ vals,
-                         size_t capacity, int32_t* __restrict__ row_ptr, int64_t* __restrict__ nnz_out,
-                         unsigned long long* __restrict__ status) {
-  __shared__ uint32_t s_warp_total[TC_THREADS / 32];
-  __shared__ float s_val[TC_CHUNK];      // the chunk's kept values in output order ...
-  __shared__ uint16_t s_elem[TC_CHUNK];  // ... and where in the chunk each one came from
+// FAST: the chunk is complete and the vector path applies -- no per-element bounds tests (the kernel is bound
+// by instruction issue, and almost every chunk is such a chunk)
+template <typename T, bool FAST>
+__device__ __forceinline__ void tc_chunk(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols, uint32_t div_mul,
+                                         uint32_t div_shift, float thr, int vec, uint32_t nchunks,
+                                         int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx,
+                                         float* __restrict__ vals, size_t capacity, int32_t* __restrict__ row_ptr,
+                                         int64_t* __restrict__ nnz_out, unsigned long long* __restrict__ status,
+                                         uint32_t* s_warp_total, float* s_val, uint16_t* s_elem) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t total = rows * cols;  // < 2^31 (checked by the host)
 
   const uint32_t chunk = blockIdx.x;
   float x[TC_GROUPS][4];
   uint32_t gr[TC_GROUPS], gc[TC_GROUPS];
-  tc_load<T>(in, ld, cols, div_mul, div_shift, vec, total, chunk * (uint32_t)TC_CHUNK, warp, lane, x, gr, gc);
+  tc_load<T, FAST>(in, ld, cols, div_mul, div_shift, vec, total, chunk * (uint32_t)TC_CHUNK, warp, lane, x, gr, gc);
 
   {
     const uint32_t e_chunk = chunk * (uint32_t)TC_CHUNK;
@@ -166,7 +165,7 @@ threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uin
 #pragma unroll
     for (int g = 0; g < TC_GROUPS; ++g) {
       const uint32_t e0 = e_chunk + (warp * TC_GROUPS + g) * 128u + lane * 4u;
-      const uint32_t n = e0 < total ? min(4u, total - e0) : 0u;
+      const uint32_t n = FAST ? 4u : (e0 < total ? min(4u, total - e0) : 0u);
       unsigned k4 = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) k4 |= ((uint32_t)i < n && fabsf(x[g][i]) > thr) ? 1u << i : 0u;
@@ -275,7 +274,7 @@ threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uin
         if (c != 0 && c + 4u <= cols) continue;  // no row starts inside this group
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (e0 + i < total) {
+          if (FAST || e0 + i < total) {
             if (c == 0) row_ptr[r] = (int32_t)(base + rank);
             rank += k4 >> i & 1u;
             if (++c == cols) {
@@ -287,6 +286,25 @@ threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uin
       }
     }
   }
+}
+
+// vec: cols % 4 == 0, ld % 4 == 0 and the base is aligned to four elements, so a group never straddles a row
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS, 6)
+threshold_compact_kernel(const T* __restrict__ in, size_t ld, uint32_t rows, uint32_t cols, uint32_t div_mul,
+                         uint32_t div_shift, float thr, int vec, uint32_t nchunks,
+                         int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, float* __restrict__ vals,
+                         size_t capacity, int32_t* __restrict__ row_ptr, int64_t* __restrict__ nnz_out,
+                         unsigned long long* __restrict__ status) {
+  __shared__ uint32_t s_warp_total[TC_THREADS / 32];
+  __shared__ float s_val[TC_CHUNK];      // the chunk's kept values in output order ...
+  __shared__ uint16_t s_elem[TC_CHUNK];  // ... and where in the chunk each one came from
+  if (vec && ((size_t)blockIdx.x + 1) * TC_CHUNK <= (size_t)rows * cols)
+    tc_chunk<T, true>(in, ld, rows, cols, div_mul, div_shift, thr, vec, nchunks, row_idx, col_idx, vals, capacity, row_ptr,
+                      nnz_out, status, s_warp_total, s_val, s_elem);
+  else
+    tc_chunk<T, false>(in, ld, rows, cols, div_mul, div_shift, thr, vec, nchunks, row_idx, col_idx, vals, capacity, row_ptr,
+                       nnz_out, status, s_warp_total, s_val, s_elem);
 }
 
 __global__ void __launch_bounds__(256)
