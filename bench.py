@@ -621,7 +621,7 @@ def main():
         e2e_ms = float(te.item()) / args.e2e_steps
         e2e = {"value": flops_step * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
-               "api": "spmma(A, B, C, m, n, k, b) per layer: pinned H2D of A and B, prune in place + compress + "
+               "api": "spmma(A, B, C, m, n, k, b) per layer: pinned H2D of A and B, TILE prune in place (as spmma.hxx:86) + compress + "
                       "tcgen05 matmul, D2H of C; copy-in / compute / copy-out on three streams"}
         # restore the resident weights for anything that follows
         del hostbuf

@@ -198,11 +198,13 @@ def spmma_compressed(comp, b, c=None, out=None, alpha=1.0, beta=0.0, op_b=capi.O
 
 
 def spmma(a, b, c, m, n, k, batch_size=1, transpose_a=capi.OP_N, transpose_b=capi.OP_N, alpha=1.0,
-          beta=0.0):
+          beta=0.0, prune_mode=capi.PRUNE_TILE_MAG):
     """sparsifyme::spmma (spmma.hxx:21-118): prune A in place (2:4 magnitude), compress, multiply
-    into C (D aliases C, :52-53).  Returns [prune_ms, compress_ms, mul_ms] like :117.  Our prune and
-    compress are one fused kernel, so it is timed under `prune` and `compress` only times the
-    (empty) remainder; batch_size is accepted and unused exactly like the reference (:29)."""
+    into C (D aliases C, :52-53).  Returns [prune_ms, compress_ms, mul_ms] like :117.  Like the header
+    (include/sparsify.me/spmma.hxx) it prunes with TILE_MAG, the algorithm the reference requests from
+    cusparseLt (:86); prune_mode=PRUNE_STRIP_MAG is the header's -DSPARSIFYME_PRUNE_STRIP.  Prune and
+    compress are timed together under `prune`; `compress` only times the (empty) remainder;
+    batch_size is accepted and unused exactly like the reference (:29)."""
     del batch_size
     if transpose_a != capi.OP_N:
         raise capi.SpfyError(capi.E_UNSUPPORTED, "spmma", "transpose_a is not supported")
@@ -217,7 +219,7 @@ def spmma(a, b, c, m, n, k, batch_size=1, transpose_a=capi.OP_N, transpose_b=cap
     comp = Compressed24(torch.empty(vb, dtype=torch.uint8, device=a.device),
                         torch.empty(mb, dtype=torch.uint8, device=a.device), m, k, a.dtype,
                         capi.LAYOUT_SM100)
-    prune24(a2, inplace=True, out=comp)
+    prune24(a2, inplace=True, out=comp, mode=prune_mode)
     prune_ms = t.end()
     t.begin()
     compress_ms = t.end()

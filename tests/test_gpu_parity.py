@@ -437,15 +437,18 @@ def test_spmma_reference_style_call(spfy, orc, cuda):
     m, n, k = 128, 256, 512
     a_bits = rand_bits(orc, 0, (m, k), seed=8)
     b_bits = rand_bits(orc, 0, (k, n), seed=9)
-    a = to_dev(a_bits, 0, cuda).reshape(-1)
     b = to_dev(b_bits, 0, cuda).reshape(-1)
-    c = torch.zeros(m * n, dtype=torch.float16, device=cuda)
-    times = spfy.spmma(a, b, c, m, n, k, 1)
-    assert len(times) == 3 and all(t >= 0 for t in times)
-    pr = orc.prune24_strip(0, a_bits, want_mask=False)
-    assert np.array_equal(bits_of(a).reshape(m, k), pr["dense"])  # A pruned in place (spmma.hxx:86)
-    want = orc.spmma_f64(0, pr["dense"], b_bits)
-    assert rel_err(c.view(m, n).float().cpu().numpy().astype(np.float64), want) <= REL_TOL
+    tile_dense, _ = orc.prune24_tile(0, a_bits)
+    strip_dense = orc.prune24_strip(0, a_bits, want_mask=False)["dense"]
+    # default: TILE, what the reference asks cusparseLt for (spmma.hxx:86); then the per-row STRIP variant
+    for kwargs, pruned in (({}, tile_dense), ({"prune_mode": spfy.PRUNE_STRIP_MAG}, strip_dense)):
+        a = to_dev(a_bits, 0, cuda).reshape(-1)
+        c = torch.zeros(m * n, dtype=torch.float16, device=cuda)
+        times = spfy.spmma(a, b, c, m, n, k, 1, **kwargs)
+        assert len(times) == 3 and all(t >= 0 for t in times)
+        assert np.array_equal(bits_of(a).reshape(m, k), pruned)  # A pruned in place
+        want = orc.spmma_f64(0, pruned, b_bits)
+        assert rel_err(c.view(m, n).float().cpu().numpy().astype(np.float64), want) <= REL_TOL
 
 
 def test_spmma_rejects_bad_arguments(spfy, cuda):
