@@ -12,6 +12,8 @@
 // count.  See DESIGN.md for the algorithmic byte counts.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace spfy {
 namespace {
 
@@ -653,6 +655,72 @@ prune24_tile_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint16_t* __r
   }
 }
 
+// TILE prune + compress in ONE pass (what sparsifyme::spmma runs): the thread that chose a tile's pattern also
+// emits, per row, the two kept values and the index nibble exactly as prune24_unit would for the pruned row
+// (same top2of4 on the pruned words, so zero-valued survivors resolve to the same indices), in either layout.
+// Needs cols % 16 == 0 and 8-byte aligned rows: the four lanes of a 16-column unit are then neighbours
+// (quad shuffles assemble the unit's metadata word) and a warp's 32 tiles are one 128-byte line of a value
+// tile.  The iteration domain is the padded one of the layout (SM100: 128-row x 128-column tiles; padding is
+// read as +0 and comes out as zeros with the neutral nibble 0x4).
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
+  const uint32_t dom_cols = P.tile_order ? P.k_tiles * 128u : P.cols;
+  const uint32_t tiles_c = dom_cols / 4u, tiles_r = (P.dom_rows + 3u) / 4u;
+  const size_t total = (size_t)tiles_r * tiles_c;  // tiles_c % 4 == 0: a quad of lanes never straddles a tile row
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += nthreads) {
+    const size_t t = base + lane;
+    const bool active = t < total;
+    const uint32_t tr = active ? (uint32_t)(t / tiles_c) : 0u, tc = active ? (uint32_t)(t - (size_t)tr * tiles_c) : 0u;
+    const uint32_t r0 = tr * 4u, c0 = tc * 4u;
+    const bool col_ok = active && c0 < P.cols;
+    uint2 w[4];
+    float mag[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      w[i] = (col_ok && r0 + i < P.rows) ? *reinterpret_cast<const uint2*>(P.in + (size_t)(r0 + i) * P.ld_in + c0)
+                                         : make_uint2(0u, 0u);
+      mag[i * 4 + 0] = tile_mag<BF16>(w[i].x);
+      mag[i * 4 + 1] = tile_mag<BF16>(w[i].x >> 16);
+      mag[i * 4 + 2] = tile_mag<BF16>(w[i].y);
+      mag[i * 4 + 3] = tile_mag<BF16>(w[i].y >> 16);
+    }
+    const uint32_t pat = c_tile_pattern[tile_select(mag)];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t row = r0 + i;
+      const uint32_t k = pat >> (i * 4);
+      const uint32_t lo = w[i].x & ((k & 1u ? 0xffffu : 0u) | (k & 2u ? 0xffff0000u : 0u));
+      const uint32_t hi = w[i].y & ((k & 4u ? 0xffffu : 0u) | (k & 8u ? 0xffff0000u : 0u));
+      if (P.out_dense && col_ok && row < P.rows)
+        *reinterpret_cast<uint2*>(P.out_dense + (size_t)row * P.ld_out + c0) = make_uint2(lo, hi);
+      uint32_t i0, i1;
+      top2of4(lo, hi, i0, i1);
+      const uint32_t cv = __byte_perm(lo, hi, (i0 + (i1 << 8)) * 0x22u + 0x1010u);
+      // the unit's four nibbles meet in the lane of its first group
+      uint32_t nibs = (i0 | i1 << 2) << (4u * (lane & 3u));
+      nibs |= __shfl_xor_sync(0xffffffffu, nibs, 1);
+      nibs |= __shfl_xor_sync(0xffffffffu, nibs, 2);
+      if (!active || row >= P.dom_rows) continue;
+      if (P.layout == SPFY_LAYOUT_SM100) {
+        const uint32_t r = row & 127u, q = (c0 & 127u) >> 4;
+        const size_t tile = (size_t)(c0 >> 7) * P.m_tiles + (row >> 7);
+        if (P.comp_vals)
+          *reinterpret_cast<uint32_t*>(P.comp_vals + tile * 16384 + r * 128 + ((q ^ (r & 7u)) << 4) + (lane & 3u) * 4u) = cv;
+        if (P.meta && (lane & 3u) == 0u)
+          *reinterpret_cast<uint16_t*>(P.meta + tile * 2048 + (r >> 4) * 256 + (q & 1u) * 128 + (r & 7u) * 16 +
+                                       (q >> 1) * 4 + ((r >> 3) & 1u) * 2) = (uint16_t)nibs;
+      } else {
+        if (P.comp_vals) reinterpret_cast<uint32_t*>(P.comp_vals)[(size_t)row * P.G + tc] = cv;
+        if (P.meta && (lane & 3u) == 0u)
+          *reinterpret_cast<uint16_t*>(P.meta + (size_t)row * P.mb + tc / 2u) = (uint16_t)nibs;
+      }
+    }
+  }
+}
+
 // number of non-zero halfwords (sign ignored) in a word: 0, 1 or 2
 __device__ __forceinline__ uint32_t nz_halves(uint32_t w) {
   const uint32_t m = w & 0x7fff7fffu;
@@ -760,6 +828,8 @@ void spfy::warm_prune_kernels() {
   touch_kernel(prune24_tile_kernel<false, true>);
   touch_kernel(prune24_tile_kernel<true, false>);
   touch_kernel(prune24_tile_kernel<true, true>);
+  touch_kernel(prune24_tile_fused_kernel<false>);
+  touch_kernel(prune24_tile_fused_kernel<true>);
   touch_kernel(prune24_check_kernel);
 }
 
@@ -848,11 +918,32 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
   if (mode == SPFY_PRUNE_TILE_MAG) {
     if (!out_dense)
       return fail(SPFY_E_INVALID, "prune24: TILE_MAG needs out_dense (it may alias the input)");
+    const bool vec = cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && (uintptr_t)src % 8 == 0 &&
+                     (uintptr_t)out_dense % 8 == 0;
+    // One pass for weight-sized matrices: the fused kernel saves a launch (every ResNet layer is launch-bound,
+    // <= 2.4 M elements) but it is issue-bound and costs 526 us on 16384 x 16384 where the two passes take 445
+    static const size_t fused_max = [] {
+      const char* e = getenv("SPFY_TILE_FUSED_MAX");
+      return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)8 << 20;
+    }();
+    if ((comp_vals || meta) && !mask && vec && cols % 16 == 0 && (uintptr_t)meta % 2 == 0 && (uintptr_t)comp_vals % 4 == 0 &&
+        rows * cols <= fused_max) {
+      // one pass: prune + compress (see prune24_tile_fused_kernel)
+      Prune24Params P;
+      int rcf = fill_prune24(&P, layout, src, ld_in, out_dense, ld_out, comp_vals, meta, nullptr, rows, cols);
+      if (rcf) return rcf;
+      const size_t dom_cols = P.tile_order ? (size_t)P.k_tiles * 128 : cols;
+      int gridf = 1;
+      rcf = grid_for(ceil_div((size_t)P.dom_rows, 4) * (dom_cols / 4), 256, &gridf);
+      if (rcf) return rcf;
+      if (dtype == SPFY_BF16) prune24_tile_fused_kernel<true><<<gridf, 256, 0, s>>>(P);
+      else prune24_tile_fused_kernel<false><<<gridf, 256, 0, s>>>(P);
+      SPFY_LAUNCH_OK("prune24_tile_fused_kernel");
+      return SPFY_OK;
+    }
     int grid = 1;
     int rc = grid_for(ceil_div(rows, 4) * ceil_div(cols, 4), 256, &grid);
     if (rc) return rc;
-    const bool vec = cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && (uintptr_t)src % 8 == 0 &&
-                     (uintptr_t)out_dense % 8 == 0;
     const uint32_t r32 = (uint32_t)rows, c32 = (uint32_t)cols;
     uint16_t* od = (uint16_t*)out_dense;
     if (dtype == SPFY_BF16) {

@@ -250,6 +250,34 @@ def test_prune24_tile_ragged_and_compress(spfy, orc, cuda, dtype, shape):
     assert np.array_equal(bits_of(view), want_dense)
 
 
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", [(128, 128), (130, 256), (64, 576), (512, 4608), (6, 16), (256, 2304)])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_prune24_tile_fused_compress_both_layouts(spfy, orc, cuda, dtype, shape, inplace):
+    """cols % 16 == 0 and a weight-sized matrix: TILE prune + compress is ONE kernel (prune24_tile_fused_kernel).  Its outputs must be those of
+    the STRIP compressor applied to the TILE-pruned matrix, in the canonical and in the SM100 (GEMM operand) layout,
+    padding tiles included, in place or not"""
+    rows, cols = shape
+    bits = rand_bits(orc, dtype, shape, seed=5 * rows + cols)
+    bits[::5, : cols // 2] &= 0xFC00  # ties, and zeros that survive the prune
+    want_dense, _ = orc.prune24_tile(dtype, bits)
+    ref = orc.prune24_strip(dtype, want_dense, want_mask=False)
+    ov, om = orc.pack_sm100(ref["vals"], ref["meta"], rows, cols)
+    for layout in (spfy.LAYOUT_SM100, spfy.LAYOUT_CANONICAL):
+        a = to_dev(bits, dtype, cuda)
+        dense = a if inplace else torch.empty_like(a)
+        before = spfy.launch_count()
+        comp = spfy.prune24(a, out_dense=dense, mode=spfy.PRUNE_TILE_MAG, layout=layout)
+        assert spfy.launch_count() - before == 1
+        assert np.array_equal(bits_of(dense), want_dense)
+        if layout == spfy.LAYOUT_SM100:
+            assert np.array_equal(comp.vals.cpu().numpy(), ov)
+            assert np.array_equal(comp.meta.cpu().numpy(), om)
+        else:
+            assert np.array_equal(comp.vals.cpu().numpy().view(np.uint16).reshape(rows, -1), ref["vals"])
+            assert np.array_equal(comp.meta.cpu().numpy().reshape(rows, -1), ref["meta"])
+
+
 def test_prune24_batched_equals_single(spfy, orc, cuda):
     import ctypes
     shapes = [(64, 147), (64, 576), (128, 1152), (256, 2304), (512, 4608), (130, 260)] * 20  # > 96 items

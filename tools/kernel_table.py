@@ -76,6 +76,17 @@ def main():
     line("A2/A3", "prune24_tile_kernel + prune24_fast_kernel", f"fp16 {rows}x{cols} TILE -> sm100", us,
          spfy.shapes.prune24_bytes(rows, cols), "what sparsifyme::spmma runs: two passes, algorithmic bytes of one")
     del a, dense, dt, comp
+    rows_w, cols_w = 512, 4608  # the largest ResNet weight matrix: TILE prune + compress is one fused launch
+    aw = (torch.rand(rows_w, cols_w, device=dev) * 2 - 1).half()
+    dw = torch.empty_like(aw)
+    cw = spfy.alloc_compressed(torch.float16, rows_w, cols_w, dev, spfy.LAYOUT_SM100)
+    us = timed(lambda: spfy.prune24(aw, out_dense=dw, mode=spfy.PRUNE_TILE_MAG, out=cw))
+    line("A2/A3", "prune24_tile_fused_kernel", f"fp16 {rows_w}x{cols_w} TILE -> sm100", us, spfy.shapes.prune24_bytes(rows_w, cols_w) + rows_w * cols_w * 2,
+         "one launch: pruned dense + compressed values + metadata (launch-bound at this size)")
+    us = timed(lambda: spfy.prune24(aw, out_dense=dw, out=cw))
+    line("A2/A3", "prune24_fast_kernel", f"fp16 {rows_w}x{cols_w} STRIP -> sm100", us, spfy.shapes.prune24_bytes(rows_w, cols_w) + rows_w * cols_w * 2,
+         "same outputs with the per-row selection")
+    del aw, dw, cw
 
     # ---- threshold -> COO (the <todo> of sparsify.hxx:58-59)
     rows, cols = 8192, 8192
