@@ -157,3 +157,56 @@ def test_gemm_oracles_against_numpy(orc):
             dense[i, ci2[i // block, e // block] * block + e % block] += vals[i, e]
     Bf = rng.uniform(-1, 1, (n, k)).astype(np.float32)
     assert np.allclose(orc.spmm_bell_f64(m, k, n, block, ell_cols, ci2, vals, Bf), (dense @ Bf.T.astype(np.float64)).T, atol=1e-12)
+
+
+# ------------------------------------------------------------------ TILE selection (cusparseLt's, see test_golden.py)
+def _all_tile_patterns():
+    import itertools
+    pr = [0x3, 0x5, 0x6, 0x9, 0xA, 0xC]
+    return np.array([p[0] | p[1] << 4 | p[2] << 8 | p[3] << 12 for p in itertools.product(pr, repeat=4)
+                     if all(sum((x >> c) & 1 for x in p) == 2 for c in range(4))], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("vals,mask", [
+    # all equal: the first complementary candidate, rows (01, 23, 01, 23)
+    (np.ones((4, 4)), [[1, 1, 0, 0], [0, 0, 1, 1], [1, 1, 0, 0], [0, 0, 1, 1]]),
+    # a heavy diagonal plus its cyclic neighbour is the unique optimum
+    ([[9, 8, 0, 0], [0, 9, 8, 0], [0, 0, 9, 8], [8, 0, 0, 9]], [[1, 1, 0, 0], [0, 1, 1, 0], [0, 0, 1, 1], [1, 0, 0, 1]]),
+    # rows 0/1 weigh 60000: the 1/1024 that separates the choices for rows 2/3 vanishes in an fp32 total (ulp 1/128
+    # at 1.2e5), but x and y of the complementary class are maximised independently, so it still decides: columns
+    # (1, 2) for row 2 -- with totals the first pattern, columns (0, 1), would have won the tie
+    ([[60000, 60000, 0, 0], [0, 0, 60000, 60000], [1, 1 + 1 / 1024, 1 + 1 / 1024, 1], [1, 1, 1, 1]],
+     [[1, 1, 0, 0], [0, 0, 1, 1], [0, 1, 1, 0], [1, 0, 0, 1]]),
+])
+def test_tile_selection_known_answers(orc, vals, mask):
+    a = orc.from_f32(orc.F16, np.array(vals, dtype=np.float32))
+    dense, m = orc.prune24_tile(orc.F16, a)
+    assert np.array_equal(m.astype(int), np.array(mask))
+    assert np.array_equal(dense, np.where(np.array(mask, bool), a, 0))
+
+
+def test_tile_selection_properties(orc):
+    """on inputs whose sums are exact (small integers): the kept pattern is one of the 90 valid ones, no valid pattern
+    is heavier, signs and a power-of-two scale do not matter, and pruning a pruned tile changes nothing"""
+    rng = np.random.default_rng(3)
+    pats = _all_tile_patterns()
+    pm = ((pats[:, None] >> np.arange(16)) & 1).astype(np.float64)
+    T = 4000
+    vals = rng.integers(-6, 7, size=(T, 4, 4)).astype(np.float32)
+    mat = vals.transpose(1, 0, 2).reshape(4, 4 * T)  # tile t = columns 4t .. 4t+3
+    a = orc.from_f32(orc.F16, mat)
+    dense, mask = orc.prune24_tile(orc.F16, a)
+    keep = mask.reshape(4, T, 4).transpose(1, 0, 2).reshape(T, 16).astype(np.uint32)
+    code = (keep << np.arange(16, dtype=np.uint32)).sum(1)
+    assert np.isin(code, pats).all()
+    mass = np.abs(vals).reshape(T, 16).astype(np.float64)
+    assert np.array_equal((mass * keep).sum(1), (mass @ pm.T).max(1))
+    flipped = orc.from_f32(orc.F16, mat * np.where(rng.random(mat.shape) < 0.5, -1.0, 1.0).astype(np.float32))
+    assert np.array_equal(orc.prune24_tile(orc.F16, flipped)[1], mask)
+    assert np.array_equal(orc.prune24_tile(orc.F16, orc.from_f32(orc.F16, mat * 0.125))[1], mask)
+    assert np.array_equal(orc.prune24_tile(orc.BF16, orc.from_f32(orc.BF16, mat))[1], mask)
+    # idempotent on values: a pruned tile keeps its non-zeros (the mask may move among zeros)
+    again, _ = orc.prune24_tile(orc.F16, dense)
+    assert np.array_equal(again, dense)
+    assert orc.prune24_check(orc.F16, dense) == 0 and orc.prune24_check(orc.F16, np.ascontiguousarray(
+        dense.reshape(4, T, 4).transpose(2, 1, 0).reshape(4, 4 * T))) == 0  # 2:4 along columns as well
