@@ -622,6 +622,42 @@ __device__ __forceinline__ void csr_fetch(const CsrSpmmParams& P, uint32_t batch
   }
 }
 
+// element offsets of a tile's 128 columns inside B and C (~0: past the last column); CSR / COO: the batch
+// elements' columns form one long column axis, blocked-ELL: tiles are per batch element
+template <bool BELL>
+__device__ __forceinline__ void spmm_tile_columns(const CsrSpmmParams& P, uint64_t j0, uint64_t ncols, size_t* colB,
+                                                  size_t* colC) {
+  if (threadIdx.x < CSR_TN) {
+    const uint64_t J = j0 + threadIdx.x;
+    size_t ob = ~(size_t)0, oc = ~(size_t)0;
+    if (J < ncols) {
+      const uint32_t bt = BELL ? 0u : (ncols <= 0xffffffffull ? (uint32_t)J / P.n : (uint32_t)(J / P.n));
+      const size_t jc = (size_t)(J - (uint64_t)bt * P.n);
+      ob = (size_t)bt * P.strideB + jc * P.ldb;
+      oc = (size_t)bt * P.strideC + jc * P.ldc;
+    }
+    colB[threadIdx.x] = ob;
+    colC[threadIdx.x] = oc;
+  }
+}
+
+// the C tile staged as sC[column][TM + 1] goes out along rows (column-major C): alpha * acc + beta * C
+template <int TM, int THREADS>
+__device__ __forceinline__ void spmm_store_c_tile(const CsrSpmmParams& P, float* Cbase, const float* sC,
+                                                  const size_t* colC, uint32_t rbase) {
+#pragma unroll 4
+  for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * TM); idx += THREADS) {
+    const uint32_t jj = idx / TM, i = idx % TM;
+    const size_t oc = colC[jj];
+    if (oc != ~(size_t)0 && rbase + i < P.m) {
+      float* dst = Cbase + oc + rbase + i;
+      float out = P.alpha * sC[jj * (TM + 1) + i];
+      if (P.beta != 0.f) out += P.beta * *dst;
+      *dst = out;
+    }
+  }
+}
+
 // MODE 0: CSR rows.  MODE 1: blocked-ELL rows, every slot an independent non-zero (any block size).
 // MODE 2: blocked-ELL with an even block size, walked as (row pair) x (column pair): the two rows of a pair
 // share their block-column ids, so one 64-bit read of B[c], B[c+1] per output column feeds four FMAs -- half
@@ -661,19 +697,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
     float* const Cbase = BELL ? P.Cs[batch] : P.C;
 
     __syncthreads();  // the previous tile's C stores have left shared memory
-    if (threadIdx.x < CSR_TN) {
-      // element offsets of this tile's columns inside B and C (~0: past the last column)
-      const uint64_t J = j0 + threadIdx.x;
-      size_t ob = ~(size_t)0, oc = ~(size_t)0;
-      if (J < ncols) {
-        const uint32_t bt = BELL ? 0u : (ncols <= 0xffffffffull ? (uint32_t)J / P.n : (uint32_t)(J / P.n));
-        const size_t jc = (size_t)(J - (uint64_t)bt * P.n);
-        ob = (size_t)bt * P.strideB + jc * P.ldb;
-        oc = (size_t)bt * P.strideC + jc * P.ldc;
-      }
-      colB[threadIdx.x] = ob;
-      colC[threadIdx.x] = oc;
-    }
+    spmm_tile_columns<BELL>(P, j0, ncols, colB, colC);
     __syncthreads();
 
     uint32_t cur[RPW];  // scan position of every row (row ends are re-read per chunk: registers are scarce)
@@ -841,18 +865,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
 #pragma unroll
       for (int j = 0; j < CSR_TJ; ++j) sC[(lane + 32 * j) * (TM + 1) + warp * RPW + r] = acc[r][j];
     __syncthreads();
-    const uint32_t rbase = rt * TM;
-#pragma unroll 4
-    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * TM); idx += CSR_THREADS) {
-      const uint32_t jj = idx / TM, i = idx % TM;
-      const size_t oc = colC[jj];
-      if (oc != ~(size_t)0 && rbase + i < P.m) {
-        float* dst = Cbase + oc + rbase + i;
-        float out = P.alpha * sC[jj * (TM + 1) + i];
-        if (P.beta != 0.f) out += P.beta * *dst;
-        *dst = out;
-      }
-    }
+    spmm_store_c_tile<TM, CSR_THREADS>(P, Cbase, sC, colC, rt * TM);
   }
 }
 
@@ -958,18 +971,7 @@ spmm_dense_walk_kernel(const __grid_constant__ CsrSpmmParams P) {
     float* const Cbase = BELL ? P.Cs[batch] : P.C;
 
     __syncthreads();  // the previous tile's C stores have left shared memory
-    if (threadIdx.x < CSR_TN) {
-      const uint64_t J = j0 + threadIdx.x;
-      size_t ob = ~(size_t)0, oc = ~(size_t)0;
-      if (J < ncols) {
-        const uint32_t bt = BELL ? 0u : (ncols <= 0xffffffffull ? (uint32_t)J / P.n : (uint32_t)(J / P.n));
-        const size_t jc = (size_t)(J - (uint64_t)bt * P.n);
-        ob = (size_t)bt * P.strideB + jc * P.ldb;
-        oc = (size_t)bt * P.strideC + jc * P.ldc;
-      }
-      colB[threadIdx.x] = ob;
-      colC[threadIdx.x] = oc;
-    }
+    spmm_tile_columns<BELL>(P, j0, ncols, colB, colC);
     __syncthreads();
 
     uint32_t cur[RPW], end[RPW];
@@ -1113,18 +1115,7 @@ spmm_dense_walk_kernel(const __grid_constant__ CsrSpmmParams P) {
         sC[(lane + 32 * j) * (TM + 1) + warp * RPW + 2 * p2 + 1] = hi;
       }
     __syncthreads();
-    const uint32_t rbase = rt * TM;
-#pragma unroll 4
-    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(CSR_TN * TM); idx += DW_THREADS) {
-      const uint32_t jj = idx / TM, i = idx % TM;
-      const size_t oc = colC[jj];
-      if (oc != ~(size_t)0 && rbase + i < P.m) {
-        float* dst = Cbase + oc + rbase + i;
-        float out = P.alpha * sC[jj * (TM + 1) + i];
-        if (P.beta != 0.f) out += P.beta * *dst;
-        *dst = out;
-      }
-    }
+    spmm_store_c_tile<TM, DW_THREADS>(P, Cbase, sC, colC, rt * TM);
   }
 }
 
