@@ -180,6 +180,25 @@ SPFY_API int spfy_spmma_plan_launch_info(spfy_spmma_plan_t plan, int index, int*
 SPFY_API int spfy_spmma_plan_destroy(spfy_spmma_plan_t plan);
 
 /* ------------------------------------------------------------------------
+ * Pruned-layer container (the artifact that follows prune + compress).
+ * One self-describing HOST buffer per compressed 2:4 operand:
+ *   64-byte header {magic "SPFY24\0\0", version, dtype, layout, rows, cols, vals_bytes,
+ *   meta_bytes, FNV-1a 64 of the payload} + values + metadata, as spfy_prune24 wrote them
+ * (copy them to the host first; these calls touch host memory only, no CUDA).  A reader
+ * checks magic / version / sizes against spfy_compressed_bytes and the checksum, then
+ * hands back offsets into the buffer, so the payload can go to the device with two copies
+ * and be used by spfy_spmma as is.
+ * ---------------------------------------------------------------------- */
+#define SPFY_PACKED_HEADER_BYTES 64
+SPFY_API int spfy_packed_bytes(int dtype, size_t rows, size_t cols, int layout, size_t* bytes);
+SPFY_API int spfy_packed_write(int dtype, int layout, size_t rows, size_t cols,
+                               const void* host_vals, const void* host_meta, void* dst,
+                               size_t dst_bytes);
+SPFY_API int spfy_packed_read(const void* src, size_t src_bytes, int* dtype, int* layout,
+                              size_t* rows, size_t* cols, size_t* vals_offset,
+                              size_t* vals_bytes, size_t* meta_offset, size_t* meta_bytes);
+
+/* ------------------------------------------------------------------------
  * Unstructured path (north_star subsystem 3).  Threshold prune keeps x iff
  * |x| > threshold (compared in fp32) and emits COO sorted by (row, col) or CSR.
  * dtype of `in` is F16/BF16/F32; emitted values are fp32 like the reference's

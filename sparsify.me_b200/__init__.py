@@ -24,12 +24,12 @@ from .capi import (F16, BF16, F32, F64, PRUNE_STRIP_MAG, PRUNE_TILE_MAG, LAYOUT_
                    LAYOUT_SM100, OP_N, OP_T, SpfyError, launch_count, last_error, version)
 from .ops import (sparsify, prune24, prune24_check, compressed_bytes, spmma_compressed, spmma,  # noqa: F401
                   threshold_to_coo, coo_to_csr, batched, Compressed24, SpmmaPlan, prune24_batched,
-                  alloc_compressed)
+                  alloc_compressed, pack_compressed, unpack_compressed)
 from . import shapes  # noqa: F401
 from . import multigpu  # noqa: F401
 
 __all__ = [
     "capi", "sparsify", "prune24", "prune24_check", "compressed_bytes", "spmma_compressed", "spmma",
-    "threshold_to_coo", "coo_to_csr", "batched", "Compressed24", "SpmmaPlan", "prune24_batched", "alloc_compressed", "shapes", "multigpu", "SpfyError",
+    "threshold_to_coo", "coo_to_csr", "batched", "Compressed24", "SpmmaPlan", "prune24_batched", "alloc_compressed", "pack_compressed", "unpack_compressed", "shapes", "multigpu", "SpfyError",
     "launch_count", "last_error", "version",
 ]

@@ -56,6 +56,10 @@ SIGNATURES = {
     "spfy_spmma_plan_run_launch": (c_int, [_P, c_int, _P]),
     "spfy_spmma_plan_launch_info": (c_int, [_P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "spfy_spmma_plan_destroy": (c_int, [_P]),
+    "spfy_packed_bytes": (c_int, [c_int, _SZ, _SZ, c_int, POINTER(_SZ)]),
+    "spfy_packed_write": (c_int, [c_int, c_int, _SZ, _SZ, _P, _P, _P, _SZ]),
+    "spfy_packed_read": (c_int, [_P, _SZ, POINTER(c_int), POINTER(c_int), POINTER(_SZ), POINTER(_SZ), POINTER(_SZ),
+                                 POINTER(_SZ), POINTER(_SZ), POINTER(_SZ)]),
     "spfy_threshold_workspace_bytes": (c_int, [_SZ, _SZ, POINTER(_SZ)]),
     "spfy_threshold_to_coo": (c_int, [c_int, _P, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, _P, _P,
                                       _P, _SZ, _P]),

@@ -105,4 +105,83 @@ int spfy_convert(int src_dtype, int dst_dtype, const void* src, void* dst, size_
   return fail(SPFY_E_UNSUPPORTED, "convert: %d -> %d is not supported (F32 <-> F16/BF16 only)", src_dtype, dst_dtype);
 }
 
+// ---------------------------------------------------------------- pruned-layer container (host memory only)
+namespace {
+struct PackedHeader {
+  char magic[8];
+  uint32_t version;
+  int32_t dtype, layout;
+  uint32_t reserved;
+  uint64_t rows, cols, vals_bytes, meta_bytes, checksum;
+};
+static_assert(sizeof(PackedHeader) == SPFY_PACKED_HEADER_BYTES, "container header is 64 bytes");
+const char kPackedMagic[8] = {'S', 'P', 'F', 'Y', '2', '4', 0, 0};
+
+uint64_t fnv1a64(const uint8_t* p, size_t n, uint64_t h) {
+  for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+  return h;
+}
+}  // namespace
+
+int spfy_packed_bytes(int dtype, size_t rows, size_t cols, int layout, size_t* bytes) {
+  size_t vb = 0, mb = 0;
+  int rc = spfy_compressed_bytes(dtype, rows, cols, layout, &vb, &mb);
+  if (rc) return rc;
+  if (bytes) *bytes = SPFY_PACKED_HEADER_BYTES + vb + mb;
+  return SPFY_OK;
+}
+
+int spfy_packed_write(int dtype, int layout, size_t rows, size_t cols, const void* host_vals,
+                      const void* host_meta, void* dst, size_t dst_bytes) {
+  size_t vb = 0, mb = 0;
+  int rc = spfy_compressed_bytes(dtype, rows, cols, layout, &vb, &mb);
+  if (rc) return rc;
+  if (!dst || (vb && !host_vals) || (mb && !host_meta)) return fail(SPFY_E_INVALID, "packed_write: null pointer");
+  if (dst_bytes < SPFY_PACKED_HEADER_BYTES + vb + mb)
+    return fail(SPFY_E_WORKSPACE, "packed_write: buffer %zu < %zu bytes", dst_bytes, (size_t)SPFY_PACKED_HEADER_BYTES + vb + mb);
+  PackedHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, kPackedMagic, 8);
+  h.version = 1;
+  h.dtype = dtype;
+  h.layout = layout;
+  h.rows = rows;
+  h.cols = cols;
+  h.vals_bytes = vb;
+  h.meta_bytes = mb;
+  h.checksum = fnv1a64((const uint8_t*)host_meta, mb, fnv1a64((const uint8_t*)host_vals, vb, 0xcbf29ce484222325ull));
+  uint8_t* out = (uint8_t*)dst;
+  memcpy(out, &h, sizeof(h));
+  memcpy(out + sizeof(h), host_vals, vb);
+  memcpy(out + sizeof(h) + vb, host_meta, mb);
+  return SPFY_OK;
+}
+
+int spfy_packed_read(const void* src, size_t src_bytes, int* dtype, int* layout, size_t* rows, size_t* cols,
+                     size_t* vals_offset, size_t* vals_bytes, size_t* meta_offset, size_t* meta_bytes) {
+  if (!src || src_bytes < SPFY_PACKED_HEADER_BYTES) return fail(SPFY_E_INVALID, "packed_read: buffer shorter than a header");
+  PackedHeader h;
+  memcpy(&h, src, sizeof(h));
+  if (memcmp(h.magic, kPackedMagic, 8) != 0) return fail(SPFY_E_INVALID, "packed_read: bad magic");
+  if (h.version != 1) return fail(SPFY_E_UNSUPPORTED, "packed_read: container version %u", h.version);
+  size_t vb = 0, mb = 0;
+  int rc = spfy_compressed_bytes(h.dtype, (size_t)h.rows, (size_t)h.cols, h.layout, &vb, &mb);
+  if (rc) return rc;
+  if (vb != h.vals_bytes || mb != h.meta_bytes)
+    return fail(SPFY_E_INVALID, "packed_read: sizes in the header do not match the shape");
+  if (src_bytes < SPFY_PACKED_HEADER_BYTES + vb + mb) return fail(SPFY_E_INVALID, "packed_read: truncated payload");
+  const uint8_t* p = (const uint8_t*)src + SPFY_PACKED_HEADER_BYTES;
+  if (fnv1a64(p + vb, mb, fnv1a64(p, vb, 0xcbf29ce484222325ull)) != h.checksum)
+    return fail(SPFY_E_INVALID, "packed_read: checksum mismatch");
+  if (dtype) *dtype = h.dtype;
+  if (layout) *layout = h.layout;
+  if (rows) *rows = (size_t)h.rows;
+  if (cols) *cols = (size_t)h.cols;
+  if (vals_offset) *vals_offset = SPFY_PACKED_HEADER_BYTES;
+  if (vals_bytes) *vals_bytes = vb;
+  if (meta_offset) *meta_offset = SPFY_PACKED_HEADER_BYTES + vb;
+  if (meta_bytes) *meta_bytes = mb;
+  return SPFY_OK;
+}
+
 }  // extern "C"

@@ -133,6 +133,33 @@ def alloc_compressed(dtype, rows, cols, device, layout=capi.LAYOUT_SM100):
                         torch.empty(mb, dtype=torch.uint8, device=device), rows, cols, dtype, layout)
 
 
+def pack_compressed(comp):
+    """Compressed24 -> one self-describing host buffer (bytes): the pruned-layer container of spfy_b200.h
+    (header + values + metadata, checksummed).  The payload is the device image byte for byte."""
+    vals = comp.vals.cpu().contiguous()
+    meta = comp.meta.cpu().contiguous()
+    n = ctypes.c_size_t()
+    capi.spfy_packed_bytes(_DT[comp.dtype], comp.rows, comp.cols, comp.layout, ctypes.byref(n))
+    buf = ctypes.create_string_buffer(n.value)
+    capi.spfy_packed_write(_DT[comp.dtype], comp.layout, comp.rows, comp.cols, vals.data_ptr(), meta.data_ptr(),
+                           ctypes.cast(buf, ctypes.c_void_p), n.value)
+    return buf.raw
+
+
+def unpack_compressed(blob, device):
+    """bytes written by pack_compressed -> Compressed24 on `device` (validated: magic, version, sizes, checksum)"""
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    dt, layout = ctypes.c_int(), ctypes.c_int()
+    rows, cols, vo, vb, mo, mb = (ctypes.c_size_t() for _ in range(6))
+    capi.spfy_packed_read(ctypes.cast(buf, ctypes.c_void_p), len(blob), ctypes.byref(dt), ctypes.byref(layout),
+                          ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(vo), ctypes.byref(vb), ctypes.byref(mo),
+                          ctypes.byref(mb))
+    raw = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    tdt = {v: k for k, v in _DT.items()}[dt.value]
+    return Compressed24(raw[vo.value: vo.value + vb.value].to(device), raw[mo.value: mo.value + mb.value].to(device),
+                        rows.value, cols.value, tdt, layout.value)
+
+
 class SpmmaPlan:
     """spfy_spmma_plan_*: a list of independent D_i = alpha_i * A_i(2:4) * op(B_i) + beta_i * C_i executed
     by one persistent launch per ring-geometry class present (tensor maps + tile schedule built once, like

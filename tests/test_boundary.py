@@ -100,3 +100,47 @@ def test_reference_drivers_compile_unchanged_against_our_headers(tmp_path, drive
            os.path.join(REF, "examples", driver + ".cu"), "-o", str(tmp_path / (driver + ".o"))]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_packed_container_roundtrip_on_the_host(spfy):
+    """the pruned-layer container is host-only code: write, read back, and refuse every kind of damage"""
+    import ctypes
+    import numpy as np
+    capi = spfy.capi
+    rows, cols = 130, 576
+    for layout in (capi.LAYOUT_CANONICAL, capi.LAYOUT_SM100):
+        vb, mb, n = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        capi.spfy_compressed_bytes(capi.F16, rows, cols, layout, ctypes.byref(vb), ctypes.byref(mb))
+        capi.spfy_packed_bytes(capi.F16, rows, cols, layout, ctypes.byref(n))
+        assert n.value == 64 + vb.value + mb.value
+        rng = np.random.default_rng(layout)
+        vals = rng.integers(0, 256, vb.value, dtype=np.uint8)
+        meta = rng.integers(0, 256, mb.value, dtype=np.uint8)
+        buf = np.zeros(n.value, dtype=np.uint8)
+        capi.spfy_packed_write(capi.F16, layout, rows, cols, vals.ctypes.data, meta.ctypes.data, buf.ctypes.data, buf.size)
+        assert bytes(buf[:6]) == b"SPFY24"
+
+        def read(b):
+            dt, lo = ctypes.c_int(), ctypes.c_int()
+            out = [ctypes.c_size_t() for _ in range(6)]
+            capi.spfy_packed_read(b.ctypes.data, b.size, ctypes.byref(dt), ctypes.byref(lo), *[ctypes.byref(x) for x in out])
+            return (dt.value, lo.value) + tuple(x.value for x in out)
+
+        dt, lo, r, c, vo, vbytes, mo, mbytes = read(buf)
+        assert (dt, lo, r, c) == (capi.F16, layout, rows, cols) and (vo, vbytes, mo, mbytes) == (64, vb.value, 64 + vb.value, mb.value)
+        assert np.array_equal(buf[vo: vo + vbytes], vals) and np.array_equal(buf[mo: mo + mbytes], meta)
+        for damage in ("payload", "magic", "truncate", "shape"):
+            b = buf.copy()
+            if damage == "payload":
+                b[64 + 5] ^= 1
+            elif damage == "magic":
+                b[0] = ord("X")
+            elif damage == "truncate":
+                b = b[:-1].copy()
+            else:
+                b[24] ^= 2  # rows
+            with pytest.raises(spfy.SpfyError):
+                read(b)
+        small = np.zeros(n.value - 1, dtype=np.uint8)
+        with pytest.raises(spfy.SpfyError):
+            capi.spfy_packed_write(capi.F16, layout, rows, cols, vals.ctypes.data, meta.ctypes.data, small.ctypes.data, small.size)

@@ -479,6 +479,22 @@ def test_spmma_reference_style_call(spfy, orc, cuda):
         assert rel_err(c.view(m, n).float().cpu().numpy().astype(np.float64), want) <= REL_TOL
 
 
+def test_packed_container_feeds_spmma(spfy, orc, cuda):
+    """prune + compress -> container bytes -> back onto the device: the reloaded operand is the same image and gives
+    the same product"""
+    m, n, k = 256, 320, 1152
+    a = to_dev(rand_bits(orc, 0, (m, k), seed=41), 0, cuda)
+    b = to_dev(rand_bits(orc, 0, (k, n), seed=42), 0, cuda)
+    comp = spfy.prune24(a, mode=spfy.PRUNE_TILE_MAG, out_dense=torch.empty_like(a))
+    blob = spfy.pack_compressed(comp)
+    back = spfy.unpack_compressed(blob, cuda)
+    assert (back.rows, back.cols, back.dtype, back.layout) == (m, k, torch.float16, spfy.LAYOUT_SM100)
+    assert torch.equal(back.vals, comp.vals) and torch.equal(back.meta, comp.meta)
+    assert torch.equal(spfy.spmma_compressed(back, b), spfy.spmma_compressed(comp, b))
+    with pytest.raises(spfy.SpfyError):
+        spfy.unpack_compressed(blob[:100] + bytes([blob[100] ^ 1]) + blob[101:], cuda)
+
+
 def test_spmma_rejects_bad_arguments(spfy, cuda):
     a = torch.zeros(128, 128, dtype=torch.float16, device=cuda)
     comp = spfy.prune24(a)
