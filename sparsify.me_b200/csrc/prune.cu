@@ -609,7 +609,9 @@ prune24_tile_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint16_t* __r
   const size_t total = (size_t)tiles_r * tiles_c;
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
-    const uint32_t tr = (uint32_t)(t / tiles_c), tc = (uint32_t)(t - (size_t)tr * tiles_c);
+    // (a 64-bit division costs ~60 instructions of a kernel that is issue-bound at ~450 per tile)
+    const uint32_t tr = (total >> 32) == 0 ? (uint32_t)t / tiles_c : (uint32_t)(t / tiles_c);
+    const uint32_t tc = (uint32_t)(t - (size_t)tr * tiles_c);
     const uint32_t r0 = tr * 4, c0 = tc * 4;
     float mag[16];
     if (VEC) {
@@ -673,7 +675,8 @@ prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
   for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += nthreads) {
     const size_t t = base + lane;
     const bool active = t < total;
-    const uint32_t tr = active ? (uint32_t)(t / tiles_c) : 0u, tc = active ? (uint32_t)(t - (size_t)tr * tiles_c) : 0u;
+    const uint32_t tr = !active ? 0u : (total >> 32) == 0 ? (uint32_t)t / tiles_c : (uint32_t)(t / tiles_c);
+    const uint32_t tc = active ? (uint32_t)(t - (size_t)tr * tiles_c) : 0u;
     const uint32_t r0 = tr * 4u, c0 = tc * 4u;
     const bool col_ok = active && c0 < P.cols;
     uint2 w[4];
