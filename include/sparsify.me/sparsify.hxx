@@ -25,6 +25,7 @@ void sparsify(type_t* weights,
               cudaStream_t stream = 0) {
   static_assert(detail::dtype_of<type_t>::value >= 0, "sparsify: unsupported element type");
   static_assert(sizeof(std::size_t) == sizeof(std::uint64_t), "mask words are 64-bit");
+  detail::lazy_init();  // first use on this device loads the device code (inside the caller's timer, like the reference)
   detail::ok(spfy_prune_blocks_ref(detail::dtype_of<type_t>::value, weights,
                                    reinterpret_cast<std::uint64_t*>(mask), m, n, BLK_M, BLK_N,
                                    sparsity_factor, reinterpret_cast<spfy_stream_t>(stream)),

@@ -47,8 +47,16 @@ float spmm(ell_t<type_t, memory_space_t::device>* As,
            float beta = 0.0f) {
   static_assert(detail::dtype_of<type_t>::value >= 0 && !std::is_same<type_t, double>::value,
                 "batched::spmm: type_t must be float, __half or __nv_bfloat16");
-  if (transpose_a != CUSPARSE_OPERATION_NON_TRANSPOSE || transpose_b != CUSPARSE_OPERATION_NON_TRANSPOSE)
-    std::cerr << "sparsify.me: batched::spmm: transposed operands are not supported; used as given." << std::endl;
+  // cusparseSpMM accepts only op(A) = N for a blocked-ELL A, and the reference's descriptors (:63-67) fix B as
+  // k x n: a transposed request fails there (status ignored, C untouched).  Here it fails loudly and computes nothing.
+  if (transpose_a != CUSPARSE_OPERATION_NON_TRANSPOSE || transpose_b != CUSPARSE_OPERATION_NON_TRANSPOSE) {
+    std::cerr << "sparsify.me: batched::spmm: transposed operands are not supported (SPFY_E_UNSUPPORTED); "
+                 "nothing was computed." << std::endl;
+#ifdef SPARSIFYME_STRICT
+    throw std::runtime_error("batched::spmm: transposed operands are not supported");
+#endif
+    return 0.f;
+  }
   if (batch_size == 0) return 0.f;
   cudaStream_t stream = nullptr;
 
@@ -65,7 +73,7 @@ float spmm(ell_t<type_t, memory_space_t::device>* As,
                   "batched::spmm");
   detail::cuda_ok(cudaDeviceSynchronize(), "batched::spmm");
 
-  detail::ok(spfy_init(), "spfy_init");  // device code loaded before any timer starts (cf. spmma.hxx:51-80)
+  detail::lazy_init();  // device code + scratch pool ready before any timer starts (cf. spmma.hxx:51-80)
   util::timer_t t;
   t.begin(stream);
 #ifdef SPARSIFYME_NVTX
@@ -105,7 +113,7 @@ float strided_coo(std::size_t A_num_rows,
   static_assert(std::is_same<type_t, float>::value,
                 "batched::strided_coo: fp32 values (CUDA_R_32F in the reference, spmm.hxx:168)");
   cudaStream_t stream = nullptr;
-  detail::ok(spfy_init(), "spfy_init");  // device code loaded before any timer starts (cf. spmma.hxx:51-80)
+  detail::lazy_init();  // device code + scratch pool ready before any timer starts (cf. spmma.hxx:51-80)
   util::timer_t t;
   t.begin(stream);  // like the reference, the interval covers set-up + workspace + SpMM (:155-187)
   const std::size_t ldb = B_num_rows, ldc = A_num_rows;

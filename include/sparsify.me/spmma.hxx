@@ -47,14 +47,24 @@ std::vector<float> spmma(
   const int dtype = is_f32 ? SPFY_F16 : detail::dtype_of<type_t>::value;
   cudaStream_t stream = nullptr;
   spfy_stream_t s = reinterpret_cast<spfy_stream_t>(stream);
-  detail::ok(spfy_init(), "spfy_init");  // device code loaded before any timer starts (cf. spmma.hxx:51-80)
+  detail::lazy_init();  // device code + scratch pool ready before any timer starts (cf. spmma.hxx:51-80)
   util::timer_t t;
 
   if (m % 8 != 0 || n % 8 != 0 || k % 8 != 0)  // same message policy as the reference (:45-49)
     std::cerr << "Invalid matrix sizes for data type __half. Rows and columns must be divisible by 8."
               << std::endl;
-  if (transpose_a != CUSPARSE_OPERATION_NON_TRANSPOSE)
-    std::cerr << "sparsify.me: spmma: transpose_a is not supported; A is used as given." << std::endl;
+  // The reference hands transpose_a to cusparseLtMatmulDescriptorInit with A described as m x k (:56-69): for
+  // op(A) = A^T the shapes only agree when m == k, and cusparseLt 0.7.1 has no transposed *structured* operand
+  // for row-major A at all, so the reference's call chain fails and leaves C untouched.  Same here: nothing is
+  // pruned or multiplied, the failure is reported, and the three timings are zero.
+  if (transpose_a != CUSPARSE_OPERATION_NON_TRANSPOSE) {
+    std::cerr << "sparsify.me: spmma: transpose_a is not supported (SPFY_E_UNSUPPORTED); nothing was computed."
+              << std::endl;
+#ifdef SPARSIFYME_STRICT
+    throw std::runtime_error("spmma: transpose_a is not supported");
+#endif
+    return {0.f, 0.f, 0.f};
+  }
 
   // float instantiation (the reference driver's: examples/spmma.cu:24): fp16 images of A, B, C
   const bool opb_t = transpose_b != CUSPARSE_OPERATION_NON_TRANSPOSE;

@@ -50,11 +50,16 @@ enum { SPFY_PRUNE_STRIP_MAG = 0, SPFY_PRUNE_TILE_MAG = 1 };
  *               meta    [rows][ceil4(cols)/8]   bytes; group g of a row sits in
  *                       byte g/2, low nibble for even g; nibble = i0 | i1<<2
  *   SM100     : what spfy_spmma consumes.  values and metadata are split into
- *               (128-row x 128-logical-k) tiles, tile (mt,kt) at index
- *               mt*k_tiles+kt; a value tile (16 KiB) is two 8 KiB K-slices, each the
- *               64B-swizzled K-major shared-memory image of 128 rows x 32 stored
- *               values; a metadata tile (2 KiB) is the tcgen05 `128x128b` image.
- *               See DESIGN.md "Data layout in HBM". */
+ *               (128-row x 128-logical-k) tiles; tile (mt,kt) sits at index
+ *               kt*m_tiles + mt (k-tile major: the m-tiles of one k-tile are adjacent).
+ *               A value tile (16 KiB) is ONE 128-row x 128-byte image, the 128B-swizzled
+ *               K-major shared-memory layout the UMMA descriptor reads: row r at r*128,
+ *               16-byte chunk c of the row (8 stored values = 16 logical k) at
+ *               ((c ^ (r & 7)) << 4).  A metadata tile (2 KiB) is the `tcgen05.cp.128x128b`
+ *               source image: the 16-bit word of in-tile row r and 16-column unit q sits at byte
+ *               (r>>4)*256 + (q&1)*128 + (r&7)*16 + (q>>1)*4 + ((r>>3)&1)*2.
+ *               Padding rows / columns hold +0 and the neutral nibble 0x4.
+ *               See DESIGN.md "Data layout in HBM"; pinned by tests/test_boundary.py. */
 enum { SPFY_LAYOUT_CANONICAL = 0, SPFY_LAYOUT_SM100 = 1 };
 
 enum { SPFY_OP_N = 0, SPFY_OP_T = 1 }; /* == cusparseOperation_t values */

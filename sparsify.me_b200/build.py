@@ -37,7 +37,7 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, dev=False):
     """Compile every .cu under csrc/ for sm_100a and link the shared library."""
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
@@ -50,7 +50,8 @@ def build_library(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+                   (["-DSPFY_DEV_SWITCHES"] if dev else []) + ["-c", s, "-o", o])
             subprocess.run(cmd, check=True)
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
@@ -60,4 +61,6 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # --dev: compile the SPFY_* environment switches in (tuning / timing experiments only, see common.cuh)
+    print(build_library(force="--force" in sys.argv or "--dev" in sys.argv, verbose="-v" in sys.argv,
+                        dev="--dev" in sys.argv))

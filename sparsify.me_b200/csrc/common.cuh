@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/spfy_b200.h"
@@ -48,6 +49,18 @@ inline std::atomic<uint64_t>& launch_counter() {
                           cudaGetErrorString(e__));                                         \
     ::spfy::launch_counter().fetch_add(1, std::memory_order_relaxed);                       \
   } while (0)
+
+// Development switches (ring depth, debug modes that skip work, kernel-choice overrides) are read from the
+// environment ONLY in builds made with -DSPFY_DEV_SWITCHES (build.py --dev); the shipped library ignores them,
+// so no environment variable can change results or skip work in production.
+inline const char* dev_switch(const char* name) {
+#ifdef SPFY_DEV_SWITCHES
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
 inline size_t round_up(size_t a, size_t b) { return ceil_div(a, b) * b; }

@@ -101,7 +101,8 @@ constexpr int BR_UNROLL = 4;
 template <typename T>
 __global__ void __launch_bounds__(256)
 prune_blocks_ref_kernel(T* __restrict__ weights, uint64_t* __restrict__ mask, size_t total,
-                        size_t nblocks, uint32_t blk_size, int vec_w, const __grid_constant__ OffsetList L) {
+                        size_t nblocks, uint32_t blk_size, int vec_w, int vec_m,
+                        const __grid_constant__ OffsetList L) {
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
   for (size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t0 * 4 < total; t0 += nthreads * BR_UNROLL) {
     unsigned zero[BR_UNROLL];
@@ -120,8 +121,13 @@ prune_blocks_ref_kernel(T* __restrict__ weights, uint64_t* __restrict__ mask, si
       if (e0 >= total) break;
       const unsigned z = zero[u];
       if (full[u]) {
-        *reinterpret_cast<ulonglong2*>(mask + e0) = make_ulonglong2(z & 1 ? 0ull : 1ull, z & 2 ? 0ull : 1ull);
-        *reinterpret_cast<ulonglong2*>(mask + e0 + 2) = make_ulonglong2(z & 4 ? 0ull : 1ull, z & 8 ? 0ull : 1ull);
+        if (vec_m) {
+          *reinterpret_cast<ulonglong2*>(mask + e0) = make_ulonglong2(z & 1 ? 0ull : 1ull, z & 2 ? 0ull : 1ull);
+          *reinterpret_cast<ulonglong2*>(mask + e0 + 2) = make_ulonglong2(z & 4 ? 0ull : 1ull, z & 8 ? 0ull : 1ull);
+        } else {  // mask only 8-byte aligned (e.g. a slice that starts at an odd word)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mask[e0 + i] = (z >> i & 1) ? 0ull : 1ull;
+        }
         if (vec_w) {
           if (z) quad_zero_store<sizeof(T)>(weights + e0, q[u], z);
         } else {
@@ -603,7 +609,7 @@ __device__ __forceinline__ float tile_mag(uint32_t bits) {
 
 template <bool BF16, bool VEC>
 __global__ void __launch_bounds__(256)
-prune24_tile_kernel(const uint16_t* __restrict__ in, size_t ld_in, uint16_t* __restrict__ out,
+prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __restrict__: out may alias in (in-place prune)
                     size_t ld_out, uint32_t rows, uint32_t cols) {
   const uint32_t tiles_c = (cols + 3) / 4, tiles_r = (rows + 3) / 4;
   const size_t total = (size_t)tiles_r * tiles_c;
@@ -870,11 +876,14 @@ int spfy_prune_blocks_ref(int dtype, void* weights, uint64_t* mask, size_t m, si
   int rc = grid_for(ceil_div(total, 4), 256, &grid);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  const int vec_w = (uintptr_t)weights % (eb == 8 ? 16 : 4 * eb) == 0 && (uintptr_t)mask % 16 == 0;
+  if ((uintptr_t)mask % 8 || (uintptr_t)weights % eb)
+    return fail(SPFY_E_INVALID, "prune_blocks_ref: weights / mask are not aligned to their element size");
+  const int vec_w = (uintptr_t)weights % (eb == 8 ? 16 : 4 * eb) == 0;  // whole-vector RMW of the weights
+  const int vec_m = (uintptr_t)mask % 16 == 0;                          // 16-byte mask stores
   switch (eb) {
-    case 2: prune_blocks_ref_kernel<uint16_t><<<grid, 256, 0, s>>>((uint16_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, L); break;
-    case 4: prune_blocks_ref_kernel<uint32_t><<<grid, 256, 0, s>>>((uint32_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, L); break;
-    default: prune_blocks_ref_kernel<uint64_t><<<grid, 256, 0, s>>>((uint64_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, L); break;
+    case 2: prune_blocks_ref_kernel<uint16_t><<<grid, 256, 0, s>>>((uint16_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, vec_m, L); break;
+    case 4: prune_blocks_ref_kernel<uint32_t><<<grid, 256, 0, s>>>((uint32_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, vec_m, L); break;
+    default: prune_blocks_ref_kernel<uint64_t><<<grid, 256, 0, s>>>((uint64_t*)weights, mask, total, nblocks, (uint32_t)blk_size, vec_w, vec_m, L); break;
   }
   SPFY_LAUNCH_OK("prune_blocks_ref_kernel");
   return SPFY_OK;
@@ -926,7 +935,7 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
     // One pass for weight-sized matrices: the fused kernel saves a launch (every ResNet layer is launch-bound,
     // <= 2.4 M elements) but it is issue-bound and costs 526 us on 16384 x 16384 where the two passes take 445
     static const size_t fused_max = [] {
-      const char* e = getenv("SPFY_TILE_FUSED_MAX");
+      const char* e = dev_switch("SPFY_TILE_FUSED_MAX");
       return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)8 << 20;
     }();
     if ((comp_vals || meta) && !mask && vec && cols % 16 == 0 && (uintptr_t)meta % 2 == 0 && (uintptr_t)comp_vals % 4 == 0 &&

@@ -1139,7 +1139,7 @@ int launch_spmm_dense_walk(const CsrSpmmParams& P, int sm_count, cudaStream_t s)
 // fraction of non-zeros from which the dense walk is used (SPFY_SPMM_WALK_DENSITY; > 1 disables it)
 double walk_density() {
   static const double d = [] {
-    const char* e = getenv("SPFY_SPMM_WALK_DENSITY");
+    const char* e = dev_switch("SPFY_SPMM_WALK_DENSITY");
     return e ? atof(e) : 0.35;  // measured crossover: M=256 K=2304 at 30 % non-zeros, M=64 K=576 at 40 % (profiles/r01_summary.md)
   }();
   return d;

@@ -355,7 +355,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
 
   // The launches of a plan are independent problems issued back to back with programmatic stream
   // serialization: letting the next launch's CTAs in as soon as ours retire overlaps its ramp-up with
-  // our tail (nobody calls griddepcontrol.wait -- there is no data dependence between them).
+  // our tail (there is no data dependence between them; griddepcontrol.wait is only issued at the very end,
+  // to keep completion transitive).
   if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 1 && lane == 0) {
     for (uint32_t s = 0; s < (uint32_t)MAX_STAGES; ++s) {
@@ -680,6 +681,11 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  // Completion must be transitive along a plan's chain of programmatic launches: this grid may have started while
+  // its predecessor's tail was still running, so one thread waits for the predecessor before the CTA retires (all
+  // the work is done by now, the ramp-up overlap is kept; a no-op for launches without the attribute).  Whatever
+  // is enqueued after spfy_spmma_plan_run therefore sees every launch of the plan finished.
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ------------------------------------------------------------- host side
@@ -869,7 +875,7 @@ void geometry(int cls, uint32_t res_vals, uint32_t res_meta, LaunchParams* L, ui
   const uint32_t fixed = 1024 /*alignment slack*/ + c_bytes + BAR_BYTES + res;
   uint32_t stages = (SMEM_LIMIT - fixed) / stage;
   if (stages > (uint32_t)MAX_STAGES) stages = MAX_STAGES;
-  if (const char* cap = getenv("SPFY_SPMMA_STAGES")) {  // tuning experiment: fewer ring stages
+  if (const char* cap = dev_switch("SPFY_SPMMA_STAGES")) {  // tuning experiment: fewer ring stages
     const uint32_t c = (uint32_t)atoi(cap);
     if (c >= 1 && c < stages) stages = c;
   }
@@ -993,7 +999,7 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
   L.total_units = d.units;
   L.idesc = make_idesc(dtype, opB);
   {
-    const char* e = getenv("SPFY_SPMMA_DEBUG");
+    const char* e = dev_switch("SPFY_SPMMA_DEBUG");
     L.dbg = e ? (uint32_t)atoi(e) : 0u;
   }
   const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
@@ -1069,7 +1075,7 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
       ln.L.total_units = units;
       ln.L.idesc = make_idesc(dtype, opB);
       {
-        const char* e = getenv("SPFY_SPMMA_DEBUG");
+        const char* e = dev_switch("SPFY_SPMMA_DEBUG");
         ln.L.dbg = e ? (uint32_t)atoi(e) : 0u;
       }
       ln.grid = (int)(units < (uint32_t)di.sm_count ? units : (uint32_t)di.sm_count);
@@ -1096,7 +1102,7 @@ int spfy_spmma_plan_run(spfy_spmma_plan_t p, spfy_stream_t stream) {
   Plan* plan = (Plan*)p;
   ProblemDev dummy;
   memset(&dummy, 0, sizeof(dummy));
-  static const bool serial = getenv("SPFY_SPMMA_NO_OVERLAP") != nullptr;
+  static const bool serial = dev_switch("SPFY_SPMMA_NO_OVERLAP") != nullptr;
   bool first = true;
   for (const auto& ln : plan->launches) {
     int rc = launch(plan->dtype, ln.opB, dummy, ln.L, ln.smem, ln.grid, (cudaStream_t)stream, !first && !serial);
