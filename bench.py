@@ -570,6 +570,28 @@ def main():
     ms_per_step = total_ms / args.steps
     value = flops_step * world / (ms_per_step * 1e-3) / 1e12
 
+    # ---- the timed outputs are checked, not just produced: D of the last timed step against a torch fp32 matmul of
+    #      the pruned weights (decoded by the same prune kernel family), first / middle / last / largest-K layers, every
+    #      column (outside the timed region; tests/test_gpu_fullsize.py checks all layers against the CPU oracle too)
+    verified = None
+    if rank == 0:
+        picks = sorted({0, len(layers) // 2, len(layers) - 1, max(range(len(layers)), key=lambda i: layers[i][0].K)})
+        worst = 0.0
+        for i in picks:
+            g, w, b, d, comp = layers[i]
+            pruned = torch.empty_like(w)
+            spfy.prune24(w, out_dense=pruned, compress=False)
+            pf = pruned.float()
+            for c0 in range(0, g.N, 50176):
+                want = pf @ b[:, c0:c0 + 50176].float()
+                scale = torch.clamp(want.abs(), min=1e-2 * float(want.abs().max()))
+                worst = max(worst, float(((d[:, c0:c0 + 50176].float() - want).abs() / scale).max()))
+            del pruned, pf
+        verified = {"layers": picks, "columns": "all", "max_rel_err": worst, "tolerance": 1e-2, "ok": worst <= 1e-2,
+                    "against": "torch fp32 matmul of the 2:4-pruned weights on the same GPU"}
+        if not verified["ok"]:
+            raise SystemExit(f"bench.py: timed outputs are wrong (max relative error {worst:.3e} > 1e-2)")
+
     # ---- end to end through the reference-shaped call with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -673,6 +695,8 @@ def main():
                   "algorithmic_bytes_per_step": prune_bytes_step,
                   "note": "all layers' weights in one launch; 23.5 M elements, 3.125 B/element"},
     }
+    if verified:
+        line["verified"] = verified
     if prune_large:
         line["prune_large"] = prune_large
     if e2e:

@@ -1,7 +1,10 @@
 // spmm.hxx -- sparsifyme::batched::spmm (blocked-ELL) and sparsifyme::batched::strided_coo.
 //
 // Reference signatures (include/sparsify.me/spmm.hxx:30-41 and :140-153) kept verbatim; the
-// cuSPARSE generic-API calls (:57-110, :164-187) are replaced by our row-split SpMM kernels:
+// cuSPARSE generic-API calls (:57-110, :164-187) are replaced by our own kernels -- the sparse operand is
+// densified and contracted on tcgen05 (3xTF32 for fp32: fp32-level accuracy) when it is dense enough to pay,
+// the row-split CUDA-core kernels otherwise (-DSPARSIFYME_SPMM_ALG=SPFY_SPMM_ALG_CUDA_CORE forces them:
+// bit-identical to cuSPARSE on exactly representable inputs; ..._TENSOR_FAST = one TF32 product):
 //   batched::spmm        C_b = alpha * A_b * B + beta * C_b,  A_b blocked-ELL per batch,
 //                        B k x n column-major (ld k) shared, C_b m x n column-major (ld m);
 //                        one launch covers every batch element (the reference spawns one
@@ -29,6 +32,10 @@
 #include <sparsify.me/containers/ell.hxx>
 #include <sparsify.me/detail/cabi.hxx>
 #include <sparsify.me/util/util.hxx>
+
+#ifndef SPARSIFYME_SPMM_ALG
+#define SPARSIFYME_SPMM_ALG SPFY_SPMM_ALG_DEFAULT
+#endif
 
 namespace sparsifyme {
 namespace batched {
@@ -81,9 +88,11 @@ float spmm(ell_t<type_t, memory_space_t::device>* As,
 #endif
   const void* const* tab = d_ptrs.as<const void*>();
   std::size_t ws_bytes = 0;
-  detail::ok(spfy_spmm_workspace_bytes(As[0].rows, 0, &ws_bytes), "batched::spmm");
+  detail::ok(spfy_spmm_bell_workspace_bytes(SPARSIFYME_SPMM_ALG, detail::dtype_of<type_t>::value, As[0].rows, As[0].cols,
+                                            n, batch_size, &ws_bytes),
+             "batched::spmm");
   detail::scratch ws(ws_bytes, stream);
-  detail::ok(spfy_spmm_bell_batched(detail::dtype_of<type_t>::value, As[0].rows, As[0].cols, n,
+  detail::ok(spfy_spmm_bell_batched(SPARSIFYME_SPMM_ALG, detail::dtype_of<type_t>::value, As[0].rows, As[0].cols, n,
                                     As[0].block_size, As[0].ell_cols, batch_size,
                                     reinterpret_cast<const std::int64_t* const*>(tab), tab + batch_size, B, k,
                                     const_cast<void* const*>(reinterpret_cast<const void* const*>(tab + 2 * batch_size)),
@@ -118,9 +127,10 @@ float strided_coo(std::size_t A_num_rows,
   t.begin(stream);  // like the reference, the interval covers set-up + workspace + SpMM (:155-187)
   const std::size_t ldb = B_num_rows, ldc = A_num_rows;
   std::size_t ws_bytes = 0;
-  detail::ok(spfy_spmm_workspace_bytes(A_num_rows, A_nnz, &ws_bytes), "batched::strided_coo");
+  detail::ok(spfy_spmm_workspace_bytes(SPARSIFYME_SPMM_ALG, A_num_rows, A_num_cols, A_nnz, &ws_bytes),
+             "batched::strided_coo");
   detail::scratch ws(ws_bytes, stream);
-  detail::ok(spfy_spmm_coo_strided_batched(A_num_rows, A_num_cols, A_nnz, B_num_cols, num_batches, dA_rows,
+  detail::ok(spfy_spmm_coo_strided_batched(SPARSIFYME_SPMM_ALG, A_num_rows, A_num_cols, A_nnz, B_num_cols, num_batches, dA_rows,
                                            dA_cols, dA_values, dB, ldb, ldb * B_num_cols, *dC, ldc,
                                            ldc * B_num_cols, alpha, beta, ws.ptr, ws_bytes,
                                            reinterpret_cast<spfy_stream_t>(stream)),

@@ -227,33 +227,55 @@ SPFY_API int spfy_coo_to_csr(const int32_t* row_idx, size_t nnz, size_t rows,
                              int32_t* row_ptr, spfy_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Algorithm of the unstructured SpMM entry points below (first argument).
+ *   DEFAULT     : the library chooses.  An A with at least 2 % non-zeros (every pruned ResNet
+ *                 weight matrix: 5-50 %) is scattered into a dense matrix in the workspace and
+ *                 contracted on tcgen05 (fp32 operands: 3xTF32, fp32-level accuracy, see
+ *                 spfy_gemm_*; 16-bit operands: kind::f16) when the operands meet the TMA
+ *                 contract (16-byte aligned bases, leading dimensions and batch strides
+ *                 multiples of 16 bytes); otherwise, and for sparser A, the CUDA-core kernels run.
+ *                 The CSR entry does not know nnz on the host: it launches both candidates and
+ *                 a device flag lets exactly one do the work, so it never reads anything back.
+ *   CUDA_CORE   : the row-split CUDA-core kernels only.  fp32 sums in ascending k order per
+ *                 output element: bit-identical to cuSPARSE 12.5 on exactly representable
+ *                 inputs (tests/golden/cusparse_*.npz).
+ *   TENSOR      : the tensor-core route or SPFY_E_UNSUPPORTED / SPFY_E_WORKSPACE.
+ *   TENSOR_FAST : same with ONE TF32 product per fp32 multiply (10-bit mantissas; the accuracy
+ *                 class of cuBLAS's TF32 mode).  16-bit operands: identical to TENSOR.
+ * ---------------------------------------------------------------------- */
+enum {
+  SPFY_SPMM_ALG_DEFAULT = 0,
+  SPFY_SPMM_ALG_CUDA_CORE = 1,
+  SPFY_SPMM_ALG_TENSOR = 2,
+  SPFY_SPMM_ALG_TENSOR_FAST = 3
+};
+
+/* ------------------------------------------------------------------------
  * A6  sparsifyme::batched::strided_coo           include/sparsify.me/spmm.hxx:140-193
  * C_b = alpha * A * B_b + beta * C_b for b in [0, num_batches): ONE sparse A
  * (stride 0, :169) shared by all batches; B_b = B + b*strideB is k x n
  * column-major (ldb >= k, :160,:170); C_b = C + b*strideC is m x n column-major
  * (ldc >= m, :161,:173).  fp32 values, int32 indices, fp32 accumulate.
- * The COO triplets must be sorted by row (any column order); row_ptr is
- * built internally in the workspace.
+ * The COO triplets must be sorted by row (any column order; repeated (row, col)
+ * entries add, like cuSPARSE); row_ptr is built internally in the workspace.
+ * The workspace query takes the algorithm: the tensor-core route keeps the dense
+ * m x k fp32 image of A there (a workspace sized for CUDA_CORE makes DEFAULT take
+ * the CUDA-core kernels).
  * ---------------------------------------------------------------------- */
-SPFY_API int spfy_spmm_workspace_bytes(size_t m, size_t nnz, size_t* bytes);
-SPFY_API int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n,
+SPFY_API int spfy_spmm_workspace_bytes(int alg, size_t m, size_t k, size_t nnz, size_t* bytes);
+SPFY_API int spfy_spmm_coo_strided_batched(int alg, size_t m, size_t k, size_t nnz, size_t n,
                                            size_t num_batches, const int32_t* row_idx,
                                            const int32_t* col_idx, const float* vals,
                                            const float* B, size_t ldb, size_t strideB,
                                            float* C, size_t ldc, size_t strideC, float alpha,
                                            float beta, void* workspace, size_t workspace_bytes,
                                            spfy_stream_t stream);
-/* Same product with A already in CSR (same workspace query; only its last 256 bytes are used:
- * two device words -- whether the column indices ascend inside every row, which selects the
- * kernels' cursor mode, and whether A holds >= 35 % non-zeros (SPFY_SPMM_WALK_DENSITY), in which
- * case the dense-walk kernel runs instead of the per-non-zero one.  The COO entry knows nnz on the
- * host and launches only the kernel that will run; this entry launches both and the flag lets
- * exactly one do the work, so it never reads anything back). */
-SPFY_API int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
-                                           const int32_t* row_ptr, const int32_t* col_idx,
-                                           const float* vals, const float* B, size_t ldb,
-                                           size_t strideB, float* C, size_t ldc,
-                                           size_t strideC, float alpha, float beta,
+/* Same product with A already in CSR (same workspace query). */
+SPFY_API int spfy_spmm_csr_strided_batched(int alg, size_t m, size_t k, size_t n,
+                                           size_t num_batches, const int32_t* row_ptr,
+                                           const int32_t* col_idx, const float* vals,
+                                           const float* B, size_t ldb, size_t strideB, float* C,
+                                           size_t ldc, size_t strideC, float alpha, float beta,
                                            void* workspace, size_t workspace_bytes,
                                            spfy_stream_t stream);
 
@@ -263,17 +285,60 @@ SPFY_API int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t 
  * (containers/ell.hxx:24-33): rows x cols, square blocks of `block`,
  * `ell_cols` stored columns per row; col_idx_b[(rows/block) x (ell_cols/block)]
  * block-column ids (int64 here because the reference stores std::size_t,
- * ell.hxx:31); values_b[rows x ell_cols] row-major.  B is k x n column-major
- * ldb = k shared by all batches (:67); C_b is m x n column-major ldc = m (:63).
- * `col_idx`, `values`, `Cs` are DEVICE arrays of num_batches device pointers.
- * dtype is that of values/B/C (F16/BF16/F32); fp32 accumulate (:82).
+ * ell.hxx:31; ids < 0 are padding); values_b[rows x ell_cols] row-major.  B is
+ * k x n column-major ldb = k shared by all batches (:67); C_b is m x n
+ * column-major ldc = m (:63).  `col_idx`, `values`, `Cs` are DEVICE arrays of
+ * num_batches device pointers.  dtype is that of values/B/C (F16/BF16/F32);
+ * fp32 accumulate (:82).
+ * Tensor-core route (DEFAULT when the operands meet the TMA contract): the batch is
+ * expanded chunk by chunk into dense row-major matrices in the workspace (every
+ * element written once, no atomics) and contracted by the dense tcgen05 GEMM; a
+ * block-row that repeats an id (undefined for cuSPARSE; our kernels add the blocks)
+ * raises a device flag that hands its chunk to the CUDA-core kernel instead.
  * ---------------------------------------------------------------------- */
-SPFY_API int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n,
+SPFY_API int spfy_spmm_bell_workspace_bytes(int alg, int dtype, size_t rows, size_t cols, size_t n,
+                                            size_t num_batches, size_t* bytes);
+SPFY_API int spfy_spmm_bell_batched(int alg, int dtype, size_t rows, size_t cols, size_t n,
                                     size_t block, size_t ell_cols, size_t num_batches,
                                     const int64_t* const* col_idx, const void* const* values,
                                     const void* B, size_t ldb, void* const* Cs, size_t ldc,
                                     float alpha, float beta, void* workspace,
                                     size_t workspace_bytes, spfy_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * N3  sparsifyme::batched::gemm                  include/sparsify.me/gemm.hxx:25-195
+ * Dense batched GEMM on tcgen05 (replaces cublas{H,S}gemmBatched, :51-186), BLAS
+ * conventions: column-major, C_b[m x n, ldc] = alpha * op(A_b)[m x k] * op(B_b)[k x n]
+ * + beta * C_b.  opX = N: the operand is stored as its op() shape; T: transposed.
+ * dtype F16 / BF16: kind::f16, fp32 accumulation in TMEM.  dtype F32:
+ *   SPFY_GEMM_PRECISE  3xTF32 -- each operand is split in shared memory into
+ *                      hi (the 11 significant bits the tensor core reads) and lo = x - hi, and
+ *                      hi*lo + lo*hi + hi*hi is accumulated in fp32: products exact to ~2^-21;
+ *   SPFY_GEMM_FAST     one TF32 product.
+ * The operands are fetched by TMA, which needs 16-byte aligned bases and lda / ldb /
+ * batch strides that are multiples of 16 bytes; an operand that misses this (ldb = k = 147
+ * floats, the first conv layer of every ResNet) is first copied into the workspace with
+ * padded rows -- one extra pass over that operand, nothing else changes.  The batched form
+ * takes HOST arrays of device pointers (what examples/gemm.cu:93-95 holds are device
+ * arrays -- the header copies them back once, outside its timer).  Both forms take a
+ * device workspace sized by the query (problem table of the batched form + padded copies
+ * of the operands whose lda / ldb need them; pass lda = 0 / ldb = 0 to size for a
+ * misaligned base pointer as well).
+ * ---------------------------------------------------------------------- */
+enum { SPFY_GEMM_PRECISE = 0, SPFY_GEMM_FAST = 1 };
+SPFY_API int spfy_gemm_workspace_bytes(int dtype, int opA, int opB, size_t m, size_t n, size_t k,
+                                       size_t lda, size_t ldb, size_t num_batches, size_t* bytes);
+SPFY_API int spfy_gemm_strided_batched(int dtype, int precision, int opA, int opB, size_t m, size_t n,
+                                       size_t k, float alpha, const void* A, size_t lda,
+                                       size_t strideA, const void* B, size_t ldb, size_t strideB,
+                                       float beta, void* C, size_t ldc, size_t strideC,
+                                       size_t num_batches, void* workspace, size_t workspace_bytes,
+                                       spfy_stream_t stream);
+SPFY_API int spfy_gemm_batched(int dtype, int precision, int opA, int opB, size_t m, size_t n, size_t k,
+                               float alpha, const void* const* A_ptrs, size_t lda,
+                               const void* const* B_ptrs, size_t ldb, float beta,
+                               void* const* C_ptrs, size_t ldc, size_t num_batches,
+                               void* workspace, size_t workspace_bytes, spfy_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <array>
+#include <map>
 #include <vector>
 
 #define CK(x)                                                                                       \
@@ -228,11 +230,110 @@ static int run_time(int argc, char** argv) {
   return 0;
 }
 
+// cusparse_ref timebell <csv> [batch] : the reference's batched::spmm as its driver runs it over a shape table
+// (examples/spmm.cu:40-116, include/sparsify.me/spmm.hxx:57-115): per CSV row (m, n, k, b) b blocked-ELL matrices
+// (block 2, ell_cols = k/2, ascending unique block-column ids), ONE shared B, one cusparseSpMM per batch element,
+// each on its own stream; timed like the reference's timer (events on the null stream around the fan-out), best
+// of 3 after a warm-up.  One CSV line per row and a JSON summary: the same-box comparator for our `spmm` column.
+static int run_timebell(int argc, char** argv) {
+  if (argc < 3) return 2;
+  FILE* f = std::fopen(argv[2], "r");
+  if (!f) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
+  const int64_t batch_override = argc > 3 ? atoll(argv[3]) : 0;
+  char line[256];
+  std::vector<std::array<int64_t, 4>> shapes;
+  bool first = true;
+  while (std::fgets(line, sizeof(line), f)) {
+    if (first) { first = false; continue; }
+    long long m, n, k, b;
+    if (std::sscanf(line, "%lld,%lld,%lld,%lld", &m, &n, &k, &b) == 4) shapes.push_back({m, n, k, batch_override ? batch_override : b});
+  }
+  std::fclose(f);
+  cusparseHandle_t h;
+  CKS(cusparseCreate(&h));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  std::map<std::array<int64_t, 4>, double> memo;
+  double total_ms = 0;
+  std::printf("m,n,k,b,cusparse_bell_ms\n");
+  for (const auto& sh : shapes) {
+    if (memo.count(sh)) { total_ms += memo[sh]; std::printf("%lld,%lld,%lld,%lld,%.5f\n", (long long)sh[0], (long long)sh[1], (long long)sh[2], (long long)sh[3], memo[sh]); continue; }
+    const int64_t m = sh[0], n = sh[1], k = sh[2], nb = sh[3], block = 2;
+    const int64_t ell_cols = k / 2 / block * block, bcols = ell_cols / block, brows = (m + block - 1) / block, nbc = k / block;
+    if (bcols == 0 || m % block) { std::printf("%lld,%lld,%lld,%lld,nan\n", (long long)m, (long long)n, (long long)k, (long long)nb); continue; }
+    std::vector<int32_t> ci((size_t)nb * brows * bcols);
+    for (int64_t b = 0; b < nb; ++b)
+      for (int64_t i = 0; i < brows; ++i) {
+        const int64_t phase = (i + b) & 1;  // every other block column: ascending, unique
+        for (int64_t j = 0; j < bcols; ++j) ci[(b * brows + i) * bcols + j] = (int32_t)std::min<int64_t>(2 * j + phase, nbc - 1);
+      }
+    int32_t* dci = to_dev(ci);
+    float *dV = nullptr, *dB = nullptr, *dC = nullptr;
+    CK(cudaMalloc(&dV, (size_t)nb * m * ell_cols * 4));
+    CK(cudaMalloc(&dB, (size_t)n * k * 4));
+    CK(cudaMalloc(&dC, (size_t)nb * n * m * 4));
+    CK(cudaMemset(dV, 0x3c, (size_t)nb * m * ell_cols * 4));
+    CK(cudaMemset(dB, 0x3c, (size_t)n * k * 4));
+    const float alpha = 1.f, beta = 0.f;
+    std::vector<cusparseSpMatDescr_t> A(nb);
+    std::vector<cusparseDnMatDescr_t> mC(nb);
+    std::vector<cudaStream_t> st(nb);
+    std::vector<void*> bufs(nb, nullptr);
+    cusparseDnMatDescr_t mB;
+    CKS(cusparseCreateDnMat(&mB, k, n, k, dB, CUDA_R_32F, CUSPARSE_ORDER_COL));
+    for (int64_t b = 0; b < nb; ++b) {
+      CKS(cusparseCreateBlockedEll(&A[b], m, k, block, ell_cols, dci + b * brows * bcols, dV + b * m * ell_cols,
+                                   CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_R_32F));
+      CKS(cusparseCreateDnMat(&mC[b], m, n, m, dC + b * n * m, CUDA_R_32F, CUSPARSE_ORDER_COL));
+      size_t bufsz = 0;
+      CKS(cusparseSpMM_bufferSize(h, CUSPARSE_OPERATION_NON_TRANSPOSE, CUSPARSE_OPERATION_NON_TRANSPOSE, &alpha, A[b], mB,
+                                  &beta, mC[b], CUDA_R_32F, CUSPARSE_SPMM_ALG_DEFAULT, &bufsz));
+      CK(cudaMalloc(&bufs[b], bufsz + 16));
+      CK(cudaStreamCreate(&st[b]));
+    }
+    double best = 1e30;
+    for (int it = 0; it < 4; ++it) {
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0, 0));
+      for (int64_t b = 0; b < nb; ++b) {
+        CKS(cusparseSetStream(h, st[b]));
+        CKS(cusparseSpMM(h, CUSPARSE_OPERATION_NON_TRANSPOSE, CUSPARSE_OPERATION_NON_TRANSPOSE, &alpha, A[b], mB, &beta,
+                         mC[b], CUDA_R_32F, CUSPARSE_SPMM_ALG_DEFAULT, bufs[b]));
+      }
+      CK(cudaEventRecord(e1, 0));  // the null stream waits for every blocking stream, like the reference's timer
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (it >= 1 && ms < best) best = ms;
+    }
+    CKS(cusparseSetStream(h, 0));
+    for (int64_t b = 0; b < nb; ++b) {
+      cusparseDestroySpMat(A[b]);
+      cusparseDestroyDnMat(mC[b]);
+      cudaFree(bufs[b]);
+      cudaStreamDestroy(st[b]);
+    }
+    cusparseDestroyDnMat(mB);
+    cudaFree(dci); cudaFree(dV); cudaFree(dB); cudaFree(dC);
+    memo[sh] = best;
+    total_ms += best;
+    std::printf("%lld,%lld,%lld,%lld,%.5f\n", (long long)m, (long long)n, (long long)k, (long long)nb, best);
+    std::fflush(stdout);
+  }
+  std::printf("{\"library\": \"cuSPARSE blocked-ELL SpMM (block 2, ell_cols k/2, fp32, one call per batch element on its own stream)\", "
+              "\"rows\": %zu, \"sum_ms\": %.4f}\n", shapes.size(), total_ms);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "timebell") return run_timebell(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "time") return run_time(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "coo") return run_coo(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "bell") return run_bell(argc, argv);
   std::fprintf(stderr, "usage: cusparse_ref coo <m> <k> <n> <nb> <thr> <alpha> <beta> <out.bin>\n"
-                       "       cusparse_ref bell <m> <k> <n> <nb> <block> <out.bin>\n");
+                       "       cusparse_ref bell <m> <k> <n> <nb> <block> <out.bin>\n"
+                       "       cusparse_ref time <m> <k> <n> <nb> <keep>\n"
+                       "       cusparse_ref timebell <table.csv> [batch]\n");
   return 2;
 }

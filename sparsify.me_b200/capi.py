@@ -18,6 +18,8 @@ F16, BF16, F32, F64 = 0, 1, 2, 3
 PRUNE_STRIP_MAG, PRUNE_TILE_MAG = 0, 1
 LAYOUT_CANONICAL, LAYOUT_SM100 = 0, 1
 OP_N, OP_T = 0, 1
+SPMM_ALG_DEFAULT, SPMM_ALG_CUDA_CORE, SPMM_ALG_TENSOR, SPMM_ALG_TENSOR_FAST = 0, 1, 2, 3
+GEMM_PRECISE, GEMM_FAST = 0, 1
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE, E_NCCL = 0, -1, -2, -3, -4, -5
 
 
@@ -64,13 +66,19 @@ SIGNATURES = {
     "spfy_threshold_to_coo": (c_int, [c_int, _P, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, _P, _P,
                                       _P, _SZ, _P]),
     "spfy_coo_to_csr": (c_int, [_P, _SZ, _SZ, _P, _P]),
-    "spfy_spmm_workspace_bytes": (c_int, [_SZ, _SZ, POINTER(_SZ)]),
-    "spfy_spmm_coo_strided_batched": (c_int, [_SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P,
+    "spfy_spmm_workspace_bytes": (c_int, [c_int, _SZ, _SZ, _SZ, POINTER(_SZ)]),
+    "spfy_spmm_coo_strided_batched": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P,
                                               _SZ, _SZ, c_float, c_float, _P, _SZ, _P]),
-    "spfy_spmm_csr_strided_batched": (c_int, [_SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P, _SZ,
+    "spfy_spmm_csr_strided_batched": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P, _SZ,
                                               _SZ, c_float, c_float, _P, _SZ, _P]),
-    "spfy_spmm_bell_batched": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _SZ, _P, _SZ,
+    "spfy_spmm_bell_workspace_bytes": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, _SZ, POINTER(_SZ)]),
+    "spfy_spmm_bell_batched": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _SZ, _P, _SZ,
                                        c_float, c_float, _P, _SZ, _P]),
+    "spfy_gemm_workspace_bytes": (c_int, [c_int, c_int, c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, POINTER(_SZ)]),
+    "spfy_gemm_strided_batched": (c_int, [c_int, c_int, c_int, c_int, _SZ, _SZ, _SZ, c_float, _P, _SZ, _SZ, _P, _SZ,
+                                          _SZ, c_float, _P, _SZ, _SZ, _SZ, _P, _SZ, _P]),
+    "spfy_gemm_batched": (c_int, [c_int, c_int, c_int, c_int, _SZ, _SZ, _SZ, c_float, _P, _SZ, _P, _SZ, c_float, _P,
+                                  _SZ, _SZ, _P, _SZ, _P]),
 }
 
 _NO_STATUS = {"spfy_version", "spfy_last_error_string", "spfy_launch_count", "spfy_spmma_plan_launches"}

@@ -80,6 +80,7 @@ int spfy_init(void) {
   spfy::warm_prune_kernels();
   spfy::warm_spmma_kernels();
   spfy::warm_spmm_kernels();
+  spfy::warm_gemm_kernels();
   touch_kernel(convert_kernel<float, __half>);
   touch_kernel(convert_kernel<float, __nv_bfloat16>);
   touch_kernel(convert_kernel<__half, float>);
@@ -120,24 +121,28 @@ int spfy_init(void) {
         float* Bm = reinterpret_cast<float*>(vals);             // >= 8 KiB: reuse the compressed-operand area as B, C
         size_t tws = 0, sws = 0;
         (void)spfy_threshold_workspace_bytes(128, 128, &tws);
-        (void)spfy_spmm_workspace_bytes(128, 16384, &sws);
+        (void)spfy_spmm_workspace_bytes(SPFY_SPMM_ALG_CUDA_CORE, 128, 128, 16384, &sws);
         if (tws <= 32768 && sws <= 32768 && vb >= 2 * 128 * 8 * sizeof(float)) {
           float* Cm = Bm + 128 * 8;
           (void)spfy_threshold_to_coo(SPFY_F32, W, 128, 128, 128, 0.5f, ri, ci, va, 16384, nnz, rp, ws, 32768, nullptr);
           for (size_t mm = 64; mm <= 128; mm += 64)
-            (void)spfy_spmm_csr_strided_batched(mm, 128, 8, 1, rp, ci, va, Bm, 128, 128 * 8, Cm, mm, mm * 8, 1.f, 0.f, ws, 32768, nullptr);
+            (void)spfy_spmm_csr_strided_batched(SPFY_SPMM_ALG_CUDA_CORE, mm, 128, 8, 1, rp, ci, va, Bm, 128, 128 * 8, Cm, mm, mm * 8, 1.f, 0.f, ws, 32768, nullptr);
           const void* hp[3] = {ci /* block-column ids (int64 view of zeros is fine) */, W, Cm};
           void** dp = reinterpret_cast<void**>(tail + 65536);
           (void)cudaMemset(ci, 0, mat);
           (void)cudaMemcpy(dp, hp, sizeof(hp), cudaMemcpyHostToDevice);
           for (size_t mm = 64; mm <= 128; mm += 64)
-            (void)spfy_spmm_bell_batched(SPFY_F32, mm, 128, 8, 2, 16, 1, reinterpret_cast<const int64_t* const*>(dp),
+            (void)spfy_spmm_bell_batched(SPFY_SPMM_ALG_CUDA_CORE, SPFY_F32, mm, 128, 8, 2, 16, 1, reinterpret_cast<const int64_t* const*>(dp),
                                          reinterpret_cast<const void* const*>(dp + 1), Bm, 128,
                                          reinterpret_cast<void* const*>(dp + 2), mm, 1.f, 0.f, ws, 32768, nullptr);
         }
       }
       (void)spfy_convert(SPFY_F32, SPFY_F16, W, A, 128 * 128, nullptr);
       (void)spfy_convert(SPFY_F16, SPFY_F32, A, W, 128 * 128, nullptr);
+      if (di.cc_major == 10)  // dense tcgen05 GEMM (batched::gemm and the tensor-core routes of the SpMM entries)
+        for (int dt = SPFY_F16; dt <= SPFY_F32; ++dt)
+          (void)spfy_gemm_strided_batched(dt, SPFY_GEMM_PRECISE, SPFY_OP_N, SPFY_OP_N, 128, 128, 128, 1.f, A, 128, 0, B, 128,
+                                          0, 0.f, D, 128, 0, 1, nullptr, 0, nullptr);
       (void)cudaDeviceSynchronize();
       (void)cudaFree(buf);
     }

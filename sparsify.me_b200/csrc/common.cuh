@@ -100,6 +100,7 @@ inline void touch_kernel(K kernel) {
 void warm_prune_kernels();
 void warm_spmma_kernels();
 void warm_spmm_kernels();
+void warm_gemm_kernels();
 
 inline size_t dtype_bytes(int dtype) {
   switch (dtype) {

@@ -1,0 +1,801 @@
+// gemm_sm100.cu -- dense batched GEMM on tcgen05 (sm_100a): kind::f16 for fp16 / bf16 operands and
+// 3xTF32 (kind::tf32, split in shared memory) for fp32 operands at fp32-level accuracy.
+//
+// Replaces the library contractions of the reference that are dense (or dense enough to be run densely):
+//     sparsifyme::batched::gemm          cublas{H,S}gemmBatched          include/sparsify.me/gemm.hxx:25-195
+//     sparsifyme::batched::strided_coo   cusparseSpMM COO_ALG4           include/sparsify.me/spmm.hxx:140-193
+//     sparsifyme::batched::spmm          cusparseSpMM blocked-ELL        include/sparsify.me/spmm.hxx:30-138
+// (the two SpMM entries scatter / expand their sparse operand into a dense one first, spmm.cu).
+//
+// The kernel works in "UMMA terms": D[Mu x Nu] = Au[Mu x K] * Bu[Nu x K]^T with fp32 accumulators in TMEM.  Each
+// operand may be K-major (K contiguous) or MN-major (its Mu / Nu dimension contiguous); the result is written
+// with either dimension contiguous.  The host maps a column-major BLAS problem onto this so that the long,
+// streamed dimension becomes Mu (128-row tiles = TMEM lanes) and the short one becomes Nu (one UMMA of up to 256
+// columns), e.g. a weight matrix with 64 rows costs N = 64 MMAs instead of a half-empty M = 128 tile.
+//
+// Persistent CTA of 320 threads, 1 CTA/SM, work unit = (problem, batch, m-tile, n-tile), n-tile fastest so that
+// CTAs running side by side share the streamed Au tile through L2:
+//   warp 0      producer : TMA tensor loads of the Au / Bu tiles of one 128-byte K slab per ring stage
+//   warp 1      MMA      : per stage 4 k-steps of 32 bytes; fp32 inputs issue three kind::tf32 MMAs per k-step
+//                          (hi*lo, lo*hi, hi*hi), 16-bit inputs one kind::f16 MMA
+//   warps 2-5   splitter : fp32 only: x -> hi = x rounded to TF32 (low 13 mantissa bits zero: the tensor core reads
+//                          it exactly), lo = x - hi (exact in fp32), hi over the raw tile and lo behind it;
+//                          the layout is irrelevant to an element-wise pass, so the swizzled tiles are
+//                          processed as flat bytes
+//   warps 6-9   epilogue : tcgen05.ld 32 columns at a time -> alpha / beta -> coalesced global stores
+// TMEM: two accumulator slots of 256 columns, so the epilogue of one unit overlaps the MMAs of the next.
+//
+// Accuracy of the fp32 path: hi carries 11 significant bits, |lo| <= 2^-11 |x| of which the tensor core reads the
+// leading 11 bits, and the lo*lo term (<= 2^-22) is dropped: every product is exact to ~2^-20 relative in the
+// worst case, accumulation is fp32.  The parity tests bound the result against an fp64 oracle by
+// 4e-6 * sum_k |a||b| (tests/test_gpu_tensor.py).
+#include "gemm_sm100.cuh"
+#include "tc_ptx.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace spfy {
+namespace {
+using namespace ptx;
+
+constexpr int GM_BM = 128;        // rows of Au per tile (UMMA M)
+constexpr int GM_MAX_BN = 256;    // columns of one UMMA / TMEM slot
+constexpr int GM_ROW_BYTES = 128; // bytes of K per operand row and stage (one swizzle atom)
+constexpr int GM_A_BYTES = GM_BM * GM_ROW_BYTES;
+constexpr int GM_THREADS = 320;
+constexpr int GM_SPLIT_WARPS = 4, GM_EPI_WARPS = 4;
+constexpr int GM_ACC_SLOTS = 2;
+constexpr int GM_MAX_STAGES = 8;
+constexpr int GM_SMEM_LIMIT = 232448;
+constexpr uint32_t GM_BAR_BYTES = 512;
+
+enum { KIND_F16 = 0, KIND_BF16 = 1, KIND_F32 = 2 };
+
+struct alignas(64) GemmProblemDev {
+  CUtensorMap tmap_a;      // Au: {inner, outer, batch}; K-major: inner = K, MN-major: inner = Mu
+  CUtensorMap tmap_b;      // Bu likewise
+  uint8_t* C;              // batch 0 of the result
+  const uint64_t* c_ptrs;  // optional device array of per-batch result pointers
+  uint64_t ldc, stride_c;  // elements
+  uint32_t mu, nu, k, nb;
+  uint32_t m_tiles, n_tiles, k_tiles;
+  uint32_t bn;             // columns of one n-tile: multiple of 16 (of the MN group when Bu is MN-major)
+  uint32_t a_mn, b_mn;     // operand is MN-major
+  uint32_t a_batched, b_batched;
+  uint32_t out_mu_contig;  // result element (i, j) at i + j*ldc (1) or j + i*ldc (0)
+  uint32_t unit_begin, units;
+  float alpha, beta;
+};
+
+struct GemmLaunch {
+  const GemmProblemDev* table;  // null -> the single problem passed by value
+  uint32_t num_problems, total_units;
+  uint32_t stages, stage_bytes, raw_bytes;  // stage = [Au raw 16 KiB][Bu raw bn_max*128] (+ the same again: lo parts)
+  uint32_t bar_off;
+  uint32_t split;     // fp32: 3xTF32 (splitter warps run)
+  uint32_t write_hi;  // splitter also stores hi over the raw tile (independent of how the tensor core rounds)
+  uint32_t idesc;     // instruction descriptor without N and the major bits
+  uint32_t kelems;    // elements of K per stage (32 fp32 / 64 half)
+  const int* gate;    // optional device word: the launch does its work only if (*gate != 0) == gate_run_if
+  uint32_t gate_run_if;
+};
+
+struct GemmWalker {
+  const GemmProblemDev* single;
+  const GemmProblemDev* table;
+  uint32_t num_problems, total_units, u, p;
+  __device__ __forceinline__ GemmWalker(const GemmProblemDev* s, const GemmLaunch& L)
+      : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units), u(blockIdx.x), p(0) {}
+  __device__ __forceinline__ const GemmProblemDev* prob(uint32_t i) const { return table ? table + i : single; }
+  __device__ __forceinline__ bool valid() const { return u < total_units; }
+  __device__ __forceinline__ const GemmProblemDev* current() {
+    while (p + 1 < num_problems && u >= prob(p)->unit_begin + prob(p)->units) ++p;
+    p = uni(p);
+    return prob(p);
+  }
+  __device__ __forceinline__ void next() { u += gridDim.x; }
+};
+
+template <int KIND>
+struct OutT { using type = float; };
+template <> struct OutT<KIND_F16> { using type = __half; };
+template <> struct OutT<KIND_BF16> { using type = __nv_bfloat16; };
+
+template <int KIND> __device__ __forceinline__ float out_to_f32(typename OutT<KIND>::type v);
+template <> __device__ __forceinline__ float out_to_f32<KIND_F16>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float out_to_f32<KIND_BF16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float out_to_f32<KIND_F32>(float v) { return v; }
+template <int KIND> __device__ __forceinline__ typename OutT<KIND>::type f32_to_out(float v);
+template <> __device__ __forceinline__ __half f32_to_out<KIND_F16>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 f32_to_out<KIND_BF16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float f32_to_out<KIND_F32>(float v) { return v; }
+
+template <int KIND>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+tcgemm_kernel(const __grid_constant__ GemmProblemDev single, const __grid_constant__ GemmLaunch L) {
+  using out_t = typename OutT<KIND>::type;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a caller that decides on the device which of two kernels handles a problem launches both (spmm.cu)
+  if (L.gate && (*L.gate != 0) != (L.gate_run_if != 0)) return;
+
+  const uint32_t NS = L.stages;
+  const uint32_t bar_full = smem_base + L.bar_off;                   // [GM_MAX_STAGES] producer -> splitter / MMA
+  const uint32_t bar_conv = bar_full + GM_MAX_STAGES * 8;            // [GM_MAX_STAGES] splitter -> MMA
+  const uint32_t bar_empty = bar_conv + GM_MAX_STAGES * 8;           // [GM_MAX_STAGES] MMA -> producer
+  const uint32_t bar_acc_full = bar_empty + GM_MAX_STAGES * 8;       // [GM_ACC_SLOTS]
+  const uint32_t bar_acc_empty = bar_acc_full + GM_ACC_SLOTS * 8;    // [GM_ACC_SLOTS]
+  const uint32_t tmem_ptr_off = L.bar_off + (3 * GM_MAX_STAGES + 2 * GM_ACC_SLOTS) * 8;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + tmem_ptr_off);
+
+  if (warp == 1 && lane == 0) {
+    for (uint32_t s = 0; s < (uint32_t)GM_MAX_STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_conv + s * 8, GM_SPLIT_WARPS);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    for (int a = 0; a < GM_ACC_SLOTS; ++a) {
+      mbar_init(bar_acc_full + a * 8, 1);
+      mbar_init(bar_acc_empty + a * 8, GM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_base + tmem_ptr_off, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  GemmWalker W(&single, L);
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    const bool leader = elect_one();
+    uint32_t stage = 0, phase = 0;
+    const GemmProblemDev* last = nullptr;
+    const CUtensorMap *tmap_a = nullptr, *tmap_b = nullptr;
+    uint32_t m_tiles = 1, n_tiles = 1, k_tiles = 0, bn = 0, a_mn = 0, b_mn = 0, a_bat = 0, b_bat = 0, unit_begin = 0;
+    const uint32_t kel = L.kelems;                      // K elements per stage == k rows of an MN-major slab
+    const uint32_t gsz = kel;                           // MN elements per 128-byte group (32 fp32 / 64 half)
+    const uint32_t group_bytes = kel * GM_ROW_BYTES;    // one MN group: kel k-rows x 128 bytes
+    for (; W.valid(); W.next()) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) {
+        last = P;
+        tmap_a = &P->tmap_a; tmap_b = &P->tmap_b;
+        if (leader) { prefetch_tmap(tmap_a); prefetch_tmap(tmap_b); }
+        m_tiles = uni(P->m_tiles); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); bn = uni(P->bn);
+        a_mn = uni(P->a_mn); b_mn = uni(P->b_mn); a_bat = uni(P->a_batched); b_bat = uni(P->b_batched);
+        unit_begin = uni(P->unit_begin);
+      }
+      const uint32_t local = W.u - unit_begin;
+      const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
+      const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
+      const int ba = a_bat ? (int)b : 0, bb = b_bat ? (int)b : 0;
+      const uint32_t tx = (uint32_t)GM_A_BYTES + bn * (uint32_t)GM_ROW_BYTES;
+      for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+        const uint32_t full = bar_full + stage * 8;
+        const uint32_t sa = smem_base + stage * L.stage_bytes, sb = sa + GM_A_BYTES;
+        if (leader) {
+          mbar_expect_tx(full, tx);
+          if (!a_mn) {
+            tma_load_3d(sa, tmap_a, (int)(kt * kel), (int)(mt * GM_BM), ba, full, HINT_EVICT_NORMAL);
+          } else {
+            for (uint32_t g = 0; g * gsz < (uint32_t)GM_BM; ++g)
+              tma_load_3d(sa + g * group_bytes, tmap_a, (int)(mt * GM_BM + g * gsz), (int)(kt * kel), ba, full,
+                          HINT_EVICT_NORMAL);
+          }
+          if (!b_mn) {
+            tma_load_3d(sb, tmap_b, (int)(kt * kel), (int)(nt * bn), bb, full, HINT_EVICT_NORMAL);
+          } else {
+            for (uint32_t g = 0; g * gsz < bn; ++g)
+              tma_load_3d(sb + g * group_bytes, tmap_b, (int)(nt * bn + g * gsz), (int)(kt * kel), bb, full,
+                          HINT_EVICT_NORMAL);
+          }
+        }
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint32_t tmem_b = uni(tmem_base);
+    uint32_t stage = 0, phase = 0, job = 0;
+    const GemmProblemDev* last = nullptr;
+    uint32_t k_tiles = 0, pk = 0, bn = 0, a_mn = 0, b_mn = 0;
+    const uint32_t kel = L.kelems;
+    const uint32_t umma_k = kel / 4u;               // K elements per MMA (32 bytes)
+    const uint32_t group_bytes = kel * GM_ROW_BYTES;
+    const uint32_t split = L.split;
+    const uint32_t wait_bar = split ? bar_conv : bar_full;
+    const uint32_t lo_off = L.raw_bytes >> 4;       // lo tiles sit raw_bytes behind the raw ones (16-byte units)
+    // K-major: rows of 128 bytes, 8-row atoms 1024 bytes apart, a k-step advances 32 bytes inside the swizzled row.
+    // MN-major: 128-byte groups of MN, 8 k-rows per 1024-byte atom (SBO), groups `group_bytes` apart (LBO); a k-step
+    // is umma_k k-rows = umma_k * 128 bytes.
+    const uint64_t desc_k = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+    const uint64_t desc_mn = make_smem_desc(0, group_bytes, 1024, LAYOUT_SW128);
+    const uint32_t step_mn = (umma_k * GM_ROW_BYTES) >> 4;
+    for (; W.valid(); W.next()) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) {
+        last = P;
+        k_tiles = uni(P->k_tiles); pk = uni(P->k); bn = uni(P->bn); a_mn = uni(P->a_mn); b_mn = uni(P->b_mn);
+      }
+      const uint32_t slot = job % GM_ACC_SLOTS, use = job / GM_ACC_SLOTS;
+      mbar_wait(bar_acc_empty + slot * 8, (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_b + slot * (uint32_t)GM_MAX_BN;
+      const uint32_t idesc = L.idesc | (a_mn << 15) | (b_mn << 16) | ((bn >> 3) << 17);
+      const uint64_t da_hi = a_mn ? desc_mn : desc_k, db_hi = b_mn ? desc_mn : desc_k;
+      const uint32_t a_step = a_mn ? step_mn : 2u, b_step = b_mn ? step_mn : 2u;
+      uint32_t k_left = pk;
+      for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= kel) {
+        mbar_wait(wait_bar + stage * 8, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * L.stage_bytes;
+        const uint32_t a0 = (sa >> 4) & 0x3fffu, b0 = ((sa + GM_A_BYTES) >> 4) & 0x3fffu;
+        const uint32_t nk = k_left >= kel ? 4u : (k_left + umma_k - 1u) / umma_k;
+        if (leader) {
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            if (j < nk) {
+              const uint64_t da = da_hi | (uint64_t)(a0 + a_step * j), db = db_hi | (uint64_t)(b0 + b_step * j);
+              const uint32_t acc = (kt | j) ? 1u : 0u;
+              if (KIND == KIND_F32) {
+                if (split) {
+                  tc_mma_tf32(tmem_d, da, db + lo_off, idesc, acc);       // hi * lo
+                  tc_mma_tf32(tmem_d, da + lo_off, db, idesc, 1u);        // lo * hi
+                  tc_mma_tf32(tmem_d, da, db, idesc, 1u);                 // hi * hi
+                } else {
+                  tc_mma_tf32(tmem_d, da, db, idesc, acc);
+                }
+              } else {
+                tc_mma_f16(tmem_d, da, db, idesc, acc);
+              }
+            }
+          }
+          tc_commit(bar_empty + stage * 8);
+        }
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) tc_commit(bar_acc_full + slot * 8);
+      ++job;
+    }
+  } else if (warp < 2 + GM_SPLIT_WARPS) {
+    // ===================== splitter (fp32 inputs only) =====================
+    if (L.split) {
+      const uint32_t t = threadIdx.x - 64u;
+      uint32_t stage = 0, phase = 0;
+      const GemmProblemDev* last = nullptr;
+      uint32_t k_tiles = 0, bn = 0;
+      const uint32_t raw = L.raw_bytes;
+      const bool write_hi = L.write_hi != 0;
+      for (; W.valid(); W.next()) {
+        const GemmProblemDev* P = W.current();
+        if (P != last) { last = P; k_tiles = P->k_tiles; bn = P->bn; }
+        const uint32_t used = (uint32_t)GM_A_BYTES + bn * (uint32_t)GM_ROW_BYTES;  // Au and Bu raw tiles are adjacent
+        for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+          mbar_wait(bar_full + stage * 8, phase);
+          const uint32_t sa = smem_base + stage * L.stage_bytes;
+#pragma unroll 4
+          for (uint32_t off = t * 16u; off < used; off += GM_SPLIT_WARPS * 32u * 16u) {
+            const uint4 x = ld_shared_v4(sa + off);
+            // hi = x rounded to the nearest TF32 (half up in magnitude; a carry into the exponent is the right
+            // answer too), so |lo| <= 2^-11 |x| and x - hi is exact in fp32
+            const uint32_t h0 = (x.x + 0x1000u) & 0xffffe000u, h1 = (x.y + 0x1000u) & 0xffffe000u;
+            const uint32_t h2 = (x.z + 0x1000u) & 0xffffe000u, h3 = (x.w + 0x1000u) & 0xffffe000u;
+            const float l0 = __uint_as_float(x.x) - __uint_as_float(h0), l1 = __uint_as_float(x.y) - __uint_as_float(h1);
+            const float l2 = __uint_as_float(x.z) - __uint_as_float(h2), l3 = __uint_as_float(x.w) - __uint_as_float(h3);
+            st_shared_v4(sa + raw + off, __float_as_uint(l0), __float_as_uint(l1), __float_as_uint(l2), __float_as_uint(l3));
+            if (write_hi) st_shared_v4(sa + off, h0, h1, h2, h3);
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_conv + stage * 8);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 6-9) =====================
+    const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter + 32)
+    uint32_t job = 0;
+    const GemmProblemDev* last = nullptr;
+    uint32_t m_tiles = 1, n_tiles = 1, bn = 0, mu = 0, nu = 0, unit_begin = 0, mu_contig = 1;
+    uint64_t ldc = 0, stride_c = 0;
+    uint8_t* Cbase = nullptr;
+    const uint64_t* c_ptrs = nullptr;
+    float alpha = 1.f, beta = 0.f;
+    for (; W.valid(); W.next(), ++job) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) {
+        last = P;
+        m_tiles = P->m_tiles; n_tiles = P->n_tiles; bn = P->bn; mu = P->mu; nu = P->nu; unit_begin = P->unit_begin;
+        mu_contig = P->out_mu_contig; ldc = P->ldc; stride_c = P->stride_c; Cbase = P->C; c_ptrs = P->c_ptrs;
+        alpha = P->alpha; beta = P->beta;
+      }
+      const uint32_t local = W.u - unit_begin;
+      const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
+      const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
+      out_t* C = c_ptrs ? reinterpret_cast<out_t*>(c_ptrs[b]) : reinterpret_cast<out_t*>(Cbase) + (size_t)b * stride_c;
+      const uint32_t slot = job % GM_ACC_SLOTS;
+      const uint32_t row = mt * GM_BM + quarter * 32u + lane;  // index along Mu
+      const bool row_ok = row < mu;
+      const bool warp_ok = mt * GM_BM + quarter * 32u < mu;
+      mbar_wait(bar_acc_full + slot * 8, (job / GM_ACC_SLOTS) & 1u);
+      tc_fence_after();
+      const uint32_t chunks = (bn + 31u) / 32u;
+      for (uint32_t c = 0; c < chunks; ++c) {
+        const uint32_t col0 = nt * bn + c * 32u;  // index along Nu
+        const uint32_t ncols = min(32u, min(bn - c * 32u, nu > col0 ? nu - col0 : 0u));
+        uint32_t acc[32];
+        if (warp_ok && ncols) {
+          tmem_ld_x32(tmem_base + slot * (uint32_t)GM_MAX_BN + c * 32u + ((quarter * 32u) << 16), acc);
+          tmem_wait_ld();
+        }
+        if (c + 1 == chunks) {
+          // accumulator fully read by this warp: hand the slot back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
+        }
+        if (!warp_ok || !ncols) continue;
+        if (mu_contig) {
+          // element (row, col) at row + col*ldc: a warp's 32 rows are one 128-byte (fp32) line per column
+          if (row_ok) {
+            out_t* dst = C + row + (size_t)col0 * ldc;
+            if (beta == 0.f) {
+#pragma unroll
+              for (uint32_t j = 0; j < 32; ++j)
+                if (j < ncols) dst[(size_t)j * ldc] = f32_to_out<KIND>(alpha * __uint_as_float(acc[j]));
+            } else {
+#pragma unroll
+              for (uint32_t j = 0; j < 32; ++j)
+                if (j < ncols)
+                  dst[(size_t)j * ldc] =
+                      f32_to_out<KIND>(alpha * __uint_as_float(acc[j]) + beta * out_to_f32<KIND>(dst[(size_t)j * ldc]));
+            }
+          }
+        } else if (row_ok) {
+          // element (row, col) at col + row*ldc: the thread owns up to 32 consecutive elements
+          out_t* dst = C + (size_t)row * ldc + col0;
+          constexpr uint32_t VEC = 16 / sizeof(out_t);  // elements per 16-byte store
+          const bool vec_ok = ncols == 32u && ((uintptr_t)dst % 16 == 0);
+          if (vec_ok) {
+#pragma unroll
+            for (uint32_t q = 0; q < 32 / VEC; ++q) {
+              float v[VEC];
+#pragma unroll
+              for (uint32_t x = 0; x < VEC; ++x) v[x] = alpha * __uint_as_float(acc[q * VEC + x]);
+              if (beta != 0.f) {
+                const uint4 old = *reinterpret_cast<const uint4*>(dst + q * VEC);
+                const out_t* o = reinterpret_cast<const out_t*>(&old);
+#pragma unroll
+                for (uint32_t x = 0; x < VEC; ++x) v[x] += beta * out_to_f32<KIND>(o[x]);
+              }
+              uint4 w;
+              out_t* wo = reinterpret_cast<out_t*>(&w);
+#pragma unroll
+              for (uint32_t x = 0; x < VEC; ++x) wo[x] = f32_to_out<KIND>(v[x]);
+              *reinterpret_cast<uint4*>(dst + q * VEC) = w;
+            }
+          } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j)
+              if (j < ncols) {
+                float v = alpha * __uint_as_float(acc[j]);
+                if (beta != 0.f) v += beta * out_to_f32<KIND>(dst[j]);
+                dst[j] = f32_to_out<KIND>(v);
+              }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// An operand TMA cannot address (base not 16-byte aligned, or a leading dimension / batch stride that is not a
+// multiple of 16 bytes -- e.g. ld = k = 147 floats for the first conv layer of every ResNet) is copied once into the
+// workspace with its rows padded to 16 bytes.  One thread per element, coalesced along the contiguous dimension.
+template <typename T>
+__global__ void __launch_bounds__(256)
+repack_kernel(const T* __restrict__ src, size_t ld, size_t stride, T* __restrict__ dst, size_t ldp, size_t stride_p,
+              size_t inner, size_t outer, size_t batches) {
+  const size_t per = inner * outer, total = per * batches;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const size_t b = i / per, r = (i - b * per) / inner, c = i - b * per - r * inner;
+    dst[b * stride_p + r * ldp + c] = src[b * stride + r * ld + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+size_t elem_bytes(int dtype) { return dtype == SPFY_F32 ? 4 : 2; }
+
+// One operand as the kernel sees it: extent `mn` x `k`, element (i, kk) at (mn_major ? i + kk*ld : kk + i*ld)
+struct OperandView {
+  const void* base;
+  size_t mn, k, ld, stride;  // stride: elements between batches, 0 = shared
+  bool mn_major;
+};
+
+bool operand_ok(int dtype, const OperandView& v, size_t nb) {
+  const size_t es = elem_bytes(dtype);
+  if ((uintptr_t)v.base % 16 || (v.ld * es) % 16) return false;
+  if (nb > 1 && v.stride && (v.stride * es) % 16) return false;
+  const size_t inner = v.mn_major ? v.mn : v.k;
+  return v.ld >= inner;
+}
+
+size_t padded_ld(int dtype, const OperandView& v) {
+  return round_up(v.mn_major ? v.mn : v.k, 16 / elem_bytes(dtype));
+}
+// bytes of workspace the padded copy of an operand takes (0: TMA can address it as it is)
+size_t repack_bytes(int dtype, const OperandView& v, size_t nb) {
+  if (operand_ok(dtype, v, nb)) return 0;
+  const size_t outer = v.mn_major ? v.k : v.mn, batches = nb > 1 && v.stride ? nb : 1;
+  return round_up(batches * outer * padded_ld(dtype, v) * elem_bytes(dtype), 256);
+}
+
+int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t nb, uint32_t box_rows) {
+  EncodeTiledFn enc0;
+  int rc = get_encoder(&enc0);
+  if (rc) return rc;
+  EncodeFn enc = (EncodeFn)enc0;
+  const size_t es = elem_bytes(dtype);
+  const uint32_t per_row = (uint32_t)(GM_ROW_BYTES / es);  // elements in 128 bytes
+  const size_t inner = v.mn_major ? v.mn : v.k, outer = v.mn_major ? v.k : v.mn;
+  const bool batched = nb > 1 && v.stride != 0;
+  cuuint64_t dims[3] = {inner, outer, batched ? nb : 1};
+  size_t bstride = batched ? v.stride * es : round_up(std::max<size_t>(outer, 1) * v.ld * es, 16);
+  cuuint64_t strides[2] = {v.ld * es, bstride};
+  // K-major: box = 128 bytes of K x box_rows rows; MN-major: 128 bytes of MN x `per_row` k-rows (one group)
+  cuuint32_t box[3] = {per_row, v.mn_major ? per_row : box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = dtype == SPFY_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == SPFY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, 3, const_cast<void*>(v.base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SPFY_E_CUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d): inner %zu outer %zu ld %zu batches %zu", (int)r,
+                inner, outer, v.ld, nb);
+  return SPFY_OK;
+}
+
+// column split of the Nu dimension: one tile when it fits a UMMA, equal tiles otherwise
+void split_nu(size_t nu, size_t gran, uint32_t* bn, uint32_t* n_tiles) {
+  size_t tiles = ceil_div(nu, (size_t)GM_MAX_BN);
+  size_t b = round_up(ceil_div(nu, tiles), gran);
+  if (b > (size_t)GM_MAX_BN) { b = GM_MAX_BN; }
+  *bn = (uint32_t)b;
+  *n_tiles = (uint32_t)ceil_div(nu, b);
+}
+
+struct Orientation {
+  OperandView a, b;  // Au, Bu
+  size_t mu, nu;
+  bool mu_contig;
+  uint32_t bn, n_tiles;
+  size_t padded;     // MACs per unit of K actually issued
+};
+
+// views of op(A) (extent m) and op(B)^T (extent n) of the column-major problem
+void blas_views(const TcGemmProblem& p, OperandView* va, OperandView* vb) {
+  // op(A)(i, kk): opA = N -> A is m x k, element i + kk*lda (MN-major); opA = T -> A is k x m, kk + i*lda (K-major)
+  *va = OperandView{p.A, p.m, p.k, p.lda, p.strideA, p.opA == SPFY_OP_N};
+  // op(B)(kk, j): opB = N -> B is k x n, element kk + j*ldb (K-major); opB = T -> B is n x k, j + kk*ldb (MN-major)
+  *vb = OperandView{p.B, p.n, p.k, p.ldb, p.strideB, p.opB != SPFY_OP_N};
+}
+
+Orientation orient(int dtype, const TcGemmProblem& p) {
+  OperandView va, vb;
+  blas_views(p, &va, &vb);
+  const size_t group = GM_ROW_BYTES / elem_bytes(dtype);
+  Orientation o[2];
+  // 0: Mu = m (C's contiguous dimension runs along TMEM lanes); 1: Mu = n
+  o[0].a = va; o[0].b = vb; o[0].mu = p.m; o[0].nu = p.n; o[0].mu_contig = true;
+  o[1].a = vb; o[1].b = va; o[1].mu = p.n; o[1].nu = p.m; o[1].mu_contig = false;
+  for (int i = 0; i < 2; ++i) {
+    split_nu(o[i].nu, o[i].b.mn_major ? group : 16, &o[i].bn, &o[i].n_tiles);
+    o[i].padded = round_up(o[i].mu, GM_BM) * (size_t)o[i].bn * o[i].n_tiles;
+  }
+  if (o[0].padded != o[1].padded) return o[0].padded < o[1].padded ? o[0] : o[1];
+  return o[0].mu >= o[1].mu ? o[0] : o[1];
+}
+
+int check_problem(int dtype, const TcGemmProblem& p, bool allow_repack) {
+  if (dtype != SPFY_F16 && dtype != SPFY_BF16 && dtype != SPFY_F32)
+    return fail(SPFY_E_UNSUPPORTED, "tc_gemm: dtype %d (need F16 / BF16 / F32)", dtype);
+  if ((p.opA != SPFY_OP_N && p.opA != SPFY_OP_T) || (p.opB != SPFY_OP_N && p.opB != SPFY_OP_T))
+    return fail(SPFY_E_INVALID, "tc_gemm: bad transpose flags %d %d", p.opA, p.opB);
+  if (p.m == 0 || p.n == 0 || p.nb == 0) return SPFY_OK;
+  if (p.k == 0) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: k == 0");
+  if (!p.A || !p.B || (!p.C && !p.c_ptrs)) return fail(SPFY_E_INVALID, "tc_gemm: null operand");
+  if (p.m >= (1ull << 31) || p.n >= (1ull << 31) || p.k >= (1ull << 31) || p.nb >= (1ull << 31))
+    return fail(SPFY_E_UNSUPPORTED, "tc_gemm: dimension too large");
+  if (p.ldc < p.m) return fail(SPFY_E_INVALID, "tc_gemm: ldc < m");
+  OperandView va, vb;
+  blas_views(p, &va, &vb);
+  if (va.ld < (va.mn_major ? va.mn : va.k) || vb.ld < (vb.mn_major ? vb.mn : vb.k))
+    return fail(SPFY_E_INVALID, "tc_gemm: leading dimension too small (lda %zu ldb %zu)", p.lda, p.ldb);
+  if (!allow_repack && (!operand_ok(dtype, va, p.nb) || !operand_ok(dtype, vb, p.nb)))
+    return fail(SPFY_E_UNSUPPORTED,
+                "tc_gemm: operands must be 16-byte aligned with leading dimensions / batch strides that are multiples "
+                "of 16 bytes (lda %zu ldb %zu strideA %zu strideB %zu)", p.lda, p.ldb, p.strideA, p.strideB);
+  return SPFY_OK;
+}
+
+int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p) {
+  memset(d, 0, sizeof(*d));
+  const Orientation o = orient(dtype, p);
+  int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM);
+  if (rc) return rc;
+  rc = make_operand_map(&d->tmap_b, dtype, o.b, p.nb, o.bn);
+  if (rc) return rc;
+  const size_t kel = GM_ROW_BYTES / elem_bytes(dtype);
+  d->C = (uint8_t*)p.C;
+  d->c_ptrs = reinterpret_cast<const uint64_t*>(p.c_ptrs);
+  d->ldc = p.ldc;
+  d->stride_c = p.strideC;
+  d->mu = (uint32_t)o.mu;
+  d->nu = (uint32_t)o.nu;
+  d->k = (uint32_t)p.k;
+  d->nb = (uint32_t)p.nb;
+  d->m_tiles = (uint32_t)ceil_div(o.mu, GM_BM);
+  d->n_tiles = o.n_tiles;
+  d->k_tiles = (uint32_t)ceil_div(p.k, kel);
+  d->bn = o.bn;
+  d->a_mn = o.a.mn_major;
+  d->b_mn = o.b.mn_major;
+  d->a_batched = p.nb > 1 && o.a.stride != 0;
+  d->b_batched = p.nb > 1 && o.b.stride != 0;
+  d->out_mu_contig = o.mu_contig;
+  d->alpha = p.alpha;
+  d->beta = p.beta;
+  const uint64_t units = (uint64_t)d->m_tiles * d->n_tiles * d->nb;
+  if (units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
+  d->units = (uint32_t)units;
+  return SPFY_OK;
+}
+
+template <int KIND>
+int launch_kind(const GemmProblemDev& single, const GemmLaunch& L, uint32_t smem, int grid, cudaStream_t s) {
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  SPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63].load()) {
+    SPFY_CUDA_OK(cudaFuncSetAttribute(tcgemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_LIMIT));
+    attr_set[dev & 63].store(1);
+  }
+  tcgemm_kernel<KIND><<<grid, GM_THREADS, smem, s>>>(single, L);
+  SPFY_LAUNCH_OK("tcgemm_kernel");
+  return SPFY_OK;
+}
+
+}  // namespace
+
+void warm_gemm_kernels() {
+  touch_kernel(tcgemm_kernel<KIND_F16>);
+  touch_kernel(tcgemm_kernel<KIND_BF16>);
+  touch_kernel(tcgemm_kernel<KIND_F32>);
+}
+
+int tc_gemm_supported(int dtype, const TcGemmProblem& p, bool allow_repack) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (di.cc_major != 10) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: needs an sm_100a device, found sm_%d%d", di.cc_major, di.cc_minor);
+  return check_problem(dtype, p, allow_repack);
+}
+
+static size_t table_bytes(size_t count) { return count > 1 ? round_up(count * sizeof(GemmProblemDev) + 64, 256) : 0; }
+
+size_t tc_gemm_workspace_bytes(int dtype, const TcGemmProblem* problems, size_t count) {
+  size_t need = table_bytes(count);
+  if (dtype != SPFY_F16 && dtype != SPFY_BF16 && dtype != SPFY_F32) return need;
+  for (size_t i = 0; i < count; ++i) {
+    OperandView va, vb;
+    blas_views(problems[i], &va, &vb);
+    need += repack_bytes(dtype, va, problems[i].nb) + repack_bytes(dtype, vb, problems[i].nb);
+  }
+  return need;
+}
+
+namespace {
+// padded copies made during one tc_gemm_run call (an operand shared by several problems is copied once)
+struct Repacked {
+  const void* src;
+  size_t inner, outer, ld, stride, batches;
+  const void* dst;
+};
+
+int repack_operand(int dtype, OperandView* v, size_t nb, uint8_t* ws, size_t ws_bytes, size_t* used,
+                   std::vector<Repacked>* done, cudaStream_t s) {
+  if (operand_ok(dtype, *v, nb)) return SPFY_OK;
+  const size_t es = elem_bytes(dtype), inner = v->mn_major ? v->mn : v->k, outer = v->mn_major ? v->k : v->mn;
+  const size_t batches = nb > 1 && v->stride ? nb : 1, ldp = padded_ld(dtype, *v);
+  for (const Repacked& r : *done)
+    if (r.src == v->base && r.inner == inner && r.outer == outer && r.ld == v->ld && r.stride == v->stride &&
+        r.batches == batches) {
+      v->base = r.dst; v->ld = ldp; v->stride = batches > 1 ? outer * ldp : 0;
+      return SPFY_OK;
+    }
+  const size_t bytes = repack_bytes(dtype, *v, nb);
+  if (!ws || *used + bytes > ws_bytes)
+    return fail(SPFY_E_WORKSPACE, "tc_gemm: workspace %zu < %zu bytes (padded copy of an operand TMA cannot address)",
+                ws_bytes, *used + bytes);
+  uint8_t* dst = ws + *used;
+  *used += bytes;
+  const size_t total = batches * outer * inner;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)std::min<size_t>(ceil_div(total, 256), (size_t)di.sm_count * 16);
+  if (es == 4)
+    repack_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)v->base, v->ld, v->stride, (uint32_t*)dst, ldp, outer * ldp,
+                                                inner, outer, batches);
+  else
+    repack_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)v->base, v->ld, v->stride, (uint16_t*)dst, ldp, outer * ldp,
+                                                inner, outer, batches);
+  SPFY_LAUNCH_OK("repack_kernel");
+  done->push_back(Repacked{v->base, inner, outer, v->ld, v->stride, batches, dst});
+  v->base = dst; v->ld = ldp; v->stride = batches > 1 ? outer * ldp : 0;
+  return SPFY_OK;
+}
+}  // namespace
+
+int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t count, void* ws, size_t ws_bytes,
+                cudaStream_t stream, const int* gate, int gate_run_if) {
+  if (count == 0) return SPFY_OK;
+  if (!problems) return fail(SPFY_E_INVALID, "tc_gemm: null problem list");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (di.cc_major != 10) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: needs an sm_100a device, found sm_%d%d", di.cc_major, di.cc_minor);
+  std::vector<GemmProblemDev> table;
+  table.reserve(count);
+  uint32_t units = 0, bn_max = 16;
+  // workspace: [device copy of the problem table (count > 1)][padded copies of operands TMA cannot address]
+  uint8_t* ws8 = (uint8_t*)ws;
+  const size_t ws_pad = ws8 ? (256 - (uintptr_t)ws8 % 256) % 256 : 0;
+  if (ws8 && ws_bytes >= ws_pad) { ws8 += ws_pad; ws_bytes -= ws_pad; } else { ws8 = nullptr; ws_bytes = 0; }
+  size_t ws_used = table_bytes(count);
+  std::vector<Repacked> repacked;
+  for (size_t i = 0; i < count; ++i) {
+    rc = check_problem(dtype, problems[i], true);
+    if (rc) return rc;
+    if (problems[i].m == 0 || problems[i].n == 0 || problems[i].nb == 0) continue;
+    TcGemmProblem q = problems[i];
+    {
+      OperandView va, vb;
+      blas_views(q, &va, &vb);
+      rc = repack_operand(dtype, &va, q.nb, ws8, ws_bytes, &ws_used, &repacked, stream);
+      if (rc) return rc;
+      rc = repack_operand(dtype, &vb, q.nb, ws8, ws_bytes, &ws_used, &repacked, stream);
+      if (rc) return rc;
+      q.A = va.base; q.lda = va.ld; q.strideA = va.stride;
+      q.B = vb.base; q.ldb = vb.ld; q.strideB = vb.stride;
+    }
+    GemmProblemDev d;
+    rc = fill_problem(&d, dtype, q);
+    if (rc) return rc;
+    d.unit_begin = units;
+    if ((uint64_t)units + d.units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
+    units += d.units;
+    bn_max = std::max(bn_max, d.bn);
+    table.push_back(d);
+  }
+  if (table.empty()) return SPFY_OK;
+
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  const bool f32 = dtype == SPFY_F32;
+  L.split = f32 && precision == TC_GEMM_PRECISE;
+  L.write_hi = 1;
+  if (const char* e = dev_switch("SPFY_GEMM_WRITE_HI")) L.write_hi = (uint32_t)atoi(e);
+  L.kelems = (uint32_t)(GM_ROW_BYTES / elem_bytes(dtype));
+  L.gate = gate;
+  L.gate_run_if = gate_run_if ? 1u : 0u;
+  L.raw_bytes = (uint32_t)GM_A_BYTES + bn_max * (uint32_t)GM_ROW_BYTES;
+  L.stage_bytes = L.raw_bytes * (L.split ? 2u : 1u);
+  uint32_t stages = (GM_SMEM_LIMIT - 1024u - GM_BAR_BYTES) / L.stage_bytes;
+  if (stages > (uint32_t)GM_MAX_STAGES) stages = GM_MAX_STAGES;
+  if (const char* e = dev_switch("SPFY_GEMM_STAGES")) {
+    const uint32_t c = (uint32_t)atoi(e);
+    if (c >= 1 && c < stages) stages = c;
+  }
+  if (stages < 2) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: tile does not fit shared memory");
+  L.stages = stages;
+  L.bar_off = stages * L.stage_bytes;
+  const uint32_t smem = L.bar_off + GM_BAR_BYTES + 1024u;
+  // instruction descriptor: D = F32; A / B format (F16 0, BF16 1, TF32 2); M = 128; N and majors per problem
+  const uint32_t fmt = f32 ? 2u : (dtype == SPFY_BF16 ? 1u : 0u);
+  L.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(GM_BM >> 4) << 24);
+  L.num_problems = (uint32_t)table.size();
+  L.total_units = units;
+  L.table = nullptr;
+  if (table.size() > 1) {
+    const size_t need = table.size() * sizeof(GemmProblemDev);
+    if (!ws8 || ws_bytes < table_bytes(count))
+      return fail(SPFY_E_WORKSPACE, "tc_gemm: workspace %zu < %zu bytes", ws_bytes, table_bytes(count));
+    // pageable source: the runtime stages the bytes before the call returns, so `table` may go out of scope
+    SPFY_CUDA_OK(cudaMemcpyAsync(ws8, table.data(), need, cudaMemcpyHostToDevice, stream));
+    L.table = reinterpret_cast<const GemmProblemDev*>(ws8);
+  }
+  const int grid = (int)std::min<uint32_t>(units, (uint32_t)di.sm_count);
+  if (f32) return launch_kind<KIND_F32>(table[0], L, smem, grid, stream);
+  if (dtype == SPFY_BF16) return launch_kind<KIND_BF16>(table[0], L, smem, grid, stream);
+  return launch_kind<KIND_F16>(table[0], L, smem, grid, stream);
+}
+
+}  // namespace spfy
+
+using namespace spfy;
+
+extern "C" {
+
+static TcGemmProblem make_problem(int opA, int opB, size_t m, size_t n, size_t k, float alpha, const void* A, size_t lda,
+                                  size_t strideA, const void* B, size_t ldb, size_t strideB, float beta, void* C,
+                                  size_t ldc, size_t strideC, size_t nb) {
+  TcGemmProblem p;
+  p.opA = opA; p.opB = opB; p.m = m; p.n = n; p.k = k; p.nb = nb;
+  p.A = A; p.lda = lda; p.strideA = strideA;
+  p.B = B; p.ldb = ldb; p.strideB = strideB;
+  p.C = C; p.ldc = ldc; p.strideC = strideC;
+  p.alpha = alpha; p.beta = beta;
+  return p;
+}
+
+int spfy_gemm_workspace_bytes(int dtype, int opA, int opB, size_t m, size_t n, size_t k, size_t lda, size_t ldb,
+                              size_t num_batches, size_t* bytes) {
+  // a table of num_batches problems (batched form) + a padded copy per batch element of every operand whose leading
+  // dimension TMA cannot address.  Bases are taken to be 16-byte aligned (cudaMalloc gives 256); pass lda = 0 /
+  // ldb = 0 to size for a misaligned base as well.
+  const size_t es = elem_bytes(dtype);
+  size_t need = 256 + (num_batches > 1 ? round_up(num_batches * sizeof(GemmProblemDev) + 64, 256) : 0);
+  const size_t a_inner = opA == SPFY_OP_N ? m : k, a_outer = opA == SPFY_OP_N ? k : m;
+  const size_t b_inner = opB == SPFY_OP_N ? k : n, b_outer = opB == SPFY_OP_N ? n : k;
+  if (lda == 0 || (lda * es) % 16) need += num_batches * round_up(a_outer * round_up(a_inner, 16 / es) * es, 256);
+  if (ldb == 0 || (ldb * es) % 16) need += num_batches * round_up(b_outer * round_up(b_inner, 16 / es) * es, 256);
+  if (bytes) *bytes = need;
+  return SPFY_OK;
+}
+
+int spfy_gemm_strided_batched(int dtype, int precision, int opA, int opB, size_t m, size_t n, size_t k, float alpha,
+                              const void* A, size_t lda, size_t strideA, const void* B, size_t ldb, size_t strideB,
+                              float beta, void* C, size_t ldc, size_t strideC, size_t num_batches, void* workspace,
+                              size_t workspace_bytes, spfy_stream_t stream) {
+  const TcGemmProblem p = make_problem(opA, opB, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+                                       num_batches);
+  return tc_gemm_run(dtype, precision, &p, 1, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int spfy_gemm_batched(int dtype, int precision, int opA, int opB, size_t m, size_t n, size_t k, float alpha,
+                      const void* const* A_ptrs, size_t lda, const void* const* B_ptrs, size_t ldb, float beta,
+                      void* const* C_ptrs, size_t ldc, size_t num_batches, void* workspace, size_t workspace_bytes,
+                      spfy_stream_t stream) {
+  if (num_batches == 0) return SPFY_OK;
+  if (!A_ptrs || !B_ptrs || !C_ptrs) return fail(SPFY_E_INVALID, "gemm_batched: null pointer array");
+  std::vector<TcGemmProblem> ps(num_batches);
+  for (size_t b = 0; b < num_batches; ++b)
+    ps[b] = make_problem(opA, opB, m, n, k, alpha, A_ptrs[b], lda, 0, B_ptrs[b], ldb, 0, beta, C_ptrs[b], ldc, 0, 1);
+  return tc_gemm_run(dtype, precision, ps.data(), ps.size(), workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

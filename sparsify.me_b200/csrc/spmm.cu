@@ -16,8 +16,10 @@
 // registers; the C tile goes back through shared memory so the column-major
 // stores are coalesced along rows.
 #include "common.cuh"
+#include "gemm_sm100.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace spfy {
 namespace {
@@ -351,12 +353,15 @@ struct SpmmDense {
   uint32_t m, k, n, num_batches;
   uint32_t kc;             // rows of B staged per chunk
   float alpha, beta;
+  const int* gate;         // device flag (null = run): work only if (*gate != 0) == gate_run_if
+  uint32_t gate_run_if;
 };
 
 template <typename T, typename Rows>
 __global__ void __launch_bounds__(SP_WARPS * 32, 1)
 spmm_rowsplit_kernel(const Rows A, const SpmmDense D) {
   extern __shared__ float sB[];  // [kc][SP_PAD]; reused as [SP_TN][SP_TM+1] for the C tile
+  if (D.gate && (*D.gate != 0) != (D.gate_run_if != 0)) return;  // another kernel handles this batch (device-side choice)
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_tiles = (D.m + SP_TM - 1) / SP_TM;
   const uint32_t col_tiles = (D.n + SP_TN - 1) / SP_TN;
@@ -499,7 +504,8 @@ struct CsrSpmmParams {
   const float* B;
   float* C;
   const int* sorted;        // device flag: columns ascend inside every row
-  const int* walk;          // device flag (null = run): 1 -> the dense-walk kernel runs, 0 -> the per-non-zero one
+  const int* gate;          // device flag (null = run): the kernel works only if (*gate != 0) == gate_run_if, so a
+  uint32_t gate_run_if;     // caller that leaves the kernel choice to the device launches every candidate
   size_t ldb, strideB, ldc, strideC;
   uint32_t m, k, n, num_batches;
   uint32_t row_tiles, col_tiles;  // col tiles over the num_batches * n columns
@@ -680,7 +686,7 @@ spmm_csr_kernel(const __grid_constant__ CsrSpmmParams P) {
   size_t* colB = reinterpret_cast<size_t*>(smem_f + CSR_TN * CSR_PITCH_PAIRS + CSR_SCRATCH_FLOATS);  // [CSR_TN]
   size_t* colC = colB + CSR_TN;                                                              // [CSR_TN]
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (P.walk && *P.walk != 0) return;  // this A is dense enough for spmm_dense_walk_kernel (launched next)
+  if (P.gate && (*P.gate != 0) != (P.gate_run_if != 0)) return;  // another kernel handles this A (device-side choice)
   const bool sorted = *P.sorted != 0;
   const uint32_t nnz_total = BELL ? P.ell_cols : (uint32_t)P.row_ptr[P.m];
   // CSR: the batch elements' columns form one long column axis; blocked-ELL: tiles are per batch element
@@ -952,7 +958,7 @@ spmm_dense_walk_kernel(const __grid_constant__ CsrSpmmParams P) {
   constexpr int TM = DW_WARPS * RPW;
   extern __shared__ __align__(16) float smem_f[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (P.walk && *P.walk == 0) return;  // sparse enough for spmm_csr_kernel (launched just before)
+  if (P.gate && (*P.gate != 0) != (P.gate_run_if != 0)) return;  // another kernel handles this A (device-side choice)
   float* const sB0 = smem_f;                                        // [2][CSR_TN][DW_PITCH]
   float* const sA = smem_f + 2 * CSR_TN * DW_PITCH + warp * RPW * DW_PITCH;  // this warp's strip [DW_KC][RPW]
   size_t* colB = reinterpret_cast<size_t*>(smem_f + 2 * CSR_TN * DW_PITCH + DW_WARPS * 16 * DW_PITCH);  // [CSR_TN]
@@ -1164,6 +1170,138 @@ int launch_spmm_csr(const CsrSpmmParams& P, int sm_count, cudaStream_t s) {
   return SPFY_OK;
 }
 
+// ------------------------------------------------------------------------
+// Tensor-core route of the unstructured SpMMs.  A ResNet weight matrix with 5-50 % non-zeros is far too dense to
+// beat a dense contraction by skipping zeros on CUDA cores: one shared-memory wavefront per FMA (the per-non-zero
+// kernel) or the fp32 pipe (the dense walk) cap at 7-13 TFLOP/s, whereas the dense 3xTF32 GEMM of gemm_sm100.cu
+// runs the whole M x K at fp32-level accuracy at a few hundred.  So the sparse operand is scattered into a dense
+// K-major matrix in the workspace (zero-filled; duplicates add, like cuSPARSE) and contracted on tcgen05.
+// ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+coo_scatter_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, const float* __restrict__ vals,
+                   size_t nnz, uint32_t m, uint32_t k, float* __restrict__ D, size_t ld) {
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += nthreads) {
+    const uint32_t r = (uint32_t)rows[i], c = (uint32_t)cols[i];
+    if (r < m && c < k) atomicAdd(D + (size_t)r * ld + c, vals[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+csr_scatter_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ cols, const float* __restrict__ vals,
+                   uint32_t m, uint32_t k, float* __restrict__ D, size_t ld) {
+  const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < m; r += warps) {
+    const int32_t b = row_ptr[r], e = row_ptr[r + 1];
+    for (int32_t i = b + (int32_t)lane; i < e; i += 32) {
+      const uint32_t c = (uint32_t)cols[i];
+      if (c < k) atomicAdd(D + (size_t)r * ld + c, vals[i]);
+    }
+  }
+}
+
+// blocked-ELL -> dense for `nbatch` matrices starting at batch `b0`, gather form: a warp owns one block-row.  It
+// first inverts the block-row's id list into shared memory (inv[block column] = position in the list, -1 = absent),
+// then writes all `block` dense rows left to right -- every dense element is written exactly once (zeros included),
+// so the target needs no memset and no atomics, and both the value reads (ids usually ascend) and the writes are
+// coalesced.  ids < 0 are padding, ids beyond the matrix are ignored.  A repeated id in one block-row (cuSPARSE
+// leaves that undefined; our CUDA-core kernel and the oracle add the blocks) cannot be expressed this way: it
+// raises *dup, and the caller's gated launches then let the CUDA-core kernel do the work instead.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bell_expand_kernel(const int64_t* const* __restrict__ col_ptrs, const void* const* __restrict__ val_ptrs, uint32_t b0,
+                   uint32_t nbatch, uint32_t rows, uint32_t cols, uint32_t ell_cols, uint32_t block, uint32_t bcols,
+                   uint32_t block_rows, uint32_t nbc, T* __restrict__ D, size_t ld, size_t stride, int* __restrict__ dup) {
+  extern __shared__ int32_t bell_inv[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int32_t* inv = bell_inv + (size_t)warp * nbc;
+  const size_t items = (size_t)nbatch * block_rows;
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  bool saw_dup = false;
+  // pairs of elements per lane when a pair can never straddle a block or an alignment boundary
+  const bool pairs = sizeof(T) <= 4 && block % 2 == 0 && ell_cols % 2 == 0 && ld % 2 == 0;
+  for (size_t item = (size_t)blockIdx.x * (blockDim.x >> 5) + warp; item < items; item += nwarps) {
+    const uint32_t b = (uint32_t)(item / block_rows), br = (uint32_t)(item - (size_t)b * block_rows);
+    for (uint32_t c = lane; c < nbc; c += 32) inv[c] = -1;
+    __syncwarp();
+    const int64_t* ids = col_ptrs[b0 + b] + (size_t)br * bcols;
+    for (uint32_t j = lane; j < bcols; j += 32) {
+      const int64_t id = ids[j];
+      if (id >= 0 && id < (int64_t)nbc) saw_dup |= atomicExch(&inv[id], (int32_t)j) != -1;
+    }
+    __syncwarp();
+    const T* vals = reinterpret_cast<const T*>(val_ptrs[b0 + b]);
+    T* out = D + (size_t)b * stride;
+    for (uint32_t r = 0; r < block; ++r) {
+      const uint32_t row = br * block + r;
+      if (row >= rows) break;
+      const T* src = vals + (size_t)row * ell_cols;
+      T* dst = out + (size_t)row * ld;
+      uint32_t done = 0;
+      if (pairs) {
+        using P2 = typename std::conditional<sizeof(T) == 4, float2, uint32_t>::type;
+        const uint32_t npairs = cols / 2;
+        for (uint32_t i = lane; i < npairs; i += 32) {
+          const uint32_t c = 2 * i;
+          const int32_t j = inv[c / block];
+          P2 v;
+          memset(&v, 0, sizeof(v));
+          if (j >= 0) v = *reinterpret_cast<const P2*>(src + (size_t)j * block + c % block);
+          *reinterpret_cast<P2*>(dst + c) = v;
+        }
+        done = npairs * 2;
+      }
+      for (uint32_t c = done + lane; c < cols; c += 32) {
+        const int32_t j = inv[c / block];
+        T v;
+        memset(&v, 0, sizeof(v));
+        if (j >= 0) v = src[(size_t)j * block + c % block];
+        dst[c] = v;
+      }
+    }
+    __syncwarp();
+  }
+  if (__any_sync(0xffffffffu, saw_dup) && lane == 0) atomicExch(dup, 1);
+}
+
+// density of non-zeros from which the tensor-core route is taken when the caller leaves the choice to the library:
+// dense 3xTF32 issues 3 x 2MKN tensor FLOPs at several hundred TFLOP/s, the per-non-zero kernel 2*nnz*N at ~7
+double tensor_density() {
+  static const double d = [] {
+    const char* e = dev_switch("SPFY_SPMM_TENSOR_DENSITY");
+    return e ? atof(e) : 0.02;
+  }();
+  return d;
+}
+
+size_t dense_ld(size_t k, size_t elem) { return round_up(k, 16 / elem); }  // TMA: row pitch multiple of 16 bytes
+
+constexpr size_t SPMM_FLAG_BYTES = 256;  // device words: [0] columns sorted, [1] dense-walk / tensor route, [2] dup ids
+
+size_t spmm_base_ws(size_t m) { return round_up((m + 1) * 4, 256) + SPMM_FLAG_BYTES; }
+
+// C_b[m x n] = alpha * A[m x k] * B_b[k x n] + beta * C_b with A given densely (row-major, pitch ld): the batches
+// are folded into the column dimension when the slabs are contiguous, so that a 196-column image does not leave a
+// quarter of every 128-row tile empty.
+TcGemmProblem coo_dense_problem(const float* dense, size_t ld, size_t m, size_t k, size_t n, size_t nb,
+                                const float* B, size_t ldb, size_t strideB, float* C, size_t ldc, size_t strideC,
+                                float alpha, float beta) {
+  TcGemmProblem p;
+  p.opA = SPFY_OP_T;  // the row-major m x k dense matrix is a column-major k x m one
+  p.opB = SPFY_OP_N;
+  p.m = m; p.k = k;
+  p.A = dense; p.lda = ld; p.strideA = 0;
+  p.B = B; p.ldb = ldb;
+  p.C = C; p.ldc = ldc;
+  p.alpha = alpha; p.beta = beta;
+  if (nb > 1 && strideB == ldb * n && strideC == ldc * n) {
+    p.n = n * nb; p.nb = 1;
+  } else {
+    p.n = n; p.nb = nb; p.strideB = strideB; p.strideC = strideC;
+  }
+  return p;
+}
+
 template <typename T>
 int threshold_impl(const void* in, size_t ld, size_t rows, size_t cols, float thr, int32_t* row_idx,
                    int32_t* col_idx, float* vals, size_t capacity, int64_t* d_nnz,
@@ -1203,6 +1341,11 @@ void spfy::warm_spmm_kernels() {
   touch_kernel(spmm_csr_kernel<8, SPMM_BELL_PAIRS>);
   touch_kernel(spmm_dense_walk_kernel<8, false>);
   touch_kernel(spmm_dense_walk_kernel<16, false>);
+  touch_kernel(coo_scatter_kernel);
+  touch_kernel(csr_scatter_kernel);
+  touch_kernel(bell_expand_kernel<float>);
+  touch_kernel(bell_expand_kernel<__half>);
+  touch_kernel(bell_expand_kernel<__nv_bfloat16>);
 }
 
 using namespace spfy;
@@ -1257,24 +1400,32 @@ int spfy_coo_to_csr(const int32_t* row_idx, size_t nnz, size_t rows, int32_t* ro
   return SPFY_OK;
 }
 
-int spfy_spmm_workspace_bytes(size_t m, size_t nnz, size_t* bytes) {
+static bool alg_ok(int alg) { return alg >= SPFY_SPMM_ALG_DEFAULT && alg <= SPFY_SPMM_ALG_TENSOR_FAST; }
+static bool alg_may_use_tensor(int alg) { return alg != SPFY_SPMM_ALG_CUDA_CORE; }
+
+int spfy_spmm_workspace_bytes(int alg, size_t m, size_t k, size_t nnz, size_t* bytes) {
   (void)nnz;
-  if (bytes) *bytes = round_up((m + 1) * 4, 256) + 256;  // row_ptr (COO entry) + the "sorted" word
+  if (!alg_ok(alg)) return fail(SPFY_E_INVALID, "spmm_workspace_bytes: bad algorithm %d", alg);
+  // row_ptr (COO entry) + the device flag words (+ the dense fp32 image of A for the tensor-core route)
+  size_t need = spmm_base_ws(m);
+  if (alg_may_use_tensor(alg)) need += round_up(m * dense_ld(k, 4) * sizeof(float), 256);
+  if (bytes) *bytes = need;
   return SPFY_OK;
 }
 
-// nnz_host < 0: the host does not know nnz (CSR entry) -- both kernels are launched and a device flag lets one run
-static int spmm_csr_impl(size_t m, size_t k, size_t n, size_t num_batches,
+// nnz_host < 0: the host does not know nnz (CSR entry) -- every candidate kernel is launched and device flags let one run
+static int spmm_csr_impl(int alg, size_t m, size_t k, size_t n, size_t num_batches,
                          const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
                          const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
                          size_t strideC, float alpha, float beta, void* workspace,
-                         size_t workspace_bytes, spfy_stream_t stream, long long nnz_host) {
+                         size_t workspace_bytes, spfy_stream_t stream, long long nnz_host,
+                         const int32_t* coo_rows) {
+  if (!alg_ok(alg)) return fail(SPFY_E_INVALID, "spmm_csr: bad algorithm %d", alg);
   if (m == 0 || n == 0 || num_batches == 0) return SPFY_OK;
   if (!row_ptr || !B || !C) return fail(SPFY_E_INVALID, "spmm_csr: null pointer");
-  size_t need = 0;
-  spfy_spmm_workspace_bytes(m, 0, &need);
-  if (!workspace || workspace_bytes < need)
-    return fail(SPFY_E_WORKSPACE, "spmm_csr: workspace %zu < %zu bytes", workspace_bytes, need);
+  const size_t base = spmm_base_ws(m);
+  if (!workspace || workspace_bytes < base)
+    return fail(SPFY_E_WORKSPACE, "spmm_csr: workspace %zu < %zu bytes", workspace_bytes, base);
   if (ldb < k || ldc < m) return fail(SPFY_E_INVALID, "spmm_csr: leading dimension too small");
   if (m >= (1ull << 31) || n >= (1ull << 31) || k >= (1ull << 31))
     return fail(SPFY_E_UNSUPPORTED, "spmm_csr: dimension too large");
@@ -1284,18 +1435,42 @@ static int spmm_csr_impl(size_t m, size_t k, size_t n, size_t num_batches,
   int rc = device_info(&di);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  // one device word: "columns ascend inside every row" (decides between cursor and rescan mode)
-  int* d_sorted = (int*)((uint8_t*)workspace + need - 256);
-  int* d_walk = d_sorted + 1;
+  int* d_sorted = (int*)((uint8_t*)workspace + base - SPMM_FLAG_BYTES);
+  int* d_dense = d_sorted + 1;  // 1 -> the dense route (tensor cores, else the CUDA-core dense walk) handles this A
+
+  // ---- tensor-core route: scatter A into a dense fp32 matrix and contract with 3xTF32 (or one TF32 product) ----
+  const size_t ld = dense_ld(k, 4);
+  const size_t dense_bytes = round_up(m * ld * sizeof(float), 256);
+  float* dense = reinterpret_cast<float*>((uint8_t*)workspace + base);
+  TcGemmProblem gp = coo_dense_problem(dense, ld, m, k, n, num_batches, B, ldb, strideB, C, ldc, strideC, alpha, beta);
+  bool tensor = false;
+  if (alg_may_use_tensor(alg)) {
+    const bool forced = alg != SPFY_SPMM_ALG_DEFAULT;
+    // (B_b is the big streamed operand here: a padded copy of it would cost a pass over all of B, so operands
+    // TMA cannot address -- k = 147 -- stay on the CUDA-core kernels)
+    int trc = workspace_bytes >= base + dense_bytes ? tc_gemm_supported(SPFY_F32, gp, false)
+                                                    : fail(SPFY_E_WORKSPACE, "spmm_csr: workspace %zu < %zu bytes for the "
+                                                           "tensor-core route", workspace_bytes, base + dense_bytes);
+    if (trc != SPFY_OK && forced) return trc;
+    tensor = trc == SPFY_OK;
+  }
+  const double dense_from = tensor ? (alg == SPFY_SPMM_ALG_DEFAULT ? tensor_density() : 0.0) : walk_density();
+  const double dense_nnz_f = dense_from * (double)m * (double)k;
+  const uint32_t dense_nnz = dense_nnz_f >= 4294967295.0 ? 0xffffffffu : (uint32_t)dense_nnz_f;
+  // host-side choice when nnz is known, device-side (flag) otherwise
+  const bool host_knows = nnz_host >= 0;
+  const bool run_dense = host_knows ? (unsigned long long)nnz_host >= dense_nnz && dense_nnz != 0xffffffffu
+                                    : dense_nnz != 0xffffffffu;
+  const bool run_sparse = host_knows ? !run_dense : dense_nnz != 0;
+  const bool gated = !host_knows && run_dense && run_sparse;
+
   SPFY_CUDA_OK(cudaMemsetAsync(d_sorted, 0xff, sizeof(int), s));
-  const double walk_nnz_f = walk_density() * (double)m * (double)k;
-  const uint32_t walk_nnz = walk_nnz_f >= 4294967295.0 ? 0xffffffffu : (uint32_t)walk_nnz_f + 1u;
-  {
+  if (run_sparse || (run_dense && !tensor)) {
     int grid = 1;
     rc = elementwise_grid(m * 32, &grid);
     if (rc) return rc;
-    csr_check_sorted_kernel<<<grid, 256, 0, s>>>(row_ptr, col_idx, (uint32_t)m, d_sorted,
-                                                 nnz_host < 0 ? d_walk : nullptr, walk_nnz);
+    csr_check_sorted_kernel<<<grid, 256, 0, s>>>(row_ptr, col_idx, (uint32_t)m, d_sorted, gated ? d_dense : nullptr,
+                                                 dense_nnz);
     SPFY_LAUNCH_OK("csr_check_sorted_kernel");
   }
   CsrSpmmParams P;
@@ -1313,116 +1488,233 @@ static int spmm_csr_impl(size_t m, size_t k, size_t n, size_t num_batches,
   P.row_tiles = (uint32_t)ceil_div(m, tall ? 128 : 64);
   if (col_tiles * P.row_tiles >= (1ull << 32)) return fail(SPFY_E_UNSUPPORTED, "spmm_csr: too many tiles");
   P.col_tiles = (uint32_t)col_tiles;
-  const bool run_sparse = nnz_host < 0 || (unsigned long long)nnz_host < walk_nnz;
-  const bool run_walk = nnz_host < 0 ? walk_nnz != 0xffffffffu : !run_sparse;
-  P.walk = nnz_host < 0 && run_walk ? d_walk : nullptr;
   if (run_sparse) {
+    P.gate = gated ? d_dense : nullptr;
+    P.gate_run_if = 0;
     rc = tall ? launch_spmm_csr<8, SPMM_CSR>(P, di.sm_count, s) : launch_spmm_csr<4, SPMM_CSR>(P, di.sm_count, s);
     if (rc) return rc;
   }
-  if (run_walk)
+  if (!run_dense) return SPFY_OK;
+  if (!tensor) {
+    P.gate = gated ? d_dense : nullptr;
+    P.gate_run_if = 1;
     return tall ? launch_spmm_dense_walk<16, false>(P, di.sm_count, s) : launch_spmm_dense_walk<8, false>(P, di.sm_count, s);
-  return SPFY_OK;
+  }
+  // (the memset and the scatter are not gated: a few MB at most, and a sparse A scatters next to nothing)
+  SPFY_CUDA_OK(cudaMemsetAsync(dense, 0, m * ld * sizeof(float), s));
+  {
+    int grid = 1;
+    if (coo_rows) {
+      rc = elementwise_grid((size_t)nnz_host, &grid);
+      if (rc) return rc;
+      if (nnz_host > 0) {
+        coo_scatter_kernel<<<grid, 256, 0, s>>>(coo_rows, col_idx, vals, (size_t)nnz_host, (uint32_t)m, (uint32_t)k, dense, ld);
+        SPFY_LAUNCH_OK("coo_scatter_kernel");
+      }
+    } else {
+      rc = elementwise_grid(m * 32, &grid);
+      if (rc) return rc;
+      csr_scatter_kernel<<<grid, 256, 0, s>>>(row_ptr, col_idx, vals, (uint32_t)m, (uint32_t)k, dense, ld);
+      SPFY_LAUNCH_OK("csr_scatter_kernel");
+    }
+  }
+  return tc_gemm_run(SPFY_F32, alg == SPFY_SPMM_ALG_TENSOR_FAST ? TC_GEMM_FAST : TC_GEMM_PRECISE, &gp, 1, nullptr, 0, s,
+                     gated ? d_dense : nullptr, 1);
 }
 
-int spfy_spmm_csr_strided_batched(size_t m, size_t k, size_t n, size_t num_batches,
+int spfy_spmm_csr_strided_batched(int alg, size_t m, size_t k, size_t n, size_t num_batches,
                                   const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
                                   const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
                                   size_t strideC, float alpha, float beta, void* workspace,
                                   size_t workspace_bytes, spfy_stream_t stream) {
-  return spmm_csr_impl(m, k, n, num_batches, row_ptr, col_idx, vals, B, ldb, strideB, C, ldc, strideC, alpha, beta,
-                       workspace, workspace_bytes, stream, -1);
+  return spmm_csr_impl(alg, m, k, n, num_batches, row_ptr, col_idx, vals, B, ldb, strideB, C, ldc, strideC, alpha, beta,
+                       workspace, workspace_bytes, stream, -1, nullptr);
 }
 
-int spfy_spmm_coo_strided_batched(size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,
+int spfy_spmm_coo_strided_batched(int alg, size_t m, size_t k, size_t nnz, size_t n, size_t num_batches,
                                   const int32_t* row_idx, const int32_t* col_idx, const float* vals,
                                   const float* B, size_t ldb, size_t strideB, float* C, size_t ldc,
                                   size_t strideC, float alpha, float beta, void* workspace,
                                   size_t workspace_bytes, spfy_stream_t stream) {
-  size_t need = 0;
-  spfy_spmm_workspace_bytes(m, nnz, &need);
-  if (!workspace || workspace_bytes < need)
-    return fail(SPFY_E_WORKSPACE, "spmm_coo: workspace %zu < %zu bytes", workspace_bytes, need);
+  if (!workspace || workspace_bytes < spmm_base_ws(m))
+    return fail(SPFY_E_WORKSPACE, "spmm_coo: workspace %zu < %zu bytes", workspace_bytes, spmm_base_ws(m));
   int rc = spfy_coo_to_csr(row_idx, nnz, m, (int32_t*)workspace, stream);
   if (rc) return rc;
-  return spmm_csr_impl(m, k, n, num_batches, (const int32_t*)workspace, col_idx, vals, B, ldb, strideB, C, ldc,
-                       strideC, alpha, beta, workspace, workspace_bytes, stream, (long long)nnz);
+  return spmm_csr_impl(alg, m, k, n, num_batches, (const int32_t*)workspace, col_idx, vals, B, ldb, strideB, C, ldc,
+                       strideC, alpha, beta, workspace, workspace_bytes, stream, (long long)nnz, row_idx);
 }
 
-int spfy_spmm_bell_batched(int dtype, size_t rows, size_t cols, size_t n, size_t block,
+// dense images of at most this many bytes are expanded at a time (the batch is processed in chunks)
+static const size_t BELL_DENSE_CHUNK_BYTES = (size_t)1 << 30;
+
+// room for the padded copy of the shared B when TMA cannot address it as given (ldb = k = 147), see gemm_sm100.cuh
+static size_t bell_gemm_ws(size_t cols, size_t n, size_t es) { return 512 + round_up(n * dense_ld(cols, es) * es, 256); }
+
+int spfy_spmm_bell_workspace_bytes(int alg, int dtype, size_t rows, size_t cols, size_t n, size_t num_batches,
+                                   size_t* bytes) {
+  if (!alg_ok(alg)) return fail(SPFY_E_INVALID, "spmm_bell_workspace_bytes: bad algorithm %d", alg);
+  const size_t es = dtype_bytes(dtype);
+  if (es != 2 && es != 4) return fail(SPFY_E_UNSUPPORTED, "spmm_bell_workspace_bytes: dtype %d", dtype);
+  size_t need = spmm_base_ws(rows);
+  if (alg_may_use_tensor(alg) && rows && cols && num_batches) {
+    need += bell_gemm_ws(cols, n, es);
+    const size_t mat = round_up(rows * dense_ld(cols, es) * es, 256);
+    size_t chunk = BELL_DENSE_CHUNK_BYTES / mat;
+    if (chunk < 1) chunk = 1;
+    if (chunk > num_batches) chunk = num_batches;
+    need += chunk * mat;
+  }
+  if (bytes) *bytes = need;
+  return SPFY_OK;
+}
+
+int spfy_spmm_bell_batched(int alg, int dtype, size_t rows, size_t cols, size_t n, size_t block,
                            size_t ell_cols, size_t num_batches, const int64_t* const* col_idx,
                            const void* const* values, const void* B, size_t ldb, void* const* Cs,
                            size_t ldc, float alpha, float beta, void* workspace, size_t workspace_bytes,
                            spfy_stream_t stream) {
+  if (!alg_ok(alg)) return fail(SPFY_E_INVALID, "spmm_bell: bad algorithm %d", alg);
   if (rows == 0 || n == 0 || num_batches == 0) return SPFY_OK;
   if (!col_idx || !values || !B || !Cs) return fail(SPFY_E_INVALID, "spmm_bell: null pointer");
   if (block == 0 || ell_cols % block) return fail(SPFY_E_INVALID, "spmm_bell: ell_cols must be a multiple of block");
   if (ldb < cols || ldc < rows) return fail(SPFY_E_INVALID, "spmm_bell: leading dimension too small");
-  if (dtype == SPFY_F32 && rows < (1ull << 31) && n < (1ull << 31) && cols < (1ull << 31) &&
-      ell_cols < (1ull << 31) && ceil_div(rows, 64) * ceil_div(n, CSR_TN) * num_batches < (1ull << 32)) {
-    // fp32 (what the reference driver instantiates, examples/spmm.cu:26): the shared-memory kernel of the
-    // CSR path with a blocked-ELL row source
-    size_t need = 0;
-    spfy_spmm_workspace_bytes(rows, 0, &need);
-    if (!workspace || workspace_bytes < need)
-      return fail(SPFY_E_WORKSPACE, "spmm_bell: workspace %zu < %zu bytes", workspace_bytes, need);
-    DeviceInfo di;
-    int rc = device_info(&di);
+  const size_t es = dtype_bytes(dtype);
+  if (es != 2 && es != 4) return fail(SPFY_E_UNSUPPORTED, "spmm_bell: dtype %d", dtype);
+  if (rows >= (1ull << 31) || n >= (1ull << 31) || cols >= (1ull << 31) || ell_cols >= (1ull << 31) ||
+      num_batches >= (1ull << 31) || ceil_div(rows, 64) * ceil_div(n, CSR_TN) * num_batches >= (1ull << 32))
+    return fail(SPFY_E_UNSUPPORTED, "spmm_bell: problem too large");
+  const size_t base = spmm_base_ws(rows);
+  if (!workspace || workspace_bytes < base)
+    return fail(SPFY_E_WORKSPACE, "spmm_bell: workspace %zu < %zu bytes", workspace_bytes, base);
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  int* d_sorted = (int*)((uint8_t*)workspace + base - SPMM_FLAG_BYTES);
+  int* d_dup = d_sorted + 2;
+  const size_t block_rows = ceil_div(rows, block), bcols = ell_cols / block, nbc = ceil_div(cols, block);
+
+  // ---- tensor-core route: expand a chunk of the batch into dense matrices, contract, next chunk ----
+  const size_t ld = dense_ld(cols, es);
+  const size_t mat = round_up(rows * ld * es, 256);
+  size_t chunk = 0;
+  bool tensor = false;
+  const size_t inv_bytes = 8 * nbc * sizeof(int32_t);  // 8 warps per CTA, one inverse map each
+  const size_t gws = bell_gemm_ws(cols, n, es);
+  if (alg_may_use_tensor(alg)) {
+    const bool forced = alg != SPFY_SPMM_ALG_DEFAULT;
+    chunk = workspace_bytes > base + gws ? (workspace_bytes - base - gws) / mat : 0;
+    if (chunk > num_batches) chunk = num_batches;
+    TcGemmProblem probe;
+    probe.opA = SPFY_OP_T; probe.opB = SPFY_OP_N;
+    probe.m = rows; probe.n = n; probe.k = cols; probe.nb = chunk ? chunk : 1;
+    probe.A = (uint8_t*)workspace + base + gws; probe.lda = ld; probe.strideA = mat / es;
+    probe.B = B; probe.ldb = ldb;
+    probe.c_ptrs = Cs; probe.ldc = ldc;
+    int trc = chunk ? tc_gemm_supported(dtype, probe, true)
+                    : fail(SPFY_E_WORKSPACE, "spmm_bell: workspace %zu < %zu bytes for the tensor-core route",
+                           workspace_bytes, base + gws + mat);
+    if (trc == SPFY_OK && inv_bytes > 200 * 1024)
+      trc = fail(SPFY_E_UNSUPPORTED, "spmm_bell: %zu block columns do not fit the expansion kernel", nbc);
+    if (trc != SPFY_OK && forced) return trc;
+    tensor = trc == SPFY_OK;
+  }
+
+  // CUDA-core launch over batches [b0, b0 + nbatch): the only route (gate == null) or the stand-in for block-rows
+  // with repeated ids (gated on *d_dup)
+  auto cuda_core = [&](size_t b0, size_t nbatch, const int* gate) -> int {
+    if (dtype == SPFY_F32) {
+      CsrSpmmParams P;
+      memset(&P, 0, sizeof(P));
+      P.B = (const float*)B; P.sorted = d_sorted;
+      P.ldb = ldb; P.ldc = ldc;
+      P.m = (uint32_t)rows; P.k = (uint32_t)cols; P.n = (uint32_t)n; P.num_batches = (uint32_t)nbatch;
+      P.alpha = alpha; P.beta = beta;
+      P.vec = ((uintptr_t)B % 16 == 0) && ldb % 4 == 0;
+      P.bell_cols = col_idx + b0; P.bell_vals = (const float* const*)values + b0; P.Cs = (float* const*)Cs + b0;
+      P.block = (uint32_t)block; P.ell_cols = (uint32_t)ell_cols; P.bcols = (uint32_t)bcols;
+      P.gate = gate; P.gate_run_if = 1;
+      const bool tall = rows > 64;
+      P.row_tiles = (uint32_t)ceil_div(rows, tall ? 128 : 64);
+      P.col_tiles = (uint32_t)ceil_div(n, CSR_TN);
+      if (block % 2 == 0 && ell_cols % 2 == 0 && cols % 2 == 0)
+        return tall ? launch_spmm_csr<8, SPMM_BELL_PAIRS>(P, di.sm_count, s)
+                    : launch_spmm_csr<4, SPMM_BELL_PAIRS>(P, di.sm_count, s);
+      return tall ? launch_spmm_csr<8, SPMM_BELL>(P, di.sm_count, s) : launch_spmm_csr<4, SPMM_BELL>(P, di.sm_count, s);
+    }
+    // 16-bit values without a tensor-core route (operands that miss the TMA contract, repeated ids): row-split kernel
+    SpmmDense D;
+    memset(&D, 0, sizeof(D));
+    D.B = B; D.C = nullptr; D.Cs = Cs + b0;
+    D.ldb = ldb; D.strideB = 0; D.ldc = ldc; D.strideC = 0;
+    D.m = (uint32_t)rows; D.k = (uint32_t)cols; D.n = (uint32_t)n; D.num_batches = (uint32_t)nbatch;
+    D.alpha = alpha; D.beta = beta;
+    D.gate = gate; D.gate_run_if = 1;
+    if (dtype == SPFY_F16) {
+      BellRows<__half> A{col_idx + b0, (const __half* const*)values + b0, (uint32_t)block, (uint32_t)ell_cols, (uint32_t)bcols};
+      return launch_spmm<__half, BellRows<__half>>(A, D, s);
+    }
+    BellRows<__nv_bfloat16> A{col_idx + b0, (const __nv_bfloat16* const*)values + b0, (uint32_t)block, (uint32_t)ell_cols,
+                              (uint32_t)bcols};
+    return launch_spmm<__nv_bfloat16, BellRows<__nv_bfloat16>>(A, D, s);
+  };
+
+  SPFY_CUDA_OK(cudaMemsetAsync(d_sorted, 0xff, sizeof(int), s));
+  SPFY_CUDA_OK(cudaMemsetAsync(d_dup, 0, sizeof(int), s));
+  if (bcols > 1 && dtype == SPFY_F32) {
+    // (the CUDA-core kernel's cursor mode needs to know whether the ids ascend; cheap next to the values)
+    int grid = 1;
+    rc = elementwise_grid(num_batches * block_rows * bcols, &grid);
     if (rc) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    int* d_sorted = (int*)((uint8_t*)workspace + need - 256);
-    SPFY_CUDA_OK(cudaMemsetAsync(d_sorted, 0xff, sizeof(int), s));
-    const size_t block_rows = ceil_div(rows, block), bcols = ell_cols / block;
-    if (bcols > 1) {
-      int grid = 1;
-      rc = elementwise_grid(num_batches * block_rows * bcols, &grid);
-      if (rc) return rc;
+    if (!tensor) {
       bell_check_sorted_kernel<<<grid, 256, 0, s>>>(col_idx, (uint32_t)block_rows, (uint32_t)bcols,
                                                    (uint32_t)num_batches, d_sorted);
       SPFY_LAUNCH_OK("bell_check_sorted_kernel");
+    } else {
+      SPFY_CUDA_OK(cudaMemsetAsync(d_sorted, 0, sizeof(int), s));  // stand-in launches rescan (always correct)
     }
-    CsrSpmmParams P;
-    memset(&P, 0, sizeof(P));
-    P.B = (const float*)B; P.sorted = d_sorted;
-    P.ldb = ldb; P.ldc = ldc;
-    P.m = (uint32_t)rows; P.k = (uint32_t)cols; P.n = (uint32_t)n; P.num_batches = (uint32_t)num_batches;
-    P.alpha = alpha; P.beta = beta;
-    P.vec = ((uintptr_t)B % 16 == 0) && ldb % 4 == 0;
-    P.bell_cols = col_idx; P.bell_vals = (const float* const*)values; P.Cs = (float* const*)Cs;
-    P.block = (uint32_t)block; P.ell_cols = (uint32_t)ell_cols; P.bcols = (uint32_t)bcols;
-    const bool tall = rows > 64;
-    P.row_tiles = (uint32_t)ceil_div(rows, tall ? 128 : 64);
-    P.col_tiles = (uint32_t)ceil_div(n, CSR_TN);
-    // (the dense walk loses here -- 570 vs 493 us on the reference driver's ell_cols = k / 2 construction,
-    // 79 vs 38 ms over the compare.csv table: every batch element brings its own A, so the strip is rebuilt
-    // per tile without being reused, and n is often below the 128-column tile)
-    if (block % 2 == 0 && ell_cols % 2 == 0 && cols % 2 == 0)
-      return tall ? launch_spmm_csr<8, SPMM_BELL_PAIRS>(P, di.sm_count, s)
-                  : launch_spmm_csr<4, SPMM_BELL_PAIRS>(P, di.sm_count, s);
-    return tall ? launch_spmm_csr<8, SPMM_BELL>(P, di.sm_count, s) : launch_spmm_csr<4, SPMM_BELL>(P, di.sm_count, s);
   }
-  SpmmDense D;
-  memset(&D, 0, sizeof(D));
-  D.B = B; D.C = nullptr; D.Cs = Cs;
-  D.ldb = ldb; D.strideB = 0; D.ldc = ldc; D.strideC = 0;
-  D.m = (uint32_t)rows; D.k = (uint32_t)cols; D.n = (uint32_t)n; D.num_batches = (uint32_t)num_batches;
-  D.alpha = alpha; D.beta = beta;
-  cudaStream_t s = (cudaStream_t)stream;
-  switch (dtype) {
-    case SPFY_F32: {
-      BellRows<float> A{col_idx, (const float* const*)values, (uint32_t)block, (uint32_t)ell_cols, (uint32_t)(ell_cols / block)};
-      return launch_spmm<float, BellRows<float>>(A, D, s);
-    }
-    case SPFY_F16: {
-      BellRows<__half> A{col_idx, (const __half* const*)values, (uint32_t)block, (uint32_t)ell_cols, (uint32_t)(ell_cols / block)};
-      return launch_spmm<__half, BellRows<__half>>(A, D, s);
-    }
-    case SPFY_BF16: {
-      BellRows<__nv_bfloat16> A{col_idx, (const __nv_bfloat16* const*)values, (uint32_t)block, (uint32_t)ell_cols, (uint32_t)(ell_cols / block)};
-      return launch_spmm<__nv_bfloat16, BellRows<__nv_bfloat16>>(A, D, s);
-    }
-    default: return fail(SPFY_E_UNSUPPORTED, "spmm_bell: dtype %d", dtype);
+  if (!tensor) return cuda_core(0, num_batches, nullptr);
+
+  uint8_t* gemm_ws = (uint8_t*)workspace + base;
+  uint8_t* dense = gemm_ws + gws;
+  const int precision = alg == SPFY_SPMM_ALG_TENSOR_FAST ? TC_GEMM_FAST : TC_GEMM_PRECISE;
+  for (size_t b0 = 0; b0 < num_batches; b0 += chunk) {
+    const size_t nbatch = std::min(chunk, num_batches - b0);
+    const size_t warps_needed = nbatch * block_rows;
+    const int grid = (int)std::min<size_t>(ceil_div(warps_needed, 8), (size_t)di.sm_count * 8);
+#define SPFY_BELL_EXPAND(T)                                                                                            \
+    do {                                                                                                                \
+      static std::atomic<int> attr_set[64];                                                                             \
+      int dev = 0;                                                                                                      \
+      SPFY_CUDA_OK(cudaGetDevice(&dev));                                                                                \
+      if (inv_bytes > 48 * 1024 && !attr_set[dev & 63].load()) {                                                        \
+        SPFY_CUDA_OK(cudaFuncSetAttribute(bell_expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        attr_set[dev & 63].store(1);                                                                                    \
+      }                                                                                                                 \
+      bell_expand_kernel<T><<<grid, 256, inv_bytes, s>>>(col_idx, values, (uint32_t)b0, (uint32_t)nbatch, (uint32_t)rows, \
+                                                        (uint32_t)cols, (uint32_t)ell_cols, (uint32_t)block,           \
+                                                        (uint32_t)bcols, (uint32_t)block_rows, (uint32_t)nbc,          \
+                                                        reinterpret_cast<T*>(dense), ld, mat / es, d_dup);             \
+    } while (0)
+    if (dtype == SPFY_F32) SPFY_BELL_EXPAND(float);
+    else if (dtype == SPFY_F16) SPFY_BELL_EXPAND(__half);
+    else SPFY_BELL_EXPAND(__nv_bfloat16);
+#undef SPFY_BELL_EXPAND
+    SPFY_LAUNCH_OK("bell_expand_kernel");
+    TcGemmProblem p;
+    p.opA = SPFY_OP_T; p.opB = SPFY_OP_N;  // row-major dense A_b = column-major k x m; B is k x n column-major
+    p.m = rows; p.n = n; p.k = cols; p.nb = nbatch;
+    p.A = dense; p.lda = ld; p.strideA = mat / es;
+    p.B = B; p.ldb = ldb; p.strideB = 0;
+    p.c_ptrs = Cs + b0; p.ldc = ldc;
+    p.alpha = alpha; p.beta = beta;
+    rc = tc_gemm_run(dtype, precision, &p, 1, gemm_ws, gws, s, d_dup, 0);
+    if (rc) return rc;
+    rc = cuda_core(b0, nbatch, d_dup);
+    if (rc) return rc;
   }
+  return SPFY_OK;
 }
 
 }  // extern "C"

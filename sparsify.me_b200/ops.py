@@ -40,6 +40,11 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _workspace(nbytes, device):
+    """caller-provided scratch for one call (256-byte aligned like every torch allocation)"""
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
 class _Timer:
     """cudaEvent pair on the current stream -- the reference's util::timer_t
     (include/sparsify.me/util/timer.hxx:24-55): begin/end record + synchronise."""
@@ -297,34 +302,36 @@ class batched:
 
     @staticmethod
     def strided_coo(a_num_rows, a_num_cols, a_nnz, b_num_rows, b_num_cols, num_batches, a_rows, a_cols,
-                    a_values, b, c, alpha=1.0, beta=0.0):
+                    a_values, b, c, alpha=1.0, beta=0.0, alg=capi.SPMM_ALG_DEFAULT):
         """batched::strided_coo (spmm.hxx:140-193): C_b = alpha*A*B_b + beta*C_b with ONE COO A
         (row-sorted), B_b = b[i] k x n column-major (ldb = k), C_b m x n column-major (ldc = m);
-        b and c are single slabs strided by ldb*n / ldc*n (:172,:175 intent).  Returns ms."""
+        b and c are single slabs strided by ldb*n / ldc*n (:172,:175 intent).  Returns ms.
+        `alg`: SPMM_ALG_* of spfy_b200.h (DEFAULT: tensor cores when A is dense enough to pay)."""
         assert b_num_rows == a_num_cols
         ldb, ldc = b_num_rows, a_num_rows
         wb = ctypes.c_size_t()
-        capi.spfy_spmm_workspace_bytes(a_num_rows, a_nnz, ctypes.byref(wb))
-        ws = torch.empty(max(wb.value, 16), dtype=torch.uint8, device=b.device)
+        capi.spfy_spmm_workspace_bytes(alg, a_num_rows, a_num_cols, a_nnz, ctypes.byref(wb))
+        ws = _workspace(wb.value, b.device)
         t = _Timer()
         t.begin()
-        capi.spfy_spmm_coo_strided_batched(a_num_rows, a_num_cols, a_nnz, b_num_cols, num_batches,
+        capi.spfy_spmm_coo_strided_batched(alg, a_num_rows, a_num_cols, a_nnz, b_num_cols, num_batches,
                                            _ptr(a_rows), _ptr(a_cols), _ptr(a_values), _ptr(b), ldb,
                                            ldb * b_num_cols, _ptr(c), ldc, ldc * b_num_cols,
                                            float(alpha), float(beta), _ptr(ws), ws.numel(), _stream())
         return t.end()
 
     @staticmethod
-    def csr(m, k, n, num_batches, row_ptr, col_idx, vals, b, c, alpha=1.0, beta=0.0):
+    def csr(m, k, n, num_batches, row_ptr, col_idx, vals, b, c, alpha=1.0, beta=0.0, alg=capi.SPMM_ALG_DEFAULT):
         wb = ctypes.c_size_t()
-        capi.spfy_spmm_workspace_bytes(m, col_idx.numel(), ctypes.byref(wb))
-        ws = torch.empty(max(wb.value, 16), dtype=torch.uint8, device=b.device)
-        capi.spfy_spmm_csr_strided_batched(m, k, n, num_batches, _ptr(row_ptr), _ptr(col_idx),
+        capi.spfy_spmm_workspace_bytes(alg, m, k, col_idx.numel(), ctypes.byref(wb))
+        ws = _workspace(wb.value, b.device)
+        capi.spfy_spmm_csr_strided_batched(alg, m, k, n, num_batches, _ptr(row_ptr), _ptr(col_idx),
                                            _ptr(vals), _ptr(b), k, k * n, _ptr(c), m, m * n,
                                            float(alpha), float(beta), _ptr(ws), ws.numel(), _stream())
 
     @staticmethod
-    def spmm(col_idx_list, values_list, b, c_list, m, n, k, block, ell_cols, alpha=1.0, beta=0.0):
+    def spmm(col_idx_list, values_list, b, c_list, m, n, k, block, ell_cols, alpha=1.0, beta=0.0,
+             alg=capi.SPMM_ALG_DEFAULT):
         """batched::spmm (spmm.hxx:30-138): per batch C_b = alpha*A_b*B + beta*C_b, A_b blocked-ELL
         (containers/ell.hxx:24-33), B k x n column-major shared, C_b m x n column-major.
         One launch covers every batch element (the reference fans out one host thread +
@@ -335,11 +342,45 @@ class batched:
         va = torch.tensor([t.data_ptr() for t in values_list], dtype=torch.int64, device=dev)
         cs = torch.tensor([t.data_ptr() for t in c_list], dtype=torch.int64, device=dev)
         wb = ctypes.c_size_t()
-        capi.spfy_spmm_workspace_bytes(m, 0, ctypes.byref(wb))
-        ws = torch.empty(max(wb.value, 16), dtype=torch.uint8, device=dev)
+        capi.spfy_spmm_bell_workspace_bytes(alg, _dtype_code(b), m, k, n, nb, ctypes.byref(wb))
+        ws = _workspace(wb.value, dev)
         t = _Timer()
         t.begin()
-        capi.spfy_spmm_bell_batched(_dtype_code(b), m, k, n, block, ell_cols, nb, _ptr(ci), _ptr(va),
+        capi.spfy_spmm_bell_batched(alg, _dtype_code(b), m, k, n, block, ell_cols, nb, _ptr(ci), _ptr(va),
                                     _ptr(b), k, _ptr(cs), m, float(alpha), float(beta), _ptr(ws), ws.numel(),
                                     _stream())
+        return t.end()
+
+
+    @staticmethod
+    def gemm(a, b, c, m, n, k, transpose_a=capi.OP_N, transpose_b=capi.OP_N, alpha=1.0, beta=0.0,
+             precision=capi.GEMM_PRECISE, strided=True):
+        """batched::gemm (gemm.hxx:25-195): column-major C_i[m x n] = alpha*op(A_i)*op(B_i) + beta*C_i on tcgen05
+        (fp16 / bf16: kind::f16; fp32: 3xTF32, or one TF32 product with precision=GEMM_FAST).
+        a: [nb, ...] slab of column-major operands (or a single matrix shared by the batch), same for b;
+        c: [nb, n, m] slab (column-major m x n per batch).  lda = m (k if transposed), ldb = k (n), ldc = m (:79-81).
+        strided=False goes through the pointer-array entry (what the header template calls).  Returns ms."""
+        nb = c.shape[0]
+        lda = m if transpose_a == capi.OP_N else k
+        ldb = k if transpose_b == capi.OP_N else n
+        sa = a.stride(0) if a.dim() == 3 and a.shape[0] == nb and nb > 1 else 0
+        sb = b.stride(0) if b.dim() == 3 and b.shape[0] == nb and nb > 1 else 0
+        t = _Timer()
+        wb = ctypes.c_size_t()
+        capi.spfy_gemm_workspace_bytes(_dtype_code(c), transpose_a, transpose_b, m, n, k, lda, ldb, nb, ctypes.byref(wb))
+        ws = _workspace(wb.value, c.device)
+        if strided:
+            t.begin()
+            capi.spfy_gemm_strided_batched(_dtype_code(c), precision, transpose_a, transpose_b, m, n, k, float(alpha),
+                                           _ptr(a), lda, sa, _ptr(b), ldb, sb, float(beta), _ptr(c), m, c.stride(0), nb,
+                                           _ptr(ws), ws.numel(), _stream())
+            return t.end()
+        es = a.element_size()
+        pa = (ctypes.c_void_p * nb)(*[a.data_ptr() + i * sa * es for i in range(nb)])
+        pb = (ctypes.c_void_p * nb)(*[b.data_ptr() + i * sb * es for i in range(nb)])
+        pc = (ctypes.c_void_p * nb)(*[c.data_ptr() + i * c.stride(0) * es for i in range(nb)])
+        t.begin()
+        capi.spfy_gemm_batched(_dtype_code(c), precision, transpose_a, transpose_b, m, n, k, float(alpha),
+                               ctypes.cast(pa, ctypes.c_void_p), lda, ctypes.cast(pb, ctypes.c_void_p), ldb, float(beta),
+                               ctypes.cast(pc, ctypes.c_void_p), m, nb, _ptr(ws), ws.numel(), _stream())
         return t.end()

@@ -745,39 +745,7 @@ def test_blocked_ell_sparse_rows(spfy, orc, cuda, block):
         assert np.allclose(c.cpu().numpy().astype(np.float64), want, rtol=2e-4, atol=2e-4)
 
 
-def test_unstructured_kernels_bit_exact_with_cusparse_golden(spfy, cuda):
-    """the CUDA path against what cuSPARSE returned for the reference's call sequences
-    (tests/golden/cusparse_*.npz; inputs exact in fp32, so any summation order gives the same bits)"""
-    import glob
-    import os
-    import sys
-    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    sys.path.insert(0, gold)
-    from make_golden import gen_f32
-    coo = sorted(glob.glob(os.path.join(gold, "cusparse_coo_*.npz")))
-    bell = sorted(glob.glob(os.path.join(gold, "cusparse_bell_*.npz")))
-    assert coo and bell
-    for path in coo:
-        z = np.load(path)
-        m, k, n, nb = int(z["m"]), int(z["k"]), int(z["n"]), int(z["nb"])
-        a = torch.from_numpy(gen_f32(1, m * k).reshape(m, k)).to(cuda)
-        B = torch.from_numpy(gen_f32(2, nb * n * k).reshape(nb, n, k)).to(cuda)
-        C = torch.from_numpy(gen_f32(3, nb * n * m).reshape(nb, n, m).copy()).to(cuda)
-        ri, ci, va, nnz = spfy.threshold_to_coo(a, float(z["thr"]))
-        assert nnz == int(z["nnz"])
-        spfy.batched.strided_coo(m, k, nnz, k, n, nb, ri, ci, va, B, C, alpha=float(z["alpha"]), beta=float(z["beta"]))
-        assert np.array_equal(C.cpu().numpy(), z["c"]), os.path.basename(path)
-    for path in bell:
-        z = np.load(path)
-        m, k, n, nb, block, ell_cols = (int(z[x]) for x in ("m", "k", "n", "nb", "block", "ell_cols"))
-        V = gen_f32(4, nb * m * ell_cols).reshape(nb, m, ell_cols)
-        B = torch.from_numpy(gen_f32(5, n * k).reshape(n, k)).to(cuda)
-        cis = [torch.from_numpy(np.ascontiguousarray(z["col_idx"][b])).to(cuda) for b in range(nb)]
-        vas = [torch.from_numpy(np.ascontiguousarray(V[b])).to(cuda) for b in range(nb)]
-        cs = [torch.zeros(n, m, dtype=torch.float32, device=cuda) for _ in range(nb)]
-        spfy.batched.spmm(cis, vas, B, cs, m, n, k, block, ell_cols)
-        for b in range(nb):
-            assert np.array_equal(cs[b].cpu().numpy(), z["c"][b]), os.path.basename(path)
+# (the cuSPARSE golden fixtures are checked for every SpMM route in tests/test_gpu_tensor.py)
 
 
 def test_launch_counter_moves(spfy, cuda):

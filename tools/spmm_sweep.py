@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--tag", default="")
     ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE comparator column")
+    ap.add_argument("--alg", default="DEFAULT", choices=["DEFAULT", "CUDA_CORE", "TENSOR", "TENSOR_FAST"],
+                    help="SPFY_SPMM_ALG_* of include/spfy_b200.h (DEFAULT: tcgen05 3xTF32 when A is dense enough to pay)")
     args = ap.parse_args()
     import torch
     spfy = ge.load_package()
@@ -42,6 +44,7 @@ def main():
     shapes = spfy.shapes.read_shapes(args.csv)
     cnt = collections.Counter((s.n, s.k, s.m) for s in shapes)  # (M, K, n = H*W)
     nb = args.batch
+    alg = getattr(spfy, "SPMM_ALG_" + args.alg)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cusp = os.path.join(ROOT, "oracle", "_ref", "cusparse_ref")  # comparator: cuSPARSE COO_ALG4 on the same GPU
     have_cusp = os.path.exists(cusp) and not args.no_cusparse
@@ -65,11 +68,16 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             thr_us = e0.elapsed_time(e1) / args.reps * 1e3
-            spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, cbuf)
+            try:
+                spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, cbuf, alg=alg)
+            except spfy.SpfyError:  # forced tensor route on an operand TMA cannot address (k = 147)
+                alg_here = spfy.SPMM_ALG_DEFAULT
+            else:
+                alg_here = alg
             torch.cuda.synchronize()
             e0.record()
             for _ in range(args.reps):
-                spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, cbuf)
+                spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, cbuf, alg=alg_here)
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / args.reps * 1e3
