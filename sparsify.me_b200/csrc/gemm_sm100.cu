@@ -79,6 +79,8 @@ struct GemmLaunch {
   uint32_t kelems;    // elements of K per stage (32 fp32 / 64 half)
   const int* gate;    // optional device word: the launch does its work only if (*gate != 0) == gate_run_if
   uint32_t gate_run_if;
+  uint32_t a_stages;  // 3xTF32 kernel: depth of the Au ring (raw tiles only; the Bu ring has `stages` slots)
+  uint32_t b_off;     // ... and where the Bu ring starts
 };
 
 struct GemmWalker {
@@ -110,6 +112,107 @@ template <int KIND> __device__ __forceinline__ typename OutT<KIND>::type f32_to_
 template <> __device__ __forceinline__ __half f32_to_out<KIND_F16>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 f32_to_out<KIND_BF16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ float f32_to_out<KIND_F32>(float v) { return v; }
+
+// Epilogue role (4 warps: TMEM lane quarter = warp & 3), shared by the two kernels: drains accumulator slot
+// job % slots (slot_cols columns apart) of every unit the CTA walks.
+template <int KIND>
+__device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base, uint32_t bar_acc_full, uint32_t bar_acc_empty,
+                                              uint32_t slots, uint32_t slot_cols, uint32_t warp, uint32_t lane) {
+  using out_t = typename OutT<KIND>::type;
+  const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter + 32)
+  uint32_t job = 0;
+  const GemmProblemDev* last = nullptr;
+  uint32_t m_tiles = 1, n_tiles = 1, bn = 0, mu = 0, nu = 0, unit_begin = 0, mu_contig = 1;
+  uint64_t ldc = 0, stride_c = 0;
+  uint8_t* Cbase = nullptr;
+  const uint64_t* c_ptrs = nullptr;
+  float alpha = 1.f, beta = 0.f;
+  for (; W.valid(); W.next(), ++job) {
+    const GemmProblemDev* P = W.current();
+    if (P != last) {
+      last = P;
+      m_tiles = P->m_tiles; n_tiles = P->n_tiles; bn = P->bn; mu = P->mu; nu = P->nu; unit_begin = P->unit_begin;
+      mu_contig = P->out_mu_contig; ldc = P->ldc; stride_c = P->stride_c; Cbase = P->C; c_ptrs = P->c_ptrs;
+      alpha = P->alpha; beta = P->beta;
+    }
+    const uint32_t local = W.u - unit_begin;
+    const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
+    const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
+    out_t* C = c_ptrs ? reinterpret_cast<out_t*>(c_ptrs[b]) : reinterpret_cast<out_t*>(Cbase) + (size_t)b * stride_c;
+    const uint32_t slot = job % slots;
+    const uint32_t row = mt * GM_BM + quarter * 32u + lane;  // index along Mu
+    const bool row_ok = row < mu;
+    const bool warp_ok = mt * GM_BM + quarter * 32u < mu;
+    mbar_wait(bar_acc_full + slot * 8, (job / slots) & 1u);
+    tc_fence_after();
+    const uint32_t chunks = (bn + 31u) / 32u;
+    for (uint32_t c = 0; c < chunks; ++c) {
+      const uint32_t col0 = nt * bn + c * 32u;  // index along Nu
+      const uint32_t ncols = min(32u, min(bn - c * 32u, nu > col0 ? nu - col0 : 0u));
+      uint32_t acc[32];
+      if (warp_ok && ncols) {
+        tmem_ld_x32(tmem_base + slot * slot_cols + c * 32u + ((quarter * 32u) << 16), acc);
+        tmem_wait_ld();
+      }
+      if (c + 1 == chunks) {
+        // accumulator fully read by this warp: hand the slot back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
+      }
+      if (!warp_ok || !ncols) continue;
+      if (mu_contig) {
+        // element (row, col) at row + col*ldc: a warp's 32 rows are one 128-byte (fp32) line per column
+        if (row_ok) {
+          out_t* dst = C + row + (size_t)col0 * ldc;
+          if (beta == 0.f) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j)
+              if (j < ncols) dst[(size_t)j * ldc] = f32_to_out<KIND>(alpha * __uint_as_float(acc[j]));
+          } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j)
+              if (j < ncols)
+                dst[(size_t)j * ldc] =
+                    f32_to_out<KIND>(alpha * __uint_as_float(acc[j]) + beta * out_to_f32<KIND>(dst[(size_t)j * ldc]));
+          }
+        }
+      } else if (row_ok) {
+        // element (row, col) at col + row*ldc: the thread owns up to 32 consecutive elements
+        out_t* dst = C + (size_t)row * ldc + col0;
+        constexpr uint32_t VEC = 16 / sizeof(out_t);  // elements per 16-byte store
+        const bool vec_ok = ncols == 32u && ((uintptr_t)dst % 16 == 0);
+        if (vec_ok) {
+#pragma unroll
+          for (uint32_t q = 0; q < 32 / VEC; ++q) {
+            float v[VEC];
+#pragma unroll
+            for (uint32_t x = 0; x < VEC; ++x) v[x] = alpha * __uint_as_float(acc[q * VEC + x]);
+            if (beta != 0.f) {
+              const uint4 old = *reinterpret_cast<const uint4*>(dst + q * VEC);
+              const out_t* o = reinterpret_cast<const out_t*>(&old);
+#pragma unroll
+              for (uint32_t x = 0; x < VEC; ++x) v[x] += beta * out_to_f32<KIND>(o[x]);
+            }
+            uint4 w;
+            out_t* wo = reinterpret_cast<out_t*>(&w);
+#pragma unroll
+            for (uint32_t x = 0; x < VEC; ++x) wo[x] = f32_to_out<KIND>(v[x]);
+            *reinterpret_cast<uint4*>(dst + q * VEC) = w;
+          }
+        } else {
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j)
+            if (j < ncols) {
+              float v = alpha * __uint_as_float(acc[j]);
+              if (beta != 0.f) v += beta * out_to_f32<KIND>(dst[j]);
+              dst[j] = f32_to_out<KIND>(v);
+            }
+        }
+      }
+    }
+  }
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(GM_THREADS, 1)
@@ -216,8 +319,11 @@ tcgemm_kernel(const __grid_constant__ GemmProblemDev single, const __grid_consta
     // K-major: rows of 128 bytes, 8-row atoms 1024 bytes apart, a k-step advances 32 bytes inside the swizzled row.
     // MN-major: 128-byte groups of MN, 8 k-rows per 1024-byte atom (SBO), groups `group_bytes` apart (LBO); a k-step
     // is umma_k k-rows = umma_k * 128 bytes.
+    // 32-bit MN-major operands exist in one shared-memory layout only: 128-byte rows of MN, 4 k-rows per 512-byte atom,
+    // 32-byte chunks XOR-ed with (k-row & 3) (TMA: SWIZZLE_128B_ATOM_32B)
     const uint64_t desc_k = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
-    const uint64_t desc_mn = make_smem_desc(0, group_bytes, 1024, LAYOUT_SW128);
+    const uint64_t desc_mn = KIND == KIND_F32 ? make_smem_desc(0, group_bytes, 512, LAYOUT_SW128_BASE32B)
+                                              : make_smem_desc(0, group_bytes, 1024, LAYOUT_SW128);
     const uint32_t step_mn = (umma_k * GM_ROW_BYTES) >> 4;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
@@ -301,100 +407,245 @@ tcgemm_kernel(const __grid_constant__ GemmProblemDev single, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 6-9) =====================
-    const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter + 32)
-    uint32_t job = 0;
+    gemm_epilogue<KIND>(W, tmem_base, bar_acc_full, bar_acc_empty, GM_ACC_SLOTS, GM_MAX_BN, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 operands at fp32-level accuracy (3xTF32) with the streamed operand in TENSOR MEMORY.
+//
+// Run from shared memory (the kernel above with `split`), 3xTF32 is bound by shared-memory bandwidth, not by the
+// tensor pipe or HBM: per 32-wide K slab the (128 + N) x 128 bytes of operands are written by TMA, read and
+// written twice over by the splitter (hi, lo) and read three times by the MMAs -- 7 passes at 128 B/clk
+// (measured: 2000 cycles per slab at N = 64 against 720 for HBM).  Here the splitter warps take the raw Au tile
+// out of shared memory ONCE, split it in registers and store hi and lo to tensor memory with tcgen05.st, and the
+// MMAs read Au from there (`tcgen05.mma [d], [a_tmem], b_desc`): shared memory carries the raw Au tile once and
+// the small Bu tile (weights: raw via TMA, hi / lo written in place, read by three MMAs per k-step).
+//
+//   warps 0, 10 producers: two rings with a producer warp each, so that the Au ring (raw 16 KiB tiles, up to 8 deep:
+//                          what is in flight from HBM) runs ahead of the 4-deep Bu ring the MMAs release
+//   warps 2-5   splitter : thread = one row of Au (TMEM lane): 32 values -> hi, lo -> TMEM slot of the Bu stage;
+//                          the Au slot is handed back as soon as it has been read; then Bu is split in place
+//   warp 1      MMA      : per k-step hi*lo, lo*hi, hi*hi; the commit frees the Bu stage and its TMEM slot
+//   warps 6-9   epilogue : as above
+// TMEM: two accumulator slots of 128 columns + 4 x (32 hi + 32 lo) columns of Au.  N per tile <= 128.
+// An MN-major Au tile is fetched unswizzled (a thread reads its row as 32 conflict-free 4-byte loads); an
+// MN-major Bu tile uses the 32B-base swizzle the tensor core requires of 32-bit MN-major operands.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TS_MAX_BN = 128;
+constexpr int TS_ACC_SLOTS = 2;
+constexpr int TS_A_COL = TS_ACC_SLOTS * TS_MAX_BN;  // first TMEM column of the Au ring
+constexpr int TS_B_STAGES = 4;                      // == TMEM Au slots (64 columns each)
+constexpr int TS_MAX_A_STAGES = 8;
+constexpr int TS_THREADS = GM_THREADS + 32;         // + warp 10: the Bu producer
+
+__global__ void __launch_bounds__(TS_THREADS, 1)
+tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_constant__ GemmLaunch L) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (L.gate && (*L.gate != 0) != (L.gate_run_if != 0)) return;
+
+  const uint32_t NA = L.a_stages, NB = L.stages;
+  const uint32_t bar_afull = smem_base + L.bar_off;                      // [TS_MAX_A_STAGES] producer -> splitter
+  const uint32_t bar_aempty = bar_afull + TS_MAX_A_STAGES * 8;           // [TS_MAX_A_STAGES] splitter -> producer
+  const uint32_t bar_bfull = bar_aempty + TS_MAX_A_STAGES * 8;           // [TS_B_STAGES] producer -> splitter
+  const uint32_t bar_ready = bar_bfull + TS_B_STAGES * 8;                // [TS_B_STAGES] splitter -> MMA
+  const uint32_t bar_bfree = bar_ready + TS_B_STAGES * 8;                // [TS_B_STAGES] MMA -> producer (and TMEM slot)
+  const uint32_t bar_acc_full = bar_bfree + TS_B_STAGES * 8;             // [TS_ACC_SLOTS]
+  const uint32_t bar_acc_empty = bar_acc_full + TS_ACC_SLOTS * 8;        // [TS_ACC_SLOTS]
+  const uint32_t tmem_ptr_off = L.bar_off + (2 * TS_MAX_A_STAGES + 3 * TS_B_STAGES + 2 * TS_ACC_SLOTS) * 8;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + tmem_ptr_off);
+
+  if (warp == 1 && lane == 0) {
+    for (uint32_t s = 0; s < (uint32_t)TS_MAX_A_STAGES; ++s) {
+      mbar_init(bar_afull + s * 8, 1);
+      mbar_init(bar_aempty + s * 8, GM_SPLIT_WARPS);
+    }
+    for (uint32_t s = 0; s < (uint32_t)TS_B_STAGES; ++s) {
+      mbar_init(bar_bfull + s * 8, 1);
+      mbar_init(bar_ready + s * 8, GM_SPLIT_WARPS);
+      mbar_init(bar_bfree + s * 8, 1);
+    }
+    for (int a = 0; a < TS_ACC_SLOTS; ++a) {
+      mbar_init(bar_acc_full + a * 8, 1);
+      mbar_init(bar_acc_empty + a * 8, GM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_base + tmem_ptr_off, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  GemmWalker W(&single, L);
+  constexpr uint32_t KEL = 32;                 // fp32 elements of K per stage (128 bytes)
+  constexpr uint32_t GROUP_BYTES = KEL * 128;  // one 32-wide MN group of an MN-major tile
+
+  if (warp == 0 || warp == 10) {
+    // ===================== producers: warp 0 streams Au, warp 10 streams Bu =====================
+    const bool leader = elect_one();
+    const bool is_a = warp == 0;
+    uint32_t st = 0, ph = 0;
+    const uint32_t depth = is_a ? NA : NB;
     const GemmProblemDev* last = nullptr;
-    uint32_t m_tiles = 1, n_tiles = 1, bn = 0, mu = 0, nu = 0, unit_begin = 0, mu_contig = 1;
-    uint64_t ldc = 0, stride_c = 0;
-    uint8_t* Cbase = nullptr;
-    const uint64_t* c_ptrs = nullptr;
-    float alpha = 1.f, beta = 0.f;
-    for (; W.valid(); W.next(), ++job) {
+    const CUtensorMap* tmap = nullptr;
+    uint32_t m_tiles = 1, n_tiles = 1, k_tiles = 0, bn = 0, mn = 0, bat = 0, unit_begin = 0;
+    for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
-        m_tiles = P->m_tiles; n_tiles = P->n_tiles; bn = P->bn; mu = P->mu; nu = P->nu; unit_begin = P->unit_begin;
-        mu_contig = P->out_mu_contig; ldc = P->ldc; stride_c = P->stride_c; Cbase = P->C; c_ptrs = P->c_ptrs;
-        alpha = P->alpha; beta = P->beta;
+        tmap = is_a ? &P->tmap_a : &P->tmap_b;
+        if (leader) prefetch_tmap(tmap);
+        m_tiles = uni(P->m_tiles); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); bn = uni(P->bn);
+        mn = uni(is_a ? P->a_mn : P->b_mn); bat = uni(is_a ? P->a_batched : P->b_batched);
+        unit_begin = uni(P->unit_begin);
       }
       const uint32_t local = W.u - unit_begin;
       const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
       const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
-      out_t* C = c_ptrs ? reinterpret_cast<out_t*>(c_ptrs[b]) : reinterpret_cast<out_t*>(Cbase) + (size_t)b * stride_c;
-      const uint32_t slot = job % GM_ACC_SLOTS;
-      const uint32_t row = mt * GM_BM + quarter * 32u + lane;  // index along Mu
-      const bool row_ok = row < mu;
-      const bool warp_ok = mt * GM_BM + quarter * 32u < mu;
-      mbar_wait(bar_acc_full + slot * 8, (job / GM_ACC_SLOTS) & 1u);
-      tc_fence_after();
-      const uint32_t chunks = (bn + 31u) / 32u;
-      for (uint32_t c = 0; c < chunks; ++c) {
-        const uint32_t col0 = nt * bn + c * 32u;  // index along Nu
-        const uint32_t ncols = min(32u, min(bn - c * 32u, nu > col0 ? nu - col0 : 0u));
-        uint32_t acc[32];
-        if (warp_ok && ncols) {
-          tmem_ld_x32(tmem_base + slot * (uint32_t)GM_MAX_BN + c * 32u + ((quarter * 32u) << 16), acc);
-          tmem_wait_ld();
-        }
-        if (c + 1 == chunks) {
-          // accumulator fully read by this warp: hand the slot back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
-        }
-        if (!warp_ok || !ncols) continue;
-        if (mu_contig) {
-          // element (row, col) at row + col*ldc: a warp's 32 rows are one 128-byte (fp32) line per column
-          if (row_ok) {
-            out_t* dst = C + row + (size_t)col0 * ldc;
-            if (beta == 0.f) {
-#pragma unroll
-              for (uint32_t j = 0; j < 32; ++j)
-                if (j < ncols) dst[(size_t)j * ldc] = f32_to_out<KIND>(alpha * __uint_as_float(acc[j]));
-            } else {
-#pragma unroll
-              for (uint32_t j = 0; j < 32; ++j)
-                if (j < ncols)
-                  dst[(size_t)j * ldc] =
-                      f32_to_out<KIND>(alpha * __uint_as_float(acc[j]) + beta * out_to_f32<KIND>(dst[(size_t)j * ldc]));
-            }
-          }
-        } else if (row_ok) {
-          // element (row, col) at col + row*ldc: the thread owns up to 32 consecutive elements
-          out_t* dst = C + (size_t)row * ldc + col0;
-          constexpr uint32_t VEC = 16 / sizeof(out_t);  // elements per 16-byte store
-          const bool vec_ok = ncols == 32u && ((uintptr_t)dst % 16 == 0);
-          if (vec_ok) {
-#pragma unroll
-            for (uint32_t q = 0; q < 32 / VEC; ++q) {
-              float v[VEC];
-#pragma unroll
-              for (uint32_t x = 0; x < VEC; ++x) v[x] = alpha * __uint_as_float(acc[q * VEC + x]);
-              if (beta != 0.f) {
-                const uint4 old = *reinterpret_cast<const uint4*>(dst + q * VEC);
-                const out_t* o = reinterpret_cast<const out_t*>(&old);
-#pragma unroll
-                for (uint32_t x = 0; x < VEC; ++x) v[x] += beta * out_to_f32<KIND>(o[x]);
-              }
-              uint4 w;
-              out_t* wo = reinterpret_cast<out_t*>(&w);
-#pragma unroll
-              for (uint32_t x = 0; x < VEC; ++x) wo[x] = f32_to_out<KIND>(v[x]);
-              *reinterpret_cast<uint4*>(dst + q * VEC) = w;
-            }
+      const int bc = bat ? (int)b : 0;
+      const uint32_t row0 = is_a ? mt * (uint32_t)GM_BM : nt * bn, rows = is_a ? (uint32_t)GM_BM : bn;
+      const uint64_t hint = is_a ? HINT_EVICT_NORMAL : HINT_EVICT_LAST;  // Au streams from HBM, Bu is re-read by every tile
+      for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+        mbar_wait((is_a ? bar_aempty : bar_bfree) + st * 8, ph ^ 1u);
+        const uint32_t full = (is_a ? bar_afull : bar_bfull) + st * 8;
+        const uint32_t dst = is_a ? smem_base + st * (uint32_t)GM_A_BYTES : smem_base + L.b_off + st * L.stage_bytes;
+        if (leader) {
+          mbar_expect_tx(full, rows * (uint32_t)GM_ROW_BYTES);
+          if (!mn) {
+            tma_load_3d(dst, tmap, (int)(kt * KEL), (int)row0, bc, full, hint);
           } else {
-#pragma unroll
-            for (uint32_t j = 0; j < 32; ++j)
-              if (j < ncols) {
-                float v = alpha * __uint_as_float(acc[j]);
-                if (beta != 0.f) v += beta * out_to_f32<KIND>(dst[j]);
-                dst[j] = f32_to_out<KIND>(v);
-              }
+            for (uint32_t g = 0; g * KEL < rows; ++g)
+              tma_load_3d(dst + g * GROUP_BYTES, tmap, (int)(row0 + g * KEL), (int)(kt * KEL), bc, full, hint);
           }
         }
+        if (++st == depth) { st = 0; ph ^= 1u; }
       }
     }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint32_t tmem_b = uni(tmem_base);
+    uint32_t sb = 0, phb = 0, job = 0;
+    const GemmProblemDev* last = nullptr;
+    uint32_t k_tiles = 0, pk = 0, bn = 0, b_mn = 0;
+    const uint32_t lo_off = L.raw_bytes >> 4;  // Bu lo tile sits raw_bytes behind the hi one (16-byte units)
+    const uint64_t desc_k = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+    const uint64_t desc_mn = make_smem_desc(0, GROUP_BYTES, 512, LAYOUT_SW128_BASE32B);
+    for (; W.valid(); W.next()) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) {
+        last = P;
+        k_tiles = uni(P->k_tiles); pk = uni(P->k); bn = uni(P->bn); b_mn = uni(P->b_mn);
+      }
+      const uint32_t slot = job % TS_ACC_SLOTS, use = job / TS_ACC_SLOTS;
+      mbar_wait(bar_acc_empty + slot * 8, (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_b + slot * (uint32_t)TS_MAX_BN;
+      const uint32_t idesc = L.idesc | (b_mn << 16) | ((bn >> 3) << 17);  // the A operand in TMEM is K-major by construction
+      const uint64_t db_hi = b_mn ? desc_mn : desc_k;
+      const uint32_t b_step = b_mn ? (8u * GM_ROW_BYTES) >> 4 : 2u;       // 8 k-rows of 128 bytes / 32 bytes inside the row
+      uint32_t k_left = pk;
+      for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= KEL) {
+        mbar_wait(bar_ready + sb * 8, phb);
+        tc_fence_after();
+        const uint32_t b0 = ((smem_base + L.b_off + sb * L.stage_bytes) >> 4) & 0x3fffu;
+        const uint32_t ta = tmem_b + (uint32_t)TS_A_COL + sb * 64u;
+        const uint32_t nk = k_left >= KEL ? 4u : (k_left + 7u) / 8u;
+        if (leader) {
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            if (j < nk) {
+              const uint64_t db = db_hi | (uint64_t)(b0 + b_step * j);
+              const uint32_t a_hi = ta + 8u * j, a_lo = a_hi + 32u;
+              tc_mma_tf32_ts(tmem_d, a_hi, db + lo_off, idesc, (kt | j) ? 1u : 0u);  // hi * lo
+              tc_mma_tf32_ts(tmem_d, a_lo, db, idesc, 1u);                           // lo * hi
+              tc_mma_tf32_ts(tmem_d, a_hi, db, idesc, 1u);                           // hi * hi
+            }
+          }
+          tc_commit(bar_bfree + sb * 8);
+        }
+        if (++sb == NB) { sb = 0; phb ^= 1u; }
+      }
+      if (leader) tc_commit(bar_acc_full + slot * 8);
+      ++job;
+    }
+  } else if (warp < 2 + GM_SPLIT_WARPS) {
+    // ===================== splitter =====================
+    const uint32_t t = threadIdx.x - 64u;
+    const uint32_t row = (warp & 3u) * 32u + lane;  // the TMEM lane quarter a warp may touch is warp % 4
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    const GemmProblemDev* last = nullptr;
+    uint32_t k_tiles = 0, bn = 0, a_mn = 0;
+    const uint32_t raw = L.raw_bytes;
+    for (; W.valid(); W.next()) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) { last = P; k_tiles = P->k_tiles; bn = P->bn; a_mn = P->a_mn; }
+      for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+        // ---- Au: my row of the raw tile -> registers; the slot goes back to the producer at once ----
+        mbar_wait(bar_afull + sa * 8, pha);
+        const uint32_t src = smem_base + sa * (uint32_t)GM_A_BYTES;
+        uint32_t x[32], h[32];
+        if (!a_mn) {
+          // K-major, 128B-swizzled: chunk c of row r at (c ^ (r & 7)) * 16 -- 8 lanes cover all banks
+          const uint32_t rbase = src + row * 128u, sw = row & 7u;
+#pragma unroll
+          for (uint32_t c = 0; c < 8; ++c) {
+            const uint4 v = ld_shared_v4(rbase + ((c ^ sw) << 4));
+            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+          }
+        } else {
+          // MN-major, unswizzled groups of 32 rows: k-row kk at kk*128, my element at (row % 32) * 4
+          const uint32_t rbase = src + (row >> 5) * GROUP_BYTES + (row & 31u) * 4u;
+#pragma unroll
+          for (uint32_t kk = 0; kk < 32; ++kk) x[kk] = ld_shared_u32(rbase + kk * 128u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_aempty + sa * 8);
+        if (++sa == NA) { sa = 0; pha ^= 1u; }
+        // hi = x rounded to the nearest TF32 (the tensor core reads it exactly), lo = x - hi (exact in fp32)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h[i] = (x[i] + 0x1000u) & 0xffffe000u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __float_as_uint(__uint_as_float(x[i]) - __uint_as_float(h[i]));
+        // ---- the Bu stage (and with it the TMEM slot: both are released by the same commit) ----
+        mbar_wait(bar_bfull + sb * 8, phb);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + (uint32_t)TS_A_COL + sb * 64u + (((warp & 3u) * 32u) << 16);
+        tmem_st_x32(ta, h);
+        tmem_st_x32(ta + 32u, x);
+        const uint32_t sbase = smem_base + L.b_off + sb * L.stage_bytes;
+        const uint32_t used = bn * (uint32_t)GM_ROW_BYTES;
+#pragma unroll 4
+        for (uint32_t off = t * 16u; off < used; off += GM_SPLIT_WARPS * 32u * 16u) {
+          const uint4 v = ld_shared_v4(sbase + off);
+          const uint32_t h0 = (v.x + 0x1000u) & 0xffffe000u, h1 = (v.y + 0x1000u) & 0xffffe000u;
+          const uint32_t h2 = (v.z + 0x1000u) & 0xffffe000u, h3 = (v.w + 0x1000u) & 0xffffe000u;
+          const float l0 = __uint_as_float(v.x) - __uint_as_float(h0), l1 = __uint_as_float(v.y) - __uint_as_float(h1);
+          const float l2 = __uint_as_float(v.z) - __uint_as_float(h2), l3 = __uint_as_float(v.w) - __uint_as_float(h3);
+          st_shared_v4(sbase + raw + off, __float_as_uint(l0), __float_as_uint(l1), __float_as_uint(l2), __float_as_uint(l3));
+          st_shared_v4(sbase + off, h0, h1, h2, h3);
+        }
+        tmem_wait_st();
+        fence_proxy_async_smem();  // generic-proxy writes of Bu -> visible to the tensor core's async-proxy reads
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready + sb * 8);
+        if (++sb == NB) { sb = 0; phb ^= 1u; }
+      }
+    }
+  } else {  // warps 6-9
+    gemm_epilogue<KIND_F32>(W, tmem_base, bar_acc_full, bar_acc_empty, TS_ACC_SLOTS, TS_MAX_BN, warp, lane);
   }
 
   tc_fence_before();
@@ -452,7 +703,8 @@ size_t repack_bytes(int dtype, const OperandView& v, size_t nb) {
   return round_up(batches * outer * padded_ld(dtype, v) * elem_bytes(dtype), 256);
 }
 
-int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t nb, uint32_t box_rows) {
+int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t nb, uint32_t box_rows,
+                     CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc0;
   int rc = get_encoder(&enc0);
   if (rc) return rc;
@@ -471,7 +723,7 @@ int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t n
                                  : dtype == SPFY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = enc(map, dt, 3, const_cast<void*>(v.base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(SPFY_E_CUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d): inner %zu outer %zu ld %zu batches %zu", (int)r,
                 inner, outer, v.ld, nb);
@@ -479,10 +731,10 @@ int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t n
 }
 
 // column split of the Nu dimension: one tile when it fits a UMMA, equal tiles otherwise
-void split_nu(size_t nu, size_t gran, uint32_t* bn, uint32_t* n_tiles) {
-  size_t tiles = ceil_div(nu, (size_t)GM_MAX_BN);
+void split_nu(size_t nu, size_t gran, size_t max_bn, uint32_t* bn, uint32_t* n_tiles) {
+  size_t tiles = ceil_div(nu, max_bn);
   size_t b = round_up(ceil_div(nu, tiles), gran);
-  if (b > (size_t)GM_MAX_BN) { b = GM_MAX_BN; }
+  if (b > max_bn) { b = max_bn; }
   *bn = (uint32_t)b;
   *n_tiles = (uint32_t)ceil_div(nu, b);
 }
@@ -503,7 +755,7 @@ void blas_views(const TcGemmProblem& p, OperandView* va, OperandView* vb) {
   *vb = OperandView{p.B, p.n, p.k, p.ldb, p.strideB, p.opB != SPFY_OP_N};
 }
 
-Orientation orient(int dtype, const TcGemmProblem& p) {
+Orientation orient(int dtype, const TcGemmProblem& p, size_t max_bn) {
   OperandView va, vb;
   blas_views(p, &va, &vb);
   const size_t group = GM_ROW_BYTES / elem_bytes(dtype);
@@ -512,7 +764,7 @@ Orientation orient(int dtype, const TcGemmProblem& p) {
   o[0].a = va; o[0].b = vb; o[0].mu = p.m; o[0].nu = p.n; o[0].mu_contig = true;
   o[1].a = vb; o[1].b = va; o[1].mu = p.n; o[1].nu = p.m; o[1].mu_contig = false;
   for (int i = 0; i < 2; ++i) {
-    split_nu(o[i].nu, o[i].b.mn_major ? group : 16, &o[i].bn, &o[i].n_tiles);
+    split_nu(o[i].nu, o[i].b.mn_major ? group : 16, max_bn, &o[i].bn, &o[i].n_tiles);
     o[i].padded = round_up(o[i].mu, GM_BM) * (size_t)o[i].bn * o[i].n_tiles;
   }
   if (o[0].padded != o[1].padded) return o[0].padded < o[1].padded ? o[0] : o[1];
@@ -541,12 +793,19 @@ int check_problem(int dtype, const TcGemmProblem& p, bool allow_repack) {
   return SPFY_OK;
 }
 
-int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p) {
+// `ts`: the 3xTF32 kernel with Au in tensor memory (tiles of at most TS_MAX_BN columns)
+int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts) {
   memset(d, 0, sizeof(*d));
-  const Orientation o = orient(dtype, p);
-  int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM);
+  const Orientation o = orient(dtype, p, ts ? TS_MAX_BN : GM_MAX_BN);
+  // K-major tiles and 16-bit MN-major tiles: 128-byte swizzle.  32-bit MN-major tiles: the tensor core reads them in
+  // the 32B-base swizzle only; the 3xTF32 kernel reads its Au tile with ordinary loads and wants it unswizzled.
+  const bool f32 = dtype == SPFY_F32;
+  const CUtensorMapSwizzle sw_a = !(f32 && o.a.mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : ts ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const CUtensorMapSwizzle sw_b = f32 && o.b.mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM, sw_a);
   if (rc) return rc;
-  rc = make_operand_map(&d->tmap_b, dtype, o.b, p.nb, o.bn);
+  rc = make_operand_map(&d->tmap_b, dtype, o.b, p.nb, o.bn, sw_b);
   if (rc) return rc;
   const size_t kel = GM_ROW_BYTES / elem_bytes(dtype);
   d->C = (uint8_t*)p.C;
@@ -588,9 +847,23 @@ int launch_kind(const GemmProblemDev& single, const GemmLaunch& L, uint32_t smem
   return SPFY_OK;
 }
 
+int launch_ts(const GemmProblemDev& single, const GemmLaunch& L, uint32_t smem, int grid, cudaStream_t s) {
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  SPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63].load()) {
+    SPFY_CUDA_OK(cudaFuncSetAttribute(tcgemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_LIMIT));
+    attr_set[dev & 63].store(1);
+  }
+  tcgemm_ts_kernel<<<grid, TS_THREADS, smem, s>>>(single, L);
+  SPFY_LAUNCH_OK("tcgemm_ts_kernel");
+  return SPFY_OK;
+}
+
 }  // namespace
 
 void warm_gemm_kernels() {
+  touch_kernel(tcgemm_ts_kernel);
   touch_kernel(tcgemm_kernel<KIND_F16>);
   touch_kernel(tcgemm_kernel<KIND_BF16>);
   touch_kernel(tcgemm_kernel<KIND_F32>);
@@ -671,6 +944,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
   std::vector<GemmProblemDev> table;
   table.reserve(count);
   uint32_t units = 0, bn_max = 16;
+  const bool ts = dtype == SPFY_F32 && precision == TC_GEMM_PRECISE && !dev_switch("SPFY_GEMM_NO_TMEM_A");
   // workspace: [device copy of the problem table (count > 1)][padded copies of operands TMA cannot address]
   uint8_t* ws8 = (uint8_t*)ws;
   const size_t ws_pad = ws8 ? (256 - (uintptr_t)ws8 % 256) % 256 : 0;
@@ -693,7 +967,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
       q.B = vb.base; q.ldb = vb.ld; q.strideB = vb.stride;
     }
     GemmProblemDev d;
-    rc = fill_problem(&d, dtype, q);
+    rc = fill_problem(&d, dtype, q, ts);
     if (rc) return rc;
     d.unit_begin = units;
     if ((uint64_t)units + d.units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
@@ -712,18 +986,36 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
   L.kelems = (uint32_t)(GM_ROW_BYTES / elem_bytes(dtype));
   L.gate = gate;
   L.gate_run_if = gate_run_if ? 1u : 0u;
-  L.raw_bytes = (uint32_t)GM_A_BYTES + bn_max * (uint32_t)GM_ROW_BYTES;
-  L.stage_bytes = L.raw_bytes * (L.split ? 2u : 1u);
-  uint32_t stages = (GM_SMEM_LIMIT - 1024u - GM_BAR_BYTES) / L.stage_bytes;
-  if (stages > (uint32_t)GM_MAX_STAGES) stages = GM_MAX_STAGES;
-  if (const char* e = dev_switch("SPFY_GEMM_STAGES")) {
-    const uint32_t c = (uint32_t)atoi(e);
-    if (c >= 1 && c < stages) stages = c;
+  uint32_t smem = 0;
+  if (ts) {
+    // [Au ring: a_stages x 16 KiB][Bu ring: 4 x (hi | lo)][barriers]
+    L.raw_bytes = bn_max * (uint32_t)GM_ROW_BYTES;
+    L.stage_bytes = 2u * L.raw_bytes;
+    L.stages = TS_B_STAGES;
+    uint32_t a_stages = (GM_SMEM_LIMIT - 1024u - GM_BAR_BYTES - L.stages * L.stage_bytes) / (uint32_t)GM_A_BYTES;
+    if (a_stages > (uint32_t)TS_MAX_A_STAGES) a_stages = TS_MAX_A_STAGES;
+    if (const char* e = dev_switch("SPFY_GEMM_STAGES")) {
+      const uint32_t c = (uint32_t)atoi(e);
+      if (c >= 1 && c < a_stages) a_stages = c;
+    }
+    L.a_stages = a_stages;
+    L.b_off = a_stages * (uint32_t)GM_A_BYTES;
+    L.bar_off = L.b_off + L.stages * L.stage_bytes;
+    smem = L.bar_off + GM_BAR_BYTES + 1024u;
+  } else {
+    L.raw_bytes = (uint32_t)GM_A_BYTES + bn_max * (uint32_t)GM_ROW_BYTES;
+    L.stage_bytes = L.raw_bytes * (L.split ? 2u : 1u);
+    uint32_t stages = (GM_SMEM_LIMIT - 1024u - GM_BAR_BYTES) / L.stage_bytes;
+    if (stages > (uint32_t)GM_MAX_STAGES) stages = GM_MAX_STAGES;
+    if (const char* e = dev_switch("SPFY_GEMM_STAGES")) {
+      const uint32_t c = (uint32_t)atoi(e);
+      if (c >= 1 && c < stages) stages = c;
+    }
+    if (stages < 2) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: tile does not fit shared memory");
+    L.stages = stages;
+    L.bar_off = stages * L.stage_bytes;
+    smem = L.bar_off + GM_BAR_BYTES + 1024u;
   }
-  if (stages < 2) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: tile does not fit shared memory");
-  L.stages = stages;
-  L.bar_off = stages * L.stage_bytes;
-  const uint32_t smem = L.bar_off + GM_BAR_BYTES + 1024u;
   // instruction descriptor: D = F32; A / B format (F16 0, BF16 1, TF32 2); M = 128; N and majors per problem
   const uint32_t fmt = f32 ? 2u : (dtype == SPFY_BF16 ? 1u : 0u);
   L.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(GM_BM >> 4) << 24);
@@ -739,6 +1031,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
     L.table = reinterpret_cast<const GemmProblemDev*>(ws8);
   }
   const int grid = (int)std::min<uint32_t>(units, (uint32_t)di.sm_count);
+  if (ts) return launch_ts(table[0], L, smem, grid, stream);
   if (f32) return launch_kind<KIND_F32>(table[0], L, smem, grid, stream);
   if (dtype == SPFY_BF16) return launch_kind<KIND_BF16>(table[0], L, smem, grid, stream);
   return launch_kind<KIND_F16>(table[0], L, smem, grid, stream);
