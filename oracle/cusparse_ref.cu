@@ -261,7 +261,8 @@ static int run_timebell(int argc, char** argv) {
     if (memo.count(sh)) { total_ms += memo[sh]; std::printf("%lld,%lld,%lld,%lld,%.5f\n", (long long)sh[0], (long long)sh[1], (long long)sh[2], (long long)sh[3], memo[sh]); continue; }
     const int64_t m = sh[0], n = sh[1], k = sh[2], nb = sh[3], block = 2;
     const int64_t ell_cols = k / 2 / block * block, bcols = ell_cols / block, brows = (m + block - 1) / block, nbc = k / block;
-    if (bcols == 0 || m % block || k % block) {  // cuSPARSE rejects rows / cols that are not multiples of the block (k = 147) std::printf("%lld,%lld,%lld,%lld,nan\n", (long long)m, (long long)n, (long long)k, (long long)nb); continue; }
+    // cuSPARSE rejects rows / cols that are not multiples of the block (k = 147)
+    if (bcols == 0 || m % block || k % block) { std::printf("%lld,%lld,%lld,%lld,nan\n", (long long)m, (long long)n, (long long)k, (long long)nb); continue; }
     std::vector<int32_t> ci((size_t)nb * brows * bcols);
     for (int64_t b = 0; b < nb; ++b)
       for (int64_t i = 0; i < brows; ++i) {

@@ -38,7 +38,13 @@ def _stale(target, deps):
 
 
 def build_library(force=False, verbose=False, dev=False):
-    """Compile every .cu under csrc/ for sm_100a and link the shared library."""
+    """Compile every .cu under csrc/ for sm_100a and link the shared library.
+    dev=True builds lib_dev/libsparsifyme_b200.so (objects in build_dev/) next to the release library: the same
+    code with the SPFY_* environment switches compiled in; select it with SPFY_LIB=<path> (tuning runs only)."""
+    global OBJ, LIBDIR, LIB
+    if dev:
+        OBJ, LIBDIR = os.path.join(HERE, "build_dev"), os.path.join(HERE, "lib_dev")
+        LIB = os.path.join(LIBDIR, "libsparsifyme_b200.so")
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
@@ -62,5 +68,4 @@ def build_library(force=False, verbose=False, dev=False):
 
 if __name__ == "__main__":
     # --dev: compile the SPFY_* environment switches in (tuning / timing experiments only, see common.cuh)
-    print(build_library(force="--force" in sys.argv or "--dev" in sys.argv, verbose="-v" in sys.argv,
-                        dev="--dev" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, dev="--dev" in sys.argv))

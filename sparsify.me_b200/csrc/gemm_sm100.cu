@@ -55,6 +55,7 @@ enum { KIND_F16 = 0, KIND_BF16 = 1, KIND_F32 = 2 };
 struct alignas(64) GemmProblemDev {
   CUtensorMap tmap_a;      // Au: {inner, outer, batch}; K-major: inner = K, MN-major: inner = Mu
   CUtensorMap tmap_b;      // Bu likewise
+  CUtensorMap tmap_a2;     // 3xTF32 kernel, K-major Au: {32, outer, K/32 full groups, batch} -- two K slabs per instruction
   uint8_t* C;              // batch 0 of the result
   const uint64_t* c_ptrs;  // optional device array of per-batch result pointers
   uint64_t ldc, stride_c;  // elements
@@ -79,6 +80,8 @@ struct GemmLaunch {
   uint32_t kelems;    // elements of K per stage (32 fp32 / 64 half)
   const int* gate;    // optional device word: the launch does its work only if (*gate != 0) == gate_run_if
   uint32_t gate_run_if;
+  uint32_t dbg;       // development switches (SPFY_GEMM_DEBUG, dev builds only; timing experiments, results are garbage):
+                      // 1 no MMAs, 2 no Bu split, 4 no tcgen05.st, 8 no hi/lo arithmetic
   uint32_t a_stages;  // 3xTF32 kernel: depth of the Au ring (raw tiles only; the Bu ring has `stages` slots)
   uint32_t b_off;     // ... and where the Bu ring starts
 };
@@ -145,13 +148,14 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
     const bool warp_ok = mt * GM_BM + quarter * 32u < mu;
     mbar_wait(bar_acc_full + slot * 8, (job / slots) & 1u);
     tc_fence_after();
-    const uint32_t chunks = (bn + 31u) / 32u;
+    // 16 accumulator columns at a time (bn is a multiple of 16): keeps the role at ~50 registers
+    const uint32_t chunks = bn / 16u;
     for (uint32_t c = 0; c < chunks; ++c) {
-      const uint32_t col0 = nt * bn + c * 32u;  // index along Nu
-      const uint32_t ncols = min(32u, min(bn - c * 32u, nu > col0 ? nu - col0 : 0u));
-      uint32_t acc[32];
+      const uint32_t col0 = nt * bn + c * 16u;  // index along Nu
+      const uint32_t ncols = nu > col0 ? min(16u, nu - col0) : 0u;
+      uint32_t acc[16];
       if (warp_ok && ncols) {
-        tmem_ld_x32(tmem_base + slot * slot_cols + c * 32u + ((quarter * 32u) << 16), acc);
+        tmem_ld_x16(tmem_base + slot * slot_cols + c * 16u + ((quarter * 32u) << 16), acc);
         tmem_wait_ld();
       }
       if (c + 1 == chunks) {
@@ -160,31 +164,24 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
       }
-      if (!warp_ok || !ncols) continue;
+      if (!row_ok || !ncols) continue;
       if (mu_contig) {
         // element (row, col) at row + col*ldc: a warp's 32 rows are one 128-byte (fp32) line per column
-        if (row_ok) {
-          out_t* dst = C + row + (size_t)col0 * ldc;
-          if (beta == 0.f) {
+        out_t* dst = C + row + (size_t)col0 * ldc;
 #pragma unroll
-            for (uint32_t j = 0; j < 32; ++j)
-              if (j < ncols) dst[(size_t)j * ldc] = f32_to_out<KIND>(alpha * __uint_as_float(acc[j]));
-          } else {
-#pragma unroll
-            for (uint32_t j = 0; j < 32; ++j)
-              if (j < ncols)
-                dst[(size_t)j * ldc] =
-                    f32_to_out<KIND>(alpha * __uint_as_float(acc[j]) + beta * out_to_f32<KIND>(dst[(size_t)j * ldc]));
+        for (uint32_t j = 0; j < 16; ++j)
+          if (j < ncols) {
+            float v = alpha * __uint_as_float(acc[j]);
+            if (beta != 0.f) v += beta * out_to_f32<KIND>(dst[(size_t)j * ldc]);
+            dst[(size_t)j * ldc] = f32_to_out<KIND>(v);
           }
-        }
-      } else if (row_ok) {
-        // element (row, col) at col + row*ldc: the thread owns up to 32 consecutive elements
+      } else {
+        // element (row, col) at col + row*ldc: the thread owns 16 consecutive elements
         out_t* dst = C + (size_t)row * ldc + col0;
         constexpr uint32_t VEC = 16 / sizeof(out_t);  // elements per 16-byte store
-        const bool vec_ok = ncols == 32u && ((uintptr_t)dst % 16 == 0);
-        if (vec_ok) {
+        if (ncols == 16u && ((uintptr_t)dst % 16 == 0)) {
 #pragma unroll
-          for (uint32_t q = 0; q < 32 / VEC; ++q) {
+          for (uint32_t q = 0; q < 16 / VEC; ++q) {
             float v[VEC];
 #pragma unroll
             for (uint32_t x = 0; x < VEC; ++x) v[x] = alpha * __uint_as_float(acc[q * VEC + x]);
@@ -202,7 +199,7 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
           }
         } else {
 #pragma unroll
-          for (uint32_t j = 0; j < 32; ++j)
+          for (uint32_t j = 0; j < 16; ++j)
             if (j < ncols) {
               float v = alpha * __uint_as_float(acc[j]);
               if (beta != 0.f) v += beta * out_to_f32<KIND>(dst[j]);
@@ -444,8 +441,11 @@ constexpr int TS_ACC_SLOTS = 2;
 constexpr int TS_A_COL = TS_ACC_SLOTS * TS_MAX_BN;  // first TMEM column of the Au ring
 constexpr int TS_B_STAGES = 4;                      // == TMEM Au slots (64 columns each)
 constexpr int TS_MAX_A_STAGES = 8;
-constexpr int TS_THREADS = GM_THREADS + 32;         // + warp 10: the Bu producer
+constexpr int TS_A_STAGE_BYTES = 2 * GM_A_BYTES;    // an Au stage carries TWO 32-wide K slabs (256 contiguous bytes per row)
+constexpr int TS_BSPLIT_WARPS = 4;
+constexpr int TS_THREADS = GM_THREADS + 32 + TS_BSPLIT_WARPS * 32;  // + warp 10 (Bu producer) + warps 11-14 (Bu splitters)
 
+// (15 warps: a scheduler holds four of them, so a thread gets at most 16384 / 4 / 32 = 128 registers)
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_constant__ GemmLaunch L) {
   extern __shared__ uint8_t smem_raw[];
@@ -455,11 +455,11 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
   if (L.gate && (*L.gate != 0) != (L.gate_run_if != 0)) return;
 
   const uint32_t NA = L.a_stages, NB = L.stages;
-  const uint32_t bar_afull = smem_base + L.bar_off;                      // [TS_MAX_A_STAGES] producer -> splitter
-  const uint32_t bar_aempty = bar_afull + TS_MAX_A_STAGES * 8;           // [TS_MAX_A_STAGES] splitter -> producer
-  const uint32_t bar_bfull = bar_aempty + TS_MAX_A_STAGES * 8;           // [TS_B_STAGES] producer -> splitter
-  const uint32_t bar_ready = bar_bfull + TS_B_STAGES * 8;                // [TS_B_STAGES] splitter -> MMA
-  const uint32_t bar_bfree = bar_ready + TS_B_STAGES * 8;                // [TS_B_STAGES] MMA -> producer (and TMEM slot)
+  const uint32_t bar_afull = smem_base + L.bar_off;                      // [TS_MAX_A_STAGES] producer -> Au splitters
+  const uint32_t bar_aempty = bar_afull + TS_MAX_A_STAGES * 8;           // [TS_MAX_A_STAGES] Au splitters -> producer
+  const uint32_t bar_bfull = bar_aempty + TS_MAX_A_STAGES * 8;           // [TS_B_STAGES] producer -> Bu splitters
+  const uint32_t bar_ready = bar_bfull + TS_B_STAGES * 8;                // [TS_B_STAGES] all splitters -> MMA
+  const uint32_t bar_bfree = bar_ready + TS_B_STAGES * 8;                // [TS_B_STAGES] MMA -> Bu producer, Au splitters
   const uint32_t bar_acc_full = bar_bfree + TS_B_STAGES * 8;             // [TS_ACC_SLOTS]
   const uint32_t bar_acc_empty = bar_acc_full + TS_ACC_SLOTS * 8;        // [TS_ACC_SLOTS]
   const uint32_t tmem_ptr_off = L.bar_off + (2 * TS_MAX_A_STAGES + 3 * TS_B_STAGES + 2 * TS_ACC_SLOTS) * 8;
@@ -472,7 +472,7 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
     }
     for (uint32_t s = 0; s < (uint32_t)TS_B_STAGES; ++s) {
       mbar_init(bar_bfull + s * 8, 1);
-      mbar_init(bar_ready + s * 8, GM_SPLIT_WARPS);
+      mbar_init(bar_ready + s * 8, GM_SPLIT_WARPS + TS_BSPLIT_WARPS);
       mbar_init(bar_bfree + s * 8, 1);
     }
     for (int a = 0; a < TS_ACC_SLOTS; ++a) {
@@ -488,15 +488,55 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   GemmWalker W(&single, L);
-  constexpr uint32_t KEL = 32;                 // fp32 elements of K per stage (128 bytes)
-  constexpr uint32_t GROUP_BYTES = KEL * 128;  // one 32-wide MN group of an MN-major tile
+  constexpr uint32_t KEL = 32;                 // fp32 elements of K per slab (128 bytes): one Bu stage, one TMEM slot
+  constexpr uint32_t GROUP_BYTES = KEL * 128;  // one 32-wide MN group of an MN-major Bu tile
 
-  if (warp == 0 || warp == 10) {
-    // ===================== producers: warp 0 streams Au, warp 10 streams Bu =====================
+  if (warp == 0) {
+    // ===================== Au producer: one stage = two K slabs =====================
     const bool leader = elect_one();
-    const bool is_a = warp == 0;
     uint32_t st = 0, ph = 0;
-    const uint32_t depth = is_a ? NA : NB;
+    const GemmProblemDev* last = nullptr;
+    const CUtensorMap *tmap = nullptr, *tmap2 = nullptr;
+    uint32_t m_tiles = 1, n_tiles = 1, k_tiles = 0, full_groups = 0, mn = 0, bat = 0, unit_begin = 0;
+    for (; W.valid(); W.next()) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) {
+        last = P;
+        tmap = &P->tmap_a; tmap2 = &P->tmap_a2;
+        if (leader) { prefetch_tmap(tmap); prefetch_tmap(tmap2); }
+        m_tiles = uni(P->m_tiles); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); full_groups = uni(P->k) / KEL;
+        mn = uni(P->a_mn); bat = uni(P->a_batched); unit_begin = uni(P->unit_begin);
+      }
+      const uint32_t local = W.u - unit_begin;
+      const uint32_t t1 = local / n_tiles;
+      const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
+      const int bc = bat ? (int)b : 0, row0 = (int)(mt * GM_BM);
+      for (uint32_t kt = 0; kt < k_tiles; kt += 2) {
+        mbar_wait(bar_aempty + st * 8, ph ^ 1u);
+        const uint32_t full = bar_afull + st * 8, dst = smem_base + st * (uint32_t)TS_A_STAGE_BYTES;
+        const uint32_t slabs = min(2u, k_tiles - kt);
+        if (leader) {
+          mbar_expect_tx(full, (mn ? 2u : slabs) * (uint32_t)GM_A_BYTES);
+          if (mn) {
+            // MN-major, unswizzled: four groups of 32 rows, each [64 k-rows][32 rows] (the box always spans both slabs;
+            // k rows beyond K are zero-filled)
+            for (uint32_t g = 0; g < 4; ++g)
+              tma_load_3d(dst + g * 2u * GROUP_BYTES, tmap, row0 + (int)(g * KEL), (int)(kt * KEL), bc, full, HINT_EVICT_NORMAL);
+          } else if (kt + 2 <= full_groups) {
+            // both slabs in one instruction: [K/32 groups][rows][32] view, box (32, 128, 2) = 256 contiguous bytes per row
+            tma_load_4d(dst, tmap2, 0, row0, (int)kt, bc, full, HINT_EVICT_NORMAL);
+          } else {
+            for (uint32_t h = 0; h < slabs; ++h)  // the ragged end of K: plain boxes, zero-filled beyond K
+              tma_load_3d(dst + h * (uint32_t)GM_A_BYTES, tmap, (int)((kt + h) * KEL), row0, bc, full, HINT_EVICT_NORMAL);
+          }
+        }
+        if (++st == NA) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== Bu producer: one stage = one K slab =====================
+    const bool leader = elect_one();
+    uint32_t st = 0, ph = 0;
     const GemmProblemDev* last = nullptr;
     const CUtensorMap* tmap = nullptr;
     uint32_t m_tiles = 1, n_tiles = 1, k_tiles = 0, bn = 0, mn = 0, bat = 0, unit_begin = 0;
@@ -504,32 +544,27 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
-        tmap = is_a ? &P->tmap_a : &P->tmap_b;
+        tmap = &P->tmap_b;
         if (leader) prefetch_tmap(tmap);
         m_tiles = uni(P->m_tiles); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); bn = uni(P->bn);
-        mn = uni(is_a ? P->a_mn : P->b_mn); bat = uni(is_a ? P->a_batched : P->b_batched);
-        unit_begin = uni(P->unit_begin);
+        mn = uni(P->b_mn); bat = uni(P->b_batched); unit_begin = uni(P->unit_begin);
       }
       const uint32_t local = W.u - unit_begin;
-      const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
-      const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
-      const int bc = bat ? (int)b : 0;
-      const uint32_t row0 = is_a ? mt * (uint32_t)GM_BM : nt * bn, rows = is_a ? (uint32_t)GM_BM : bn;
-      const uint64_t hint = is_a ? HINT_EVICT_NORMAL : HINT_EVICT_LAST;  // Au streams from HBM, Bu is re-read by every tile
+      const uint32_t nt = local % n_tiles, b = local / n_tiles / m_tiles;
+      const int bc = bat ? (int)b : 0, row0 = (int)(nt * bn);
       for (uint32_t kt = 0; kt < k_tiles; ++kt) {
-        mbar_wait((is_a ? bar_aempty : bar_bfree) + st * 8, ph ^ 1u);
-        const uint32_t full = (is_a ? bar_afull : bar_bfull) + st * 8;
-        const uint32_t dst = is_a ? smem_base + st * (uint32_t)GM_A_BYTES : smem_base + L.b_off + st * L.stage_bytes;
+        mbar_wait(bar_bfree + st * 8, ph ^ 1u);
+        const uint32_t full = bar_bfull + st * 8, dst = smem_base + L.b_off + st * L.stage_bytes;
         if (leader) {
-          mbar_expect_tx(full, rows * (uint32_t)GM_ROW_BYTES);
+          mbar_expect_tx(full, bn * (uint32_t)GM_ROW_BYTES);
           if (!mn) {
-            tma_load_3d(dst, tmap, (int)(kt * KEL), (int)row0, bc, full, hint);
+            tma_load_3d(dst, tmap, (int)(kt * KEL), row0, bc, full, HINT_EVICT_LAST);  // re-read by every tile: keep in L2
           } else {
-            for (uint32_t g = 0; g * KEL < rows; ++g)
-              tma_load_3d(dst + g * GROUP_BYTES, tmap, (int)(row0 + g * KEL), (int)(kt * KEL), bc, full, hint);
+            for (uint32_t g = 0; g * KEL < bn; ++g)
+              tma_load_3d(dst + g * GROUP_BYTES, tmap, row0 + (int)(g * KEL), (int)(kt * KEL), bc, full, HINT_EVICT_LAST);
           }
         }
-        if (++st == depth) { st = 0; ph ^= 1u; }
+        if (++st == NB) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -565,7 +600,7 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
         if (leader) {
 #pragma unroll
           for (uint32_t j = 0; j < 4; ++j) {
-            if (j < nk) {
+            if (j < nk && !(L.dbg & 1u)) {
               const uint64_t db = db_hi | (uint64_t)(b0 + b_step * j);
               const uint32_t a_hi = ta + 8u * j, a_lo = a_hi + 32u;
               tc_mma_tf32_ts(tmem_d, a_hi, db + lo_off, idesc, (kt | j) ? 1u : 0u);  // hi * lo
@@ -581,64 +616,105 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
       ++job;
     }
   } else if (warp < 2 + GM_SPLIT_WARPS) {
-    // ===================== splitter =====================
-    const uint32_t t = threadIdx.x - 64u;
+    // ===================== Au splitters: thread = one row of the tile = one TMEM lane =====================
     const uint32_t row = (warp & 3u) * 32u + lane;  // the TMEM lane quarter a warp may touch is warp % 4
     uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
     const GemmProblemDev* last = nullptr;
-    uint32_t k_tiles = 0, bn = 0, a_mn = 0;
+    uint32_t k_tiles = 0, a_mn = 0;
+    for (; W.valid(); W.next()) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) { last = P; k_tiles = P->k_tiles; a_mn = P->a_mn; }
+      for (uint32_t kt = 0; kt < k_tiles; kt += 2) {
+        mbar_wait(bar_afull + sa * 8, pha);
+        const uint32_t src = smem_base + sa * (uint32_t)TS_A_STAGE_BYTES;
+        const uint32_t slabs = min(2u, k_tiles - kt);
+        for (uint32_t hf = 0; hf < slabs; ++hf) {
+          const uint32_t ta = tmem_base + (uint32_t)TS_A_COL + sb * 64u + (((warp & 3u) * 32u) << 16);
+          // the slab in two pieces of 16 values (keeps the working set at 32 registers)
+#pragma unroll
+          for (uint32_t q = 0; q < 2; ++q) {
+            uint32_t x[16], h[16];
+            if (!a_mn) {
+              // K-major, 128B-swizzled: chunk c of row r at (c ^ (r & 7)) * 16 -- 8 lanes cover all banks
+              const uint32_t rbase = src + hf * (uint32_t)GM_A_BYTES + row * 128u, sw = row & 7u;
+#pragma unroll
+              for (uint32_t c = 0; c < 4; ++c) {
+                const uint4 v = ld_shared_v4(rbase + (((4u * q + c) ^ sw) << 4));
+                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+              }
+            } else {
+              // MN-major, unswizzled groups of 32 rows x 64 k-rows: k-row kk at kk*128, my element at (row % 32) * 4
+              const uint32_t rbase = src + (row >> 5) * 2u * GROUP_BYTES + (hf * 32u + q * 16u) * 128u + (row & 31u) * 4u;
+#pragma unroll
+              for (uint32_t kk = 0; kk < 16; ++kk) x[kk] = ld_shared_u32(rbase + kk * 128u);
+            }
+            if (q == 1 && hf + 1 == slabs) {  // the stage has been read: hand it back before doing anything else
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_aempty + sa * 8);
+            }
+            // hi = x rounded to the nearest TF32 (the tensor core reads it exactly), lo = x - hi (exact in fp32)
+            if (!(L.dbg & 8u)) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) h[i] = (x[i] + 0x1000u) & 0xffffe000u;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = __float_as_uint(__uint_as_float(x[i]) - __uint_as_float(h[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) h[i] = x[i];
+            }
+            if (q == 0) {
+              // TMEM slot sb is free once the MMAs of the stage that used it last have completed
+              mbar_wait(bar_bfree + sb * 8, phb ^ 1u);
+              tc_fence_after();
+            }
+            if (!(L.dbg & 4u)) {
+              tmem_st_x16(ta + q * 16u, h);
+              tmem_st_x16(ta + 32u + q * 16u, x);
+            }
+          }
+          if (!(L.dbg & 4u)) tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_ready + sb * 8);
+          if (++sb == NB) { sb = 0; phb ^= 1u; }
+        }
+        if (++sa == NA) { sa = 0; pha ^= 1u; }
+      }
+    }
+  } else if (warp >= 11) {
+    // ===================== Bu splitters: element-wise over the stage (the layout does not matter) =====================
+    const uint32_t t = threadIdx.x - 11u * 32u;
+    uint32_t sb = 0, phb = 0;
+    const GemmProblemDev* last = nullptr;
+    uint32_t k_tiles = 0, bn = 0;
     const uint32_t raw = L.raw_bytes;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
-      if (P != last) { last = P; k_tiles = P->k_tiles; bn = P->bn; a_mn = P->a_mn; }
+      if (P != last) { last = P; k_tiles = P->k_tiles; bn = P->bn; }
+      const uint32_t used = (L.dbg & 2u) ? 0u : bn * (uint32_t)GM_ROW_BYTES;
       for (uint32_t kt = 0; kt < k_tiles; ++kt) {
-        // ---- Au: my row of the raw tile -> registers; the slot goes back to the producer at once ----
-        mbar_wait(bar_afull + sa * 8, pha);
-        const uint32_t src = smem_base + sa * (uint32_t)GM_A_BYTES;
-        uint32_t x[32], h[32];
-        if (!a_mn) {
-          // K-major, 128B-swizzled: chunk c of row r at (c ^ (r & 7)) * 16 -- 8 lanes cover all banks
-          const uint32_t rbase = src + row * 128u, sw = row & 7u;
-#pragma unroll
-          for (uint32_t c = 0; c < 8; ++c) {
-            const uint4 v = ld_shared_v4(rbase + ((c ^ sw) << 4));
-            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-          }
-        } else {
-          // MN-major, unswizzled groups of 32 rows: k-row kk at kk*128, my element at (row % 32) * 4
-          const uint32_t rbase = src + (row >> 5) * GROUP_BYTES + (row & 31u) * 4u;
-#pragma unroll
-          for (uint32_t kk = 0; kk < 32; ++kk) x[kk] = ld_shared_u32(rbase + kk * 128u);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_aempty + sa * 8);
-        if (++sa == NA) { sa = 0; pha ^= 1u; }
-        // hi = x rounded to the nearest TF32 (the tensor core reads it exactly), lo = x - hi (exact in fp32)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = (x[i] + 0x1000u) & 0xffffe000u;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = __float_as_uint(__uint_as_float(x[i]) - __uint_as_float(h[i]));
-        // ---- the Bu stage (and with it the TMEM slot: both are released by the same commit) ----
         mbar_wait(bar_bfull + sb * 8, phb);
-        tc_fence_after();
-        const uint32_t ta = tmem_base + (uint32_t)TS_A_COL + sb * 64u + (((warp & 3u) * 32u) << 16);
-        tmem_st_x32(ta, h);
-        tmem_st_x32(ta + 32u, x);
         const uint32_t sbase = smem_base + L.b_off + sb * L.stage_bytes;
-        const uint32_t used = bn * (uint32_t)GM_ROW_BYTES;
-#pragma unroll 4
-        for (uint32_t off = t * 16u; off < used; off += GM_SPLIT_WARPS * 32u * 16u) {
-          const uint4 v = ld_shared_v4(sbase + off);
-          const uint32_t h0 = (v.x + 0x1000u) & 0xffffe000u, h1 = (v.y + 0x1000u) & 0xffffe000u;
-          const uint32_t h2 = (v.z + 0x1000u) & 0xffffe000u, h3 = (v.w + 0x1000u) & 0xffffe000u;
-          const float l0 = __uint_as_float(v.x) - __uint_as_float(h0), l1 = __uint_as_float(v.y) - __uint_as_float(h1);
-          const float l2 = __uint_as_float(v.z) - __uint_as_float(h2), l3 = __uint_as_float(v.w) - __uint_as_float(h3);
-          st_shared_v4(sbase + raw + off, __float_as_uint(l0), __float_as_uint(l1), __float_as_uint(l2), __float_as_uint(l3));
-          st_shared_v4(sbase + off, h0, h1, h2, h3);
+        // four 16-byte pieces per trip, loads first: the trip costs one shared-memory round trip, not four
+        constexpr uint32_t STRIDE = TS_BSPLIT_WARPS * 32u * 16u;
+        for (uint32_t off = t * 16u; off < used; off += 4u * STRIDE) {
+          uint4 v[4];
+#pragma unroll
+          for (uint32_t u = 0; u < 4; ++u)
+            if (off + u * STRIDE < used) v[u] = ld_shared_v4(sbase + off + u * STRIDE);
+#pragma unroll
+          for (uint32_t u = 0; u < 4; ++u) {
+            if (off + u * STRIDE >= used) break;
+            const uint32_t h0 = (v[u].x + 0x1000u) & 0xffffe000u, h1 = (v[u].y + 0x1000u) & 0xffffe000u;
+            const uint32_t h2 = (v[u].z + 0x1000u) & 0xffffe000u, h3 = (v[u].w + 0x1000u) & 0xffffe000u;
+            const float l0 = __uint_as_float(v[u].x) - __uint_as_float(h0), l1 = __uint_as_float(v[u].y) - __uint_as_float(h1);
+            const float l2 = __uint_as_float(v[u].z) - __uint_as_float(h2), l3 = __uint_as_float(v[u].w) - __uint_as_float(h3);
+            st_shared_v4(sbase + raw + off + u * STRIDE, __float_as_uint(l0), __float_as_uint(l1), __float_as_uint(l2),
+                         __float_as_uint(l3));
+            st_shared_v4(sbase + off + u * STRIDE, h0, h1, h2, h3);
+          }
         }
-        tmem_wait_st();
         fence_proxy_async_smem();  // generic-proxy writes of Bu -> visible to the tensor core's async-proxy reads
-        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ready + sb * 8);
         if (++sb == NB) { sb = 0; phb ^= 1u; }
@@ -704,7 +780,7 @@ size_t repack_bytes(int dtype, const OperandView& v, size_t nb) {
 }
 
 int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t nb, uint32_t box_rows,
-                     CUtensorMapSwizzle swizzle) {
+                     CUtensorMapSwizzle swizzle, uint32_t mn_box_k = 0) {
   EncodeTiledFn enc0;
   int rc = get_encoder(&enc0);
   if (rc) return rc;
@@ -717,7 +793,7 @@ int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t n
   size_t bstride = batched ? v.stride * es : round_up(std::max<size_t>(outer, 1) * v.ld * es, 16);
   cuuint64_t strides[2] = {v.ld * es, bstride};
   // K-major: box = 128 bytes of K x box_rows rows; MN-major: 128 bytes of MN x `per_row` k-rows (one group)
-  cuuint32_t box[3] = {per_row, v.mn_major ? per_row : box_rows, 1};
+  cuuint32_t box[3] = {per_row, v.mn_major ? (mn_box_k ? mn_box_k : per_row) : box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapDataType dt = dtype == SPFY_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : dtype == SPFY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -727,6 +803,29 @@ int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t n
   if (r != CUDA_SUCCESS)
     return fail(SPFY_E_CUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d): inner %zu outer %zu ld %zu batches %zu", (int)r,
                 inner, outer, v.ld, nb);
+  return SPFY_OK;
+}
+
+// K-major fp32 operand viewed as [K/32 full groups][rows][32]: a box (32, 128, 2) lands as two consecutive 128B-swizzled
+// (128 x 32) slabs -- 256 contiguous bytes per row -- with one instruction.  Only FULL groups are part of the view (a
+// partial last group would read past the row), so the ragged end of K goes through the plain map.
+int make_grouped_map(CUtensorMap* map, const OperandView& v, size_t nb) {
+  EncodeTiledFn enc0;
+  int rc = get_encoder(&enc0);
+  if (rc) return rc;
+  EncodeFn enc = (EncodeFn)enc0;
+  const bool batched = nb > 1 && v.stride != 0;
+  const size_t groups = std::max<size_t>(v.k / 32, 1);
+  cuuint64_t dims[4] = {32, v.mn, groups, batched ? nb : 1};
+  const size_t bstride = batched ? v.stride * 4 : round_up(std::max<size_t>(v.mn, 1) * v.ld * 4, 16);
+  cuuint64_t strides[3] = {v.ld * 4, 128, bstride};
+  cuuint32_t box[4] = {32, GM_BM, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(v.base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SPFY_E_CUDA, "tc_gemm: cuTensorMapEncodeTiled (grouped) failed (%d): rows %zu k %zu ld %zu", (int)r, v.mn, v.k, v.ld);
   return SPFY_OK;
 }
 
@@ -803,8 +902,13 @@ int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts) 
   const CUtensorMapSwizzle sw_a = !(f32 && o.a.mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : ts ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   const CUtensorMapSwizzle sw_b = f32 && o.b.mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-  int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM, sw_a);
+  // (3xTF32 kernel, MN-major Au: the box spans the two K slabs of a stage)
+  int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM, sw_a, ts && o.a.mn_major ? 64u : 0u);
   if (rc) return rc;
+  if (ts && !o.a.mn_major) {
+    rc = make_grouped_map(&d->tmap_a2, o.a, p.nb);
+    if (rc) return rc;
+  }
   rc = make_operand_map(&d->tmap_b, dtype, o.b, p.nb, o.bn, sw_b);
   if (rc) return rc;
   const size_t kel = GM_ROW_BYTES / elem_bytes(dtype);
@@ -986,20 +1090,22 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
   L.kelems = (uint32_t)(GM_ROW_BYTES / elem_bytes(dtype));
   L.gate = gate;
   L.gate_run_if = gate_run_if ? 1u : 0u;
+  if (const char* e = dev_switch("SPFY_GEMM_DEBUG")) L.dbg = (uint32_t)atoi(e);
   uint32_t smem = 0;
   if (ts) {
     // [Au ring: a_stages x 16 KiB][Bu ring: 4 x (hi | lo)][barriers]
     L.raw_bytes = bn_max * (uint32_t)GM_ROW_BYTES;
     L.stage_bytes = 2u * L.raw_bytes;
     L.stages = TS_B_STAGES;
-    uint32_t a_stages = (GM_SMEM_LIMIT - 1024u - GM_BAR_BYTES - L.stages * L.stage_bytes) / (uint32_t)GM_A_BYTES;
+    uint32_t a_stages = (GM_SMEM_LIMIT - 1024u - GM_BAR_BYTES - L.stages * L.stage_bytes) / (uint32_t)TS_A_STAGE_BYTES;
     if (a_stages > (uint32_t)TS_MAX_A_STAGES) a_stages = TS_MAX_A_STAGES;
     if (const char* e = dev_switch("SPFY_GEMM_STAGES")) {
       const uint32_t c = (uint32_t)atoi(e);
       if (c >= 1 && c < a_stages) a_stages = c;
     }
     L.a_stages = a_stages;
-    L.b_off = a_stages * (uint32_t)GM_A_BYTES;
+    if (a_stages < 2) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: tile does not fit shared memory");
+    L.b_off = a_stages * (uint32_t)TS_A_STAGE_BYTES;
     L.bar_off = L.b_off + L.stages * L.stage_bytes;
     smem = L.bar_off + GM_BAR_BYTES + 1024u;
   } else {
