@@ -196,6 +196,37 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
+def bind_near_gpu(local, ngpus):
+    """Pin this process (and so the pages its pinned host buffers are first touched on) to the NUMA node of its GPU.
+    With every rank left on node 0 the staging buffers of all GPUs share one socket's memory controllers (round 1:
+    e2e 8.5 -> 19.5 TFLOP/s from 1 to 8 GPUs).  The node comes from sysfs; when the platform does not report one, the
+    GPUs are spread evenly over the nodes in index order."""
+    try:
+        import torch
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if len(nodes) < 2:
+            return {"node": nodes[0] if nodes else 0, "source": "single node"}
+        p = torch.cuda.get_device_properties(local)
+        node, src = -1, "sysfs"
+        try:
+            path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/numa_node"
+            node = int(open(path).read().strip())
+        except Exception:  # noqa: BLE001
+            node = -1
+        if node not in nodes:
+            node, src = nodes[min(len(nodes) - 1, local * len(nodes) // max(ngpus, 1))], "even spread (no node in sysfs)"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"node": node, "source": src, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"node": None, "source": f"not bound: {e}"[:120]}
+
+
 def layer_table(spfy, csv, batch):
     shapes = spfy.shapes.read_shapes(csv)
     return [spfy.shapes.to_gemm(s, "weights", batch) for s in shapes]
@@ -253,8 +284,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    spfy = ge.load_package()
+    # the reference arm runs none of the product: the shape table is loaded by path (not through the package, which
+    # would map libsparsifyme_b200.so into this process), the arithmetic is the oracle port on ALL host cores
+    # (torchrun exports OMP_NUM_THREADS=1 to its workers; rank 0 is the only one that works here)
+    class _Pkg:
+        shapes = ge._load_by_path("spfy_shapes_only", os.path.join(ge.PKG_DIR, "shapes.py"))
+    spfy = _Pkg
     orc = ge.load_oracle()
+    orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     gemms = layer_table(spfy, args.csv, args.batch)
     dt = 0 if args.dtype == "fp16" else 1
     vals, best = [], None
@@ -461,6 +498,177 @@ def run_coo(args):
 
 
 # ------------------------------------------------------------------------------ our arm
+# ------------------------------------------------------------------------------ strong scaling with the output gather
+def run_strong(args):
+    """BASELINE.json configs[4]: the 2:4 spmma sweep over datasets/resnet152.csv at a FIXED global batch (256 images),
+    N-sharded on image boundaries across the ranks (rank r owns b/g images of every layer = columns [r*N/g, (r+1)*N/g)
+    of B and D; weights replicated and pruned redundantly), followed by the path's only collective: the gather of every
+    layer's output onto every rank (north_star: "NCCL used only to gather outputs").
+
+    Each rank's GEMMs write D_r [M x N/g] straight into slab r of a per-chunk gather arena; the arena's other slabs are
+    filled by ONE in-place ncclAllGather per chunk (spfy_mg_allgather: layout [g][M][N/g] per layer, no transpose, no
+    copy) on a second stream, so the gather of chunk c runs under the GEMMs of chunk c+1.  Reported: compute-only,
+    gather-only and the overlapped whole; `value` is the whole job (compute + gather)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (sparsify.me_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    json_out = claim_stdout() if world > 1 else sys.stdout
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spfy = ge.load_package()
+    csv = args.csv if args.csv != "resnet50.csv" else "resnet152.csv"
+    gbatch = args.batch if args.batch != 32 else 256
+    lo, hi = spfy.multigpu.shard_batch(gbatch, world, rank)
+    nb = hi - lo
+    if gbatch % world:
+        raise SystemExit("bench.py --strong: the global batch must be divisible by the number of GPUs (equal slabs)")
+    tdt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    shapes = spfy.shapes.read_shapes(csv)
+    gemms = [spfy.shapes.to_gemm(s, "weights", nb) for s in shapes]          # this rank's shard
+    gemms_global = [spfy.shapes.to_gemm(s, "weights", gbatch) for s in shapes]
+    hbm_peak, _, tc_sust, peak_src = read_peaks()
+    need = sum((g.K * g.N + world * g.M * g.N) * 2 for g in gemms)
+    if need > 150e9:
+        raise SystemExit(f"bench.py --strong: {need/1e9:.0f} GB per GPU do not fit; use more GPUs")
+
+    nchunks = max(1, min(args.chunks, len(gemms)))
+    bounds = [len(gemms) * c // nchunks for c in range(nchunks + 1)]
+    gen_w = torch.Generator(device=dev)
+    gen_w.manual_seed(0x5EED)          # same weights on every rank
+    gen_b = torch.Generator(device=dev)
+    gen_b.manual_seed(0xB0 + rank)     # every rank its own images
+    layers, arenas, plans = [], [], []
+    for c in range(nchunks):
+        idx = range(bounds[c], bounds[c + 1])
+        elems = sum(gemms[i].M * gemms[i].N for i in idx)
+        elems = -(-elems // 64) * 64
+        arena = torch.empty(world, elems, dtype=tdt, device=dev)
+        arenas.append(arena)
+        off, probs = 0, []
+        for i in idx:
+            g = gemms[i]
+            w = (torch.rand(g.M, g.K, device=dev, generator=gen_w) * 2 - 1).to(tdt)
+            b = (torch.rand(g.K, g.N, device=dev, generator=gen_b) * 2 - 1).to(tdt)
+            d = arena[rank, off: off + g.M * g.N].view(g.M, g.N)
+            off += g.M * g.N
+            comp = spfy.alloc_compressed(tdt, g.M, g.K, dev)
+            layers.append((g, w, b, d, comp, c, off - g.M * g.N))
+            probs.append(dict(comp=comp, b=b, out=d))
+        plans.append(spfy.SpmmaPlan(probs))
+    gather = spfy.multigpu.OutputGather() if world > 1 else None
+    s_comm = torch.cuda.Stream(dev)
+
+    def prune_all():
+        spfy.prune24_batched([l[1] for l in layers], [l[4] for l in layers])
+
+    def step(do_compute, do_gather):
+        cur = torch.cuda.current_stream()
+        if do_compute:
+            prune_all()
+        for c in range(nchunks):
+            if do_compute:
+                plans[c].run()
+            if do_gather and gather is not None:
+                s_comm.wait_event(cur.record_event())
+                gather.allgather(arenas[c], stream=s_comm)
+        if do_gather:
+            cur.wait_event(s_comm.record_event())
+
+    def timed(do_compute, do_gather, steps):
+        for _ in range(max(1, args.warmup // 2)):
+            step(do_compute, do_gather)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(do_compute, do_gather)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step(True, True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local, str(torch.cuda.get_device_properties(local).uuid))
+    launches0 = spfy.launch_count()
+    if rank == 0:
+        sampler.start()
+    both_ms = timed(True, True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (spfy.launch_count() - launches0) // (args.steps + max(1, args.warmup // 2))
+    compute_ms = timed(True, False, args.steps)
+    gather_ms = timed(False, True, max(2, args.steps // 2)) if world > 1 else 0.0
+
+    # ---- the gathered slabs are what the other ranks computed: per-rank checksums travel by all_gather and are compared
+    #      with the sums of the slabs received (and the local slab against a torch fp32 matmul, first and last layer)
+    step(True, True)
+    torch.cuda.synchronize()
+    sums = torch.stack([a.float().sum(dim=1, dtype=torch.float64) for a in arenas])            # [chunks, world] as seen here
+    mine = torch.stack([a[rank].float().sum(dtype=torch.float64) for a in arenas])              # [chunks] my own slab
+    ok_gather = True
+    if world > 1:
+        allmine = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allmine, mine)
+        for r in range(world):
+            ok_gather &= bool(torch.allclose(sums[:, r], allmine[r], rtol=1e-9, atol=1e-6))
+    worst = 0.0
+    for i in (0, len(layers) - 1):
+        g, w, b, d, comp, c, off = layers[i]
+        pruned = torch.empty_like(w)
+        spfy.prune24(w, out_dense=pruned, compress=False)
+        n1 = min(g.N, 50176)
+        want = pruned.float() @ b[:, :n1].float()
+        scale = torch.clamp(want.abs(), min=1e-2 * float(want.abs().max()))
+        worst = max(worst, float(((d[:, :n1].float() - want).abs() / scale).max()))
+    flag = torch.tensor([1.0 if (ok_gather and worst <= 1e-2) else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if float(flag.item()) != 1.0:
+        raise SystemExit(f"bench.py --strong: verification failed on some rank (gather ok {ok_gather}, max rel err {worst:.3e})")
+
+    if rank == 0:
+        flops = sum(spfy.shapes.spmma_flops(g) for g in gemms_global)
+        bytes_rank = sum(spfy.shapes.spmma_bytes(g) for g in gemms)
+        recv = sum(a[0].numel() * a.element_size() for a in arenas) * (world - 1)
+        line = {
+            "metric": METRIC, "value": flops / (both_ms * 1e-3) / 1e12, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": both_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
+            "config": {"workload": f"datasets/{csv}: all {len(gemms)} layers, 2:4 prune+compress + spmma at GLOBAL batch {gbatch} "
+                                   f"(BASELINE.json configs[4]), N-sharded on image boundaries: {nb} images per GPU; every layer's "
+                                   f"output gathered onto every GPU ([g][M][N/g], in-place ncclAllGather per chunk of layers, "
+                                   f"{nchunks} chunks, overlapped with the next chunk's GEMMs)",
+                       "csv": csv, "global_batch": gbatch, "batch_per_gpu": nb, "chunks": nchunks,
+                       "l2_policy": "inputs larger than L2", "parallelism": f"N-sharded x{world} + output all-gather"},
+            "clocks": clocks, "gpu_launches": launches,
+            "compute_only": {"ms_per_step": compute_ms, "tflops": flops / (compute_ms * 1e-3) / 1e12,
+                             "hbm_frac": bytes_rank / (compute_ms * 1e-3) / 1e9 / hbm_peak},
+            "gather_only": {"ms_per_step": gather_ms, "bytes_received_per_rank": recv,
+                            "algbw_GBs_per_rank": recv / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
+                            "collective": "ncclAllGather via spfy_mg_allgather (NCCL loaded at run time), in place"},
+            "compute_plus_gather": {"ms_per_step": both_ms, "overlap_saved_ms": compute_ms + gather_ms - both_ms},
+            "verified": {"gather_checksums_match": ok_gather, "max_rel_err_local": worst, "tolerance": 1e-2},
+        }
+        print(json.dumps(line), file=json_out, flush=True)
+    if gather is not None:
+        gather.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -480,11 +688,17 @@ def main():
                     help="spmma: the headline (BASELINE.json configs[1]); coo: unstructured threshold prune + batched COO "
                          "SpMM over a table, batch-sharded across ranks (configs[2]/[3])")
     ap.add_argument("--sparsity", type=float, default=0.9, help="--workload coo: fraction of the weights dropped")
+    ap.add_argument("--strong", action="store_true",
+                    help="BASELINE.json configs[4]: fixed global batch (256) over resnet152.csv, N-sharded across the ranks, "
+                         "outputs all-gathered onto every rank (compute-only / gather-only / overlapped are all reported)")
+    ap.add_argument("--chunks", type=int, default=6, help="--strong: groups of layers per gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "coo":
         return run_coo(args)
+    if args.strong:
+        return run_strong(args)
 
     import ctypes
     import numpy as np
@@ -595,6 +809,7 @@ def main():
     # ---- end to end through the reference-shaped call with host buffers ----
     e2e = None
     if not args.no_e2e:
+        numa = bind_near_gpu(local, torch.cuda.device_count())
         hostbuf = {}
 
         def pinned(key, shape):
@@ -643,6 +858,8 @@ def main():
         e2e_ms = float(te.item()) / args.e2e_steps
         e2e = {"value": flops_step * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+               "pcie_GBs_per_rank": {"h2d": h2d / (e2e_ms * 1e-3) / 1e9, "d2h": d2h / (e2e_ms * 1e-3) / 1e9},
+               "host_numa": numa,
                "api": "spmma(A, B, C, m, n, k, b) per layer: pinned H2D of A and B, TILE prune in place (as spmma.hxx:86) + compress + "
                       "tcgen05 matmul, D2H of C; copy-in / compute / copy-out on three streams"}
         # restore the resident weights for anything that follows

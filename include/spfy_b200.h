@@ -340,6 +340,35 @@ SPFY_API int spfy_gemm_batched(int dtype, int precision, int opA, int opB, size_
                                void* const* C_ptrs, size_t ldc, size_t num_batches,
                                void* workspace, size_t workspace_bytes, spfy_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Multi-GPU: the per-layer problems and, inside one GEMM, the N = batch x
+ * spatial columns are independent, so the path shards with NO exchange during compute;
+ * the only collective is a gather of outputs (north_star).  The reference has no
+ * multi-GPU code (examples/spmma.cu:27-28 queries device 0 only).  One process per GPU.
+ * NCCL is loaded at run time (libnccl.so.2, or the path in SPFY_NCCL_LIB): without it these
+ * calls return SPFY_E_NCCL and nothing else in the library is affected.
+ *   bootstrap : rank 0 calls spfy_mg_unique_id (128 bytes), the host program hands the
+ *               bytes to every rank (torch.distributed, MPI, a file ...), all call
+ *               spfy_mg_create with the current device set.
+ *   allgather : N-sharded GEMMs.  Rank r holds D_r [M x N/g] row-major (its images' columns);
+ *               the gathered result is [g][M][N/g] -- the ranks' slabs back to back.  In
+ *               place when `send` == `recv` + r * bytes_per_rank: let the GEMM write D_r
+ *               there and no copy is made at all.
+ *   broadcast_many : layer sharding.  Entry i is sent from rank roots[i] to everybody, all
+ *               entries as ONE NCCL group (the lists are HOST arrays).
+ * All work is enqueued on the caller's stream.
+ * ---------------------------------------------------------------------- */
+typedef struct spfy_mg_comm_st* spfy_mg_comm_t;
+SPFY_API int spfy_mg_unique_id(void* id128);
+SPFY_API int spfy_mg_create(int rank, int world, const void* id128, spfy_mg_comm_t* comm);
+SPFY_API int spfy_mg_destroy(spfy_mg_comm_t comm);
+SPFY_API int spfy_mg_rank(spfy_mg_comm_t comm);
+SPFY_API int spfy_mg_world(spfy_mg_comm_t comm);
+SPFY_API int spfy_mg_allgather(spfy_mg_comm_t comm, const void* send, void* recv, size_t bytes_per_rank,
+                               spfy_stream_t stream);
+SPFY_API int spfy_mg_broadcast_many(spfy_mg_comm_t comm, void* const* buffers, const size_t* bytes,
+                                    const int* roots, size_t count, spfy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,10 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
 def from_f32(dtype, x):
     x = np.ascontiguousarray(x, dtype=np.float32)
     out = np.empty(x.shape, dtype=np.uint16)

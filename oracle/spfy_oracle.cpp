@@ -157,6 +157,15 @@ int orc_num_threads() {
 #endif
 }
 
+// a launcher may have exported OMP_NUM_THREADS=1 for its workers (torchrun does): the baseline arm asks for all cores
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 // --- scalar conversions exposed for the tests ---------------------------
 uint16_t orc_f32_to_f16(float f) { return float_to_half_bits(f); }
 uint16_t orc_f32_to_bf16(float f) { return float_to_bf16_bits(f); }

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsparsifyme_b200.so")
-SOURCES = ["api.cu", "prune.cu", "spmma_sm100.cu", "gemm_sm100.cu", "spmm.cu"]
+SOURCES = ["api.cu", "prune.cu", "spmma_sm100.cu", "gemm_sm100.cu", "spmm.cu", "multigpu.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -61,7 +61,7 @@ def build_library(force=False, verbose=False, dev=False):
             subprocess.run(cmd, check=True)
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                    "-cudart", "static"]
+                                                    "-cudart", "static", "-ldl"]
         subprocess.run(cmd, check=True)
     return LIB
 

@@ -74,6 +74,13 @@ SIGNATURES = {
     "spfy_spmm_bell_workspace_bytes": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, _SZ, POINTER(_SZ)]),
     "spfy_spmm_bell_batched": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _SZ, _P, _SZ,
                                        c_float, c_float, _P, _SZ, _P]),
+    "spfy_mg_unique_id": (c_int, [_P]),
+    "spfy_mg_create": (c_int, [c_int, c_int, _P, POINTER(c_void_p)]),
+    "spfy_mg_destroy": (c_int, [_P]),
+    "spfy_mg_rank": (c_int, [_P]),
+    "spfy_mg_world": (c_int, [_P]),
+    "spfy_mg_allgather": (c_int, [_P, _P, _P, _SZ, _P]),
+    "spfy_mg_broadcast_many": (c_int, [_P, _P, _P, _P, _SZ, _P]),
     "spfy_gemm_workspace_bytes": (c_int, [c_int, c_int, c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, POINTER(_SZ)]),
     "spfy_gemm_strided_batched": (c_int, [c_int, c_int, c_int, c_int, _SZ, _SZ, _SZ, c_float, _P, _SZ, _SZ, _P, _SZ,
                                           _SZ, c_float, _P, _SZ, _SZ, _SZ, _P, _SZ, _P]),
@@ -81,7 +88,8 @@ SIGNATURES = {
                                   _SZ, _SZ, _P, _SZ, _P]),
 }
 
-_NO_STATUS = {"spfy_version", "spfy_last_error_string", "spfy_launch_count", "spfy_spmma_plan_launches"}
+_NO_STATUS = {"spfy_version", "spfy_last_error_string", "spfy_launch_count", "spfy_spmma_plan_launches", "spfy_mg_rank",
+              "spfy_mg_world"}
 
 
 class SpmmaProblem(ctypes.Structure):

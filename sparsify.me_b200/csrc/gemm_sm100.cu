@@ -684,6 +684,7 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
   } else if (warp >= 11) {
     // ===================== Bu splitters: element-wise over the stage (the layout does not matter) =====================
     const uint32_t t = threadIdx.x - 11u * 32u;
+    const bool write_hi = L.write_hi != 0;
     uint32_t sb = 0, phb = 0;
     const GemmProblemDev* last = nullptr;
     uint32_t k_tiles = 0, bn = 0;
@@ -705,13 +706,16 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
 #pragma unroll
           for (uint32_t u = 0; u < 4; ++u) {
             if (off + u * STRIDE >= used) break;
-            const uint32_t h0 = (v[u].x + 0x1000u) & 0xffffe000u, h1 = (v[u].y + 0x1000u) & 0xffffe000u;
-            const uint32_t h2 = (v[u].z + 0x1000u) & 0xffffe000u, h3 = (v[u].w + 0x1000u) & 0xffffe000u;
+            // write_hi: hi = x rounded to nearest TF32, stored over the raw tile.  Without it the raw tile stays and the
+            // tensor core itself drops the low 13 mantissa bits, so hi = x truncated and lo = x - hi (one store less)
+            const uint32_t rnd = write_hi ? 0x1000u : 0u;
+            const uint32_t h0 = (v[u].x + rnd) & 0xffffe000u, h1 = (v[u].y + rnd) & 0xffffe000u;
+            const uint32_t h2 = (v[u].z + rnd) & 0xffffe000u, h3 = (v[u].w + rnd) & 0xffffe000u;
             const float l0 = __uint_as_float(v[u].x) - __uint_as_float(h0), l1 = __uint_as_float(v[u].y) - __uint_as_float(h1);
             const float l2 = __uint_as_float(v[u].z) - __uint_as_float(h2), l3 = __uint_as_float(v[u].w) - __uint_as_float(h3);
             st_shared_v4(sbase + raw + off + u * STRIDE, __float_as_uint(l0), __float_as_uint(l1), __float_as_uint(l2),
                          __float_as_uint(l3));
-            st_shared_v4(sbase + off + u * STRIDE, h0, h1, h2, h3);
+            if (write_hi) st_shared_v4(sbase + off + u * STRIDE, h0, h1, h2, h3);
           }
         }
         fence_proxy_async_smem();  // generic-proxy writes of Bu -> visible to the tensor core's async-proxy reads
@@ -1085,7 +1089,10 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
   memset(&L, 0, sizeof(L));
   const bool f32 = dtype == SPFY_F32;
   L.split = f32 && precision == TC_GEMM_PRECISE;
-  L.write_hi = 1;
+  // The tensor core ignores the low 13 mantissa bits of a TF32 operand (measured: tools/gpu_wh.sh, same error with and
+  // without the store), so the 3xTF32 kernel leaves the raw Bu tile in place as "hi" and only writes lo = x - trunc(x).
+  // The shared-memory-only split of the kernel above keeps writing a rounded hi.
+  L.write_hi = ts ? 0 : 1;
   if (const char* e = dev_switch("SPFY_GEMM_WRITE_HI")) L.write_hi = (uint32_t)atoi(e);
   L.kelems = (uint32_t)(GM_ROW_BYTES / elem_bytes(dtype));
   L.gate = gate;

@@ -31,16 +31,12 @@ namespace {
 template <typename T>
 __device__ __forceinline__ float load_as_float(const T* p);
 template <>
-__device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
-template <>
 __device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
 template <>
 __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 template <typename T>
 __device__ __forceinline__ void store_from_float(T* p, float v);
-template <>
-__device__ __forceinline__ void store_from_float<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void store_from_float<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 template <>

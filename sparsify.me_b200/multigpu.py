@@ -11,10 +11,85 @@ outputs.  Two plans:
       i.e. columns [r*N/g, (r+1)*N/g) of B and D; weights are replicated and pruned
       redundantly (<= 4.7 MB, cheaper than a broadcast).
 
-Everything here is host logic and is covered by world_size-2 gloo tests on CPU.
+The partitioning helpers are host logic covered by world_size-2 gloo tests on CPU.  `OutputGather` is the data path
+on GPUs: the C ABI's spfy_mg_* (NCCL loaded at run time) on the ranks' own communicator, bootstrapped through
+torch.distributed -- ncclAllGather straight into the documented [g][M][N/g] layout, in place, no transpose.
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def nccl_library_path():
+    """libnccl.so.2 as shipped with PyTorch (nvidia-nccl wheel), else whatever the loader finds"""
+    try:
+        import nvidia.nccl as n
+        base = os.path.dirname(n.__file__) if getattr(n, "__file__", None) else list(n.__path__)[0]
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:  # noqa: BLE001
+        pass
+    return "libnccl.so.2"
+
+
+class OutputGather:
+    """spfy_mg_* on one communicator per process (include/spfy_b200.h, "Multi-GPU").
+
+    N sharding: every rank allocates `slab_bytes * world` for a layer (or a group of layers), lets its GEMMs write
+    D_r into slab `rank` (`slab(buf)`), and `allgather(buf)` fills in the other ranks' slabs in place.
+    Layer sharding: `broadcast_many(tensors, owners)` sends each layer's output from its owner to everybody as one
+    NCCL group."""
+
+    def __init__(self, group=None):
+        from . import capi
+        self._capi = capi
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        os.environ.setdefault("SPFY_NCCL_LIB", nccl_library_path())
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            capi.spfy_mg_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        backend = dist.get_backend(group)
+        t = uid.to(dev) if backend == "nccl" else uid
+        dist.broadcast(t, src=0, group=group)  # 128 bytes over whatever the process group runs on
+        raw = bytes(t.cpu().numpy().tobytes())
+        self._h = ctypes.c_void_p()
+        capi.spfy_mg_create(self.rank, self.world, ctypes.c_char_p(raw), ctypes.byref(self._h))
+
+    def slab(self, buf, rank=None):
+        """view of rank's slab of a gather buffer whose leading dimension is the world size"""
+        return buf[self.rank if rank is None else rank]
+
+    def allgather(self, buf, stream=None):
+        """buf: [world, ...] contiguous; slab `rank` holds this rank's data, the others are filled in"""
+        assert buf.is_contiguous() and buf.shape[0] == self.world
+        per = buf[0].numel() * buf.element_size()
+        s = stream if stream is not None else torch.cuda.current_stream()
+        send = buf.data_ptr() + self.rank * per
+        self._capi.spfy_mg_allgather(self._h, ctypes.c_void_p(send), ctypes.c_void_p(buf.data_ptr()), per,
+                                     ctypes.c_void_p(s.cuda_stream))
+        return per * (self.world - 1)  # bytes this rank received
+
+    def broadcast_many(self, tensors, owners, stream=None):
+        n = len(tensors)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        sizes = (ctypes.c_size_t * n)(*[t.numel() * t.element_size() for t in tensors])
+        roots = (ctypes.c_int * n)(*owners)
+        s = stream if stream is not None else torch.cuda.current_stream()
+        self._capi.spfy_mg_broadcast_many(self._h, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(sizes, ctypes.c_void_p),
+                                          ctypes.cast(roots, ctypes.c_void_p), n, ctypes.c_void_p(s.cuda_stream))
+        return sum(t.numel() * t.element_size() for t, o in zip(tensors, owners) if o != self.rank)
+
+    def close(self):
+        if self._h:
+            self._capi.spfy_mg_destroy(self._h)
+            self._h = None
 
 
 def partition_layers_lpt(costs, world):
