@@ -921,20 +921,28 @@ def main():
     if not args.no_cpu and world == 1:
         orc = ge.load_oracle()
         line["cpu_baseline"] = cpu_baseline(spfy, orc, gemms, 0 if args.dtype == "fp16" else 1)
-    if args.per_layer:
-        per_layer_report(spfy, layers, hbm_peak, tc_sust)
+    # the drop-in call is ONE spmma per layer: its cost next to the plan's (and next to cusparseLt's single_ms / back_to_back_ms
+    # of the reference arm, which are taken the same two ways)
+    single_ms = per_layer_report(spfy, layers, hbm_peak, tc_sust, quiet=not args.per_layer)
+    line["single_call"] = {"ms_sum_over_layers": single_ms, "frac_of_hbm": spmma_bytes_step / (single_ms * 1e-3) / 1e9 / hbm_peak,
+                           "timing": "spfy_spmma per layer, median of 5 launches, L2 flushed before each",
+                           "plan_ms": spmma_ms}
     print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def per_layer_report(spfy, layers, hbm_peak, tc_peak):
-    """Per-shape timing (unique shapes), cold operands: stderr table for profiles/."""
+def per_layer_report(spfy, layers, hbm_peak, tc_peak, quiet=False):
+    """Per-shape timing of the SINGLE call spfy_spmma (what one sparsifyme::spmma issues), cold operands (L2 flushed
+    before every launch, median of 5): a stderr table for profiles/, and the sum over all layers of the table -- the
+    figure to put beside cusparseLt's `single_ms` (oracle/cusparselt_ref.cu sweep times each layer the same way)."""
     import torch
     seen = {}
+    total = 0.0
     for g, w, b, d, comp in layers:
         if g in seen:
+            total += seen[g]
             continue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=b.device)
@@ -950,8 +958,11 @@ def per_layer_report(spfy, layers, hbm_peak, tc_peak):
         by = spfy.shapes.spmma_bytes(g)
         fl = spfy.shapes.spmma_flops(g)
         seen[g] = ms
-        print(f"layer M={g.M:5d} K={g.K:5d} N={g.N:7d}  {ms*1e3:8.1f} us  {by/ms/1e6:7.0f} GB/s ({by/ms/1e6/hbm_peak:5.2f} of HBM)"
-              f"  {fl/ms/1e9:7.1f} TFLOP/s ({fl/ms/1e9/(2*tc_peak):5.2f} of sparse TC)", file=sys.stderr)
+        total += ms
+        if not quiet:
+            print(f"layer M={g.M:5d} K={g.K:5d} N={g.N:7d}  {ms*1e3:8.1f} us  {by/ms/1e6:7.0f} GB/s ({by/ms/1e6/hbm_peak:5.2f} of HBM)"
+                  f"  {fl/ms/1e9:7.1f} TFLOP/s ({fl/ms/1e9/(2*tc_peak):5.2f} of sparse TC)", file=sys.stderr)
+    return total
 
 
 if __name__ == "__main__":

@@ -178,6 +178,24 @@ static float median(std::vector<float> v) {
   return v[v.size() / 2];
 }
 
+// device-side random fill (values in [-1, 1) like `gen`, any count): timing must not run on a constant operand
+__global__ void fill_random_half(__half* p, size_t n, uint64_t seed) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint64_t z = (seed * 0x632BE59BD9B4E019ull + i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    p[i] = __float2half((float)((int64_t)(z >> 40) - (1 << 23)) / (float)(1 << 23));
+  }
+}
+
+// cusparselt_ref sweep <table.csv> <batch> : the reference's spmma call sequence (include/sparsify.me/spmma.hxx:51-114)
+// over a whole shape table in the weights orientation, as a like-for-like comparator for bench.py:
+//   * every layer keeps its own A / B / C (nothing is re-read from L2 between layers), B is random;
+//   * the kernel of every plan is chosen by cusparseLtMatmulSearch (the library's own auto-tuner), not ALG_DEFAULT;
+//   * two timings of the matmuls: each layer alone (median of 5 launches, L2 flushed before each, one event pair per
+//     launch) and the whole table BACK TO BACK (all layers enqueued one after the other, 20 steps under one event
+//     pair) -- the mode bench.py times our plan in.
 static int sweep(int argc, char** argv) {
   if (argc != 4) return 2;
   const int batch = std::atoi(argv[3]);
@@ -205,72 +223,118 @@ static int sweep(int argc, char** argv) {
   CK(cudaMalloc(&flush, flush_bytes));
   int* d_valid;
   CK(cudaMalloc(&d_valid, 4));
-  double tot_prune = 0, tot_comp = 0, tot_mm = 0, flops = 0, bytes = 0;
-  int skipped = 0;
-  for (const Shape& s : shapes) {
+  struct Layer {
+    Shape s;
+    int64_t K;
+    Problem p;
+    __half *A0 = nullptr, *A = nullptr, *B = nullptr, *C = nullptr;
+    void *Ac = nullptr, *Abuf = nullptr, *ws = nullptr;
+    float prune_ms = 0, comp_ms = 0, mm_ms = 0;
+  };
+  std::vector<Layer*> layers;
+  const float alpha = 1.f, beta = 0.f;
+  int skipped = 0, searched = 0;
+  for (size_t li = 0; li < shapes.size(); ++li) {
+    const Shape& s = shapes[li];
+    Layer* L = new Layer();
+    L->s = s;
     // cusparseLt wants k % 16 == 0 for fp16 structured operands: pad K like we do (zero columns)
-    const int64_t K = (s.K + 15) / 16 * 16, M = s.M, N = s.N;
-    __half *A0, *A, *B, *C;
-    CK(cudaMalloc(&A0, M * K * 2));
-    CK(cudaMalloc(&A, M * K * 2));
-    CK(cudaMalloc(&B, K * N * 2));
-    CK(cudaMalloc(&C, M * N * 2));
+    const int64_t K = L->K = (s.K + 15) / 16 * 16, M = s.M, N = s.N;
+    CK(cudaMalloc(&L->A0, M * K * 2));
+    CK(cudaMalloc(&L->A, M * K * 2));
+    CK(cudaMalloc(&L->B, K * N * 2));
+    CK(cudaMalloc(&L->C, M * N * 2));
     {
       std::vector<__half> hA(M * K);
-      for (int64_t i = 0; i < M * K; ++i) hA[i] = __float2half((i % K) < s.K ? gen(1, i) : 0.f);
-      CK(cudaMemcpy(A0, hA.data(), M * K * 2, cudaMemcpyHostToDevice));
-      CK(cudaMemset(B, 0x3c, K * N * 2));  // fp16 1.0586: timing does not depend on the values
+      for (int64_t i = 0; i < M * K; ++i) hA[i] = __float2half((i % K) < s.K ? gen(1 + li, i) : 0.f);
+      CK(cudaMemcpy(L->A0, hA.data(), M * K * 2, cudaMemcpyHostToDevice));
+      fill_random_half<<<1184, 256>>>(L->B, (size_t)K * N, 1000 + li);
+      CK(cudaGetLastError());
     }
-    Problem p;
-    if (p.init(&h, M, N, K)) {
+    if (L->p.init(&h, M, N, K)) {
       ++skipped;
+      delete L;
       continue;
     }
     size_t csz = 0, cbuf = 0;
-    CKS(cusparseLtSpMMACompressedSize(&h, &p.plan, &csz, &cbuf));
-    void *Ac, *Abuf = nullptr, *ws = nullptr;
-    CK(cudaMalloc(&Ac, csz));
-    if (cbuf) CK(cudaMalloc(&Abuf, cbuf));
-    if (p.ws) CK(cudaMalloc(&ws, p.ws));
-    float alpha = 1.f, beta = 0.f;
-    std::vector<float> tp, tc, tm;
-    for (int it = 0; it < 7; ++it) {
+    CKS(cusparseLtSpMMACompressedSize(&h, &L->p.plan, &csz, &cbuf));
+    CK(cudaMalloc(&L->Ac, csz));
+    if (cbuf) CK(cudaMalloc(&L->Abuf, cbuf));
+    // prune + compress, timed like the reference's phases (spmma.hxx:82-104)
+    std::vector<float> tp, tc;
+    for (int it = 0; it < 5; ++it) {
       float ms;
-      CK(cudaMemcpy(A, A0, M * K * 2, cudaMemcpyDeviceToDevice));
-      CK(cudaMemsetAsync(flush, it, flush_bytes, 0));
+      CK(cudaMemcpy(L->A, L->A0, M * K * 2, cudaMemcpyDeviceToDevice));
       CK(cudaEventRecord(e0, 0));
-      CKS(cusparseLtSpMMAPrune(&h, &p.mm, A, A, CUSPARSELT_PRUNE_SPMMA_STRIP, 0));
-      CKS(cusparseLtSpMMAPruneCheck(&h, &p.mm, A, d_valid, 0));
+      CKS(cusparseLtSpMMAPrune(&h, &L->p.mm, L->A, L->A, CUSPARSELT_PRUNE_SPMMA_STRIP, 0));
+      CKS(cusparseLtSpMMAPruneCheck(&h, &L->p.mm, L->A, d_valid, 0));
       CK(cudaEventRecord(e1, 0));
       CK(cudaEventSynchronize(e1));
       CK(cudaEventElapsedTime(&ms, e0, e1));
       if (it >= 2) tp.push_back(ms);
       CK(cudaEventRecord(e0, 0));
-      CKS(cusparseLtSpMMACompress(&h, &p.plan, A, Ac, Abuf, 0));
+      CKS(cusparseLtSpMMACompress(&h, &L->p.plan, L->A, L->Ac, L->Abuf, 0));
       CK(cudaEventRecord(e1, 0));
       CK(cudaEventSynchronize(e1));
       CK(cudaEventElapsedTime(&ms, e0, e1));
       if (it >= 2) tc.push_back(ms);
+    }
+    L->prune_ms = median(tp);
+    L->comp_ms = median(tc);
+    // the library's auto-tuner picks the kernel (it may need a larger workspace than the default algorithm)
+    {
+      size_t ws_max = std::max<size_t>(L->p.ws, 64ull << 20);
+      CK(cudaMalloc(&L->ws, ws_max));
+      cusparseStatus_t st = cusparseLtMatmulSearch(&h, &L->p.plan, &alpha, L->Ac, L->B, &beta, L->C, L->C, L->ws, nullptr, 0);
+      if (st == CUSPARSE_STATUS_SUCCESS) {
+        ++searched;
+        size_t need = 0;
+        CKS(cusparseLtMatmulGetWorkspace(&h, &L->p.plan, &need));
+        if (need > ws_max) {
+          cudaFree(L->ws);
+          CK(cudaMalloc(&L->ws, need));
+        }
+      }
+    }
+    layers.push_back(L);
+  }
+  // ---- each layer alone, L2 flushed before every launch ----
+  double tot_prune = 0, tot_comp = 0, tot_mm = 0, flops = 0, bytes = 0;
+  for (Layer* L : layers) {
+    std::vector<float> tm;
+    for (int it = 0; it < 7; ++it) {
+      float ms;
       CK(cudaMemsetAsync(flush, it + 1, flush_bytes, 0));
       CK(cudaEventRecord(e0, 0));
-      CKS(cusparseLtMatmul(&h, &p.plan, &alpha, Ac, B, &beta, C, C, ws, nullptr, 0));
+      CKS(cusparseLtMatmul(&h, &L->p.plan, &alpha, L->Ac, L->B, &beta, L->C, L->C, L->ws, nullptr, 0));
       CK(cudaEventRecord(e1, 0));
       CK(cudaEventSynchronize(e1));
       CK(cudaEventElapsedTime(&ms, e0, e1));
       if (it >= 2) tm.push_back(ms);
     }
-    const float pm = median(tp), cm = median(tc), mm = median(tm);
-    std::printf("layer M=%lld K=%lld N=%lld prune %.4f ms compress %.4f ms matmul %.4f ms (%.1f TFLOP/s)\n",
-                (long long)M, (long long)s.K, (long long)N, pm, cm, mm, 2.0 * M * N * s.K / mm / 1e9);
-    tot_prune += pm;
-    tot_comp += cm;
-    tot_mm += mm;
-    flops += 2.0 * M * N * s.K;
-    bytes += 2.0 * s.K * N + 2.0 * M * N + 1.125 * M * s.K;
-    p.destroy();
-    cudaFree(A0); cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Ac);
-    if (Abuf) cudaFree(Abuf);
-    if (ws) cudaFree(ws);
+    L->mm_ms = median(tm);
+    const Shape& s = L->s;
+    std::printf("layer M=%lld K=%lld N=%lld prune %.4f ms compress %.4f ms matmul %.4f ms (%.1f TFLOP/s)\n", (long long)s.M,
+                (long long)s.K, (long long)s.N, L->prune_ms, L->comp_ms, L->mm_ms, 2.0 * s.M * s.N * s.K / L->mm_ms / 1e9);
+    tot_prune += L->prune_ms;
+    tot_comp += L->comp_ms;
+    tot_mm += L->mm_ms;
+    flops += 2.0 * s.M * s.N * s.K;
+    bytes += 2.0 * s.K * s.N + 2.0 * s.M * s.N + 1.125 * s.M * s.K;
+  }
+  // ---- the whole table back to back: 3 warm-up steps, 20 timed steps under one event pair ----
+  float b2b_ms = 0;
+  {
+    const int steps = 20;
+    for (int it = 0; it < 3 + steps; ++it) {
+      if (it == 3) CK(cudaEventRecord(e0, 0));
+      for (Layer* L : layers)
+        CKS(cusparseLtMatmul(&h, &L->p.plan, &alpha, L->Ac, L->B, &beta, L->C, L->C, L->ws, nullptr, 0));
+    }
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&b2b_ms, e0, e1));
+    b2b_ms /= steps;
   }
   int ver = 0;
   cusparseLtGetProperty(MAJOR_VERSION, &ver);
@@ -278,11 +342,14 @@ static int sweep(int argc, char** argv) {
   cusparseLtGetProperty(MINOR_VERSION, &minor);
   cusparseLtGetProperty(PATCH_LEVEL, &patch);
   std::printf("{\"library\": \"cusparseLt %d.%d.%d\", \"layers\": %zu, \"skipped\": %d, \"dtype\": \"f16\", "
-              "\"compute\": \"32F\", \"timing\": \"median of 5 single launches, L2 flushed before each\", "
-              "\"prune_ms\": %.4f, \"compress_ms\": %.4f, \"matmul_ms\": %.4f, "
-              "\"matmul_tflops\": %.2f, \"matmul_gbs\": %.1f, \"total_tflops\": %.2f}\n",
-              ver, minor, patch, shapes.size(), skipped, tot_prune, tot_comp, tot_mm, flops / tot_mm / 1e9,
-              bytes / tot_mm / 1e6, flops / (tot_mm + tot_prune + tot_comp) / 1e9);
+              "\"compute\": \"32F\", \"search\": %s, \"searched_layers\": %d, \"operands\": \"per-layer buffers, random B\", "
+              "\"timing\": \"single_ms: sum over layers of the median of 5 launches, L2 flushed before each; "
+              "back_to_back_ms: all layers enqueued back to back, mean of 20 steps under one event pair\", "
+              "\"prune_ms\": %.4f, \"compress_ms\": %.4f, \"matmul_ms\": %.4f, \"single_ms\": %.4f, \"back_to_back_ms\": %.4f, "
+              "\"matmul_tflops\": %.2f, \"matmul_gbs\": %.1f, \"back_to_back_tflops\": %.2f, \"total_tflops\": %.2f}\n",
+              ver, minor, patch, shapes.size(), skipped, searched == (int)layers.size() ? "true" : "false", searched,
+              tot_prune, tot_comp, tot_mm, tot_mm, b2b_ms, flops / tot_mm / 1e9, bytes / tot_mm / 1e6, flops / b2b_ms / 1e9,
+              flops / (tot_mm + tot_prune + tot_comp) / 1e9);
   cusparseLtDestroy(&h);
   return 0;
 }
