@@ -117,10 +117,14 @@ SPFY_API int spfy_compressed_bytes(int dtype, size_t rows, size_t cols, int layo
 SPFY_API int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in,
                           void* out_dense, size_t ld_out, void* comp_vals, void* meta,
                           uint64_t* mask, size_t rows, size_t cols, spfy_stream_t stream);
-/* Whole-model variant: prune+compress `count` matrices (STRIP_MAG) in as few launches as
- * possible.  The per-layer weight matrices of datasets/ *.csv are <= 4.7 MB, so one launch
- * per layer is launch-latency-bound; this is the call the prune GB/s figure is quoted on.
- * `items` is a HOST array; fields as in spfy_prune24 (null outputs are skipped). */
+/* Whole-model variant: prune+compress `count` matrices in as few launches as possible (one
+ * per 96 matrices).  The per-layer weight matrices of datasets/ *.csv are <= 4.7 MB, so one
+ * launch per layer is launch-latency-bound; this is the call the prune GB/s figure is quoted
+ * on (mode STRIP_MAG).  TILE_MAG -- the algorithm the reference requests (spmma.hxx:86) --
+ * needs out_dense per item (it may alias the input) and takes the one-pass prune + compress
+ * kernel for every matrix with cols % 16 == 0 and 8-byte aligned rows; the others (k = 147)
+ * go through spfy_prune24 one by one.  `items` is a HOST array; fields as in spfy_prune24
+ * (null outputs are skipped). */
 typedef struct spfy_prune24_item {
   const void* in;
   size_t ld_in;
@@ -130,7 +134,7 @@ typedef struct spfy_prune24_item {
   void* meta;
   size_t rows, cols;
 } spfy_prune24_item;
-SPFY_API int spfy_prune24_batched(int dtype, int layout, const spfy_prune24_item* items,
+SPFY_API int spfy_prune24_batched(int dtype, int mode, int layout, const spfy_prune24_item* items,
                                   size_t count, spfy_stream_t stream);
 /* A dense matrix obeys 2:4 along its rows iff *d_invalid == 0 afterwards
  * (same convention as cusparseLtSpMMAPruneCheck, spmma.hxx:88-94). */

@@ -48,7 +48,7 @@ SIGNATURES = {
     "spfy_compressed_bytes": (c_int, [c_int, _SZ, _SZ, c_int, POINTER(_SZ), POINTER(_SZ)]),
     "spfy_prune24": (c_int, [c_int, c_int, c_int, _P, _SZ, _P, _SZ, _P, _P, _P, _SZ, _SZ, _P]),
     "spfy_prune24_check": (c_int, [c_int, _P, _SZ, _SZ, _SZ, _P, _P]),
-    "spfy_prune24_batched": (c_int, [c_int, c_int, _P, _SZ, _P]),
+    "spfy_prune24_batched": (c_int, [c_int, c_int, c_int, _P, _SZ, _P]),
     "spfy_spmma_workspace_bytes": (c_int, [c_int, _SZ, _SZ, _SZ, POINTER(_SZ)]),
     "spfy_spmma": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, c_float, _P, _SZ,
                            _P, _SZ, _P, _SZ, _P]),

@@ -670,15 +670,18 @@ prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __re
 // (quad shuffles assemble the unit's metadata word) and a warp's 32 tiles are one 128-byte line of a value
 // tile.  The iteration domain is the padded one of the layout (SM100: 128-row x 128-column tiles; padding is
 // read as +0 and comes out as zeros with the neutral nibble 0x4).
-template <bool BF16>
-__global__ void __launch_bounds__(256)
-prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
+// number of 4x4 tiles of the (padded) iteration domain, and tiles per tile row
+__device__ __host__ __forceinline__ size_t tile_fused_total(const Prune24Params& P, uint32_t* tiles_c) {
   const uint32_t dom_cols = P.tile_order ? P.k_tiles * 128u : P.cols;
-  const uint32_t tiles_c = dom_cols / 4u, tiles_r = (P.dom_rows + 3u) / 4u;
-  const size_t total = (size_t)tiles_r * tiles_c;  // tiles_c % 4 == 0: a quad of lanes never straddles a tile row
-  const uint32_t lane = threadIdx.x & 31u;
-  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-  for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += nthreads) {
+  *tiles_c = dom_cols / 4u;  // % 4 == 0: a quad of lanes never straddles a tile row
+  return (size_t)((P.dom_rows + 3u) / 4u) * *tiles_c;
+}
+
+// one warp, 32 consecutive tiles starting at `base` (a multiple of 32)
+template <bool BF16>
+__device__ __forceinline__ void tile_fused_warp(const Prune24Params& P, size_t base, size_t total, uint32_t tiles_c,
+                                                uint32_t lane) {
+  {
     const size_t t = base + lane;
     const bool active = t < total;
     const uint32_t tr = !active ? 0u : (total >> 32) == 0 ? (uint32_t)t / tiles_c : (uint32_t)(t / tiles_c);
@@ -726,6 +729,42 @@ prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
         if (P.meta && (lane & 3u) == 0u)
           *reinterpret_cast<uint16_t*>(P.meta + (size_t)row * P.mb + tc / 2u) = (uint16_t)nibs;
       }
+    }
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
+  uint32_t tiles_c;
+  const size_t total = tile_fused_total(P, &tiles_c);
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += nthreads)
+    tile_fused_warp<BF16>(P, base, total, tiles_c, lane);
+}
+
+// TILE prune + compress of many matrices in one launch (what sparsifyme::spmma asks for, spmma.hxx:86, over a whole
+// model's weight set): CTA tiles of 1024 4x4 tiles, each belonging to exactly one matrix (binary search as above)
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+prune24_tile_batched_kernel(const __grid_constant__ Prune24Batch Bt) {
+  const uint32_t tiles = Bt.tile_prefix[Bt.count];
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int lo = 0, hi = Bt.count - 1;  // last item with tile_prefix <= tile
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (Bt.tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+    }
+    const Prune24Params& P = Bt.item[lo];
+    uint32_t tiles_c;
+    const size_t total = tile_fused_total(P, &tiles_c);
+    const size_t first = (size_t)(tile - Bt.tile_prefix[lo]) * 1024u;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const size_t base = first + i * 256 + (threadIdx.x & ~31u);
+      if (base < total) tile_fused_warp<BF16>(P, base, total, tiles_c, lane);
     }
   }
 }
@@ -833,6 +872,8 @@ void spfy::warm_prune_kernels() {
   touch_kernel(prune24_strip_kernel);
   touch_kernel(prune24_fast_kernel);
   touch_kernel(prune24_batched_kernel);
+  touch_kernel(prune24_tile_batched_kernel<false>);
+  touch_kernel(prune24_tile_batched_kernel<true>);
   touch_kernel(prune24_tile_kernel<false, false>);
   touch_kernel(prune24_tile_kernel<false, true>);
   touch_kernel(prune24_tile_kernel<true, false>);
@@ -910,6 +951,13 @@ int spfy_compressed_bytes(int dtype, size_t rows, size_t cols, int layout, size_
   return SPFY_OK;
 }
 
+// can this TILE_MAG request go through the one-pass prune + compress kernel?
+static bool tile_fused_ok(const void* in, size_t ld_in, const void* out_dense, size_t ld_out, const void* comp_vals,
+                          const void* meta, const uint64_t* mask, size_t cols) {
+  const bool vec = cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && (uintptr_t)in % 8 == 0 && (uintptr_t)out_dense % 8 == 0;
+  return (comp_vals || meta) && !mask && vec && cols % 16 == 0 && (uintptr_t)meta % 2 == 0 && (uintptr_t)comp_vals % 4 == 0;
+}
+
 int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, void* out_dense,
                  size_t ld_out, void* comp_vals, void* meta, uint64_t* mask, size_t rows,
                  size_t cols, spfy_stream_t stream) {
@@ -938,8 +986,7 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
       const char* e = dev_switch("SPFY_TILE_FUSED_MAX");
       return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)8 << 20;
     }();
-    if ((comp_vals || meta) && !mask && vec && cols % 16 == 0 && (uintptr_t)meta % 2 == 0 && (uintptr_t)comp_vals % 4 == 0 &&
-        rows * cols <= fused_max) {
+    if (tile_fused_ok(src, ld_in, out_dense, ld_out, comp_vals, meta, mask, cols) && rows * cols <= fused_max) {
       // one pass: prune + compress (see prune24_tile_fused_kernel)
       Prune24Params P;
       int rcf = fill_prune24(&P, layout, src, ld_in, out_dense, ld_out, comp_vals, meta, nullptr, rows, cols);
@@ -993,10 +1040,11 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
   return SPFY_OK;
 }
 
-int spfy_prune24_batched(int dtype, int layout, const spfy_prune24_item* items, size_t count,
+int spfy_prune24_batched(int dtype, int mode, int layout, const spfy_prune24_item* items, size_t count,
                          spfy_stream_t stream) {
   if (dtype != SPFY_F16 && dtype != SPFY_BF16)
     return fail(SPFY_E_UNSUPPORTED, "prune24_batched: dtype %d (need F16/BF16)", dtype);
+  if (mode != SPFY_PRUNE_STRIP_MAG && mode != SPFY_PRUNE_TILE_MAG) return fail(SPFY_E_INVALID, "prune24_batched: bad mode %d", mode);
   if (layout != SPFY_LAYOUT_CANONICAL && layout != SPFY_LAYOUT_SM100)
     return fail(SPFY_E_INVALID, "prune24_batched: bad layout %d", layout);
   if (count && !items) return fail(SPFY_E_INVALID, "prune24_batched: null item table");
@@ -1004,6 +1052,7 @@ int spfy_prune24_batched(int dtype, int layout, const spfy_prune24_item* items, 
   int rc = device_info(&di);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  const bool tile = mode == SPFY_PRUNE_TILE_MAG;
   static thread_local Prune24Batch Bt;  // 10 KB: keep it off the stack
   size_t i = 0;
   while (i < count) {
@@ -1017,11 +1066,22 @@ int spfy_prune24_batched(int dtype, int layout, const spfy_prune24_item* items, 
         return fail(SPFY_E_INVALID, "prune24_batched: item %zu leading dimension smaller than cols", i);
       if (it.rows >= (1ull << 31) || it.cols >= (1ull << 31))
         return fail(SPFY_E_UNSUPPORTED, "prune24_batched: item %zu too large", i);
+      if (tile && !it.out_dense)
+        return fail(SPFY_E_INVALID, "prune24_batched: item %zu: TILE_MAG needs out_dense (it may alias the input)", i);
+      if (tile && !tile_fused_ok(it.in, it.ld_in, it.out_dense, it.ld_out, it.comp_vals, it.meta, nullptr, it.cols)) {
+        // ragged / unaligned matrix (k = 147): the general two-pass route, on its own
+        rc = spfy_prune24(dtype, mode, layout, it.in, it.ld_in, it.out_dense, it.ld_out, it.comp_vals, it.meta, nullptr,
+                          it.rows, it.cols, stream);
+        if (rc) return rc;
+        continue;
+      }
       Prune24Params& P = Bt.item[Bt.count];
       rc = fill_prune24(&P, layout, (const uint16_t*)it.in, it.ld_in, it.out_dense, it.ld_out,
                         it.comp_vals, it.meta, nullptr, it.rows, it.cols);
       if (rc) return rc;
-      const size_t tiles = P.fast ? fast_passes(P) : ceil_div((size_t)P.dom_rows * P.units_per_row, 1024);
+      uint32_t tiles_c = 0;
+      const size_t tiles = tile ? ceil_div(tile_fused_total(P, &tiles_c), 1024)
+                                : (P.fast ? fast_passes(P) : ceil_div((size_t)P.dom_rows * P.units_per_row, 1024));
       if ((size_t)Bt.tile_prefix[Bt.count] + tiles >= (1ull << 32))
         return fail(SPFY_E_UNSUPPORTED, "prune24_batched: batch too large");
       Bt.tile_prefix[Bt.count + 1] = Bt.tile_prefix[Bt.count] + (uint32_t)tiles;
@@ -1030,8 +1090,15 @@ int spfy_prune24_batched(int dtype, int layout, const spfy_prune24_item* items, 
     if (Bt.count == 0) continue;
     const uint32_t tiles = Bt.tile_prefix[Bt.count];
     const uint32_t cap = (uint32_t)di.sm_count * 16;
-    prune24_batched_kernel<<<tiles < cap ? tiles : cap, 256, 0, s>>>(Bt);
-    SPFY_LAUNCH_OK("prune24_batched_kernel");
+    const uint32_t grid = tiles < cap ? tiles : cap;
+    if (!tile) {
+      prune24_batched_kernel<<<grid, 256, 0, s>>>(Bt);
+      SPFY_LAUNCH_OK("prune24_batched_kernel");
+    } else {
+      if (dtype == SPFY_BF16) prune24_tile_batched_kernel<true><<<grid, 256, 0, s>>>(Bt);
+      else prune24_tile_batched_kernel<false><<<grid, 256, 0, s>>>(Bt);
+      SPFY_LAUNCH_OK("prune24_tile_batched_kernel");
+    }
   }
   return SPFY_OK;
 }

@@ -121,14 +121,18 @@ def prune24_check(a):
     return int(flag.item())
 
 
-def prune24_batched(mats, comps, layout=capi.LAYOUT_SM100):
+def prune24_batched(mats, comps, layout=capi.LAYOUT_SM100, mode=capi.PRUNE_STRIP_MAG, inplace=False):
     """Prune+compress a whole list of weight matrices with as few launches as possible
-    (spfy_prune24_batched).  `mats`: 2-D row-major tensors; `comps`: matching Compressed24."""
+    (spfy_prune24_batched).  `mats`: 2-D row-major tensors; `comps`: matching Compressed24.
+    mode=PRUNE_TILE_MAG (what the reference asks cusparseLt for, spmma.hxx:86) prunes the matrices IN PLACE
+    like cusparseLtSpMMAPrune(dA, dA) -- TILE needs the dense pruned matrix as an output; `inplace` asks for the
+    same with STRIP."""
     items = (capi.Prune24Item * len(mats))()
+    dense = inplace or mode == capi.PRUNE_TILE_MAG
     for i, (a, c) in enumerate(zip(mats, comps)):
-        items[i] = capi.Prune24Item(a.data_ptr(), a.stride(0), None, 0, c.vals.data_ptr(), c.meta.data_ptr(),
-                                    a.shape[0], a.shape[1])
-    capi.spfy_prune24_batched(_dtype_code(mats[0]), layout, ctypes.cast(items, ctypes.c_void_p), len(mats),
+        items[i] = capi.Prune24Item(a.data_ptr(), a.stride(0), a.data_ptr() if dense else None, a.stride(0) if dense else 0,
+                                    c.vals.data_ptr(), c.meta.data_ptr(), a.shape[0], a.shape[1])
+    capi.spfy_prune24_batched(_dtype_code(mats[0]), mode, layout, ctypes.cast(items, ctypes.c_void_p), len(mats),
                               _stream())
 
 

@@ -297,11 +297,39 @@ def test_prune24_batched_equals_single(spfy, orc, cuda):
     items = (Item * len(shapes))()
     for i, ((r, c), a, (v, m)) in enumerate(zip(shapes, ins, comps)):
         items[i] = Item(a.data_ptr(), a.stride(0), None, 0, v.data_ptr(), m.data_ptr(), r, c)
-    spfy.capi.spfy_prune24_batched(spfy.F16, spfy.LAYOUT_SM100, ctypes.cast(items, ctypes.c_void_p), len(shapes),
-                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    spfy.capi.spfy_prune24_batched(spfy.F16, spfy.PRUNE_STRIP_MAG, spfy.LAYOUT_SM100, ctypes.cast(items, ctypes.c_void_p),
+                                   len(shapes), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     for (v, m), s in zip(comps, singles):
         assert torch.equal(v, s.vals) and torch.equal(m, s.meta)
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+def test_prune24_batched_tile_mode(spfy, orc, cuda, dt):
+    """TILE_MAG over a whole weight set in one launch (plus the ragged first-conv matrix, which takes the general
+    route on its own): pruned in place like cusparseLtSpMMAPrune(dA, dA) (spmma.hxx:86), bit-exact with the oracle's
+    cusparseLt-pinned TILE selection, compressed operand identical to the single call's"""
+    tdt = torch.float16 if dt == 0 else torch.bfloat16
+    shapes = [(64, 147), (64, 576), (128, 1152), (256, 2304), (130, 256), (512, 512), (64, 64)] * 15  # > 96 items
+    mats, comps, want_dense, singles = [], [], [], []
+    for i, (r, c) in enumerate(shapes):
+        bits = rand_bits(orc, dt, (r, c), seed=2000 + i)
+        a = to_dev(bits, dt, cuda)
+        mats.append(a)
+        comps.append(spfy.alloc_compressed(tdt, r, c, cuda))
+        if i < 7:
+            want_dense.append(orc.prune24_tile(dt, bits)[0])
+        ref = a.clone()
+        singles.append(spfy.prune24(ref, inplace=True, mode=spfy.PRUNE_TILE_MAG))
+    before = spfy.launch_count()
+    spfy.prune24_batched(mats, comps, mode=spfy.PRUNE_TILE_MAG)
+    torch.cuda.synchronize()
+    # 90 eligible matrices -> one batched launch; 15 ragged ones -> tile + compress kernels each
+    assert spfy.launch_count() - before == 1 + 15 * 2
+    for i, want in enumerate(want_dense):
+        assert np.array_equal(bits_of(mats[i]), want), shapes[i]
+    for c, s_ in zip(comps, singles):
+        assert torch.equal(c.vals, s_.vals) and torch.equal(c.meta, s_.meta)
 
 
 # ------------------------------------------------------------------ A4 spmma
