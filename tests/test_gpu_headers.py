@@ -151,3 +151,22 @@ def test_our_example_drivers_run(cuda, name, argv):
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
     assert "sparsify.me:" not in r.stderr, r.stderr[-2000:]
     assert r.stdout.strip()
+
+
+def test_profiling_drivers_keep_the_reference_command_lines(cuda, tmp_path):
+    """profiling/gemm_timing <f|h|d> out.csv [shapes.csv] -> "m,n,k,b,elapsed" rows (reference profiling/gemm_timing.cu:38-43,110);
+    profiling/spmm_timing m n k b -> "prune, compress, multiply" ms (profiling/spmm_timing.cu:64-66)"""
+    gt, st = os.path.join(ROOT, "profiling", "gemm_timing"), os.path.join(ROOT, "profiling", "spmm_timing")
+    assert os.path.exists(gt) and os.path.exists(st), "profiling/ is not built: run __graft_entry__.build()"
+    table = tmp_path / "shapes.csv"
+    table.write_text("m,n,k,b\r\n392,64,147,4\r\n196,128,256,4\r\n")
+    for prec in ("f", "h"):
+        out = tmp_path / f"gemm_{prec}.csv"
+        r = subprocess.run([gt, prec, str(out), str(table)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "sparsify.me:" not in r.stderr, (r.stdout + r.stderr)[-2000:]
+        rows = out.read_text().strip().splitlines()
+        assert rows[0] == "m,n,k,b,elapsed" and len(rows) == 3
+        assert rows[1].startswith("392,64,147,4,") and float(rows[1].split(",")[4]) > 0
+    r = subprocess.run([st, "128", "256", "512", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "sparsify.me:" not in r.stderr, (r.stdout + r.stderr)[-2000:]
+    assert len([float(x) for x in r.stdout.strip().split(",")]) == 3
