@@ -127,7 +127,7 @@ float strided_coo(std::size_t A_num_rows,
   t.begin(stream);  // like the reference, the interval covers set-up + workspace + SpMM (:155-187)
   const std::size_t ldb = B_num_rows, ldc = A_num_rows;
   std::size_t ws_bytes = 0;
-  detail::ok(spfy_spmm_workspace_bytes(SPARSIFYME_SPMM_ALG, A_num_rows, A_num_cols, A_nnz, &ws_bytes),
+  detail::ok(spfy_spmm_workspace_bytes(SPARSIFYME_SPMM_ALG, A_num_rows, A_num_cols, B_num_cols, num_batches, A_nnz, &ws_bytes),
              "batched::strided_coo");
   detail::scratch ws(ws_bytes, stream);
   detail::ok(spfy_spmm_coo_strided_batched(SPARSIFYME_SPMM_ALG, A_num_rows, A_num_cols, A_nnz, B_num_cols, num_batches, dA_rows,

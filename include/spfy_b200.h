@@ -262,11 +262,13 @@ enum {
  * (ldc >= m, :161,:173).  fp32 values, int32 indices, fp32 accumulate.
  * The COO triplets must be sorted by row (any column order; repeated (row, col)
  * entries add, like cuSPARSE); row_ptr is built internally in the workspace.
- * The workspace query takes the algorithm: the tensor-core route keeps the dense
- * m x k fp32 image of A there (a workspace sized for CUDA_CORE makes DEFAULT take
- * the CUDA-core kernels).
+ * The workspace query takes the algorithm and the batch extent: the tensor-core route keeps
+ * the dense m x k fp32 image of A there and, when ldb = k is not a multiple of 16 bytes
+ * (k = 147), a padded copy of every B_b (a workspace sized for CUDA_CORE makes DEFAULT
+ * take the CUDA-core kernels).
  * ---------------------------------------------------------------------- */
-SPFY_API int spfy_spmm_workspace_bytes(int alg, size_t m, size_t k, size_t nnz, size_t* bytes);
+SPFY_API int spfy_spmm_workspace_bytes(int alg, size_t m, size_t k, size_t n, size_t num_batches,
+                                       size_t nnz, size_t* bytes);
 SPFY_API int spfy_spmm_coo_strided_batched(int alg, size_t m, size_t k, size_t nnz, size_t n,
                                            size_t num_batches, const int32_t* row_idx,
                                            const int32_t* col_idx, const float* vals,

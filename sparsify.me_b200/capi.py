@@ -66,7 +66,7 @@ SIGNATURES = {
     "spfy_threshold_to_coo": (c_int, [c_int, _P, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, _P, _P,
                                       _P, _SZ, _P]),
     "spfy_coo_to_csr": (c_int, [_P, _SZ, _SZ, _P, _P]),
-    "spfy_spmm_workspace_bytes": (c_int, [c_int, _SZ, _SZ, _SZ, POINTER(_SZ)]),
+    "spfy_spmm_workspace_bytes": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _SZ, POINTER(_SZ)]),
     "spfy_spmm_coo_strided_batched": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P,
                                               _SZ, _SZ, c_float, c_float, _P, _SZ, _P]),
     "spfy_spmm_csr_strided_batched": (c_int, [c_int, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _SZ, _SZ, _P, _SZ,

@@ -121,7 +121,7 @@ int spfy_init(void) {
         float* Bm = reinterpret_cast<float*>(vals);             // >= 8 KiB: reuse the compressed-operand area as B, C
         size_t tws = 0, sws = 0;
         (void)spfy_threshold_workspace_bytes(128, 128, &tws);
-        (void)spfy_spmm_workspace_bytes(SPFY_SPMM_ALG_CUDA_CORE, 128, 128, 16384, &sws);
+        (void)spfy_spmm_workspace_bytes(SPFY_SPMM_ALG_CUDA_CORE, 128, 128, 8, 1, 16384, &sws);
         if (tws <= 32768 && sws <= 32768 && vb >= 2 * 128 * 8 * sizeof(float)) {
           float* Cm = Bm + 128 * 8;
           (void)spfy_threshold_to_coo(SPFY_F32, W, 128, 128, 128, 0.5f, ri, ci, va, 16384, nnz, rp, ws, 32768, nullptr);

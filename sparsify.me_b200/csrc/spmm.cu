@@ -1399,12 +1399,18 @@ int spfy_coo_to_csr(const int32_t* row_idx, size_t nnz, size_t rows, int32_t* ro
 static bool alg_ok(int alg) { return alg >= SPFY_SPMM_ALG_DEFAULT && alg <= SPFY_SPMM_ALG_TENSOR_FAST; }
 static bool alg_may_use_tensor(int alg) { return alg != SPFY_SPMM_ALG_CUDA_CORE; }
 
-int spfy_spmm_workspace_bytes(int alg, size_t m, size_t k, size_t nnz, size_t* bytes) {
+// padded copy of all B_b when their leading dimension is not a multiple of 16 bytes (k = 147: the first conv layer)
+static size_t spmm_repack_ws(size_t k, size_t n, size_t num_batches) {
+  return k % 4 ? 512 + round_up(num_batches * n * dense_ld(k, 4) * sizeof(float), 256) : 0;
+}
+
+int spfy_spmm_workspace_bytes(int alg, size_t m, size_t k, size_t n, size_t num_batches, size_t nnz, size_t* bytes) {
   (void)nnz;
   if (!alg_ok(alg)) return fail(SPFY_E_INVALID, "spmm_workspace_bytes: bad algorithm %d", alg);
-  // row_ptr (COO entry) + the device flag words (+ the dense fp32 image of A for the tensor-core route)
+  // row_ptr (COO entry) + the device flag words (+ the dense fp32 image of A for the tensor-core route, + the padded
+  // copy of B when ldb = k is not TMA-addressable)
   size_t need = spmm_base_ws(m);
-  if (alg_may_use_tensor(alg)) need += round_up(m * dense_ld(k, 4) * sizeof(float), 256);
+  if (alg_may_use_tensor(alg)) need += round_up(m * dense_ld(k, 4) * sizeof(float), 256) + spmm_repack_ws(k, n, num_batches);
   if (bytes) *bytes = need;
   return SPFY_OK;
 }
@@ -1439,18 +1445,30 @@ static int spmm_csr_impl(int alg, size_t m, size_t k, size_t n, size_t num_batch
   const size_t dense_bytes = round_up(m * ld * sizeof(float), 256);
   float* dense = reinterpret_cast<float*>((uint8_t*)workspace + base);
   TcGemmProblem gp = coo_dense_problem(dense, ld, m, k, n, num_batches, B, ldb, strideB, C, ldc, strideC, alpha, beta);
-  bool tensor = false;
+  bool tensor = false, repack = false;
+  size_t gemm_ws_bytes = 0;
   if (alg_may_use_tensor(alg)) {
     const bool forced = alg != SPFY_SPMM_ALG_DEFAULT;
-    // (B_b is the big streamed operand here: a padded copy of it would cost a pass over all of B, so operands
-    // TMA cannot address -- k = 147 -- stay on the CUDA-core kernels)
     int trc = workspace_bytes >= base + dense_bytes ? tc_gemm_supported(SPFY_F32, gp, false)
                                                     : fail(SPFY_E_WORKSPACE, "spmm_csr: workspace %zu < %zu bytes for the "
                                                            "tensor-core route", workspace_bytes, base + dense_bytes);
+    if (trc == SPFY_E_UNSUPPORTED && tc_gemm_supported(SPFY_F32, gp, true) == SPFY_OK) {
+      // B_b is not TMA-addressable as given (ldb = k = 147 floats): the GEMM can run on a padded copy, one extra pass
+      // over all of B -- taken when the caller sized the workspace for it (and, if the choice is ours, only for an A
+      // dense enough that the CUDA-core kernels lose by more than that pass: 20 % non-zeros)
+      gemm_ws_bytes = tc_gemm_workspace_bytes(SPFY_F32, &gp, 1);
+      if (workspace_bytes >= base + dense_bytes + gemm_ws_bytes + 256) {
+        trc = SPFY_OK;
+        repack = true;
+      } else {
+        trc = fail(SPFY_E_WORKSPACE, "spmm_csr: workspace %zu < %zu bytes for the tensor-core route with a padded copy of B",
+                   workspace_bytes, base + dense_bytes + gemm_ws_bytes + 256);
+      }
+    }
     if (trc != SPFY_OK && forced) return trc;
     tensor = trc == SPFY_OK;
   }
-  const double dense_from = tensor ? (alg == SPFY_SPMM_ALG_DEFAULT ? tensor_density() : 0.0) : walk_density();
+  const double dense_from = tensor ? (alg == SPFY_SPMM_ALG_DEFAULT ? (repack ? 0.2 : tensor_density()) : 0.0) : walk_density();
   const double dense_nnz_f = dense_from * (double)m * (double)k;
   const uint32_t dense_nnz = dense_nnz_f >= 4294967295.0 ? 0xffffffffu : (uint32_t)dense_nnz_f;
   // host-side choice when nnz is known, device-side (flag) otherwise
@@ -1514,7 +1532,8 @@ static int spmm_csr_impl(int alg, size_t m, size_t k, size_t n, size_t num_batch
       SPFY_LAUNCH_OK("csr_scatter_kernel");
     }
   }
-  return tc_gemm_run(SPFY_F32, alg == SPFY_SPMM_ALG_TENSOR_FAST ? TC_GEMM_FAST : TC_GEMM_PRECISE, &gp, 1, nullptr, 0, s,
+  return tc_gemm_run(SPFY_F32, alg == SPFY_SPMM_ALG_TENSOR_FAST ? TC_GEMM_FAST : TC_GEMM_PRECISE, &gp, 1,
+                     repack ? (uint8_t*)workspace + base + dense_bytes : nullptr, repack ? gemm_ws_bytes + 256 : 0, s,
                      gated ? d_dense : nullptr, 1);
 }
 

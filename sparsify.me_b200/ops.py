@@ -314,7 +314,7 @@ class batched:
         assert b_num_rows == a_num_cols
         ldb, ldc = b_num_rows, a_num_rows
         wb = ctypes.c_size_t()
-        capi.spfy_spmm_workspace_bytes(alg, a_num_rows, a_num_cols, a_nnz, ctypes.byref(wb))
+        capi.spfy_spmm_workspace_bytes(alg, a_num_rows, a_num_cols, b_num_cols, num_batches, a_nnz, ctypes.byref(wb))
         ws = _workspace(wb.value, b.device)
         t = _Timer()
         t.begin()
@@ -327,7 +327,7 @@ class batched:
     @staticmethod
     def csr(m, k, n, num_batches, row_ptr, col_idx, vals, b, c, alpha=1.0, beta=0.0, alg=capi.SPMM_ALG_DEFAULT):
         wb = ctypes.c_size_t()
-        capi.spfy_spmm_workspace_bytes(alg, m, k, col_idx.numel(), ctypes.byref(wb))
+        capi.spfy_spmm_workspace_bytes(alg, m, k, n, num_batches, col_idx.numel(), ctypes.byref(wb))
         ws = _workspace(wb.value, b.device)
         capi.spfy_spmm_csr_strided_batched(alg, m, k, n, num_batches, _ptr(row_ptr), _ptr(col_idx),
                                            _ptr(vals), _ptr(b), k, k * n, _ptr(c), m, m * n,

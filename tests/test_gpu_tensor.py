@@ -203,19 +203,34 @@ def test_coo_spmm_tensor_route_exact_on_integers_and_duplicates(spfy, orc, cuda)
         assert np.array_equal(dC.cpu().numpy().astype(np.float64), want), alg
 
 
-def test_coo_spmm_tensor_route_needs_tma_addressable_operands(spfy, orc, cuda):
-    """k = 147 (the first conv layer): ldb = 147 floats is not a multiple of 16 bytes.  TENSOR fails loudly, DEFAULT
-    takes the CUDA-core kernels and is still right."""
+def test_coo_spmm_first_conv_layer_runs_on_a_padded_copy(spfy, orc, cuda):
+    """k = 147 (the first conv layer): ldb = 147 floats is not a multiple of 16 bytes, so TMA cannot address B_b.  The
+    tensor-core route then runs on a padded copy of B in the workspace; a workspace without room for it makes TENSOR
+    fail loudly (SPFY_E_WORKSPACE) and DEFAULT take the CUDA-core kernels."""
+    import ctypes
     m, k, n, nb = 64, 147, 96, 2
     ri, ci, va, B = coo_problem(orc, m, k, n, nb, 0.5, seed=3)
-    args = (m, k, ri.size, k, n, nb, torch.from_numpy(ri).to(cuda), torch.from_numpy(ci).to(cuda),
-            torch.from_numpy(va).to(cuda), torch.from_numpy(B).to(cuda))
-    dC = torch.zeros(nb, n, m, device=cuda)
-    with pytest.raises(spfy.SpfyError) as e:
-        spfy.batched.strided_coo(*args, dC, alg=spfy.SPMM_ALG_TENSOR)
-    assert e.value.code == spfy.capi.E_UNSUPPORTED
-    spfy.batched.strided_coo(*args, dC)
+    dri, dci, dva, dB = (torch.from_numpy(x).to(cuda) for x in (ri, ci, va, B))
     want = orc.spmm_coo_batched_f64(m, k, n, nb, ri, ci, va, B)
+    bound = abs_bound(orc, m, k, n, nb, ri, ci, va, B)
+    for alg in (spfy.SPMM_ALG_TENSOR, spfy.SPMM_ALG_DEFAULT):
+        dC = torch.zeros(nb, n, m, device=cuda)
+        before = spfy.launch_count()
+        spfy.batched.strided_coo(m, k, ri.size, k, n, nb, dri, dci, dva, dB, dC, alg=alg)
+        assert spfy.launch_count() - before == 4  # coo_to_csr + scatter + repack + tcgemm
+        err = np.abs(dC.cpu().numpy().astype(np.float64) - want)
+        assert np.all(err <= F32_TOL * bound + 1e-30)
+    capi = spfy.capi
+    small = ctypes.c_size_t()
+    capi.spfy_spmm_workspace_bytes(capi.SPMM_ALG_TENSOR, m, k, n, 0, ri.size, ctypes.byref(small))  # sized for no batch at all
+    ws = torch.empty(small.value, dtype=torch.uint8, device=cuda)
+    dC = torch.zeros(nb, n, m, device=cuda)
+    args = (m, k, ri.size, n, nb, dri.data_ptr(), dci.data_ptr(), dva.data_ptr(), dB.data_ptr(), k, k * n, dC.data_ptr(), m,
+            m * n, 1.0, 0.0, ws.data_ptr(), ws.numel(), None)
+    with pytest.raises(spfy.SpfyError) as e:
+        capi.spfy_spmm_coo_strided_batched(capi.SPMM_ALG_TENSOR, *args)
+    assert e.value.code == capi.E_WORKSPACE
+    capi.spfy_spmm_coo_strided_batched(capi.SPMM_ALG_DEFAULT, *args)
     assert np.allclose(dC.cpu().numpy(), want, rtol=2e-4, atol=2e-4)
 
 
@@ -331,8 +346,6 @@ def test_unstructured_routes_bit_exact_with_cusparse_golden(spfy, cuda, alg):
     for path in sorted(glob.glob(os.path.join(gold, "cusparse_coo_*.npz"))):
         z = np.load(path)
         m, k, n, nb = int(z["m"]), int(z["k"]), int(z["n"]), int(z["nb"])
-        if alg == "TENSOR" and k % 4:
-            continue  # not TMA-addressable (ldb = k floats): covered by the loud-failure test above
         a = torch.from_numpy(gen_f32(1, m * k).reshape(m, k)).to(cuda)
         B = torch.from_numpy(gen_f32(2, nb * n * k).reshape(nb, n, k)).to(cuda)
         C = torch.from_numpy(gen_f32(3, nb * n * m).reshape(nb, n, m).copy()).to(cuda)
@@ -343,8 +356,6 @@ def test_unstructured_routes_bit_exact_with_cusparse_golden(spfy, cuda, alg):
     for path in sorted(glob.glob(os.path.join(gold, "cusparse_bell_*.npz"))):
         z = np.load(path)
         m, k, n, nb, block, ell_cols = (int(z[x]) for x in ("m", "k", "n", "nb", "block", "ell_cols"))
-        if alg == "TENSOR" and k % 4:
-            continue
         V = gen_f32(4, nb * m * ell_cols).reshape(nb, m, ell_cols)
         B = torch.from_numpy(gen_f32(5, n * k).reshape(n, k)).to(cuda)
         cis = [torch.from_numpy(np.ascontiguousarray(z["col_idx"][b])).to(cuda) for b in range(nb)]
