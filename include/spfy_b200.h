@@ -158,6 +158,28 @@ SPFY_API int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float 
                         float beta, const void* C, size_t ldc, void* D, size_t ldd,
                         void* workspace, size_t workspace_bytes, spfy_stream_t stream);
 
+/* Implicit GEMM: the step BEFORE the path fused into it.  The K x N operand of every CSV row
+ * is the `unfold` of a convolution input (datasets/get_shapes.py:29-41 of the reference): a 3 x 3 layer reads each
+ * activation nine times.  Here B is never materialised: X is the NHWC activation tensor [batch][h][w][c] and the
+ * kernel's producer gathers each (128 positions x 64 channels) piece of a B stage with one TMA im2col instruction.
+ *     D[m x N] = alpha * A(2:4)[m x K] * im2col(X)[K x N] + beta * C,   N = batch * ho * wo  (image, row, column),
+ *     K = kh * kw * c ordered (kh, kw, c): permute the weight columns from PyTorch's (c, kh, kw) BEFORE pruning
+ *     (spfy_permute_conv_weights), the 2:4 groups are formed along the new order.
+ * c must be a multiple of 64 (every ResNet layer but the first; that one is unfolded explicitly), dilation 1.
+ * D is row-major m x N like spfy_spmma (ldd % 8 == 0). */
+typedef struct spfy_conv_desc {
+  size_t batch, h, w, c; /* NHWC input */
+  size_t kh, kw;         /* filter */
+  size_t stride, pad;    /* same in both directions */
+} spfy_conv_desc;
+SPFY_API int spfy_spmma_conv(int dtype, const spfy_conv_desc* conv, size_t m, float alpha,
+                             const void* comp_vals, const void* meta, const void* X, float beta,
+                             const void* C, size_t ldc, void* D, size_t ldd, spfy_stream_t stream);
+/* weights [m][c * kh * kw] in (c, kh, kw) column order (what torch's unfold / a flattened conv weight uses)
+ * -> [m][kh * kw * c] in (kh, kw, c) order; 16-bit elements */
+SPFY_API int spfy_permute_conv_weights(const void* in, void* out, size_t m, size_t c, size_t kh, size_t kw,
+                                       spfy_stream_t stream);
+
 /* Many independent problems (the per-layer GEMMs of a datasets/ *.csv table) as ONE plan:
  * tensor maps and the tile schedule are built once (like cusparseLtMatmulPlanInit,
  * spmma.hxx:79, which the reference also keeps outside its timers) and every run issues at

@@ -25,7 +25,7 @@ from .capi import (F16, BF16, F32, F64, PRUNE_STRIP_MAG, PRUNE_TILE_MAG, LAYOUT_
                    SPMM_ALG_TENSOR_FAST, GEMM_PRECISE, GEMM_FAST, SpfyError, launch_count, last_error, version)
 from .ops import (sparsify, prune24, prune24_check, compressed_bytes, spmma_compressed, spmma,  # noqa: F401
                   threshold_to_coo, coo_to_csr, batched, Compressed24, SpmmaPlan, prune24_batched,
-                  alloc_compressed, pack_compressed, unpack_compressed)
+                  alloc_compressed, pack_compressed, unpack_compressed, spmma_conv, permute_conv_weights)
 from . import shapes  # noqa: F401
 from . import multigpu  # noqa: F401
 

@@ -52,6 +52,8 @@ SIGNATURES = {
     "spfy_spmma_workspace_bytes": (c_int, [c_int, _SZ, _SZ, _SZ, POINTER(_SZ)]),
     "spfy_spmma": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, c_float, _P, _SZ,
                            _P, _SZ, _P, _SZ, _P]),
+    "spfy_spmma_conv": (c_int, [c_int, _P, _SZ, c_float, _P, _P, _P, c_float, _P, _SZ, _P, _SZ, _P]),
+    "spfy_permute_conv_weights": (c_int, [_P, _P, _SZ, _SZ, _SZ, _SZ, _P]),
     "spfy_spmma_plan_create": (c_int, [c_int, _P, _SZ, POINTER(c_void_p)]),
     "spfy_spmma_plan_run": (c_int, [_P, _P]),
     "spfy_spmma_plan_launches": (c_int, [_P]),
@@ -97,6 +99,12 @@ class SpmmaProblem(ctypes.Structure):
     _fields_ = [("opB", c_int), ("m", c_size_t), ("n", c_size_t), ("k", c_size_t), ("comp_vals", c_void_p),
                 ("meta", c_void_p), ("B", c_void_p), ("ldb", c_size_t), ("C", c_void_p), ("ldc", c_size_t),
                 ("D", c_void_p), ("ldd", c_size_t), ("alpha", c_float), ("beta", c_float)]
+
+
+class ConvDesc(ctypes.Structure):
+    """struct spfy_conv_desc"""
+    _fields_ = [("batch", c_size_t), ("h", c_size_t), ("w", c_size_t), ("c", c_size_t), ("kh", c_size_t), ("kw", c_size_t),
+                ("stride", c_size_t), ("pad", c_size_t)]
 
 
 class Prune24Item(ctypes.Structure):

@@ -59,12 +59,40 @@ int launch_convert(const void* src, void* dst, size_t n, cudaStream_t s) {
   return SPFY_OK;
 }
 
+// conv weights [m][c][kh*kw] -> [m][kh*kw][c]: the K order of the implicit GEMM (spfy_spmma_conv)
+__global__ void __launch_bounds__(256)
+permute_conv_weights_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, size_t m, uint32_t c, uint32_t taps) {
+  const size_t total = m * c * taps;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const size_t row = i / ((size_t)c * taps);
+    const uint32_t r = (uint32_t)(i - row * c * taps), tap = r / c, ch = r - tap * c;  // i walks the OUTPUT
+    out[i] = in[row * c * taps + (size_t)ch * taps + tap];
+  }
+}
+
 }  // namespace
 }  // namespace spfy
 
 using namespace spfy;
 
 extern "C" {
+
+int spfy_permute_conv_weights(const void* in, void* out, size_t m, size_t c, size_t kh, size_t kw, spfy_stream_t stream) {
+  if (m == 0 || c == 0 || kh == 0 || kw == 0) return SPFY_OK;
+  if (!in || !out) return fail(SPFY_E_INVALID, "permute_conv_weights: null pointer");
+  if (in == out) return fail(SPFY_E_INVALID, "permute_conv_weights: in place is not supported");
+  if (c >= (1ull << 31) || kh * kw >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "permute_conv_weights: too large");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  size_t blocks = ceil_div(m * c * kh * kw, 256);
+  if (blocks > (size_t)di.sm_count * 8) blocks = (size_t)di.sm_count * 8;
+  permute_conv_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in, (uint16_t*)out, m,
+                                                                                  (uint32_t)c, (uint32_t)(kh * kw));
+  SPFY_LAUNCH_OK("permute_conv_weights_kernel");
+  return SPFY_OK;
+}
 
 int spfy_version(void) { return 100; }  // 0.1.0
 

@@ -85,6 +85,12 @@ struct alignas(64) ProblemDev {
   uint32_t unit_begin, units;  // this problem's range in the launch-wide unit order
   float alpha, beta;
   uint64_t hint_b;
+  // implicit GEMM (spfy_spmma_conv): B is never materialised -- tmap_b is an im2col map over the NHWC activations and a
+  // B stage (128 positions x 128 k) is gathered as two (128 positions x 64 channels) pieces, one filter tap each
+  uint32_t conv;               // 0: B is a matrix
+  uint32_t conv_c, conv_kw;    // channels (multiple of 64), filter width
+  uint32_t conv_wo, conv_ho;   // output width / height
+  uint32_t conv_stride, conv_pad;
 };
 
 struct LaunchParams {
@@ -190,6 +196,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       const CUtensorMap* tmap_b = nullptr;
       const uint8_t *a_vals = nullptr, *a_meta = nullptr;
       uint32_t pm = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, b3d = 0;
+      uint32_t conv = 0, conv_c = 64, conv_kw = 1, conv_wo = 1, conv_ho = 1, conv_stride = 1, conv_pad = 0, pk = 0;
       uint64_t hint_b = 0;
       const bool no_b = (L.dbg & 4u) != 0, no_a = (L.dbg & 16u) != 0;
       for (; W.valid(); W.next()) {
@@ -202,11 +209,24 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           pm = uni(P->m); k_tiles = uni(P->k_tiles); m_tiles = uni(P->m_tiles); b3d = uni(P->b3d);
           m_groups = uni(P->m_groups); G = uni(P->G); resident = uni(P->resident); unit_begin = uni(P->unit_begin);
           hint_b = uni(P->hint_b);
+          conv = uni(P->conv); pk = uni(P->k);
+          if (conv) {
+            conv_c = uni(P->conv_c); conv_kw = uni(P->conv_kw); conv_wo = uni(P->conv_wo); conv_ho = uni(P->conv_ho);
+            conv_stride = uni(P->conv_stride); conv_pad = uni(P->conv_pad);
+          }
         }
         const uint32_t local = W.u - unit_begin;
         const uint32_t nt = local / m_groups, mg = local - nt * m_groups;
         const uint32_t mt0 = mg * G;
         const uint32_t g_count = min(G, m_tiles - mt0);
+        // implicit GEMM: base pixel of the unit's first output position (input coordinates of filter tap (0, 0))
+        int cw = 0, ch = 0, cn = 0;
+        if (conv) {
+          const uint32_t p0 = nt * (uint32_t)BN, row = p0 / conv_wo;
+          cw = (int)((p0 - row * conv_wo) * conv_stride) - (int)conv_pad;
+          cn = (int)(row / conv_ho);
+          ch = (int)((row - (uint32_t)cn * conv_ho) * conv_stride) - (int)conv_pad;
+        }
         if (resident && res_owner != P) {
           // (re)load the whole compressed A of this problem into the resident region
           mbar_wait(bar_res_empty, (res_loads & 1u) ^ 1u);
@@ -241,15 +261,28 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const uint8_t* am = a_meta + (size_t)mt0 * E_TILE_BYTES;
         const size_t av_step = (size_t)m_tiles * A_TILE_BYTES, am_step = (size_t)m_tiles * E_TILE_BYTES;
         const bool stream_a = !resident && !no_a;
-        const uint32_t tx = (no_b ? 0u : L.bk * (uint32_t)(BN * 2)) + (stream_a ? a_bytes + e_bytes : 0u);
+        const uint32_t tx_a = stream_a ? a_bytes + e_bytes : 0u;
+        const uint32_t tx_full = (no_b ? 0u : L.bk * (uint32_t)(BN * 2)) + tx_a;
         for (uint32_t kt = 0; kt < k_tiles; ++kt, av += av_step, am += am_step) {
           mbar_wait(bar_empty + stage * 8, phase ^ 1u);
           const uint32_t full = bar_full + stage * 8;
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
+          // implicit GEMM: 64-channel pieces of this k-tile that exist (K = taps * C is a multiple of 64, not of 128)
+          const uint32_t pieces = conv ? min(L.bk / 64u, (pk - kt * L.bk + 63u) / 64u) : 0u;
+          const uint32_t tx = conv && !no_b ? pieces * (uint32_t)(BN * 128) + tx_a : tx_full;
           if (leader) {
             if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
             // B first: it comes from DRAM and is the long pole of the stage; A and its metadata are L2 hits
             if (no_b) {
+            } else if (conv) {
+              if (OPB_T) {
+                for (uint32_t h = 0; h < pieces; ++h) {
+                  const uint32_t k0 = kt * L.bk + h * 64u, tap = k0 / conv_c, c0 = k0 - tap * conv_c;
+                  const uint32_t tr = tap / conv_kw, ts = tap - tr * conv_kw;
+                  tma_load_im2col_4d(sbase + h * (uint32_t)(BN * 128), tmap_b, (int)c0, cw, ch, cn, (uint16_t)ts, (uint16_t)tr,
+                                     full, hint_b);
+                }
+              }
             } else if (b3d) {
               // one box fills the stage: [2 groups of 64][128 outer rows][64]
               if (!OPB_T) tma_load_3d(sbase, tmap_b, 0, (int)(kt * BK), (int)(nt * 2), full, hint_b);
@@ -534,7 +567,30 @@ struct HostProblem {
   void* D;
   size_t ldb, ldc, ldd;
   float alpha, beta;
+  const spfy_conv_desc* conv = nullptr;  // implicit GEMM: B is the NHWC activation tensor, never unfolded
 };
+
+// NHWC activations {C, W, H, N} in im2col mode: one instruction gathers 128 consecutive output positions x 64 channels
+// of one filter tap.  The bounding box of base pixels is [-pad, dim + pad - (filter - 1)) per spatial dimension, walked
+// with the convolution stride -- exactly the output positions, row by row, image by image.
+int make_tmap_im2col(CUtensorMap* map, int dtype, const void* x, const spfy_conv_desc& c) {
+  EncodeIm2colFn enc;
+  int rc = get_im2col_encoder(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[4] = {c.c, c.w, c.h, c.batch};
+  cuuint64_t strides[3] = {c.c * 2, c.w * c.c * 2, c.h * c.w * c.c * 2};
+  int lower[2] = {-(int)c.pad, -(int)c.pad};
+  int upper[2] = {(int)c.pad - (int)(c.kw - 1), (int)c.pad - (int)(c.kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+  CUresult r = enc(map, dtype == SPFY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                   const_cast<void*>(x), dims, strides, lower, upper, /*channelsPerPixel*/ 64, /*pixelsPerColumn*/ BN, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SPFY_E_CUDA, "cuTensorMapEncodeIm2col failed (%d) for NHWC %zu x %zu x %zu x %zu, filter %zu x %zu stride %zu pad %zu",
+                (int)r, c.batch, c.h, c.w, c.c, c.kh, c.kw, c.stride, c.pad);
+  return SPFY_OK;
+}
 
 int validate(int dtype, const HostProblem& h, const char* who) {
   if (dtype != SPFY_F16 && dtype != SPFY_BF16)
@@ -547,10 +603,10 @@ int validate(int dtype, const HostProblem& h, const char* who) {
   if (h.m >= (1u << 31) || h.n >= (1u << 31) || h.k >= (1u << 31))
     return fail(SPFY_E_UNSUPPORTED, "%s: dimension too large", who);
   const size_t b_inner = h.opB == SPFY_OP_N ? h.n : h.k;
-  if (h.ldb < b_inner || h.ldd < h.n || (h.beta != 0.f && h.ldc < h.n))
+  if ((!h.conv && h.ldb < b_inner) || h.ldd < h.n || (h.beta != 0.f && h.ldc < h.n))
     return fail(SPFY_E_INVALID, "%s: leading dimension too small", who);
   // TMA contract == the reference's own fp16 contract (spmma.hxx:45-49): multiples of 8
-  if (h.ldb % 8 || h.ldd % 8 || (h.beta != 0.f && h.ldc % 8) || h.n % 8 || (h.opB == SPFY_OP_T && h.k % 8))
+  if ((!h.conv && h.ldb % 8) || h.ldd % 8 || (h.beta != 0.f && h.ldc % 8) || h.n % 8 || (h.opB == SPFY_OP_T && h.k % 8))
     return fail(SPFY_E_UNSUPPORTED,
                 "%s: n, ldb, ldc, ldd (and k for opB=T) must be multiples of 8 elements "
                 "(n=%zu k=%zu ldb=%zu ldc=%zu ldd=%zu)", who, h.n, h.k, h.ldb, h.ldc, h.ldd);
@@ -603,10 +659,23 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   // one stage of B: opB = N -> bk rows of k x 128 columns (two 64-column groups);
   //                 opB = T -> 128 rows of n x bk columns of k (bk/64 groups)
   const uint32_t box_outer = h.opB == SPFY_OP_N ? bk : 128u, box_groups = h.opB == SPFY_OP_N ? 2u : bk / 64u;
-  if (d->b3d && make_tmap_grouped(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, box_outer, box_groups) != SPFY_OK)
-    d->b3d = 0;  // the driver refused the grouped view: fall back to 2-D boxes (64 inner elements each)
-  if (!d->b3d) rc = make_tmap_2d(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 64, box_outer);
-  if (rc) return rc;
+  if (h.conv) {
+    d->b3d = 0;
+    rc = make_tmap_im2col(&d->tmap_b, dtype, h.B, *h.conv);
+    if (rc) return rc;
+    d->conv = 1;
+    d->conv_c = (uint32_t)h.conv->c;
+    d->conv_kw = (uint32_t)h.conv->kw;
+    d->conv_wo = (uint32_t)((h.conv->w + 2 * h.conv->pad - h.conv->kw) / h.conv->stride + 1);
+    d->conv_ho = (uint32_t)((h.conv->h + 2 * h.conv->pad - h.conv->kh) / h.conv->stride + 1);
+    d->conv_stride = (uint32_t)h.conv->stride;
+    d->conv_pad = (uint32_t)h.conv->pad;
+  } else {
+    if (d->b3d && make_tmap_grouped(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, box_outer, box_groups) != SPFY_OK)
+      d->b3d = 0;  // the driver refused the grouped view: fall back to 2-D boxes (64 inner elements each)
+    if (!d->b3d) rc = make_tmap_2d(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 64, box_outer);
+    if (rc) return rc;
+  }
   rc = make_tmap_2d(&d->tmap_d, dtype, h.D, h.n, h.m, h.ldd, 64, 32);
   if (rc) return rc;
   d->a_vals = (const uint8_t*)h.comp_vals;
@@ -781,6 +850,47 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
   }
   const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
   return launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
+}
+
+int spfy_spmma_conv(int dtype, const spfy_conv_desc* conv, size_t m, float alpha, const void* comp_vals,
+                    const void* meta, const void* X, float beta, const void* C, size_t ldc, void* D, size_t ldd,
+                    spfy_stream_t stream) {
+  if (!conv) return fail(SPFY_E_INVALID, "spmma_conv: null descriptor");
+  const spfy_conv_desc& c = *conv;
+  if (!c.batch || !c.h || !c.w || !c.c || !c.kh || !c.kw || !c.stride)
+    return fail(SPFY_E_INVALID, "spmma_conv: empty dimension in the descriptor");
+  if (c.c % 64) return fail(SPFY_E_UNSUPPORTED, "spmma_conv: channels must be a multiple of 64 (got %zu): unfold explicitly", c.c);
+  if (c.h + 2 * c.pad < c.kh || c.w + 2 * c.pad < c.kw) return fail(SPFY_E_INVALID, "spmma_conv: filter larger than the padded image");
+  if (c.kh > 16 || c.kw > 16 || c.pad > 8 || c.stride > 8)
+    return fail(SPFY_E_UNSUPPORTED, "spmma_conv: filter / padding / stride outside what the im2col tensor map encodes");
+  if ((uintptr_t)X % 16) return fail(SPFY_E_INVALID, "spmma_conv: activations must be 16-byte aligned");
+  const size_t ho = (c.h + 2 * c.pad - c.kh) / c.stride + 1, wo = (c.w + 2 * c.pad - c.kw) / c.stride + 1;
+  const size_t n = c.batch * ho * wo, k = c.kh * c.kw * c.c;
+  HostProblem h{SPFY_OP_T, m, n, k, comp_vals, meta, X, C, D, /*ldb*/ k, ldc, ldd, alpha, beta};
+  h.conv = conv;
+  int rc = validate(dtype, h, "spmma_conv");
+  if (rc) return rc;
+  if (m == 0 || n == 0) return SPFY_OK;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  if (di.cc_major != 10)
+    return fail(SPFY_E_UNSUPPORTED, "spmma_conv: needs an sm_100a device, found sm_%d%d", di.cc_major, di.cc_minor);
+  const int cls = classify(h, false, di.sm_count);
+  ProblemDev d;
+  rc = fill_problem(&d, dtype, h, cls);
+  if (rc) return rc;
+  d.unit_begin = 0;
+  LaunchParams L;
+  memset(&L, 0, sizeof(L));
+  uint32_t smem = 0;
+  geometry(cls, res_values_bytes(d), res_meta_bytes(d), &L, &smem);
+  L.table = nullptr;
+  L.num_problems = 1;
+  L.total_units = d.units;
+  L.idesc = make_idesc(dtype, SPFY_OP_T);
+  const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
+  return launch(dtype, SPFY_OP_T, d, L, smem, grid, (cudaStream_t)stream);
 }
 
 int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t count,

@@ -86,6 +86,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
       : "memory");
 }
+// im2col mode (4-D NHWC tensor {C, W, H, N}): `pixels` consecutive output positions starting at base pixel (w, h, n) --
+// walking W, then H, then N inside the bounding box of the tensor map -- x `channels` channels from c, at filter tap
+// (off_w, off_h); out-of-image taps are zero-filled
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h, uint32_t bar, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "l"(hint)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes,
                                              uint32_t bar, uint64_t hint) {
   asm volatile(
@@ -308,6 +319,25 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+inline int get_im2col_encoder(EncodeIm2colFn* out) {
+  static std::atomic<void*> cached{nullptr};
+  void* fn = cached.load(std::memory_order_acquire);
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    SPFY_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn)
+      return fail(SPFY_E_CUDA, "cuTensorMapEncodeIm2col not available from this driver");
+    cached.store(fn, std::memory_order_release);
+  }
+  *out = (EncodeIm2colFn)fn;
+  return SPFY_OK;
+}
 
 inline int get_encoder(EncodeTiledFn* out) {
   static std::atomic<void*> cached{nullptr};

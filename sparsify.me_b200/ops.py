@@ -233,6 +233,32 @@ def spmma_compressed(comp, b, c=None, out=None, alpha=1.0, beta=0.0, op_b=capi.O
     return out
 
 
+def permute_conv_weights(w, c, kh, kw):
+    """[m, c*kh*kw] conv weights in (c, kh, kw) column order (a flattened torch conv weight, the K order of `unfold`)
+    -> [m, kh*kw*c] in (kh, kw, c) order, the K order of spmma_conv.  Do this BEFORE pruning."""
+    out = torch.empty_like(w)
+    capi.spfy_permute_conv_weights(_ptr(w), _ptr(out), w.shape[0], c, kh, kw, _stream())
+    return out
+
+
+def spmma_conv(comp, x, kh, kw, stride=1, pad=0, c=None, out=None, alpha=1.0, beta=0.0):
+    """Implicit GEMM (spfy_spmma_conv): D[m, batch*ho*wo] = alpha * A(2:4) * im2col(x) + beta * C with x the NHWC
+    activation tensor [batch, h, w, ch] -- the unfolded K x N operand of datasets/get_shapes.py:29-41 is never built.
+    `comp`: compressed weights whose K is ordered (kh, kw, ch) (permute_conv_weights before prune24)."""
+    assert x.dim() == 4 and x.is_contiguous()
+    nb, h, w, ch = x.shape
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    assert comp.cols == kh * kw * ch
+    n = nb * ho * wo
+    if out is None:
+        out = torch.empty(comp.rows, n, dtype=comp.dtype, device=x.device)
+    desc = capi.ConvDesc(nb, h, w, ch, kh, kw, stride, pad)
+    capi.spfy_spmma_conv(_DT[comp.dtype], ctypes.byref(desc), comp.rows, float(alpha), _ptr(comp.vals), _ptr(comp.meta),
+                         _ptr(x), float(beta), _ptr(c), c.stride(0) if c is not None else 0, _ptr(out), out.stride(0),
+                         _stream())
+    return out
+
+
 def spmma(a, b, c, m, n, k, batch_size=1, transpose_a=capi.OP_N, transpose_b=capi.OP_N, alpha=1.0,
           beta=0.0, prune_mode=capi.PRUNE_TILE_MAG):
     """sparsifyme::spmma (spmma.hxx:21-118): prune A in place (2:4 magnitude), compress, multiply

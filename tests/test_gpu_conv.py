@@ -1,0 +1,81 @@
+"""Implicit GEMM (spfy_spmma_conv): the `unfold` that produces every CSV shape
+(reference datasets/get_shapes.py:29-41) fused into the spmma B-operand load with TMA im2col.
+
+Parity bar: the explicit path -- torch unfold of the same activations, K reordered to (kh, kw, c), then
+spfy_spmma on the materialised K x N matrix -- runs the SAME MMAs on the SAME operand bytes, so the two results must be
+identical bit for bit; the explicit path itself is tied to the fp64 oracle in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def explicit_b(x_nhwc, kh, kw, stride, pad):
+    """[K = kh*kw*c, N = batch*ho*wo] row-major, K ordered (kh, kw, c), N ordered (image, row, column)"""
+    nb, h, w, c = x_nhwc.shape
+    cols = F.unfold(x_nhwc.permute(0, 3, 1, 2).float(), (kh, kw), padding=pad, stride=stride)  # [nb, c*kh*kw, L], (c, kh, kw)
+    L = cols.shape[2]
+    cols = cols.view(nb, c, kh * kw, L).permute(2, 1, 0, 3).reshape(kh * kw * c, nb * L)       # (tap, c) x (image, position)
+    return cols.to(x_nhwc.dtype).contiguous()
+
+
+# 3 x 3 layers of datasets/resnet18.csv (m = ho*wo, n = C_out, k = 9*C_in) and the strided / 1 x 1 variants of the other tables
+CONV_CASES = [  # (batch, h, w, c_in, c_out, kh, kw, stride, pad)
+    (4, 56, 56, 64, 64, 3, 3, 1, 1),     # 3136,64,576
+    (4, 56, 56, 64, 128, 3, 3, 2, 1),    # 784,128,576   (stride 2)
+    (4, 28, 28, 128, 128, 3, 3, 1, 1),   # 784,128,1152
+    (2, 28, 28, 128, 256, 3, 3, 2, 1),   # 196,256,1152
+    (2, 14, 14, 256, 256, 3, 3, 1, 1),   # 196,256,2304
+    (8, 7, 7, 512, 512, 3, 3, 1, 1),     # 49,512,4608
+    (2, 56, 56, 64, 128, 1, 1, 2, 0),    # 1 x 1 stride-2 downsample
+    (3, 10, 12, 64, 72, 3, 3, 1, 1),     # ragged: N = 360 is not a multiple of 128, rows wrap inside a tile
+    (1, 9, 9, 192, 64, 5, 3, 2, 2),      # rectangular filter, K = 15 * 192: odd number of 64-channel pieces
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(str(v) for v in c))
+@pytest.mark.parametrize("tdt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_implicit_gemm_equals_explicit_unfold(spfy, cuda, case, tdt):
+    nb, h, w, c, cout, kh, kw, stride, pad = case
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(sum(case))
+    x = (torch.rand(nb, h, w, c, device=cuda, generator=gen) * 2 - 1).to(tdt)
+    wt = (torch.rand(cout, c * kh * kw, device=cuda, generator=gen) * 2 - 1).to(tdt)  # (c, kh, kw) columns like a torch conv
+    wp = spfy.permute_conv_weights(wt, c, kh, kw)
+    assert torch.equal(wp.view(cout, kh * kw, c), wt.view(cout, c, kh * kw).transpose(1, 2))
+    comp = spfy.prune24(wp)
+    b = explicit_b(x, kh, kw, stride, pad)
+    want = spfy.spmma_compressed(comp, b)
+    got = spfy.spmma_conv(comp, x, kh, kw, stride=stride, pad=pad)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+
+
+def test_implicit_gemm_matches_a_real_convolution(spfy, cuda):
+    """end to end against torch's own conv2d on the pruned weights (fp32 reference, max relative error 1e-2)"""
+    nb, h, w, c, cout = 4, 28, 28, 128, 256
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(5)
+    x = (torch.rand(nb, h, w, c, device=cuda, generator=gen) * 2 - 1).half()
+    wt = (torch.rand(cout, c * 9, device=cuda, generator=gen) * 2 - 1).half()
+    wp = spfy.permute_conv_weights(wt, c, 3, 3)
+    pruned = torch.empty_like(wp)
+    comp = spfy.prune24(wp, out_dense=pruned)
+    got = spfy.spmma_conv(comp, x, 3, 3, stride=1, pad=1)                      # [cout, nb*h*w]
+    w4 = pruned.view(cout, 3, 3, c).permute(0, 3, 1, 2).float()               # back to [cout, c, kh, kw]
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w4, padding=1)              # [nb, cout, h, w]
+    ref = ref.permute(1, 0, 2, 3).reshape(cout, -1)
+    scale = torch.clamp(ref.abs(), min=1e-2 * float(ref.abs().max()))
+    assert float(((got.float() - ref).abs() / scale).max()) <= 1e-2
+
+
+def test_implicit_gemm_rejects_what_it_cannot_gather(spfy, cuda):
+    x = torch.zeros(2, 8, 8, 3, dtype=torch.float16, device=cuda)  # the first conv layer: 3 channels
+    comp = spfy.prune24(torch.zeros(64, 3 * 49 + 1, dtype=torch.float16, device=cuda))
+    comp.cols = 147
+    with pytest.raises(spfy.SpfyError) as e:
+        spfy.spmma_conv(comp, x, 7, 7, stride=2, pad=3)
+    assert e.value.code == spfy.capi.E_UNSUPPORTED
