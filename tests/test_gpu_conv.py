@@ -31,7 +31,7 @@ CONV_CASES = [  # (batch, h, w, c_in, c_out, kh, kw, stride, pad)
     (8, 7, 7, 512, 512, 3, 3, 1, 1),     # 49,512,4608
     (2, 56, 56, 64, 128, 1, 1, 2, 0),    # 1 x 1 stride-2 downsample
     (3, 10, 12, 64, 72, 3, 3, 1, 1),     # ragged: N = 360 is not a multiple of 128, rows wrap inside a tile
-    (1, 9, 9, 192, 64, 5, 3, 2, 2),      # rectangular filter, K = 15 * 192: odd number of 64-channel pieces
+    (4, 9, 9, 192, 64, 5, 3, 2, 2),      # rectangular filter, K = 15 * 192 = 45 pieces of 64 channels (odd), N = 120
 ]
 
 
