@@ -642,7 +642,15 @@ int classify(const HostProblem& h, bool grouped, int sm_count) {
     if (h.k <= 64) return CLASS_RES_K64;
     return resident_bytes(h.m, h.k) <= RES_SMALL_BYTES ? CLASS_RES_SMALL : CLASS_RES_LARGE;
   }
-  if (m_tiles >= 2 && (grouped || ceil_div(m_tiles, 2) * n_tiles >= 2 * (size_t)sm_count))
+  static const double g2_min_waves = [] {
+    const char* e = dev_switch("SPFY_SPMMA_G2_MIN_WAVES");
+    return e ? atof(e) : 0.5;
+  }();
+  // Two m-tiles share every B stage whenever there are two: the L2 -> SM path is barely faster than HBM on this part,
+  // so a second CTA re-reading the same B columns costs nearly as much as reading them from DRAM again.  Measured on
+  // single calls (bench.py --per-layer): 256 x 2304 x 25088 41.0 -> 36.9 us, 512 x 4608 x 6272 41.0 -> 33.7 us with
+  // G = 2 even though only 98-196 units are left for 148 SMs.  One m-tile per unit only below half a wave.
+  if (m_tiles >= 2 && (grouped || (double)(ceil_div(m_tiles, 2) * n_tiles) >= g2_min_waves * (double)sm_count))
     return h.k <= SHORT_K ? CLASS_STREAM_G2_SHORT : CLASS_STREAM_G2;
   return CLASS_STREAM_G1;
 }

@@ -10,6 +10,6 @@ timeout 900 $TR bench.py --gpus $N --strong --steps 5 --warmup 3 > $O/${T}_stron
 echo "strong rc=$?" >> $O/${T}_status.txt
 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 2 > $O/${T}_weak.json 2> $O/${T}_weak.err
 echo "weak rc=$?" >> $O/${T}_status.txt
-timeout 600 $TR bench.py --gpus $N --impl reference --steps 2 --warmup 1 > $O/${T}_ref.json 2> $O/${T}_ref.err
-echo "ref rc=$?" >> $O/${T}_status.txt
-cat $O/${T}_status.txt; tail -3 $O/${T}_pytest.log; tail -3 $O/${T}_strong.err; head -c 1500 $O/${T}_strong.json
+timeout 900 $TR bench.py --gpus $N --workload coo --steps 5 --warmup 2 > $O/${T}_coo.json 2> $O/${T}_coo.err
+echo "coo rc=$?" >> $O/${T}_status.txt
+cat $O/${T}_status.txt; tail -3 $O/${T}_pytest.log; tail -3 $O/${T}_strong.err; head -c 600 $O/${T}_strong.json
