@@ -55,12 +55,12 @@ enum { KIND_F16 = 0, KIND_BF16 = 1, KIND_F32 = 2 };
 struct alignas(64) GemmProblemDev {
   CUtensorMap tmap_a;      // Au: {inner, outer, batch}; K-major: inner = K, MN-major: inner = Mu
   CUtensorMap tmap_b;      // Bu likewise
-  CUtensorMap tmap_a2;     // 3xTF32 kernel, K-major Au: {32, outer, K/32 full groups, batch} -- two K slabs per instruction
   uint8_t* C;              // batch 0 of the result
   const uint64_t* c_ptrs;  // optional device array of per-batch result pointers
   uint64_t ldc, stride_c;  // elements
   uint32_t mu, nu, k, nb;
   uint32_t m_tiles, n_tiles, k_tiles;
+  uint32_t g, m_groups;    // m-tiles per unit (1; 2 in the 3xTF32 kernel when there are two) and units along Mu
   uint32_t bn;             // columns of one n-tile: multiple of 16 (of the MN group when Bu is MN-major)
   uint32_t a_mn, b_mn;     // operand is MN-major
   uint32_t a_batched, b_batched;
@@ -83,6 +83,7 @@ struct GemmLaunch {
   uint32_t dbg;       // development switches (SPFY_GEMM_DEBUG, dev builds only; timing experiments, results are garbage):
                       // 1 no MMAs, 2 no Bu split, 4 no tcgen05.st, 8 no hi/lo arithmetic
   uint32_t a_stages;  // 3xTF32 kernel: depth of the Au ring (raw tiles only; the Bu ring has `stages` slots)
+  uint32_t acc_slots, d_cols;  // 3xTF32 kernel: accumulator slots (2 x TS_G x 64 columns, or 1 x TS_G x 128)
   uint32_t b_off;     // ... and where the Bu ring starts
 };
 
@@ -118,14 +119,16 @@ template <> __device__ __forceinline__ float f32_to_out<KIND_F32>(float v) { ret
 
 // Epilogue role (4 warps: TMEM lane quarter = warp & 3), shared by the two kernels: drains accumulator slot
 // job % slots (slot_cols columns apart) of every unit the CTA walks.
+// A unit holds g accumulators (m-tiles mg*g ...), tile_cols columns apart inside its slot.
 template <int KIND>
 __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base, uint32_t bar_acc_full, uint32_t bar_acc_empty,
-                                              uint32_t slots, uint32_t slot_cols, uint32_t warp, uint32_t lane) {
+                                              uint32_t slots, uint32_t slot_cols, uint32_t tile_cols, uint32_t warp,
+                                              uint32_t lane) {
   using out_t = typename OutT<KIND>::type;
   const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter + 32)
   uint32_t job = 0;
   const GemmProblemDev* last = nullptr;
-  uint32_t m_tiles = 1, n_tiles = 1, bn = 0, mu = 0, nu = 0, unit_begin = 0, mu_contig = 1;
+  uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, bn = 0, mu = 0, nu = 0, unit_begin = 0, mu_contig = 1;
   uint64_t ldc = 0, stride_c = 0;
   uint8_t* Cbase = nullptr;
   const uint64_t* c_ptrs = nullptr;
@@ -134,20 +137,26 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
     const GemmProblemDev* P = W.current();
     if (P != last) {
       last = P;
-      m_tiles = P->m_tiles; n_tiles = P->n_tiles; bn = P->bn; mu = P->mu; nu = P->nu; unit_begin = P->unit_begin;
+      m_tiles = P->m_tiles; m_groups = P->m_groups; g = P->g; n_tiles = P->n_tiles; bn = P->bn; mu = P->mu; nu = P->nu;
+      unit_begin = P->unit_begin;
       mu_contig = P->out_mu_contig; ldc = P->ldc; stride_c = P->stride_c; Cbase = P->C; c_ptrs = P->c_ptrs;
       alpha = P->alpha; beta = P->beta;
     }
     const uint32_t local = W.u - unit_begin;
     const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
-    const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
+    const uint32_t mg = t1 % m_groups, b = t1 / m_groups;
+    const uint32_t g_count = min(g, m_tiles - mg * g);
     out_t* C = c_ptrs ? reinterpret_cast<out_t*>(c_ptrs[b]) : reinterpret_cast<out_t*>(Cbase) + (size_t)b * stride_c;
     const uint32_t slot = job % slots;
+    mbar_wait(bar_acc_full + slot * 8, (job / slots) & 1u);
+    tc_fence_after();
+    for (uint32_t tile = 0; tile < g_count; ++tile) {
+    const uint32_t mt = mg * g + tile;
     const uint32_t row = mt * GM_BM + quarter * 32u + lane;  // index along Mu
     const bool row_ok = row < mu;
     const bool warp_ok = mt * GM_BM + quarter * 32u < mu;
-    mbar_wait(bar_acc_full + slot * 8, (job / slots) & 1u);
-    tc_fence_after();
+    const uint32_t tcol = tmem_base + slot * slot_cols + tile * tile_cols + ((quarter * 32u) << 16);
+    const bool last_tile = tile + 1 == g_count;
     // 16 accumulator columns at a time (bn is a multiple of 16): keeps the role at ~50 registers
     const uint32_t chunks = bn / 16u;
     for (uint32_t c = 0; c < chunks; ++c) {
@@ -155,10 +164,10 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
       const uint32_t ncols = nu > col0 ? min(16u, nu - col0) : 0u;
       uint32_t acc[16];
       if (warp_ok && ncols) {
-        tmem_ld_x16(tmem_base + slot * slot_cols + c * 16u + ((quarter * 32u) << 16), acc);
+        tmem_ld_x16(tcol + c * 16u, acc);
         tmem_wait_ld();
       }
-      if (c + 1 == chunks) {
+      if (c + 1 == chunks && last_tile) {
         // accumulator fully read by this warp: hand the slot back to the MMA warp
         tc_fence_before();
         __syncwarp();
@@ -208,6 +217,7 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
         }
       }
     }
+    }  // tile
   }
 }
 
@@ -404,7 +414,7 @@ tcgemm_kernel(const __grid_constant__ GemmProblemDev single, const __grid_consta
       }
     }
   } else {
-    gemm_epilogue<KIND>(W, tmem_base, bar_acc_full, bar_acc_empty, GM_ACC_SLOTS, GM_MAX_BN, warp, lane);
+    gemm_epilogue<KIND>(W, tmem_base, bar_acc_full, bar_acc_empty, GM_ACC_SLOTS, GM_MAX_BN, GM_MAX_BN, warp, lane);
   }
 
   tc_fence_before();
@@ -424,24 +434,31 @@ tcgemm_kernel(const __grid_constant__ GemmProblemDev single, const __grid_consta
 // (measured: 2000 cycles per slab at N = 64 against 720 for HBM).  Here the splitter warps take the raw Au tile
 // out of shared memory ONCE, split it in registers and store hi and lo to tensor memory with tcgen05.st, and the
 // MMAs read Au from there (`tcgen05.mma [d], [a_tmem], b_desc`): shared memory carries the raw Au tile once and
-// the small Bu tile (weights: raw via TMA, hi / lo written in place, read by three MMAs per k-step).
+// the small Bu tile (weights: raw via TMA, lo written behind it, read by three MMAs per k-step).
 //
-//   warps 0, 10 producers: two rings with a producer warp each, so that the Au ring (raw 16 KiB tiles, up to 8 deep:
-//                          what is in flight from HBM) runs ahead of the 4-deep Bu ring the MMAs release
-//   warps 2-5   splitter : thread = one row of Au (TMEM lane): 32 values -> hi, lo -> TMEM slot of the Bu stage;
-//                          the Au slot is handed back as soon as it has been read; then Bu is split in place
-//   warp 1      MMA      : per k-step hi*lo, lo*hi, hi*hi; the commit frees the Bu stage and its TMEM slot
-//   warps 6-9   epilogue : as above
-// TMEM: two accumulator slots of 128 columns + 4 x (32 hi + 32 lo) columns of Au.  N per tile <= 128.
+// What is left is the traffic INTO the SM: a byte costs the same from L2 as from HBM on this part, and
+// the weight tile is fetched again for every 128-row tile of Au.  So a unit covers up to TWO m-tiles (g = 2) that
+// share every Bu stage: half the weight traffic and half the splitting work per byte of Au.
+//
+//   warps 0, 10 producers: two rings with a producer warp each, so that the Au ring (raw tiles of one 32-wide K slab for
+//                          the unit's m-tiles, 32 KiB a stage) runs ahead of the 4-deep Bu ring the MMAs release
+//   warps 2-5   Au splitters: thread = one row = one TMEM lane, per m-tile 32 values -> hi, lo -> tcgen05.st; the Au stage is
+//                          handed back as soon as it has been read
+//   warps 11-14 Bu splitters: lo = x - trunc(x) behind the raw tile (the tensor core ignores the low 13 mantissa bits itself)
+//   warp 1      MMA      : per m-tile and k-step hi*lo, lo*hi, hi*hi; commits free the Bu stage and the TMEM operand slot
+//   warps 6-9   epilogue : as above, one accumulator per m-tile
+// TMEM (512 columns): accumulators [0, 256) = slots x 2 m-tiles x (64 or 128) columns -- two slots when every tile of the
+// launch has at most 64 columns, else one; Au operand ring [256, 512) = 2 slots x 2 m-tiles x (32 hi + 32 lo).
 // An MN-major Au tile is fetched unswizzled (a thread reads its row as 32 conflict-free 4-byte loads); an
 // MN-major Bu tile uses the 32B-base swizzle the tensor core requires of 32-bit MN-major operands.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int TS_MAX_BN = 128;
-constexpr int TS_ACC_SLOTS = 2;
-constexpr int TS_A_COL = TS_ACC_SLOTS * TS_MAX_BN;  // first TMEM column of the Au ring
-constexpr int TS_B_STAGES = 4;                      // == TMEM Au slots (64 columns each)
+constexpr int TS_G = 2;                             // m-tiles per unit that share a Bu stage
+constexpr int TS_A_COL = 256;                       // first TMEM column of the Au operand ring
+constexpr int TS_T_SLOTS = 2;                       // TMEM operand slots (each TS_G x 64 columns)
+constexpr int TS_B_STAGES = 4;
 constexpr int TS_MAX_A_STAGES = 8;
-constexpr int TS_A_STAGE_BYTES = 2 * GM_A_BYTES;    // an Au stage carries TWO 32-wide K slabs (256 contiguous bytes per row)
+constexpr int TS_A_STAGE_BYTES = TS_G * GM_A_BYTES; // one K slab of the unit's m-tiles
 constexpr int TS_BSPLIT_WARPS = 4;
 constexpr int TS_THREADS = GM_THREADS + 32 + TS_BSPLIT_WARPS * 32;  // + warp 10 (Bu producer) + warps 11-14 (Bu splitters)
 
@@ -459,10 +476,11 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
   const uint32_t bar_aempty = bar_afull + TS_MAX_A_STAGES * 8;           // [TS_MAX_A_STAGES] Au splitters -> producer
   const uint32_t bar_bfull = bar_aempty + TS_MAX_A_STAGES * 8;           // [TS_B_STAGES] producer -> Bu splitters
   const uint32_t bar_ready = bar_bfull + TS_B_STAGES * 8;                // [TS_B_STAGES] all splitters -> MMA
-  const uint32_t bar_bfree = bar_ready + TS_B_STAGES * 8;                // [TS_B_STAGES] MMA -> Bu producer, Au splitters
-  const uint32_t bar_acc_full = bar_bfree + TS_B_STAGES * 8;             // [TS_ACC_SLOTS]
-  const uint32_t bar_acc_empty = bar_acc_full + TS_ACC_SLOTS * 8;        // [TS_ACC_SLOTS]
-  const uint32_t tmem_ptr_off = L.bar_off + (2 * TS_MAX_A_STAGES + 3 * TS_B_STAGES + 2 * TS_ACC_SLOTS) * 8;
+  const uint32_t bar_bfree = bar_ready + TS_B_STAGES * 8;                // [TS_B_STAGES] MMA -> Bu producer
+  const uint32_t bar_tfree = bar_bfree + TS_B_STAGES * 8;                // [TS_T_SLOTS] MMA -> Au splitters (TMEM operand slot)
+  const uint32_t bar_acc_full = bar_tfree + TS_T_SLOTS * 8;              // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 2 * 8;                   // [2]
+  const uint32_t tmem_ptr_off = L.bar_off + (2 * TS_MAX_A_STAGES + 3 * TS_B_STAGES + TS_T_SLOTS + 4) * 8;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + tmem_ptr_off);
 
   if (warp == 1 && lane == 0) {
@@ -475,7 +493,8 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
       mbar_init(bar_ready + s * 8, GM_SPLIT_WARPS + TS_BSPLIT_WARPS);
       mbar_init(bar_bfree + s * 8, 1);
     }
-    for (int a = 0; a < TS_ACC_SLOTS; ++a) {
+    for (uint32_t s = 0; s < (uint32_t)TS_T_SLOTS; ++s) mbar_init(bar_tfree + s * 8, 1);
+    for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full + a * 8, 1);
       mbar_init(bar_acc_empty + a * 8, GM_EPI_WARPS);
     }
@@ -488,69 +507,68 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   GemmWalker W(&single, L);
-  constexpr uint32_t KEL = 32;                 // fp32 elements of K per slab (128 bytes): one Bu stage, one TMEM slot
-  constexpr uint32_t GROUP_BYTES = KEL * 128;  // one 32-wide MN group of an MN-major Bu tile
+  constexpr uint32_t KEL = 32;                 // fp32 elements of K per slab (128 bytes): one stage of either ring
+  constexpr uint32_t GROUP_BYTES = KEL * 128;  // one 32-wide MN group of an MN-major tile
 
   if (warp == 0) {
-    // ===================== Au producer: one stage = two K slabs =====================
+    // ===================== Au producer: one stage = one K slab of the unit's m-tiles =====================
     const bool leader = elect_one();
     uint32_t st = 0, ph = 0;
     const GemmProblemDev* last = nullptr;
-    const CUtensorMap *tmap = nullptr, *tmap2 = nullptr;
-    uint32_t m_tiles = 1, n_tiles = 1, k_tiles = 0, full_groups = 0, mn = 0, bat = 0, unit_begin = 0;
+    const CUtensorMap* tmap = nullptr;
+    uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, k_tiles = 0, mn = 0, bat = 0, unit_begin = 0;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
-        tmap = &P->tmap_a; tmap2 = &P->tmap_a2;
-        if (leader) { prefetch_tmap(tmap); prefetch_tmap(tmap2); }
-        m_tiles = uni(P->m_tiles); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); full_groups = uni(P->k) / KEL;
-        mn = uni(P->a_mn); bat = uni(P->a_batched); unit_begin = uni(P->unit_begin);
+        tmap = &P->tmap_a;
+        if (leader) prefetch_tmap(tmap);
+        m_tiles = uni(P->m_tiles); m_groups = uni(P->m_groups); g = uni(P->g); n_tiles = uni(P->n_tiles);
+        k_tiles = uni(P->k_tiles); mn = uni(P->a_mn); bat = uni(P->a_batched); unit_begin = uni(P->unit_begin);
       }
       const uint32_t local = W.u - unit_begin;
       const uint32_t t1 = local / n_tiles;
-      const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
-      const int bc = bat ? (int)b : 0, row0 = (int)(mt * GM_BM);
-      for (uint32_t kt = 0; kt < k_tiles; kt += 2) {
+      const uint32_t mg = t1 % m_groups, b = t1 / m_groups;
+      const uint32_t mt0 = mg * g, g_count = min(g, m_tiles - mt0);
+      const int bc = bat ? (int)b : 0;
+      for (uint32_t kt = 0; kt < k_tiles; ++kt) {
         mbar_wait(bar_aempty + st * 8, ph ^ 1u);
         const uint32_t full = bar_afull + st * 8, dst = smem_base + st * (uint32_t)TS_A_STAGE_BYTES;
-        const uint32_t slabs = min(2u, k_tiles - kt);
         if (leader) {
-          mbar_expect_tx(full, (mn ? 2u : slabs) * (uint32_t)GM_A_BYTES);
-          if (mn) {
-            // MN-major, unswizzled: four groups of 32 rows, each [64 k-rows][32 rows] (the box always spans both slabs;
-            // k rows beyond K are zero-filled)
-            for (uint32_t g = 0; g < 4; ++g)
-              tma_load_3d(dst + g * 2u * GROUP_BYTES, tmap, row0 + (int)(g * KEL), (int)(kt * KEL), bc, full, HINT_EVICT_NORMAL);
-          } else if (kt + 2 <= full_groups) {
-            // both slabs in one instruction: [K/32 groups][rows][32] view, box (32, 128, 2) = 256 contiguous bytes per row
-            tma_load_4d(dst, tmap2, 0, row0, (int)kt, bc, full, HINT_EVICT_NORMAL);
-          } else {
-            for (uint32_t h = 0; h < slabs; ++h)  // the ragged end of K: plain boxes, zero-filled beyond K
-              tma_load_3d(dst + h * (uint32_t)GM_A_BYTES, tmap, (int)((kt + h) * KEL), row0, bc, full, HINT_EVICT_NORMAL);
+          mbar_expect_tx(full, g_count * (uint32_t)GM_A_BYTES);
+          for (uint32_t t = 0; t < g_count; ++t) {
+            const int row0 = (int)((mt0 + t) * GM_BM);
+            const uint32_t d = dst + t * (uint32_t)GM_A_BYTES;
+            if (!mn) {
+              tma_load_3d(d, tmap, (int)(kt * KEL), row0, bc, full, HINT_EVICT_NORMAL);
+            } else {
+              // MN-major, unswizzled: four groups of 32 rows, each [32 k-rows][32 rows]; k rows beyond K are zero-filled
+              for (uint32_t q = 0; q < 4; ++q)
+                tma_load_3d(d + q * GROUP_BYTES, tmap, row0 + (int)(q * KEL), (int)(kt * KEL), bc, full, HINT_EVICT_NORMAL);
+            }
           }
         }
         if (++st == NA) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 10) {
-    // ===================== Bu producer: one stage = one K slab =====================
+    // ===================== Bu producer =====================
     const bool leader = elect_one();
     uint32_t st = 0, ph = 0;
     const GemmProblemDev* last = nullptr;
     const CUtensorMap* tmap = nullptr;
-    uint32_t m_tiles = 1, n_tiles = 1, k_tiles = 0, bn = 0, mn = 0, bat = 0, unit_begin = 0;
+    uint32_t m_groups = 1, n_tiles = 1, k_tiles = 0, bn = 0, mn = 0, bat = 0, unit_begin = 0;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
         tmap = &P->tmap_b;
         if (leader) prefetch_tmap(tmap);
-        m_tiles = uni(P->m_tiles); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); bn = uni(P->bn);
+        m_groups = uni(P->m_groups); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); bn = uni(P->bn);
         mn = uni(P->b_mn); bat = uni(P->b_batched); unit_begin = uni(P->unit_begin);
       }
       const uint32_t local = W.u - unit_begin;
-      const uint32_t nt = local % n_tiles, b = local / n_tiles / m_tiles;
+      const uint32_t nt = local % n_tiles, b = local / n_tiles / m_groups;
       const int bc = bat ? (int)b : 0, row0 = (int)(nt * bn);
       for (uint32_t kt = 0; kt < k_tiles; ++kt) {
         mbar_wait(bar_bfree + st * 8, ph ^ 1u);
@@ -558,10 +576,10 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
         if (leader) {
           mbar_expect_tx(full, bn * (uint32_t)GM_ROW_BYTES);
           if (!mn) {
-            tma_load_3d(dst, tmap, (int)(kt * KEL), row0, bc, full, HINT_EVICT_LAST);  // re-read by every tile: keep in L2
+            tma_load_3d(dst, tmap, (int)(kt * KEL), row0, bc, full, HINT_EVICT_LAST);  // re-read by every unit: keep in L2
           } else {
-            for (uint32_t g = 0; g * KEL < bn; ++g)
-              tma_load_3d(dst + g * GROUP_BYTES, tmap, row0 + (int)(g * KEL), (int)(kt * KEL), bc, full, HINT_EVICT_LAST);
+            for (uint32_t q = 0; q * KEL < bn; ++q)
+              tma_load_3d(dst + q * GROUP_BYTES, tmap, row0 + (int)(q * KEL), (int)(kt * KEL), bc, full, HINT_EVICT_LAST);
           }
         }
         if (++st == NB) { st = 0; ph ^= 1u; }
@@ -571,44 +589,55 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
     const uint32_t tmem_b = uni(tmem_base);
-    uint32_t sb = 0, phb = 0, job = 0;
+    uint32_t sb = 0, phb = 0, slab = 0, job = 0;
     const GemmProblemDev* last = nullptr;
-    uint32_t k_tiles = 0, pk = 0, bn = 0, b_mn = 0;
-    const uint32_t lo_off = L.raw_bytes >> 4;  // Bu lo tile sits raw_bytes behind the hi one (16-byte units)
+    uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, k_tiles = 0, pk = 0, bn = 0, b_mn = 0, unit_begin = 0;
+    const uint32_t lo_off = L.raw_bytes >> 4;  // Bu lo tile sits raw_bytes behind the raw one (16-byte units)
     const uint64_t desc_k = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
     const uint64_t desc_mn = make_smem_desc(0, GROUP_BYTES, 512, LAYOUT_SW128_BASE32B);
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
-        k_tiles = uni(P->k_tiles); pk = uni(P->k); bn = uni(P->bn); b_mn = uni(P->b_mn);
+        m_tiles = uni(P->m_tiles); m_groups = uni(P->m_groups); g = uni(P->g); n_tiles = uni(P->n_tiles);
+        k_tiles = uni(P->k_tiles); pk = uni(P->k); bn = uni(P->bn); b_mn = uni(P->b_mn); unit_begin = uni(P->unit_begin);
       }
-      const uint32_t slot = job % TS_ACC_SLOTS, use = job / TS_ACC_SLOTS;
+      const uint32_t local = W.u - unit_begin;
+      const uint32_t mg = (local / n_tiles) % m_groups;
+      const uint32_t g_count = min(g, m_tiles - mg * g);
+      const uint32_t slot = job % L.acc_slots, use = job / L.acc_slots;
       mbar_wait(bar_acc_empty + slot * 8, (use & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_b + slot * (uint32_t)TS_MAX_BN;
+      const uint32_t tmem_d = tmem_b + slot * (uint32_t)TS_G * L.d_cols;  // m-tile t at + t * d_cols
       const uint32_t idesc = L.idesc | (b_mn << 16) | ((bn >> 3) << 17);  // the A operand in TMEM is K-major by construction
       const uint64_t db_hi = b_mn ? desc_mn : desc_k;
       const uint32_t b_step = b_mn ? (8u * GM_ROW_BYTES) >> 4 : 2u;       // 8 k-rows of 128 bytes / 32 bytes inside the row
       uint32_t k_left = pk;
-      for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= KEL) {
+      for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= KEL, ++slab) {
         mbar_wait(bar_ready + sb * 8, phb);
         tc_fence_after();
         const uint32_t b0 = ((smem_base + L.b_off + sb * L.stage_bytes) >> 4) & 0x3fffu;
-        const uint32_t ta = tmem_b + (uint32_t)TS_A_COL + sb * 64u;
+        const uint32_t ts = slab % TS_T_SLOTS;
+        const uint32_t ta = tmem_b + (uint32_t)TS_A_COL + ts * (uint32_t)(TS_G * 64);
         const uint32_t nk = k_left >= KEL ? 4u : (k_left + 7u) / 8u;
         if (leader) {
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) {
-            if (j < nk && !(L.dbg & 1u)) {
-              const uint64_t db = db_hi | (uint64_t)(b0 + b_step * j);
-              const uint32_t a_hi = ta + 8u * j, a_lo = a_hi + 32u;
-              tc_mma_tf32_ts(tmem_d, a_hi, db + lo_off, idesc, (kt | j) ? 1u : 0u);  // hi * lo
-              tc_mma_tf32_ts(tmem_d, a_lo, db, idesc, 1u);                           // lo * hi
-              tc_mma_tf32_ts(tmem_d, a_hi, db, idesc, 1u);                           // hi * hi
+          for (uint32_t t = 0; t < (uint32_t)TS_G; ++t) {
+            if (t < g_count && !(L.dbg & 1u)) {
+#pragma unroll
+              for (uint32_t j = 0; j < 4; ++j) {
+                if (j < nk) {
+                  const uint64_t db = db_hi | (uint64_t)(b0 + b_step * j);
+                  const uint32_t a_hi = ta + t * 64u + 8u * j, a_lo = a_hi + 32u, d = tmem_d + t * L.d_cols;
+                  tc_mma_tf32_ts(d, a_hi, db + lo_off, idesc, (kt | j) ? 1u : 0u);  // hi * lo
+                  tc_mma_tf32_ts(d, a_lo, db, idesc, 1u);                           // lo * hi
+                  tc_mma_tf32_ts(d, a_hi, db, idesc, 1u);                           // hi * hi
+                }
+              }
             }
           }
           tc_commit(bar_bfree + sb * 8);
+          tc_commit(bar_tfree + ts * 8);
         }
         if (++sb == NB) { sb = 0; phb ^= 1u; }
       }
@@ -616,39 +645,45 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
       ++job;
     }
   } else if (warp < 2 + GM_SPLIT_WARPS) {
-    // ===================== Au splitters: thread = one row of the tile = one TMEM lane =====================
+    // ===================== Au splitters: thread = one row of a tile = one TMEM lane =====================
     const uint32_t row = (warp & 3u) * 32u + lane;  // the TMEM lane quarter a warp may touch is warp % 4
-    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0, slab = 0;
     const GemmProblemDev* last = nullptr;
-    uint32_t k_tiles = 0, a_mn = 0;
+    uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, k_tiles = 0, a_mn = 0, unit_begin = 0;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
-      if (P != last) { last = P; k_tiles = P->k_tiles; a_mn = P->a_mn; }
-      for (uint32_t kt = 0; kt < k_tiles; kt += 2) {
+      if (P != last) {
+        last = P;
+        m_tiles = P->m_tiles; m_groups = P->m_groups; g = P->g; n_tiles = P->n_tiles; k_tiles = P->k_tiles; a_mn = P->a_mn;
+        unit_begin = P->unit_begin;
+      }
+      const uint32_t mg = ((W.u - unit_begin) / n_tiles) % m_groups;
+      const uint32_t g_count = min(g, m_tiles - mg * g);
+      for (uint32_t kt = 0; kt < k_tiles; ++kt, ++slab) {
         mbar_wait(bar_afull + sa * 8, pha);
         const uint32_t src = smem_base + sa * (uint32_t)TS_A_STAGE_BYTES;
-        const uint32_t slabs = min(2u, k_tiles - kt);
-        for (uint32_t hf = 0; hf < slabs; ++hf) {
-          const uint32_t ta = tmem_base + (uint32_t)TS_A_COL + sb * 64u + (((warp & 3u) * 32u) << 16);
-          // the slab in two pieces of 16 values (keeps the working set at 32 registers)
+        const uint32_t ts = slab % TS_T_SLOTS;
+        const uint32_t ta = tmem_base + (uint32_t)TS_A_COL + ts * (uint32_t)(TS_G * 64) + (((warp & 3u) * 32u) << 16);
+        for (uint32_t t = 0; t < g_count; ++t) {
+          // the row in two pieces of 16 values (keeps the working set at 32 registers)
 #pragma unroll
           for (uint32_t q = 0; q < 2; ++q) {
             uint32_t x[16], h[16];
             if (!a_mn) {
               // K-major, 128B-swizzled: chunk c of row r at (c ^ (r & 7)) * 16 -- 8 lanes cover all banks
-              const uint32_t rbase = src + hf * (uint32_t)GM_A_BYTES + row * 128u, sw = row & 7u;
+              const uint32_t rbase = src + t * (uint32_t)GM_A_BYTES + row * 128u, sw = row & 7u;
 #pragma unroll
               for (uint32_t c = 0; c < 4; ++c) {
                 const uint4 v = ld_shared_v4(rbase + (((4u * q + c) ^ sw) << 4));
                 x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
               }
             } else {
-              // MN-major, unswizzled groups of 32 rows x 64 k-rows: k-row kk at kk*128, my element at (row % 32) * 4
-              const uint32_t rbase = src + (row >> 5) * 2u * GROUP_BYTES + (hf * 32u + q * 16u) * 128u + (row & 31u) * 4u;
+              // MN-major, unswizzled groups of 32 rows x 32 k-rows: k-row kk at kk*128, my element at (row % 32) * 4
+              const uint32_t rbase = src + t * (uint32_t)GM_A_BYTES + (row >> 5) * GROUP_BYTES + q * 16u * 128u + (row & 31u) * 4u;
 #pragma unroll
               for (uint32_t kk = 0; kk < 16; ++kk) x[kk] = ld_shared_u32(rbase + kk * 128u);
             }
-            if (q == 1 && hf + 1 == slabs) {  // the stage has been read: hand it back before doing anything else
+            if (q == 1 && t + 1 == g_count) {  // the stage has been read: hand it back before doing anything else
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_aempty + sa * 8);
             }
@@ -662,23 +697,23 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
 #pragma unroll
               for (int i = 0; i < 16; ++i) h[i] = x[i];
             }
-            if (q == 0) {
-              // TMEM slot sb is free once the MMAs of the stage that used it last have completed
-              mbar_wait(bar_bfree + sb * 8, phb ^ 1u);
+            if (q == 0 && t == 0) {
+              // the TMEM operand slot is free once the MMAs of the slab that used it last have completed
+              mbar_wait(bar_tfree + ts * 8, (((slab / TS_T_SLOTS) & 1u) ^ 1u));
               tc_fence_after();
             }
             if (!(L.dbg & 4u)) {
-              tmem_st_x16(ta + q * 16u, h);
-              tmem_st_x16(ta + 32u + q * 16u, x);
+              tmem_st_x16(ta + t * 64u + q * 16u, h);
+              tmem_st_x16(ta + t * 64u + 32u + q * 16u, x);
             }
           }
-          if (!(L.dbg & 4u)) tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_ready + sb * 8);
-          if (++sb == NB) { sb = 0; phb ^= 1u; }
         }
         if (++sa == NA) { sa = 0; pha ^= 1u; }
+        if (!(L.dbg & 4u)) tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready + sb * 8);
+        if (++sb == NB) { sb = 0; phb ^= 1u; }
       }
     }
   } else if (warp >= 11) {
@@ -725,7 +760,7 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
       }
     }
   } else {  // warps 6-9
-    gemm_epilogue<KIND_F32>(W, tmem_base, bar_acc_full, bar_acc_empty, TS_ACC_SLOTS, TS_MAX_BN, warp, lane);
+    gemm_epilogue<KIND_F32>(W, tmem_base, bar_acc_full, bar_acc_empty, L.acc_slots, (uint32_t)TS_G * L.d_cols, L.d_cols, warp, lane);
   }
 
   tc_fence_before();
@@ -810,29 +845,6 @@ int make_operand_map(CUtensorMap* map, int dtype, const OperandView& v, size_t n
   return SPFY_OK;
 }
 
-// K-major fp32 operand viewed as [K/32 full groups][rows][32]: a box (32, 128, 2) lands as two consecutive 128B-swizzled
-// (128 x 32) slabs -- 256 contiguous bytes per row -- with one instruction.  Only FULL groups are part of the view (a
-// partial last group would read past the row), so the ragged end of K goes through the plain map.
-int make_grouped_map(CUtensorMap* map, const OperandView& v, size_t nb) {
-  EncodeTiledFn enc0;
-  int rc = get_encoder(&enc0);
-  if (rc) return rc;
-  EncodeFn enc = (EncodeFn)enc0;
-  const bool batched = nb > 1 && v.stride != 0;
-  const size_t groups = std::max<size_t>(v.k / 32, 1);
-  cuuint64_t dims[4] = {32, v.mn, groups, batched ? nb : 1};
-  const size_t bstride = batched ? v.stride * 4 : round_up(std::max<size_t>(v.mn, 1) * v.ld * 4, 16);
-  cuuint64_t strides[3] = {v.ld * 4, 128, bstride};
-  cuuint32_t box[4] = {32, GM_BM, 2, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(v.base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(SPFY_E_CUDA, "tc_gemm: cuTensorMapEncodeTiled (grouped) failed (%d): rows %zu k %zu ld %zu", (int)r, v.mn, v.k, v.ld);
-  return SPFY_OK;
-}
-
 // column split of the Nu dimension: one tile when it fits a UMMA, equal tiles otherwise
 void split_nu(size_t nu, size_t gran, size_t max_bn, uint32_t* bn, uint32_t* n_tiles) {
   size_t tiles = ceil_div(nu, max_bn);
@@ -896,8 +908,8 @@ int check_problem(int dtype, const TcGemmProblem& p, bool allow_repack) {
   return SPFY_OK;
 }
 
-// `ts`: the 3xTF32 kernel with Au in tensor memory (tiles of at most TS_MAX_BN columns)
-int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts) {
+// `ts`: the 3xTF32 kernel with Au in tensor memory (tiles of at most TS_MAX_BN columns, up to two m-tiles per unit)
+int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, int sm_count) {
   memset(d, 0, sizeof(*d));
   const Orientation o = orient(dtype, p, ts ? TS_MAX_BN : GM_MAX_BN);
   // K-major tiles and 16-bit MN-major tiles: 128-byte swizzle.  32-bit MN-major tiles: the tensor core reads them in
@@ -906,13 +918,8 @@ int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts) 
   const CUtensorMapSwizzle sw_a = !(f32 && o.a.mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : ts ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   const CUtensorMapSwizzle sw_b = f32 && o.b.mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-  // (3xTF32 kernel, MN-major Au: the box spans the two K slabs of a stage)
-  int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM, sw_a, ts && o.a.mn_major ? 64u : 0u);
+  int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM, sw_a);
   if (rc) return rc;
-  if (ts && !o.a.mn_major) {
-    rc = make_grouped_map(&d->tmap_a2, o.a, p.nb);
-    if (rc) return rc;
-  }
   rc = make_operand_map(&d->tmap_b, dtype, o.b, p.nb, o.bn, sw_b);
   if (rc) return rc;
   const size_t kel = GM_ROW_BYTES / elem_bytes(dtype);
@@ -935,7 +942,14 @@ int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts) 
   d->out_mu_contig = o.mu_contig;
   d->alpha = p.alpha;
   d->beta = p.beta;
-  const uint64_t units = (uint64_t)d->m_tiles * d->n_tiles * d->nb;
+  // two m-tiles share every Bu stage whenever that leaves at least half a wave of units (bytes entering the SMs, not
+  // units, are what the kernel is short of: DESIGN.md 4)
+  d->g = 1;
+  if (ts && d->m_tiles >= 2 &&
+      2 * (uint64_t)ceil_div(d->m_tiles, TS_G) * d->n_tiles * d->nb >= (uint64_t)sm_count && !dev_switch("SPFY_GEMM_G1"))
+    d->g = TS_G;
+  d->m_groups = (uint32_t)ceil_div(d->m_tiles, d->g);
+  const uint64_t units = (uint64_t)d->m_groups * d->n_tiles * d->nb;
   if (units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
   d->units = (uint32_t)units;
   return SPFY_OK;
@@ -1075,7 +1089,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
       q.B = vb.base; q.ldb = vb.ld; q.strideB = vb.stride;
     }
     GemmProblemDev d;
-    rc = fill_problem(&d, dtype, q, ts);
+    rc = fill_problem(&d, dtype, q, ts, di.sm_count);
     if (rc) return rc;
     d.unit_begin = units;
     if ((uint64_t)units + d.units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
@@ -1112,6 +1126,8 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
     }
     L.a_stages = a_stages;
     if (a_stages < 2) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: tile does not fit shared memory");
+    L.d_cols = bn_max <= 64 ? 64u : 128u;   // accumulators [0, 256): slots x TS_G m-tiles x d_cols
+    L.acc_slots = bn_max <= 64 ? 2u : 1u;
     L.b_off = a_stages * (uint32_t)TS_A_STAGE_BYTES;
     L.bar_off = L.b_off + L.stages * L.stage_bytes;
     smem = L.bar_off + GM_BAR_BYTES + 1024u;

@@ -78,14 +78,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint32_t bar, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
-      : "memory");
-}
 // im2col mode (4-D NHWC tensor {C, W, H, N}): `pixels` consecutive output positions starting at base pixel (w, h, n) --
 // walking W, then H, then N inside the bounding box of the tensor map -- x `channels` channels from c, at filter tap
 // (off_w, off_h); out-of-image taps are zero-filled
