@@ -491,10 +491,12 @@ def run_coo(args):
                             "kernel launches of one eager step x steps") if graphs else "eager",
             "phases": {"threshold_to_coo_ms": prune_ms, "spmm_ms": spmm_ms, "spmm_tflops": fl_all / spmm_ms / 1e9,
                        "note": "the threshold prune is replicated on every rank; no host read-back (CSR row_ptr stays on the device)"},
-            "roofline": {"bound": "hbm", "kernel": "spmm_csr_kernel", "achieved": by_all / spmm_ms / 1e6, "peak": hbm_peak * world,
+            "roofline": {"bound": "hbm", "kernel": "coo_scatter_kernel + tcgemm_ts_kernel (3xTF32, A in tensor memory; k = 147 on a padded "
+                                                   "copy of B)", "achieved": by_all / spmm_ms / 1e6, "peak": hbm_peak * world,
                          "unit": "GB/s", "frac": by_all / spmm_ms / 1e6 / (hbm_peak * world), "traffic": None,
                          "peak_source": peak_src,
-                         "note": "the binding roofline of this kernel is shared-memory wavefronts, not HBM (DESIGN.md 4)"}}),
+                         "note": "bytes are the SPARSE algorithmic ones (12 nnz + 4KN + 4MN per batch); the dense contraction is "
+                                 "bound by the traffic into the SMs and the 3x tensor work, not by HBM (DESIGN.md 4)"}}),
               file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
