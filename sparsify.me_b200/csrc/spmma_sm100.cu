@@ -80,7 +80,8 @@ struct alignas(64) ProblemDev {
   uint32_t m, n, k;
   uint32_t m_tiles, k_tiles, n_tiles, m_groups;
   uint32_t G;          // m-tiles per unit
-  uint32_t resident;   // whole A lives in shared memory
+  uint32_t resident;   // 1: whole A lives in shared memory; 2: the unit's m-group slice of A does (reloaded when the
+                       // CTA's next unit belongs to another m-group, which never happens when gridDim % m_groups == 0)
   uint32_t b3d;
   uint32_t unit_begin, units;  // this problem's range in the launch-wide unit order
   float alpha, beta;
@@ -192,6 +193,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       uint32_t stage = 0, phase = 0;  // ring position (continuous over units)
       uint32_t res_loads = 0;         // resident (re)loads issued so far
       const ProblemDev* res_owner = nullptr;
+      uint32_t res_mg = 0;            // ... and the m-group they hold (sliced residency)
       const ProblemDev* last = nullptr;
       const CUtensorMap* tmap_b = nullptr;
       const uint8_t *a_vals = nullptr, *a_meta = nullptr;
@@ -227,11 +229,26 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           cn = (int)(row / conv_ho);
           ch = (int)((row - (uint32_t)cn * conv_ho) * conv_stride) - (int)conv_pad;
         }
-        if (resident && res_owner != P) {
-          // (re)load the whole compressed A of this problem into the resident region
+        // the G tiles of a k-tile are adjacent in the operand, so one copy per array fetches a group's share of it
+        const uint32_t rv0 = rows_valid_of(pm, mt0);
+        const uint32_t rv1 = g_count > 1 ? rows_valid_of(pm, mt0 + 1) : 0u;
+        const uint32_t a_bytes = g_count > 1 ? (uint32_t)A_TILE_BYTES + rv1 * 128u : rv0 * 128u;
+        const uint32_t e_bytes = g_count > 1 ? (uint32_t)E_TILE_BYTES + rv1 * 16u : rv0 * 16u;
+        const uint32_t res_key = resident == 2u ? mg : 0u;
+        if (resident && (res_owner != P || res_mg != res_key)) {
+          // (re)load the compressed A of this problem (or of this m-group of it) into the resident region
           mbar_wait(bar_res_empty, (res_loads & 1u) ^ 1u);
           if (leader) {
-            if (m_tiles == 1) {
+            if (resident == 2u) {
+              // m-group slice: k-tile kt of the group at kt * G tiles
+              mbar_expect_tx(bar_res_full, k_tiles * (a_bytes + e_bytes));
+              for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+                bulk_load_1d(smem_base + L.res_off + kt * G * (uint32_t)A_TILE_BYTES,
+                             a_vals + ((size_t)kt * m_tiles + mt0) * A_TILE_BYTES, a_bytes, bar_res_full, HINT_EVICT_LAST);
+                bulk_load_1d(smem_base + L.res_e_off + kt * G * (uint32_t)E_TILE_BYTES,
+                             a_meta + ((size_t)kt * m_tiles + mt0) * E_TILE_BYTES, e_bytes, bar_res_full, HINT_EVICT_LAST);
+              }
+            } else if (m_tiles == 1) {
               // a single, possibly short, m-tile: compact rows, one copy per k-tile and array
               const uint32_t rv = rows_valid_of(pm, 0);
               mbar_expect_tx(bar_res_full, k_tiles * rv * 144u);
@@ -250,13 +267,9 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             }
           }
           res_owner = P;
+          res_mg = res_key;
           ++res_loads;
         }
-        // per-unit registers: the G tiles of a k-tile are adjacent, so one copy per array and stage
-        const uint32_t rv0 = rows_valid_of(pm, mt0);
-        const uint32_t rv1 = g_count > 1 ? rows_valid_of(pm, mt0 + 1) : 0u;
-        const uint32_t a_bytes = g_count > 1 ? (uint32_t)A_TILE_BYTES + rv1 * 128u : rv0 * 128u;
-        const uint32_t e_bytes = g_count > 1 ? (uint32_t)E_TILE_BYTES + rv1 * 16u : rv0 * 16u;
         const uint8_t* av = a_vals + (size_t)mt0 * A_TILE_BYTES;
         const uint8_t* am = a_meta + (size_t)mt0 * E_TILE_BYTES;
         const size_t av_step = (size_t)m_tiles * A_TILE_BYTES, am_step = (size_t)m_tiles * E_TILE_BYTES;
@@ -310,7 +323,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     {
       const bool leader = elect_one();
       const uint32_t tmem_b = uni(tmem_base);
-      uint32_t stage = 0, phase = 0, job = 0, eblk = 0, res_loads = 0;
+      uint32_t stage = 0, phase = 0, job = 0, eblk = 0, res_loads = 0, res_mg = 0;
       const ProblemDev* res_owner = nullptr;
       const ProblemDev* last = nullptr;
       uint32_t pm = 0, pk = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, units = 0;
@@ -332,9 +345,11 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const uint32_t mg = local % m_groups;
         const uint32_t mt0 = mg * G;
         const uint32_t g_count = min(G, m_tiles - mt0);
-        if (resident && res_owner != P) {
+        const uint32_t res_key = resident == 2u ? mg : 0u;
+        if (resident && (res_owner != P || res_mg != res_key)) {
           mbar_wait(bar_res_full, res_loads & 1u);
           res_owner = P;
+          res_mg = res_key;
           ++res_loads;
         }
         // accumulator slots of this unit's jobs
@@ -348,9 +363,11 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const uint32_t rv_single = rows_valid_of(pm, 0);
         const uint32_t rsv = m_tiles == 1 ? rv_single * 128u : (uint32_t)A_TILE_BYTES;
         const uint32_t rse = m_tiles == 1 ? rv_single * 16u : (uint32_t)E_TILE_BYTES;
-        uint32_t ra = smem_base + L.res_off + mt0 * rsv, re = smem_base + L.res_e_off + mt0 * rse;
+        // (a slice holds the G tiles of its m-group only)
+        const uint32_t res_first = resident == 2u ? 0u : mt0, res_tiles = resident == 2u ? G : m_tiles;
+        uint32_t ra = smem_base + L.res_off + res_first * rsv, re = smem_base + L.res_e_off + res_first * rse;
         uint32_t k_left = pk;
-        for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= BK, ra += m_tiles * rsv, re += m_tiles * rse) {
+        for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= BK, ra += res_tiles * rsv, re += res_tiles * rse) {
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
@@ -391,7 +408,9 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
         const uint32_t nu = W.u + gridDim.x;
-        const bool last_of_problem = resident && (nu >= L.total_units || nu >= unit_begin + units);
+        // last use of what the resident region holds: the CTA's next unit is another problem's, or another m-group's
+        const bool last_of_problem = resident && (nu >= L.total_units || nu >= unit_begin + units ||
+                                                  (resident == 2u && (nu - unit_begin) % m_groups != mg));
         if (leader) {
           tc_commit(bar_acc_full + slot0 * 8);
           if (g_count > 1) tc_commit(bar_acc_full + slot1 * 8);
@@ -636,12 +655,26 @@ size_t resident_bytes(size_t m, size_t k) {
   return m_tiles * k_tiles * rows * 144;  // 128 B of values + 16 B of metadata per row and k-tile
 }
 
+// Sliced residency: A as a whole is too large, but the two m-tiles of one m-group (all k-tiles) fit, and every CTA
+// keeps meeting the same m-group (units are dealt nt-major with the m-group fastest and a stride of gridDim, so the
+// group a CTA sees is constant when the grid is a multiple of m_groups).  The CTA then loads its slice once and streams
+// B only, like the resident classes, instead of pulling the same 36 KiB per k-tile through the ring for every unit.
+size_t slice_bytes(size_t k) { return 2 * ceil_div(k, 128) * (size_t)(A_TILE_BYTES + E_TILE_BYTES); }
+
+bool sliced_residency(const HostProblem& h, int sm_count) {
+  static const bool off = dev_switch("SPFY_SPMMA_NO_SLICES") != nullptr;
+  const size_t m_tiles = ceil_div(h.m, BM), n_tiles = ceil_div(h.n, BN), m_groups = ceil_div(m_tiles, 2);
+  return !off && m_tiles >= 2 && h.k > 64 && resident_bytes(h.m, h.k) > RES_MAX_BYTES && slice_bytes(h.k) <= RES_MAX_BYTES &&
+         (size_t)sm_count % m_groups == 0 && m_groups * n_tiles >= 2 * (size_t)sm_count;
+}
+
 int classify(const HostProblem& h, bool grouped, int sm_count) {
   const size_t m_tiles = ceil_div(h.m, BM), n_tiles = ceil_div(h.n, BN);
   if (resident_bytes(h.m, h.k) <= RES_MAX_BYTES && n_tiles >= (size_t)sm_count) {
     if (h.k <= 64) return CLASS_RES_K64;
     return resident_bytes(h.m, h.k) <= RES_SMALL_BYTES ? CLASS_RES_SMALL : CLASS_RES_LARGE;
   }
+  if (sliced_residency(h, sm_count)) return slice_bytes(h.k) <= RES_SMALL_BYTES ? CLASS_RES_SMALL : CLASS_RES_LARGE;
   static const double g2_min_waves = [] {
     const char* e = dev_switch("SPFY_SPMMA_G2_MIN_WAVES");
     return e ? atof(e) : 0.5;
@@ -696,7 +729,7 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   d->m_tiles = (uint32_t)ceil_div(h.m, BM);
   d->k_tiles = (uint32_t)ceil_div(h.k, 128);
   d->n_tiles = (uint32_t)ceil_div(h.n, BN);
-  d->resident = is_resident_class(cls);
+  d->resident = !is_resident_class(cls) ? 0u : (resident_bytes(h.m, h.k) <= RES_MAX_BYTES ? 1u : 2u);
   d->G = (cls == CLASS_STREAM_G1) ? 1u : (d->m_tiles >= 2 ? 2u : 1u);
   d->m_groups = (uint32_t)ceil_div(d->m_tiles, d->G);
   d->units = d->m_groups * d->n_tiles;
@@ -788,8 +821,9 @@ int launch(int dtype, int opB, const ProblemDev& single, const LaunchParams& L, 
 }
 
 uint32_t res_rows(const ProblemDev& d) { return d.m_tiles == 1 ? (uint32_t)round_up(d.m, 16) : 128u; }
-uint32_t res_values_bytes(const ProblemDev& d) { return d.m_tiles * d.k_tiles * res_rows(d) * 128u; }
-uint32_t res_meta_bytes(const ProblemDev& d) { return d.m_tiles * d.k_tiles * res_rows(d) * 16u; }
+uint32_t res_tiles(const ProblemDev& d) { return (d.resident == 2u ? d.G : d.m_tiles) * d.k_tiles; }
+uint32_t res_values_bytes(const ProblemDev& d) { return res_tiles(d) * res_rows(d) * 128u; }
+uint32_t res_meta_bytes(const ProblemDev& d) { return res_tiles(d) * res_rows(d) * 16u; }
 
 struct Plan {
   int dtype = 0;

@@ -354,11 +354,13 @@ def test_spmma_matches_fp64_oracle(spfy, orc, cuda, M, K, N, dt):
 
 # one shape per launch class of the v2 kernel (single-problem entry point):
 #   resident A (whole compressed A in shared memory, N >= 148 tiles; three ring geometries), streaming G=2 (two m-tiles share a
-#   B slice), streaming G=1; ragged M / K / N edges in each
+#   B slice), streaming G=1, m-group slices of A resident (A too large as a whole, >= 2 waves of units); ragged M / K / N
+#   edges in each
 CLASS_SHAPES = [(64, 147, 19008), (200, 72, 19080), (512, 128, 18944), (100, 576, 19000),  # resident
                 (64, 64, 19008), (256, 64, 19200), (200, 40, 19080), (130, 24, 18960),        # resident, k <= 64 (half stages)
                 (128, 512, 19008),                                                             # resident, large operand
                 (512, 200, 9600), (300, 264, 9480), (1024, 256, 4800),                       # stream, G=2
+                (1024, 256, 9600), (400, 256, 19000), (384, 250, 19000),                     # resident m-group slices (G=2; short / odd last group)
                 (128, 1152, 2048), (96, 2304, 1000)]                                         # stream, G=1
 
 
@@ -377,7 +379,8 @@ def test_spmma_plan_matches_single_calls_and_oracle(spfy, orc, cuda):
     """grouped persistent launch over a mixed list (all three classes, both opB, alpha/beta, bf16 is a
     separate plan): every output must equal the single-call result bit for bit and the oracle within tol."""
     shapes = [(64, 147, 19008), (512, 128, 18944), (256, 64, 20000), (512, 200, 1600), (1024, 256, 1200),
-              (128, 1152, 520), (256, 2304, 392), (2048, 512, 264), (64, 576, 19000), (130, 260, 264)]
+              (128, 1152, 520), (256, 2304, 392), (2048, 512, 264), (64, 576, 19000), (130, 260, 264),
+              (1024, 256, 9600), (384, 250, 19000)]
     problems, singles, wants = [], [], []
     for i, (M, K, N) in enumerate(shapes):
         a_bits = rand_bits(orc, 0, (M, K), seed=500 + i)
