@@ -202,6 +202,15 @@ typedef struct spfy_spmma_problem {
 typedef struct spfy_spmma_plan_st* spfy_spmma_plan_t;
 SPFY_API int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t count,
                                     spfy_spmma_plan_t* plan);
+/* Replicated outputs -- the fused form of the output gather (north_star: the path's only exchange).  Every D tile of
+ * problem i is stored, by the same TMA store that writes problems[i].D, to `replicas` further matrices
+ * replica_D[i * replicas + r] of the same shape and ldd.  With one process per GPU these are this rank's slab of the
+ * gather arena in every PEER GPU's memory (spfy_peer_open mappings, reached over NVLink): the GEMM epilogue is then
+ * the all-gather, tile by tile, and no collective follows -- only a barrier among the ranks before anyone reads
+ * (completion of the launch on rank r makes rank r's stores visible; it says nothing about the other ranks').
+ * replicas <= 15; replica pointers 16-byte aligned; beta != 0 still reads problems[i].C only. */
+SPFY_API int spfy_spmma_plan_create_replicated(int dtype, const spfy_spmma_problem* problems, size_t count,
+                                               size_t replicas, void* const* replica_D, spfy_spmma_plan_t* plan);
 SPFY_API int spfy_spmma_plan_run(spfy_spmma_plan_t plan, spfy_stream_t stream);
 SPFY_API int spfy_spmma_plan_launches(spfy_spmma_plan_t plan); /* kernel launches per run */
 /* introspection / profiling: run one of the plan's launches, or describe it */
@@ -386,6 +395,16 @@ SPFY_API int spfy_gemm_batched(int dtype, int precision, int opA, int opB, size_
  *               entries as ONE NCCL group (the lists are HOST arrays).
  * All work is enqueued on the caller's stream.
  * ---------------------------------------------------------------------- */
+/* Peer memory for the fused gather (spfy_spmma_plan_create_replicated): device memory another process on the same box
+ * can map.  spfy_peer_alloc = cudaMalloc + cudaIpcGetMemHandle (the 64 handle bytes travel through the host program,
+ * like the NCCL id); spfy_peer_open = cudaIpcOpenMemHandle with lazy peer access, in a DIFFERENT process than the
+ * owner; the mapping is an ordinary device pointer for every entry point of this library. */
+#define SPFY_PEER_HANDLE_BYTES 64
+SPFY_API int spfy_peer_alloc(size_t bytes, void** ptr, void* handle64);
+SPFY_API int spfy_peer_free(void* ptr);
+SPFY_API int spfy_peer_open(const void* handle64, void** ptr);
+SPFY_API int spfy_peer_close(void* ptr);
+
 typedef struct spfy_mg_comm_st* spfy_mg_comm_t;
 SPFY_API int spfy_mg_unique_id(void* id128);
 SPFY_API int spfy_mg_create(int rank, int world, const void* id128, spfy_mg_comm_t* comm);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "spfy_spmma_conv": (c_int, [c_int, _P, _SZ, c_float, _P, _P, _P, c_float, _P, _SZ, _P, _SZ, _P]),
     "spfy_permute_conv_weights": (c_int, [_P, _P, _SZ, _SZ, _SZ, _SZ, _P]),
     "spfy_spmma_plan_create": (c_int, [c_int, _P, _SZ, POINTER(c_void_p)]),
+    "spfy_spmma_plan_create_replicated": (c_int, [c_int, _P, _SZ, _SZ, _P, POINTER(c_void_p)]),
     "spfy_spmma_plan_run": (c_int, [_P, _P]),
     "spfy_spmma_plan_launches": (c_int, [_P]),
     "spfy_spmma_plan_run_launch": (c_int, [_P, c_int, _P]),
@@ -76,6 +77,10 @@ SIGNATURES = {
     "spfy_spmm_bell_workspace_bytes": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, _SZ, POINTER(_SZ)]),
     "spfy_spmm_bell_batched": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _SZ, _P, _SZ,
                                        c_float, c_float, _P, _SZ, _P]),
+    "spfy_peer_alloc": (c_int, [_SZ, POINTER(c_void_p), _P]),
+    "spfy_peer_free": (c_int, [_P]),
+    "spfy_peer_open": (c_int, [_P, POINTER(c_void_p)]),
+    "spfy_peer_close": (c_int, [_P]),
     "spfy_mg_unique_id": (c_int, [_P]),
     "spfy_mg_create": (c_int, [c_int, c_int, _P, POINTER(c_void_p)]),
     "spfy_mg_destroy": (c_int, [_P]),

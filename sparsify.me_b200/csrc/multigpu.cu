@@ -151,6 +151,49 @@ int spfy_mg_broadcast_many(spfy_mg_comm_t h, void* const* buffers, const size_t*
   return e ? nccl_fail("ncclGroupEnd", e) : SPFY_OK;
 }
 
+// ---- peer memory (fused gather: the spmma epilogue stores into every peer's arena, spfy_spmma_plan_create_replicated)
+int spfy_peer_alloc(size_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64) return fail(SPFY_E_INVALID, "peer_alloc: null pointer");
+  *ptr = nullptr;
+  if (!bytes) return fail(SPFY_E_INVALID, "peer_alloc: zero bytes");
+  static_assert(sizeof(cudaIpcMemHandle_t) == SPFY_PEER_HANDLE_BYTES, "handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(SPFY_E_CUDA, "peer_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(SPFY_E_CUDA, "peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, sizeof(h));
+  *ptr = p;
+  return SPFY_OK;
+}
+
+int spfy_peer_free(void* ptr) {
+  if (!ptr) return SPFY_OK;
+  const cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? SPFY_OK : fail(SPFY_E_CUDA, "peer_free: %s", cudaGetErrorString(e));
+}
+
+int spfy_peer_open(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(SPFY_E_INVALID, "peer_open: null pointer");
+  *ptr = nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? SPFY_OK
+                          : fail(SPFY_E_CUDA, "peer_open: cudaIpcOpenMemHandle: %s (the owner must be another process "
+                                              "on the same box, its GPU reachable by peer access)", cudaGetErrorString(e));
+}
+
+int spfy_peer_close(void* ptr) {
+  if (!ptr) return SPFY_OK;
+  const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? SPFY_OK : fail(SPFY_E_CUDA, "peer_close: %s", cudaGetErrorString(e));
+}
+
 int spfy_mg_rank(spfy_mg_comm_t h) { return h ? reinterpret_cast<MgComm*>(h)->rank : -1; }
 int spfy_mg_world(spfy_mg_comm_t h) { return h ? reinterpret_cast<MgComm*>(h)->world : 0; }
 

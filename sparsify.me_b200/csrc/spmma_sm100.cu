@@ -86,6 +86,11 @@ struct alignas(64) ProblemDev {
   uint32_t unit_begin, units;  // this problem's range in the launch-wide unit order
   float alpha, beta;
   uint64_t hint_b;
+  // replicated outputs (fused output gather, spfy_spmma_plan_create_replicated): every D tile is also stored through
+  // these maps -- the same matrix at other base addresses, e.g. this rank's slab of the gather arena in every peer
+  // GPU's memory (peer mappings over NVLink)
+  const CUtensorMap* tmap_rep;
+  uint32_t n_rep;
   // implicit GEMM (spfy_spmma_conv): B is never materialised -- tmap_b is an im2col map over the NHWC activations and a
   // B stage (128 positions x 128 k) is gathered as two (128 positions x 64 channels) pieces, one filter tap each
   uint32_t conv;               // 0: B is a matrix
@@ -434,6 +439,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     uint32_t job = 0;
     const ProblemDev* last = nullptr;
     const CUtensorMap* tmap_d = nullptr;
+    const CUtensorMap* tmap_rep = nullptr;
+    uint32_t n_rep = 0;
     const uint16_t* Cptr = nullptr;
     uint64_t ldc = 0;
     uint32_t pm = 0, pn = 0, m_tiles = 0, m_groups = 1, G = 1, unit_begin = 0;
@@ -443,6 +450,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       if (P != last) {
         last = P;
         tmap_d = &P->tmap_d;
+        tmap_rep = P->tmap_rep;
+        n_rep = P->n_rep;
         Cptr = reinterpret_cast<const uint16_t*>(P->C);
         ldc = P->ldc;
         pm = P->m; pn = P->n; m_tiles = P->m_tiles; m_groups = P->m_groups; G = P->G; unit_begin = P->unit_begin;
@@ -514,6 +523,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             __syncwarp();
             if (lane == 0 && !no_store) {
               tma_store_2d(tmap_d, sc, (int)n0, (int)(m0 + quarter * 32));
+              for (uint32_t r = 0; r < n_rep; ++r) tma_store_2d(tmap_rep + r, sc, (int)n0, (int)(m0 + quarter * 32));
               bulk_commit();
             }
           }
@@ -828,6 +838,7 @@ uint32_t res_meta_bytes(const ProblemDev& d) { return res_tiles(d) * res_rows(d)
 struct Plan {
   int dtype = 0;
   ProblemDev* d_table = nullptr;  // all launches back to back
+  CUtensorMap* d_rep = nullptr;   // replica maps of all problems ([problem in table order][n_rep])
   struct Launch {
     int opB;
     uint32_t first, count;  // range in d_table
@@ -935,8 +946,32 @@ int spfy_spmma_conv(int dtype, const spfy_conv_desc* conv, size_t m, float alpha
   return launch(dtype, SPFY_OP_T, d, L, smem, grid, (cudaStream_t)stream);
 }
 
+static void plan_free(Plan* plan) {
+  if (plan->d_table) cudaFree(plan->d_table);
+  if (plan->d_rep) cudaFree(plan->d_rep);
+  delete plan;
+}
+static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_t count, size_t n_rep, void* const* rep_d,
+                            spfy_spmma_plan_t* out);
+
 int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t count,
                            spfy_spmma_plan_t* out) {
+  return plan_create_impl(dtype, problems, count, 0, nullptr, out);
+}
+
+int spfy_spmma_plan_create_replicated(int dtype, const spfy_spmma_problem* problems, size_t count, size_t replicas,
+                                      void* const* replica_d, spfy_spmma_plan_t* out) {
+  if (replicas > 15) return fail(SPFY_E_UNSUPPORTED, "spmma_plan_create_replicated: %zu replicas (at most 15)", replicas);
+  if (replicas && count && !replica_d) return fail(SPFY_E_INVALID, "spmma_plan_create_replicated: null replica list");
+  for (size_t i = 0; i < count * replicas; ++i)
+    if (problems && problems[i / replicas].m && problems[i / replicas].n && (!replica_d[i] || (uintptr_t)replica_d[i] % 16))
+      return fail(SPFY_E_INVALID, "spmma_plan_create_replicated: replica %zu of problem %zu is null or not 16-byte aligned",
+                  i % replicas, i / replicas);
+  return plan_create_impl(dtype, problems, count, replicas, replica_d, out);
+}
+
+static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_t count, size_t n_rep, void* const* rep_d,
+                            spfy_spmma_plan_t* out) {
   if (!out) return fail(SPFY_E_INVALID, "spmma_plan_create: null plan pointer");
   *out = nullptr;
   if (count && !problems) return fail(SPFY_E_INVALID, "spmma_plan_create: null problem list");
@@ -949,6 +984,14 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
   Plan* plan = new Plan();
   plan->dtype = dtype;
   std::vector<ProblemDev> table;
+  std::vector<CUtensorMap> reps;  // replica maps in table order
+  if (n_rep && count) {
+    const cudaError_t e = cudaMalloc((void**)&plan->d_rep, count * n_rep * sizeof(CUtensorMap));
+    if (e != cudaSuccess) {
+      plan_free(plan);
+      return fail(SPFY_E_CUDA, "spmma_plan_create: %s", cudaGetErrorString(e));
+    }
+  }
   // launches overlap tail-to-head (programmatic stream serialization), so only the last launch's tail is
   // exposed: go from the class with the longest units (streaming, G = 2) to the one with the shortest (k <= 64)
   for (int cls = NUM_CLASSES - 1; cls >= 0; --cls) {
@@ -968,7 +1011,7 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
         if (h.opB != opB) continue;
         rc = validate(dtype, h, "spmma_plan_create");
         if (rc) {
-          delete plan;
+          plan_free(plan);
           return rc;
         }
         if (h.m == 0 || h.n == 0) continue;
@@ -984,15 +1027,28 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
         ProblemDev d;
         rc = fill_problem(&d, dtype, h, cls);
         if (rc) {
-          delete plan;
+          plan_free(plan);
           return rc;
         }
         d.unit_begin = units;
         if ((uint64_t)units + d.units >= (1ull << 32)) {
-          delete plan;
+          plan_free(plan);
           return fail(SPFY_E_UNSUPPORTED, "spmma_plan_create: too many tiles");
         }
         units += d.units;
+        if (n_rep) {
+          d.tmap_rep = plan->d_rep + reps.size();
+          d.n_rep = (uint32_t)n_rep;
+          for (size_t r = 0; r < n_rep && !rc; ++r) {
+            CUtensorMap tm;
+            rc = make_tmap_2d(&tm, dtype, rep_d[i * n_rep + r], h.n, h.m, h.ldd, 64, 32);
+            reps.push_back(tm);
+          }
+          if (rc) {
+            plan_free(plan);
+            return rc;
+          }
+        }
         if (d.resident && res_values_bytes(d) > res_vals) res_vals = res_values_bytes(d);
         if (d.resident && res_meta_bytes(d) > res_meta) res_meta = res_meta_bytes(d);
         table.push_back(d);
@@ -1015,9 +1071,10 @@ int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t
     cudaError_t e = cudaMalloc((void**)&plan->d_table, table.size() * sizeof(ProblemDev));
     if (e == cudaSuccess)
       e = cudaMemcpy(plan->d_table, table.data(), table.size() * sizeof(ProblemDev), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !reps.empty())
+      e = cudaMemcpy(plan->d_rep, reps.data(), reps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
-      if (plan->d_table) cudaFree(plan->d_table);
-      delete plan;
+      plan_free(plan);
       return fail(SPFY_E_CUDA, "spmma_plan_create: %s", cudaGetErrorString(e));
     }
     for (auto& ln : plan->launches) ln.L.table = plan->d_table + ln.first;
@@ -1070,9 +1127,7 @@ int spfy_spmma_plan_launch_info(spfy_spmma_plan_t p, int index, int* problems, i
 
 int spfy_spmma_plan_destroy(spfy_spmma_plan_t p) {
   if (!p) return SPFY_OK;
-  Plan* plan = (Plan*)p;
-  if (plan->d_table) cudaFree(plan->d_table);
-  delete plan;
+  plan_free((Plan*)p);
   return SPFY_OK;
 }
 

@@ -92,6 +92,74 @@ class OutputGather:
             self._h = None
 
 
+class _DeviceBuffer:
+    """raw device memory as seen by torch.as_tensor (CUDA array interface v2)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerArena:
+    """A gather arena every rank of the box can store into: the fused form of the output gather.
+
+    Every rank allocates `world * slab_bytes` of peer-mappable device memory (spfy_peer_alloc), the 64-byte handles
+    travel through torch.distributed, and every rank maps every other rank's arena (spfy_peer_open).  Rank r's GEMMs
+    write D_r into slab r of its own arena and, through `SpmmaPlan(..., replicas=...)`, into slab r of every peer's
+    arena in the same TMA stores: when all ranks' launches have completed (`barrier()`), every arena holds
+    [g][...] exactly as `OutputGather.allgather` would have left it -- without a collective.
+    `local` is this rank's arena as a uint8 tensor [world, slab_bytes]."""
+
+    def __init__(self, slab_bytes, group=None):
+        from . import capi
+        self._capi = capi
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.group = group
+        self.slab_bytes = int(slab_bytes)
+        assert self.slab_bytes % 128 == 0, "slab size must be a multiple of 128 bytes"
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        capi.spfy_peer_alloc(self.world * self.slab_bytes, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))
+        self.base = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peer_base = [None] * self.world  # base address of rank p's arena as mapped HERE
+        for p_, h in enumerate(handles):
+            if p_ == self.rank:
+                self.peer_base[p_] = self.base
+                continue
+            q = ctypes.c_void_p()
+            capi.spfy_peer_open(ctypes.c_char_p(h), ctypes.byref(q))
+            self.peer_base[p_] = q.value
+        self.local = torch.as_tensor(_DeviceBuffer(self.base, self.world * self.slab_bytes), device=self.dev).view(
+            self.world, self.slab_bytes)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+    def replica_addresses(self, byte_offset):
+        """where a matrix at `byte_offset` of MY slab lives in every PEER's arena (addresses valid in this process)"""
+        off = self.rank * self.slab_bytes + int(byte_offset)
+        return [self.peer_base[p_] + off for p_ in range(self.world) if p_ != self.rank]
+
+    def barrier(self):
+        """stream-ordered rendezvous: returns (on the stream) once every rank's earlier work on its current stream has
+        completed, i.e. once every slab of every arena is written"""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        if self.base is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody unmaps or frees while a peer may still be storing
+        for p_, q in enumerate(self.peer_base):
+            if p_ != self.rank and q:
+                self._capi.spfy_peer_close(ctypes.c_void_p(q))
+        dist.barrier(group=self.group)
+        self.local = None
+        self._capi.spfy_peer_free(ctypes.c_void_p(self.base))
+        self.base = None
+
+
 def partition_layers_lpt(costs, world):
     """Longest-processing-time-first assignment.  Returns a list (per rank) of layer indices,
     each in ascending order.  Deterministic: ties go to the lower rank / lower layer index."""

@@ -173,7 +173,10 @@ class SpmmaPlan:
     """spfy_spmma_plan_*: a list of independent D_i = alpha_i * A_i(2:4) * op(B_i) + beta_i * C_i executed
     by one persistent launch per ring-geometry class present (tensor maps + tile schedule built once, like
     cusparseLtMatmulPlanInit at spmma.hxx:79).  `problems`: dicts with comp, b, out and optional c, alpha,
-    beta, op_b.  The plan keeps the tensors alive."""
+    beta, op_b.  The plan keeps the tensors alive.
+    Optional `replicas` per problem: device addresses (ints) of further copies of `out` (same shape and row pitch) that
+    the epilogue stores every tile to as well -- e.g. the slab of this rank in the gather arena of every peer GPU
+    (spfy_spmma_plan_create_replicated: the fused output gather); every problem must name the same number of them."""
 
     def __init__(self, problems):
         self._keep = problems
@@ -191,7 +194,16 @@ class SpmmaPlan:
                                        c.stride(0) if c is not None else 0, out.data_ptr(), out.stride(0),
                                        float(q.get("alpha", 1.0)), float(q.get("beta", 0.0)))
         self._h = ctypes.c_void_p()
-        capi.spfy_spmma_plan_create(_DT[dtype], ctypes.cast(arr, ctypes.c_void_p), n, ctypes.byref(self._h))
+        nrep = len(problems[0].get("replicas", ())) if n else 0
+        if any(len(q.get("replicas", ())) != nrep for q in problems):
+            raise ValueError("SpmmaPlan: every problem needs the same number of replicas")
+        if nrep:
+            rep = (ctypes.c_void_p * (n * nrep))(*[int(a) for q in problems for a in q["replicas"]])
+            capi.spfy_spmma_plan_create_replicated(_DT[dtype], ctypes.cast(arr, ctypes.c_void_p), n, nrep,
+                                                   ctypes.cast(rep, ctypes.c_void_p), ctypes.byref(self._h))
+        else:
+            capi.spfy_spmma_plan_create(_DT[dtype], ctypes.cast(arr, ctypes.c_void_p), n, ctypes.byref(self._h))
+        self.replicas = nrep
         self.launches = capi.spfy_spmma_plan_launches(self._h)
 
     def run(self):

@@ -1,7 +1,9 @@
 """Worker of tests/test_gpu_multi.py (launched by torchrun, one process per GPU): the output gather on real NCCL.
 
 N sharding: every rank prunes the same weights, multiplies them into ITS images' columns, writing D_r straight into
-slab r of the gather arena; one in-place spfy_mg_allgather fills in the others.  Every rank can regenerate every other
+slab r of the gather arena; one in-place spfy_mg_allgather fills in the others;
+then the same through the FUSED gather (PeerArena + replicated plan: the epilogue stores into every peer's memory) -- the
+two arenas must be bit-identical.  Every rank can regenerate every other
 rank's inputs (seeded by rank), so it checks all slabs against a torch fp32 matmul of the pruned weights.
 Layer sharding: spfy_mg_broadcast_many from each layer's owner."""
 import os
@@ -59,6 +61,26 @@ def main():
             scale = torch.clamp(want.abs(), min=1e-2 * float(want.abs().max()))
             err = float(((got - want).abs() / scale).max())
             assert err <= 1e-2, (rank, r, M, K, N, err)
+    # ---- the fused gather: the GEMM epilogue stores every tile into every peer's arena (no collective) ----
+    slab = -(-elems * 2 // 128) * 128
+    pa = spfy.multigpu.PeerArena(slab)
+    pa.local.zero_()
+    torch.cuda.synchronize()
+    dist.barrier()  # nobody stores into an arena its owner is still clearing
+    mine = pa.local[rank].view(torch.float16)
+    probs2 = []
+    for q, (off, M, K, N) in zip(probs, views):
+        probs2.append(dict(comp=q["comp"], b=q["b"], out=mine[off: off + M * N].view(M, N),
+                           replicas=pa.replica_addresses(off * 2)))
+    plan2 = spfy.SpmmaPlan(probs2)
+    assert plan2.replicas == world - 1
+    plan2.run()
+    pa.barrier()
+    torch.cuda.synchronize()
+    fused = pa.local.view(torch.float16)[:, :elems]
+    assert torch.equal(fused, arena), (rank, "fused gather differs from GEMM + ncclAllGather")
+    plan2.close()
+    pa.close()
     # ---- layer sharding: every layer's output travels from its owner ----
     costs = [M * K + K * N + M * N for M, K, N in shapes]
     owned = spfy.multigpu.partition_layers_lpt(costs, world)

@@ -380,7 +380,7 @@ def test_spmma_plan_matches_single_calls_and_oracle(spfy, orc, cuda):
     separate plan): every output must equal the single-call result bit for bit and the oracle within tol."""
     shapes = [(64, 147, 19008), (512, 128, 18944), (256, 64, 20000), (512, 200, 1600), (1024, 256, 1200),
               (128, 1152, 520), (256, 2304, 392), (2048, 512, 264), (64, 576, 19000), (130, 260, 264),
-              (1024, 256, 9600), (384, 250, 19000)]
+              (1024, 256, 9600), (384, 256, 19000)]
     problems, singles, wants = [], [], []
     for i, (M, K, N) in enumerate(shapes):
         a_bits = rand_bits(orc, 0, (M, K), seed=500 + i)
@@ -408,6 +408,37 @@ def test_spmma_plan_matches_single_calls_and_oracle(spfy, orc, cuda):
         assert torch.equal(q["out"], single)
         assert rel_err(q["out"].float().cpu().numpy().astype(np.float64), want) <= REL_TOL
     plan.close()
+
+
+def test_spmma_plan_replicated_outputs(spfy, orc, cuda):
+    """spfy_spmma_plan_create_replicated on one GPU: every replica (here: other buffers of the same device; across GPUs:
+    peer mappings, tests/mg_worker.py) ends up bit-identical to the primary output, for every launch class, both
+    epilogue paths and a pitched destination."""
+    shapes = [(64, 147, 19008), (256, 64, 19200), (512, 200, 1600), (1024, 256, 9600), (128, 1152, 520), (130, 260, 264)]
+    problems, copies = [], []
+    for i, (M, K, N) in enumerate(shapes):
+        comp = spfy.prune24(to_dev(rand_bits(orc, 0, (M, K), seed=900 + i), 0, cuda))
+        b = to_dev(rand_bits(orc, 0, (K, N), seed=950 + i), 0, cuda)
+        beta = 0.5 if i % 2 else 0.0
+        c = to_dev(rand_bits(orc, 0, (M, N), seed=970 + i), 0, cuda) if beta else None
+        ld = N + 8 * (i % 3)  # all copies of a problem share the row pitch
+        bufs = [torch.zeros(M, ld, dtype=torch.float16, device=cuda) for _ in range(3)]
+        copies.append((N, bufs))
+        problems.append(dict(comp=comp, b=b, c=c, beta=beta, out=bufs[0][:, :N], replicas=[t.data_ptr() for t in bufs[1:]]))
+    plan = spfy.SpmmaPlan(problems)
+    assert plan.replicas == 2
+    plan.run()
+    torch.cuda.synchronize()
+    for q, (N, bufs) in zip(problems, copies):
+        single = spfy.spmma_compressed(q["comp"], q["b"], c=q["c"], beta=q["beta"])
+        assert torch.equal(bufs[0][:, :N], single)
+        for t in bufs[1:]:
+            assert torch.equal(t, bufs[0])  # the padding columns stay zero in every copy
+    plan.close()
+    with pytest.raises(ValueError):
+        spfy.SpmmaPlan([dict(problems[0], replicas=[copies[0][1][1].data_ptr()]), problems[1]])
+    with pytest.raises(spfy.SpfyError):
+        spfy.SpmmaPlan([dict(problems[0], replicas=[copies[0][1][1].data_ptr() + 2])])
 
 
 def test_spmma_plan_resnet18_table(spfy, cuda):
