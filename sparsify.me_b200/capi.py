@@ -20,6 +20,7 @@ LAYOUT_CANONICAL, LAYOUT_SM100 = 0, 1
 OP_N, OP_T = 0, 1
 SPMM_ALG_DEFAULT, SPMM_ALG_CUDA_CORE, SPMM_ALG_TENSOR, SPMM_ALG_TENSOR_FAST = 0, 1, 2, 3
 GEMM_PRECISE, GEMM_FAST = 0, 1
+GEMM_CTA_PAIRS = 0x10  # flag, OR-ed into `precision`: the cta_group::2 kernel where it applies
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE, E_NCCL = 0, -1, -2, -3, -4, -5
 
 

@@ -91,8 +91,13 @@ struct GemmWalker {
   const GemmProblemDev* single;
   const GemmProblemDev* table;
   uint32_t num_problems, total_units, u, p;
+  uint32_t stride;
   __device__ __forceinline__ GemmWalker(const GemmProblemDev* s, const GemmLaunch& L)
-      : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units), u(blockIdx.x), p(0) {}
+      : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units), u(blockIdx.x), p(0),
+        stride(gridDim.x) {}
+  // CTA pairs: both CTAs of a cluster walk the same units
+  __device__ __forceinline__ GemmWalker(const GemmProblemDev* s, const GemmLaunch& L, uint32_t first, uint32_t step)
+      : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units), u(first), p(0), stride(step) {}
   __device__ __forceinline__ const GemmProblemDev* prob(uint32_t i) const { return table ? table + i : single; }
   __device__ __forceinline__ bool valid() const { return u < total_units; }
   __device__ __forceinline__ const GemmProblemDev* current() {
@@ -100,7 +105,7 @@ struct GemmWalker {
     p = uni(p);
     return prob(p);
   }
-  __device__ __forceinline__ void next() { u += gridDim.x; }
+  __device__ __forceinline__ void next() { u += stride; }
 };
 
 template <int KIND>
@@ -123,7 +128,11 @@ template <> __device__ __forceinline__ float f32_to_out<KIND_F32>(float v) { ret
 template <int KIND>
 __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base, uint32_t bar_acc_full, uint32_t bar_acc_empty,
                                               uint32_t slots, uint32_t slot_cols, uint32_t tile_cols, uint32_t warp,
-                                              uint32_t lane) {
+                                              uint32_t lane, uint32_t pair_rank = 0xffffffffu) {
+  // pair_rank != ~0: CTA pair (tcgemm2_kernel) -- a unit is two m-tiles, mine is number pair_rank, and the slot is handed
+  // back on the LEADER's barrier (the one thread that issues the MMAs for both CTAs waits there)
+  const bool pair = pair_rank != 0xffffffffu;
+  const uint32_t acc_empty_remote = pair ? mapa_shared(bar_acc_empty, 0) : 0u;
   using out_t = typename OutT<KIND>::type;
   const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter + 32)
   uint32_t job = 0;
@@ -145,13 +154,13 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
     const uint32_t local = W.u - unit_begin;
     const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
     const uint32_t mg = t1 % m_groups, b = t1 / m_groups;
-    const uint32_t g_count = min(g, m_tiles - mg * g);
+    const uint32_t g_count = pair ? 1u : min(g, m_tiles - mg * g);
     out_t* C = c_ptrs ? reinterpret_cast<out_t*>(c_ptrs[b]) : reinterpret_cast<out_t*>(Cbase) + (size_t)b * stride_c;
     const uint32_t slot = job % slots;
     mbar_wait(bar_acc_full + slot * 8, (job / slots) & 1u);
     tc_fence_after();
     for (uint32_t tile = 0; tile < g_count; ++tile) {
-    const uint32_t mt = mg * g + tile;
+    const uint32_t mt = pair ? mg * 2u + pair_rank : mg * g + tile;
     const uint32_t row = mt * GM_BM + quarter * 32u + lane;  // index along Mu
     const bool row_ok = row < mu;
     const bool warp_ok = mt * GM_BM + quarter * 32u < mu;
@@ -171,7 +180,9 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
         // accumulator fully read by this warp: hand the slot back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
+        if (lane == 0) {
+          if (pair) mbar_arrive_cluster(acc_empty_remote + slot * 8); else mbar_arrive(bar_acc_empty + slot * 8);
+        }
       }
       if (!row_ok || !ncols) continue;
       if (mu_contig) {
@@ -422,6 +433,180 @@ tcgemm_kernel(const __grid_constant__ GemmProblemDev single, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): the same GEMM on tiles of 256 rows of Au.
+//
+// The single-CTA kernel above is bound by the bytes that ENTER an SM, not by the tensor pipe: a 128 x 256 tile takes
+// (128 + 256) x 128 bytes of operands per K slab for 512 tensor cycles (96 B/clk, the L2 -> SM path gives ~25).  Two CTAs
+// of a cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256: each CTA loads its own 128 rows of Au and only
+// HALF of the Bu tile (the tensor cores read the other half from the peer's shared memory), so the weight tile enters
+// each SM half as often -- (128 + 128) x 128 bytes per slab and CTA -- and the ring is 6 deep instead of 4.
+//   both CTAs : producer warp (its Au tile + its half of Bu; the bytes are counted on the LEADER's `full` barrier),
+//               epilogue warps (own accumulator rows from own tensor memory; slot handed back on the leader's barrier)
+//   leader    : MMA warp: waits the leader's `full`, issues the MMAs for the pair, commits with a multicast arrive on
+//               the `empty` / `acc_full` barriers of both CTAs
+// Units: (problem, batch, pair of m-tiles, n-tile), n-tile fastest; both CTAs of a cluster walk the same sequence.
+// 16-bit operands and single-product TF32 only (no splitter warps).
+// ------------------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+tcgemm2_kernel(const __grid_constant__ GemmProblemDev single, const __grid_constant__ GemmLaunch L) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  // (no early return for a gated launch before the cluster barriers: both CTAs take the same branch)
+  const bool gated_off = L.gate && (*L.gate != 0) != (L.gate_run_if != 0);
+  if (gated_off) return;
+
+  const uint32_t NS = L.stages;
+  const uint32_t bar_full = smem_base + L.bar_off;                   // [GM_MAX_STAGES] used in the leader only
+  const uint32_t bar_empty = bar_full + GM_MAX_STAGES * 8;           // [GM_MAX_STAGES] per CTA (multicast commit)
+  const uint32_t bar_acc_full = bar_empty + GM_MAX_STAGES * 8;       // [GM_ACC_SLOTS]  per CTA (multicast commit)
+  const uint32_t bar_acc_empty = bar_acc_full + GM_ACC_SLOTS * 8;    // [GM_ACC_SLOTS]  used in the leader only
+  const uint32_t tmem_ptr_off = L.bar_off + (2 * GM_MAX_STAGES + 2 * GM_ACC_SLOTS) * 8;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + tmem_ptr_off);
+
+  if (warp == 1 && lane == 0) {
+    for (uint32_t s = 0; s < (uint32_t)GM_MAX_STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    for (int a = 0; a < GM_ACC_SLOTS; ++a) {
+      mbar_init(bar_acc_full + a * 8, 1);
+      mbar_init(bar_acc_empty + a * 8, 2 * GM_EPI_WARPS);  // the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(smem_base + tmem_ptr_off, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything of mine can arrive on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  GemmWalker W(&single, L, blockIdx.x >> 1, gridDim.x >> 1);
+
+  if (warp == 0) {
+    // ===================== producer (both CTAs) =====================
+    const bool leader = elect_one();
+    uint32_t stage = 0, phase = 0;
+    const GemmProblemDev* last = nullptr;
+    const CUtensorMap *tmap_a = nullptr, *tmap_b = nullptr;
+    uint32_t n_tiles = 1, m_pairs = 1, k_tiles = 0, bn = 0, a_mn = 0, b_mn = 0, a_bat = 0, b_bat = 0, unit_begin = 0;
+    const uint32_t kel = L.kelems;
+    const uint32_t gsz = kel;
+    const uint32_t group_bytes = kel * GM_ROW_BYTES;
+    const uint32_t full0 = mapa_shared(bar_full, 0);  // the leader's `full` barriers as seen from here
+    for (; W.valid(); W.next()) {
+      const GemmProblemDev* P = W.current();
+      if (P != last) {
+        last = P;
+        tmap_a = &P->tmap_a; tmap_b = &P->tmap_b;
+        if (leader) { prefetch_tmap(tmap_a); prefetch_tmap(tmap_b); }
+        n_tiles = uni(P->n_tiles); m_pairs = uni(P->m_groups); k_tiles = uni(P->k_tiles); bn = uni(P->bn);
+        a_mn = uni(P->a_mn); b_mn = uni(P->b_mn); a_bat = uni(P->a_batched); b_bat = uni(P->b_batched);
+        unit_begin = uni(P->unit_begin);
+      }
+      const uint32_t local = W.u - unit_begin;
+      const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
+      const uint32_t mp = t1 % m_pairs, b = t1 / m_pairs;
+      const uint32_t mt = mp * 2u + rank;                 // my m-tile of the pair
+      const uint32_t half = bn >> 1, n0 = nt * bn + rank * half;  // my half of the Bu tile
+      const int ba = a_bat ? (int)b : 0, bb = b_bat ? (int)b : 0;
+      const uint32_t tx_pair = 2u * ((uint32_t)GM_A_BYTES + half * (uint32_t)GM_ROW_BYTES);
+      for (uint32_t kt = 0; kt < k_tiles; ++kt) {
+        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+        const uint32_t full = full0 + stage * 8;
+        const uint32_t sa = smem_base + stage * L.stage_bytes, sb = sa + GM_A_BYTES;
+        if (leader) {
+          if (rank == 0) mbar_expect_tx(bar_full + stage * 8, tx_pair);
+          if (!a_mn) {
+            tma_load_3d_2cta(sa, tmap_a, (int)(kt * kel), (int)(mt * GM_BM), ba, full, HINT_EVICT_NORMAL);
+          } else {
+            for (uint32_t g = 0; g * gsz < (uint32_t)GM_BM; ++g)
+              tma_load_3d_2cta(sa + g * group_bytes, tmap_a, (int)(mt * GM_BM + g * gsz), (int)(kt * kel), ba, full,
+                               HINT_EVICT_NORMAL);
+          }
+          if (!b_mn) {
+            tma_load_3d_2cta(sb, tmap_b, (int)(kt * kel), (int)n0, bb, full, HINT_EVICT_NORMAL);
+          } else {
+            for (uint32_t g = 0; g * gsz < half; ++g)
+              tma_load_3d_2cta(sb + g * group_bytes, tmap_b, (int)(n0 + g * gsz), (int)(kt * kel), bb, full,
+                               HINT_EVICT_NORMAL);
+          }
+        }
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      const bool leader = elect_one();
+      const uint32_t tmem_b = uni(tmem_base);
+      uint32_t stage = 0, phase = 0, job = 0;
+      const GemmProblemDev* last = nullptr;
+      uint32_t k_tiles = 0, pk = 0, bn = 0, a_mn = 0, b_mn = 0;
+      const uint32_t kel = L.kelems;
+      const uint32_t umma_k = kel / 4u;
+      const uint32_t group_bytes = kel * GM_ROW_BYTES;
+      const uint64_t desc_k = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      const uint64_t desc_mn = KIND == KIND_F32 ? make_smem_desc(0, group_bytes, 512, LAYOUT_SW128_BASE32B)
+                                                : make_smem_desc(0, group_bytes, 1024, LAYOUT_SW128);
+      const uint32_t step_mn = (umma_k * GM_ROW_BYTES) >> 4;
+      for (; W.valid(); W.next()) {
+        const GemmProblemDev* P = W.current();
+        if (P != last) {
+          last = P;
+          k_tiles = uni(P->k_tiles); pk = uni(P->k); bn = uni(P->bn); a_mn = uni(P->a_mn); b_mn = uni(P->b_mn);
+        }
+        const uint32_t slot = job % GM_ACC_SLOTS, use = job / GM_ACC_SLOTS;
+        mbar_wait(bar_acc_empty + slot * 8, (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_b + slot * (uint32_t)GM_MAX_BN;
+        // M = 256 for the pair; N = the whole Bu tile (its halves sit in the two CTAs)
+        const uint32_t idesc = L.idesc | (a_mn << 15) | (b_mn << 16) | ((bn >> 3) << 17);
+        const uint64_t da_hi = a_mn ? desc_mn : desc_k, db_hi = b_mn ? desc_mn : desc_k;
+        const uint32_t a_step = a_mn ? step_mn : 2u, b_step = b_mn ? step_mn : 2u;
+        uint32_t k_left = pk;
+        for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= kel) {
+          mbar_wait(bar_full + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L.stage_bytes;
+          const uint32_t a0 = (sa >> 4) & 0x3fffu, b0 = ((sa + GM_A_BYTES) >> 4) & 0x3fffu;
+          const uint32_t nk = k_left >= kel ? 4u : (k_left + umma_k - 1u) / umma_k;
+          if (leader) {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+              if (j < nk) {
+                const uint64_t da = da_hi | (uint64_t)(a0 + a_step * j), db = db_hi | (uint64_t)(b0 + b_step * j);
+                const uint32_t acc = (kt | j) ? 1u : 0u;
+                if (KIND == KIND_F32) tc_mma_tf32_2cta(tmem_d, da, db, idesc, acc);
+                else                  tc_mma_f16_2cta(tmem_d, da, db, idesc, acc);
+              }
+            }
+            tc_commit_2cta(bar_empty + stage * 8, 3u);  // the stage is free in both CTAs
+          }
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+        if (leader) tc_commit_2cta(bar_acc_full + slot * 8, 3u);
+        ++job;
+      }
+    }
+  } else if (warp >= 2 + GM_SPLIT_WARPS) {
+    gemm_epilogue<KIND>(W, tmem_base, bar_acc_full, bar_acc_empty, GM_ACC_SLOTS, GM_MAX_BN, GM_MAX_BN, warp, lane, rank);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody retires (or frees tensor memory) while the peer may still arrive on its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 
@@ -870,7 +1055,8 @@ void blas_views(const TcGemmProblem& p, OperandView* va, OperandView* vb) {
   *vb = OperandView{p.B, p.n, p.k, p.ldb, p.strideB, p.opB != SPFY_OP_N};
 }
 
-Orientation orient(int dtype, const TcGemmProblem& p, size_t max_bn) {
+// `pair`: CTA pairs split a Bu tile in halves, each a whole number of 16-column (or MN-group) units
+Orientation orient(int dtype, const TcGemmProblem& p, size_t max_bn, bool pair = false) {
   OperandView va, vb;
   blas_views(p, &va, &vb);
   const size_t group = GM_ROW_BYTES / elem_bytes(dtype);
@@ -879,7 +1065,7 @@ Orientation orient(int dtype, const TcGemmProblem& p, size_t max_bn) {
   o[0].a = va; o[0].b = vb; o[0].mu = p.m; o[0].nu = p.n; o[0].mu_contig = true;
   o[1].a = vb; o[1].b = va; o[1].mu = p.n; o[1].nu = p.m; o[1].mu_contig = false;
   for (int i = 0; i < 2; ++i) {
-    split_nu(o[i].nu, o[i].b.mn_major ? group : 16, max_bn, &o[i].bn, &o[i].n_tiles);
+    split_nu(o[i].nu, (o[i].b.mn_major ? group : 16) * (pair ? 2 : 1), max_bn, &o[i].bn, &o[i].n_tiles);
     o[i].padded = round_up(o[i].mu, GM_BM) * (size_t)o[i].bn * o[i].n_tiles;
   }
   if (o[0].padded != o[1].padded) return o[0].padded < o[1].padded ? o[0] : o[1];
@@ -909,9 +1095,9 @@ int check_problem(int dtype, const TcGemmProblem& p, bool allow_repack) {
 }
 
 // `ts`: the 3xTF32 kernel with Au in tensor memory (tiles of at most TS_MAX_BN columns, up to two m-tiles per unit)
-int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, int sm_count) {
+int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, int sm_count, bool pair = false) {
   memset(d, 0, sizeof(*d));
-  const Orientation o = orient(dtype, p, ts ? TS_MAX_BN : GM_MAX_BN);
+  const Orientation o = orient(dtype, p, ts ? TS_MAX_BN : GM_MAX_BN, pair);
   // K-major tiles and 16-bit MN-major tiles: 128-byte swizzle.  32-bit MN-major tiles: the tensor core reads them in
   // the 32B-base swizzle only; the 3xTF32 kernel reads its Au tile with ordinary loads and wants it unswizzled.
   const bool f32 = dtype == SPFY_F32;
@@ -920,7 +1106,7 @@ int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, 
   const CUtensorMapSwizzle sw_b = f32 && o.b.mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   int rc = make_operand_map(&d->tmap_a, dtype, o.a, p.nb, GM_BM, sw_a);
   if (rc) return rc;
-  rc = make_operand_map(&d->tmap_b, dtype, o.b, p.nb, o.bn, sw_b);
+  rc = make_operand_map(&d->tmap_b, dtype, o.b, p.nb, pair ? o.bn / 2 : o.bn, sw_b);  // a CTA of a pair loads half a tile
   if (rc) return rc;
   const size_t kel = GM_ROW_BYTES / elem_bytes(dtype);
   d->C = (uint8_t*)p.C;
@@ -948,6 +1134,7 @@ int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, 
   if (ts && d->m_tiles >= 2 &&
       2 * (uint64_t)ceil_div(d->m_tiles, TS_G) * d->n_tiles * d->nb >= (uint64_t)sm_count && !dev_switch("SPFY_GEMM_G1"))
     d->g = TS_G;
+  if (pair) d->g = 2;  // a unit is a pair of m-tiles, one per CTA of the cluster
   d->m_groups = (uint32_t)ceil_div(d->m_tiles, d->g);
   const uint64_t units = (uint64_t)d->m_groups * d->n_tiles * d->nb;
   if (units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
@@ -966,6 +1153,20 @@ int launch_kind(const GemmProblemDev& single, const GemmLaunch& L, uint32_t smem
   }
   tcgemm_kernel<KIND><<<grid, GM_THREADS, smem, s>>>(single, L);
   SPFY_LAUNCH_OK("tcgemm_kernel");
+  return SPFY_OK;
+}
+
+template <int KIND>
+int launch_pairs(const GemmProblemDev& single, const GemmLaunch& L, uint32_t smem, int grid, cudaStream_t s) {
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  SPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63].load()) {
+    SPFY_CUDA_OK(cudaFuncSetAttribute(tcgemm2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_LIMIT));
+    attr_set[dev & 63].store(1);
+  }
+  tcgemm2_kernel<KIND><<<grid, GM_THREADS, smem, s>>>(single, L);  // clusters of two (__cluster_dims__)
+  SPFY_LAUNCH_OK("tcgemm2_kernel");
   return SPFY_OK;
 }
 
@@ -989,6 +1190,9 @@ void warm_gemm_kernels() {
   touch_kernel(tcgemm_kernel<KIND_F16>);
   touch_kernel(tcgemm_kernel<KIND_BF16>);
   touch_kernel(tcgemm_kernel<KIND_F32>);
+  touch_kernel(tcgemm2_kernel<KIND_F16>);
+  touch_kernel(tcgemm2_kernel<KIND_BF16>);
+  touch_kernel(tcgemm2_kernel<KIND_F32>);
 }
 
 int tc_gemm_supported(int dtype, const TcGemmProblem& p, bool allow_repack) {
@@ -1066,6 +1270,8 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
   std::vector<GemmProblemDev> table;
   table.reserve(count);
   uint32_t units = 0, bn_max = 16;
+  const bool want_pairs = (precision & TC_GEMM_CTA_PAIRS) != 0;
+  precision &= ~TC_GEMM_CTA_PAIRS;
   const bool ts = dtype == SPFY_F32 && precision == TC_GEMM_PRECISE && !dev_switch("SPFY_GEMM_NO_TMEM_A");
   // workspace: [device copy of the problem table (count > 1)][padded copies of operands TMA cannot address]
   uint8_t* ws8 = (uint8_t*)ws;
@@ -1073,6 +1279,16 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
   if (ws8 && ws_bytes >= ws_pad) { ws8 += ws_pad; ws_bytes -= ws_pad; } else { ws8 = nullptr; ws_bytes = 0; }
   size_t ws_used = table_bytes(count);
   std::vector<Repacked> repacked;
+  // CTA pairs (tcgemm2_kernel) on request, when no operand needs splitting and every problem has at least two m-tiles.
+  // Not the default: measured on the ResNet shapes the pair kernel is 5-25 % SLOWER than the single-CTA one
+  // (profiles/r02_gemm_cta_pairs.txt) -- it halves the weight bytes entering each SM, but its loads run at 6.2 TB/s
+  // chip-wide against 11.2 TB/s (the L2 output limit) for single CTAs.
+  bool pair = want_pairs && !ts && !(dtype == SPFY_F32 && precision == TC_GEMM_PRECISE) && di.sm_count >= 2;
+  for (size_t i = 0; i < count && pair; ++i) {
+    if (check_problem(dtype, problems[i], true) != SPFY_OK || problems[i].m == 0 || problems[i].n == 0 || problems[i].nb == 0)
+      continue;
+    if (orient(dtype, problems[i], GM_MAX_BN, true).mu <= (size_t)GM_BM) pair = false;
+  }
   for (size_t i = 0; i < count; ++i) {
     rc = check_problem(dtype, problems[i], true);
     if (rc) return rc;
@@ -1089,7 +1305,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
       q.B = vb.base; q.ldb = vb.ld; q.strideB = vb.stride;
     }
     GemmProblemDev d;
-    rc = fill_problem(&d, dtype, q, ts, di.sm_count);
+    rc = fill_problem(&d, dtype, q, ts, di.sm_count, pair);
     if (rc) return rc;
     d.unit_begin = units;
     if ((uint64_t)units + d.units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
@@ -1132,7 +1348,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
     L.bar_off = L.b_off + L.stages * L.stage_bytes;
     smem = L.bar_off + GM_BAR_BYTES + 1024u;
   } else {
-    L.raw_bytes = (uint32_t)GM_A_BYTES + bn_max * (uint32_t)GM_ROW_BYTES;
+    L.raw_bytes = (uint32_t)GM_A_BYTES + (pair ? bn_max / 2 : bn_max) * (uint32_t)GM_ROW_BYTES;
     L.stage_bytes = L.raw_bytes * (L.split ? 2u : 1u);
     uint32_t stages = (GM_SMEM_LIMIT - 1024u - GM_BAR_BYTES) / L.stage_bytes;
     if (stages > (uint32_t)GM_MAX_STAGES) stages = GM_MAX_STAGES;
@@ -1147,7 +1363,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
   }
   // instruction descriptor: D = F32; A / B format (F16 0, BF16 1, TF32 2); M = 128; N and majors per problem
   const uint32_t fmt = f32 ? 2u : (dtype == SPFY_BF16 ? 1u : 0u);
-  L.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(GM_BM >> 4) << 24);
+  L.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((pair ? 2 * GM_BM : GM_BM) >> 4) << 24);
   L.num_problems = (uint32_t)table.size();
   L.total_units = units;
   L.table = nullptr;
@@ -1158,6 +1374,12 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
     // pageable source: the runtime stages the bytes before the call returns, so `table` may go out of scope
     SPFY_CUDA_OK(cudaMemcpyAsync(ws8, table.data(), need, cudaMemcpyHostToDevice, stream));
     L.table = reinterpret_cast<const GemmProblemDev*>(ws8);
+  }
+  if (pair) {
+    const int grid2 = 2 * (int)std::min<uint32_t>(units, (uint32_t)di.sm_count / 2);
+    if (f32) return launch_pairs<KIND_F32>(table[0], L, smem, grid2, stream);
+    if (dtype == SPFY_BF16) return launch_pairs<KIND_BF16>(table[0], L, smem, grid2, stream);
+    return launch_pairs<KIND_F16>(table[0], L, smem, grid2, stream);
   }
   const int grid = (int)std::min<uint32_t>(units, (uint32_t)di.sm_count);
   if (ts) return launch_ts(table[0], L, smem, grid, stream);

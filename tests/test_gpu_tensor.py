@@ -83,6 +83,23 @@ def test_gemm_half_matches_fp64(spfy, cuda, tdt, m, n, k, nb, ta, tb):
     assert float(np.max(np.abs(got - want) / scale)) <= REL_TOL
 
 
+@pytest.mark.parametrize("tdt", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("m,n,k,nb", [(200, 72, 104, 3), (520, 264, 1000, 2), (64, 392, 256, 2), (784, 256, 2304, 2),
+                                      (1000, 520, 72, 1), (300, 16, 40, 2)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_gemm_cta_pairs_give_the_same_results(spfy, cuda, tdt, m, n, k, nb, ta, tb):
+    """GEMM_CTA_PAIRS: tcgen05.mma.cta_group::2 (M = 256 across a two-CTA cluster, each CTA holding its own 128 rows of
+    the long operand and half of the other tile; odd tile counts, ragged edges, every major-ness) -- bitwise the
+    results of the single-CTA kernel (same products, same accumulation order), and within the fp64 bound"""
+    prec = spfy.GEMM_FAST if tdt == torch.float32 else spfy.GEMM_PRECISE
+    one, want, bound = gemm_case(spfy, cuda, tdt, m, n, k, nb, ta, tb, 0.5, 0.25, False, nb > 1, prec, True, seed=m + 7 * n + k)
+    two, _, _ = gemm_case(spfy, cuda, tdt, m, n, k, nb, ta, tb, 0.5, 0.25, False, nb > 1, prec | spfy.GEMM_CTA_PAIRS, True,
+                          seed=m + 7 * n + k)
+    assert np.array_equal(one, two)
+    tol = TF32_TOL if tdt == torch.float32 else 2.0 ** -7
+    assert np.all(np.abs(two - want) <= tol * bound + 1e-30)
+
+
 @pytest.mark.parametrize("strided", [True, False])
 @pytest.mark.parametrize("shared_a,shared_b", [(False, True), (True, False), (False, False)])
 def test_gemm_alpha_beta_sharing_and_pointer_arrays(spfy, cuda, strided, shared_a, shared_b):

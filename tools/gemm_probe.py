@@ -5,6 +5,7 @@ worst error relative to sum|a||b| against fp64, and optional timing against torc
 A configuration that faults takes the CUDA context with it: each line is printed (flushed) BEFORE its launch."""
 import argparse
 import os
+import statistics
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -57,12 +58,9 @@ def main():
             for _ in range(2):
                 spfy.batched.gemm(A, B, C, m, n, k, transpose_a=ta, precision=prec)
             torch.cuda.synchronize()
-            e0.record()
-            for _ in range(5):
-                spfy.batched.gemm(A, B, C, m, n, k, transpose_a=ta, precision=prec)
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) / 5 * 1e3
+            # the wrapper brackets the call with an event pair and synchronises (like the reference's timer_t), so a
+            # loop under ONE outer event pair would time the host round trips, not the kernel: take its own figure
+            us = statistics.median(spfy.batched.gemm(A, B, C, m, n, k, transpose_a=ta, precision=prec) for _ in range(9)) * 1e3
             fl = 2.0 * m * n * k * nb
             by = (m * k * nb + n * k + m * n * nb) * A.element_size()
             print(f"time {args.dtype} ta={ta} prec={prec} m={m} n={n} k={k} nb={nb}: {us:.1f} us  {fl/us/1e6:.1f} TFLOP/s  "
@@ -72,12 +70,14 @@ def main():
             for _ in range(2):
                 torch.matmul(A, Bt)
             torch.cuda.synchronize()
-            e0.record()
-            for _ in range(5):
+            ts = []
+            for _ in range(9):  # same method: one event pair per call
+                e0.record()
                 torch.matmul(A, Bt)
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) / 5 * 1e3
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            us = statistics.median(ts)
             print(f"     torch.matmul (cuBLAS, {'fp32 no-TF32' if tdt == torch.float32 else args.dtype}): {us:.1f} us", flush=True)
 
 

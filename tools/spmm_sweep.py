@@ -6,7 +6,7 @@ A = W [C_out x K] shared by the batch, B_b = [K x H*W] column-major per image, C
 column-major, fp32 -- the operand types of spmm.hxx:165-180) and every sparsity s in --sparsity, time
   * spfy_threshold_to_coo    (threshold = the ceil(s*M*K)-th smallest |w|),
   * spfy_spmm_coo_strided_batched over nb = b images,
-with CUDA events over `--reps` back-to-back launches (operands of one launch exceed L2 for every
+one CUDA-event pair per call, median of `--reps` calls (operands of one launch exceed L2 for every
 ResNet shape at b=32).  Algorithmic bytes (SURVEY.md 8d): threshold 4*M*K*2 reads + 12*nnz;
 SpMM 12*nnz + 4*K*N*nb + 4*M*N*nb.  One CSV line per (shape, sparsity) on stdout.
 
@@ -14,6 +14,7 @@ SpMM 12*nnz + 4*K*N*nb + 4*M*N*nb.  One CSV line per (shape, sparsity) on stdout
 """
 import argparse
 import collections
+import statistics
 import json
 import os
 import subprocess
@@ -75,12 +76,10 @@ def main():
             else:
                 alg_here = alg
             torch.cuda.synchronize()
-            e0.record()
-            for _ in range(args.reps):
-                spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, cbuf, alg=alg_here)
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) / args.reps * 1e3
+            # the wrapper brackets the call with an event pair and synchronises (the reference's timer_t semantics): its
+            # own figure is the time of the call on the GPU; a loop under one outer pair would add a host round trip each
+            us = statistics.median(spfy.batched.strided_coo(M, K, nnz, K, n, nb, ri, ci, va, b, cbuf, alg=alg_here)
+                                   for _ in range(args.reps)) * 1e3
             thr_bytes = 2 * 4 * M * K + 12 * nnz
             by = 12 * nnz + 4 * K * n * nb + 4 * M * n * nb
             fl = 2.0 * nnz * n * nb
