@@ -1,0 +1,11 @@
+#!/bin/bash
+# write-heavy launch classes with pieces of the kernel switched off (dev build): where does the time go?
+T=${1:-dbgc}; O=gpurun_out; mkdir -p $O
+export SPFY_LIB=$PWD/sparsify.me_b200/lib_dev/libsparsifyme_b200.so
+for shapes in "64,64,401408;256,64,401408" "1024,256,25088" "512,128,100352;128,512,100352" "256,512,100352;2048,512,6272"; do
+  for d in 0 32 2 4 36; do
+    echo "== shapes=$shapes DEBUG=$d" >> $O/${T}.log
+    SPFY_SPMMA_DEBUG=$d timeout 300 python tools/layer_sweep.py --plan-only --plan --plan-shapes "$shapes" --tag d$d 2>&1 | grep "PLAN\|Error\|error" >> $O/${T}.log
+  done
+done
+cat $O/${T}.log
