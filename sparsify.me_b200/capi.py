@@ -142,8 +142,20 @@ def _bind(name, restype, argtypes):
     return checked
 
 
+def _missing(name):
+    def stub(*_args):
+        raise SpfyError(E_UNSUPPORTED, name, "not exported by the library selected with SPFY_LIB")
+    stub.__name__ = name
+    return stub
+
+
 for _name, (_res, _args) in SIGNATURES.items():
-    globals()[_name] = _bind(_name, _res, _args)
+    try:
+        globals()[_name] = _bind(_name, _res, _args)
+    except AttributeError:
+        if not os.environ.get("SPFY_LIB"):  # the shipped library must export everything the header declares
+            raise
+        globals()[_name] = _missing(_name)  # A/B runs against an older build
 
 
 def version():

@@ -33,6 +33,7 @@
 #include "tc_ptx.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace spfy {
@@ -1095,9 +1096,40 @@ int check_problem(int dtype, const TcGemmProblem& p, bool allow_repack) {
 }
 
 // `ts`: the 3xTF32 kernel with Au in tensor memory (tiles of at most TS_MAX_BN columns, up to two m-tiles per unit)
-int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, int sm_count, bool pair = false) {
+// Tile width and m-tiles per unit of a problem that has a 3xTF32 launch to itself, chosen for the WAVE count: units are
+// dealt to one CTA per SM, so 224 equal units on 148 SMs take as long as 296 (784 x 256 x 2304 at b = 32: seven tiles of
+// 112 columns -> nine of 96 fills two waves with 14 % shorter units).  Cost of a unit per 32-wide K slab = the larger of
+// its MMA time (3 MMAs per k-step and m-tile, ~0.66 cycles per column and k-step measured) and the time its operand bytes
+// take to enter the SM (~28 B/clk), plus a per-unit constant for the epilogue.
+void balance_tiles(const Orientation& o, size_t nb, size_t k_tiles, int sm_count, size_t gran, uint32_t* bn, uint32_t* n_tiles,
+                   uint32_t* g) {
+  const size_t m_tiles = ceil_div(o.mu, GM_BM);
+  double best = 0;
+  for (size_t b = gran; b <= (size_t)TS_MAX_BN; b += gran) {
+    const size_t nt = ceil_div(o.nu, b);
+    if (nt > 1 && (nt - 1) * b >= o.nu) continue;
+    for (uint32_t gg = 1; gg <= (uint32_t)TS_G; ++gg) {
+      if (gg > m_tiles) break;
+      const double units = (double)ceil_div(m_tiles, gg) * (double)nt * (double)nb;
+      const double rounds = std::ceil(units / (double)sm_count);
+      const double mma = 4.0 * 3.0 * 0.66 * (double)b * gg;
+      const double ingest = (double)(gg * GM_BM + b) * GM_ROW_BYTES / 28.0;
+      const double cost = rounds * ((double)k_tiles * std::max(mma, ingest) + 3000.0 + 8.0 * (double)b * gg);
+      if (best == 0 || cost < best * 0.999) { best = cost; *bn = (uint32_t)b; *n_tiles = (uint32_t)nt; *g = gg; }
+    }
+  }
+}
+
+// `launch_half_units`: units of the whole launch if every problem paired its m-tiles (the G = 2 rule looks at the launch,
+// not at one problem: a pointer-array batch is a table of one-batch problems)
+int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, int sm_count, bool pair = false,
+                 bool alone = false, uint64_t launch_half_units = 0) {
   memset(d, 0, sizeof(*d));
-  const Orientation o = orient(dtype, p, ts ? TS_MAX_BN : GM_MAX_BN, pair);
+  Orientation o = orient(dtype, p, ts ? TS_MAX_BN : GM_MAX_BN, pair);
+  uint32_t g_balanced = 0;
+  if (ts && alone && !dev_switch("SPFY_GEMM_NO_BALANCE"))
+    balance_tiles(o, p.nb, ceil_div(p.k, GM_ROW_BYTES / elem_bytes(dtype)), sm_count,
+                  o.b.mn_major ? GM_ROW_BYTES / elem_bytes(dtype) : 16, &o.bn, &o.n_tiles, &g_balanced);
   // K-major tiles and 16-bit MN-major tiles: 128-byte swizzle.  32-bit MN-major tiles: the tensor core reads them in
   // the 32B-base swizzle only; the 3xTF32 kernel reads its Au tile with ordinary loads and wants it unswizzled.
   const bool f32 = dtype == SPFY_F32;
@@ -1131,9 +1163,10 @@ int fill_problem(GemmProblemDev* d, int dtype, const TcGemmProblem& p, bool ts, 
   // two m-tiles share every Bu stage whenever that leaves at least half a wave of units (bytes entering the SMs, not
   // units, are what the kernel is short of: DESIGN.md 4)
   d->g = 1;
-  if (ts && d->m_tiles >= 2 &&
-      2 * (uint64_t)ceil_div(d->m_tiles, TS_G) * d->n_tiles * d->nb >= (uint64_t)sm_count && !dev_switch("SPFY_GEMM_G1"))
+  const uint64_t half_units = std::max<uint64_t>(launch_half_units, (uint64_t)ceil_div(d->m_tiles, TS_G) * d->n_tiles * d->nb);
+  if (ts && d->m_tiles >= 2 && 2 * half_units >= (uint64_t)sm_count && !dev_switch("SPFY_GEMM_G1"))
     d->g = TS_G;
+  if (g_balanced) d->g = g_balanced;
   if (pair) d->g = 2;  // a unit is a pair of m-tiles, one per CTA of the cluster
   d->m_groups = (uint32_t)ceil_div(d->m_tiles, d->g);
   const uint64_t units = (uint64_t)d->m_groups * d->n_tiles * d->nb;
@@ -1289,6 +1322,13 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
       continue;
     if (orient(dtype, problems[i], GM_MAX_BN, true).mu <= (size_t)GM_BM) pair = false;
   }
+  uint64_t launch_half_units = 0;
+  for (size_t i = 0; i < count && ts; ++i) {
+    if (check_problem(dtype, problems[i], true) != SPFY_OK || problems[i].m == 0 || problems[i].n == 0 || problems[i].nb == 0)
+      continue;
+    const Orientation o = orient(dtype, problems[i], TS_MAX_BN);
+    launch_half_units += (uint64_t)ceil_div(ceil_div(o.mu, GM_BM), TS_G) * o.n_tiles * problems[i].nb;
+  }
   for (size_t i = 0; i < count; ++i) {
     rc = check_problem(dtype, problems[i], true);
     if (rc) return rc;
@@ -1305,7 +1345,7 @@ int tc_gemm_run(int dtype, int precision, const TcGemmProblem* problems, size_t 
       q.B = vb.base; q.ldb = vb.ld; q.strideB = vb.stride;
     }
     GemmProblemDev d;
-    rc = fill_problem(&d, dtype, q, ts, di.sm_count, pair);
+    rc = fill_problem(&d, dtype, q, ts, di.sm_count, pair, count == 1, launch_half_units);
     if (rc) return rc;
     d.unit_begin = units;
     if ((uint64_t)units + d.units >= (1ull << 31)) return fail(SPFY_E_UNSUPPORTED, "tc_gemm: too many tiles");
