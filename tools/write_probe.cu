@@ -49,6 +49,30 @@ __global__ void mix_kernel(const uint4* src, uint4* dst, size_t n, int reads, ui
   if (acc == 0x12345678u) *sink = acc;
 }
 
+// The store pattern of a GEMM epilogue on a row-major [rows x cols] output (16-bit elements): a CTA owns tiles of
+// `tile_rows` rows x `tile_bytes` bytes, consecutive CTAs take consecutive column tiles (round robin), every warp store
+// instruction covers 512 bytes = (512 / tile_bytes) rows of the tile.  Optionally every tile is preceded by reading
+// `read_rows` rows x tile_bytes of a second matrix of the same pitch (the B tile of a small-K GEMM).
+__global__ void tile_write_kernel(uint4* out, const uint4* in, size_t pitch_bytes, uint32_t rows, uint32_t tile_rows,
+                                  uint32_t tile_bytes, uint32_t col_tiles, uint32_t read_rows, uint32_t* sink) {
+  const uint32_t row_tiles = rows / tile_rows, total = row_tiles * col_tiles;
+  const uint32_t per_row = tile_bytes / 16, rows_per_pass = blockDim.x / per_row;
+  const uint32_t r_in = threadIdx.x / per_row, c_in = threadIdx.x % per_row;
+  uint32_t acc = 0;
+  for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const uint32_t ct = t / row_tiles, rt = t % row_tiles;  // row tile fastest, like the m-groups of a unit list
+    const size_t col0 = (size_t)ct * tile_bytes;
+    for (uint32_t r = r_in; r < read_rows; r += rows_per_pass) {
+      const uint4 v = in[((size_t)r * pitch_bytes + col0) / 16 + c_in];
+      acc ^= v.x ^ v.w;
+    }
+    const uint4 v = make_uint4(acc, 2, 3, 4);
+    for (uint32_t r = r_in; r < tile_rows; r += rows_per_pass)
+      out[((size_t)(rt * tile_rows + r) * pitch_bytes + col0) / 16 + c_in] = v;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
 template <typename F>
 static double time_ms(F f, int reps = 10) {
   cudaEvent_t a, b;
@@ -87,6 +111,22 @@ int main() {
     const double ms = time_ms([&] { mix_kernel<<<sms * 8, 512>>>(a, b, nn, reads, sink); });
     printf("mix %d read : 1 write (16 B each), %4zu MiB written: %7.0f GB/s total, %7.0f GB/s of writes\n", reads, nn * 16 >> 20,
            (reads + 1) * nn * 16 / ms / 1e6, nn * 16 / ms / 1e6);
+  }
+  {
+    // D of 256 x 64 x 401408 (k <= 64 class): 256 rows x 802816 bytes; B: 64 rows of the same pitch
+    const size_t pitch = 401408 * 2;
+    uint4 *d2, *b2;
+    cudaMalloc(&d2, 256 * pitch); cudaMalloc(&b2, 64 * pitch);
+    cudaMemset(b2, 1, 64 * pitch);
+    for (int per_sm : {1, 2, 4})
+      for (uint32_t tile_bytes : {256u, 512u, 1024u})
+        for (uint32_t read_rows : {0u, 64u}) {
+          const uint32_t col_tiles = (uint32_t)(pitch / tile_bytes);
+          const double ms = time_ms([&] { tile_write_kernel<<<sms * per_sm, 512>>>(d2, b2, pitch, 256, 256, tile_bytes, col_tiles, read_rows, sink); });
+          const double wb = 256.0 * pitch, rb = (double)read_rows * pitch;
+          printf("epilogue pattern: %d CTA/SM, tiles of 256 rows x %4u B, pitch %zu B, %2u rows read per tile: %7.0f GB/s total (%6.1f us)\n",
+                 per_sm, tile_bytes, pitch, read_rows, (wb + rb) / ms / 1e6, ms * 1e3);
+        }
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
