@@ -63,6 +63,10 @@ enum { SPFY_PRUNE_STRIP_MAG = 0, SPFY_PRUNE_TILE_MAG = 1 };
 enum { SPFY_LAYOUT_CANONICAL = 0, SPFY_LAYOUT_SM100 = 1 };
 
 enum { SPFY_OP_N = 0, SPFY_OP_T = 1 }; /* == cusparseOperation_t values */
+/* OR-ed into the `opB` argument of spfy_spmma / spfy_spmma_problem: D is written TRANSPOSED, [n][m] row-major with pitch
+ * ldd >= m -- for a convolution layer that is NHWC, what spfy_spmma_conv of the next layer reads.  beta must be 0 and
+ * m a multiple of 8 (the contiguous dimension of an output always is: n for the row-major one). */
+enum { SPFY_OUT_T = 0x10 };
 
 enum {
   SPFY_OK = 0,
@@ -150,6 +154,7 @@ SPFY_API int spfy_prune24_check(int dtype, const void* in, size_t ld_in, size_t 
  * opB = T: B is n x k, ldb >= k.  C and D are m x n; D may alias C.
  * n, ldb, ldc, ldd must be multiples of 8 elements and all base pointers
  * 16-byte aligned (the reference's own fp16 contract, spmma.hxx:45-49).
+ * opB | SPFY_OUT_T: D is n x m (the transpose, pitch ldd >= m), beta must be 0, m % 8 == 0.
  * ---------------------------------------------------------------------- */
 SPFY_API int spfy_spmma_workspace_bytes(int dtype, size_t m, size_t n, size_t k,
                                         size_t* bytes);
@@ -175,6 +180,12 @@ typedef struct spfy_conv_desc {
 SPFY_API int spfy_spmma_conv(int dtype, const spfy_conv_desc* conv, size_t m, float alpha,
                              const void* comp_vals, const void* meta, const void* X, float beta,
                              const void* C, size_t ldc, void* D, size_t ldd, spfy_stream_t stream);
+/* The same with the output in NHWC: Y[N][m] (pitch ldy >= m, ldy % 8 == 0), i.e. [batch][ho][wo][m] -- the X of the next
+ * layer's spfy_spmma_conv, so a chain of convolutions never transposes or unfolds anything.  A unit's 128 positions x m
+ * channels are then one contiguous run of Y instead of m rows 2 * N bytes apart.  beta = 0. */
+SPFY_API int spfy_spmma_conv_nhwc(int dtype, const spfy_conv_desc* conv, size_t m, float alpha,
+                                  const void* comp_vals, const void* meta, const void* X, void* Y, size_t ldy,
+                                  spfy_stream_t stream);
 /* weights [m][c * kh * kw] in (c, kh, kw) column order (what torch's unfold / a flattened conv weight uses)
  * -> [m][kh * kw * c] in (kh, kw, c) order; 16-bit elements */
 SPFY_API int spfy_permute_conv_weights(const void* in, void* out, size_t m, size_t c, size_t kh, size_t kw,

@@ -21,11 +21,11 @@ import os
 
 from . import capi  # noqa: F401  (fails loudly if the .so is missing)
 from .capi import (F16, BF16, F32, F64, PRUNE_STRIP_MAG, PRUNE_TILE_MAG, LAYOUT_CANONICAL,  # noqa: F401
-                   LAYOUT_SM100, OP_N, OP_T, SPMM_ALG_DEFAULT, SPMM_ALG_CUDA_CORE, SPMM_ALG_TENSOR,
+                   LAYOUT_SM100, OP_N, OP_T, OUT_T, SPMM_ALG_DEFAULT, SPMM_ALG_CUDA_CORE, SPMM_ALG_TENSOR,
                    SPMM_ALG_TENSOR_FAST, GEMM_PRECISE, GEMM_FAST, GEMM_CTA_PAIRS, SpfyError, launch_count, last_error, version)
 from .ops import (sparsify, prune24, prune24_check, compressed_bytes, spmma_compressed, spmma,  # noqa: F401
                   threshold_to_coo, coo_to_csr, batched, Compressed24, SpmmaPlan, prune24_batched,
-                  alloc_compressed, pack_compressed, unpack_compressed, spmma_conv, permute_conv_weights)
+                  alloc_compressed, pack_compressed, unpack_compressed, spmma_conv, spmma_conv_nhwc, permute_conv_weights)
 from . import shapes  # noqa: F401
 from . import multigpu  # noqa: F401
 

@@ -18,6 +18,7 @@ F16, BF16, F32, F64 = 0, 1, 2, 3
 PRUNE_STRIP_MAG, PRUNE_TILE_MAG = 0, 1
 LAYOUT_CANONICAL, LAYOUT_SM100 = 0, 1
 OP_N, OP_T = 0, 1
+OUT_T = 0x10  # flag OR-ed into opB: D is written transposed, [n][m]
 SPMM_ALG_DEFAULT, SPMM_ALG_CUDA_CORE, SPMM_ALG_TENSOR, SPMM_ALG_TENSOR_FAST = 0, 1, 2, 3
 GEMM_PRECISE, GEMM_FAST = 0, 1
 GEMM_CTA_PAIRS = 0x10  # flag, OR-ed into `precision`: the cta_group::2 kernel where it applies
@@ -54,6 +55,7 @@ SIGNATURES = {
     "spfy_spmma": (c_int, [c_int, c_int, _SZ, _SZ, _SZ, c_float, _P, _P, _P, _SZ, c_float, _P, _SZ,
                            _P, _SZ, _P, _SZ, _P]),
     "spfy_spmma_conv": (c_int, [c_int, _P, _SZ, c_float, _P, _P, _P, c_float, _P, _SZ, _P, _SZ, _P]),
+    "spfy_spmma_conv_nhwc": (c_int, [c_int, _P, _SZ, c_float, _P, _P, _P, _P, _SZ, _P]),
     "spfy_permute_conv_weights": (c_int, [_P, _P, _SZ, _SZ, _SZ, _SZ, _P]),
     "spfy_spmma_plan_create": (c_int, [c_int, _P, _SZ, POINTER(c_void_p)]),
     "spfy_spmma_plan_create_replicated": (c_int, [c_int, _P, _SZ, _SZ, _P, POINTER(c_void_p)]),

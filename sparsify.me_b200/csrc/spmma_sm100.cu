@@ -91,6 +91,7 @@ struct alignas(64) ProblemDev {
   // GPU's memory (peer mappings over NVLink)
   const CUtensorMap* tmap_rep;
   uint32_t n_rep;
+  uint32_t out_t;              // D (and its replicas) are [n][m]: tmap_d boxes are (32 m, 64 n), unswizzled
   // implicit GEMM (spfy_spmma_conv): B is never materialised -- tmap_b is an im2col map over the NHWC activations and a
   // B stage (128 positions x 128 k) is gathered as two (128 positions x 64 channels) pieces, one filter tap each
   uint32_t conv;               // 0: B is a matrix
@@ -440,7 +441,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     const ProblemDev* last = nullptr;
     const CUtensorMap* tmap_d = nullptr;
     const CUtensorMap* tmap_rep = nullptr;
-    uint32_t n_rep = 0;
+    uint32_t n_rep = 0, out_t = 0;
     const uint16_t* Cptr = nullptr;
     uint64_t ldc = 0;
     uint32_t pm = 0, pn = 0, m_tiles = 0, m_groups = 1, G = 1, unit_begin = 0;
@@ -452,6 +453,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         tmap_d = &P->tmap_d;
         tmap_rep = P->tmap_rep;
         n_rep = P->n_rep;
+        out_t = P->out_t;
         Cptr = reinterpret_cast<const uint16_t*>(P->C);
         ldc = P->ldc;
         pm = P->m; pn = P->n; m_tiles = P->m_tiles; m_groups = P->m_groups; G = P->G; unit_begin = P->unit_begin;
@@ -487,7 +489,16 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             if (lane == 0) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
             __syncwarp();
             const uint32_t grow = m0 + row_in_tile;
-            if (alpha == 1.f && beta == 0.f) {
+            if (out_t) {
+              // transposed output [n][m]: the staging buffer holds 64 rows (n) of 32 halfwords (my quarter's m), so a
+              // lane -- one m -- drops column j of its 64 into row j; beta == 0 by contract
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const uint32_t w = pack2<BF16>(alpha * __uint_as_float(acc[2 * j]), alpha * __uint_as_float(acc[2 * j + 1]));
+                st_shared_u16(sc + (uint32_t)(2 * j) * 64u + lane * 2u, w);
+                st_shared_u16(sc + (uint32_t)(2 * j + 1) * 64u + lane * 2u, w >> 16);
+              }
+            } else if (alpha == 1.f && beta == 0.f) {
               // the common case (the reference's defaults, spmma.hxx:32-33): convert and stage, nothing else.
               // Kept apart from the general path: predicated-off C loads / FMAs still cost issue slots, and
               // with two epilogue warps per scheduler the conversion loop is what bounds the small-K classes.
@@ -522,8 +533,10 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && !no_store) {
-              tma_store_2d(tmap_d, sc, (int)n0, (int)(m0 + quarter * 32));
-              for (uint32_t r = 0; r < n_rep; ++r) tma_store_2d(tmap_rep + r, sc, (int)n0, (int)(m0 + quarter * 32));
+              // (coordinates are (inner, outer): (n, m) for the row-major output, (m, n) for the transposed one)
+              const int c0 = out_t ? (int)(m0 + quarter * 32) : (int)n0, c1 = out_t ? (int)n0 : (int)(m0 + quarter * 32);
+              tma_store_2d(tmap_d, sc, c0, c1);
+              for (uint32_t r = 0; r < n_rep; ++r) tma_store_2d(tmap_rep + r, sc, c0, c1);
               bulk_commit();
             }
           }
@@ -549,7 +562,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
 // ------------------------------------------------------------- host side
 // 2-D row-major tensor [outer x inner] of 16-bit elements, pitch ld elements
 int make_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t inner, uint64_t outer,
-                 uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+                 uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc;
   int rc = get_encoder(&enc);
   if (rc) return rc;
@@ -559,7 +573,7 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t inner, 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == SPFY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(SPFY_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %llu x %llu ld %llu", (int)r,
@@ -597,7 +611,12 @@ struct HostProblem {
   size_t ldb, ldc, ldd;
   float alpha, beta;
   const spfy_conv_desc* conv = nullptr;  // implicit GEMM: B is the NHWC activation tensor, never unfolded
+  bool out_t = false;                    // D is written transposed: [n][m] row-major, pitch ldd >= m (SPFY_OUT_T)
 };
+
+// the `opB` argument of the C ABI carries the output layout in bit 4 (SPFY_OUT_T)
+inline int op_of(int opB) { return opB & ~SPFY_OUT_T; }
+inline bool out_t_of(int opB) { return (opB & SPFY_OUT_T) != 0; }
 
 // NHWC activations {C, W, H, N} in im2col mode: one instruction gathers 128 consecutive output positions x 64 channels
 // of one filter tap.  The bounding box of base pixels is [-pad, dim + pad - (filter - 1)) per spatial dimension, walked
@@ -632,7 +651,12 @@ int validate(int dtype, const HostProblem& h, const char* who) {
   if (h.m >= (1u << 31) || h.n >= (1u << 31) || h.k >= (1u << 31))
     return fail(SPFY_E_UNSUPPORTED, "%s: dimension too large", who);
   const size_t b_inner = h.opB == SPFY_OP_N ? h.n : h.k;
-  if ((!h.conv && h.ldb < b_inner) || h.ldd < h.n || (h.beta != 0.f && h.ldc < h.n))
+  if (h.out_t && h.beta != 0.f)
+    return fail(SPFY_E_UNSUPPORTED, "%s: a transposed output (SPFY_OUT_T) needs beta == 0", who);
+  // (a TMA store moves whole 16-byte pieces of a row: the contiguous dimension of the output is a multiple of 8 elements)
+  if (h.out_t && h.m % 8)
+    return fail(SPFY_E_UNSUPPORTED, "%s: a transposed output (SPFY_OUT_T) needs m %% 8 == 0 (m=%zu)", who, h.m);
+  if ((!h.conv && h.ldb < b_inner) || h.ldd < (h.out_t ? h.m : h.n) || (h.beta != 0.f && h.ldc < h.n))
     return fail(SPFY_E_INVALID, "%s: leading dimension too small", who);
   // TMA contract == the reference's own fp16 contract (spmma.hxx:45-49): multiples of 8
   if ((!h.conv && h.ldb % 8) || h.ldd % 8 || (h.beta != 0.f && h.ldc % 8) || h.n % 8 || (h.opB == SPFY_OP_T && h.k % 8))
@@ -727,8 +751,10 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
     if (!d->b3d) rc = make_tmap_2d(&d->tmap_b, dtype, h.B, b_inner, b_outer, h.ldb, 64, box_outer);
     if (rc) return rc;
   }
-  rc = make_tmap_2d(&d->tmap_d, dtype, h.D, h.n, h.m, h.ldd, 64, 32);
+  rc = h.out_t ? make_tmap_2d(&d->tmap_d, dtype, h.D, h.m, h.n, h.ldd, 32, 64, CU_TENSOR_MAP_SWIZZLE_NONE)
+               : make_tmap_2d(&d->tmap_d, dtype, h.D, h.n, h.m, h.ldd, 64, 32);
   if (rc) return rc;
+  d->out_t = h.out_t;
   d->a_vals = (const uint8_t*)h.comp_vals;
   d->a_meta = (const uint8_t*)h.meta;
   d->C = h.C;
@@ -875,7 +901,9 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
                const void* meta, const void* B, size_t ldb, float beta, const void* C, size_t ldc,
                void* D, size_t ldd, void* workspace, size_t workspace_bytes, spfy_stream_t stream) {
   (void)workspace; (void)workspace_bytes;
-  HostProblem h{opB, m, n, k, comp_vals, meta, B, C, D, ldb, ldc, ldd, alpha, beta};
+  HostProblem h{op_of(opB), m, n, k, comp_vals, meta, B, C, D, ldb, ldc, ldd, alpha, beta};
+  h.out_t = out_t_of(opB);
+  opB = h.opB;
   int rc = validate(dtype, h, "spmma");
   if (rc) return rc;
   if (m == 0 || n == 0) return SPFY_OK;
@@ -905,9 +933,24 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
   return launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
 }
 
+static int spmma_conv_impl(int dtype, const spfy_conv_desc* conv, size_t m, float alpha, const void* comp_vals,
+                           const void* meta, const void* X, float beta, const void* C, size_t ldc, void* D, size_t ldd,
+                           bool out_t, spfy_stream_t stream);
+
 int spfy_spmma_conv(int dtype, const spfy_conv_desc* conv, size_t m, float alpha, const void* comp_vals,
                     const void* meta, const void* X, float beta, const void* C, size_t ldc, void* D, size_t ldd,
                     spfy_stream_t stream) {
+  return spmma_conv_impl(dtype, conv, m, alpha, comp_vals, meta, X, beta, C, ldc, D, ldd, false, stream);
+}
+
+int spfy_spmma_conv_nhwc(int dtype, const spfy_conv_desc* conv, size_t m, float alpha, const void* comp_vals,
+                         const void* meta, const void* X, void* Y, size_t ldy, spfy_stream_t stream) {
+  return spmma_conv_impl(dtype, conv, m, alpha, comp_vals, meta, X, 0.f, nullptr, 0, Y, ldy, true, stream);
+}
+
+static int spmma_conv_impl(int dtype, const spfy_conv_desc* conv, size_t m, float alpha, const void* comp_vals,
+                           const void* meta, const void* X, float beta, const void* C, size_t ldc, void* D, size_t ldd,
+                           bool out_t, spfy_stream_t stream) {
   if (!conv) return fail(SPFY_E_INVALID, "spmma_conv: null descriptor");
   const spfy_conv_desc& c = *conv;
   if (!c.batch || !c.h || !c.w || !c.c || !c.kh || !c.kw || !c.stride)
@@ -921,6 +964,7 @@ int spfy_spmma_conv(int dtype, const spfy_conv_desc* conv, size_t m, float alpha
   const size_t n = c.batch * ho * wo, k = c.kh * c.kw * c.c;
   HostProblem h{SPFY_OP_T, m, n, k, comp_vals, meta, X, C, D, /*ldb*/ k, ldc, ldd, alpha, beta};
   h.conv = conv;
+  h.out_t = out_t;
   int rc = validate(dtype, h, "spmma_conv");
   if (rc) return rc;
   if (m == 0 || n == 0) return SPFY_OK;
@@ -1007,7 +1051,8 @@ static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_
       std::vector<size_t> members;
       for (size_t i = 0; i < count; ++i) {
         const spfy_spmma_problem& q = problems[i];
-        HostProblem h{q.opB, q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
+        HostProblem h{op_of(q.opB), q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
+        h.out_t = out_t_of(q.opB);
         if (h.opB != opB) continue;
         rc = validate(dtype, h, "spmma_plan_create");
         if (rc) {
@@ -1023,7 +1068,8 @@ static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_
       });
       for (size_t i : members) {
         const spfy_spmma_problem& q = problems[i];
-        HostProblem h{q.opB, q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
+        HostProblem h{op_of(q.opB), q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
+        h.out_t = out_t_of(q.opB);
         ProblemDev d;
         rc = fill_problem(&d, dtype, h, cls);
         if (rc) {
@@ -1041,7 +1087,8 @@ static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_
           d.n_rep = (uint32_t)n_rep;
           for (size_t r = 0; r < n_rep && !rc; ++r) {
             CUtensorMap tm;
-            rc = make_tmap_2d(&tm, dtype, rep_d[i * n_rep + r], h.n, h.m, h.ldd, 64, 32);
+            rc = h.out_t ? make_tmap_2d(&tm, dtype, rep_d[i * n_rep + r], h.m, h.n, h.ldd, 32, 64, CU_TENSOR_MAP_SWIZZLE_NONE)
+                         : make_tmap_2d(&tm, dtype, rep_d[i * n_rep + r], h.n, h.m, h.ldd, 64, 32);
             reps.push_back(tm);
           }
           if (rc) {

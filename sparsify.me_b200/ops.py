@@ -173,7 +173,7 @@ class SpmmaPlan:
     """spfy_spmma_plan_*: a list of independent D_i = alpha_i * A_i(2:4) * op(B_i) + beta_i * C_i executed
     by one persistent launch per ring-geometry class present (tensor maps + tile schedule built once, like
     cusparseLtMatmulPlanInit at spmma.hxx:79).  `problems`: dicts with comp, b, out and optional c, alpha,
-    beta, op_b.  The plan keeps the tensors alive.
+    beta, op_b, out_t (out is then [n, m], the transposed result; beta must be 0).  The plan keeps the tensors alive.
     Optional `replicas` per problem: device addresses (ints) of further copies of `out` (same shape and row pitch) that
     the epilogue stores every tile to as well -- e.g. the slab of this rank in the gather arena of every peer GPU
     (spfy_spmma_plan_create_replicated: the fused output gather); every problem must name the same number of them."""
@@ -189,6 +189,8 @@ class SpmmaPlan:
             op_b = q.get("op_b", capi.OP_N)
             dtype = comp.dtype
             nn = b.shape[1] if op_b == capi.OP_N else b.shape[0]
+            if q.get("out_t"):  # `out` is [n, m]: the transposed result
+                op_b |= capi.OUT_T
             arr[i] = capi.SpmmaProblem(op_b, comp.rows, nn, comp.cols, comp.vals.data_ptr(), comp.meta.data_ptr(),
                                        b.data_ptr(), b.stride(0), c.data_ptr() if c is not None else None,
                                        c.stride(0) if c is not None else 0, out.data_ptr(), out.stride(0),
@@ -230,15 +232,18 @@ class SpmmaPlan:
 
 
 # ----------------------------------------------------------------------------- A4
-def spmma_compressed(comp, b, c=None, out=None, alpha=1.0, beta=0.0, op_b=capi.OP_N):
+def spmma_compressed(comp, b, c=None, out=None, alpha=1.0, beta=0.0, op_b=capi.OP_N, out_t=False):
     """D = alpha * A(2:4) * op(B) + beta * C on tcgen05.mma.sp (cusparseLtMatmul, spmma.hxx:106-114).
-    All dense operands row-major.  Returns D (== out, or a new tensor)."""
+    All dense operands row-major.  Returns D (== out, or a new tensor); out_t: D is [n, m], the transposed result
+    (SPFY_OUT_T: NHWC for a convolution layer; beta must be 0)."""
     assert comp.layout == capi.LAYOUT_SM100
     m, k = comp.rows, comp.cols
     n = b.shape[1] if op_b == capi.OP_N else b.shape[0]
     assert (b.shape[0] if op_b == capi.OP_N else b.shape[1]) == k
     if out is None:
-        out = torch.empty(m, n, dtype=comp.dtype, device=b.device)
+        out = torch.empty((n, m) if out_t else (m, n), dtype=comp.dtype, device=b.device)
+    if out_t:
+        op_b |= capi.OUT_T
     capi.spfy_spmma(_DT[comp.dtype], op_b, m, n, k, float(alpha), _ptr(comp.vals), _ptr(comp.meta),
                     _ptr(b), b.stride(0), float(beta), _ptr(c), c.stride(0) if c is not None else 0,
                     _ptr(out), out.stride(0), None, 0, _stream())
@@ -268,6 +273,22 @@ def spmma_conv(comp, x, kh, kw, stride=1, pad=0, c=None, out=None, alpha=1.0, be
     capi.spfy_spmma_conv(_DT[comp.dtype], ctypes.byref(desc), comp.rows, float(alpha), _ptr(comp.vals), _ptr(comp.meta),
                          _ptr(x), float(beta), _ptr(c), c.stride(0) if c is not None else 0, _ptr(out), out.stride(0),
                          _stream())
+    return out
+
+
+def spmma_conv_nhwc(comp, x, kh, kw, stride=1, pad=0, out=None, alpha=1.0):
+    """spfy_spmma_conv_nhwc: the same implicit GEMM with the result in NHWC, [batch, ho, wo, m] -- the `x` of the next
+    layer, so a chain of convolutions never transposes or unfolds anything."""
+    assert x.dim() == 4 and x.is_contiguous()
+    nb, h, w, ch = x.shape
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    assert comp.cols == kh * kw * ch
+    if out is None:
+        out = torch.empty(nb, ho, wo, comp.rows, dtype=comp.dtype, device=x.device)
+    assert out.is_contiguous() and out.numel() == nb * ho * wo * comp.rows
+    desc = capi.ConvDesc(nb, h, w, ch, kh, kw, stride, pad)
+    capi.spfy_spmma_conv_nhwc(_DT[comp.dtype], ctypes.byref(desc), comp.rows, float(alpha), _ptr(comp.vals),
+                              _ptr(comp.meta), _ptr(x), _ptr(out), comp.rows, _stream())
     return out
 
 

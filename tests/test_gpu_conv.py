@@ -54,6 +54,46 @@ def test_implicit_gemm_equals_explicit_unfold(spfy, cuda, case, tdt):
     assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
 
 
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(str(v) for v in c))
+def test_implicit_gemm_nhwc_output_is_the_transpose(spfy, cuda, case):
+    """spfy_spmma_conv_nhwc: the same accumulators written as [batch, ho, wo, c_out] -- bit for bit the transpose of the
+    row-major result, odd tile edges included (c_out = 72: the last 8 channels of a 32-row store box are clipped)"""
+    nb, h, w, c, cout, kh, kw, stride, pad = case
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(sum(case) + 1)
+    x = (torch.rand(nb, h, w, c, device=cuda, generator=gen) * 2 - 1).half()
+    wt = (torch.rand(cout, c * kh * kw, device=cuda, generator=gen) * 2 - 1).half()
+    comp = spfy.prune24(spfy.permute_conv_weights(wt, c, kh, kw))
+    want = spfy.spmma_conv(comp, x, kh, kw, stride=stride, pad=pad)            # [cout, N]
+    got = spfy.spmma_conv_nhwc(comp, x, kh, kw, stride=stride, pad=pad)       # [nb, ho, wo, cout]
+    torch.cuda.synchronize()
+    assert got.shape[0] == nb and got.shape[3] == cout
+    assert torch.equal(got.view(-1, cout), want.t())
+
+
+def test_two_convolutions_chained_in_nhwc(spfy, cuda):
+    """layer 1's NHWC output is layer 2's input as it stands: no transpose, no unfold between them (checked against
+    torch's conv2d applied twice to the pruned weights)"""
+    nb, h, w, c0, c1, c2 = 2, 28, 28, 64, 128, 64
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(11)
+    x = (torch.rand(nb, h, w, c0, device=cuda, generator=gen) * 2 - 1).half()
+    w1 = ((torch.rand(c1, c0 * 9, device=cuda, generator=gen) * 2 - 1) * 0.1).half()
+    w2 = ((torch.rand(c2, c1 * 9, device=cuda, generator=gen) * 2 - 1) * 0.1).half()
+    p1, p2 = spfy.permute_conv_weights(w1, c0, 3, 3), spfy.permute_conv_weights(w2, c1, 3, 3)
+    d1, d2 = torch.empty_like(p1), torch.empty_like(p2)
+    k1, k2 = spfy.prune24(p1, out_dense=d1), spfy.prune24(p2, out_dense=d2)
+    y1 = spfy.spmma_conv_nhwc(k1, x, 3, 3, stride=1, pad=1)                    # [nb, 28, 28, c1]
+    y2 = spfy.spmma_conv_nhwc(k2, y1, 3, 3, stride=2, pad=1)                   # [nb, 14, 14, c2]
+    torch.cuda.synchronize()
+    f1 = d1.view(c1, 3, 3, c0).permute(0, 3, 1, 2).float()
+    f2 = d2.view(c2, 3, 3, c1).permute(0, 3, 1, 2).float()
+    r1 = F.conv2d(x.permute(0, 3, 1, 2).float(), f1, padding=1).half().float()  # layer 1 rounds to fp16 like ours
+    r2 = F.conv2d(r1, f2, padding=1, stride=2).permute(0, 2, 3, 1)
+    scale = torch.clamp(r2.abs(), min=1e-2 * float(r2.abs().max()))
+    assert float(((y2.float() - r2).abs() / scale).max()) <= 1e-2
+
+
 def test_implicit_gemm_matches_a_real_convolution(spfy, cuda):
     """end to end against torch's own conv2d on the pruned weights (fp32 reference, max relative error 1e-2)"""
     nb, h, w, c, cout = 4, 28, 28, 128, 256

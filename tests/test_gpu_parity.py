@@ -410,6 +410,53 @@ def test_spmma_plan_matches_single_calls_and_oracle(spfy, orc, cuda):
     plan.close()
 
 
+@pytest.mark.parametrize("M,K,N", [(64, 147, 19008), (256, 64, 19200), (512, 200, 9600), (1024, 256, 9600), (128, 1152, 2048),
+                                   (104, 576, 19000), (136, 260, 264), (2048, 512, 392)])
+@pytest.mark.parametrize("dt", [0, 1])
+def test_spmma_transposed_output(spfy, orc, cuda, M, K, N, dt):
+    """SPFY_OUT_T: D written as [n][m] (NHWC for a convolution layer) -- bit for bit the transpose of the row-major
+    result in every launch class, with alpha, a pitched destination and rows that do not fill a 32-row store box"""
+    comp = spfy.prune24(to_dev(rand_bits(orc, dt, (M, K), seed=M + K), dt, cuda))
+    b = to_dev(rand_bits(orc, dt, (K, N), seed=N + 1), dt, cuda)
+    want = spfy.spmma_compressed(comp, b, alpha=0.5)
+    ld = (M + 15) // 8 * 8
+    buf = torch.full((N, ld), 7.0, dtype=want.dtype, device=cuda)
+    spfy.spmma_compressed(comp, b, alpha=0.5, out=buf[:, :M], out_t=True)
+    torch.cuda.synchronize()
+    assert torch.equal(buf[:, :M], want.t())
+    assert bool((buf[:, M:] == 7.0).all())  # nothing written beyond column m
+    if K % 8 == 0:  # opB = T needs k % 8 == 0
+        buf2 = torch.empty((N, ld), dtype=want.dtype, device=cuda)
+        spfy.spmma_compressed(comp, b.t().contiguous(), op_b=spfy.OP_T, out=buf2[:, :M], out_t=True)
+        assert torch.equal(buf2[:, :M], spfy.spmma_compressed(comp, b).t())
+    with pytest.raises(spfy.SpfyError):
+        spfy.spmma_compressed(comp, b, c=want, beta=1.0, out_t=True)
+    if M == 104:  # the contiguous dimension of an output is a multiple of 8 elements
+        odd = spfy.prune24(to_dev(rand_bits(orc, dt, (100, K), seed=1), dt, cuda))
+        with pytest.raises(spfy.SpfyError) as e:
+            spfy.spmma_compressed(odd, b, out=buf[:, :100], out_t=True)
+        assert e.value.code == spfy.capi.E_UNSUPPORTED
+
+
+def test_spmma_plan_mixes_output_layouts(spfy, orc, cuda):
+    shapes = [(64, 147, 19008), (256, 64, 19200), (1024, 256, 9600), (256, 2304, 392), (136, 260, 264), (512, 128, 18944)]
+    problems, wants = [], []
+    for i, (M, K, N) in enumerate(shapes):
+        comp = spfy.prune24(to_dev(rand_bits(orc, 0, (M, K), seed=40 + i), 0, cuda))
+        b = to_dev(rand_bits(orc, 0, (K, N), seed=60 + i), 0, cuda)
+        t = i % 2 == 0
+        wants.append(spfy.spmma_compressed(comp, b))
+        ld = (M + 7) // 8 * 8  # the pitch of a transposed output is a multiple of 8 elements like every other
+        out = torch.zeros(N, ld, dtype=torch.float16, device=cuda)[:, :M] if t else torch.zeros(M, N, dtype=torch.float16, device=cuda)
+        problems.append(dict(comp=comp, b=b, out=out, out_t=t))
+    plan = spfy.SpmmaPlan(problems)
+    plan.run()
+    torch.cuda.synchronize()
+    for q, want in zip(problems, wants):
+        assert torch.equal(q["out"], want.t() if q.get("out_t") else want)
+    plan.close()
+
+
 def test_spmma_plan_replicated_outputs(spfy, orc, cuda):
     """spfy_spmma_plan_create_replicated on one GPU: every replica (here: other buffers of the same device; across GPUs:
     peer mappings, tests/mg_worker.py) ends up bit-identical to the primary output, for every launch class, both
