@@ -84,6 +84,10 @@ struct alignas(64) ProblemDev {
                        // CTA's next unit belongs to another m-group, which never happens when gridDim % m_groups == 0)
   uint32_t b3d;
   uint32_t unit_begin, units;  // this problem's range in the launch-wide unit order
+  // Tail splitting (single calls): units [0, split_units) pair the m-tiles (G) of n-tiles [0, split_nt); the n-tiles
+  // from split_nt on -- the last, partial wave -- are dealt one m-tile per unit, so that the tail costs about half a unit
+  // on twice as many SMs instead of a whole unit on a few.  No split: split_units = units, split_nt = n_tiles.
+  uint32_t split_units, split_nt;
   float alpha, beta;
   uint64_t hint_b;
   // replicated outputs (fused output gather, spfy_spmma_plan_create_replicated): every D tile is also stored through
@@ -122,6 +126,24 @@ __device__ __forceinline__ uint32_t rows_valid_of(uint32_t m, uint32_t mt) {
   return left >= (uint32_t)BM ? (uint32_t)BM : ((left + 15u) & ~15u);
 }
 
+
+// unit number inside a problem -> (n-tile, first m-tile, m-tiles of the unit)
+struct UnitPos { uint32_t nt, mt0, g_count; };
+__device__ __forceinline__ UnitPos decode_unit(uint32_t local, uint32_t m_groups, uint32_t G, uint32_t m_tiles,
+                                               uint32_t split_units, uint32_t split_nt) {
+  UnitPos p;
+  if (local < split_units) {
+    p.nt = local / m_groups;
+    p.mt0 = (local - p.nt * m_groups) * G;
+    p.g_count = min(G, m_tiles - p.mt0);
+  } else {
+    const uint32_t l2 = local - split_units, q = l2 / m_tiles;
+    p.nt = split_nt + q;
+    p.mt0 = l2 - q * m_tiles;
+    p.g_count = 1u;
+  }
+  return p;
+}
 
 // All three roles walk the same sequence of units: u = blockIdx.x, blockIdx.x + gridDim.x, ...
 struct UnitWalker {
@@ -204,6 +226,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       const CUtensorMap* tmap_b = nullptr;
       const uint8_t *a_vals = nullptr, *a_meta = nullptr;
       uint32_t pm = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, b3d = 0;
+      uint32_t split_units = 0, split_nt = 0;
       uint32_t conv = 0, conv_c = 64, conv_kw = 1, conv_wo = 1, conv_ho = 1, conv_stride = 1, conv_pad = 0, pk = 0;
       uint64_t hint_b = 0;
       const bool no_b = (L.dbg & 4u) != 0, no_a = (L.dbg & 16u) != 0;
@@ -216,6 +239,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           a_vals = uni(P->a_vals); a_meta = uni(P->a_meta);
           pm = uni(P->m); k_tiles = uni(P->k_tiles); m_tiles = uni(P->m_tiles); b3d = uni(P->b3d);
           m_groups = uni(P->m_groups); G = uni(P->G); resident = uni(P->resident); unit_begin = uni(P->unit_begin);
+          split_units = uni(P->split_units); split_nt = uni(P->split_nt);
           hint_b = uni(P->hint_b);
           conv = uni(P->conv); pk = uni(P->k);
           if (conv) {
@@ -224,9 +248,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           }
         }
         const uint32_t local = W.u - unit_begin;
-        const uint32_t nt = local / m_groups, mg = local - nt * m_groups;
-        const uint32_t mt0 = mg * G;
-        const uint32_t g_count = min(G, m_tiles - mt0);
+        const UnitPos up = decode_unit(local, m_groups, G, m_tiles, split_units, split_nt);
+        const uint32_t nt = up.nt, mt0 = up.mt0, g_count = up.g_count, mg = mt0 / G;
         // implicit GEMM: base pixel of the unit's first output position (input coordinates of filter tap (0, 0))
         int cw = 0, ch = 0, cn = 0;
         if (conv) {
@@ -333,6 +356,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       const ProblemDev* res_owner = nullptr;
       const ProblemDev* last = nullptr;
       uint32_t pm = 0, pk = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, units = 0;
+      uint32_t split_units = 0, split_nt = 0;
       const bool no_mma = (L.dbg & 8u) != 0;
       // constant halves of the shared-memory descriptors (the start address is OR-ed in per MMA)
       const uint64_t desc_a_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
@@ -346,11 +370,11 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           pm = uni(P->m); pk = uni(P->k); k_tiles = uni(P->k_tiles); m_tiles = uni(P->m_tiles);
           m_groups = uni(P->m_groups); G = uni(P->G); resident = uni(P->resident);
           unit_begin = uni(P->unit_begin); units = uni(P->units);
+          split_units = uni(P->split_units); split_nt = uni(P->split_nt);
         }
         const uint32_t local = W.u - unit_begin;
-        const uint32_t mg = local % m_groups;
-        const uint32_t mt0 = mg * G;
-        const uint32_t g_count = min(G, m_tiles - mt0);
+        const UnitPos up = decode_unit(local, m_groups, G, m_tiles, split_units, split_nt);
+        const uint32_t mt0 = up.mt0, g_count = up.g_count, mg = mt0 / G;
         const uint32_t res_key = resident == 2u ? mg : 0u;
         if (resident && (res_owner != P || res_mg != res_key)) {
           mbar_wait(bar_res_full, res_loads & 1u);
@@ -444,7 +468,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
     uint32_t n_rep = 0, out_t = 0;
     const uint16_t* Cptr = nullptr;
     uint64_t ldc = 0;
-    uint32_t pm = 0, pn = 0, m_tiles = 0, m_groups = 1, G = 1, unit_begin = 0;
+    uint32_t pm = 0, pn = 0, m_tiles = 0, m_groups = 1, G = 1, unit_begin = 0, split_units = 0, split_nt = 0;
     float alpha = 1.f, beta = 0.f;
     for (; W.valid(); W.next()) {
       const ProblemDev* P = W.current();
@@ -457,12 +481,12 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         Cptr = reinterpret_cast<const uint16_t*>(P->C);
         ldc = P->ldc;
         pm = P->m; pn = P->n; m_tiles = P->m_tiles; m_groups = P->m_groups; G = P->G; unit_begin = P->unit_begin;
+        split_units = P->split_units; split_nt = P->split_nt;
         alpha = P->alpha; beta = P->beta;
       }
       const uint32_t local = W.u - unit_begin;
-      const uint32_t nt = local / m_groups, mg = local - nt * m_groups;
-      const uint32_t mt0 = mg * G;
-      const uint32_t g_count = min(G, m_tiles - mt0);
+      const UnitPos up = decode_unit(local, m_groups, G, m_tiles, split_units, split_nt);
+      const uint32_t nt = up.nt, mt0 = up.mt0, g_count = up.g_count;
       for (uint32_t g = 0; g < g_count; ++g, ++job) {
         const uint32_t slot = job % ACC_SLOTS;
         const uint32_t m0 = (mt0 + g) * BM;
@@ -769,6 +793,8 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   d->G = (cls == CLASS_STREAM_G1) ? 1u : (d->m_tiles >= 2 ? 2u : 1u);
   d->m_groups = (uint32_t)ceil_div(d->m_tiles, d->G);
   d->units = d->m_groups * d->n_tiles;
+  d->split_units = d->units;
+  d->split_nt = d->n_tiles;
   d->alpha = h.alpha;
   d->beta = h.beta;
   // B is streamed once when one unit covers all of M; otherwise the other m-groups of the same
@@ -809,6 +835,21 @@ void geometry(int cls, uint32_t res_vals, uint32_t res_meta, LaunchParams* L, ui
   L->c_off = L->res_off + res;
   L->bar_off = L->c_off + c_bytes;
   *smem_bytes = L->bar_off + BAR_BYTES + 1024;
+}
+
+// A single streaming call whose last wave is partial: deal that wave's n-tiles one m-tile per unit when the G = 1 units
+// still fit one wave (256 x 2304 x 25088: 196 units on 148 SMs = 148 + 48 -> 148 + 96 half units).
+void split_tail(ProblemDev* d, int cls, int sm_count) {
+  static const bool off = dev_switch("SPFY_SPMMA_NO_TAIL_SPLIT") != nullptr;
+  if (off || is_resident_class(cls) || d->G != 2u || d->m_tiles < 2u) return;
+  const uint32_t sm = (uint32_t)sm_count, full = d->units / sm, rem = d->units % sm;
+  if (full == 0 || rem == 0 || rem % d->m_groups) return;
+  const uint32_t tail_nt = rem / d->m_groups, tail_units = tail_nt * d->m_tiles;
+  if (tail_units > sm) return;
+  d->split_units = d->units - rem;
+  d->split_nt = d->n_tiles - tail_nt;
+  d->units = d->split_units + tail_units;
+  d->hint_b = HINT_EVICT_NORMAL;  // the tail's B tiles are read by every m-tile's unit
 }
 
 uint32_t make_idesc(int dtype, int opB) {
@@ -917,6 +958,7 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
   rc = fill_problem(&d, dtype, h, cls);
   if (rc) return rc;
   d.unit_begin = 0;
+  split_tail(&d, cls, di.sm_count);
   LaunchParams L;
   memset(&L, 0, sizeof(L));
   uint32_t smem = 0;
@@ -978,6 +1020,7 @@ static int spmma_conv_impl(int dtype, const spfy_conv_desc* conv, size_t m, floa
   rc = fill_problem(&d, dtype, h, cls);
   if (rc) return rc;
   d.unit_begin = 0;
+  split_tail(&d, cls, di.sm_count);
   LaunchParams L;
   memset(&L, 0, sizeof(L));
   uint32_t smem = 0;

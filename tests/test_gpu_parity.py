@@ -361,7 +361,8 @@ CLASS_SHAPES = [(64, 147, 19008), (200, 72, 19080), (512, 128, 18944), (100, 576
                 (128, 512, 19008),                                                             # resident, large operand
                 (512, 200, 9600), (300, 264, 9480), (1024, 256, 4800),                       # stream, G=2
                 (1024, 256, 9600), (400, 256, 19000), (384, 250, 19000),                     # resident m-group slices (G=2; short / odd last group)
-                (128, 1152, 2048), (96, 2304, 1000)]                                         # stream, G=1
+                (128, 1152, 2048), (96, 2304, 1000),                                         # stream, G=1
+                (256, 384, 25088), (384, 640, 12752), (512, 600, 11480)]                      # stream, G=2 with a split tail wave
 
 
 @pytest.mark.parametrize("M,K,N", CLASS_SHAPES)
@@ -380,7 +381,7 @@ def test_spmma_plan_matches_single_calls_and_oracle(spfy, orc, cuda):
     separate plan): every output must equal the single-call result bit for bit and the oracle within tol."""
     shapes = [(64, 147, 19008), (512, 128, 18944), (256, 64, 20000), (512, 200, 1600), (1024, 256, 1200),
               (128, 1152, 520), (256, 2304, 392), (2048, 512, 264), (64, 576, 19000), (130, 260, 264),
-              (1024, 256, 9600), (384, 256, 19000)]
+              (1024, 256, 9600), (384, 256, 19000), (384, 640, 12752)]  # the last one: single call splits its tail wave
     problems, singles, wants = [], [], []
     for i, (M, K, N) in enumerate(shapes):
         a_bits = rand_bits(orc, 0, (M, K), seed=500 + i)
