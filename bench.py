@@ -738,6 +738,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="coo workload: eager launches instead of CUDA graph replays")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-implicit", action="store_true", help="skip the implicit-GEMM variants (plan and e2e)")
     ap.add_argument("--no-prune-large", action="store_true", help="skip the large-matrix prune24 measurement")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--per-layer", action="store_true", help="also print a per-layer table to stderr")
@@ -864,6 +865,67 @@ def main():
         if not verified["ok"]:
             raise SystemExit(f"bench.py: timed outputs are wrong (max relative error {worst:.3e} > 1e-2)")
 
+    # ---- the same table with the 3 x 3 layers as implicit GEMMs: ONE plan in which those layers read
+    #      their NHWC activations through TMA im2col instead of the unfolded K x N operand (spfy_spmma_plan_create_conv).
+    #      Same FLOPs, same outputs (checked below); reported beside the headline, which multiplies the CSV's matrices.
+    conv_geom = {}
+    for g in gemms:
+        hw = g.N // args.batch
+        ho = math.isqrt(hw)
+        if g.K % 9 == 0 and (g.K // 9) % 64 == 0 and ho * ho == hw and hw * args.batch == g.N:
+            conv_geom[g] = (ho, g.K // 9)  # 3 x 3, pad 1, stride 1 (the CSV does not record strides)
+    xdev, xl, implicit_plan = {}, {}, None
+    if conv_geom and not args.no_implicit:
+        for g, (ho, cin) in conv_geom.items():
+            xdev[g] = (torch.rand(args.batch, ho, ho, cin, device=dev, generator=gen) * 2 - 1).to(tdt)
+        xl = {id(l[3]): xdev[l[0]].clone() for l in layers if l[0] in conv_geom}  # one x per layer: nothing is shared through L2
+        plan_i = spfy.SpmmaPlan([dict(comp=comp, b=xl[id(d)], out=d, conv=(3, 3, 1, 1)) if g in conv_geom else
+                                 dict(comp=comp, b=b, out=d) for g, w, b, d, comp in layers])
+        for _ in range(args.warmup):
+            prune_all()
+            plan_i.run()
+        barrier()
+        torch.cuda.synchronize()
+        evi = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        e0.record()
+        for s_ in range(args.steps):
+            prune_all()
+            evi[s_][0].record()
+            plan_i.run()
+            evi[s_][1].record()
+        e1.record()
+        torch.cuda.synchronize()
+        ti = torch.tensor([e0.elapsed_time(e1) / args.steps, sum(a.elapsed_time(b_) for a, b_ in evi) / args.steps],
+                          dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+        step_i, spmma_i = (float(v) for v in ti.tolist())
+        if rank == 0:
+            import torch.nn.functional as F
+            same = True
+            for g0 in sorted(conv_geom, key=lambda q: q.K)[-2:]:  # the two largest-K conv shapes: every column, bit for bit
+                li = next(i for i, l in enumerate(layers) if l[0] == g0)
+                _, _, _, d0, comp0 = layers[li]
+                ho, cin = conv_geom[g0]
+                cols = F.unfold(xl[id(d0)].permute(0, 3, 1, 2).float(), 3, padding=1).view(args.batch, cin, 9, ho * ho)
+                bx = cols.permute(2, 1, 0, 3).reshape(g0.K, g0.N).to(tdt).contiguous()
+                del cols
+                same = same and bool(torch.equal(spfy.spmma_compressed(comp0, bx), d0))
+                del bx
+            if not same:
+                raise SystemExit("bench.py: the implicit-GEMM plan's outputs differ from the explicit operand's")
+            bytes_i = sum((spfy.shapes.spmma_bytes(g) - 2 * g.K * g.N + 2 * xdev[g].numel()) if g in conv_geom
+                          else spfy.shapes.spmma_bytes(g) for g in gemms)
+            implicit_plan = {
+                "ms_per_step": step_i, "spmma_ms_per_step": spmma_i, "value": flops_step * world / (step_i * 1e-3) / 1e12, "unit": UNIT,
+                "conv_layers": sum(1 for g in gemms if g in conv_geom), "launches_per_step": plan_i.launches,
+                "algorithmic_bytes_per_step": bytes_i, "achieved_GBs": bytes_i / (spmma_i * 1e-3) / 1e9,
+                "frac_of_hbm_on_its_own_bytes": bytes_i / (spmma_i * 1e-3) / 1e9 / hbm_peak,
+                "explicit_spmma_ms_per_step": spmma_ms, "identical_to_explicit_operand": same,
+                "note": "3 x 3 layers (pad 1, stride 1 assumed: the CSV has no strides) read NHWC activations through TMA im2col; "
+                        "HBM bytes drop, the bytes entering the SMs do not (DESIGN.md 4), so the gain is bounded by the L2 -> SM path"}
+        plan_i.close()
+
     # ---- end to end through the reference-shaped call with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -928,19 +990,10 @@ def main():
         #      activation, datasets/get_shapes.py:29-41) never exists on the host either -- the NHWC activations travel and
         #      spfy_spmma_conv gathers the operand with TMA im2col (weights stored (kh, kw, c)-major, a layout chosen once
         #      at export).  Reported BESIDE e2e, not instead of it: the reference's call takes the unfolded matrix.
-        conv_geom = {}
-        for g in gemms:
-            hw = g.N // args.batch
-            ho = math.isqrt(hw)
-            if g.K % 9 == 0 and (g.K // 9) % 64 == 0 and ho * ho == hw and hw * args.batch == g.N:
-                conv_geom[g] = (ho, g.K // 9)  # 3 x 3, pad 1, stride 1 (the CSV does not record strides)
-        if conv_geom:
-            xdev = {}
-            for g, (ho, cin) in conv_geom.items():
-                xdev[g] = (torch.rand(args.batch, ho, ho, cin, device=dev, generator=gen) * 2 - 1).to(tdt)
+        if xl:
+            for g in conv_geom:
                 hostbuf[("x", g)] = torch.empty(xdev[g].shape, dtype=tdt).pin_memory()
                 hostbuf[("x", g)].copy_(xdev[g])
-            xl = {id(l[3]): torch.empty_like(xdev[l[0]]) for l in layers if l[0] in conv_geom}  # one x per layer
             h2d_i = sum((g.M * g.K + (xdev[g].numel() if g in conv_geom else g.K * g.N)) * 2 for g in gemms)
 
             def e2e_implicit_step():
@@ -1002,7 +1055,6 @@ def main():
                 "pcie_GBs_per_rank": {"h2d": h2d_i / (ei_ms * 1e-3) / 1e9, "d2h": d2h / (ei_ms * 1e-3) / 1e9},
                 "api": "as e2e, but the 3 x 3 layers go through spfy_spmma_conv: host NHWC activations in, the K x N operand "
                        "(9 x the activation bytes) is never built on either side of PCIe; same outputs, same FLOPs counted"}
-            del xdev, xl
         # restore the resident weights for anything that follows
         del hostbuf
 
@@ -1059,6 +1111,8 @@ def main():
         line["prune_large"] = prune_large
     if e2e:
         line["e2e"] = e2e
+    if implicit_plan:
+        line["implicit_plan"] = implicit_plan
     if not args.no_cpu and world == 1:
         orc = ge.load_oracle()
         line["cpu_baseline"] = cpu_baseline(spfy, orc, gemms, 0 if args.dtype == "fp16" else 1)

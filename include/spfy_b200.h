@@ -222,6 +222,14 @@ SPFY_API int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problem
  * replicas <= 15; replica pointers 16-byte aligned; beta != 0 still reads problems[i].C only. */
 SPFY_API int spfy_spmma_plan_create_replicated(int dtype, const spfy_spmma_problem* problems, size_t count,
                                                size_t replicas, void* const* replica_D, spfy_spmma_plan_t* plan);
+/* A plan whose problems may be convolution layers (a whole network's table with the 3 x 3 layers never unfolded):
+ * convs[i] != NULL makes problem i the implicit GEMM of spfy_spmma_conv -- problems[i].B is then the NHWC activation
+ * tensor X, n / k follow from the descriptor (problems[i].n, .k, .ldb and the transpose bits of .opB are ignored;
+ * SPFY_OUT_T in .opB still selects the NHWC output of spfy_spmma_conv_nhwc), comp_vals / meta hold the weights with K in
+ * (kh, kw, c) order.  convs == NULL or convs[i] == NULL: as spfy_spmma_plan_create.  Descriptors are read at creation
+ * only.  Results are bitwise those of the single calls. */
+SPFY_API int spfy_spmma_plan_create_conv(int dtype, const spfy_spmma_problem* problems,
+                                         const spfy_conv_desc* const* convs, size_t count, spfy_spmma_plan_t* plan);
 SPFY_API int spfy_spmma_plan_run(spfy_spmma_plan_t plan, spfy_stream_t stream);
 SPFY_API int spfy_spmma_plan_launches(spfy_spmma_plan_t plan); /* kernel launches per run */
 /* introspection / profiling: run one of the plan's launches, or describe it */

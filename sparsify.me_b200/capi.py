@@ -59,6 +59,7 @@ SIGNATURES = {
     "spfy_permute_conv_weights": (c_int, [_P, _P, _SZ, _SZ, _SZ, _SZ, _P]),
     "spfy_spmma_plan_create": (c_int, [c_int, _P, _SZ, POINTER(c_void_p)]),
     "spfy_spmma_plan_create_replicated": (c_int, [c_int, _P, _SZ, _SZ, _P, POINTER(c_void_p)]),
+    "spfy_spmma_plan_create_conv": (c_int, [c_int, _P, _P, _SZ, POINTER(c_void_p)]),
     "spfy_spmma_plan_run": (c_int, [_P, _P]),
     "spfy_spmma_plan_launches": (c_int, [_P]),
     "spfy_spmma_plan_run_launch": (c_int, [_P, c_int, _P]),

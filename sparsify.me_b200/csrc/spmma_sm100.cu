@@ -902,6 +902,29 @@ uint32_t res_tiles(const ProblemDev& d) { return (d.resident == 2u ? d.G : d.m_t
 uint32_t res_values_bytes(const ProblemDev& d) { return res_tiles(d) * res_rows(d) * 128u; }
 uint32_t res_meta_bytes(const ProblemDev& d) { return res_tiles(d) * res_rows(d) * 16u; }
 
+// a convolution layer as a GEMM problem: n and k follow from the descriptor, B is the NHWC activation tensor (opB = T:
+// a B stage is [128 positions][128 k], gathered by the im2col tensor map)
+int conv_problem(int dtype, const spfy_conv_desc* conv, size_t m, float alpha, const void* comp_vals, const void* meta,
+                 const void* X, float beta, const void* C, size_t ldc, void* D, size_t ldd, bool out_t, const char* who,
+                 HostProblem* out) {
+  if (!conv) return fail(SPFY_E_INVALID, "%s: null descriptor", who);
+  const spfy_conv_desc& c = *conv;
+  if (!c.batch || !c.h || !c.w || !c.c || !c.kh || !c.kw || !c.stride)
+    return fail(SPFY_E_INVALID, "%s: empty dimension in the descriptor", who);
+  if (c.c % 64) return fail(SPFY_E_UNSUPPORTED, "%s: channels must be a multiple of 64 (got %zu): unfold explicitly", who, c.c);
+  if (c.h + 2 * c.pad < c.kh || c.w + 2 * c.pad < c.kw) return fail(SPFY_E_INVALID, "%s: filter larger than the padded image", who);
+  if (c.kh > 16 || c.kw > 16 || c.pad > 8 || c.stride > 8)
+    return fail(SPFY_E_UNSUPPORTED, "%s: filter / padding / stride outside what the im2col tensor map encodes", who);
+  if ((uintptr_t)X % 16) return fail(SPFY_E_INVALID, "%s: activations must be 16-byte aligned", who);
+  const size_t ho = (c.h + 2 * c.pad - c.kh) / c.stride + 1, wo = (c.w + 2 * c.pad - c.kw) / c.stride + 1;
+  const size_t n = c.batch * ho * wo, k = c.kh * c.kw * c.c;
+  HostProblem h{SPFY_OP_T, m, n, k, comp_vals, meta, X, C, D, /*ldb*/ k, ldc, ldd, alpha, beta};
+  h.conv = conv;
+  h.out_t = out_t;
+  *out = h;
+  return validate(dtype, h, who);
+}
+
 struct Plan {
   int dtype = 0;
   ProblemDev* d_table = nullptr;  // all launches back to back
@@ -993,22 +1016,10 @@ int spfy_spmma_conv_nhwc(int dtype, const spfy_conv_desc* conv, size_t m, float 
 static int spmma_conv_impl(int dtype, const spfy_conv_desc* conv, size_t m, float alpha, const void* comp_vals,
                            const void* meta, const void* X, float beta, const void* C, size_t ldc, void* D, size_t ldd,
                            bool out_t, spfy_stream_t stream) {
-  if (!conv) return fail(SPFY_E_INVALID, "spmma_conv: null descriptor");
-  const spfy_conv_desc& c = *conv;
-  if (!c.batch || !c.h || !c.w || !c.c || !c.kh || !c.kw || !c.stride)
-    return fail(SPFY_E_INVALID, "spmma_conv: empty dimension in the descriptor");
-  if (c.c % 64) return fail(SPFY_E_UNSUPPORTED, "spmma_conv: channels must be a multiple of 64 (got %zu): unfold explicitly", c.c);
-  if (c.h + 2 * c.pad < c.kh || c.w + 2 * c.pad < c.kw) return fail(SPFY_E_INVALID, "spmma_conv: filter larger than the padded image");
-  if (c.kh > 16 || c.kw > 16 || c.pad > 8 || c.stride > 8)
-    return fail(SPFY_E_UNSUPPORTED, "spmma_conv: filter / padding / stride outside what the im2col tensor map encodes");
-  if ((uintptr_t)X % 16) return fail(SPFY_E_INVALID, "spmma_conv: activations must be 16-byte aligned");
-  const size_t ho = (c.h + 2 * c.pad - c.kh) / c.stride + 1, wo = (c.w + 2 * c.pad - c.kw) / c.stride + 1;
-  const size_t n = c.batch * ho * wo, k = c.kh * c.kw * c.c;
-  HostProblem h{SPFY_OP_T, m, n, k, comp_vals, meta, X, C, D, /*ldb*/ k, ldc, ldd, alpha, beta};
-  h.conv = conv;
-  h.out_t = out_t;
-  int rc = validate(dtype, h, "spmma_conv");
+  HostProblem h;
+  int rc = conv_problem(dtype, conv, m, alpha, comp_vals, meta, X, beta, C, ldc, D, ldd, out_t, "spmma_conv", &h);
   if (rc) return rc;
+  const size_t n = h.n;
   if (m == 0 || n == 0) return SPFY_OK;
   DeviceInfo di;
   rc = device_info(&di);
@@ -1038,12 +1049,17 @@ static void plan_free(Plan* plan) {
   if (plan->d_rep) cudaFree(plan->d_rep);
   delete plan;
 }
-static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_t count, size_t n_rep, void* const* rep_d,
-                            spfy_spmma_plan_t* out);
+static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, const spfy_conv_desc* const* convs, size_t count,
+                            size_t n_rep, void* const* rep_d, spfy_spmma_plan_t* out);
 
 int spfy_spmma_plan_create(int dtype, const spfy_spmma_problem* problems, size_t count,
                            spfy_spmma_plan_t* out) {
-  return plan_create_impl(dtype, problems, count, 0, nullptr, out);
+  return plan_create_impl(dtype, problems, nullptr, count, 0, nullptr, out);
+}
+
+int spfy_spmma_plan_create_conv(int dtype, const spfy_spmma_problem* problems, const spfy_conv_desc* const* convs,
+                                size_t count, spfy_spmma_plan_t* out) {
+  return plan_create_impl(dtype, problems, convs, count, 0, nullptr, out);
 }
 
 int spfy_spmma_plan_create_replicated(int dtype, const spfy_spmma_problem* problems, size_t count, size_t replicas,
@@ -1054,11 +1070,22 @@ int spfy_spmma_plan_create_replicated(int dtype, const spfy_spmma_problem* probl
     if (problems && problems[i / replicas].m && problems[i / replicas].n && (!replica_d[i] || (uintptr_t)replica_d[i] % 16))
       return fail(SPFY_E_INVALID, "spmma_plan_create_replicated: replica %zu of problem %zu is null or not 16-byte aligned",
                   i % replicas, i / replicas);
-  return plan_create_impl(dtype, problems, count, replicas, replica_d, out);
+  return plan_create_impl(dtype, problems, nullptr, count, replicas, replica_d, out);
 }
 
-static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_t count, size_t n_rep, void* const* rep_d,
-                            spfy_spmma_plan_t* out) {
+// problem i of a plan as the host sees it (a convolution layer when convs[i] is given: B = X, n / k / ldb / opB from the
+// descriptor, the SPFY_OUT_T bit of opB still selects the NHWC output)
+static int plan_problem(int dtype, const spfy_spmma_problem& q, const spfy_conv_desc* conv, HostProblem* h) {
+  if (conv)
+    return conv_problem(dtype, conv, q.m, q.alpha, q.comp_vals, q.meta, q.B, q.beta, q.C, q.ldc, q.D, q.ldd, out_t_of(q.opB),
+                        "spmma_plan_create", h);
+  *h = HostProblem{op_of(q.opB), q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
+  h->out_t = out_t_of(q.opB);
+  return validate(dtype, *h, "spmma_plan_create");
+}
+
+static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, const spfy_conv_desc* const* convs, size_t count,
+                            size_t n_rep, void* const* rep_d, spfy_spmma_plan_t* out) {
   if (!out) return fail(SPFY_E_INVALID, "spmma_plan_create: null plan pointer");
   *out = nullptr;
   if (count && !problems) return fail(SPFY_E_INVALID, "spmma_plan_create: null problem list");
@@ -1094,10 +1121,10 @@ static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_
       std::vector<size_t> members;
       for (size_t i = 0; i < count; ++i) {
         const spfy_spmma_problem& q = problems[i];
-        HostProblem h{op_of(q.opB), q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
-        h.out_t = out_t_of(q.opB);
-        if (h.opB != opB) continue;
-        rc = validate(dtype, h, "spmma_plan_create");
+        const spfy_conv_desc* cv = convs ? convs[i] : nullptr;
+        if ((cv ? SPFY_OP_T : op_of(q.opB)) != opB) continue;
+        HostProblem h;
+        rc = plan_problem(dtype, q, cv, &h);
         if (rc) {
           plan_free(plan);
           return rc;
@@ -1106,13 +1133,16 @@ static int plan_create_impl(int dtype, const spfy_spmma_problem* problems, size_
         if (classify(h, true, di.sm_count) != cls) continue;
         members.push_back(i);
       }
+      auto k_of = [&](size_t i) {
+        const spfy_conv_desc* cv = convs ? convs[i] : nullptr;
+        return cv ? cv->kh * cv->kw * cv->c : problems[i].k;
+      };
       std::stable_sort(members.begin(), members.end(), [&](size_t a, size_t b) {
-        return ceil_div(problems[a].k, 128) > ceil_div(problems[b].k, 128);
+        return ceil_div(k_of(a), 128) > ceil_div(k_of(b), 128);
       });
       for (size_t i : members) {
-        const spfy_spmma_problem& q = problems[i];
-        HostProblem h{op_of(q.opB), q.m, q.n, q.k, q.comp_vals, q.meta, q.B, q.C, q.D, q.ldb, q.ldc, q.ldd, q.alpha, q.beta};
-        h.out_t = out_t_of(q.opB);
+        HostProblem h;
+        (void)plan_problem(dtype, problems[i], convs ? convs[i] : nullptr, &h);  // validated above
         ProblemDev d;
         rc = fill_problem(&d, dtype, h, cls);
         if (rc) {

@@ -176,30 +176,57 @@ class SpmmaPlan:
     beta, op_b, out_t (out is then [n, m], the transposed result; beta must be 0).  The plan keeps the tensors alive.
     Optional `replicas` per problem: device addresses (ints) of further copies of `out` (same shape and row pitch) that
     the epilogue stores every tile to as well -- e.g. the slab of this rank in the gather arena of every peer GPU
-    (spfy_spmma_plan_create_replicated: the fused output gather); every problem must name the same number of them."""
+    (spfy_spmma_plan_create_replicated: the fused output gather); every problem must name the same number of them.
+    A problem with `conv=(kh, kw, stride, pad)` is a convolution layer (spfy_spmma_plan_create_conv): `b` is then the
+    NHWC activation tensor [batch, h, w, ch] and comp holds the weights with K in (kh, kw, ch) order; the unfolded
+    operand is never built.  `out` is [m, batch*ho*wo], or NHWC [batch, ho, wo, m] with out_t."""
 
     def __init__(self, problems):
         self._keep = problems
         n = len(problems)
         arr = (capi.SpmmaProblem * n)()
+        convs = (capi.ConvDesc * max(n, 1))()
+        conv_ptrs = (ctypes.c_void_p * max(n, 1))()
+        any_conv = False
         dtype = None
         for i, q in enumerate(problems):
             comp, b, out = q["comp"], q["b"], q["out"]
             c = q.get("c")
             op_b = q.get("op_b", capi.OP_N)
             dtype = comp.dtype
-            nn = b.shape[1] if op_b == capi.OP_N else b.shape[0]
+            ldb = b.stride(0)
+            ldd = out.stride(0)
+            if q.get("conv"):
+                kh, kw, stride, pad = q["conv"]
+                assert b.dim() == 4 and b.is_contiguous()
+                nb, h, w, ch = b.shape
+                assert comp.cols == kh * kw * ch
+                convs[i] = capi.ConvDesc(nb, h, w, ch, kh, kw, stride, pad)
+                conv_ptrs[i] = ctypes.addressof(convs[i])
+                any_conv = True
+                op_b, ldb = capi.OP_T, comp.cols
+                nn = nb * ((h + 2 * pad - kh) // stride + 1) * ((w + 2 * pad - kw) // stride + 1)
+                if q.get("out_t"):
+                    assert out.is_contiguous()
+                    ldd = comp.rows
+            else:
+                nn = b.shape[1] if op_b == capi.OP_N else b.shape[0]
             if q.get("out_t"):  # `out` is [n, m]: the transposed result
                 op_b |= capi.OUT_T
             arr[i] = capi.SpmmaProblem(op_b, comp.rows, nn, comp.cols, comp.vals.data_ptr(), comp.meta.data_ptr(),
-                                       b.data_ptr(), b.stride(0), c.data_ptr() if c is not None else None,
-                                       c.stride(0) if c is not None else 0, out.data_ptr(), out.stride(0),
+                                       b.data_ptr(), ldb, c.data_ptr() if c is not None else None,
+                                       c.stride(0) if c is not None else 0, out.data_ptr(), ldd,
                                        float(q.get("alpha", 1.0)), float(q.get("beta", 0.0)))
         self._h = ctypes.c_void_p()
         nrep = len(problems[0].get("replicas", ())) if n else 0
         if any(len(q.get("replicas", ())) != nrep for q in problems):
             raise ValueError("SpmmaPlan: every problem needs the same number of replicas")
-        if nrep:
+        if any_conv:
+            if nrep:
+                raise ValueError("SpmmaPlan: replicas and convolution problems cannot be combined")
+            capi.spfy_spmma_plan_create_conv(_DT[dtype], ctypes.cast(arr, ctypes.c_void_p), ctypes.cast(conv_ptrs, ctypes.c_void_p),
+                                             n, ctypes.byref(self._h))
+        elif nrep:
             rep = (ctypes.c_void_p * (n * nrep))(*[int(a) for q in problems for a in q["replicas"]])
             capi.spfy_spmma_plan_create_replicated(_DT[dtype], ctypes.cast(arr, ctypes.c_void_p), n, nrep,
                                                    ctypes.cast(rep, ctypes.c_void_p), ctypes.byref(self._h))

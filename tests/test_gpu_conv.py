@@ -119,3 +119,46 @@ def test_implicit_gemm_rejects_what_it_cannot_gather(spfy, cuda):
     with pytest.raises(spfy.SpfyError) as e:
         spfy.spmma_conv(comp, x, 7, 7, stride=2, pad=3)
     assert e.value.code == spfy.capi.E_UNSUPPORTED
+
+
+def test_plan_mixes_convolution_layers_and_matrices(spfy, cuda):
+    """spfy_spmma_plan_create_conv: a table whose 3 x 3 layers are implicit GEMMs next to plain matrix problems (both
+    operand orientations) in ONE plan -- every output bitwise the single call's, NHWC outputs bitwise the transpose, and the
+    plan issues one launch per (class, orientation) present, whatever the mix."""
+    tdt = torch.float16
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(77)
+    problems, wants = [], []
+    for nb, h, w, c, cout, kh, kw, stride, pad, nhwc in [(4, 56, 56, 64, 64, 3, 3, 1, 1, False), (4, 56, 56, 64, 128, 3, 3, 2, 1, False),
+                                                          (2, 28, 28, 128, 256, 3, 3, 1, 1, True), (8, 7, 7, 512, 512, 3, 3, 1, 1, False),
+                                                          (3, 10, 12, 64, 72, 3, 3, 1, 1, True), (2, 56, 56, 64, 128, 1, 1, 2, 0, False)]:
+        x = (torch.rand(nb, h, w, c, device=cuda, generator=gen) * 2 - 1).to(tdt)
+        wt = (torch.rand(cout, c * kh * kw, device=cuda, generator=gen) * 2 - 1).to(tdt)
+        comp = spfy.prune24(spfy.permute_conv_weights(wt, c, kh, kw))
+        want = spfy.spmma_conv(comp, x, kh, kw, stride=stride, pad=pad)
+        ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+        out = torch.zeros(nb, ho, wo, cout, dtype=tdt, device=cuda) if nhwc else torch.zeros_like(want)
+        problems.append(dict(comp=comp, b=x, out=out, conv=(kh, kw, stride, pad), out_t=nhwc))
+        wants.append(want.t().reshape(nb, ho, wo, cout) if nhwc else want)
+    for i, (M, K, N) in enumerate([(64, 147, 19008), (512, 200, 1600), (256, 2304, 392), (128, 1152, 520)]):
+        a = (torch.rand(M, K, device=cuda, generator=gen) * 2 - 1).to(tdt)
+        op_t = i % 2 == 1
+        b = (torch.rand((N, K) if op_t else (K, N), device=cuda, generator=gen) * 2 - 1).to(tdt)
+        comp = spfy.prune24(a)
+        op_b = spfy.OP_T if op_t else spfy.OP_N
+        wants.append(spfy.spmma_compressed(comp, b, op_b=op_b))
+        problems.append(dict(comp=comp, b=b, out=torch.zeros(M, N, dtype=tdt, device=cuda), op_b=op_b))
+    plan = spfy.SpmmaPlan(problems)
+    plan.run()
+    plan.run()
+    torch.cuda.synchronize()
+    for q, want in zip(problems, wants):
+        assert torch.equal(q["out"], want)
+    assert 1 <= plan.launches <= 12
+    plan.close()
+    # a bad descriptor is refused at creation
+    bad = dict(problems[0])
+    bad["b"] = torch.zeros(4, 56, 56, 48, dtype=tdt, device=cuda)  # channels not a multiple of 64
+    bad["comp"] = spfy.prune24(torch.zeros(64, 9 * 48, dtype=tdt, device=cuda))
+    with pytest.raises(spfy.SpfyError):
+        spfy.SpmmaPlan([bad])
