@@ -548,57 +548,91 @@ prune24_batched_kernel(const __grid_constant__ Prune24Batch Bt) {
 __constant__ uint16_t c_tile_pattern[90] = {
     0xc3c3, 0xa5c3, 0x96c3, 0x69c3, 0x5ac3, 0x3cc3, 0xc3a5, 0xa5a5, 0x96a5, 0x69a5, 0x5aa5, 0x3ca5, 0xc396, 0xa596, 0x9696, 0x6996, 0x5a96, 0x3c96, 0xc369, 0xa569, 0x9669, 0x6969, 0x5a69, 0x3c69, 0xc35a, 0xa55a, 0x965a, 0x695a, 0x5a5a, 0x3c5a, 0xc33c, 0xa53c, 0x963c, 0x693c, 0x5a3c, 0x3c3c, 0xcc33, 0xaa55, 0x9966, 0x6699, 0x55aa, 0x33cc, 0xac35, 0xca35, 0xac53, 0xca53, 0x9c36, 0xc936, 0x9c63, 0xc963, 0x6c39, 0xc639, 0x6c93, 0xc693, 0x5c3a, 0xc53a, 0x5ca3, 0xc5a3, 0x9a56, 0xa956, 0x9a65, 0xa965, 0x6a59, 0xa659, 0x6a95, 0xa695, 0x3a5c, 0xa35c, 0x3ac5, 0xa3c5, 0x596a, 0x956a, 0x59a6, 0x95a6, 0x396c, 0x936c, 0x39c6, 0x93c6, 0x569a, 0x659a, 0x56a9, 0x65a9, 0x369c, 0x639c, 0x36c9, 0x63c9, 0x35ac, 0x53ac, 0x35ca, 0x53ca};
 
+// two fp32 additions in one instruction (FADD2): every sum of the selection exists once for the upper row pair of a
+// tile and once for the lower one, so the two travel as the halves of one 64-bit register pair
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc;\n"
+      "  mov.b64 ra, {%2, %3};\n"
+      "  mov.b64 rb, {%4, %5};\n"
+      "  add.rn.f32x2 rc, ra, rb;\n"
+      "  mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+
 // returns the candidate code (index into c_tile_pattern); the selection is tracked as small integers and
 // turned into a keep mask once -- the first version carried 16-bit patterns through every compare and was
-// integer-ALU bound (600 instructions per tile)
+// integer-ALU bound (600 instructions per tile).  Third version: the 115 fp32 additions are 48 packed ones and 19
+// scalar ones -- .x of every pair belongs to rows 0/1, .y to rows 2/3:
+//   rpA[i] = (rp[0][i], rp[2][i]),  rpB[i] = (rp[1][i], rp[3][i]),  X(a, b) = rpA[a] + rpB[b] = (rp0[a] + rp1[b], rp2[a] + rp3[b])
 __device__ __forceinline__ uint32_t tile_select(const float (&m)[16]) {
   // column-pair index -> (c0, c1); the complement of pair i is pair 5 - i
   constexpr int C0[6] = {0, 0, 1, 0, 1, 2}, C1[6] = {1, 2, 2, 3, 3, 3};
-  float rp[4][6];
+  float2 rpA[6], rpB[6];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) rp[r][i] = __fadd_rn(m[r * 4 + C0[i]], m[r * 4 + C1[i]]);
+  for (int i = 0; i < 6; ++i) {
+    rpA[i] = add2(make_float2(m[C0[i]], m[8 + C0[i]]), make_float2(m[C1[i]], m[8 + C1[i]]));
+    rpB[i] = add2(make_float2(m[4 + C0[i]], m[12 + C0[i]]), make_float2(m[4 + C1[i]], m[12 + C1[i]]));
+  }
   // complementary class: x and y maximised independently, first maximum wins
-  float b01 = __fadd_rn(rp[0][0], rp[1][5]), b23 = __fadd_rn(rp[2][0], rp[3][5]);
+  float2 b = add2(rpA[0], rpB[5]);
   uint32_t x01 = 0, y23 = 0;
 #pragma unroll
   for (int x = 1; x < 6; ++x) {
-    const float g = __fadd_rn(rp[0][x], rp[1][5 - x]), h = __fadd_rn(rp[2][x], rp[3][5 - x]);
-    const bool pg = g > b01, ph = h > b23;
-    b01 = pg ? g : b01;
-    x01 = pg ? (uint32_t)x : x01;
-    b23 = ph ? h : b23;
+    const float2 g = add2(rpA[x], rpB[5 - x]);
+    const bool pg = g.x > b.x, ph = g.y > b.y;
+    b.x = pg ? g.x : b.x;
+    x01 = pg ? (uint32_t)(6 * x) : x01;
+    b.y = ph ? g.y : b.y;
     y23 = ph ? (uint32_t)x : y23;
   }
-  float best = __fadd_rn(b01, b23);
-  uint32_t code = x01 * 6u + y23;
-  // same class
+  float best = __fadd_rn(b.x, b.y);
+  uint32_t code = x01 + y23;
+  // same class: (rp0[x] + rp1[x]) + (rp2[5-x] + rp3[5-x])
+  {
+    float2 d[6];
 #pragma unroll
-  for (int x = 0; x < 6; ++x) {
-    const float s = __fadd_rn(__fadd_rn(rp[0][x], rp[1][x]), __fadd_rn(rp[2][5 - x], rp[3][5 - x]));
-    const bool p = s > best;
-    best = p ? s : best;
-    code = p ? (uint32_t)(36 + x) : code;
+    for (int x = 0; x < 6; ++x) d[x] = add2(rpA[x], rpB[x]);
+#pragma unroll
+    for (int x = 0; x < 6; ++x) {
+      const float s = __fadd_rn(d[x].x, d[5 - x].y);
+      const bool p = s > best;
+      best = p ? s : best;
+      code = p ? (uint32_t)(36 + x) : code;
+    }
   }
-  // mixed class
+  // mixed class: group (i, j) takes X(j, i).x / X(i, j).x for rows 0/1 and X(5-i, 5-j).y / X(5-j, 5-i).y for rows 2/3
+  float2 X[6][6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+      if (a != c && c != 5 - a) X[a][c] = add2(rpA[a], rpB[c]);
   int g = 0;
+  float d01 = 0.f, d23 = 0.f;  // stay 0 unless a mixed candidate wins
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = i + 1; j < 6; ++j) {
       if (j == 5 - i) continue;
-      const float s1 = __fadd_rn(rp[0][j], rp[1][i]), s2 = __fadd_rn(rp[0][i], rp[1][j]);
-      const float t1 = __fadd_rn(rp[2][5 - i], rp[3][5 - j]), t2 = __fadd_rn(rp[2][5 - j], rp[3][5 - i]);
-      const bool sw01 = s2 > s1, sw23 = t2 > t1;
-      const float s = __fadd_rn(sw01 ? s2 : s1, sw23 ? t2 : t1);
-      const uint32_t c = (uint32_t)(42 + 4 * g) + (sw01 ? 2u : 0u) + (sw23 ? 1u : 0u);
+      const float s1 = X[j][i].x, s2 = X[i][j].x;
+      const float t1 = X[5 - i][5 - j].y, t2 = X[5 - j][5 - i].y;
+      // The order bits are only needed for the group that wins: the compares are replaced by maxima, and the winner
+      // carries s2 - s1 and t2 - t1 along (exact in sign: a difference of distinct floats never rounds to zero).  The
+      // kernel is bound by the ALU pipe (compares and selects issue every other cycle); the subtractions go down the
+      // FMA pipe, which has room.
+      const float s = __fadd_rn(fmaxf(s1, s2), fmaxf(t1, t2));
+      const float e01 = __fsub_rn(s2, s1), e23 = __fsub_rn(t2, t1);
       const bool p = s > best;
       best = p ? s : best;
-      code = p ? c : code;
+      code = p ? (uint32_t)(42 + 4 * g) : code;
+      d01 = p ? e01 : d01;
+      d23 = p ? e23 : d23;
       ++g;
     }
-  return code;
+  return code + (d01 > 0.f ? 2u : 0u) + (d23 > 0.f ? 1u : 0u);
 }
 
 template <bool BF16>
@@ -607,40 +641,98 @@ __device__ __forceinline__ float tile_mag(uint32_t bits) {
   return BF16 ? __uint_as_float(ab << 16) : __half2float(__ushort_as_half((unsigned short)ab));
 }
 
+// |x| of both halves of a word as fp32 (one mask for the two signs, no half-word extraction)
+template <bool BF16>
+__device__ __forceinline__ void tile_mag2(uint32_t w, float& lo, float& hi) {
+  if (BF16) {
+    lo = __uint_as_float((w << 16) & 0x7fff0000u);
+    hi = __uint_as_float(w & 0x7fff0000u);
+  } else {
+    const uint32_t a = w & 0x7fff7fffu;
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a));
+    lo = f.x;
+    hi = f.y;
+  }
+}
+
+// the candidate -> pattern table in shared memory: the index differs from lane to lane, and a constant-bank read with
+// divergent addresses is replayed once per distinct address
+struct TilePatterns {
+  uint16_t pat[96];
+  __device__ __forceinline__ void load() {
+    if (threadIdx.x < 90) pat[threadIdx.x] = c_tile_pattern[threadIdx.x];
+    __syncthreads();
+  }
+};
+
+// Keep masks of the four tile rows from the 16-bit pattern.  Row i's nibble k is spread so that its bits sit in the
+// sign positions of the four bytes of z[i] (k << 7 | k << 14 | k << 21 | k << 28: bits 7 / 15 / 23 / 31 = b0..b3, one
+// multiplication); PRMT's sign-replicate mode then turns (z, z) into a halfword mask, one instruction per word.
+struct TileKeep {
+  uint32_t z[4];
+  __device__ __forceinline__ explicit TileKeep(uint32_t pat) {
+    const uint32_t hi = pat >> 8;
+    z[0] = (pat & 0xfu) * 0x10204080u;
+    z[1] = (pat & 0xf0u) * 0x01020408u;
+    z[2] = (hi & 0xfu) * 0x10204080u;
+    z[3] = (hi & 0xf0u) * 0x01020408u;
+  }
+  // (inline PTX: the __byte_perm intrinsic only honours three bits of every selector nibble)
+  static __device__ __forceinline__ uint32_t sign_bytes(uint32_t z, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(z), "r"(sel));
+    return r;
+  }
+  __device__ __forceinline__ uint2 row(int i, uint2 w) const {
+    return make_uint2(w.x & sign_bytes(z[i], 0x9988u), w.y & sign_bytes(z[i], 0xbbaau));
+  }
+};
+
+// Block = 32 tile columns (one 256-byte piece of four rows per warp) x 8 tile rows; blockIdx.x walks the tile columns,
+// the tile rows are walked with stride 8 * gridDim.y -- no division anywhere (the flat index of the first version paid
+// ~60 instructions of a kernel that is issue-bound at ~400 per tile for it).
 template <bool BF16, bool VEC>
 __global__ void __launch_bounds__(256)
 prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __restrict__: out may alias in (in-place prune)
                     size_t ld_out, uint32_t rows, uint32_t cols) {
+  __shared__ TilePatterns T;
+  T.load();
   const uint32_t tiles_c = (cols + 3) / 4, tiles_r = (rows + 3) / 4;
-  const size_t total = (size_t)tiles_r * tiles_c;
-  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
-    // (a 64-bit division costs ~60 instructions of a kernel that is issue-bound at ~450 per tile)
-    const uint32_t tr = (total >> 32) == 0 ? (uint32_t)t / tiles_c : (uint32_t)(t / tiles_c);
-    const uint32_t tc = (uint32_t)(t - (size_t)tr * tiles_c);
-    const uint32_t r0 = tr * 4, c0 = tc * 4;
+  const uint32_t tc = blockIdx.x * 32u + (threadIdx.x & 31u);
+  if (tc >= tiles_c) return;
+  const uint32_t c0 = tc * 4;
+  const uint32_t tr_step = gridDim.y * 8u;
+  // the next tile of the thread is fetched before the current one is worked on: 32 bytes per thread in flight are a
+  // third of what the DRAM latency asks for at three resident blocks per SM (measured: 3.7 TB/s without)
+  auto fetch = [&](uint32_t tr, uint2 (&w)[4]) {
+    const uint32_t r0 = tr * 4;
+    const uint16_t* src = in + (size_t)r0 * ld_in + c0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      w[i] = r0 + i < rows ? *reinterpret_cast<const uint2*>(src + i * ld_in) : make_uint2(0u, 0u);  // (covers tr >= tiles_r)
+  };
+  uint2 nw[4];
+  const uint32_t tr_first = blockIdx.y * 8u + (threadIdx.x >> 5);
+  if (VEC) fetch(tr_first, nw);
+  for (uint32_t tr = tr_first; tr < tiles_r; tr += tr_step) {
+    const uint32_t r0 = tr * 4;
     float mag[16];
     if (VEC) {
       uint2 w[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        w[i] = r0 + i < rows ? *reinterpret_cast<const uint2*>(in + (size_t)(r0 + i) * ld_in + c0) : make_uint2(0u, 0u);
+      for (int i = 0; i < 4; ++i) w[i] = nw[i];
+      fetch(tr + tr_step, nw);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        mag[i * 4 + 0] = tile_mag<BF16>(w[i].x);
-        mag[i * 4 + 1] = tile_mag<BF16>(w[i].x >> 16);
-        mag[i * 4 + 2] = tile_mag<BF16>(w[i].y);
-        mag[i * 4 + 3] = tile_mag<BF16>(w[i].y >> 16);
+        tile_mag2<BF16>(w[i].x, mag[i * 4 + 0], mag[i * 4 + 1]);
+        tile_mag2<BF16>(w[i].y, mag[i * 4 + 2], mag[i * 4 + 3]);
       }
-      const uint32_t pat = c_tile_pattern[tile_select(mag)];
+      const TileKeep keep(T.pat[tile_select(mag)]);
+      uint16_t* dst = out + (size_t)r0 * ld_out + c0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (r0 + i >= rows) break;
-        const uint32_t k = pat >> (i * 4);
-        uint2 o;
-        o.x = w[i].x & ((k & 1u ? 0xffffu : 0u) | (k & 2u ? 0xffff0000u : 0u));
-        o.y = w[i].y & ((k & 4u ? 0xffffu : 0u) | (k & 8u ? 0xffff0000u : 0u));
-        *reinterpret_cast<uint2*>(out + (size_t)(r0 + i) * ld_out + c0) = o;
+        *reinterpret_cast<uint2*>(dst + i * ld_out) = keep.row(i, w[i]);
       }
     } else {
       uint16_t v[16];
@@ -652,7 +744,7 @@ prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __re
           v[i * 4 + j] = ok ? in[(size_t)(r0 + i) * ld_in + c0 + j] : (uint16_t)0;
           mag[i * 4 + j] = tile_mag<BF16>(v[i * 4 + j]);
         }
-      const uint32_t pat = c_tile_pattern[tile_select(mag)];
+      const uint32_t pat = T.pat[tile_select(mag)];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -677,35 +769,35 @@ __device__ __host__ __forceinline__ size_t tile_fused_total(const Prune24Params&
   return (size_t)((P.dom_rows + 3u) / 4u) * *tiles_c;
 }
 
-// one warp, 32 consecutive tiles starting at `base` (a multiple of 32)
+// one warp, 32 consecutive tiles of one tile row: lane's tile is (tr, tc) (inactive lanes only take part in the shuffles)
+// the four rows of tile (tr, tc); padding of the iteration domain reads as +0
+__device__ __forceinline__ void tile_fused_fetch(const Prune24Params& P, uint32_t tr, uint32_t tc, bool active, uint2 (&w)[4]) {
+  const uint32_t r0 = tr * 4u, c0 = tc * 4u;
+  const bool col_ok = active && c0 < P.cols;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = (col_ok && r0 + i < P.rows) ? *reinterpret_cast<const uint2*>(P.in + (size_t)(r0 + i) * P.ld_in + c0)
+                                       : make_uint2(0u, 0u);
+}
+
 template <bool BF16>
-__device__ __forceinline__ void tile_fused_warp(const Prune24Params& P, size_t base, size_t total, uint32_t tiles_c,
-                                                uint32_t lane) {
+__device__ __forceinline__ void tile_fused_tiles(const Prune24Params& P, const TilePatterns& T, uint32_t tr, uint32_t tc,
+                                                 bool active, uint32_t lane, const uint2 (&w)[4]) {
   {
-    const size_t t = base + lane;
-    const bool active = t < total;
-    const uint32_t tr = !active ? 0u : (total >> 32) == 0 ? (uint32_t)t / tiles_c : (uint32_t)(t / tiles_c);
-    const uint32_t tc = active ? (uint32_t)(t - (size_t)tr * tiles_c) : 0u;
     const uint32_t r0 = tr * 4u, c0 = tc * 4u;
     const bool col_ok = active && c0 < P.cols;
-    uint2 w[4];
     float mag[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      w[i] = (col_ok && r0 + i < P.rows) ? *reinterpret_cast<const uint2*>(P.in + (size_t)(r0 + i) * P.ld_in + c0)
-                                         : make_uint2(0u, 0u);
-      mag[i * 4 + 0] = tile_mag<BF16>(w[i].x);
-      mag[i * 4 + 1] = tile_mag<BF16>(w[i].x >> 16);
-      mag[i * 4 + 2] = tile_mag<BF16>(w[i].y);
-      mag[i * 4 + 3] = tile_mag<BF16>(w[i].y >> 16);
+      tile_mag2<BF16>(w[i].x, mag[i * 4 + 0], mag[i * 4 + 1]);
+      tile_mag2<BF16>(w[i].y, mag[i * 4 + 2], mag[i * 4 + 3]);
     }
-    const uint32_t pat = c_tile_pattern[tile_select(mag)];
+    const TileKeep keep(T.pat[tile_select(mag)]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t row = r0 + i;
-      const uint32_t k = pat >> (i * 4);
-      const uint32_t lo = w[i].x & ((k & 1u ? 0xffffu : 0u) | (k & 2u ? 0xffff0000u : 0u));
-      const uint32_t hi = w[i].y & ((k & 4u ? 0xffffu : 0u) | (k & 8u ? 0xffff0000u : 0u));
+      const uint2 kept = keep.row(i, w[i]);
+      const uint32_t lo = kept.x, hi = kept.y;
       if (P.out_dense && col_ok && row < P.rows)
         *reinterpret_cast<uint2*>(P.out_dense + (size_t)row * P.ld_out + c0) = make_uint2(lo, hi);
       uint32_t i0, i1;
@@ -733,15 +825,42 @@ __device__ __forceinline__ void tile_fused_warp(const Prune24Params& P, size_t b
   }
 }
 
+// 32 consecutive tiles starting at flat index `base` (a multiple of 32; tiles_c is one too, or the row is the last)
+template <bool BF16>
+__device__ __forceinline__ void tile_fused_warp(const Prune24Params& P, const TilePatterns& T, size_t base, size_t total,
+                                                uint32_t tiles_c, uint32_t lane) {
+  const size_t t = base + lane;
+  const bool active = t < total;
+  const uint32_t tr = !active ? 0u : (total >> 32) == 0 ? (uint32_t)t / tiles_c : (uint32_t)(t / tiles_c);
+  const uint32_t tc = active ? (uint32_t)(t - (size_t)tr * tiles_c) : 0u;
+  uint2 w[4];
+  tile_fused_fetch(P, tr, tc, active, w);
+  tile_fused_tiles<BF16>(P, T, tr, tc, active, lane, w);
+}
+
+// grid: x = 32-tile column chunks, y walks the tile rows with stride 8 * gridDim.y (no division, like prune24_tile_kernel)
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
+  __shared__ TilePatterns T;
+  T.load();
   uint32_t tiles_c;
   const size_t total = tile_fused_total(P, &tiles_c);
+  const uint32_t tiles_r = (uint32_t)(total / tiles_c);
   const uint32_t lane = threadIdx.x & 31u;
-  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-  for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += nthreads)
-    tile_fused_warp<BF16>(P, base, total, tiles_c, lane);
+  const uint32_t tc = blockIdx.x * 32u + lane;
+  const bool col_in = tc < tiles_c;
+  const uint32_t tcc = col_in ? tc : 0u, tr_step = gridDim.y * 8u;
+  uint32_t tr = blockIdx.y * 8u + (threadIdx.x >> 5);
+  uint2 nw[4];
+  tile_fused_fetch(P, tr, tcc, col_in && tr < tiles_r, nw);
+  for (; tr < tiles_r; tr += tr_step) {
+    uint2 w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = nw[i];
+    tile_fused_fetch(P, tr + tr_step, tcc, col_in && tr + tr_step < tiles_r, nw);  // next tile in flight under this one
+    tile_fused_tiles<BF16>(P, T, tr, tcc, col_in, lane, w);
+  }
 }
 
 // TILE prune + compress of many matrices in one launch (what sparsifyme::spmma asks for, spmma.hxx:86, over a whole
@@ -749,6 +868,8 @@ prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 prune24_tile_batched_kernel(const __grid_constant__ Prune24Batch Bt) {
+  __shared__ TilePatterns T;
+  T.load();
   const uint32_t tiles = Bt.tile_prefix[Bt.count];
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -764,7 +885,7 @@ prune24_tile_batched_kernel(const __grid_constant__ Prune24Batch Bt) {
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
       const size_t base = first + i * 256 + (threadIdx.x & ~31u);
-      if (base < total) tile_fused_warp<BF16>(P, base, total, tiles_c, lane);
+      if (base < total) tile_fused_warp<BF16>(P, T, base, total, tiles_c, lane);
     }
   }
 }
@@ -992,17 +1113,31 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
       int rcf = fill_prune24(&P, layout, src, ld_in, out_dense, ld_out, comp_vals, meta, nullptr, rows, cols);
       if (rcf) return rcf;
       const size_t dom_cols = P.tile_order ? (size_t)P.k_tiles * 128 : cols;
-      int gridf = 1;
-      rcf = grid_for(ceil_div((size_t)P.dom_rows, 4) * (dom_cols / 4), 256, &gridf);
+      int blocksf = 1;
+      rcf = grid_for(ceil_div((size_t)P.dom_rows, 4) * (dom_cols / 4), 256, &blocksf);
       if (rcf) return rcf;
+      const size_t fx = ceil_div(dom_cols / 4, 32), fy_all = ceil_div(ceil_div((size_t)P.dom_rows, 4), 8);
+      size_t fy = ceil_div((size_t)blocksf, fx);
+      if (fy > fy_all) fy = fy_all;
+      if (fy > 65535) fy = 65535;
+      if (fy == 0) fy = 1;
+      const dim3 gridf((unsigned)fx, (unsigned)fy);
       if (dtype == SPFY_BF16) prune24_tile_fused_kernel<true><<<gridf, 256, 0, s>>>(P);
       else prune24_tile_fused_kernel<false><<<gridf, 256, 0, s>>>(P);
       SPFY_LAUNCH_OK("prune24_tile_fused_kernel");
       return SPFY_OK;
     }
-    int grid = 1;
-    int rc = grid_for(ceil_div(rows, 4) * ceil_div(cols, 4), 256, &grid);
+    int blocks = 1;
+    int rc = grid_for(ceil_div(rows, 4) * ceil_div(cols, 4), 256, &blocks);  // cap: two waves of resident warps
     if (rc) return rc;
+    // 32 tile columns x 8 tile rows per block; the rows are walked with a stride when the cap binds
+    const size_t gx = ceil_div(ceil_div(cols, 4), 32), gy_all = ceil_div(ceil_div(rows, 4), 8);
+    if (gx >= (1u << 31)) return fail(SPFY_E_UNSUPPORTED, "prune24: too many columns");
+    size_t gy = ceil_div((size_t)blocks, gx);
+    if (gy > gy_all) gy = gy_all;
+    if (gy > 65535) gy = 65535;
+    if (gy == 0) gy = 1;
+    const dim3 grid((unsigned)gx, (unsigned)gy);
     const uint32_t r32 = (uint32_t)rows, c32 = (uint32_t)cols;
     uint16_t* od = (uint16_t*)out_dense;
     if (dtype == SPFY_BF16) {

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--tag", default="")
     ap.add_argument("--only-large", action="store_true", help="just the 401408 x 576 SM100 case (what ncu wraps)")
+    ap.add_argument("--tile", action="store_true", help="TILE_MAG (the mode spmma.hxx:86 requests): dense prune alone, and prune + compress")
     args = ap.parse_args()
     import torch
     spfy = ge.load_package()
@@ -50,6 +51,20 @@ def main():
         return e0.elapsed_time(e1) / args.reps * 1e3
 
     print("tag,case,rows,cols,layout,dense_out,us,GBs,frac_hbm")
+    if args.tile:
+        # TILE needs the dense pruned matrix as an output: 2 B read + 2 B written per element (+ 1.125 compressed)
+        for rows, cols in ((16384, 16384), (12544 * 32, 576), (4096, 4608)):
+            w = (torch.rand(rows, cols, device=dev) * 2 - 1).to(tdt)
+            out = torch.empty_like(w)
+            us = timed(lambda: spfy.prune24(w, out_dense=out, mode=spfy.PRUNE_TILE_MAG, compress=False))
+            by = 4.0 * rows * cols
+            print(f"{args.tag},tile-dense,{rows},{cols},-,1,{us:.1f},{by/us/1e3:.0f},{by/us/1e3/hbm:.3f}", flush=True)
+            comp = spfy.alloc_compressed(tdt, rows, cols, dev)
+            us = timed(lambda: spfy.prune24(w, out_dense=out, mode=spfy.PRUNE_TILE_MAG, out=comp))
+            by = 5.125 * rows * cols
+            print(f"{args.tag},tile-compress,{rows},{cols},sm100,1,{us:.1f},{by/us/1e3:.0f},{by/us/1e3/hbm:.3f}", flush=True)
+            del w, out, comp
+        return
     cases = ((12544 * 32, 576),) if args.only_large else ((12544 * 32, 576), (16384, 16384), (4096, 4608))
     for rows, cols in cases:
         w = (torch.rand(rows, cols, device=dev) * 2 - 1).to(tdt)
