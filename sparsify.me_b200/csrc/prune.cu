@@ -648,8 +648,8 @@ __device__ __forceinline__ void tile_mag2(uint32_t w, float& lo, float& hi) {
     lo = __uint_as_float((w << 16) & 0x7fff0000u);
     hi = __uint_as_float(w & 0x7fff0000u);
   } else {
-    const uint32_t a = w & 0x7fff7fffu;
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a));
+    // (|x| rides on the conversion: HADD2.F32 takes an absolute-value modifier, no mask instruction)
+    const float2 f = __half22float2(__habs2(*reinterpret_cast<const __half2*>(&w)));
     lo = f.x;
     hi = f.y;
   }
@@ -692,7 +692,7 @@ struct TileKeep {
 // the tile rows are walked with stride 8 * gridDim.y -- no division anywhere (the flat index of the first version paid
 // ~60 instructions of a kernel that is issue-bound at ~400 per tile for it).
 template <bool BF16, bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, VEC ? 3 : 2)  // three blocks per SM: at most 80 registers (allocated in eights)
 prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __restrict__: out may alias in (in-place prune)
                     size_t ld_out, uint32_t rows, uint32_t cols) {
   __shared__ TilePatterns T;
@@ -704,12 +704,17 @@ prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __re
   const uint32_t tr_step = gridDim.y * 8u;
   // the next tile of the thread is fetched before the current one is worked on: 32 bytes per thread in flight are a
   // third of what the DRAM latency asks for at three resident blocks per SM (measured: 3.7 TB/s without)
+  // (row addresses as column pointer + row * 32-bit byte pitch: one IMAD.WIDE on the FMA pipe instead of a 64-bit add
+  // on the ALU pipe, the one this kernel is bound by; the host checks that the pitches fit)
+  const uint32_t pitch_in = (uint32_t)ld_in * 2u, pitch_out = (uint32_t)ld_out * 2u;
+  const char* in_col = reinterpret_cast<const char*>(in + c0);
+  char* out_col = reinterpret_cast<char*>(out + c0);
   auto fetch = [&](uint32_t tr, uint2 (&w)[4]) {
     const uint32_t r0 = tr * 4;
-    const uint16_t* src = in + (size_t)r0 * ld_in + c0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      w[i] = r0 + i < rows ? *reinterpret_cast<const uint2*>(src + i * ld_in) : make_uint2(0u, 0u);  // (covers tr >= tiles_r)
+      w[i] = r0 + i < rows ? *reinterpret_cast<const uint2*>(in_col + (uint64_t)(r0 + i) * pitch_in)
+                           : make_uint2(0u, 0u);  // (covers tr >= tiles_r)
   };
   uint2 nw[4];
   const uint32_t tr_first = blockIdx.y * 8u + (threadIdx.x >> 5);
@@ -728,11 +733,10 @@ prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __re
         tile_mag2<BF16>(w[i].y, mag[i * 4 + 2], mag[i * 4 + 3]);
       }
       const TileKeep keep(T.pat[tile_select(mag)]);
-      uint16_t* dst = out + (size_t)r0 * ld_out + c0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (r0 + i >= rows) break;
-        *reinterpret_cast<uint2*>(dst + i * ld_out) = keep.row(i, w[i]);
+        *reinterpret_cast<uint2*>(out_col + (uint64_t)(r0 + i) * pitch_out) = keep.row(i, w[i]);
       }
     } else {
       uint16_t v[16];
@@ -776,8 +780,9 @@ __device__ __forceinline__ void tile_fused_fetch(const Prune24Params& P, uint32_
   const bool col_ok = active && c0 < P.cols;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    w[i] = (col_ok && r0 + i < P.rows) ? *reinterpret_cast<const uint2*>(P.in + (size_t)(r0 + i) * P.ld_in + c0)
-                                       : make_uint2(0u, 0u);
+    w[i] = (col_ok && r0 + i < P.rows)
+               ? *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(P.in + c0) + (uint64_t)(r0 + i) * ((uint32_t)P.ld_in * 2u))
+               : make_uint2(0u, 0u);
 }
 
 template <bool BF16>
@@ -799,7 +804,8 @@ __device__ __forceinline__ void tile_fused_tiles(const Prune24Params& P, const T
       const uint2 kept = keep.row(i, w[i]);
       const uint32_t lo = kept.x, hi = kept.y;
       if (P.out_dense && col_ok && row < P.rows)
-        *reinterpret_cast<uint2*>(P.out_dense + (size_t)row * P.ld_out + c0) = make_uint2(lo, hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<char*>(P.out_dense + c0) + (uint64_t)row * ((uint32_t)P.ld_out * 2u)) =
+            make_uint2(lo, hi);
       uint32_t i0, i1;
       top2of4(lo, hi, i0, i1);
       const uint32_t cv = __byte_perm(lo, hi, (i0 + (i1 << 8)) * 0x22u + 0x1010u);
@@ -840,7 +846,7 @@ __device__ __forceinline__ void tile_fused_warp(const Prune24Params& P, const Ti
 
 // grid: x = 32-tile column chunks, y walks the tile rows with stride 8 * gridDim.y (no division, like prune24_tile_kernel)
 template <bool BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 prune24_tile_fused_kernel(const __grid_constant__ Prune24Params P) {
   __shared__ TilePatterns T;
   T.load();
@@ -1089,7 +1095,7 @@ int spfy_prune24(int dtype, int mode, int layout, const void* in, size_t ld_in, 
   if (!in) return fail(SPFY_E_INVALID, "prune24: null input");
   if (ld_in < cols || (out_dense && ld_out < cols))
     return fail(SPFY_E_INVALID, "prune24: leading dimension smaller than cols");
-  if (rows >= (1ull << 31) || cols >= (1ull << 31))
+  if (rows >= (1ull << 31) || cols >= (1ull << 31) || ld_in >= (1ull << 31) || (out_dense && ld_out >= (1ull << 31)))
     return fail(SPFY_E_UNSUPPORTED, "prune24: dimension too large");
   if (rows == 0 || cols == 0) return SPFY_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1199,7 +1205,7 @@ int spfy_prune24_batched(int dtype, int mode, int layout, const spfy_prune24_ite
       if (!it.in) return fail(SPFY_E_INVALID, "prune24_batched: item %zu has a null input", i);
       if (it.ld_in < it.cols || (it.out_dense && it.ld_out < it.cols))
         return fail(SPFY_E_INVALID, "prune24_batched: item %zu leading dimension smaller than cols", i);
-      if (it.rows >= (1ull << 31) || it.cols >= (1ull << 31))
+      if (it.rows >= (1ull << 31) || it.cols >= (1ull << 31) || it.ld_in >= (1ull << 31) || (it.out_dense && it.ld_out >= (1ull << 31)))
         return fail(SPFY_E_UNSUPPORTED, "prune24_batched: item %zu too large", i);
       if (tile && !it.out_dense)
         return fail(SPFY_E_INVALID, "prune24_batched: item %zu: TILE_MAG needs out_dense (it may alias the input)", i);
