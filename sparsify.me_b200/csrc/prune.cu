@@ -692,7 +692,7 @@ struct TileKeep {
 // the tile rows are walked with stride 8 * gridDim.y -- no division anywhere (the flat index of the first version paid
 // ~60 instructions of a kernel that is issue-bound at ~400 per tile for it).
 template <bool BF16, bool VEC>
-__global__ void __launch_bounds__(256, VEC ? 3 : 2)  // three blocks per SM: at most 80 registers (allocated in eights)
+__global__ void __launch_bounds__(256, VEC ? 3 : 2)  // three blocks per SM: at most 80 registers (four blocks at 64 registers spill 60 bytes: 223 -> 235 us)
 prune24_tile_kernel(const uint16_t* in, size_t ld_in, uint16_t* out,  // no __restrict__: out may alias in (in-place prune)
                     size_t ld_out, uint32_t rows, uint32_t cols) {
   __shared__ TilePatterns T;
