@@ -117,7 +117,21 @@ struct LaunchParams {
   uint32_t bk;         // logical k per ring stage: 128, or 64 for the k <= 64 class (half-size stages)
   uint32_t dbg;        // development switches (SPFY_SPMMA_DEBUG): 2 no epilogue work, 4 no B loads, 8 no MMAs,
                        // 16 no streamed A loads, 32 no TMA stores (timing experiments only: results are garbage)
+#ifdef SPFY_DEV_SWITCHES
+  long long* trace;    // SPFY_SPMMA_TRACE: CTA 0 logs clock64() at the hand-over points of its first TRACE_UNITS units
+#endif
 };
+
+#ifdef SPFY_DEV_SWITCHES
+constexpr uint32_t TRACE_UNITS = 24, TRACE_SLOTS = 8;  // [role 0 producer / 1 MMA / 2 epilogue warp 2][unit][slot]
+#define SPFY_TRACE(role, unit, slot)                                                                     \
+  do {                                                                                                   \
+    if (L.trace && blockIdx.x == 0 && (unit) < TRACE_UNITS && (threadIdx.x & 31u) == 0u)                 \
+      L.trace[((role) * TRACE_UNITS + (unit)) * TRACE_SLOTS + (slot)] = clock64();                       \
+  } while (0)
+#else
+#define SPFY_TRACE(role, unit, slot) do { } while (0)
+#endif
 
 using namespace ptx;
 
@@ -230,6 +244,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       uint32_t conv = 0, conv_c = 64, conv_kw = 1, conv_wo = 1, conv_ho = 1, conv_stride = 1, conv_pad = 0, pk = 0;
       uint64_t hint_b = 0;
       const bool no_b = (L.dbg & 4u) != 0, no_a = (L.dbg & 16u) != 0;
+      uint32_t tr_unit = 0;
+      (void)tr_unit;
       for (; W.valid(); W.next()) {
         const ProblemDev* P = W.current();
         if (P != last) {
@@ -306,7 +322,9 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const uint32_t tx_a = stream_a ? a_bytes + e_bytes : 0u;
         const uint32_t tx_full = (no_b ? 0u : L.bk * (uint32_t)(BN * 2)) + tx_a;
         for (uint32_t kt = 0; kt < k_tiles; ++kt, av += av_step, am += am_step) {
+          if (kt == 0) SPFY_TRACE(0, tr_unit, 0);
           mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+          if (kt == 0) SPFY_TRACE(0, tr_unit, 1);
           const uint32_t full = bar_full + stage * 8;
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
           // implicit GEMM: 64-channel pieces of this k-tile that exist (K = taps * C is a multiple of 64, not of 128)
@@ -345,6 +363,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           }
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
+        SPFY_TRACE(0, tr_unit, 2);
+        ++tr_unit;
       }
     }
   } else if (warp == 1) {
@@ -358,6 +378,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       uint32_t pm = 0, pk = 0, k_tiles = 0, m_tiles = 0, m_groups = 1, G = 1, resident = 0, unit_begin = 0, units = 0;
       uint32_t split_units = 0, split_nt = 0;
       const bool no_mma = (L.dbg & 8u) != 0;
+      uint32_t tr_unit = 0;
+      (void)tr_unit;
       // constant halves of the shared-memory descriptors (the start address is OR-ed in per MMA)
       const uint64_t desc_a_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       const uint64_t desc_b_hi = OPB_T ? make_smem_desc(0, 16, 1024, LAYOUT_SW128)
@@ -385,9 +407,11 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         // accumulator slots of this unit's jobs
         const uint32_t slot0 = job % ACC_SLOTS, use0 = job / ACC_SLOTS;
         const uint32_t slot1 = (job + 1) % ACC_SLOTS, use1 = (job + 1) / ACC_SLOTS;
+        SPFY_TRACE(1, tr_unit, 0);
         mbar_wait(bar_acc_empty + slot0 * 8, (use0 & 1u) ^ 1u);
         if (g_count > 1) mbar_wait(bar_acc_empty + slot1 * 8, (use1 & 1u) ^ 1u);
         tc_fence_after();
+        SPFY_TRACE(1, tr_unit, 1);
         const uint32_t tmem_d0 = tmem_b + slot0 * BN, tmem_d1 = tmem_b + slot1 * BN;
         // resident operands: tile (kt, mt) at (kt*m_tiles + mt) * stride
         const uint32_t rv_single = rows_valid_of(pm, 0);
@@ -400,6 +424,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         for (uint32_t kt = 0; kt < k_tiles; ++kt, k_left -= BK, ra += res_tiles * rsv, re += res_tiles * rse) {
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
+          if (kt == 0) SPFY_TRACE(1, tr_unit, 2);
           const uint32_t sbase = smem_base + stage * L.stage_bytes;
           // metadata of these 128 logical k -> TMEM (4 columns per m-tile)
           const uint32_t ecol0 = tmem_b + TMEM_E_COL + (eblk & 1u) * (MAX_G * 4u), ecol1 = ecol0 + 4u;
@@ -447,6 +472,8 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
           if (last_of_problem) tc_commit(bar_res_empty);  // every MMA that reads the resident region has completed
         }
         job += g_count;
+        SPFY_TRACE(1, tr_unit, 3);
+        ++tr_unit;
         if (last_of_problem) res_owner = nullptr;
       }
     }
@@ -490,8 +517,10 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
       for (uint32_t g = 0; g < g_count; ++g, ++job) {
         const uint32_t slot = job % ACC_SLOTS;
         const uint32_t m0 = (mt0 + g) * BM;
+        if (e == 0) SPFY_TRACE(2, job, 0);
         mbar_wait(bar_acc_full + slot * 8, (job / ACC_SLOTS) & 1u);
         tc_fence_after();
+        if (e == 0) SPFY_TRACE(2, job, 1);
         for (uint32_t hh = 0; hh < halves; ++hh) {
           const uint32_t half = half0 + hh;
           const uint32_t n0 = nt * BN + half * 64;
@@ -508,10 +537,12 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty + slot * 8);
+            if (e == 0) SPFY_TRACE(2, job, 2);
           }
           if (warp_has_rows && !no_epi) {
             if (lane == 0) bulk_wait_read_all();  // my previous store has finished reading the staging buffer
             __syncwarp();
+            if (e == 0 && hh == 0) SPFY_TRACE(2, job, 3);
             const uint32_t grow = m0 + row_in_tile;
             if (out_t) {
               // transposed output [n][m]: the staging buffer holds 64 rows (n) of 32 halfwords (my quarter's m), so a
@@ -563,6 +594,7 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
               for (uint32_t r = 0; r < n_rep; ++r) tma_store_2d(tmap_rep + r, sc, c0, c1);
               bulk_commit();
             }
+            if (e == 0 && hh == 0) SPFY_TRACE(2, job, 4);
           }
         }
       }
@@ -995,6 +1027,38 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
     L.dbg = e ? (uint32_t)atoi(e) : 0u;
   }
   const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
+#ifdef SPFY_DEV_SWITCHES
+  if (const char* path = dev_switch("SPFY_SPMMA_TRACE")) {
+    // CTA 0's hand-over timestamps of this launch, written to `path` (the call becomes synchronous)
+    static long long* trace = nullptr;
+    const size_t n = 3 * TRACE_UNITS * TRACE_SLOTS;
+    if (!trace) SPFY_CUDA_OK(cudaMallocManaged((void**)&trace, n * sizeof(long long)));
+    SPFY_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    memset(trace, 0, n * sizeof(long long));
+    L.trace = trace;
+    rc = launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
+    if (rc) return rc;
+    SPFY_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (FILE* f = fopen(path, "w")) {
+      fprintf(f, "# m=%zu n=%zu k=%zu units=%u grid=%d stages=%u\nrole,unit", m, n, k, d.units, grid, L.stages);
+      for (uint32_t sl = 0; sl < TRACE_SLOTS; ++sl) fprintf(f, ",t%u", sl);
+      fprintf(f, "\n");
+      long long t0 = 0;
+      for (size_t i = 0; i < n; ++i) if (trace[i] && (!t0 || trace[i] < t0)) t0 = trace[i];
+      for (uint32_t r = 0; r < 3; ++r)
+        for (uint32_t u = 0; u < TRACE_UNITS; ++u) {
+          fprintf(f, "%u,%u", r, u);
+          for (uint32_t sl = 0; sl < TRACE_SLOTS; ++sl) {
+            const long long v = trace[(r * TRACE_UNITS + u) * TRACE_SLOTS + sl];
+            fprintf(f, ",%lld", v ? v - t0 : -1);
+          }
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+    return SPFY_OK;
+  }
+#endif
   return launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
 }
 
