@@ -95,3 +95,45 @@ def test_resnet152_per_gpu_shard_of_batch_256(spfy, orc, cuda):
     assert hi - lo == 32
     worst = check_table(spfy, orc, cuda, "resnet152.csv", hi - lo, torch.float16, oracle_cols=2048)
     assert worst <= REL_TOL
+
+
+def test_resnet50_b32_implicit_plan_exactly_as_benchmarked(spfy, cuda):
+    """bench.py's `implicit_plan`: the resnet50 table at b = 32 as ONE plan whose 16 3 x 3 layers read NHWC activations
+    through TMA im2col (spfy_spmma_plan_create_conv) next to the 33 matrix problems.  Every conv layer's output must be
+    bit for bit what the plan of plain matrices computes on the unfolded operand ((kh, kw, c)-ordered K), and the
+    matrix layers must be untouched by the mix."""
+    import math
+    import torch.nn.functional as F
+    tdt, batch = torch.float16, 32
+    layers, plan = build_like_bench(spfy, cuda, "resnet50.csv", batch, tdt)
+    plan.close()
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(99)
+    problems, convs = [], []
+    for i, (g, w, b, d, comp) in enumerate(layers):
+        hw = g.N // batch
+        ho = math.isqrt(hw)
+        if g.K % 9 == 0 and (g.K // 9) % 64 == 0 and ho * ho == hw:
+            x = (torch.rand(batch, ho, ho, g.K // 9, device=cuda, generator=gen) * 2 - 1).to(tdt)
+            out = torch.zeros_like(d)
+            problems.append(dict(comp=comp, b=x, out=out, conv=(3, 3, 1, 1)))
+            convs.append((i, x, out))
+        else:
+            problems.append(dict(comp=comp, b=b, out=torch.zeros_like(d)))
+    assert len(convs) == 16
+    mixed = spfy.SpmmaPlan(problems)
+    mixed.run()
+    torch.cuda.synchronize()
+    for i, (g, w, b, d, comp) in enumerate(layers):  # the matrix problems: same bits as the all-matrix plan
+        if "conv" not in problems[i]:
+            assert torch.equal(problems[i]["out"], d), g
+    for i, x, out in convs:
+        g, _, _, _, comp = layers[i]
+        ho, cin = x.shape[1], x.shape[3]
+        cols = F.unfold(x.permute(0, 3, 1, 2).float(), 3, padding=1).view(batch, cin, 9, ho * ho)
+        bx = cols.permute(2, 1, 0, 3).reshape(g.K, g.N).to(tdt).contiguous()
+        del cols
+        want = spfy.spmma_compressed(comp, bx)
+        assert torch.equal(out, want), g
+        del bx, want
+    mixed.close()
