@@ -860,6 +860,12 @@ int fill_problem(ProblemDev* d, int dtype, const HostProblem& h, int cls) {
   // B is streamed once when one unit covers all of M; otherwise the other m-groups of the same
   // columns will want it from L2 shortly after
   d->hint_b = d->m_groups == 1 ? HINT_EVICT_FIRST : HINT_EVICT_NORMAL;
+  // implicit GEMM: every activation is read kh * kw times (by the other filter taps and the neighbouring tiles), so the
+  // lines must not be marked for early eviction
+  if (h.conv) {
+    const char* e = dev_switch("SPFY_CONV_HINT");
+    d->hint_b = e && atoi(e) == 1 ? HINT_EVICT_FIRST : e && atoi(e) == 2 ? HINT_EVICT_LAST : HINT_EVICT_NORMAL;
+  }
   return SPFY_OK;
 }
 
