@@ -354,6 +354,10 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
         const bool stream_a = !resident && !no_a;
         const uint32_t tx_a = stream_a ? a_bytes + e_bytes : 0u;
         const uint32_t tx_full = (no_b ? 0u : L.bk * (uint32_t)(BN * 2)) + tx_a;
+        // implicit GEMM: (channel offset, filter column, filter row) of the next 64-channel piece, stepped without
+        // divisions (the two per piece that stood here made the producer the slowest warp of every convolution layer:
+        // ~1340 cycles per k-tile, ncu stall samples spread evenly over its scalar code)
+        uint32_t pc0 = 0, pts = 0, ptr = 0;
         for (uint32_t kt = 0; kt < k_tiles; ++kt, av += av_step, am += am_step) {
           if (kt == 0) SPFY_TRACE(0, tr_unit, 0);
           mbar_wait(bar_empty + stage * 8, phase ^ 1u);
@@ -369,10 +373,15 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             if (no_b) {
             } else if (conv) {
               if (OPB_T) {
-                for (uint32_t h = 0; h < pieces; ++h) {
-                  const uint32_t k0 = kt * L.bk + h * 64u, tap = k0 / conv_c, c0 = k0 - tap * conv_c;
-                  const uint32_t tr = tap / conv_kw, ts = tap - tr * conv_kw;
-                  tma_load_im2col_4d(sbase + h * (uint32_t)(BN * 128), tmap_b, (int)c0, cw, ch, cn, (uint16_t)ts, (uint16_t)tr,
+                // (the leader issues; every lane steps the position below.  At most two pieces per stage.)
+                tma_load_im2col_4d(sbase, tmap_b, (int)pc0, cw, ch, cn, (uint16_t)pts, (uint16_t)ptr, full, hint_b);
+                if (pieces > 1u) {
+                  uint32_t c0 = pc0 + 64u, ts = pts, tr = ptr;
+                  if (c0 == conv_c) {
+                    c0 = 0;
+                    if (++ts == conv_kw) { ts = 0; ++tr; }
+                  }
+                  tma_load_im2col_4d(sbase + (uint32_t)(BN * 128), tmap_b, (int)c0, cw, ch, cn, (uint16_t)ts, (uint16_t)tr,
                                      full, hint_b);
                 }
               }
@@ -392,6 +401,16 @@ spmma_kernel(const __grid_constant__ ProblemDev single, const __grid_constant__ 
             if (stream_a) {
               bulk_load_1d(sbase + L.a_off, av, a_bytes, full, HINT_EVICT_LAST);
               bulk_load_1d(sbase + L.e_off, am, e_bytes, full, HINT_EVICT_LAST);
+            }
+          }
+#pragma unroll
+          for (uint32_t h = 0; h < 2u; ++h) {
+            if (h < pieces) {
+              pc0 += 64u;
+              if (pc0 == conv_c) {
+                pc0 = 0;
+                if (++pts == conv_kw) { pts = 0; ++ptr; }
+              }
             }
           }
           if (++stage == NS) { stage = 0; phase ^= 1u; }
