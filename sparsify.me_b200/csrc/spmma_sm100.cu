@@ -982,6 +982,39 @@ int launch(int dtype, int opB, const ProblemDev& single, const LaunchParams& L, 
                           : launch_t<false, true>(single, L, smem, grid, s, overlap_previous);
 }
 
+#ifdef SPFY_DEV_SWITCHES
+// SPFY_SPMMA_TRACE=path: CTA 0's hand-over timestamps of this launch, written to `path` (the call becomes synchronous)
+int launch_traced(const char* path, int dtype, int opB, const ProblemDev& d, LaunchParams L, uint32_t smem, int grid, cudaStream_t s) {
+  static long long* trace = nullptr;
+  const size_t n = 3 * TRACE_UNITS * TRACE_SLOTS;
+  if (!trace) SPFY_CUDA_OK(cudaMallocManaged((void**)&trace, n * sizeof(long long)));
+  SPFY_CUDA_OK(cudaStreamSynchronize(s));
+  memset(trace, 0, n * sizeof(long long));
+  L.trace = trace;
+  int rc = launch(dtype, opB, d, L, smem, grid, s);
+  if (rc) return rc;
+  SPFY_CUDA_OK(cudaStreamSynchronize(s));
+  if (FILE* f = fopen(path, "w")) {
+    fprintf(f, "# m=%u n=%u k=%u units=%u grid=%d stages=%u conv=%u\nrole,unit", d.m, d.n, d.k, d.units, grid, L.stages, d.conv);
+    for (uint32_t sl = 0; sl < TRACE_SLOTS; ++sl) fprintf(f, ",t%u", sl);
+    fprintf(f, "\n");
+    long long t0 = 0;
+    for (size_t i = 0; i < n; ++i) if (trace[i] && (!t0 || trace[i] < t0)) t0 = trace[i];
+    for (uint32_t r = 0; r < 3; ++r)
+      for (uint32_t u = 0; u < TRACE_UNITS; ++u) {
+        fprintf(f, "%u,%u", r, u);
+        for (uint32_t sl = 0; sl < TRACE_SLOTS; ++sl) {
+          const long long v = trace[(r * TRACE_UNITS + u) * TRACE_SLOTS + sl];
+          fprintf(f, ",%lld", v ? v - t0 : -1);
+        }
+        fprintf(f, "\n");
+      }
+    fclose(f);
+  }
+  return SPFY_OK;
+}
+#endif
+
 uint32_t res_rows(const ProblemDev& d) { return d.m_tiles == 1 ? (uint32_t)round_up(d.m, 16) : 128u; }
 uint32_t res_tiles(const ProblemDev& d) { return (d.resident == 2u ? d.G : d.m_tiles) * d.k_tiles; }
 uint32_t res_values_bytes(const ProblemDev& d) { return res_tiles(d) * res_rows(d) * 128u; }
@@ -1081,36 +1114,7 @@ int spfy_spmma(int dtype, int opB, size_t m, size_t n, size_t k, float alpha, co
   }
   const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
 #ifdef SPFY_DEV_SWITCHES
-  if (const char* path = dev_switch("SPFY_SPMMA_TRACE")) {
-    // CTA 0's hand-over timestamps of this launch, written to `path` (the call becomes synchronous)
-    static long long* trace = nullptr;
-    const size_t n = 3 * TRACE_UNITS * TRACE_SLOTS;
-    if (!trace) SPFY_CUDA_OK(cudaMallocManaged((void**)&trace, n * sizeof(long long)));
-    SPFY_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    memset(trace, 0, n * sizeof(long long));
-    L.trace = trace;
-    rc = launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
-    if (rc) return rc;
-    SPFY_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    if (FILE* f = fopen(path, "w")) {
-      fprintf(f, "# m=%zu n=%zu k=%zu units=%u grid=%d stages=%u\nrole,unit", m, n, k, d.units, grid, L.stages);
-      for (uint32_t sl = 0; sl < TRACE_SLOTS; ++sl) fprintf(f, ",t%u", sl);
-      fprintf(f, "\n");
-      long long t0 = 0;
-      for (size_t i = 0; i < n; ++i) if (trace[i] && (!t0 || trace[i] < t0)) t0 = trace[i];
-      for (uint32_t r = 0; r < 3; ++r)
-        for (uint32_t u = 0; u < TRACE_UNITS; ++u) {
-          fprintf(f, "%u,%u", r, u);
-          for (uint32_t sl = 0; sl < TRACE_SLOTS; ++sl) {
-            const long long v = trace[(r * TRACE_UNITS + u) * TRACE_SLOTS + sl];
-            fprintf(f, ",%lld", v ? v - t0 : -1);
-          }
-          fprintf(f, "\n");
-        }
-      fclose(f);
-    }
-    return SPFY_OK;
-  }
+  if (const char* path = dev_switch("SPFY_SPMMA_TRACE")) return launch_traced(path, dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
 #endif
   return launch(dtype, opB, d, L, smem, grid, (cudaStream_t)stream);
 }
@@ -1158,6 +1162,9 @@ static int spmma_conv_impl(int dtype, const spfy_conv_desc* conv, size_t m, floa
   L.total_units = d.units;
   L.idesc = make_idesc(dtype, SPFY_OP_T);
   const int grid = (int)(d.units < (uint32_t)di.sm_count ? d.units : (uint32_t)di.sm_count);
+#ifdef SPFY_DEV_SWITCHES
+  if (const char* path = dev_switch("SPFY_SPMMA_TRACE")) return launch_traced(path, dtype, SPFY_OP_T, d, L, smem, grid, (cudaStream_t)stream);
+#endif
   return launch(dtype, SPFY_OP_T, d, L, smem, grid, (cudaStream_t)stream);
 }
 
