@@ -88,25 +88,54 @@ struct GemmLaunch {
   uint32_t b_off;     // ... and where the Bu ring starts
 };
 
+// Units are numbered (batch, m-group, n-tile) with the n-tile fastest.  The walker keeps that position incrementally --
+// the stride is split once per problem into its (batch, m-group, n-tile) digits -- and reads the problem table only when
+// a unit leaves the cached range: five roles decode every unit, and a 32-bit division is ~40 dependent instructions.
 struct GemmWalker {
   const GemmProblemDev* single;
   const GemmProblemDev* table;
   uint32_t num_problems, total_units, u, p;
   uint32_t stride;
+  uint32_t p_begin, p_end;          // unit range of problem p; p_end == 0: nothing cached yet
+  uint32_t n_tiles, m_groups;       // of problem p
+  uint32_t nt, md, bb;              // n-tile, m-group and batch of unit u
+  uint32_t s_nt, s_md, s_bb;        // the stride in the same digits
   __device__ __forceinline__ GemmWalker(const GemmProblemDev* s, const GemmLaunch& L)
       : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units), u(blockIdx.x), p(0),
-        stride(gridDim.x) {}
+        stride(gridDim.x), p_begin(0), p_end(0) {}
   // CTA pairs: both CTAs of a cluster walk the same units
   __device__ __forceinline__ GemmWalker(const GemmProblemDev* s, const GemmLaunch& L, uint32_t first, uint32_t step)
-      : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units), u(first), p(0), stride(step) {}
+      : single(s), table(L.table), num_problems(L.num_problems), total_units(L.total_units), u(first), p(0), stride(step),
+        p_begin(0), p_end(0) {}
   __device__ __forceinline__ const GemmProblemDev* prob(uint32_t i) const { return table ? table + i : single; }
   __device__ __forceinline__ bool valid() const { return u < total_units; }
   __device__ __forceinline__ const GemmProblemDev* current() {
-    while (p + 1 < num_problems && u >= prob(p)->unit_begin + prob(p)->units) ++p;
-    p = uni(p);
+    if (u >= p_end) {  // (also the first call)
+      while (p + 1 < num_problems && u >= prob(p)->unit_begin + prob(p)->units) ++p;
+      p = uni(p);
+      const GemmProblemDev* P = prob(p);
+      p_begin = uni(P->unit_begin);
+      p_end = p_begin + uni(P->units);
+      n_tiles = uni(P->n_tiles);
+      m_groups = uni(P->m_groups);
+      const uint32_t local = u - p_begin, t1 = local / n_tiles, sq = stride / n_tiles;
+      nt = local - t1 * n_tiles;
+      bb = t1 / m_groups;
+      md = t1 - bb * m_groups;
+      s_nt = stride - sq * n_tiles;
+      s_bb = sq / m_groups;
+      s_md = sq - s_bb * m_groups;
+    }
     return prob(p);
   }
-  __device__ __forceinline__ void next() { u += stride; }
+  __device__ __forceinline__ void next() {
+    u += stride;
+    nt += s_nt;
+    md += s_md;
+    bb += s_bb;
+    if (nt >= n_tiles) { nt -= n_tiles; ++md; }
+    if (md >= m_groups) { md -= m_groups; ++bb; }
+  }
 };
 
 template <int KIND>
@@ -138,7 +167,7 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
   const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter + 32)
   uint32_t job = 0;
   const GemmProblemDev* last = nullptr;
-  uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, bn = 0, mu = 0, nu = 0, unit_begin = 0, mu_contig = 1;
+  uint32_t m_tiles = 1, g = 1, bn = 0, mu = 0, nu = 0, mu_contig = 1;
   uint64_t ldc = 0, stride_c = 0;
   uint8_t* Cbase = nullptr;
   const uint64_t* c_ptrs = nullptr;
@@ -147,14 +176,11 @@ __device__ __forceinline__ void gemm_epilogue(GemmWalker& W, uint32_t tmem_base,
     const GemmProblemDev* P = W.current();
     if (P != last) {
       last = P;
-      m_tiles = P->m_tiles; m_groups = P->m_groups; g = P->g; n_tiles = P->n_tiles; bn = P->bn; mu = P->mu; nu = P->nu;
-      unit_begin = P->unit_begin;
+      m_tiles = P->m_tiles; g = P->g; bn = P->bn; mu = P->mu; nu = P->nu;
       mu_contig = P->out_mu_contig; ldc = P->ldc; stride_c = P->stride_c; Cbase = P->C; c_ptrs = P->c_ptrs;
       alpha = P->alpha; beta = P->beta;
     }
-    const uint32_t local = W.u - unit_begin;
-    const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
-    const uint32_t mg = t1 % m_groups, b = t1 / m_groups;
+    const uint32_t nt = W.nt, mg = W.md, b = W.bb;
     const uint32_t g_count = pair ? 1u : min(g, m_tiles - mg * g);
     out_t* C = c_ptrs ? reinterpret_cast<out_t*>(c_ptrs[b]) : reinterpret_cast<out_t*>(Cbase) + (size_t)b * stride_c;
     const uint32_t slot = job % slots;
@@ -293,9 +319,7 @@ tcgemm_kernel(const __grid_constant__ GemmProblemDev single, const __grid_consta
         a_mn = uni(P->a_mn); b_mn = uni(P->b_mn); a_bat = uni(P->a_batched); b_bat = uni(P->b_batched);
         unit_begin = uni(P->unit_begin);
       }
-      const uint32_t local = W.u - unit_begin;
-      const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
-      const uint32_t mt = t1 % m_tiles, b = t1 / m_tiles;
+      const uint32_t nt = W.nt, mt = W.md, b = W.bb;  // (one m-tile per unit in this kernel: m-group = m-tile)
       const int ba = a_bat ? (int)b : 0, bb = b_bat ? (int)b : 0;
       const uint32_t tx = (uint32_t)GM_A_BYTES + bn * (uint32_t)GM_ROW_BYTES;
       for (uint32_t kt = 0; kt < k_tiles; ++kt) {
@@ -513,9 +537,7 @@ tcgemm2_kernel(const __grid_constant__ GemmProblemDev single, const __grid_const
         a_mn = uni(P->a_mn); b_mn = uni(P->b_mn); a_bat = uni(P->a_batched); b_bat = uni(P->b_batched);
         unit_begin = uni(P->unit_begin);
       }
-      const uint32_t local = W.u - unit_begin;
-      const uint32_t nt = local % n_tiles, t1 = local / n_tiles;
-      const uint32_t mp = t1 % m_pairs, b = t1 / m_pairs;
+      const uint32_t nt = W.nt, mp = W.md, b = W.bb;
       const uint32_t mt = mp * 2u + rank;                 // my m-tile of the pair
       const uint32_t half = bn >> 1, n0 = nt * bn + rank * half;  // my half of the Bu tile
       const int ba = a_bat ? (int)b : 0, bb = b_bat ? (int)b : 0;
@@ -702,19 +724,17 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
     uint32_t st = 0, ph = 0;
     const GemmProblemDev* last = nullptr;
     const CUtensorMap* tmap = nullptr;
-    uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, k_tiles = 0, mn = 0, bat = 0, unit_begin = 0;
+    uint32_t m_tiles = 1, g = 1, k_tiles = 0, mn = 0, bat = 0;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
         tmap = &P->tmap_a;
         if (leader) prefetch_tmap(tmap);
-        m_tiles = uni(P->m_tiles); m_groups = uni(P->m_groups); g = uni(P->g); n_tiles = uni(P->n_tiles);
-        k_tiles = uni(P->k_tiles); mn = uni(P->a_mn); bat = uni(P->a_batched); unit_begin = uni(P->unit_begin);
+        m_tiles = uni(P->m_tiles); g = uni(P->g);
+        k_tiles = uni(P->k_tiles); mn = uni(P->a_mn); bat = uni(P->a_batched);
       }
-      const uint32_t local = W.u - unit_begin;
-      const uint32_t t1 = local / n_tiles;
-      const uint32_t mg = t1 % m_groups, b = t1 / m_groups;
+      const uint32_t mg = W.md, b = W.bb;
       const uint32_t mt0 = mg * g, g_count = min(g, m_tiles - mt0);
       const int bc = bat ? (int)b : 0;
       for (uint32_t kt = 0; kt < k_tiles; ++kt) {
@@ -743,18 +763,17 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
     uint32_t st = 0, ph = 0;
     const GemmProblemDev* last = nullptr;
     const CUtensorMap* tmap = nullptr;
-    uint32_t m_groups = 1, n_tiles = 1, k_tiles = 0, bn = 0, mn = 0, bat = 0, unit_begin = 0;
+    uint32_t k_tiles = 0, bn = 0, mn = 0, bat = 0;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
         tmap = &P->tmap_b;
         if (leader) prefetch_tmap(tmap);
-        m_groups = uni(P->m_groups); n_tiles = uni(P->n_tiles); k_tiles = uni(P->k_tiles); bn = uni(P->bn);
-        mn = uni(P->b_mn); bat = uni(P->b_batched); unit_begin = uni(P->unit_begin);
+        k_tiles = uni(P->k_tiles); bn = uni(P->bn);
+        mn = uni(P->b_mn); bat = uni(P->b_batched);
       }
-      const uint32_t local = W.u - unit_begin;
-      const uint32_t nt = local % n_tiles, b = local / n_tiles / m_groups;
+      const uint32_t nt = W.nt, b = W.bb;
       const int bc = bat ? (int)b : 0, row0 = (int)(nt * bn);
       for (uint32_t kt = 0; kt < k_tiles; ++kt) {
         mbar_wait(bar_bfree + st * 8, ph ^ 1u);
@@ -777,7 +796,7 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
     const uint32_t tmem_b = uni(tmem_base);
     uint32_t sb = 0, phb = 0, slab = 0, job = 0;
     const GemmProblemDev* last = nullptr;
-    uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, k_tiles = 0, pk = 0, bn = 0, b_mn = 0, unit_begin = 0;
+    uint32_t m_tiles = 1, g = 1, k_tiles = 0, pk = 0, bn = 0, b_mn = 0;
     const uint32_t lo_off = L.raw_bytes >> 4;  // Bu lo tile sits raw_bytes behind the raw one (16-byte units)
     const uint64_t desc_k = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
     const uint64_t desc_mn = make_smem_desc(0, GROUP_BYTES, 512, LAYOUT_SW128_BASE32B);
@@ -785,11 +804,10 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
-        m_tiles = uni(P->m_tiles); m_groups = uni(P->m_groups); g = uni(P->g); n_tiles = uni(P->n_tiles);
-        k_tiles = uni(P->k_tiles); pk = uni(P->k); bn = uni(P->bn); b_mn = uni(P->b_mn); unit_begin = uni(P->unit_begin);
+        m_tiles = uni(P->m_tiles); g = uni(P->g);
+        k_tiles = uni(P->k_tiles); pk = uni(P->k); bn = uni(P->bn); b_mn = uni(P->b_mn);
       }
-      const uint32_t local = W.u - unit_begin;
-      const uint32_t mg = (local / n_tiles) % m_groups;
+      const uint32_t mg = W.md;
       const uint32_t g_count = min(g, m_tiles - mg * g);
       const uint32_t slot = job % L.acc_slots, use = job / L.acc_slots;
       mbar_wait(bar_acc_empty + slot * 8, (use & 1u) ^ 1u);
@@ -835,15 +853,14 @@ tcgemm_ts_kernel(const __grid_constant__ GemmProblemDev single, const __grid_con
     const uint32_t row = (warp & 3u) * 32u + lane;  // the TMEM lane quarter a warp may touch is warp % 4
     uint32_t sa = 0, pha = 0, sb = 0, phb = 0, slab = 0;
     const GemmProblemDev* last = nullptr;
-    uint32_t m_tiles = 1, m_groups = 1, g = 1, n_tiles = 1, k_tiles = 0, a_mn = 0, unit_begin = 0;
+    uint32_t m_tiles = 1, g = 1, k_tiles = 0, a_mn = 0;
     for (; W.valid(); W.next()) {
       const GemmProblemDev* P = W.current();
       if (P != last) {
         last = P;
-        m_tiles = P->m_tiles; m_groups = P->m_groups; g = P->g; n_tiles = P->n_tiles; k_tiles = P->k_tiles; a_mn = P->a_mn;
-        unit_begin = P->unit_begin;
+        m_tiles = P->m_tiles; g = P->g; k_tiles = P->k_tiles; a_mn = P->a_mn;
       }
-      const uint32_t mg = ((W.u - unit_begin) / n_tiles) % m_groups;
+      const uint32_t mg = W.md;
       const uint32_t g_count = min(g, m_tiles - mg * g);
       for (uint32_t kt = 0; kt < k_tiles; ++kt, ++slab) {
         mbar_wait(bar_afull + sa * 8, pha);
